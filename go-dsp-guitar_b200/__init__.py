@@ -1,0 +1,419 @@
+"""go-dsp-guitar_b200 - host-side mirror of go-dsp-guitar's hot-path interfaces over libgdg.
+
+The reference's host language (Go) is not available in this image, so the
+reference-facing interface is mirrored here in Python over the C ABI
+(include/gdg.h) with ctypes; the cgo binding a maintainer would add is in
+INTEGRATION.md.  Names follow the reference:
+
+    signal.Chain            -> Chain        (signal/signal.go:21-36)
+    filter.ImpulseResponses -> IRBank       (filter/filter.go:79-82, Import :704)
+    spatializer.Spatializer -> Spatializer  (spatializer/spatializer.go:30-41)
+    tuner.Tuner             -> Tuner        (tuner/tuner.go:62-65)
+    controller.process      -> controller_process (controller/controller.go:2648-2783)
+
+Methods are the Go methods in snake_case with the same argument meaning; Go
+`error` returns become GdgError carrying the reference's message text.
+
+The package directory name contains a '-', so import it with
+    importlib.import_module("go-dsp-guitar_b200")      (see gdg.py at the repo root)
+
+PyTorch is not needed by this module; tests/bench use torch only for device
+tensors, streams and torch.distributed.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+DEFAULT_LIBRARY = os.path.join(HERE, "libgdg.so")
+
+UNIT_TYPES = ["signal_generator", "noise_gate", "bandpass", "auto_wah", "auto_yoy", "compressor", "octaver",
+              "excess", "fuzz", "overdrive", "distortion", "tone_stack", "chorus", "flanger", "phaser", "tremolo",
+              "ring_modulator", "delay", "reverb", "power_amp", "cabinet"]          # effects.go:543-565
+PARAMETER_TYPES = ["invalid", "discrete", "numeric"]                                  # effects.go:526-530
+
+
+class GdgError(RuntimeError):
+    pass
+
+
+class _Parameter(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("type", C.c_int32), ("physical_unit", C.c_char_p),
+                ("minimum", C.c_int32), ("maximum", C.c_int32), ("numeric_value", C.c_int32),
+                ("discrete_value_index", C.c_int32), ("discrete_value_count", C.c_int32)]
+
+
+class _TunerResult(C.Structure):
+    _fields_ = [("cents", C.c_int8), ("frequency", C.c_double), ("note", C.c_char_p)]
+
+
+_vp, _sz, _u32, _i32, _dbl, _int, _cp = C.c_void_p, C.c_size_t, C.c_uint32, C.c_int32, C.c_double, C.c_int, C.c_char_p
+
+# every symbol include/gdg.h declares: name -> (restype, argtypes)
+ABI = {
+    "gdg_init": (_int, [_int]),
+    "gdg_last_error": (_cp, []),
+    "gdg_backend_name": (_cp, []),
+    "gdg_version": (_cp, []),
+    "gdg_launch_count": (C.c_uint64, []),
+    "gdg_pinned_alloc": (_vp, [_sz]),
+    "gdg_pinned_free": (None, [_vp]),
+    "gdg_stream": (_vp, []),
+    "gdg_synchronize": (_int, []),
+    "gdg_unit_type_count": (_int, []),
+    "gdg_unit_type_name": (_cp, [_int]),
+    "gdg_irbank_import": (_vp, [_cp]),
+    "gdg_irbank_create": (_vp, []),
+    "gdg_irbank_destroy": (None, [_vp]),
+    "gdg_irbank_add": (_int, [_vp, _cp, _i32, _vp, _sz, _u32]),
+    "gdg_irbank_add_raw": (_int, [_vp, _cp, _i32, _vp, _sz, _u32]),
+    "gdg_irbank_name_count": (_sz, [_vp]),
+    "gdg_irbank_name": (_cp, [_vp, _sz]),
+    "gdg_chain_create": (_vp, [_vp]),
+    "gdg_chain_destroy": (None, [_vp]),
+    "gdg_chain_append_unit": (_int, [_vp, _int]),
+    "gdg_chain_remove_unit": (_int, [_vp, _int]),
+    "gdg_chain_move_up": (_int, [_vp, _int]),
+    "gdg_chain_move_down": (_int, [_vp, _int]),
+    "gdg_chain_unit_type": (_int, [_vp, _int]),
+    "gdg_chain_set_bypass": (_int, [_vp, _int, _int]),
+    "gdg_chain_get_bypass": (_int, [_vp, _int, C.POINTER(_int)]),
+    "gdg_chain_set_discrete_value": (_int, [_vp, _int, _cp, _cp]),
+    "gdg_chain_get_discrete_value": (_int, [_vp, _int, _cp, C.POINTER(_cp)]),
+    "gdg_chain_set_numeric_value": (_int, [_vp, _int, _cp, _i32]),
+    "gdg_chain_get_numeric_value": (_int, [_vp, _int, _cp, C.POINTER(_i32)]),
+    "gdg_chain_length": (_int, [_vp]),
+    "gdg_chain_parameter_count": (_int, [_vp, _int]),
+    "gdg_chain_parameter": (_int, [_vp, _int, _int, C.POINTER(_Parameter)]),
+    "gdg_chain_parameter_discrete_value": (_cp, [_vp, _int, _int, _int]),
+    "gdg_chain_process": (_int, [_vp, _vp, _vp, _sz, _u32]),
+    "gdg_process_batch": (_int, [_vp, _sz, _vp, _vp, _sz, _u32]),
+    "gdg_process_batch_device": (_int, [_vp, _sz, _vp, _vp, _sz, _sz, _u32, _vp]),
+    "gdg_spatializer_create": (_vp, [_u32]),
+    "gdg_spatializer_destroy": (None, [_vp]),
+    "gdg_spatializer_set_azimuth": (_int, [_vp, _u32, _dbl]),
+    "gdg_spatializer_get_azimuth": (_int, [_vp, _u32, C.POINTER(_dbl)]),
+    "gdg_spatializer_set_distance": (_int, [_vp, _u32, _dbl]),
+    "gdg_spatializer_get_distance": (_int, [_vp, _u32, C.POINTER(_dbl)]),
+    "gdg_spatializer_set_level": (_int, [_vp, _u32, _dbl]),
+    "gdg_spatializer_get_level": (_int, [_vp, _u32, C.POINTER(_dbl)]),
+    "gdg_spatializer_input_count": (_u32, [_vp]),
+    "gdg_spatializer_output_count": (_u32, [_vp]),
+    "gdg_spatializer_set_sample_rate": (_int, [_vp, _u32]),
+    "gdg_spatializer_process": (_int, [_vp, _vp, _u32, _vp, _vp, _u32, _sz]),
+    "gdg_spatializer_process_device": (_int, [_vp, _vp, _sz, _vp, _vp, _sz, _sz, _int, _vp]),
+    "gdg_tuner_create": (_vp, []),
+    "gdg_tuner_destroy": (None, [_vp]),
+    "gdg_tuner_process": (_int, [_vp, _vp, _sz, _u32]),
+    "gdg_tuner_process_device": (_int, [_vp, _vp, _sz, _u32, _vp]),
+    "gdg_tuner_analyze": (_int, [_vp, C.POINTER(_TunerResult)]),
+    "gdg_controller_process": (_int, [_vp, _u32, _vp, _int, _vp, _vp, _vp, _u32, _sz, _u32]),
+}
+
+_LIBS = {}
+
+
+def load(path=None):
+    """dlopen libgdg (default: the in-tree CUDA build) and bind the ABI.  Fails loudly if the
+    library is missing - there is no Python / CPU fallback for any processing call."""
+    path = os.path.abspath(path or DEFAULT_LIBRARY)
+    if path not in _LIBS:
+        if not os.path.exists(path):
+            raise GdgError("libgdg not built: %s is missing (run `python go-dsp-guitar_b200/build.py`); "
+                           "there is no CPU fallback" % path)
+        lib = C.CDLL(path)
+        for name, (res, args) in ABI.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _LIBS[path] = lib
+    return _LIBS[path]
+
+
+def _f64(x):
+    return np.ascontiguousarray(x, dtype=np.float64)
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class _Base:
+    def __init__(self, lib=None):
+        self._lib = lib if lib is not None else load()
+
+    def _err(self):
+        return GdgError(self._lib.gdg_last_error().decode("utf-8", "replace"))
+
+    def _check(self, rc):
+        if rc < 0:
+            raise self._err()
+        return rc
+
+
+def init(device=-1, lib=None):
+    lib = lib if lib is not None else load()
+    if lib.gdg_init(device) != 0:
+        raise GdgError(lib.gdg_last_error().decode())
+
+
+def backend_name(lib=None):
+    return (lib if lib is not None else load()).gdg_backend_name().decode()
+
+
+def launch_count(lib=None):
+    return (lib if lib is not None else load()).gdg_launch_count()
+
+
+class IRBank(_Base):
+    """filter.ImpulseResponses (filter/filter.go:79-82)."""
+
+    def __init__(self, lib=None, _handle=None):
+        super().__init__(lib)
+        self._h = _handle if _handle is not None else self._lib.gdg_irbank_create()
+
+    @classmethod
+    def import_file(cls, index_json_path, lib=None):
+        """filter.Import (filter/filter.go:704-802)."""
+        lib = lib if lib is not None else load()
+        h = lib.gdg_irbank_import(os.fsencode(index_json_path))
+        if not h:
+            raise GdgError(lib.gdg_last_error().decode())
+        return cls(lib, _handle=h)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._lib.gdg_irbank_destroy(self._h)
+
+    def add(self, name, compensation_db, samples, source_rate):
+        s = _f64(samples)
+        self._check(self._lib.gdg_irbank_add(self._h, name.encode(), compensation_db, _ptr(s), len(s), source_rate))
+
+    def add_raw(self, name, compensation_db, samples, rate):
+        s = _f64(samples)
+        self._check(self._lib.gdg_irbank_add_raw(self._h, name.encode(), compensation_db, _ptr(s), len(s), rate))
+
+    def names(self):
+        return [self._lib.gdg_irbank_name(self._h, i).decode() for i in range(self._lib.gdg_irbank_name_count(self._h))]
+
+
+class Chain(_Base):
+    """signal.Chain (signal/signal.go:21-36) backed by the fused sm_100a segment kernel."""
+
+    def __init__(self, bank=None, lib=None):
+        super().__init__(lib if lib is not None else (bank._lib if bank is not None else None))
+        self._bank = bank                                   # keep alive
+        self._h = self._lib.gdg_chain_create(bank._h if bank is not None else None)
+        if not self._h:
+            raise self._err()
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._lib.gdg_chain_destroy(self._h)
+
+    def append_unit(self, unit_type):
+        if isinstance(unit_type, str):
+            unit_type = UNIT_TYPES.index(unit_type)
+        r = self._lib.gdg_chain_append_unit(self._h, unit_type)
+        if r < 0:
+            raise self._err()
+        return r
+
+    def remove_unit(self, i):
+        self._check(self._lib.gdg_chain_remove_unit(self._h, i))
+
+    def move_up(self, i):
+        self._check(self._lib.gdg_chain_move_up(self._h, i))
+
+    def move_down(self, i):
+        self._check(self._lib.gdg_chain_move_down(self._h, i))
+
+    def unit_type(self, i):
+        return self._check(self._lib.gdg_chain_unit_type(self._h, i))
+
+    def set_bypass(self, i, bypass):
+        self._check(self._lib.gdg_chain_set_bypass(self._h, i, int(bool(bypass))))
+
+    def get_bypass(self, i):
+        v = C.c_int()
+        self._check(self._lib.gdg_chain_get_bypass(self._h, i, C.byref(v)))
+        return bool(v.value)
+
+    def set_discrete_value(self, i, name, value):
+        self._check(self._lib.gdg_chain_set_discrete_value(self._h, i, name.encode(), value.encode()))
+
+    def get_discrete_value(self, i, name):
+        v = C.c_char_p()
+        self._check(self._lib.gdg_chain_get_discrete_value(self._h, i, name.encode(), C.byref(v)))
+        return v.value.decode()
+
+    def set_numeric_value(self, i, name, value):
+        self._check(self._lib.gdg_chain_set_numeric_value(self._h, i, name.encode(), int(value)))
+
+    def get_numeric_value(self, i, name):
+        v = C.c_int32()
+        self._check(self._lib.gdg_chain_get_numeric_value(self._h, i, name.encode(), C.byref(v)))
+        return v.value
+
+    def parameters(self, i):
+        """Chain.Parameters(id) -> list of effects.Parameter-like dicts (effects.go:69-78)."""
+        n = self._check(self._lib.gdg_chain_parameter_count(self._h, i))
+        out = []
+        for k in range(n):
+            p = _Parameter()
+            self._check(self._lib.gdg_chain_parameter(self._h, i, k, C.byref(p)))
+            vals = [self._lib.gdg_chain_parameter_discrete_value(self._h, i, k, j).decode()
+                    for j in range(p.discrete_value_count)]
+            out.append({"Name": p.name.decode(), "Type": p.type, "PhysicalUnit": p.physical_unit.decode(),
+                        "Minimum": p.minimum, "Maximum": p.maximum, "NumericValue": p.numeric_value,
+                        "DiscreteValueIndex": p.discrete_value_index, "DiscreteValues": vals})
+        return out
+
+    def length(self):
+        return self._lib.gdg_chain_length(self._h)
+
+    def process(self, x, sample_rate):
+        """Chain.Process(in, out, sampleRate) with host buffers (signal.go:361-414)."""
+        x = _f64(x)
+        out = np.empty_like(x)
+        self._check(self._lib.gdg_chain_process(self._h, _ptr(x), _ptr(out), len(x), sample_rate))
+        return out
+
+
+def _handles(objs):
+    return (C.c_void_p * len(objs))(*[o._h for o in objs])
+
+
+def process_batch(chains, inputs, sample_rate):
+    """The channel fan-out of controller.process (controller.go:2682-2705), host buffers [C][n]."""
+    lib = chains[0]._lib
+    x = _f64(inputs)
+    c, n = x.shape
+    out = np.empty_like(x)
+    ip = (C.c_void_p * c)(*[x[i].ctypes.data for i in range(c)])
+    op = (C.c_void_p * c)(*[out[i].ctypes.data for i in range(c)])
+    if lib.gdg_process_batch(_handles(chains), c, ip, op, n, sample_rate) < 0:
+        raise GdgError(lib.gdg_last_error().decode())
+    return out
+
+
+class BatchRunner:
+    """Pre-marshalled handle array for repeated device-resident batches (bench / streaming)."""
+
+    def __init__(self, chains):
+        self.chains = list(chains)
+        self._lib = chains[0]._lib
+        self._arr = _handles(self.chains)
+
+    def process_device(self, d_in_ptr, d_out_ptr, stride, n, sample_rate, stream=None):
+        if self._lib.gdg_process_batch_device(self._arr, len(self.chains), d_in_ptr, d_out_ptr, stride, n, sample_rate, stream) < 0:
+            raise GdgError(self._lib.gdg_last_error().decode())
+
+    def process_host(self, in_ptrs, out_ptrs, n, sample_rate):
+        if self._lib.gdg_process_batch(self._arr, len(self.chains), in_ptrs, out_ptrs, n, sample_rate) < 0:
+            raise GdgError(self._lib.gdg_last_error().decode())
+
+
+class Spatializer(_Base):
+    """spatializer.Spatializer (spatializer/spatializer.go:30-41)."""
+
+    def __init__(self, input_channels, lib=None):
+        super().__init__(lib)
+        self.n = input_channels
+        self._h = self._lib.gdg_spatializer_create(input_channels)
+        if not self._h:
+            raise self._err()
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._lib.gdg_spatializer_destroy(self._h)
+
+    def set_azimuth(self, ch, v):
+        self._check(self._lib.gdg_spatializer_set_azimuth(self._h, ch, v))
+
+    def get_azimuth(self, ch):
+        v = C.c_double()
+        self._check(self._lib.gdg_spatializer_get_azimuth(self._h, ch, C.byref(v)))
+        return v.value
+
+    def set_distance(self, ch, v):
+        self._check(self._lib.gdg_spatializer_set_distance(self._h, ch, v))
+
+    def get_distance(self, ch):
+        v = C.c_double()
+        self._check(self._lib.gdg_spatializer_get_distance(self._h, ch, C.byref(v)))
+        return v.value
+
+    def set_level(self, ch, v):
+        self._check(self._lib.gdg_spatializer_set_level(self._h, ch, v))
+
+    def get_level(self, ch):
+        v = C.c_double()
+        self._check(self._lib.gdg_spatializer_get_level(self._h, ch, C.byref(v)))
+        return v.value
+
+    def get_input_count(self):
+        return self._lib.gdg_spatializer_input_count(self._h)
+
+    def get_output_count(self):
+        return self._lib.gdg_spatializer_output_count(self._h)
+
+    def set_sample_rate(self, rate):
+        self._check(self._lib.gdg_spatializer_set_sample_rate(self._h, rate))
+
+    def process(self, inputs, aux=None):
+        x = _f64(inputs)
+        c, n = x.shape
+        out = np.zeros((2, n))
+        ip = (C.c_void_p * c)(*[x[i].ctypes.data for i in range(c)])
+        op = (C.c_void_p * 2)(out[0].ctypes.data, out[1].ctypes.data)
+        a = _f64(aux) if aux is not None else None
+        self._check(self._lib.gdg_spatializer_process(self._h, ip, c, _ptr(a) if a is not None else None, op, 2, n))
+        return out
+
+    def process_device(self, d_in_ptr, stride, d_out_ptr, out_stride, n, d_aux_ptr=None, accumulate=False, stream=None):
+        self._check(self._lib.gdg_spatializer_process_device(self._h, d_in_ptr, stride, d_aux_ptr, d_out_ptr, out_stride,
+                                                             n, int(accumulate), stream))
+
+
+class Tuner(_Base):
+    """tuner.Tuner (tuner/tuner.go:62-65)."""
+
+    def __init__(self, lib=None):
+        super().__init__(lib)
+        self._h = self._lib.gdg_tuner_create()
+        if not self._h:
+            raise self._err()
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._lib.gdg_tuner_destroy(self._h)
+
+    def process(self, samples, sample_rate):
+        s = _f64(samples)
+        self._check(self._lib.gdg_tuner_process(self._h, _ptr(s), len(s), sample_rate))
+
+    def process_device(self, d_ptr, n, sample_rate, stream=None):
+        self._check(self._lib.gdg_tuner_process_device(self._h, d_ptr, n, sample_rate, stream))
+
+    def analyze(self):
+        r = _TunerResult()
+        self._check(self._lib.gdg_tuner_analyze(self._h, C.byref(r)))
+        return {"cents": r.cents, "frequency": r.frequency, "note": r.note.decode()}
+
+
+def controller_process(chains, tuner, tuner_channel, spat, inputs, sample_rate):
+    """controller.process (controller.go:2648-2783) with host buffers: returns out[C (+2)][n]."""
+    lib = chains[0]._lib
+    x = _f64(inputs)
+    c, n = x.shape
+    n_out = c + (2 if spat is not None else 0)
+    out = np.zeros((n_out, n))
+    ip = (C.c_void_p * c)(*[x[i].ctypes.data for i in range(c)])
+    op = (C.c_void_p * n_out)(*[out[i].ctypes.data for i in range(n_out)])
+    rc = lib.gdg_controller_process(_handles(chains), c, tuner._h if tuner else None, tuner_channel,
+                                    spat._h if spat else None, ip, op, n_out, n, sample_rate)
+    if rc < 0:
+        raise GdgError(lib.gdg_last_error().decode())
+    return out

@@ -1,0 +1,54 @@
+/*
+ * gdg_backend.h - what the host runtime (gdg_host.cpp) needs from the device
+ * side.  The product implements it with CUDA (gdg_kernels.cu); tests/emu/ builds
+ * a host-only implementation of the same kernels' source for CPU-side checks of
+ * the parallel formulation (never shipped, never a fallback: the CUDA backend
+ * fails loudly when no device is present).
+ */
+#ifndef GDG_BACKEND_H
+#define GDG_BACKEND_H
+
+#include <stddef.h>
+#include <stdint.h>
+#include "gdg_device.h"
+
+/* all calls return 0 on success; on failure the message is in gdgb_error() */
+const char *gdgb_error(void);
+const char *gdgb_name(void);                    /* "cuda:sm_100a" or "host-emulation (tests only)" */
+int gdgb_init(int device);                      /* selects the device, uploads constant tables */
+int gdgb_device(void);
+int gdgb_sm_count(void);
+void *gdgb_stream(void);                        /* the library's stream (cudaStream_t) */
+
+void *gdgb_alloc(size_t bytes);                 /* zero-initialised device memory, NULL on failure */
+void gdgb_free(void *p);
+int gdgb_zero(void *p, size_t bytes);
+int gdgb_upload(void *dst, const void *src, size_t bytes);      /* host -> device, stream ordered */
+int gdgb_download(void *dst, const void *src, size_t bytes);    /* device -> host, synchronises */
+int gdgb_copy(void *dst, const void *src, size_t bytes);        /* device -> device */
+int gdgb_sync(void);
+void *gdgb_pinned_alloc(size_t bytes);
+void gdgb_pinned_free(void *p);
+int gdgb_is_pinned(const void *p);
+
+/* constant tables: anti-aliasing FIRs, Lanczos phase weights; twiddles live in device memory */
+int gdgb_set_tables(const double *aa2, const double *aa4, const double *lz2, const double *lz4,
+                    const double *twiddles /* GDG_MAX_FFT/2 complex */);
+
+/* fused chain segment: CTA c runs descs[c] (NULL -> pass-through copy when in != out, else nothing)
+ * on in + c*stride -> out + c*stride */
+int gdgb_launch_chains(const gdg_chain_desc *const *d_descs, int channels, const double *d_in, double *d_out,
+                       long stride, int n, void *stream);
+
+/* spatializer: out[2][n] (+)= sum over channels; hist_in/hist_out: [C][hs] double-buffered history */
+int gdgb_launch_spatializer(const gdg_spat_channel *d_ch, int channels, const double *d_in, long stride,
+                            const double *d_hist_in, double *d_hist_out, int hs, const double *d_aux,
+                            double *d_outL, double *d_outR, int n, int accumulate, void *stream);
+
+/* tuner: autocorrelation of `ring` (n_ring samples, oldest at `pos`) zero-padded to fft_size (power of two):
+ * d_work: 2*fft_size doubles; result corr[0..fft_size) left in d_work */
+int gdgb_autocorrelate(const double *d_ring, int n_ring, int pos, double *d_work, int fft_size, void *stream);
+
+uint64_t gdgb_launch_count(void);               /* kernels launched so far (bench "gpu_launches") */
+
+#endif

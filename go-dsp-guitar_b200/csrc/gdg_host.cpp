@@ -1,0 +1,1316 @@
+/*
+ * gdg_host.cpp - host runtime of libgdg: the C ABI of include/gdg.h.
+ *
+ * Mirrors the reference's control surface for the hot path - effects.Unit
+ * parameter store (effects/effects.go:96-384), signal.Chain slot list
+ * (signal/signal.go), filter.ImpulseResponses + IR algebra
+ * (filter/filter.go:127-336, 520-802), spatializer and tuner control state - and
+ * turns it into POD descriptors + device state for the sm_100a kernels
+ * (gdg_kernels.cu through gdg_backend.h).  No audio sample is ever computed
+ * here: the only arithmetic on this side is parameter resolution (dB -> factor,
+ * RC coefficients, delay lengths) and impulse-response compilation (control
+ * path, runs when a power-amp parameter or the sample rate changes).
+ */
+#include "../../include/gdg.h"
+#include "../../include/gdg_consts.h"
+#include "../../include/gdg_tables.h"
+#include "gdg_backend.h"
+#include "gdg_device.h"
+
+#include <algorithm>
+#include <cmath>
+#include <complex>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_error;
+int fail(const char *fmt, ...)
+{
+    char buf[1024];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    g_error = buf;
+    return -1;
+}
+int backend_fail(const char *what) { return fail("%s: %s", what, gdgb_error()); }
+
+std::once_flag g_init_once;
+int g_init_status = -1;
+std::string g_init_error;
+
+/* ------------------------------------------------------------------------ */
+/* small host-side numerics used by the control path                         */
+/* ------------------------------------------------------------------------ */
+typedef std::complex<double> cplx;
+
+uint64_t next_pow2(uint64_t v, uint32_t *exp_out = nullptr)     /* fft/fft.go:393-409 */
+{
+    uint64_t p = 1; uint32_t e = 0;
+    while (p < v) { p <<= 1; e++; }
+    if (exp_out) *exp_out = e;
+    return p;
+}
+
+/* iterative radix-2 complex FFT (forward, unscaled); n power of two */
+void fft_inplace(std::vector<cplx> &a, bool inverse)
+{
+    const size_t n = a.size();
+    for (size_t i = 1, j = 0; i < n; i++) {
+        size_t bit = n >> 1;
+        for (; j & bit; bit >>= 1) j ^= bit;
+        j ^= bit;
+        if (i < j) std::swap(a[i], a[j]);
+    }
+    for (size_t len = 2; len <= n; len <<= 1) {
+        const double ang = (inverse ? 2.0 : -2.0) * GDG_MATH_PI / (double)len;
+        for (size_t i = 0; i < n; i += len)
+            for (size_t k = 0; k < len / 2; k++) {
+                const cplx w(std::cos(ang * (double)k), std::sin(ang * (double)k));
+                const cplx u = a[i + k], v = a[i + k + len / 2] * w;
+                a[i + k] = u + v; a[i + k + len / 2] = u - v;
+            }
+    }
+    if (inverse) for (auto &x : a) x /= (double)n;
+}
+/* full spectrum of a real sequence (what RealFourier yields, fft/fft.go:744-856) */
+std::vector<cplx> real_spectrum(const std::vector<double> &x)
+{
+    std::vector<cplx> a(x.begin(), x.end());
+    if (a.size() > 1) fft_inplace(a, false);
+    return a;
+}
+
+/* resample/resample.go:10-31, 36-66 */
+double lanczos_kernel(double x, double a)
+{
+    if (x == 0) return 1.0;
+    if (-a < x && x < a) {
+        const double pix = GDG_MATH_PI * x;
+        return (a * (std::sin(pix) * std::sin(pix / a))) / (pix * pix);
+    }
+    return 0.0;
+}
+double lanczos_interpolate(const double *s, long n, double x, int a)
+{
+    const long idx = (long)std::floor(x);
+    double sum = 0.0;
+    for (long i = idx + 1 - a; i < idx + 1 + a; i++)
+        if (i >= 0 && i < n) sum += s[i] * lanczos_kernel(x - (double)i, (double)a);
+    return sum;
+}
+/* resample/resample.go:72-103 Time */
+std::vector<double> resample_time(const std::vector<double> &in, uint32_t src, uint32_t dst)
+{
+    const double lf = (double)in.size() * ((double)dst / (double)src);
+    const double fl = std::floor(lf);
+    long len = (long)fl;
+    if (fl == lf) len--;
+    if (len < 0) len = 0;
+    std::vector<double> out((size_t)len);
+    const double dx = (double)src / (double)dst;
+    for (long i = 0; i < len; i++) out[(size_t)i] = lanczos_interpolate(in.data(), (long)in.size(), (double)i * dx, 3);
+    return out;
+}
+
+double db2fac(int32_t db) { return std::pow(10.0, 0.05 * (double)db); }     /* effects.go:389-394 */
+
+/* ------------------------------------------------------------------------ */
+/* impulse responses + IR algebra (filter/filter.go)                          */
+/* ------------------------------------------------------------------------ */
+const uint32_t k_sample_rates[7] = {22050, 32000, 44100, 48000, 88200, 96000, 192000};   /* filter.go:25-33 */
+
+struct ImpulseResponse { std::string name; uint32_t rate; double comp; std::vector<double> data; };
+
+struct FilterIR {                    /* the coefficient side of filter.filterStruct */
+    std::vector<double> coeffs; uint32_t rate = 0; double comp = 0.0;
+};
+FilterIR ir_multiply(const FilterIR &f, double s)          /* filter.go:270-323 (compensation resets to 0) */
+{
+    FilterIR r; r.rate = f.rate; r.comp = 0.0; r.coeffs.resize(f.coeffs.size());
+    for (size_t i = 0; i < f.coeffs.size(); i++) r.coeffs[i] = s * f.coeffs[i];
+    return r;
+}
+FilterIR ir_normalize(const FilterIR &f)                   /* filter.go:127-138, 328-336 */
+{
+    double sum = 0.0;
+    for (double c : f.coeffs) sum += c * c;
+    return ir_multiply(f, f.comp / std::sqrt(sum));
+}
+FilterIR ir_add(const FilterIR &a, const FilterIR &b)      /* filter.go:167-253 */
+{
+    FilterIR r; r.rate = a.rate; r.comp = 0.0;
+    r.coeffs.assign(std::max(a.coeffs.size(), b.coeffs.size()), 0.0);
+    std::copy(a.coeffs.begin(), a.coeffs.end(), r.coeffs.begin());
+    for (size_t i = 0; i < b.coeffs.size(); i++) r.coeffs[i] += b.coeffs[i];
+    return r;
+}
+FilterIR ir_reduce(const FilterIR &f, uint32_t order)      /* filter.go:520-604 */
+{
+    const uint64_t n = f.coeffs.size();
+    if (n <= (uint64_t)order) return f;
+    const uint64_t n_src = next_pow2(n), n_tgt = next_pow2(order);
+    std::vector<double> padded(n_src, 0.0);
+    std::copy(f.coeffs.begin(), f.coeffs.end(), padded.begin());
+    std::vector<cplx> fr = real_spectrum(padded);
+    const uint32_t pos_src = (uint32_t)(n_src >> 1) + 1, half_tgt = (uint32_t)(n_tgt >> 1), pos_tgt = half_tgt + 1;
+    std::vector<double> re(pos_src), im(pos_src);
+    for (uint32_t i = 0; i < pos_src; i++) { re[i] = fr[i].real(); im[i] = fr[i].imag(); }
+    std::vector<cplx> pos(pos_tgt);
+    const double dx = (double)pos_src / (double)pos_tgt;                      /* resample.go:109-142 Frequency */
+    for (uint32_t i = 0; i < pos_tgt; i++) {
+        const double x = (double)i * dx;
+        pos[i] = cplx(lanczos_interpolate(re.data(), pos_src, x, 3), lanczos_interpolate(im.data(), pos_src, x, 3));
+    }
+    /* RealInverseFourier of [pos | conj mirror] (fft.go:863-990): it symmetrises the bins, keeps only the
+     * real parts of DC and Nyquist, and inverts - equivalent to a complex inverse FFT of the Hermitian
+     * completion with real DC/Nyquist. */
+    std::vector<cplx> full(n_tgt);
+    for (uint32_t i = 0; i < pos_tgt && i < n_tgt; i++) full[i] = pos[i];
+    for (uint32_t i = 1; i < half_tgt; i++) full[n_tgt - i] = std::conj(pos[i]);
+    full[0] = cplx(full[0].real(), 0.0);
+    if (half_tgt > 0) full[half_tgt] = cplx(full[half_tgt].real(), 0.0);
+    fft_inplace(full, true);
+    FilterIR r; r.rate = f.rate; r.comp = f.comp; r.coeffs.resize(order);
+    for (uint32_t i = 0; i < order; i++) r.coeffs[i] = full[i].real();
+    return r;
+}
+
+} // namespace
+
+struct gdg_irbank {
+    std::vector<ImpulseResponse> responses;
+    std::vector<std::string> names() const                 /* filter.go:681-699 */
+    {
+        std::vector<std::string> out;
+        for (auto &r : responses) if (std::find(out.begin(), out.end(), r.name) == out.end()) out.push_back(r.name);
+        return out;
+    }
+    const ImpulseResponse *find(const std::string &name, uint32_t rate) const   /* CreateFilter filter.go:619-660 */
+    {
+        for (auto &r : responses) if (r.name == name && r.rate == rate) return &r;
+        return nullptr;
+    }
+    std::vector<std::string> name_cache;
+};
+
+namespace {
+
+/* ------------------------------------------------------------------------ */
+/* compiled power-amp filters: device spectrum shared between chains           */
+/* ------------------------------------------------------------------------ */
+struct DeviceSpectrum { double *d_H = nullptr; int L = 0, F = 0, logM = 0; ~DeviceSpectrum() { if (d_H) gdgb_free(d_H); } };
+std::mutex g_spec_mutex;
+std::map<std::string, std::weak_ptr<DeviceSpectrum>> g_spec_cache;
+
+std::shared_ptr<DeviceSpectrum> make_spectrum(const std::vector<double> &coeffs)
+{
+    const int L = (int)coeffs.size();
+    uint32_t e = 0;
+    const uint64_t B = next_pow2((uint64_t)L, &e);
+    const int F = (int)(2 * B);
+    std::string key((const char *)coeffs.data(), coeffs.size() * sizeof(double));
+    std::lock_guard<std::mutex> lk(g_spec_mutex);
+    auto it = g_spec_cache.find(key);
+    if (it != g_spec_cache.end()) if (auto sp = it->second.lock()) return sp;
+    auto sp = std::make_shared<DeviceSpectrum>();
+    sp->L = L; sp->F = F; sp->logM = (int)e;               /* M = F/2 = B = 2^e */
+    std::vector<double> padded((size_t)F, 0.0);
+    std::copy(coeffs.begin(), coeffs.end(), padded.begin());
+    std::vector<cplx> H = real_spectrum(padded);            /* filter.go:395-401 */
+    std::vector<double> packed(2 * ((size_t)F / 2 + 1));
+    for (int k = 0; k <= F / 2; k++) { packed[2 * k] = H[(size_t)k].real(); packed[2 * k + 1] = H[(size_t)k].imag(); }
+    sp->d_H = (double *)gdgb_alloc(packed.size() * sizeof(double));
+    if (!sp->d_H || gdgb_upload(sp->d_H, packed.data(), packed.size() * sizeof(double))) return nullptr;
+    g_spec_cache[key] = sp;
+    return sp;
+}
+
+/* ------------------------------------------------------------------------ */
+/* effects.Unit                                                               */
+/* ------------------------------------------------------------------------ */
+struct Param {
+    std::string name; int32_t type; std::string phys;
+    int32_t min, max, num; int32_t didx; std::vector<std::string> disc;
+};
+
+std::vector<std::string> split_bar(const char *s)
+{
+    std::vector<std::string> out; std::string cur;
+    for (const char *c = s; *c; c++) { if (*c == '|') { out.push_back(cur); cur.clear(); } else cur.push_back(*c); }
+    out.push_back(cur);
+    return out;
+}
+
+struct Unit {
+    int type;
+    std::vector<Param> params;
+    gdg_irbank *bank = nullptr;
+    /* device state */
+    double *d_st = nullptr; size_t st_words = 0; long st_key = -1;
+    /* cached descriptor */
+    gdg_unit_desc desc; bool dirty = true; uint32_t cached_rate = 0; bool valid = false;
+    /* power amp */
+    uint32_t pa_rate = 0; bool pa_has_filter = false; FilterIR pa_filter; bool pa_new_filter = false;
+    std::shared_ptr<DeviceSpectrum> pa_spec;
+
+    explicit Unit(int t) : type(t) { memset(&desc, 0, sizeof desc); }
+    ~Unit() { if (d_st) gdgb_free(d_st); }
+
+    void add_num(const char *n, const char *ph, int32_t mn, int32_t mx, int32_t def)
+    { params.push_back(Param{n, GDG_PARAMETER_TYPE_NUMERIC, ph, mn, mx, def, -1, {}}); }
+    void add_disc(const char *n, int didx, std::vector<std::string> vals)
+    { params.push_back(Param{n, GDG_PARAMETER_TYPE_DISCRETE, "", -1, -1, -1, didx, std::move(vals)}); }
+
+    int find(const char *name) const     /* last match wins, like the reference's linear search (effects.go:130-140) */
+    {
+        int idx = -1;
+        for (size_t i = 0; i < params.size(); i++) if (params[i].name == name) idx = (int)i;
+        return idx;
+    }
+    int32_t num(const char *name) const { int i = find(name); return (i >= 0 && params[i].type == GDG_PARAMETER_TYPE_NUMERIC) ? params[i].num : 0; }
+    std::string disc(const char *name) const
+    { int i = find(name); return (i >= 0 && params[i].type == GDG_PARAMETER_TYPE_DISCRETE) ? params[i].disc[params[i].didx] : std::string(); }
+    int disc_index(const char *name) const { int i = find(name); return i >= 0 ? params[i].didx : -1; }
+
+    /* (re)allocate zeroed state when its shape key changes (the reference re-makes its slices the same way) */
+    int ensure_state(size_t words, long key, size_t keep_words = 0)
+    {
+        if (d_st && st_key == key && st_words == words) return 0;
+        double *fresh = (double *)gdgb_alloc(words * sizeof(double));
+        if (!fresh) return backend_fail("device allocation for unit state failed");
+        /* scalar fields of the Go struct (previousPhase, envelope) survive when only the history slice is re-made */
+        if (d_st && keep_words && gdgb_copy(fresh, d_st, std::min(keep_words, std::min(words, st_words)) * sizeof(double)))
+            return backend_fail("state copy failed");
+        if (d_st) { gdgb_sync(); gdgb_free(d_st); }
+        d_st = fresh; st_words = words; st_key = key;
+        return 0;
+    }
+    int follow_mode() const { std::string f = disc("follow"); return f == "envelope" ? GDG_FOLLOW_ENVELOPE : (f == "level" ? GDG_FOLLOW_LEVEL : GDG_FOLLOW_OTHER); }
+    int os_factor() const { std::string o = disc("oversampling"); return o == "2" ? 2 : (o == "4" ? 4 : 1); }
+
+    int compile_poweramp(uint32_t rate);
+    int prepare(uint32_t rate);
+};
+
+/* effects/poweramp.go:25-127 compile */
+int Unit::compile_poweramp(uint32_t rate)
+{
+    if (!bank) return -1;                                   /* "No impulse responses were loaded." */
+    const uint32_t target = (uint32_t)strtoul(disc("filter_order").c_str(), nullptr, 10);
+    FilterIR comp; comp.rate = rate;                        /* filter.Empty */
+    for (int i = 0; i < 8; i++) {
+        char pf[32], pl[32];
+        snprintf(pf, sizeof pf, "filter_%d", i + 1);
+        snprintf(pl, sizeof pl, "level_%d", i + 1);
+        const std::string name = disc(pf);
+        if (name != "- NONE -") {
+            const ImpulseResponse *ir = bank->find(name, rate);
+            if (!ir) return -1;                             /* "Failed to load filter '%s' for sample rate '%d'." */
+            FilterIR f; f.coeffs = ir->data; f.rate = rate; f.comp = ir->comp;
+            if (target > 0) f = ir_reduce(f, target);
+            f = ir_normalize(f);
+            f = ir_multiply(f, db2fac(num(pl)));
+            comp = ir_add(comp, f);
+        }
+    }
+    pa_filter = comp; pa_has_filter = true; pa_new_filter = true;
+    return 0;
+}
+
+/* Resolve parameters -> descriptor (what each Process body recomputes per block in the reference). */
+int Unit::prepare(uint32_t rate)
+{
+    if (type == GDG_UNIT_POWERAMP && rate != pa_rate) {     /* poweramp.go:187-199 */
+        pa_rate = rate;
+        compile_poweramp(rate);
+        dirty = true;
+    }
+    if (valid && !dirty && cached_rate == rate) return 0;
+    gdg_unit_desc d; memset(&d, 0, sizeof d);
+    d.type = type;
+    const double sr = (double)rate;
+    const double m2pi = -GDG_MATH_TWO_PI / sr;
+    switch (type) {
+    case GDG_UNIT_SIGNALGENERATOR: {
+        const std::string t = disc("signal_type");
+        d.i[0] = t == "sine" ? 0 : t == "triangle" ? 1 : t == "square" ? 2 : t == "sawtooth" ? 3 : 4;
+        d.p[0] = (0.01 * (double)num("input_amplitude")) * db2fac(num("input_gain"));
+        d.p[1] = (0.01 * (double)num("signal_amplitude")) * db2fac(num("signal_gain"));
+        d.p[2] = GDG_MATH_TWO_PI * ((double)num("signal_frequency") / sr);
+        const bool fresh = !d_st;
+        if (ensure_state(2, 0)) return -1;
+        if (fresh) {                                       /* random.CreatePRNG(1337): random.go:40-55 */
+            const uint64_t x = ((64979ull * 1337ull) + 83ull) % 2147483647ull;
+            double w[2] = {0.0, 0.0}; memcpy(&w[1], &x, 8);
+            if (gdgb_upload(d_st, w, sizeof w)) return backend_fail("upload");
+        }
+        break; }
+    case GDG_UNIT_NOISEGATE: {
+        const int32_t lo = num("threshold_open"), lc = num("threshold_close");
+        d.i[0] = lo < lc;
+        d.i[1] = (int32_t)(uint32_t)std::floor(((0.001 * (double)num("hold_time")) * sr) + 0.5);
+        d.p[0] = db2fac(lo); d.p[1] = db2fac(lc);
+        if (ensure_state(2, 0)) return -1;
+        break; }
+    case GDG_UNIT_BANDPASS: {
+        const int half = (int)(strtoul(disc("filter_order").c_str(), nullptr, 10) >> 1);
+        int32_t fa = num("frequency_1"), fb = num("frequency_2");
+        if (fa > fb) std::swap(fa, fb);
+        d.i[0] = half;
+        d.p[0] = 1.0 - std::exp(m2pi * (double)fa);
+        d.p[1] = 1.0 - std::exp(m2pi * (double)fb);
+        if (ensure_state(8, half)) return -1;              /* bandpass.go:47-54: re-made when the order changes */
+        break; }
+    case GDG_UNIT_AUTOWAH: {
+        int32_t la = num("level_1"), lb = num("level_2"), fa = num("frequency_1"), fb = num("frequency_2");
+        if (la > lb) { std::swap(la, lb); std::swap(fa, fb); }
+        d.i[0] = follow_mode();
+        d.p[0] = std::exp(-20.0 / sr); d.p[1] = 1.0 - d.p[0];
+        d.p[2] = la; d.p[3] = lb; d.p[4] = fa; d.p[5] = fb;
+        d.p[6] = ((double)fb - (double)fa) / ((double)lb - (double)la);
+        d.p[7] = sr; d.p[8] = std::pow(2.0, 8.0);
+        if (ensure_state(17, 0)) return -1;
+        break; }
+    case GDG_UNIT_AUTOYOY: {
+        int32_t la = num("level_1"), lb = num("level_2");
+        double da = 0.0, dbb = 0.01 * (double)num("depth");
+        if (la > lb) { std::swap(la, lb); std::swap(da, dbb); }
+        const double sr_inv = 1.0 / sr;
+        const int hs = (int)std::floor((0.01 * sr) + 0.5);
+        d.i[0] = hs; d.i[1] = follow_mode();
+        d.p[0] = std::exp(-20.0 * sr_inv); d.p[1] = 1.0 - d.p[0];
+        d.p[2] = la; d.p[3] = lb; d.p[4] = da; d.p[5] = dbb;
+        d.p[6] = (dbb - da) / ((double)lb - (double)la);
+        d.p[7] = sr;
+        if (ensure_state(2 + (size_t)hs, hs, 1)) return -1;
+        break; }
+    case GDG_UNIT_COMPRESSOR:
+        d.i[0] = follow_mode();
+        d.p[0] = std::exp(-20.0 / sr); d.p[1] = 1.0 - d.p[0];
+        d.p[2] = db2fac(num("target_level")); d.p[3] = db2fac(num("gain_limit"));
+        if (ensure_state(1, 0)) return -1;
+        break;
+    case GDG_UNIT_OCTAVER:
+        d.i[0] = follow_mode();
+        d.p[0] = std::exp(-20.0 / sr); d.p[1] = 1.0 - d.p[0];
+        d.p[2] = db2fac(num("level_octave_up")); d.p[3] = db2fac(num("level_clean")); d.p[4] = db2fac(num("level_dist"));
+        d.p[5] = db2fac(num("level_octave_down_first")); d.p[6] = db2fac(num("level_octave_down_second"));
+        d.p[7] = db2fac(num("level_hysteresis"));
+        if (ensure_state(4, 0)) return -1;
+        break;
+    case GDG_UNIT_EXCESS: case GDG_UNIT_FUZZ: case GDG_UNIT_OVERDRIVE: case GDG_UNIT_DISTORTION: {
+        const int f = os_factor();
+        d.i[0] = f;
+        d.p[1] = db2fac(num("level"));
+        if (type == GDG_UNIT_EXCESS) d.p[0] = db2fac(num("gain"));
+        else d.p[0] = db2fac(num("boost") + num("gain"));
+        if (type == GDG_UNIT_FUZZ) {
+            d.i[1] = follow_mode();
+            d.p[2] = 0.01 * (double)num("bias");
+            d.p[3] = 0.01 * (double)num("fuzz"); d.p[4] = 1.0 - d.p[3];
+            const double sr_os = (double)((uint32_t)f * rate);           /* fuzz.go:162-163 */
+            d.p[5] = std::exp(-20.0 / sr_os); d.p[6] = 1.0 - d.p[5];
+        }
+        if (type == GDG_UNIT_OVERDRIVE) {
+            const std::string v = disc("valve");
+            d.i[2] = v == "ECC82 (12AU7)" ? 0 : (v == "ECC83 (12AX7)" ? 1 : -1);
+            d.p[2] = 0.01 * (double)num("drive"); d.p[3] = 1.0 - d.p[2];
+        }
+        if (ensure_state(GDG_OS_ST_WORDS, 0)) return -1;
+        break; }
+    case GDG_UNIT_TONESTACK: {
+        static const double freqs[5] = {20.0, 300.0, 3000.0, 6000.0, 20000.0};
+        static const char *names[4] = {"low", "middle", "presence", "high"};
+        for (int j = 0; j < 4; j++) {
+            d.p[j] = 1.0 - std::exp(m2pi * freqs[j]);
+            d.p[4 + j] = 1.0 - std::exp(m2pi * freqs[j + 1]);
+            d.p[8 + j] = db2fac(num(names[j]));
+        }
+        if (ensure_state(8, 0)) return -1;
+        break; }
+    case GDG_UNIT_CHORUS: {
+        double depth = 0.1 * (double)num("depth");
+        depth = depth < 0.0 ? 0.0 : (depth > 10.0 ? 10.0 : depth);
+        const int hs = (int)std::floor((0.05 * sr) + 0.5);
+        d.i[0] = hs; d.p[0] = depth; d.p[1] = GDG_MATH_PI_THOUSANDTH * (double)num("speed"); d.p[2] = sr;
+        if (ensure_state(2 + (size_t)hs, hs, 1)) return -1;
+        break; }
+    case GDG_UNIT_FLANGER: case GDG_UNIT_PHASER: {
+        double depth = 0.01 * (double)num("depth");
+        depth = depth < 0.0 ? 0.0 : (depth > 1.0 ? 1.0 : depth);
+        const int hs = (int)std::floor((0.002 * sr) + 0.5);
+        d.i[0] = hs; d.p[0] = depth; d.p[1] = GDG_MATH_TWO_PI_HUNDREDTH * (double)num("speed");
+        d.p[2] = sr; d.p[3] = 1.0 / sr; d.p[4] = 0.5; d.p[5] = 0.5;
+        if (type == GDG_UNIT_PHASER) {
+            d.p[5] = 0.5 * std::sin(GDG_MATH_DEGREE_TO_RADIANS * (double)num("phase"));
+            d.p[4] = 1.0 - std::fabs(d.p[5]);
+        }
+        if (ensure_state(2 + (size_t)hs, hs, 1)) return -1;
+        break; }
+    case GDG_UNIT_TREMOLO: {
+        const double period_f = sr / (0.1 * (double)num("frequency"));
+        const uint32_t period = (uint32_t)period_f;
+        const uint32_t un = (uint32_t)(period_f * (0.01 * (double)num("phase")));
+        d.i[0] = (int32_t)(period - un); d.i[1] = (int32_t)un;
+        d.p[0] = db2fac(num("depth"));
+        if (ensure_state(2, 0)) return -1;
+        break; }
+    case GDG_UNIT_RINGMODULATOR:
+        d.p[0] = (GDG_MATH_TWO_PI * (double)num("frequency")) / sr;
+        if (ensure_state(1, 0)) return -1;
+        break;
+    case GDG_UNIT_DELAY: {
+        const int ds = (int)std::floor(((0.001 * (double)num("delay_time")) * sr) + 0.5);
+        d.i[0] = ds; d.p[0] = db2fac(num("feedback")); d.p[1] = db2fac(num("level"));
+        if (ensure_state(2 + (size_t)ds, ds)) return -1;
+        break; }
+    case GDG_UNIT_REVERB: {
+        static const double ap[3] = {0.04204, 0.01348, 0.00452};
+        static const double tt[4] = {0.19196, 0.19996, 0.21596, 0.23204};
+        static const double tc[4] = {0.1855, 0.18325, 0.17875, 0.17425};
+        const double wet = 0.01 * (double)num("mix");
+        d.p[0] = 1.0 - wet; d.p[1] = 0.5 * wet; d.p[6] = 0.7;
+        int hs = 0; size_t total = GDG_RV_ST_DATA;
+        for (int j = 0; j < 4; j++) { d.i[1 + j] = (int32_t)(uint32_t)std::round(tt[j] * sr); d.p[2 + j] = tc[j]; hs = std::max(hs, d.i[1 + j]); }
+        d.i[0] = hs; total += (size_t)hs; d.i[8] = (int32_t)total;
+        for (int a = 0; a < 3; a++) { d.i[5 + a] = (int)std::round(ap[a] * sr); total += (size_t)(2 * std::max(0, d.i[5 + a] - 1)); }
+        if (ensure_state(total, (long)rate)) return -1;   /* reverb.go:199-262: rebuilt when the rate changes */
+        break; }
+    case GDG_UNIT_POWERAMP: {
+        if (!pa_has_filter) { d.i[0] = -1; break; }        /* poweramp.go:210-214: zeros */
+        const int L = (int)pa_filter.coeffs.size();
+        d.i[0] = L;
+        if (L > 0) {
+            if (pa_new_filter || !pa_spec) {
+                uint32_t e = 0;
+                const uint64_t B = next_pow2((uint64_t)L, &e);
+                if (2 * B > GDG_MAX_FFT)
+                    return fail("power_amp: compiled filter has %d taps; filters beyond %d taps (FFT > %d) are not supported by the "
+                                "shared-memory convolution yet - choose filter_order <= %d", L, GDG_MAX_FFT / 2, GDG_MAX_FFT, GDG_MAX_FFT / 2);
+                pa_spec = make_spectrum(pa_filter.coeffs);
+                if (!pa_spec) return backend_fail("filter spectrum upload failed");
+                /* a recompiled filter is a NEW filter object in the reference: fresh (zero) overlap tail */
+                if (d_st) { gdgb_free(d_st); d_st = nullptr; }
+                if (ensure_state((size_t)pa_spec->F, pa_spec->F)) return -1;
+                pa_new_filter = false;
+            }
+            d.i[1] = pa_spec->F; d.i[2] = pa_spec->logM; d.aux = pa_spec->d_H;
+        }
+        break; }
+    case GDG_UNIT_CABINET: {
+        static const double f[7] = {300.0, 120.0, 80.0, 3000.0, 4000.0, 5000.0, 6000.0};
+        for (int j = 0; j < 7; j++) d.p[j] = 1.0 - std::exp(m2pi * f[j]);
+        if (ensure_state(7, 0)) return -1;
+        break; }
+    default: return fail("unknown unit type %d", type);
+    }
+    d.st = d_st;
+    desc = d; dirty = false; cached_rate = rate; valid = true;
+    return 1;       /* descriptor changed */
+}
+
+Unit *create_unit(int type, gdg_irbank *bank)
+{
+    if (type < 0 || type >= GDG_UNIT_COUNT) return nullptr;
+    Unit *u = new Unit(type);
+#define GDG_UNIT(code, ident, name)
+#define GDG_NUM(ident, name, phys, mn, mx, def) if (type == GDG_UNIT_##ident) u->add_num(name, phys, mn, mx, def);
+#define GDG_DISC(ident, name, didx, vals) if (type == GDG_UNIT_##ident) u->add_disc(name, didx, split_bar(vals));
+#include "../../include/gdg_unit_params.def"
+#undef GDG_UNIT
+#undef GDG_NUM
+#undef GDG_DISC
+    if (type == GDG_UNIT_POWERAMP && bank) {               /* effects.PreparePowerAmp: poweramp.go:221-289 */
+        std::vector<std::string> ext{"- NONE -"};
+        for (auto &n : bank->names()) ext.push_back(n);
+        for (int i = 0; i < 8; i++) {
+            char nm[32];
+            snprintf(nm, sizeof nm, "filter_%d", i + 1); u->add_disc(nm, 0, ext);
+            snprintf(nm, sizeof nm, "level_%d", i + 1); u->add_num(nm, "dB", -60, 0, 0);
+        }
+        u->bank = bank;
+    }
+    return u;
+}
+
+const char *k_unit_names[GDG_UNIT_COUNT] = {
+#define GDG_UNIT(code, ident, name) name,
+#define GDG_NUM(...)
+#define GDG_DISC(...)
+#include "../../include/gdg_unit_params.def"
+#undef GDG_UNIT
+#undef GDG_NUM
+#undef GDG_DISC
+};
+
+int ensure_init()
+{
+    std::call_once(g_init_once, [] {
+        int dev = -1;
+        if (const char *e = getenv("GDG_DEVICE")) dev = atoi(e);
+        g_init_status = gdg_init(dev);
+    });
+    if (g_init_status) { g_error = g_init_error; return -1; }
+    return 0;
+}
+
+int check_block(size_t n)
+{
+    if (n == 0 || n > GDG_MAX_N || (n & (n - 1)))
+        return fail("block length %zu is not supported: must be a power of two <= %d", n, GDG_MAX_N);
+    return 0;
+}
+
+} // namespace
+
+/* ---- signal.Chain ----------------------------------------------------------- */
+struct Slot { std::unique_ptr<Unit> unit; bool bypass; };
+struct gdg_chain {
+    gdg_irbank *bank;
+    std::vector<Slot> slots;
+    /* device descriptors: one per fused segment of <= GDG_MAX_SLOTS active units */
+    std::vector<gdg_chain_desc *> d_desc; std::vector<gdg_chain_desc> h_desc;
+    bool topo_dirty = true;
+    bool uploaded = false;                                      /* set when prepare() touched device memory */
+    double *d_in = nullptr, *d_out = nullptr; size_t d_n = 0;   /* single-channel staging for gdg_chain_process */
+    ~gdg_chain() { for (auto p : d_desc) gdgb_free(p); if (d_in) gdgb_free(d_in); if (d_out) gdgb_free(d_out); }
+
+    /* bring the device descriptors up to date; returns number of segments or -1 */
+    int prepare(uint32_t rate)
+    {
+        bool changed = topo_dirty;
+        std::vector<Unit *> active;
+        for (auto &s : slots) if (!s.bypass) {
+            int r = s.unit->prepare(rate);
+            if (r < 0) return -1;
+            if (r > 0) changed = true;
+            active.push_back(s.unit.get());
+        }
+        const size_t nseg = active.empty() ? 1 : (active.size() + GDG_MAX_SLOTS - 1) / GDG_MAX_SLOTS;
+        if (!changed && h_desc.size() == nseg) return (int)nseg;
+        uploaded = true;
+        h_desc.assign(nseg, gdg_chain_desc());
+        for (size_t g = 0; g < nseg; g++) {
+            gdg_chain_desc &cd = h_desc[g];
+            memset(&cd, 0, sizeof cd);
+            for (size_t k = g * GDG_MAX_SLOTS; k < active.size() && k < (g + 1) * GDG_MAX_SLOTS; k++)
+                cd.slot[cd.nslots++] = active[k]->desc;
+        }
+        while (d_desc.size() < nseg) {
+            gdg_chain_desc *p = (gdg_chain_desc *)gdgb_alloc(sizeof(gdg_chain_desc));
+            if (!p) return backend_fail("descriptor allocation failed");
+            d_desc.push_back(p);
+        }
+        for (size_t g = 0; g < nseg; g++)
+            if (gdgb_upload(d_desc[g], &h_desc[g], sizeof(gdg_chain_desc))) return backend_fail("descriptor upload failed");
+        topo_dirty = false;
+        return (int)nseg;
+    }
+};
+
+namespace {
+
+/* a batch = ordered list of chains; caches the device array of descriptor pointers per segment round */
+struct Batch {
+    std::vector<gdg_chain *> chains;
+    std::vector<std::vector<const gdg_chain_desc *>> h_ptrs;     /* [round][channel] */
+    std::vector<const gdg_chain_desc **> d_ptrs;
+    double *d_in = nullptr, *d_out = nullptr; size_t cap = 0;    /* device staging for host-buffer calls */
+    double *h_stage = nullptr; size_t h_cap = 0;                 /* pinned staging */
+    ~Batch() { for (auto p : d_ptrs) gdgb_free((void *)p); if (d_in) gdgb_free(d_in); if (d_out) gdgb_free(d_out); if (h_stage) gdgb_pinned_free(h_stage); }
+};
+std::mutex g_batch_mutex;
+std::unique_ptr<Batch> g_batch;
+
+int run_batch_device(gdg_chain *const *chains, size_t C, const double *d_in, double *d_out, size_t stride, size_t n,
+                     uint32_t rate, void *stream)
+{
+    if (check_block(n)) return -1;
+    std::lock_guard<std::mutex> lk(g_batch_mutex);
+    if (!g_batch || g_batch->chains.size() != C || !std::equal(g_batch->chains.begin(), g_batch->chains.end(), chains)) {
+        g_batch.reset(new Batch());
+        g_batch->chains.assign(chains, chains + C);
+    }
+    Batch &b = *g_batch;
+    size_t rounds = 1;
+    std::vector<int> nseg(C);
+    for (size_t c = 0; c < C; c++) {
+        const int r = chains[c]->prepare(rate);
+        if (r < 0) return -1;
+        nseg[c] = r; rounds = std::max(rounds, (size_t)r);
+    }
+    bool ptr_changed = b.h_ptrs.size() != rounds;
+    std::vector<std::vector<const gdg_chain_desc *>> ptrs(rounds, std::vector<const gdg_chain_desc *>(C, nullptr));
+    for (size_t r = 0; r < rounds; r++)
+        for (size_t c = 0; c < C; c++) if ((int)r < nseg[c]) ptrs[r][c] = chains[c]->d_desc[r];
+    if (!ptr_changed) for (size_t r = 0; r < rounds; r++) if (ptrs[r] != b.h_ptrs[r]) { ptr_changed = true; break; }
+    if (ptr_changed) {
+        for (auto p : b.d_ptrs) gdgb_free((void *)p);
+        b.d_ptrs.clear();
+        for (size_t r = 0; r < rounds; r++) {
+            const gdg_chain_desc **dp = (const gdg_chain_desc **)gdgb_alloc(C * sizeof(void *));
+            if (!dp || gdgb_upload((void *)dp, ptrs[r].data(), C * sizeof(void *))) return backend_fail("descriptor table upload failed");
+            b.d_ptrs.push_back(dp);
+        }
+        b.h_ptrs = ptrs;
+    }
+    /* descriptor / state uploads run on the library stream: order a foreign stream after them */
+    bool touched = ptr_changed;
+    for (size_t c = 0; c < C; c++) if (chains[c]->uploaded) { touched = true; chains[c]->uploaded = false; }
+    if (touched && stream != gdgb_stream() && gdgb_sync()) return backend_fail("synchronize failed");
+    for (size_t r = 0; r < rounds; r++) {
+        const double *src = r == 0 ? d_in : d_out;
+        if (gdgb_launch_chains(b.d_ptrs[r], (int)C, src, d_out, (long)stride, (int)n, stream)) return backend_fail("chain kernel launch failed");
+    }
+    return 0;
+}
+
+bool contiguous(const double *const *p, size_t C, size_t n)
+{
+    for (size_t c = 1; c < C; c++) if (p[c] != p[0] + c * n) return false;
+    return true;
+}
+
+int stage_buffers(Batch &b, size_t words)
+{
+    if (b.cap < words) {
+        if (b.d_in) gdgb_free(b.d_in);
+        if (b.d_out) gdgb_free(b.d_out);
+        b.d_in = (double *)gdgb_alloc(words * sizeof(double));
+        b.d_out = (double *)gdgb_alloc(words * sizeof(double));
+        if (!b.d_in || !b.d_out) return backend_fail("device staging allocation failed");
+        b.cap = words;
+    }
+    return 0;
+}
+
+/* host [C][n] (array of pointers) -> device planar */
+int upload_channels(const double *const *in, size_t C, size_t n, double *d_dst)
+{
+    if (contiguous(in, C, n)) return gdgb_upload(d_dst, in[0], C * n * sizeof(double)) ? backend_fail("upload failed") : 0;
+    for (size_t c = 0; c < C; c++)
+        if (gdgb_upload(d_dst + c * n, in[c], n * sizeof(double))) return backend_fail("upload failed");
+    return 0;
+}
+int download_channels(double *const *out, size_t C, size_t n, const double *d_src)
+{
+    if (contiguous((const double *const *)out, C, n)) return gdgb_download(out[0], d_src, C * n * sizeof(double)) ? backend_fail("download failed") : 0;
+    for (size_t c = 0; c < C; c++)
+        if (gdgb_download(out[c], d_src + c * n, n * sizeof(double))) return backend_fail("download failed");
+    return 0;
+}
+
+} // namespace
+
+/* ---- spatializer -------------------------------------------------------------- */
+struct gdg_spatializer {
+    uint32_t count; uint32_t sample_rate = 96000;         /* never updated: spatializer.go:418-431 does not store the rate */
+    struct Pos { double az = 0, dist = 0, level = 1.0; };
+    std::vector<Pos> pos;
+    int hs; bool dirty = true; int flip = 0;
+    gdg_spat_channel *d_ch = nullptr; double *d_hist[2] = {nullptr, nullptr};
+    double *d_in = nullptr, *d_out = nullptr, *d_aux = nullptr; size_t cap_n = 0;
+    ~gdg_spatializer() { gdgb_free(d_ch); gdgb_free(d_hist[0]); gdgb_free(d_hist[1]); gdgb_free(d_in); gdgb_free(d_out); gdgb_free(d_aux); }
+
+    int alloc_hist(uint32_t rate)
+    {
+        hs = (int)std::ceil((double)rate * GDG_SPAT_GROUP_DELAY);
+        for (int k = 0; k < 2; k++) {
+            gdgb_free(d_hist[k]);
+            d_hist[k] = (double *)gdgb_alloc(std::max<size_t>(1, (size_t)count * hs) * sizeof(double));
+            if (!d_hist[k]) return backend_fail("spatializer history allocation failed");
+        }
+        flip = 0; dirty = true;
+        return 0;
+    }
+    /* per-channel constants of spatializer.go:171-232 */
+    int upload_channels()
+    {
+        std::vector<gdg_spat_channel> ch(count);
+        const double sr = (double)sample_rate;
+        for (uint32_t c = 0; c < count; c++) {
+            const Pos &p = pos[c];
+            const double az = GDG_MATH_DEGREE_TO_RADIANS * p.az;
+            const double sn = std::sin(az), cs = std::cos(az);
+            const double xp = p.dist * sn, yp = p.dist * cs;
+            const double xl = std::fabs(xp + GDG_SPAT_HALF_EFFECTIVE_DISTANCE), xr = std::fabs(xp - GDG_SPAT_HALF_EFFECTIVE_DISTANCE);
+            const double yd = std::fabs(yp), yd2 = yd * yd;
+            const double dl = std::sqrt(xl * xl + yd2), dr = std::sqrt(xr * xr + yd2);
+            double pl = 1.0 / dl; if (pl > 1.0) pl = 1.0;
+            double pr = 1.0 / dr; if (pr > 1.0) pr = 1.0;
+            gdg_spat_channel &o = ch[c];
+            o.fac_left = p.level * pl; o.fac_right = p.level * pr;
+            o.delay_time = GDG_SPAT_DELAY_PER_METRE * (dl - dr);
+            const double ds = std::fabs(o.delay_time) * sr;
+            const double early = std::floor(ds), late = std::ceil(ds);
+            o.d_early = (int)early; if (o.d_early >= hs) o.d_early = hs - 1;
+            o.d_late = (int)late; if (o.d_late >= hs) o.d_late = hs - 1;
+            o.w_early = 1.0 - (ds - early); o.w_late = 1.0 - (late - ds);
+        }
+        if (!d_ch) d_ch = (gdg_spat_channel *)gdgb_alloc(std::max<size_t>(1, count) * sizeof(gdg_spat_channel));
+        if (!d_ch || gdgb_upload(d_ch, ch.data(), count * sizeof(gdg_spat_channel))) return backend_fail("spatializer upload failed");
+        dirty = false;
+        return 0;
+    }
+};
+
+/* ---- tuner ---------------------------------------------------------------------- */
+struct gdg_tuner {
+    static const int N = 96000;                           /* tuner.go:16 NUM_SAMPLES */
+    double *d_ring = nullptr, *d_work = nullptr, *d_block = nullptr; size_t block_cap = 0;
+    int pos = 0; uint32_t rate = 0;
+    std::vector<double> corr;
+    ~gdg_tuner() { gdgb_free(d_ring); gdgb_free(d_work); gdgb_free(d_block); }
+};
+
+/* ================================================================================ */
+/* C ABI                                                                             */
+/* ================================================================================ */
+extern "C" {
+
+const char *gdg_last_error(void) { return g_error.c_str(); }
+const char *gdg_backend_name(void) { return gdgb_name(); }
+const char *gdg_version(void) { return GDG_VERSION; }
+uint64_t gdg_launch_count(void) { return gdgb_launch_count(); }
+void *gdg_pinned_alloc(size_t bytes) { if (ensure_init()) return nullptr; return gdgb_pinned_alloc(bytes); }
+void gdg_pinned_free(void *p) { gdgb_pinned_free(p); }
+void *gdg_stream(void) { if (ensure_init()) return nullptr; return gdgb_stream(); }
+int gdg_synchronize(void) { if (ensure_init()) return -1; return gdgb_sync() ? backend_fail("synchronize") : 0; }
+int gdg_unit_type_count(void) { return GDG_UNIT_COUNT; }
+const char *gdg_unit_type_name(int t) { return (t >= 0 && t < GDG_UNIT_COUNT) ? k_unit_names[t] : nullptr; }
+
+int gdg_init(int device)
+{
+    static std::mutex m; static bool done = false; static int status = -1;
+    std::lock_guard<std::mutex> lk(m);
+    if (done) return status;
+    done = true;
+    if (gdgb_init(device)) { g_init_error = std::string("gdg_init: no usable CUDA device (there is no CPU fallback): ") + gdgb_error(); g_error = g_init_error; return status = -1; }
+    /* constant tables */
+    static const double h2[] = GDG_AA2_HALF_INIT, h4[] = GDG_AA4_HALF_INIT;
+    std::vector<double> aa2(80, 0.0), aa4(160, 0.0);
+    for (int k = 0; k < GDG_AA2_TAPS; k++) aa2[k] = h2[std::min(k, GDG_AA2_TAPS - 1 - k)];
+    for (int k = 0; k < GDG_AA4_TAPS; k++) aa4[k] = h4[std::min(k, GDG_AA4_TAPS - 1 - k)];
+    double lz2[6], lz4[18];
+    for (int q = 0; q < 6; q++) lz2[q] = lanczos_kernel(2.0 - (double)q + 0.5, 3.0);
+    for (int p = 1; p < 4; p++) for (int q = 0; q < 6; q++) lz4[(p - 1) * 6 + q] = lanczos_kernel(2.0 - (double)q + (double)p * 0.25, 3.0);
+    std::vector<double> tw(GDG_MAX_FFT);                   /* GDG_MAX_FFT/2 complex */
+    for (int k = 0; k < GDG_MAX_FFT / 2; k++) {
+        const double arg = (GDG_MATH_MINUS_TWO_PI * (double)k) / (double)GDG_MAX_FFT;
+        tw[2 * k] = std::cos(arg); tw[2 * k + 1] = std::sin(arg);
+    }
+    if (gdgb_set_tables(aa2.data(), aa4.data(), lz2, lz4, tw.data())) { g_init_error = std::string("gdg_init: table upload failed: ") + gdgb_error(); g_error = g_init_error; return status = -1; }
+    g_init_status = 0;
+    return status = 0;
+}
+
+/* ---- impulse responses ---- */
+gdg_irbank *gdg_irbank_create(void) { return new gdg_irbank(); }
+void gdg_irbank_destroy(gdg_irbank *b) { delete b; }
+int gdg_irbank_add(gdg_irbank *b, const char *name, int32_t comp_db, const double *s, size_t n, uint32_t src_rate)
+{
+    if (!b || !name || (!s && n)) return fail("gdg_irbank_add: bad argument");
+    if (src_rate == 0) return fail("gdg_irbank_add: source rate must not be zero");
+    const double fac = std::pow(10.0, 0.05 * (double)comp_db);      /* filter.go:742-745 */
+    std::vector<double> in(s, s + n);
+    for (uint32_t r : k_sample_rates) b->responses.push_back(ImpulseResponse{name, r, fac, resample_time(in, src_rate, r)});
+    return 0;
+}
+int gdg_irbank_add_raw(gdg_irbank *b, const char *name, int32_t comp_db, const double *s, size_t n, uint32_t rate)
+{
+    if (!b || !name || (!s && n)) return fail("gdg_irbank_add_raw: bad argument");
+    b->responses.push_back(ImpulseResponse{name, rate, std::pow(10.0, 0.05 * (double)comp_db), std::vector<double>(s, s + n)});
+    return 0;
+}
+size_t gdg_irbank_name_count(const gdg_irbank *b) { return b ? b->names().size() : 0; }
+const char *gdg_irbank_name(const gdg_irbank *b, size_t i)
+{
+    if (!b) return nullptr;
+    gdg_irbank *mb = const_cast<gdg_irbank *>(b);
+    mb->name_cache = b->names();
+    return i < mb->name_cache.size() ? mb->name_cache[i].c_str() : nullptr;
+}
+
+/* minimal readers for filter.Import: a JSON array of {"Name","Path","Compensation"} and mono RIFF/WAVE */
+static bool read_file(const std::string &path, std::vector<unsigned char> &out)
+{
+    FILE *f = fopen(path.c_str(), "rb");
+    if (!f) return false;
+    fseek(f, 0, SEEK_END); long sz = ftell(f); fseek(f, 0, SEEK_SET);
+    out.resize(sz > 0 ? (size_t)sz : 0);
+    const size_t got = sz > 0 ? fread(out.data(), 1, (size_t)sz, f) : 0;
+    fclose(f);
+    return got == out.size();
+}
+static bool json_string(const std::string &s, size_t &i, std::string &out)
+{
+    if (s[i] != '"') return false;
+    out.clear();
+    for (i++; i < s.size() && s[i] != '"'; i++) {
+        if (s[i] == '\\' && i + 1 < s.size()) {
+            i++;
+            switch (s[i]) { case 'n': out.push_back('\n'); break; case 't': out.push_back('\t'); break;
+                case 'u': { unsigned cp = (unsigned)strtoul(s.substr(i + 1, 4).c_str(), nullptr, 16); i += 4;
+                    if (cp < 0x80) out.push_back((char)cp);
+                    else if (cp < 0x800) { out.push_back((char)(0xC0 | (cp >> 6))); out.push_back((char)(0x80 | (cp & 0x3F))); }
+                    else { out.push_back((char)(0xE0 | (cp >> 12))); out.push_back((char)(0x80 | ((cp >> 6) & 0x3F))); out.push_back((char)(0x80 | (cp & 0x3F))); }
+                    break; }
+                default: out.push_back(s[i]); }
+        } else out.push_back(s[i]);
+    }
+    if (i >= s.size()) return false;
+    i++;
+    return true;
+}
+struct Descriptor { std::string name, path; int32_t comp = 0; };
+static bool parse_index(const std::string &s, std::vector<Descriptor> &out)
+{
+    size_t i = 0;
+    auto ws = [&] { while (i < s.size() && isspace((unsigned char)s[i])) i++; };
+    ws(); if (i >= s.size() || s[i] != '[') return false;
+    i++;
+    for (;;) {
+        ws(); if (i < s.size() && s[i] == ']') return true;
+        if (i >= s.size() || s[i] != '{') return false;
+        i++;
+        Descriptor d;
+        for (;;) {
+            ws(); if (i < s.size() && s[i] == '}') { i++; break; }
+            std::string key; if (i >= s.size() || !json_string(s, i, key)) return false;
+            ws(); if (i >= s.size() || s[i] != ':') return false; i++; ws();
+            if (i < s.size() && s[i] == '"') { std::string v; if (!json_string(s, i, v)) return false;
+                if (!strcasecmp(key.c_str(), "Name")) d.name = v; else if (!strcasecmp(key.c_str(), "Path")) d.path = v; }
+            else { char *end; const double v = strtod(s.c_str() + i, &end); if (end == s.c_str() + i) return false; i = (size_t)(end - s.c_str());
+                if (!strcasecmp(key.c_str(), "Compensation")) d.comp = (int32_t)v; }
+            ws(); if (i < s.size() && s[i] == ',') i++;
+        }
+        out.push_back(d);
+        ws(); if (i < s.size() && s[i] == ',') i++;
+    }
+}
+/* mono PCM16 (wave.go:400-428) and IEEE float64 (wave.go:714-732) payloads */
+static int parse_wav(const std::vector<unsigned char> &b, std::vector<double> &samples, uint32_t &rate, int &channels, std::string &err)
+{
+    if (b.size() < 12 || memcmp(b.data(), "RIFF", 4) || memcmp(b.data() + 8, "WAVE", 4)) { err = "not a RIFF/WAVE file"; return -1; }
+    size_t pos = 12; int fmt = 0, bits = 0; channels = 0; rate = 0; bool have_fmt = false;
+    while (pos + 8 <= b.size()) {
+        uint32_t size; memcpy(&size, b.data() + pos + 4, 4);
+        const unsigned char *payload = b.data() + pos + 8;
+        const size_t avail = std::min<size_t>(size, b.size() - pos - 8);
+        if (!memcmp(b.data() + pos, "fmt ", 4) && avail >= 16) {
+            uint16_t f, c, bp; uint32_t r; memcpy(&f, payload, 2); memcpy(&c, payload + 2, 2); memcpy(&r, payload + 4, 4); memcpy(&bp, payload + 14, 2);
+            if (f == 0xFFFE && avail >= 26) memcpy(&f, payload + 24, 2);       /* WAVE_FORMAT_EXTENSIBLE sub-format */
+            fmt = f; channels = c; rate = r; bits = bp; have_fmt = true;
+        } else if (!memcmp(b.data() + pos, "data", 4)) {
+            if (!have_fmt) { err = "data chunk before fmt chunk"; return -1; }
+            if (fmt == 1 && bits == 16) {
+                const size_t ns = avail / 2; samples.resize(ns);
+                for (size_t i = 0; i < ns; i++) { int16_t v; memcpy(&v, payload + 2 * i, 2); samples[i] = GDG_PCM16_DECODE_SCALE * (double)v; }
+            } else if (fmt == 3 && bits == 64) {
+                const size_t ns = avail / 8; samples.resize(ns);
+                memcpy(samples.data(), payload, ns * 8);
+            } else { err = "unsupported sample format (only 16-bit PCM and 64-bit IEEE float are read here)"; return -1; }
+            return 0;
+        }
+        pos += 8 + (size_t)size + (size & 1);
+    }
+    err = "no data chunk";
+    return -1;
+}
+
+gdg_irbank *gdg_irbank_import(const char *index_json_path)
+{
+    std::vector<unsigned char> buf;
+    if (!index_json_path || !read_file(index_json_path, buf)) { fail("Failed to read descriptor file: '%s'", index_json_path ? index_json_path : "(null)"); return nullptr; }
+    std::vector<Descriptor> ds;
+    if (!parse_index(std::string(buf.begin(), buf.end()), ds)) { fail("Failed to decode descriptor file: '%s'", index_json_path); return nullptr; }
+    gdg_irbank *bank = new gdg_irbank();
+    for (auto &d : ds) {
+        std::vector<unsigned char> wav;
+        if (!read_file(d.path, wav)) { printf("WARNING: During filter import: Could not read file '%s'. - Skipping.\n", d.path.c_str()); continue; }
+        std::vector<double> s; uint32_t rate; int ch; std::string err;
+        if (parse_wav(wav, s, rate, ch, err)) { printf("WARNING: During filter import (file '%s'): %s\n", d.path.c_str(), err.c_str()); continue; }
+        if (ch != 1) { printf("WARNING: During filter import: File '%s' contains %d channels, expected: %d - Skipping.\n", d.path.c_str(), ch, 1); continue; }
+        gdg_irbank_add(bank, d.name.c_str(), d.comp, s.data(), s.size(), rate);
+    }
+    return bank;
+}
+
+/* ---- chain ---- */
+gdg_chain *gdg_chain_create(gdg_irbank *bank)
+{
+    if (ensure_init()) return nullptr;
+    gdg_chain *c = new gdg_chain();
+    c->bank = bank;
+    return c;
+}
+void gdg_chain_destroy(gdg_chain *c)
+{
+    std::lock_guard<std::mutex> lk(g_batch_mutex);
+    if (g_batch && std::find(g_batch->chains.begin(), g_batch->chains.end(), c) != g_batch->chains.end()) g_batch.reset();
+    delete c;
+}
+#define CHAIN_CHECK(c) if (!(c)) return fail("chain is NULL")
+int gdg_chain_append_unit(gdg_chain *c, int type)
+{
+    if (!c) { fail("chain is NULL"); return -1; }
+    Unit *u = create_unit(type, c->bank);
+    if (!u) { fail("%s", "Failed to create effects unit."); return -1; }
+    c->slots.push_back(Slot{std::unique_ptr<Unit>(u), true});          /* starts bypassed: signal.go:74 */
+    c->topo_dirty = true;
+    return (int)c->slots.size() - 1;
+}
+int gdg_chain_remove_unit(gdg_chain *c, int id)
+{
+    CHAIN_CHECK(c);
+    if (id < 0 || id >= (int)c->slots.size()) return fail("Cannot remove unit %d.", id);
+    gdgb_sync();
+    c->slots.erase(c->slots.begin() + id); c->topo_dirty = true;
+    return 0;
+}
+int gdg_chain_move_up(gdg_chain *c, int id)
+{
+    CHAIN_CHECK(c);
+    if (id <= 0 || id >= (int)c->slots.size()) return fail("Cannot move unit %d up.", id);
+    std::swap(c->slots[id], c->slots[id - 1]); c->topo_dirty = true;
+    return 0;
+}
+int gdg_chain_move_down(gdg_chain *c, int id)
+{
+    CHAIN_CHECK(c);
+    if (id < 0 || id >= (int)c->slots.size() - 1) return fail("Cannot move unit %d down.", id);
+    std::swap(c->slots[id], c->slots[id + 1]); c->topo_dirty = true;
+    return 0;
+}
+int gdg_chain_unit_type(gdg_chain *c, int id)
+{
+    if (!c) { fail("chain is NULL"); return -1; }
+    if (id < 0 || id >= (int)c->slots.size()) { fail("Cannot get unit type: No unit %d.", id); return -1; }
+    return c->slots[id].unit->type;
+}
+int gdg_chain_set_bypass(gdg_chain *c, int id, int bypass)
+{
+    CHAIN_CHECK(c);
+    if (id < 0 || id >= (int)c->slots.size()) return fail("Cannot %s bypass: No unit %d.", bypass ? "enable" : "disable", id);
+    if (c->slots[id].bypass != (bypass != 0)) { c->slots[id].bypass = bypass != 0; c->topo_dirty = true; }
+    return 0;
+}
+int gdg_chain_get_bypass(gdg_chain *c, int id, int *bypass)
+{
+    CHAIN_CHECK(c);
+    if (id < 0 || id >= (int)c->slots.size()) return fail("Cannot get bypass value: No unit %d.", id);
+    *bypass = c->slots[id].bypass;
+    return 0;
+}
+int gdg_chain_set_discrete_value(gdg_chain *c, int id, const char *name, const char *value)
+{
+    CHAIN_CHECK(c);
+    if (id < 0 || id >= (int)c->slots.size()) return fail("Cannot set discrete value: No unit %d.", id);
+    Unit *u = c->slots[id].unit.get();
+    const int idx = u->find(name);
+    if (idx < 0) return fail("Failed to set discrete value: Could not find parameter with name '%s'.", name);
+    Param &p = u->params[idx];
+    if (p.type != GDG_PARAMETER_TYPE_DISCRETE) return fail("Failed to set discrete value: Parameter '%s' is not discrete.", name);
+    int v = -1;
+    for (size_t i = 0; i < p.disc.size(); i++) if (p.disc[i] == value) v = (int)i;
+    if (v < 0) return fail("Failed to set discrete value: Value '%s' is not valid for parameter '%s'.", value, name);
+    p.didx = v; u->dirty = true;
+    if (u->type == GDG_UNIT_POWERAMP) u->compile_poweramp(u->pa_rate);     /* poweramp.go:132-154 */
+    return 0;
+}
+int gdg_chain_get_discrete_value(gdg_chain *c, int id, const char *name, const char **value)
+{
+    CHAIN_CHECK(c);
+    if (id < 0 || id >= (int)c->slots.size()) return fail("Cannot get discrete value: No unit %d.", id);
+    Unit *u = c->slots[id].unit.get();
+    const int idx = u->find(name);
+    if (idx < 0) return fail("Failed to get discrete value: Could not find parameter with name '%s'.", name);
+    if (u->params[idx].type != GDG_PARAMETER_TYPE_DISCRETE) return fail("Failed to get discrete value: Parameter '%s' is not discrete.", name);
+    *value = u->params[idx].disc[u->params[idx].didx].c_str();
+    return 0;
+}
+int gdg_chain_set_numeric_value(gdg_chain *c, int id, const char *name, int32_t value)
+{
+    CHAIN_CHECK(c);
+    if (id < 0 || id >= (int)c->slots.size()) return fail("Cannot set numeric value: No unit %d.", id);
+    Unit *u = c->slots[id].unit.get();
+    const int idx = u->find(name);
+    if (idx < 0) return fail("Failed to set numeric value: Could not find parameter with name '%s'.", name);
+    Param &p = u->params[idx];
+    if (p.type != GDG_PARAMETER_TYPE_NUMERIC) return fail("Failed to set numeric value: Parameter '%s' is not numeric.", name);
+    if (value < p.min || value > p.max)
+        return fail("Failed to set numeric value: Parameter '%s' must be between '%d' and '%d' - got '%d'.", name, p.min, p.max, value);
+    p.num = value; u->dirty = true;
+    if (u->type == GDG_UNIT_POWERAMP) u->compile_poweramp(u->pa_rate);     /* poweramp.go:159-181 */
+    return 0;
+}
+int gdg_chain_get_numeric_value(gdg_chain *c, int id, const char *name, int32_t *value)
+{
+    CHAIN_CHECK(c);
+    if (id < 0 || id >= (int)c->slots.size()) return fail("Cannot get numeric value: No unit %d.", id);
+    Unit *u = c->slots[id].unit.get();
+    const int idx = u->find(name);
+    if (idx < 0) return fail("Failed to get numeric value: Could not find parameter with name '%s'.", name);
+    if (u->params[idx].type != GDG_PARAMETER_TYPE_NUMERIC) return fail("Failed to get numeric value: Parameter '%s' is not numeric.", name);
+    *value = u->params[idx].num;
+    return 0;
+}
+int gdg_chain_length(gdg_chain *c) { return c ? (int)c->slots.size() : 0; }
+int gdg_chain_parameter_count(gdg_chain *c, int id)
+{
+    if (!c) { fail("chain is NULL"); return -1; }
+    if (id < 0 || id >= (int)c->slots.size()) { fail("Cannot get parameters: No unit %d.", id); return -1; }
+    return (int)c->slots[id].unit->params.size();
+}
+int gdg_chain_parameter(gdg_chain *c, int id, int index, gdg_parameter *out)
+{
+    CHAIN_CHECK(c);
+    if (id < 0 || id >= (int)c->slots.size()) return fail("Cannot get parameters: No unit %d.", id);
+    Unit *u = c->slots[id].unit.get();
+    if (index < 0 || index >= (int)u->params.size()) return fail("Cannot get parameter %d of unit %d.", index, id);
+    const Param &p = u->params[index];
+    out->name = p.name.c_str(); out->type = p.type; out->physical_unit = p.phys.c_str();
+    out->minimum = p.min; out->maximum = p.max; out->numeric_value = p.num;
+    out->discrete_value_index = p.didx; out->discrete_value_count = (int32_t)p.disc.size();
+    return 0;
+}
+const char *gdg_chain_parameter_discrete_value(gdg_chain *c, int id, int index, int vi)
+{
+    if (!c || id < 0 || id >= (int)c->slots.size()) return nullptr;
+    Unit *u = c->slots[id].unit.get();
+    if (index < 0 || index >= (int)u->params.size()) return nullptr;
+    const Param &p = u->params[index];
+    return (vi >= 0 && vi < (int)p.disc.size()) ? p.disc[vi].c_str() : nullptr;
+}
+
+int gdg_process_batch_device(gdg_chain *const *chains, size_t C, const double *d_in, double *d_out, size_t stride,
+                             size_t n, uint32_t rate, void *stream)
+{
+    if (ensure_init()) return -1;
+    if (!chains || !C || !d_in || !d_out) return fail("gdg_process_batch_device: bad argument");
+    if (stride < n) return fail("gdg_process_batch_device: stride < n");
+    return run_batch_device(chains, C, d_in, d_out, stride, n, rate, stream ? stream : gdgb_stream());
+}
+
+int gdg_process_batch(gdg_chain *const *chains, size_t C, const double *const *in, double *const *out, size_t n, uint32_t rate)
+{
+    if (ensure_init()) return -1;
+    if (!chains || !C || !in || !out) return fail("gdg_process_batch: bad argument");
+    if (check_block(n)) return -1;
+    {   /* make sure the batch object (and its staging) matches */
+        std::lock_guard<std::mutex> lk(g_batch_mutex);
+        if (!g_batch || g_batch->chains.size() != C || !std::equal(g_batch->chains.begin(), g_batch->chains.end(), chains)) {
+            g_batch.reset(new Batch()); g_batch->chains.assign(chains, chains + C);
+        }
+        if (stage_buffers(*g_batch, C * n)) return -1;
+    }
+    Batch &b = *g_batch;
+    if (upload_channels(in, C, n, b.d_in)) return -1;
+    if (run_batch_device(chains, C, b.d_in, b.d_out, n, n, rate, gdgb_stream())) return -1;
+    return download_channels(out, C, n, b.d_out);
+}
+
+int gdg_chain_process(gdg_chain *c, const double *in, double *out, size_t n, uint32_t rate)
+{
+    if (ensure_init()) return -1;
+    CHAIN_CHECK(c);
+    if (!in || !out) return fail("gdg_chain_process: bad argument");
+    if (check_block(n)) return -1;
+    if (c->d_n < n) {
+        gdgb_free(c->d_in); gdgb_free(c->d_out);
+        c->d_in = (double *)gdgb_alloc(n * sizeof(double)); c->d_out = (double *)gdgb_alloc(n * sizeof(double));
+        if (!c->d_in || !c->d_out) return backend_fail("device staging allocation failed");
+        c->d_n = n;
+    }
+    if (gdgb_upload(c->d_in, in, n * sizeof(double))) return backend_fail("upload failed");
+    gdg_chain *one[1] = {c};
+    if (run_batch_device(one, 1, c->d_in, c->d_out, n, n, rate, gdgb_stream())) return -1;
+    return gdgb_download(out, c->d_out, n * sizeof(double)) ? backend_fail("download failed") : 0;
+}
+
+/* ---- spatializer ---- */
+gdg_spatializer *gdg_spatializer_create(uint32_t n)
+{
+    if (ensure_init()) return nullptr;
+    gdg_spatializer *s = new gdg_spatializer();
+    s->count = n; s->pos.resize(n);
+    if (s->alloc_hist(96000)) { delete s; return nullptr; }
+    return s;
+}
+void gdg_spatializer_destroy(gdg_spatializer *s) { delete s; }
+#define SPAT_CH(s, ch, what) if (!(s)) return fail("spatializer is NULL"); \
+    if ((ch) >= (s)->count) return fail("Cannot " what " for channel %d: Only %d channels exist.", (int)(ch), (int)(s)->count)
+int gdg_spatializer_set_azimuth(gdg_spatializer *s, uint32_t ch, double v) { SPAT_CH(s, ch, "set azimuth"); s->pos[ch].az = v; s->dirty = true; return 0; }
+int gdg_spatializer_get_azimuth(gdg_spatializer *s, uint32_t ch, double *v) { SPAT_CH(s, ch, "get azimuth"); *v = s->pos[ch].az; return 0; }
+int gdg_spatializer_set_distance(gdg_spatializer *s, uint32_t ch, double v)
+{
+    SPAT_CH(s, ch, "set distance");
+    if (v < 0.0 || v > 10.0) return fail("%s", "Failed to set distance: Value must be within [0, 10].");
+    s->pos[ch].dist = v; s->dirty = true; return 0;
+}
+int gdg_spatializer_get_distance(gdg_spatializer *s, uint32_t ch, double *v) { SPAT_CH(s, ch, "get distance"); *v = s->pos[ch].dist; return 0; }
+int gdg_spatializer_set_level(gdg_spatializer *s, uint32_t ch, double v)
+{
+    SPAT_CH(s, ch, "set distance");                         /* sic: spatializer.go:393 reuses the "distance" wording */
+    if (v < 0.0 || v > 1.0) return fail("%s", "Failed to set level: Value must be within [0, 1].");
+    s->pos[ch].level = v; s->dirty = true; return 0;
+}
+int gdg_spatializer_get_level(gdg_spatializer *s, uint32_t ch, double *v) { SPAT_CH(s, ch, "get level"); *v = s->pos[ch].level; return 0; }
+uint32_t gdg_spatializer_input_count(gdg_spatializer *s) { return s ? s->count : 0; }
+uint32_t gdg_spatializer_output_count(gdg_spatializer *) { return 2; }
+int gdg_spatializer_set_sample_rate(gdg_spatializer *s, uint32_t rate)
+{
+    if (!s) return fail("spatializer is NULL");
+    gdgb_sync();
+    return s->alloc_hist(rate);
+}
+int gdg_spatializer_process_device(gdg_spatializer *s, const double *d_in, size_t stride, const double *d_aux,
+                                   double *d_out, size_t out_stride, size_t n, int accumulate, void *stream)
+{
+    if (ensure_init()) return -1;
+    if (!s || !d_in || !d_out) return fail("gdg_spatializer_process_device: bad argument");
+    if (n == 0 || n > (size_t)1 << 24) return fail("gdg_spatializer_process_device: bad block length");
+    if (s->dirty) { if (s->upload_channels()) return -1; if (stream && stream != gdgb_stream() && gdgb_sync()) return backend_fail("synchronize failed"); }
+    if (gdgb_launch_spatializer(s->d_ch, (int)s->count, d_in, (long)stride, s->d_hist[s->flip], s->d_hist[s->flip ^ 1], s->hs,
+                                d_aux, d_out, d_out + out_stride, (int)n, accumulate, stream ? stream : gdgb_stream()))
+        return backend_fail("spatializer kernel launch failed");
+    s->flip ^= 1;
+    return 0;
+}
+int gdg_spatializer_process(gdg_spatializer *s, const double *const *in, uint32_t n_in, const double *aux,
+                            double *const *out, uint32_t n_out, size_t n)
+{
+    if (ensure_init()) return -1;
+    if (!s || !in || !out) return fail("gdg_spatializer_process: bad argument");
+    if (n_in != s->count || n_out != 2) return 0;           /* silent no-op like spatializer.go:149 */
+    if (s->cap_n < n) {
+        gdgb_free(s->d_in); gdgb_free(s->d_out); gdgb_free(s->d_aux);
+        s->d_in = (double *)gdgb_alloc(std::max<size_t>(1, s->count) * n * sizeof(double));
+        s->d_out = (double *)gdgb_alloc(2 * n * sizeof(double));
+        s->d_aux = (double *)gdgb_alloc(n * sizeof(double));
+        if (!s->d_in || !s->d_out || !s->d_aux) return backend_fail("spatializer staging allocation failed");
+        s->cap_n = n;
+    }
+    if (upload_channels(in, s->count, n, s->d_in)) return -1;
+    if (aux && gdgb_upload(s->d_aux, aux, n * sizeof(double))) return backend_fail("upload failed");
+    if (gdg_spatializer_process_device(s, s->d_in, n, aux ? s->d_aux : nullptr, s->d_out, n, n, 0, nullptr)) return -1;
+    return download_channels(out, 2, n, s->d_out);
+}
+
+/* ---- tuner ---- */
+gdg_tuner *gdg_tuner_create(void)
+{
+    if (ensure_init()) return nullptr;
+    gdg_tuner *t = new gdg_tuner();
+    t->d_ring = (double *)gdgb_alloc(gdg_tuner::N * sizeof(double));
+    t->d_work = (double *)gdgb_alloc(2 * 262144 * sizeof(double));
+    if (!t->d_ring || !t->d_work) { backend_fail("tuner allocation failed"); delete t; return nullptr; }
+    return t;
+}
+void gdg_tuner_destroy(gdg_tuner *t) { delete t; }
+/* circular.Enqueue (circular/circular.go:33-71) on the device ring */
+int gdg_tuner_process_device(gdg_tuner *t, const double *d, size_t n, uint32_t rate, void *)
+{
+    if (ensure_init()) return -1;
+    if (!t || (!d && n)) return fail("gdg_tuner_process_device: bad argument");
+    const size_t N = gdg_tuner::N;
+    int rc = 0;
+    if (n >= N) { rc = gdgb_copy(t->d_ring, d + (n - N), N * sizeof(double)); t->pos = 0; }
+    else if (n > 0) {
+        const size_t inc = (size_t)t->pos + n;
+        if (inc < N) { rc = gdgb_copy(t->d_ring + t->pos, d, n * sizeof(double)); t->pos = (int)inc; }
+        else {
+            const size_t head = inc - N, tail = N - (size_t)t->pos;
+            rc = gdgb_copy(t->d_ring + t->pos, d, tail * sizeof(double));
+            if (!rc && head) rc = gdgb_copy(t->d_ring, d + tail, head * sizeof(double));
+            t->pos = (int)head;
+        }
+    }
+    t->rate = rate;
+    return rc ? backend_fail("tuner ring copy failed") : 0;
+}
+int gdg_tuner_process(gdg_tuner *t, const double *s, size_t n, uint32_t rate)
+{
+    if (ensure_init()) return -1;
+    if (!t || (!s && n)) return fail("gdg_tuner_process: bad argument");
+    const size_t N = gdg_tuner::N;
+    if (n > N) { s += n - N; n = N; }                       /* only the tail can survive the enqueue */
+    if (t->block_cap < n) { gdgb_free(t->d_block); t->d_block = (double *)gdgb_alloc(std::max<size_t>(1, n) * sizeof(double)); t->block_cap = n; if (!t->d_block) return backend_fail("tuner staging allocation failed"); }
+    if (n && gdgb_upload(t->d_block, s, n * sizeof(double))) return backend_fail("upload failed");
+    return gdg_tuner_process_device(t, t->d_block, n == N ? N : n, rate, nullptr);
+}
+/* tuner.Analyze: tuner/tuner.go:379-577 - the 262144-point autocorrelation runs on the device;
+ * the scalar peak pick / note lookup below is the control-plane tail of the call. */
+int gdg_tuner_analyze(gdg_tuner *t, gdg_tuner_result *res)
+{
+    static const char *names[GDG_TUNER_NOTE_COUNT] = GDG_TUNER_NOTE_NAMES_INIT;
+    static const double freqs[GDG_TUNER_NOTE_COUNT] = GDG_TUNER_NOTE_FREQS_INIT;
+    if (ensure_init()) return -1;
+    if (!t || !res) return fail("gdg_tuner_analyze: bad argument");
+    const long n = gdg_tuner::N;
+    const uint64_t two_n = 2 * (uint64_t)n;
+    const int fft_size = (int)next_pow2(two_n);
+    if (gdgb_autocorrelate(t->d_ring, (int)n, t->pos, t->d_work, fft_size, gdgb_stream())) return backend_fail("autocorrelation failed");
+    const double sr = (double)t->rate;
+    long low = (long)((sr / freqs[GDG_TUNER_NOTE_COUNT - 1]) + 0.5);
+    if (low < 0 || (uint64_t)low >= two_n) low = 0;
+    long high = (long)((sr / freqs[0]) + 0.5);
+    if (high < 0 || (uint64_t)high >= two_n) high = (long)(two_n - 1);
+    const long lo_fetch = std::max<long>(0, low - 1), hi_fetch = std::min<long>((long)fft_size, std::max(high, low) + 2);
+    t->corr.assign((size_t)(hi_fetch - lo_fetch), 0.0);
+    if (gdgb_download(t->corr.data(), t->d_work + lo_fetch, t->corr.size() * sizeof(double))) return backend_fail("download failed");
+    auto corr = [&](long i) { return t->corr[(size_t)(i - lo_fetch)]; };
+    double max_val = -INFINITY; long max_idx = -1;
+    for (long i = low; i < high; i++) if (corr(i) > max_val) { max_val = corr(i); max_idx = i - low; }
+    const long idx = low + max_idx;
+    long up = idx + 1; if (up > n) up = n;
+    long down = idx - 1; if (down < 0) down = 0;
+    down = std::max(down, lo_fetch); up = std::min(up, hi_fetch - 1);
+    const double left = corr(down), right = corr(up);
+    double shift = (0.5 * (right - left)) / ((2.0 * max_val) - (right + left));
+    if (shift < -0.5) shift = -0.5; else if (shift > 0.5) shift = 0.5;
+    const double freq = sr / ((double)idx + shift);
+    const char *note = "Unknown"; double cents = INFINITY, cents_abs = INFINITY;
+    for (int k = 0; k < GDG_TUNER_NOTE_COUNT; k++) {
+        const double dc = 1200.0 * std::log2(freq / freqs[k]);
+        if (std::fabs(dc) < cents_abs) { note = names[k]; cents = dc; cents_abs = std::fabs(dc); }
+    }
+    res->cents = (std::isinf(cents) || std::isnan(cents)) ? 0 : (int8_t)cents;
+    res->frequency = freq; res->note = note;
+    return 0;
+}
+
+/* ---- controller.process mirror ---- */
+int gdg_controller_process(gdg_chain *const *chains, uint32_t C, gdg_tuner *tuner, int tuner_channel, gdg_spatializer *spat,
+                           const double *const *in, double *const *out, uint32_t n_out, size_t n, uint32_t rate)
+{
+    if (ensure_init()) return -1;
+    if (!chains || !C || !in || !out) return fail("gdg_controller_process: bad argument");
+    if (check_block(n)) return -1;
+    if (n_out < C) return 0;                                /* controller.go:2682: nothing happens */
+    {
+        std::lock_guard<std::mutex> lk(g_batch_mutex);
+        if (!g_batch || g_batch->chains.size() != C || !std::equal(g_batch->chains.begin(), g_batch->chains.end(), chains)) {
+            g_batch.reset(new Batch()); g_batch->chains.assign(chains, chains + C);
+        }
+        if (stage_buffers(*g_batch, ((size_t)C + 2) * n)) return -1;
+    }
+    Batch &b = *g_batch;
+    if (upload_channels(in, C, n, b.d_in)) return -1;
+    if (tuner && tuner_channel >= 0 && (uint32_t)tuner_channel < C)
+        if (gdg_tuner_process_device(tuner, b.d_in + (size_t)tuner_channel * n, n, rate, nullptr)) return -1;
+    if (run_batch_device(chains, C, b.d_in, b.d_out, n, n, rate, gdgb_stream())) return -1;
+    const bool do_spat = spat && n_out >= C + 2 && spat->count == C;
+    if (do_spat && gdg_spatializer_process_device(spat, b.d_out, n, nullptr, b.d_out + (size_t)C * n, n, n, 0, nullptr)) return -1;
+    return download_channels(out, (size_t)C + (do_spat ? 2 : 0), n, b.d_out);
+}
+
+} /* extern "C" */

@@ -1,0 +1,185 @@
+/*
+ * gdg_interp.cuh - the fused chain-segment interpreter: one CTA walks the
+ * non-bypassed slots of its channel's chain (signal/signal.go:361-414) with the
+ * block resident in shared memory, plus the spatializer mix-down and the tuner
+ * ring feed.  Compiles for sm_100a (gdg_kernels.cu) and, for tests only, as host
+ * C++ (GDG_HOST_EMU).
+ */
+#ifndef GDG_INTERP_CUH
+#define GDG_INTERP_CUH
+
+#include "gdg_stages2.cuh"
+
+/* shared-memory carve-up (doubles) */
+#define GDG_SMEM_R 0
+#define GDG_SMEM_S (2 * GDG_MAX_N)
+#define GDG_SMEM_SCANB (GDG_SMEM_S + GDG_MAX_N)
+#define GDG_SMEM_SCANA (GDG_SMEM_SCANB + GDG_SCAN_LANES * GDG_NT)
+#define GDG_SMEM_SEG (GDG_SMEM_SCANA + GDG_NT)
+#define GDG_SMEM_MISC (GDG_SMEM_SEG + 3 * GDG_SCAN_LANES * GDG_NSEG)
+#define GDG_SMEM_DOUBLES (GDG_SMEM_MISC + 64)
+#define GDG_SMEM_BYTES (GDG_SMEM_DOUBLES * 8)
+
+GDG_DEVI void ctx_init(gdg_ctx &cx, double *smem, int n)
+{
+    cx.R = smem + GDG_SMEM_R; cx.cur = cx.R; cx.alt = cx.R + GDG_MAX_N;
+    cx.S = smem + GDG_SMEM_S; cx.scanB = smem + GDG_SMEM_SCANB; cx.scanA = smem + GDG_SMEM_SCANA;
+    cx.seg = smem + GDG_SMEM_SEG; cx.misc = smem + GDG_SMEM_MISC; cx.n = n;
+}
+
+GDG_DEV void run_unit(gdg_ctx &cx, const gdg_unit_desc &d, const double *tw)
+{
+    switch (d.type) {
+    case GDG_UNIT_SIGNALGENERATOR: stage_siggen(cx, d); break;
+    case GDG_UNIT_NOISEGATE: stage_noisegate(cx, d); break;
+    case GDG_UNIT_BANDPASS: stage_bandpass(cx, d); break;
+    case GDG_UNIT_AUTOWAH: stage_autowah(cx, d); break;
+    case GDG_UNIT_AUTOYOY: stage_autoyoy(cx, d); break;
+    case GDG_UNIT_COMPRESSOR: stage_compressor(cx, d); break;
+    case GDG_UNIT_OCTAVER: stage_octaver(cx, d); break;
+    case GDG_UNIT_EXCESS: case GDG_UNIT_FUZZ: case GDG_UNIT_OVERDRIVE: case GDG_UNIT_DISTORTION:
+        stage_oversampled(cx, d); break;
+    case GDG_UNIT_TONESTACK: stage_tonestack(cx, d); break;
+    case GDG_UNIT_CHORUS: stage_chorus(cx, d); break;
+    case GDG_UNIT_FLANGER: case GDG_UNIT_PHASER: stage_flanger(cx, d); break;
+    case GDG_UNIT_TREMOLO: stage_tremolo(cx, d); break;
+    case GDG_UNIT_RINGMODULATOR: stage_ringmod(cx, d); break;
+    case GDG_UNIT_DELAY: stage_delay(cx, d); break;
+    case GDG_UNIT_REVERB: stage_reverb(cx, d); break;
+    case GDG_UNIT_POWERAMP: stage_poweramp(cx, d, tw); break;
+    case GDG_UNIT_CABINET: stage_cascade(cx, d, 7, 3); break;
+    default: break;
+    }
+}
+
+/* one channel, one block: load -> every slot -> store */
+GDG_DEV void run_chain(double *smem, const gdg_chain_desc *cd, const double *in, double *out, int n, const double *tw)
+{
+    gdg_ctx cx;
+    ctx_init(cx, smem, n);
+    GDG_THREADS_BEGIN
+        for (int k = tid; k < n; k += GDG_NT) cx.cur[sw(k)] = in[k];
+    GDG_THREADS_END
+    const int ns = cd->nslots;
+    for (int s = 0; s < ns; s++) run_unit(cx, cd->slot[s], tw);
+    GDG_THREADS_BEGIN
+        for (int k = tid; k < n; k += GDG_NT) out[k] = cx.cur[sw(k)];
+    GDG_THREADS_END
+}
+
+/* --------------------------------------------------------------------------
+ * spatializer mix-down (spatializer/spatializer.go:140-335): each thread owns
+ * frames; channels are accumulated in ascending order exactly like the
+ * reference (0..C-1, then aux).  hist: [C][hs] linear history (oldest first).
+ * Launched over frames; a second pass (same launch, after the loop) is not
+ * possible because other CTAs still read the history -> the history update is
+ * its own kernel (spat_push).
+ * -------------------------------------------------------------------------- */
+GDG_DEVI void spat_frame(const gdg_spat_channel *ch, int C, const double *in, long stride, const double *hist, int hs,
+                         const double *aux, double *outL, double *outR, int j, int accumulate)
+{
+    double l = accumulate ? outL[j] : 0.0, r = accumulate ? outR[j] : 0.0;
+    for (int c = 0; c < C; c++) {
+        const gdg_spat_channel &p = ch[c];
+        const double *x = in + (long)c * stride;
+        const double cur = x[j];
+        if (p.delay_time == 0.0) {
+            l += p.fac_left * cur;
+            r += p.fac_right * cur;
+        } else {
+            const int ie = j - p.d_early, il = j - p.d_late;
+            const double *h = hist + (long)c * hs;
+            const double se = ie >= 0 ? x[ie] : h[hs + ie];
+            const double sl = il >= 0 ? x[il] : h[hs + il];
+            const double dsmp = (p.w_early * se) + (p.w_late * sl);
+            if (p.delay_time > 0.0) { l += p.fac_left * dsmp; r += p.fac_right * cur; }
+            else { l += p.fac_left * cur; r += p.fac_right * dsmp; }
+        }
+    }
+    if (aux) { l += aux[j]; r += aux[j]; }
+    outL[j] = l; outR[j] = r;
+}
+
+
+/* --------------------------------------------------------------------------
+ * tuner autocorrelation (tuner/tuner.go:379-446): real FFT of size F through a
+ * complex FFT of size M = F/2 living in global memory; per-index bodies shared by
+ * the CUDA kernels and the test-only host build.
+ * -------------------------------------------------------------------------- */
+#if defined(__CUDACC__) && !defined(GDG_HOST_EMU)
+#define GDG_SINCOSPI(x, s, c) sincospi((x), (s), (c))
+#else
+#define GDG_SINCOSPI(x, s, c) do { *(s) = sin(GDG_PI * (x)); *(c) = cos(GDG_PI * (x)); } while (0)
+#endif
+GDG_DEVI void ac_load_body(const double *ring, int n_ring, int pos, double *w, int i)
+{
+    double v = 0.0;
+    if (i < n_ring) { int p = pos + i; if (p >= n_ring) p -= n_ring; v = ring[p]; }     /* circular.Retrieve: oldest first */
+    w[i] = v;
+}
+GDG_DEVI void ac_twiddle(int pos, int h, double &re, double &im)
+{
+    double s, c;
+    GDG_SINCOSPI(-(double)pos / (double)h, &s, &c);            /* exp(-2 pi i pos / (2h)) */
+    re = c; im = s;
+}
+GDG_DEVI void ac_dif_body(double *w, int h, int b)
+{
+    {
+        const int grp = b / h, pos = b - grp * h, i0 = grp * 2 * h + pos, i1 = i0 + h;
+        const double ar = w[2 * i0], ai = w[2 * i0 + 1], cr = w[2 * i1], ci = w[2 * i1 + 1];
+        double tr, ti; ac_twiddle(pos, h, tr, ti);
+        const double dr = ar - cr, di = ai - ci;
+        w[2 * i0] = ar + cr; w[2 * i0 + 1] = ai + ci;
+        w[2 * i1] = dr * tr - di * ti; w[2 * i1 + 1] = dr * ti + di * tr;
+    }
+}
+GDG_DEVI void ac_dit_body(double *w, int h, int b)
+{
+    {
+        const int grp = b / h, pos = b - grp * h, i0 = grp * 2 * h + pos, i1 = i0 + h;
+        const double ar = w[2 * i0], ai = w[2 * i0 + 1], cr = w[2 * i1], ci = w[2 * i1 + 1];
+        double tr, ti; ac_twiddle(pos, h, tr, ti); ti = -ti;
+        const double xr = cr * tr - ci * ti, xi = cr * ti + ci * tr;
+        w[2 * i0] = ar + xr; w[2 * i0 + 1] = ai + xi;
+        w[2 * i1] = ar - xr; w[2 * i1 + 1] = ai - xi;
+    }
+}
+/* split -> |X|^2 (tuner.go:437-440) -> inverse split, on bit-reversed storage */
+GDG_DEVI void ac_power_body(double *w, int M, int logM, int k)
+{
+    if (k == 0) {
+        const double zr = w[0], zi = w[1];
+        const double x0 = zr + zi, xm = zr - zi;
+        const double y0 = x0 * x0, ym = xm * xm;
+        w[0] = 0.5 * (y0 + ym); w[1] = 0.5 * (y0 - ym);
+        return;
+    }
+    const int k2 = M - k;
+    const int p1 = brev(k, logM), p2 = brev(k2, logM);
+    const double ar = w[2 * p1], ai = w[2 * p1 + 1], br = w[2 * p2], bi = w[2 * p2 + 1];
+    double s, c;
+    GDG_SINCOSPI(-(double)k / (double)M, &s, &c);               /* W_F^k, F = 2M */
+    /* X[k] = 0.5((A + conj B) - jW (A - conj B)) */
+    const double sr = ar + br, si = ai - bi, dr = ar - br, di = ai + bi;
+    const double jr = -s, ji = c;                           /* jW */
+    const double tr = jr * dr - ji * di, ti = jr * di + ji * dr;
+    const double xr = 0.5 * (sr - tr), xi = 0.5 * (si - ti);
+    const double pa = xr * xr + xi * xi;                    /* |X[k]|^2 ( = |X[M-k]|^2 by symmetry of a real input) */
+    /* X[M-k] */
+    const double s2r = br + ar, s2i = bi - ai, d2r = br - ar, d2i = bi + ai;
+    const double j2r = jr, j2i = -ji;                       /* conj(jW) */
+    const double t2r = j2r * d2r - j2i * d2i, t2i = j2r * d2i + j2i * d2r;
+    const double x2r = 0.5 * (s2r - t2r), x2i = 0.5 * (s2i - t2i);
+    const double pb = x2r * x2r + x2i * x2i;
+    /* Z'[k] = 0.5((Ya + conj Yb) + j (Ya - conj Yb) conj(W)) with real Ya = pa, Yb = pb */
+    const double er = pa + pb, od = pa - pb;                /* even real, odd real */
+    /* o = od * conj(W) = od*(c - j s) ; j*o = od*(s + j c) */
+    w[2 * p1] = 0.5 * (er + od * s); w[2 * p1 + 1] = 0.5 * (od * c);
+    if (p2 != p1) {
+        /* roles swapped: W_F^{M-k} = (-c, s); conj = (-c, -s); o2 = -od * (-c - j s) = od*(c + j s); j*o2 = od*(-s + j c) */
+        w[2 * p2] = 0.5 * (er - od * s); w[2 * p2 + 1] = 0.5 * (od * c);
+    }
+}
+
+#endif

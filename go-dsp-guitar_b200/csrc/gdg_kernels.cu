@@ -1,0 +1,196 @@
+/*
+ * gdg_kernels.cu - CUDA backend (sm_100a) of libgdg: kernel wrappers around the
+ * CTA-cooperative stages (gdg_interp.cuh) and the device plumbing the host
+ * runtime needs (gdg_backend.h).  There is no CPU path in this file: if no CUDA
+ * device is usable, gdgb_init() fails and with it every constructor of the ABI.
+ */
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "gdg_backend.h"
+#include "gdg_interp.cuh"
+
+static thread_local std::string t_err;
+static int g_device = -1, g_sms = 0;
+static cudaStream_t g_stream = nullptr;
+static double *g_d_tw = nullptr;
+static std::atomic<uint64_t> g_launches{0};
+
+static int cu_fail(const char *what, cudaError_t e)
+{
+    t_err = std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
+    return -1;
+}
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cu_fail(#call, e_); } while (0)
+
+/* ---- kernels ------------------------------------------------------------------- */
+__global__ void __launch_bounds__(GDG_NT, 1)
+k_chain(const gdg_chain_desc *const *descs, const double *in, double *out, long stride, int n, const double *tw)
+{
+    extern __shared__ __align__(16) double smem[];
+    const int c = blockIdx.x;
+    const gdg_chain_desc *cd = descs[c];
+    const double *src = in + (long)c * stride;
+    double *dst = out + (long)c * stride;
+    if (cd == nullptr) {                                   /* no segment in this round: pass through */
+        if (src != dst) for (int k = threadIdx.x; k < n; k += GDG_NT) dst[k] = src[k];
+        return;
+    }
+    run_chain(smem, cd, src, dst, n, tw);
+}
+
+__global__ void k_spat(const gdg_spat_channel *ch, int C, const double *in, long stride, const double *hist, int hs,
+                       const double *aux, double *outL, double *outR, int n, int accumulate)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) spat_frame(ch, C, in, stride, hist, hs, aux, outL, outR, j, accumulate);
+}
+/* history <- last hs samples of (history ++ block): spatializer.go:316-331 */
+__global__ void k_spat_push(int C, const double *in, long stride, const double *hist_in, double *hist_out, int hs, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = blockIdx.y;
+    if (i < hs && c < C) {
+        const long src = (long)i + n - hs;                 /* index into the block; negative -> old history */
+        hist_out[(long)c * hs + i] = src >= 0 ? in[(long)c * stride + src] : hist_in[(long)c * hs + i + n];
+    }
+}
+
+/* --- tuner autocorrelation: real FFT of size F through a complex FFT of size M = F/2 in global memory --- */
+__global__ void k_ac_load(const double *ring, int n_ring, int pos, double *w, int F)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < F) ac_load_body(ring, n_ring, pos, w, i);
+}
+__global__ void k_ac_dif(double *w, int M, int h)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < M / 2) ac_dif_body(w, h, b);
+}
+__global__ void k_ac_dit(double *w, int M, int h)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < M / 2) ac_dit_body(w, h, b);
+}
+__global__ void k_ac_power(double *w, int M, int logM)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k <= M / 2) ac_power_body(w, M, logM, k);
+}
+__global__ void k_scale(double *w, int n, double f)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) w[i] *= f;
+}
+
+/* ---- backend API ---------------------------------------------------------------- */
+const char *gdgb_error(void) { return t_err.c_str(); }
+const char *gdgb_name(void) { return "cuda:sm_100a"; }
+int gdgb_device(void) { return g_device; }
+int gdgb_sm_count(void) { return g_sms; }
+void *gdgb_stream(void) { return (void *)g_stream; }
+uint64_t gdgb_launch_count(void) { return g_launches.load(); }
+
+int gdgb_init(int device)
+{
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess) return cu_fail("cudaGetDeviceCount", e);
+    if (count == 0) { t_err = "no CUDA device"; return -1; }
+    if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) device = 0; }
+    if (device >= count) { t_err = "device index out of range"; return -1; }
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) { t_err = std::string("device '") + prop.name + "' is not a Blackwell (sm_100a) GPU"; return -1; }
+    g_device = device; g_sms = prop.multiProcessorCount;
+    CU(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+    CU(cudaFuncSetAttribute(k_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, GDG_SMEM_BYTES));
+    return 0;
+}
+
+void *gdgb_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (bytes == 0) bytes = 8;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) { cu_fail("cudaMalloc", e); return nullptr; }
+    e = cudaMemsetAsync(p, 0, bytes, g_stream);
+    if (e != cudaSuccess) { cu_fail("cudaMemsetAsync", e); cudaFree(p); return nullptr; }
+    return p;
+}
+void gdgb_free(void *p) { if (p) cudaFree(p); }
+int gdgb_zero(void *p, size_t bytes) { CU(cudaMemsetAsync(p, 0, bytes, g_stream)); return 0; }
+int gdgb_upload(void *dst, const void *src, size_t bytes) { if (bytes) CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, g_stream)); return 0; }
+int gdgb_download(void *dst, const void *src, size_t bytes)
+{
+    if (bytes) CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, g_stream));
+    CU(cudaStreamSynchronize(g_stream));
+    return 0;
+}
+int gdgb_copy(void *dst, const void *src, size_t bytes) { if (bytes) CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, g_stream)); return 0; }
+int gdgb_sync(void) { if (g_stream) CU(cudaStreamSynchronize(g_stream)); return 0; }
+void *gdgb_pinned_alloc(size_t bytes) { void *p = nullptr; if (cudaMallocHost(&p, bytes ? bytes : 8) != cudaSuccess) return nullptr; return p; }
+void gdgb_pinned_free(void *p) { if (p) cudaFreeHost(p); }
+int gdgb_is_pinned(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+int gdgb_set_tables(const double *aa2, const double *aa4, const double *lz2, const double *lz4, const double *tw)
+{
+    CU(cudaMemcpyToSymbol(c_aa2, aa2, sizeof(double) * 80));
+    CU(cudaMemcpyToSymbol(c_aa4, aa4, sizeof(double) * 160));
+    CU(cudaMemcpyToSymbol(c_lz2, lz2, sizeof(double) * 6));
+    CU(cudaMemcpyToSymbol(c_lz4, lz4, sizeof(double) * 18));
+    if (!g_d_tw) CU(cudaMalloc((void **)&g_d_tw, sizeof(double) * GDG_MAX_FFT));
+    CU(cudaMemcpy(g_d_tw, tw, sizeof(double) * GDG_MAX_FFT, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int gdgb_launch_chains(const gdg_chain_desc *const *d_descs, int channels, const double *d_in, double *d_out,
+                       long stride, int n, void *stream)
+{
+    k_chain<<<channels, GDG_NT, GDG_SMEM_BYTES, (cudaStream_t)stream>>>(d_descs, d_in, d_out, stride, n, g_d_tw);
+    g_launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int gdgb_launch_spatializer(const gdg_spat_channel *d_ch, int channels, const double *d_in, long stride,
+                            const double *d_hist_in, double *d_hist_out, int hs, const double *d_aux,
+                            double *d_outL, double *d_outR, int n, int accumulate, void *stream)
+{
+    cudaStream_t s = (cudaStream_t)stream;
+    k_spat<<<(n + 255) / 256, 256, 0, s>>>(d_ch, channels, d_in, stride, d_hist_in, hs, d_aux, d_outL, d_outR, n, accumulate);
+    g_launches++;
+    CU(cudaGetLastError());
+    if (channels > 0 && hs > 0) {
+        dim3 grid((hs + 127) / 128, channels);
+        k_spat_push<<<grid, 128, 0, s>>>(channels, d_in, stride, d_hist_in, d_hist_out, hs, n);
+        g_launches++;
+        CU(cudaGetLastError());
+    }
+    return 0;
+}
+
+int gdgb_autocorrelate(const double *d_ring, int n_ring, int pos, double *d_work, int F, void *stream)
+{
+    cudaStream_t s = (cudaStream_t)stream;
+    const int M = F / 2;
+    int logM = 0;
+    while ((1 << logM) < M) logM++;
+    k_ac_load<<<(F + 255) / 256, 256, 0, s>>>(d_ring, n_ring, pos, d_work, F); g_launches++;
+    for (int h = M / 2; h >= 1; h >>= 1) { k_ac_dif<<<(M / 2 + 255) / 256, 256, 0, s>>>(d_work, M, h); g_launches++; }
+    k_ac_power<<<(M / 2 + 1 + 255) / 256, 256, 0, s>>>(d_work, M, logM); g_launches++;
+    for (int h = 1; h <= M / 2; h <<= 1) { k_ac_dit<<<(M / 2 + 255) / 256, 256, 0, s>>>(d_work, M, h); g_launches++; }
+    k_scale<<<(F + 255) / 256, 256, 0, s>>>(d_work, F, 1.0 / (double)M); g_launches++;
+    CU(cudaGetLastError());
+    return 0;
+}

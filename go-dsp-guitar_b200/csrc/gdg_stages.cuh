@@ -1,0 +1,728 @@
+/*
+ * gdg_stages.cuh - CTA-cooperative float64 "stages": one per effects unit.
+ *
+ * Execution model.  One CTA (GDG_NT threads) owns one channel's audio block
+ * (n <= 8192 samples) which stays in shared memory across the whole fused chain
+ * segment.  Every stage is a sequence of PHASES; a phase is a pure function of
+ * (thread id, shared/global memory) and phases are separated by CTA barriers.
+ * Thread-private values never live across a phase boundary - they go through
+ * shared memory - so the very same source also compiles as plain C++ (macro
+ * GDG_HOST_EMU: a phase becomes a loop over thread ids).  That build exists only
+ * for tests/ (CPU-side check of the parallel formulation against the oracle);
+ * the product library contains the CUDA build alone.
+ *
+ * How the reference's strictly sequential per-sample loops become parallel:
+ *   - one-pole RC sections and "level" followers  v += (x - v) k  are affine
+ *     recurrences: each thread owns a contiguous chunk, computes the chunk's
+ *     zero-state response, a block-level scan yields every chunk's carry-in, and
+ *     the chunk is then replayed with the reference's own update formula;
+ *   - "envelope" followers  e = max(|x|, d e)  are max-plus recurrences: same scheme;
+ *   - threshold state machines (noise gate, octaver register, tremolo) become
+ *     "last event" / counting scans or closed forms in the sample index;
+ *   - delay-line units are gathers from [history ring | block];
+ *   - the reverb all-passes (lag D-1 recurrences) run in rounds of D-1 samples;
+ *   - oversampled nonlinear units run tile-wise: polyphase Lanczos-3 up-sampling
+ *     (constant weights), nonlinearity, direct polyphase FIR decimation that only
+ *     evaluates the retained every-f-th output (+ clamp, -0.5 dB);
+ *   - power_amp is FFT overlap-add convolution with the whole FFT in shared memory
+ *     (real transform through a half-size complex transform, DIF forward / DIT
+ *     inverse so no bit-reversal pass is needed).
+ *
+ * Reference citations are /root/reference paths (file:line).
+ */
+#ifndef GDG_STAGES_CUH
+#define GDG_STAGES_CUH
+
+#include <math.h>
+#include <stdint.h>
+#include "gdg_device.h"
+
+#if defined(__CUDACC__) && !defined(GDG_HOST_EMU)
+#define GDG_DEV __device__ __noinline__
+#define GDG_DEVI __device__ __forceinline__
+#define GDG_THREADS_BEGIN { const int tid = (int)threadIdx.x;
+#define GDG_THREADS_END } __syncthreads();
+#define GDG_CONST __constant__
+#define GDG_LDG(p) __ldg(p)
+#else
+#define GDG_DEV static
+#define GDG_DEVI static inline
+#define GDG_THREADS_BEGIN for (int tid = 0; tid < GDG_NT; ++tid) {
+#define GDG_THREADS_END }
+#define GDG_CONST static
+#define GDG_LDG(p) (*(p))
+#endif
+
+#define GDG_PI 3.14159265358979323846
+#define GDG_TWO_PI (2.0 * GDG_PI)
+#define GDG_NSEG (GDG_NT / 32)
+
+/* ---- constant tables (filled by the host at start-up) --------------------- */
+GDG_CONST double c_aa2[80];            /* 77-tap x2 anti-aliasing FIR (oversampling.go:239-317) */
+GDG_CONST double c_aa4[160];           /* 155-tap x4 anti-aliasing FIR (oversampling.go:357-513) */
+GDG_CONST double c_lz2[1][6];          /* Lanczos-3 weights of the fractional phases, x2 (resample.go:10-66) */
+GDG_CONST double c_lz4[3][6];          /* ... x4: phase p/4, taps q: L(2 - q + p/4) */
+
+/* ---- execution context: shared-memory carve-up ------------------------------ */
+struct gdg_ctx {
+    double *R;        /* 2*GDG_MAX_N doubles: bufA = R, bufB = R + GDG_MAX_N; also the FFT workspace */
+    double *cur;      /* current block (swizzled layout), R or R + GDG_MAX_N */
+    double *alt;      /* the other half */
+    double *S;        /* GDG_MAX_N doubles scratch */
+    double *scanB;    /* GDG_SCAN_LANES * GDG_NT */
+    double *scanA;    /* GDG_NT */
+    double *seg;      /* 3 * GDG_SCAN_LANES * GDG_NSEG */
+    double *misc;     /* 64 */
+    int n;
+};
+
+/* XOR swizzle of the block buffers: a thread that walks its own 16-sample chunk
+ * (stride-16 across the warp) and a warp that reads 32 consecutive samples are
+ * both bank-conflict-free. */
+GDG_DEVI int sw(int i) { return i ^ ((i >> 4) & 15); }
+
+GDG_DEVI double clamp1(double x) { return x < -1.0 ? -1.0 : (x > 1.0 ? 1.0 : x); }
+GDG_DEVI int imin(int a, int b) { return a < b ? a : b; }
+GDG_DEVI int imax(int a, int b) { return a > b ? a : b; }
+GDG_DEVI long long st_geti(const double *st, int k) { return ((const long long *)st)[k]; }
+GDG_DEVI void st_seti(double *st, int k, long long v) { ((long long *)st)[k] = v; }
+GDG_DEVI int chunk_len(int n) { return (n + GDG_NT - 1) / GDG_NT; }
+GDG_DEVI void swap_bufs(gdg_ctx &cx) { double *t = cx.cur; cx.cur = cx.alt; cx.alt = t; }
+
+GDG_DEVI double pow_int(double a, int k)
+{
+    double r = 1.0;
+    for (int i = 0; i < k; i++) r *= a;
+    return r;
+}
+
+/* compressor.go:44-58 (shared by autowah/autoyoy/octaver/fuzz) */
+GDG_DEVI double follow_step(int mode, double env, double abs_s, double d_inv, double d)
+{
+    if (mode == GDG_FOLLOW_ENVELOPE) { env *= d_inv; if (abs_s > env) env = abs_s; return env; }
+    if (mode == GDG_FOLLOW_LEVEL) { double diff = abs_s - env; return env + diff * d; }
+    return 1.0;
+}
+GDG_DEVI double follow_A(int mode, double d_inv, double d)
+{
+    return mode == GDG_FOLLOW_ENVELOPE ? d_inv : (mode == GDG_FOLLOW_LEVEL ? 1.0 - d : 0.0);
+}
+
+/* --------------------------------------------------------------------------
+ * Block scan of per-chunk recurrence summaries.
+ *   chunk t maps carry c to   affine: A_t c + B_t     maxplus: max(A_t c, B_t)
+ * In : scanB[lane*NT + t] = B_t (zero-state response of chunk t),
+ *      A_t = a_full for complete chunks, a_last for the trailing partial chunk,
+ *            or scanA[t] when vary != 0 (lane 0 only).
+ * Out: scanB[lane*NT + t] = carry entering chunk t (chunk 0 gets init[lane]).
+ * Two-level serial scan (32-chunk segments): three phases.
+ * -------------------------------------------------------------------------- */
+struct gdg_scan_par { double a_full[GDG_SCAN_LANES], a_last[GDG_SCAN_LANES], init[GDG_SCAN_LANES]; };
+
+GDG_DEVI double scan_apply(int maxplus, double a, double c, double b)
+{
+    double v = a * c;
+    if (maxplus) return v > b ? v : b;
+    return v + b;
+}
+
+GDG_DEV void block_scan(gdg_ctx &cx, int lanes, int maxplus, int vary, const gdg_scan_par &sp, int n, int S)
+{
+    const int nfull = n / S;                 /* complete chunks */
+    const int nch = (n + S - 1) / S;         /* chunks in use   */
+    double *segA = cx.seg, *segB = cx.seg + GDG_SCAN_LANES * GDG_NSEG, *segV = cx.seg + 2 * GDG_SCAN_LANES * GDG_NSEG;
+    GDG_THREADS_BEGIN
+        if (tid < lanes * GDG_NSEG) {
+            const int lane = tid / GDG_NSEG, g = tid % GDG_NSEG;
+            double accA = 1.0, accB = 0.0;
+            for (int k = 0; k < 32; k++) {
+                const int idx = g * 32 + k;
+                if (idx < nch) {
+                    const double a = vary ? cx.scanA[idx] : (idx < nfull ? sp.a_full[lane] : sp.a_last[lane]);
+                    const double b = cx.scanB[lane * GDG_NT + idx];
+                    accB = scan_apply(maxplus, a, accB, b);
+                    accA *= a;
+                }
+            }
+            segA[lane * GDG_NSEG + g] = accA;
+            segB[lane * GDG_NSEG + g] = accB;
+        }
+    GDG_THREADS_END
+    GDG_THREADS_BEGIN
+        if (tid < lanes) {
+            double v = sp.init[tid];
+            for (int g = 0; g < GDG_NSEG; g++) {
+                segV[tid * GDG_NSEG + g] = v;
+                v = scan_apply(maxplus, segA[tid * GDG_NSEG + g], v, segB[tid * GDG_NSEG + g]);
+            }
+        }
+    GDG_THREADS_END
+    GDG_THREADS_BEGIN
+        if (tid < lanes * GDG_NSEG) {
+            const int lane = tid / GDG_NSEG, g = tid % GDG_NSEG;
+            double c = segV[lane * GDG_NSEG + g];
+            for (int k = 0; k < 32; k++) {
+                const int idx = g * 32 + k;
+                if (idx < nch) {
+                    const double a = vary ? cx.scanA[idx] : (idx < nfull ? sp.a_full[lane] : sp.a_last[lane]);
+                    const double b = cx.scanB[lane * GDG_NT + idx];
+                    cx.scanB[lane * GDG_NT + idx] = c;
+                    c = scan_apply(maxplus, a, c, b);
+                }
+            }
+        }
+    GDG_THREADS_END
+}
+
+GDG_DEVI void scan_par_const(gdg_scan_par &sp, int lane, double a_step, int n, int S, double init)
+{
+    sp.a_full[lane] = pow_int(a_step, S);
+    sp.a_last[lane] = pow_int(a_step, n % S);
+    sp.init[lane] = init;
+}
+
+/* History rings of the delay-type units.  The reference keeps the last `hs`
+ * inputs oldest-first and memmoves them every block (e.g. chorus.go:119-129);
+ * here they are rings: logical index q (0 = oldest) lives at (pos + q) % hs. */
+GDG_DEVI double ring_get(const double *ring, int hs, int pos, int q)
+{
+    int p = pos + q;
+    if (p >= hs) p -= hs;
+    return ring[p];
+}
+/* x[idx] for idx in [-hs, n): block sample or history */
+GDG_DEVI double hist_or_block(const double *blk, const double *ring, int hs, int pos, int idx)
+{
+    return idx >= 0 ? blk[sw(idx)] : ring_get(ring, hs, pos, hs + idx);
+}
+/* push the block into the ring (one phase), returns nothing; new pos written by thread 0 */
+GDG_DEV void ring_push(gdg_ctx &cx, const double *blk, double *st, int hs)
+{
+    const int n = cx.n;
+    double *ring = st + GDG_RING_ST_DATA;
+    GDG_THREADS_BEGIN
+        const int pos = (int)st_geti(st, GDG_RING_ST_POS);
+        if (hs > 0) {
+            if (n >= hs) {
+                for (int q = tid; q < hs; q += GDG_NT) ring[q] = blk[sw(n - hs + q)];
+            } else {
+                for (int k = tid; k < n; k += GDG_NT) { int p = pos + k; if (p >= hs) p -= hs; ring[p] = blk[sw(k)]; }
+            }
+        }
+    GDG_THREADS_END
+    GDG_THREADS_BEGIN
+        if (tid == 0 && hs > 0) {
+            const int pos = (int)st_geti(st, GDG_RING_ST_POS);
+            st_seti(st, GDG_RING_ST_POS, n >= hs ? 0 : (pos + n) % hs);
+        }
+    GDG_THREADS_END
+}
+
+/* ==========================================================================
+ * noise_gate  (effects/noisegate.go:19-96)
+ *   i[0] bypass-like flag (threshold_open < threshold_close), i[1] holdSamples
+ *   p[0] facOpen p[1] facClose        st: [0] gateOpen (i64) [1] onHoldSince (i64)
+ * "since" at sample k = k - (index of the last sample above the close threshold)
+ * -> max-scan; gate = type of the last open/close event -> last-event scan.
+ * ========================================================================== */
+GDG_DEV void stage_noisegate(gdg_ctx &cx, const gdg_unit_desc &d)
+{
+    const int n = cx.n, S = chunk_len(n);
+    double *x = cx.cur, *st = d.st;
+    if (d.i[0]) {                                   /* levelOpen < levelClose: copy, force open */
+        GDG_THREADS_BEGIN
+            if (tid == 0) { st_seti(st, 0, 1); st_seti(st, 1, 0); }
+        GDG_THREADS_END
+        return;
+    }
+    const double facOpen = d.p[0], facClose = d.p[1];
+    const unsigned long long hold = (unsigned long long)(unsigned int)d.i[1];
+    const unsigned long long since0 = (unsigned long long)st_geti(st, 1);
+    const int open0 = (int)st_geti(st, 0);
+    /* P1: last close-threshold crossing per chunk (as index+1, 0 = none) */
+    GDG_THREADS_BEGIN
+        const int k0 = tid * S, k1 = imin(n, k0 + S);
+        double last = 0.0;
+        for (int k = k0; k < k1; k++) if (fabs(x[sw(k)]) > facClose) last = (double)(k + 1);
+        cx.scanB[tid] = last;
+    GDG_THREADS_END
+    { gdg_scan_par sp; sp.a_full[0] = 1.0; sp.a_last[0] = 1.0; sp.init[0] = 0.0; block_scan(cx, 1, 1, 0, sp, n, S); }
+    /* P2: gate events per chunk: 0 none, 1 open, 2 close (close wins on the same sample) -> last event */
+    GDG_THREADS_BEGIN
+        const int k0 = tid * S, k1 = imin(n, k0 + S);
+        long long lc = (long long)cx.scanB[tid];            /* last crossing index+1 before the chunk */
+        double ev = 0.0;
+        for (int k = k0; k < k1; k++) {
+            const double amp = fabs(x[sw(k)]);
+            if (amp > facClose) lc = k + 1;
+            unsigned long long since = lc > 0 ? (unsigned long long)(k + 1 - lc) : since0 + (unsigned long long)k;
+            if (since > 0xffffffffull) since = 0xffffffffull;
+            if (amp > facOpen) ev = 1.0;
+            if (since >= hold) ev = 2.0;
+        }
+        cx.scanB[GDG_NT + tid] = ev;                          /* lane 1 */
+    GDG_THREADS_END
+    /* last-event scan over chunks: serial two-level is overkill - it is "last nonzero": use maxplus on (t+1)*4+ev */
+    GDG_THREADS_BEGIN
+        const double ev = cx.scanB[GDG_NT + tid];
+        cx.scanB[2 * GDG_NT + tid] = ev > 0.0 ? (double)((tid + 1) * 4) + ev : 0.0;   /* lane 2 */
+    GDG_THREADS_END
+    {
+        /* scan lane 2 with max: shift arrays so block_scan (lane-major) sees it as lane 0 of a 1-lane scan */
+        GDG_THREADS_BEGIN
+            cx.scanA[tid] = cx.scanB[tid];                    /* keep the close-crossing carry */
+            cx.scanB[tid] = cx.scanB[2 * GDG_NT + tid];
+        GDG_THREADS_END
+        gdg_scan_par sp; sp.a_full[0] = 1.0; sp.a_last[0] = 1.0; sp.init[0] = 0.0;
+        block_scan(cx, 1, 1, 0, sp, n, S);
+    }
+    /* P3: replay */
+    GDG_THREADS_BEGIN
+        const int k0 = tid * S, k1 = imin(n, k0 + S);
+        long long lc = (long long)cx.scanA[tid];
+        const long long code = (long long)cx.scanB[tid];
+        int open = code > 0 ? ((code & 3) == 1) : open0;
+        unsigned long long since = 0;
+        for (int k = k0; k < k1; k++) {
+            const double s = x[sw(k)];
+            const double amp = fabs(s);
+            if (amp > facClose) lc = k + 1;
+            since = lc > 0 ? (unsigned long long)(k + 1 - lc) : since0 + (unsigned long long)k;
+            if (since > 0xffffffffull) since = 0xffffffffull;
+            if (amp > facOpen) open = 1;
+            if (since >= hold) open = 0;
+            x[sw(k)] = (open ? 1.0 : 0.0) * s;
+        }
+        if (k0 < n && k1 == n) {
+            if (since < 0xffffffffull) since++;
+            st_seti(st, 0, open); st_seti(st, 1, (long long)since);
+        }
+    GDG_THREADS_END
+}
+
+/* ==========================================================================
+ * compressor  (effects/compressor.go:18-84)
+ *   i[0] follow mode; p[0] dInv p[1] d p[2] targetFac p[3] limitFac; st[0] envelope
+ * ========================================================================== */
+GDG_DEV void stage_compressor(gdg_ctx &cx, const gdg_unit_desc &d)
+{
+    const int n = cx.n, S = chunk_len(n), mode = d.i[0];
+    const double dinv = d.p[0], dd = d.p[1], target = d.p[2], limit = d.p[3];
+    double *x = cx.cur, *st = d.st;
+    GDG_THREADS_BEGIN
+        const int k0 = tid * S, k1 = imin(n, k0 + S);
+        double e = 0.0;
+        for (int k = k0; k < k1; k++) e = follow_step(mode, e, fabs(x[sw(k)]), dinv, dd);
+        cx.scanB[tid] = e;
+    GDG_THREADS_END
+    { gdg_scan_par sp; scan_par_const(sp, 0, follow_A(mode, dinv, dd), n, S, st[0]); block_scan(cx, 1, mode == GDG_FOLLOW_ENVELOPE, 0, sp, n, S); }
+    GDG_THREADS_BEGIN
+        const int k0 = tid * S, k1 = imin(n, k0 + S);
+        double e = cx.scanB[tid];
+        for (int k = k0; k < k1; k++) {
+            const double s = x[sw(k)];
+            e = follow_step(mode, e, fabs(s), dinv, dd);
+            double gain = target / e;
+            if (gain > limit) gain = limit;
+            x[sw(k)] = clamp1(gain * s);
+        }
+        if (k0 < n && k1 == n) st[0] = e;
+    GDG_THREADS_END
+}
+
+/* ==========================================================================
+ * tone_stack  (effects/tonestack.go:19-100): 4 bands HP(f_j) -> LP(f_{j+1}),
+ * LP output taken BEFORE its update, weighted sum, clamp.
+ *   p[0..3] HP k, p[4..7] LP k, p[8..11] band factors; st[0..3] hcv, st[4..7] lcv
+ * ========================================================================== */
+GDG_DEV void stage_tonestack(gdg_ctx &cx, const gdg_unit_desc &d)
+{
+    const int n = cx.n, S = chunk_len(n);
+    double *x = cx.cur, *st = d.st;
+    /* P1: HP zero-state responses (4 lanes) */
+    GDG_THREADS_BEGIN
+        const int k0 = tid * S, k1 = imin(n, k0 + S);
+        double h[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int k = k0; k < k1; k++) {
+            const double s = x[sw(k)];
+            for (int j = 0; j < 4; j++) h[j] += (s - h[j]) * d.p[j];
+        }
+        for (int j = 0; j < 4; j++) cx.scanB[j * GDG_NT + tid] = h[j];
+    GDG_THREADS_END
+    { gdg_scan_par sp; for (int j = 0; j < 4; j++) scan_par_const(sp, j, 1.0 - d.p[j], n, S, st[j]); block_scan(cx, 4, 0, 0, sp, n, S); }
+    /* P2: replay HP, LP zero-state responses; keep the HP carries in S[0..4*NT) */
+    GDG_THREADS_BEGIN
+        const int k0 = tid * S, k1 = imin(n, k0 + S);
+        double h[4], l[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int j = 0; j < 4; j++) { h[j] = cx.scanB[j * GDG_NT + tid]; cx.S[j * GDG_NT + tid] = h[j]; }
+        for (int k = k0; k < k1; k++) {
+            const double s = x[sw(k)];
+            for (int j = 0; j < 4; j++) {
+                double diff = s - h[j];
+                h[j] += diff * d.p[j];
+                diff -= l[j];
+                l[j] += diff * d.p[4 + j];
+            }
+        }
+        for (int j = 0; j < 4; j++) cx.scanB[j * GDG_NT + tid] = l[j];
+    GDG_THREADS_END
+    { gdg_scan_par sp; for (int j = 0; j < 4; j++) scan_par_const(sp, j, 1.0 - d.p[4 + j], n, S, st[4 + j]); block_scan(cx, 4, 0, 0, sp, n, S); }
+    /* P3: replay both, emit */
+    GDG_THREADS_BEGIN
+        const int k0 = tid * S, k1 = imin(n, k0 + S);
+        double h[4], l[4];
+        for (int j = 0; j < 4; j++) { h[j] = cx.S[j * GDG_NT + tid]; l[j] = cx.scanB[j * GDG_NT + tid]; }
+        for (int k = k0; k < k1; k++) {
+            const double s = x[sw(k)];
+            double sum = 0.0;
+            for (int j = 0; j < 4; j++) {
+                double diff = s - h[j];
+                h[j] += diff * d.p[j];
+                diff -= l[j];
+                const double pre = l[j];
+                l[j] += diff * d.p[4 + j];
+                sum += d.p[8 + j] * pre;
+            }
+            x[sw(k)] = clamp1(sum);
+        }
+        if (k0 < n && k1 == n) for (int j = 0; j < 4; j++) { st[j] = h[j]; st[4 + j] = l[j]; }
+    GDG_THREADS_END
+}
+
+/* ==========================================================================
+ * cabinet  (effects/cabinet.go:27-162): 3 cascaded one-pole high-passes
+ * (out = x - v_old) then 4 cascaded low-passes (out = v_old), clamp.
+ *   p[0..6] k of the 7 sections; st[0..6] cap voltages
+ * The replay of section s also accumulates the zero-state response of section s+1.
+ * ========================================================================== */
+GDG_DEVI double onepole_out(int highpass, double xin, double &v, double k)
+{
+    const double diff = xin - v;
+    const double out = highpass ? diff : v;
+    v += diff * k;
+    return out;
+}
+
+GDG_DEV void stage_cascade(gdg_ctx &cx, const gdg_unit_desc &d, int nsec, int nhp)
+{
+    const int n = cx.n, S = chunk_len(n);
+    double *x = cx.cur, *st = d.st;
+    GDG_THREADS_BEGIN
+        const int k0 = tid * S, k1 = imin(n, k0 + S);
+        double v = 0.0;
+        for (int k = k0; k < k1; k++) v += (x[sw(k)] - v) * d.p[0];
+        cx.scanB[tid] = v;
+    GDG_THREADS_END
+    for (int s = 0; s < nsec; s++) {
+        { gdg_scan_par sp; scan_par_const(sp, 0, 1.0 - d.p[s], n, S, st[s]); block_scan(cx, 1, 0, 0, sp, n, S); }
+        const int last = (s == nsec - 1);
+        GDG_THREADS_BEGIN
+            const int k0 = tid * S, k1 = imin(n, k0 + S);
+            double v = cx.scanB[tid], w = 0.0;
+            const double kk = d.p[s], kn = last ? 0.0 : d.p[s + 1];
+            for (int k = k0; k < k1; k++) {
+                double y = onepole_out(s < nhp, x[sw(k)], v, kk);
+                if (last) y = clamp1(y); else w += (y - w) * kn;
+                x[sw(k)] = y;
+            }
+            cx.scanB[tid] = w;
+            if (k0 < n && k1 == n) st[s] = v;
+        GDG_THREADS_END
+    }
+}
+
+/* ==========================================================================
+ * bandpass  (effects/bandpass.go:20-98): order/2 cascaded HP+LP pairs, the LP
+ * output (pre-update value) is clamped between pairs.
+ *   i[0] halfOrder; p[0] HP k, p[1] LP k; st[0..3] hcv, st[4..7] lcv
+ * ========================================================================== */
+GDG_DEV void stage_bandpass(gdg_ctx &cx, const gdg_unit_desc &d)
+{
+    const int n = cx.n, S = chunk_len(n), half = d.i[0];
+    const double ka = d.p[0], kb = d.p[1];
+    double *x = cx.cur, *st = d.st;
+    for (int j = 0; j < half; j++) {
+        GDG_THREADS_BEGIN
+            const int k0 = tid * S, k1 = imin(n, k0 + S);
+            double h = 0.0;
+            for (int k = k0; k < k1; k++) h += (x[sw(k)] - h) * ka;
+            cx.scanB[tid] = h;
+        GDG_THREADS_END
+        { gdg_scan_par sp; scan_par_const(sp, 0, 1.0 - ka, n, S, st[j]); block_scan(cx, 1, 0, 0, sp, n, S); }
+        GDG_THREADS_BEGIN
+            const int k0 = tid * S, k1 = imin(n, k0 + S);
+            double h = cx.scanB[tid], l = 0.0;
+            cx.scanA[tid] = h;
+            for (int k = k0; k < k1; k++) {
+                double diff = x[sw(k)] - h;
+                h += diff * ka;
+                diff -= l;
+                l += diff * kb;
+            }
+            cx.scanB[tid] = l;
+        GDG_THREADS_END
+        GDG_THREADS_BEGIN
+            cx.S[tid] = cx.scanA[tid];            /* HP carries survive the next scan (which may use scanA) */
+        GDG_THREADS_END
+        { gdg_scan_par sp; scan_par_const(sp, 0, 1.0 - kb, n, S, st[4 + j]); block_scan(cx, 1, 0, 0, sp, n, S); }
+        GDG_THREADS_BEGIN
+            const int k0 = tid * S, k1 = imin(n, k0 + S);
+            double h = cx.S[tid], l = cx.scanB[tid];
+            for (int k = k0; k < k1; k++) {
+                double diff = x[sw(k)] - h;
+                h += diff * ka;
+                diff -= l;
+                const double iv = l;
+                l += diff * kb;
+                x[sw(k)] = clamp1(iv);
+            }
+            if (k0 < n && k1 == n) { st[j] = h; st[4 + j] = l; }
+        GDG_THREADS_END
+    }
+}
+
+/* ==========================================================================
+ * pointwise closed-form units
+ * ========================================================================== */
+
+/* tremolo (effects/tremolo.go:15-65): two-state counter machine in closed form.
+ *   i[0] samplesAttenuated i[1] samplesUnattenuated (uint32 bit patterns); p[0] fac
+ *   st[0] attenuated (i64) st[1] inStateSince (i64) */
+GDG_DEVI void tremolo_at(long long i, int att0, unsigned long long s0, unsigned long long lenA, unsigned long long lenU,
+                         int &att, unsigned long long &since)
+{
+    const unsigned long long lenCur = att0 ? lenA : lenU;
+    const unsigned long long r0 = s0 >= lenCur ? 0ull : lenCur - s0;
+    if ((unsigned long long)i < r0) { att = att0; since = s0 + (unsigned long long)i; return; }
+    const unsigned long long dA = lenA > 1 ? lenA : 1, dU = lenU > 1 ? lenU : 1;
+    const unsigned long long j = (unsigned long long)i - r0;
+    const unsigned long long m = j % (dA + dU);
+    const unsigned long long dFirst = att0 ? dU : dA;   /* first state after the toggle is !att0 */
+    if (m < dFirst) { att = !att0; since = m; }
+    else { att = att0; since = m - dFirst; }
+}
+GDG_DEV void stage_tremolo(gdg_ctx &cx, const gdg_unit_desc &d)
+{
+    const int n = cx.n;
+    double *x = cx.cur, *st = d.st;
+    const unsigned long long lenA = (unsigned int)d.i[0], lenU = (unsigned int)d.i[1];
+    const double fac = d.p[0];
+    GDG_THREADS_BEGIN
+        const int att0 = (int)st_geti(st, 0);
+        const unsigned long long s0 = (unsigned long long)st_geti(st, 1) & 0xffffffffull;
+        for (int k = tid; k < n; k += GDG_NT) {
+            int att; unsigned long long since;
+            tremolo_at(k, att0, s0, lenA, lenU, att, since);
+            if (att) x[sw(k)] *= fac;
+        }
+    GDG_THREADS_END
+    GDG_THREADS_BEGIN
+        if (tid == 0 && n > 0) {
+            const int att0 = (int)st_geti(st, 0);
+            const unsigned long long s0 = (unsigned long long)st_geti(st, 1) & 0xffffffffull;
+            int att; unsigned long long since;
+            tremolo_at(n - 1, att0, s0, lenA, lenU, att, since);
+            st_seti(st, 0, att); st_seti(st, 1, (long long)((since + 1) & 0xffffffffull));
+        }
+    GDG_THREADS_END
+}
+
+/* ring_modulator (effects/ringmodulator.go:18-47): p[0] phaseFraction; st[0] phase */
+GDG_DEV void stage_ringmod(gdg_ctx &cx, const gdg_unit_desc &d)
+{
+    const int n = cx.n;
+    double *x = cx.cur, *st = d.st;
+    const double frac = d.p[0];
+    GDG_THREADS_BEGIN
+        const double phase = st[0];
+        for (int k = tid; k < n; k += GDG_NT) {
+            const double cp = fmod(phase + ((double)k * frac), GDG_TWO_PI);
+            x[sw(k)] = sin(cp) * x[sw(k)];
+        }
+    GDG_THREADS_END
+    GDG_THREADS_BEGIN
+        if (tid == 0) st[0] = fmod(st[0] + ((double)n * frac), GDG_TWO_PI);
+    GDG_THREADS_END
+}
+
+/* signal_generator (effects/signalgenerator.go:20-153)
+ *   i[0] type (0 sine 1 triangle 2 square 3 sawtooth 4 noise); p[0] facInput p[1] facSignal p[2] phaseIncrement
+ *   st[0] phase, st[1] LCG state x (random/random.go:23-55; a = 16807, m = 2^31 - 1) */
+GDG_DEVI unsigned long long lcg_pow(unsigned long long e)
+{
+    const unsigned long long m = 2147483647ull;
+    unsigned long long r = 1, b = 16807ull;
+    while (e) { if (e & 1) r = (r * b) % m; b = (b * b) % m; e >>= 1; }
+    return r;
+}
+GDG_DEV void stage_siggen(gdg_ctx &cx, const gdg_unit_desc &d)
+{
+    const int n = cx.n, S = chunk_len(n), type = d.i[0];
+    double *x = cx.cur, *st = d.st;
+    const double fin = d.p[0], fsig = d.p[1], inc = d.p[2];
+    if (type == 4) {
+        GDG_THREADS_BEGIN
+            const int k0 = tid * S, k1 = imin(n, k0 + S);
+            const unsigned long long m = 2147483647ull;
+            if (k0 < n) {
+                unsigned long long xs = ((unsigned long long)st_geti(st, 1) * lcg_pow((unsigned long long)k0)) % m;
+                for (int k = k0; k < k1; k++) {
+                    xs = (16807ull * xs) % m;
+                    const double r = (double)xs / (double)(m - 1);
+                    x[sw(k)] = (fin * x[sw(k)]) + (fsig * (1.0 - (2.0 * r)));
+                }
+                if (k1 == n) cx.misc[0] = (double)xs;
+            }
+        GDG_THREADS_END
+        GDG_THREADS_BEGIN
+            if (tid == 0 && n > 0) st_seti(st, 1, (long long)cx.misc[0]);
+        GDG_THREADS_END
+        return;
+    }
+    GDG_THREADS_BEGIN
+        const double phase = st[0];
+        const double two_over_pi = 2.0 / GDG_PI;
+        for (int k = tid; k < n; k += GDG_NT) {
+            const double cp = fmod(phase + ((double)k * inc), GDG_TWO_PI);
+            double sig;
+            if (type == 0) sig = sin(cp);
+            else if (type == 1) sig = cp < GDG_PI ? (two_over_pi * cp) - 1.0 : 3.0 - (two_over_pi * cp);
+            else if (type == 2) { const double v = GDG_PI - cp; sig = v < 0.0 ? -1.0 : (v > 0.0 ? 1.0 : 0.0); }
+            else { sig = cp / GDG_PI; if (cp > GDG_PI) sig -= 2.0; }
+            x[sw(k)] = (fin * x[sw(k)]) + (fsig * sig);
+        }
+    GDG_THREADS_END
+    GDG_THREADS_BEGIN
+        if (tid == 0) { double ph = st[0] + (double)n * inc; st[0] = fmod(ph, GDG_TWO_PI); }
+    GDG_THREADS_END
+}
+
+/* ==========================================================================
+ * delay-line gathers
+ * ========================================================================== */
+GDG_DEVI double frac_delay_read(const double *blk, const double *ring, int hs, int pos, int i, double ds)
+{
+    /* e.g. chorus.go:82-108: weights 1-(ds-floor) and 1-(ceil-ds) (sum to 2 when ds is integral) */
+    const double early = floor(ds), late = ceil(ds);
+    const double se = hist_or_block(blk, ring, hs, pos, i - (int)early);
+    const double sl = hist_or_block(blk, ring, hs, pos, i - (int)late);
+    const double we = 1.0 - (ds - early), wl = 1.0 - (late - ds);
+    return (we * se) + (wl * sl);
+}
+
+/* delay (effects/delay.go:17-91): i[0] delaySamples (= ring size); p[0] feedbackFac p[1] levelFac */
+GDG_DEV void stage_delay(gdg_ctx &cx, const gdg_unit_desc &d)
+{
+    const int n = cx.n, ds = d.i[0];
+    const double fb = d.p[0], lvl = d.p[1];
+    double *x = cx.cur, *y = cx.alt, *st = d.st;
+    GDG_THREADS_BEGIN
+        const int pos = (int)st_geti(st, GDG_RING_ST_POS);
+        const double *ring = st + GDG_RING_ST_DATA;
+        for (int k = tid; k < n; k += GDG_NT) {
+            const double dl = hist_or_block(x, ring, ds, pos, k - ds);
+            y[sw(k)] = clamp1(lvl * (x[sw(k)] + (fb * dl)));
+        }
+    GDG_THREADS_END
+    ring_push(cx, x, st, ds);
+    swap_bufs(cx);
+}
+
+/* chorus (effects/chorus.go:19-130): i[0] ring size; p[0] depth p[1] angularSpeed p[2] sampleRate
+ * st[0] previousPhase (advanced by the RING length per call, chorus.go:114-117) */
+GDG_DEV void stage_chorus(gdg_ctx &cx, const gdg_unit_desc &d)
+{
+    const int n = cx.n, hs = d.i[0];
+    const double depth = d.p[0], ang = d.p[1], sr = d.p[2];
+    double *x = cx.cur, *y = cx.alt, *st = d.st;
+    GDG_THREADS_BEGIN
+        const int pos = (int)st_geti(st, GDG_RING_ST_POS);
+        const double *ring = st + GDG_RING_ST_DATA;
+        const double prev = st[0];
+        for (int k = tid; k < n; k += GDG_NT) {
+            const double t = (double)k / sr;
+            const double zero_phase = fmod(prev + (ang * t), GDG_TWO_PI);
+            double eff = 0.0;
+            for (int j = 0; j < 5; j++) {
+                const double phase = fmod(zero_phase + ((0.4 * GDG_PI) * (double)j), GDG_TWO_PI);
+                const double offset = depth * sin(phase);
+                const double dsmp = (0.001 * (40.0 + offset)) * sr;
+                eff += 0.2 * frac_delay_read(x, ring, hs, pos, k, dsmp);
+            }
+            y[sw(k)] = (0.5 * x[sw(k)]) + (0.5 * eff);
+        }
+    GDG_THREADS_END
+    GDG_THREADS_BEGIN
+        if (tid == 0) st[0] = fmod(st[0] + (ang * ((double)hs / sr)), GDG_TWO_PI);
+    GDG_THREADS_END
+    ring_push(cx, x, st, hs);
+    swap_bufs(cx);
+}
+
+/* flanger / phaser (effects/flanger.go:19-117, phaser.go:19-125)
+ *   i[0] ring size; p[0] depth p[1] angularSpeed p[2] sampleRate p[3] 1/sampleRate p[4] dry weight p[5] wet weight */
+GDG_DEV void stage_flanger(gdg_ctx &cx, const gdg_unit_desc &d)
+{
+    const int n = cx.n, hs = d.i[0];
+    const double depth = d.p[0], ang = d.p[1], sr = d.p[2], sr_inv = d.p[3], wa = d.p[4], wb = d.p[5];
+    double *x = cx.cur, *y = cx.alt, *st = d.st;
+    GDG_THREADS_BEGIN
+        const int pos = (int)st_geti(st, GDG_RING_ST_POS);
+        const double *ring = st + GDG_RING_ST_DATA;
+        const double prev = st[0];
+        for (int k = tid; k < n; k += GDG_NT) {
+            const double t = (double)k * sr_inv;
+            const double phase = fmod(prev + (ang * t), GDG_TWO_PI);
+            const double offset = depth * sin(phase);
+            const double dsmp = (0.001 * (depth + offset)) * sr;
+            y[sw(k)] = (wa * x[sw(k)]) + (wb * frac_delay_read(x, ring, hs, pos, k, dsmp));
+        }
+    GDG_THREADS_END
+    GDG_THREADS_BEGIN
+        if (tid == 0) st[0] = fmod(st[0] + (ang * ((double)hs * sr_inv)), GDG_TWO_PI);
+    GDG_THREADS_END
+    ring_push(cx, x, st, hs);
+    swap_bufs(cx);
+}
+
+/* auto_yoy (effects/autoyoy.go:19-156)
+ *   i[0] ring size i[1] follow; p[0] dInv p[1] d p[2] levelA p[3] levelB p[4] depthA p[5] depthB p[6] slope p[7] sampleRate
+ *   st[0] envelope */
+GDG_DEV void stage_autoyoy(gdg_ctx &cx, const gdg_unit_desc &d)
+{
+    const int n = cx.n, S = chunk_len(n), hs = d.i[0], mode = d.i[1];
+    const double dinv = d.p[0], dd = d.p[1];
+    double *x = cx.cur, *y = cx.alt, *st = d.st;
+    GDG_THREADS_BEGIN
+        const int k0 = tid * S, k1 = imin(n, k0 + S);
+        double e = 0.0;
+        for (int k = k0; k < k1; k++) e = follow_step(mode, e, fabs(x[sw(k)]), dinv, dd);
+        cx.scanB[tid] = e;
+    GDG_THREADS_END
+    { gdg_scan_par sp; scan_par_const(sp, 0, follow_A(mode, dinv, dd), n, S, st[0]); block_scan(cx, 1, mode == GDG_FOLLOW_ENVELOPE, 0, sp, n, S); }
+    GDG_THREADS_BEGIN
+        const int k0 = tid * S, k1 = imin(n, k0 + S);
+        const int pos = (int)st_geti(st, GDG_RING_ST_POS);
+        const double *ring = st + GDG_RING_ST_DATA;
+        double e = cx.scanB[tid];
+        for (int k = k0; k < k1; k++) {
+            const double s = x[sw(k)];
+            e = follow_step(mode, e, fabs(s), dinv, dd);
+            const double level = 20.0 * log10(e);
+            double dfac;
+            if (level <= d.p[2]) dfac = d.p[4];
+            else if (level >= d.p[3]) dfac = d.p[5];
+            else dfac = d.p[4] + (d.p[6] * (level - d.p[2]));
+            const double dsmp = (0.01 * dfac) * d.p[7];
+            y[sw(k)] = (0.5 * s) + (0.5 * frac_delay_read(x, ring, hs, pos, k, dsmp));
+        }
+        if (k0 < n && k1 == n) cx.misc[0] = e;
+    GDG_THREADS_END
+    GDG_THREADS_BEGIN
+        if (tid == 0 && n > 0) st[0] = cx.misc[0];
+    GDG_THREADS_END
+    ring_push(cx, x, st, hs);
+    swap_bufs(cx);
+}
+
+#endif /* GDG_STAGES_CUH */

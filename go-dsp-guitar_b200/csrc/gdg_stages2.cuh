@@ -1,0 +1,582 @@
+/*
+ * gdg_stages2.cuh - the heavier stages: oversampled nonlinear units, octaver,
+ * auto_wah, reverb and the power_amp FFT convolution.  See gdg_stages.cuh for
+ * the execution model.
+ */
+#ifndef GDG_STAGES2_CUH
+#define GDG_STAGES2_CUH
+
+#include "gdg_stages.cuh"
+
+/* ==========================================================================
+ * Oversampled nonlinear units: excess / fuzz / overdrive / distortion
+ *   (effects/excess.go, fuzz.go, overdrive.go, distortion.go; the shared
+ *    Oversample -> processOversampled -> Decimate wrapper e.g. overdrive.go:83-144)
+ *
+ *   i[0] factor (1, 2, 4)   i[1] follow mode (fuzz)   i[2] valve (overdrive: 0 ECC82, 1 ECC83, -1 none)
+ *   p[0] gainFac p[1] levelFac
+ *   fuzz:      p[2] biasFac p[3] fuzzFac p[4] 1-fuzzFac p[5] dInv (at the oversampled rate) p[6] d
+ *   overdrive: p[2] driveFac p[3] cleanFac
+ *
+ * Up-sampling (oversampling.go:54-115 + resample.go:148-176): emitted sample
+ * M = f*j + p of the block equals in[j-4] for p == 0 and
+ * sum_{q<6} in[j-6+q] * L(2 - q + p/f) otherwise (4-sample look-ahead latency;
+ * the last 8 inputs are carried).  Decimation (oversampling.go:126-184 via
+ * filter.go:342-515): out[i] = 0.94406 * clamp(sum_k h[k] z[f i - k]) - the
+ * reference filters (and clamps) all f*N samples and keeps every f-th; only the
+ * kept ones are computed here, as a direct FIR over the carried z history.
+ * ========================================================================== */
+#define GDG_ZHALO 160                       /* >= L-1 = 154, multiple of 8 */
+GDG_DEVI int zp(int q) { return q + (q >> 3); }   /* padded layout: chunks of 8 start in distinct banks */
+
+GDG_DEVI double nl_pointwise(int type, const gdg_unit_desc &d, double s)
+{
+    if (type == GDG_UNIT_DISTORTION) return d.p[1] * clamp1(d.p[0] * s);        /* distortion.go:36-47 */
+    if (type == GDG_UNIT_OVERDRIVE) {                                           /* overdrive.go:59-76 */
+        const double arg = d.p[0] * s;
+        double dist = 0.0;
+        if (d.i[2] == 0) dist = (2.0 / GDG_PI) * atan((0.25 * GDG_PI) * arg);
+        else if (d.i[2] == 1) { const double e = exp(-arg); dist = (2.0 / (1.0 + e)) - 1.0; }
+        return d.p[1] * ((d.p[2] * dist) + (d.p[3] * s));
+    }
+    /* excess.go:37-64: triangular wave folding */
+    double pre = d.p[0] * s;
+    const double ap = fabs(pre);
+    const int exceeded = ap > 1.0, negative = pre < 0.0;
+    const int section = (int)(0.5 * floor(ap + 1.0));
+    const int odd = (section % 2) != 0;
+    const int inverted = odd != (exceeded && negative);
+    const double ex = fmod(ap + 1.0, 2.0);
+    if (exceeded) pre = inverted ? 1.0 - ex : ex - 1.0;
+    return d.p[1] * pre;
+}
+
+/* fuzz.go:52-105 on `cnt` consecutive samples held (padded layout) at z[zp(q0..)]: three passes + two scans */
+GDG_DEV void fuzz_run(gdg_ctx &cx, const gdg_unit_desc &d, double *z, int q0, int cnt, int padded)
+{
+    const int S = chunk_len(cnt), mode = d.i[1];
+    const double gain = d.p[0], lvl = d.p[1], bias = d.p[2], ff = d.p[3], ffi = d.p[4], dinv = d.p[5], dd = d.p[6];
+    double *st = d.st;
+    GDG_THREADS_BEGIN
+        const int k0 = tid * S, k1 = imin(cnt, k0 + S);
+        double e = 0.0;
+        for (int k = k0; k < k1; k++) { const int a = padded ? zp(q0 + k) : sw(k); e = follow_step(mode, e, fabs(z[a]), dinv, dd); }
+        cx.scanB[tid] = e;
+    GDG_THREADS_END
+    { gdg_scan_par sp; scan_par_const(sp, 0, follow_A(mode, dinv, dd), cnt, S, st[GDG_OS_ST_ENV]);
+      block_scan(cx, 1, mode == GDG_FOLLOW_ENVELOPE, 0, sp, cnt, S); }
+    GDG_THREADS_BEGIN
+        const int k0 = tid * S, k1 = imin(cnt, k0 + S);
+        double e = cx.scanB[tid], c = 0.0;
+        cx.scanA[tid] = e;
+        for (int k = k0; k < k1; k++) {
+            const int a = padded ? zp(q0 + k) : sw(k);
+            const double s = z[a];
+            e = follow_step(mode, e, fabs(s), dinv, dd);
+            double pre = clamp1(gain * (s - (bias * e)));
+            pre = (ff * pre) + (ffi * s);
+            c += (pre - c) * dd;
+        }
+        cx.scanB[tid] = c;
+        if (k0 < cnt && k1 == cnt) cx.misc[0] = e;
+    GDG_THREADS_END
+    GDG_THREADS_BEGIN
+        cx.scanB[GDG_NT + tid] = cx.scanA[tid];          /* follower carries -> lane 1 (untouched by a 1-lane scan) */
+    GDG_THREADS_END
+    { gdg_scan_par sp; scan_par_const(sp, 0, 1.0 - dd, cnt, S, st[GDG_OS_ST_CCV]); block_scan(cx, 1, 0, 0, sp, cnt, S); }
+    GDG_THREADS_BEGIN
+        const int k0 = tid * S, k1 = imin(cnt, k0 + S);
+        double e = cx.scanB[GDG_NT + tid], c = cx.scanB[tid];
+        for (int k = k0; k < k1; k++) {
+            const int a = padded ? zp(q0 + k) : sw(k);
+            const double s = z[a];
+            e = follow_step(mode, e, fabs(s), dinv, dd);
+            double pre = clamp1(gain * (s - (bias * e)));
+            pre = (ff * pre) + (ffi * s);
+            const double diff = pre - c;
+            c += diff * dd;
+            pre -= c;
+            z[a] = lvl * clamp1(pre);
+        }
+        if (k0 < cnt && k1 == cnt) { st[GDG_OS_ST_ENV] = cx.misc[0]; st[GDG_OS_ST_CCV] = c; }
+    GDG_THREADS_END
+}
+
+GDG_DEV void stage_oversampled(gdg_ctx &cx, const gdg_unit_desc &d)
+{
+    const int n = cx.n, f = d.i[0], type = d.type;
+    double *x = cx.cur, *st = d.st;
+    if (f <= 1) {
+        if (type == GDG_UNIT_FUZZ) { fuzz_run(cx, d, x, 0, n, 0); return; }
+        GDG_THREADS_BEGIN
+            for (int k = tid; k < n; k += GDG_NT) x[sw(k)] = nl_pointwise(type, d, x[sw(k)]);
+        GDG_THREADS_END
+        return;
+    }
+    const int L = f == 2 ? 77 : 155;
+    const double *h = f == 2 ? c_aa2 : c_aa4;
+    double *uph = st + (f == 2 ? GDG_OS_ST_UP2 : GDG_OS_ST_UP4);
+    double *zh = st + (f == 2 ? GDG_OS_ST_Z2 : GDG_OS_ST_Z4);
+    double *y = cx.alt, *z = cx.S;
+    const int T = imin(n, GDG_OS_TILE);
+    /* load the z history into the halo: logical q in [GDG_ZHALO-(L-1), GDG_ZHALO) */
+    GDG_THREADS_BEGIN
+        if (tid < GDG_ZHALO) z[zp(tid)] = tid >= GDG_ZHALO - (L - 1) ? zh[tid - (GDG_ZHALO - (L - 1))] : 0.0;
+    GDG_THREADS_END
+    for (int t0 = 0; t0 < n; t0 += T) {
+        const int Tt = imin(T, n - t0), cnt = f * Tt;
+        /* up-sample (+ stateless nonlinearity) */
+        GDG_THREADS_BEGIN
+            for (int m = tid; m < cnt; m += GDG_NT) {
+                const int M = f * t0 + m, jj = M / f, p = M - jj * f;
+                double u;
+                if (p == 0) {
+                    const int idx = jj - 4;
+                    u = idx >= 0 ? x[sw(idx)] : uph[8 + idx];
+                } else {
+                    const double *w = f == 2 ? c_lz2[0] : c_lz4[p - 1];
+                    u = 0.0;
+                    for (int q = 0; q < 6; q++) {
+                        const int idx = jj - 6 + q;
+                        const double s = idx >= 0 ? x[sw(idx)] : uph[8 + idx];
+                        u += s * w[q];
+                    }
+                }
+                if (type != GDG_UNIT_FUZZ) u = nl_pointwise(type, d, u);
+                z[zp(GDG_ZHALO + m)] = u;
+            }
+        GDG_THREADS_END
+        if (type == GDG_UNIT_FUZZ) fuzz_run(cx, d, z, GDG_ZHALO, cnt, 1);
+        /* decimate: two adjacent outputs per thread share one pass over the z window */
+        GDG_THREADS_BEGIN
+            for (int i = 2 * tid; i < Tt; i += 2 * GDG_NT) {
+                const int two = (i + 1 < Tt);
+                const int qtop = GDG_ZHALO + f * (i + 1);           /* newest sample used by output i+1 */
+                double acc0 = 0.0, acc1 = 0.0;
+                for (int k = 0; k < L + f; k++) {
+                    const int q = qtop - k;
+                    const double zv = (two || k >= f) ? z[zp(q)] : 0.0;
+                    if (k < L) acc1 += h[k] * zv;
+                    if (k >= f) acc0 += h[k - f] * zv;
+                }
+                y[sw(t0 + i)] = 0.9440608762859234 * clamp1(acc0);
+                if (two) y[sw(t0 + i + 1)] = 0.9440608762859234 * clamp1(acc1);
+            }
+        GDG_THREADS_END
+        /* slide the window: halo <- last GDG_ZHALO samples (through scanB as staging) */
+        GDG_THREADS_BEGIN
+            if (tid < GDG_ZHALO) cx.scanB[tid] = z[zp(tid + cnt)];
+        GDG_THREADS_END
+        GDG_THREADS_BEGIN
+            if (tid < GDG_ZHALO) z[zp(tid)] = cx.scanB[tid];
+        GDG_THREADS_END
+    }
+    /* carry: z history and the last 8 inputs (oversampling.go:91-93) */
+    GDG_THREADS_BEGIN
+        if (tid < L - 1) zh[tid] = z[zp(GDG_ZHALO - (L - 1) + tid)];
+        if (tid < 8) cx.misc[8 + tid] = (n - 8 + tid) >= 0 ? x[sw(n - 8 + tid)] : uph[tid + n];
+    GDG_THREADS_END
+    GDG_THREADS_BEGIN
+        if (tid < 8) uph[tid] = cx.misc[8 + tid];
+    GDG_THREADS_END
+    swap_bufs(cx);
+}
+
+/* ==========================================================================
+ * octaver  (effects/octaver.go:21-139)
+ *   i[0] follow; p[0] dInv p[1] d p[2] facUp p[3] facClean p[4] facDist p[5] facDown1 p[6] facDown2 p[7] facHyst
+ *   st[0] previousPolarity st[1] octaveRegister (i64) st[2] envelope st[3] coupling
+ * polarity after a sample = sign of the last "candidate" (nonzero sample above the
+ * hysteresis level); the register counts sign changes between successive candidates.
+ * ========================================================================== */
+GDG_DEV void stage_octaver(gdg_ctx &cx, const gdg_unit_desc &d)
+{
+    const int n = cx.n, S = chunk_len(n), mode = d.i[0];
+    const double dinv = d.p[0], dd = d.p[1], fUp = d.p[2], fClean = d.p[3], fDist = d.p[4], fD1 = d.p[5], fD2 = d.p[6], fH = d.p[7];
+    double *x = cx.cur, *st = d.st;
+    double *envc = cx.S, *first = cx.S + GDG_NT, *last = cx.S + 2 * GDG_NT, *flips = cx.S + 3 * GDG_NT,
+           *polin = cx.S + 4 * GDG_NT, *regin = cx.S + 5 * GDG_NT;
+    GDG_THREADS_BEGIN
+        const int k0 = tid * S, k1 = imin(n, k0 + S);
+        double e = 0.0;
+        for (int k = k0; k < k1; k++) e = follow_step(mode, e, fabs(x[sw(k)]), dinv, dd);
+        cx.scanB[tid] = e;
+    GDG_THREADS_END
+    { gdg_scan_par sp; scan_par_const(sp, 0, follow_A(mode, dinv, dd), n, S, st[2]); block_scan(cx, 1, mode == GDG_FOLLOW_ENVELOPE, 0, sp, n, S); }
+    GDG_THREADS_BEGIN
+        const int k0 = tid * S, k1 = imin(n, k0 + S);
+        double e = cx.scanB[tid], fs = 0.0, ls = 0.0, fl = 0.0;
+        envc[tid] = e;
+        for (int k = k0; k < k1; k++) {
+            const double s = x[sw(k)], sa = fabs(s);
+            e = follow_step(mode, e, sa, dinv, dd);
+            const double sign = s < 0.0 ? -1.0 : (s > 0.0 ? 1.0 : 0.0);
+            if (sign != 0.0 && sa > e * fH) {
+                if (fs == 0.0) fs = sign; else if (sign != ls) fl += 1.0;
+                ls = sign;
+            }
+        }
+        first[tid] = fs; last[tid] = ls; flips[tid] = fl;
+        if (k0 < n && k1 == n) cx.misc[0] = e;
+    GDG_THREADS_END
+    GDG_THREADS_BEGIN
+        if (tid == 0) {                                /* serial combine over the chunk summaries */
+            double pol = st[0];
+            long long reg = st_geti(st, 1);
+            for (int t = 0; t < GDG_NT; t++) {
+                polin[t] = pol; regin[t] = (double)reg;
+                if (first[t] != 0.0) {
+                    if (first[t] != pol) reg++;
+                    reg += (long long)flips[t];
+                    pol = last[t];
+                }
+            }
+            cx.misc[1] = pol; cx.misc[2] = (double)(reg & 7);
+        }
+    GDG_THREADS_END
+    /* pre-coupling signal -> alt, coupling zero-state response */
+    GDG_THREADS_BEGIN
+        const int k0 = tid * S, k1 = imin(n, k0 + S);
+        double e = envc[tid], pol = polin[tid], c = 0.0;
+        long long reg = (long long)regin[tid];
+        for (int k = k0; k < k1; k++) {
+            const double s = x[sw(k)], sa = fabs(s);
+            e = follow_step(mode, e, sa, dinv, dd);
+            const double sign = s < 0.0 ? -1.0 : (s > 0.0 ? 1.0 : 0.0);
+            if ((sign != 0.0) && (sign != pol) && (sa > e * fH)) { reg = (reg + 1) & 7; pol = sign; }
+            const double fd = (reg & 2) ? -1.0 : 1.0, sd = (reg & 4) ? -1.0 : 1.0;
+            double pre = fClean * s;
+            if (e > 0.0001) pre += fUp * ((s * s) / e);
+            pre += fDist * (sign * e);
+            pre += fD1 * (fd * e);
+            pre += fD2 * (sd * e);
+            cx.alt[sw(k)] = pre;
+            c += (pre - c) * dd;
+        }
+        cx.scanB[tid] = c;
+    GDG_THREADS_END
+    { gdg_scan_par sp; scan_par_const(sp, 0, 1.0 - dd, n, S, st[3]); block_scan(cx, 1, 0, 0, sp, n, S); }
+    GDG_THREADS_BEGIN
+        const int k0 = tid * S, k1 = imin(n, k0 + S);
+        double c = cx.scanB[tid];
+        for (int k = k0; k < k1; k++) {
+            double pre = cx.alt[sw(k)];
+            c += (pre - c) * dd;
+            pre -= c;
+            x[sw(k)] = clamp1(pre);
+        }
+        if (k0 < n && k1 == n) { st[0] = cx.misc[1]; st_seti(st, 1, (long long)cx.misc[2]); st[2] = cx.misc[0]; st[3] = c; }
+    GDG_THREADS_END
+}
+
+/* ==========================================================================
+ * auto_wah  (effects/autowah.go:20-130)
+ *   i[0] follow; p[0] dInv p[1] d p[2] levelA p[3] levelB p[4] freqA p[5] freqB p[6] slope p[7] sampleRate p[8] gainCompensation
+ *   st[0] envelope st[1..8] hcv st[9..16] lcv
+ * k[n] = 1 - exp(-f(env[n])/fs) is stored in alt; the 8 HP/LP pairs are affine
+ * recurrences with that time-varying coefficient (the NEW lp value feeds the next pair).
+ * ========================================================================== */
+GDG_DEV void stage_autowah(gdg_ctx &cx, const gdg_unit_desc &d)
+{
+    const int n = cx.n, S = chunk_len(n), mode = d.i[0];
+    const double dinv = d.p[0], dd = d.p[1];
+    double *x = cx.cur, *kv = cx.alt, *st = d.st;
+    GDG_THREADS_BEGIN
+        const int k0 = tid * S, k1 = imin(n, k0 + S);
+        double e = 0.0;
+        for (int k = k0; k < k1; k++) e = follow_step(mode, e, fabs(x[sw(k)]), dinv, dd);
+        cx.scanB[tid] = e;
+    GDG_THREADS_END
+    { gdg_scan_par sp; scan_par_const(sp, 0, follow_A(mode, dinv, dd), n, S, st[0]); block_scan(cx, 1, mode == GDG_FOLLOW_ENVELOPE, 0, sp, n, S); }
+    GDG_THREADS_BEGIN
+        const int k0 = tid * S, k1 = imin(n, k0 + S);
+        double e = cx.scanB[tid];
+        for (int k = k0; k < k1; k++) {
+            e = follow_step(mode, e, fabs(x[sw(k)]), dinv, dd);
+            const double level = 20.0 * log10(e);
+            double freq;
+            if (level <= d.p[2]) freq = d.p[4];
+            else if (level >= d.p[3]) freq = d.p[5];
+            else freq = d.p[4] + (d.p[6] * (level - d.p[2]));
+            kv[sw(k)] = 1.0 - exp(-freq / d.p[7]);
+        }
+        if (k0 < n && k1 == n) cx.misc[0] = e;
+    GDG_THREADS_END
+    for (int j = 0; j < 8; j++) {
+        /* HP zero-state + chunk coefficient product */
+        GDG_THREADS_BEGIN
+            const int k0 = tid * S, k1 = imin(n, k0 + S);
+            double h = 0.0, a = 1.0;
+            for (int k = k0; k < k1; k++) { const double kk = kv[sw(k)]; h += (x[sw(k)] - h) * kk; a *= (1.0 - kk); }
+            cx.scanB[tid] = h; cx.scanA[tid] = a;
+        GDG_THREADS_END
+        { gdg_scan_par sp; sp.init[0] = st[1 + j]; sp.a_full[0] = sp.a_last[0] = 1.0; block_scan(cx, 1, 0, 1, sp, n, S); }
+        GDG_THREADS_BEGIN
+            const int k0 = tid * S, k1 = imin(n, k0 + S);
+            double h = cx.scanB[tid], l = 0.0;
+            cx.S[tid] = h;
+            for (int k = k0; k < k1; k++) {
+                const double kk = kv[sw(k)];
+                double diff = x[sw(k)] - h;
+                h += diff * kk;
+                diff -= l;
+                l += diff * kk;
+            }
+            cx.scanB[tid] = l;                       /* scanA still holds prod(1-k) of the chunk */
+        GDG_THREADS_END
+        { gdg_scan_par sp; sp.init[0] = st[9 + j]; sp.a_full[0] = sp.a_last[0] = 1.0; block_scan(cx, 1, 0, 1, sp, n, S); }
+        GDG_THREADS_BEGIN
+            const int k0 = tid * S, k1 = imin(n, k0 + S);
+            double h = cx.S[tid], l = cx.scanB[tid];
+            for (int k = k0; k < k1; k++) {
+                const double kk = kv[sw(k)];
+                double diff = x[sw(k)] - h;
+                h += diff * kk;
+                diff -= l;
+                l += diff * kk;
+                x[sw(k)] = (j == 7) ? clamp1(d.p[8] * l) : l;
+            }
+            if (k0 < n && k1 == n) { st[1 + j] = h; st[9 + j] = l; if (j == 7) st[0] = cx.misc[0]; }
+        GDG_THREADS_END
+    }
+}
+
+/* ==========================================================================
+ * reverb  (effects/reverb.go:41-60 all-pass, 65-116 delay line, 179-338 Process)
+ *   i[0] line ring size (max tap) i[1..4] taps i[5..7] all-pass delays D (device ring: 2*(D-1) slots)
+ *   i[8] offset of the first all-pass ring inside st (line ring starts at GDG_RV_ST_DATA)
+ *   p[0] dryFrac p[1] halfWetFrac p[2..5] tap coefficients p[6] all-pass feedback
+ * All-pass: pre[i] = x[i] - g*pre[i-(D-1)], out[i] = g*pre[i] + pre[i-(D-1)] with the
+ * pre ring in global memory -> rounds of D-1 independent samples.
+ * ========================================================================== */
+GDG_DEV void stage_reverb(gdg_ctx &cx, const gdg_unit_desc &d)
+{
+    const int n = cx.n, hs = d.i[0];
+    double *x = cx.cur, *line = cx.alt, *w = cx.S, *st = d.st;
+    double *lring = st + GDG_RV_ST_DATA;
+    const double g = d.p[6];
+    GDG_THREADS_BEGIN
+        const int pos = (int)st_geti(st, GDG_RV_ST_LINEPOS);
+        for (int k = tid; k < n; k += GDG_NT) {
+            double pre = 0.0;
+            for (int j = 0; j < 4; j++) {
+                const int idx = k - d.i[1 + j];
+                double cs = 0.0;
+                if (idx >= 0) cs = x[sw(idx)];
+                else if (idx >= -hs) cs = ring_get(lring, hs, pos, hs + idx);
+                pre += d.p[2 + j] * cs;
+            }
+            line[sw(k)] = pre;
+            w[sw(k)] = pre;
+        }
+    GDG_THREADS_END
+    /* push the dry block into the line ring */
+    GDG_THREADS_BEGIN
+        const int pos = (int)st_geti(st, GDG_RV_ST_LINEPOS);
+        if (n >= hs) { for (int q = tid; q < hs; q += GDG_NT) lring[q] = x[sw(n - hs + q)]; }
+        else { for (int k = tid; k < n; k += GDG_NT) { int p = pos + k; if (p >= hs) p -= hs; lring[p] = x[sw(k)]; } }
+    GDG_THREADS_END
+    GDG_THREADS_BEGIN
+        if (tid == 0) { const int pos = (int)st_geti(st, GDG_RV_ST_LINEPOS); st_seti(st, GDG_RV_ST_LINEPOS, n >= hs ? 0 : (pos + n) % hs); }
+    GDG_THREADS_END
+    int off = d.i[8];
+    for (int a = 0; a < 3; a++) {
+        /* pre[i] = x[i] - g*pre[i-lag], out[i] = g*pre[i] + pre[i-lag], lag = D-1 (reverb.go:51-56: the read
+         * pointer runs one slot ahead of the write pointer in a ring of D).  The device ring has 2*lag slots
+         * indexed by time, so the slots written in a round of <= lag samples are disjoint from the slots read. */
+        const int D = d.i[5 + a], lag = D - 1, Dr = 2 * lag;
+        double *ring = st + off;
+        off += Dr;
+        if (lag <= 0) continue;                              /* not reachable: D >= 100 for every supported rate */
+        const int w0 = (int)st_geti(st, GDG_RV_ST_APPTR + a);
+        for (int r0 = 0; r0 < n; r0 += lag) {
+            const int r1 = imin(n, r0 + lag);
+            GDG_THREADS_BEGIN
+                for (int k = r0 + tid; k < r1; k += GDG_NT) {
+                    const int pw = (w0 + k) % Dr;
+                    int pr = pw - lag;
+                    if (pr < 0) pr += Dr;
+                    const double dl = ring[pr];
+                    const double pre = w[sw(k)] - (g * dl);
+                    ring[pw] = pre;
+                    w[sw(k)] = (g * pre) + dl;
+                }
+            GDG_THREADS_END
+        }
+        GDG_THREADS_BEGIN
+            if (tid == 0) st_seti(st, GDG_RV_ST_APPTR + a, (w0 + n) % Dr);
+        GDG_THREADS_END
+    }
+    GDG_THREADS_BEGIN
+        for (int k = tid; k < n; k += GDG_NT)
+            x[sw(k)] = clamp1((d.p[0] * x[sw(k)]) + (d.p[1] * (line[sw(k)] + w[sw(k)])));
+    GDG_THREADS_END
+}
+
+/* ==========================================================================
+ * power_amp: FFT overlap-add FIR  (effects/poweramp.go:186-216 -> filter/filter.go:342-515)
+ *   i[0] L (taps; 0 = empty filter -> zeros, -1 = no filter compiled -> zeros)
+ *   i[1] F (real FFT size = 2*nextPow2(L) <= GDG_MAX_FFT)   i[2] log2(F/2)
+ *   aux: H[k], k = 0..F/2 (interleaved re,im) = first half of RealFourier(zero-padded h)
+ *   st: tail[F]
+ * Blocks of B = F/2 samples (filter.go:372-388): out = clamp(y[0:ns] + tail[0:ns]),
+ * tail <- (y + tail)[ns:F] shifted, zero-filled.  All nb = ceil(n/B) block FFTs sit in
+ * R side by side (2B doubles each) and are transformed together.
+ * tw: global twiddle table exp(-2 pi i k / GDG_MAX_FFT), k in [0, GDG_MAX_FFT/2)
+ * ========================================================================== */
+struct gdg_c2 { double re, im; };
+GDG_DEVI gdg_c2 cmul(gdg_c2 a, gdg_c2 b) { gdg_c2 r; r.re = a.re * b.re - a.im * b.im; r.im = a.re * b.im + a.im * b.re; return r; }
+GDG_DEVI gdg_c2 cadd(gdg_c2 a, gdg_c2 b) { gdg_c2 r; r.re = a.re + b.re; r.im = a.im + b.im; return r; }
+GDG_DEVI gdg_c2 csub(gdg_c2 a, gdg_c2 b) { gdg_c2 r; r.re = a.re - b.re; r.im = a.im - b.im; return r; }
+GDG_DEVI gdg_c2 cconj(gdg_c2 a) { gdg_c2 r; r.re = a.re; r.im = -a.im; return r; }
+GDG_DEVI gdg_c2 cld(const double *p, int i) { gdg_c2 r; r.re = p[2 * i]; r.im = p[2 * i + 1]; return r; }
+GDG_DEVI void cst(double *p, int i, gdg_c2 v) { p[2 * i] = v.re; p[2 * i + 1] = v.im; }
+GDG_DEVI gdg_c2 twd(const double *tw, int idx) { gdg_c2 r; r.re = GDG_LDG(tw + 2 * idx); r.im = GDG_LDG(tw + 2 * idx + 1); return r; }
+GDG_DEVI int brev(int v, int bits)
+{
+    unsigned int r = (unsigned int)v;
+    r = ((r >> 1) & 0x55555555u) | ((r & 0x55555555u) << 1);
+    r = ((r >> 2) & 0x33333333u) | ((r & 0x33333333u) << 2);
+    r = ((r >> 4) & 0x0f0f0f0fu) | ((r & 0x0f0f0f0fu) << 4);
+    r = ((r >> 8) & 0x00ff00ffu) | ((r & 0x00ff00ffu) << 8);
+    r = (r >> 16) | (r << 16);
+    return bits ? (int)(r >> (32 - bits)) : 0;
+}
+
+/* forward: decimation in frequency, natural in -> bit-reversed out; nseg transforms of M complex points */
+GDG_DEV void fft_dif(gdg_ctx &cx, double *R, const double *tw, int M, int logM, int nseg)
+{
+    (void)logM;
+    const int total = nseg * (M / 2);
+    for (int h = M / 2; h >= 1; h >>= 1) {
+        const int tstep = (GDG_MAX_FFT / 2) / h;              /* W_{2h}^pos = tw[pos * MAXFFT/(2h)] */
+        GDG_THREADS_BEGIN
+            for (int b = tid; b < total; b += GDG_NT) {
+                const int seg = b / (M / 2), r = b - seg * (M / 2);
+                const int grp = r / h, pos = r - grp * h;
+                const int i0 = seg * M + grp * 2 * h + pos, i1 = i0 + h;
+                const gdg_c2 a = cld(R, i0), c = cld(R, i1);
+                cst(R, i0, cadd(a, c));
+                cst(R, i1, cmul(csub(a, c), twd(tw, pos * tstep)));
+            }
+        GDG_THREADS_END
+    }
+}
+/* inverse: decimation in time, bit-reversed in -> natural out (unnormalised, conjugate twiddles) */
+GDG_DEV void fft_dit_inv(gdg_ctx &cx, double *R, const double *tw, int M, int logM, int nseg)
+{
+    (void)logM;
+    const int total = nseg * (M / 2);
+    for (int h = 1; h <= M / 2; h <<= 1) {
+        const int tstep = (GDG_MAX_FFT / 2) / h;
+        GDG_THREADS_BEGIN
+            for (int b = tid; b < total; b += GDG_NT) {
+                const int seg = b / (M / 2), r = b - seg * (M / 2);
+                const int grp = r / h, pos = r - grp * h;
+                const int i0 = seg * M + grp * 2 * h + pos, i1 = i0 + h;
+                const gdg_c2 a = cld(R, i0), t = cmul(cld(R, i1), cconj(twd(tw, pos * tstep)));
+                cst(R, i0, cadd(a, t));
+                cst(R, i1, csub(a, t));
+            }
+        GDG_THREADS_END
+    }
+}
+
+GDG_DEV void stage_poweramp(gdg_ctx &cx, const gdg_unit_desc &d, const double *tw)
+{
+    const int n = cx.n, L = d.i[0];
+    double *x = cx.cur;
+    if (L <= 0) {                                              /* filter.go:366-367 / poweramp.go:210-214 */
+        GDG_THREADS_BEGIN
+            for (int k = tid; k < n; k += GDG_NT) x[sw(k)] = 0.0;
+        GDG_THREADS_END
+        return;
+    }
+    const int F = d.i[1], M = F / 2, logM = d.i[2], B = M;       /* B samples per block = M complex points * ... */
+    const int nb = n <= B ? 1 : n / B;                           /* n and B are powers of two */
+    const int ns = n <= B ? n : B;                               /* samples per block */
+    double *R = cx.R, *S = cx.S, *tail = d.st;
+    const double *H = d.aux;
+    /* stage the block in plain layout, then spread: block j -> R[j*F .. j*F + ns), zero padded to F */
+    GDG_THREADS_BEGIN
+        for (int k = tid; k < n; k += GDG_NT) S[k] = x[sw(k)];
+    GDG_THREADS_END
+    GDG_THREADS_BEGIN
+        for (int q = tid; q < nb * F; q += GDG_NT) {
+            const int j = q / F, r = q - j * F;
+            R[q] = r < ns ? S[j * ns + r] : 0.0;
+        }
+    GDG_THREADS_END
+    fft_dif(cx, R, tw, M, logM, nb);
+    /* split (fft.go:801-818) * H (filter.go:459) * inverse split (fft.go:899-955), on bit-reversed storage */
+    const int fstep = GDG_MAX_FFT / F;                            /* W_F^k = tw[k * MAXFFT/F] */
+    GDG_THREADS_BEGIN
+        for (int b = tid; b < nb * (M / 2 + 1); b += GDG_NT) {
+            const int seg = b / (M / 2 + 1), k = b - seg * (M / 2 + 1);
+            double *Z = R + seg * F;
+            if (k == 0) {
+                const gdg_c2 z0 = cld(Z, 0);
+                const double x0 = z0.re + z0.im, xm = z0.re - z0.im;     /* X[0], X[M] (real) */
+                const double y0 = x0 * GDG_LDG(H + 0), ym = xm * GDG_LDG(H + 2 * M);  /* real(dc), real(nyquist) of the product */
+                gdg_c2 o; o.re = 0.5 * (y0 + ym); o.im = 0.5 * (y0 - ym);
+                cst(Z, 0, o);
+            } else {
+                const int k2 = M - k;
+                const int p1 = brev(k, logM), p2 = brev(k2, logM);
+                const gdg_c2 za = cld(Z, p1), zb = cld(Z, p2);
+                const gdg_c2 wk = twd(tw, k * fstep);
+                gdg_c2 jw; jw.re = -wk.im; jw.im = wk.re;                 /* j * W_F^k */
+                /* X[k] = 0.5((Za + conj Zb) - jW (Za - conj Zb));  X[M-k] = conj of the same with roles swapped */
+                const gdg_c2 s1 = cadd(za, cconj(zb)), d1 = csub(za, cconj(zb));
+                const gdg_c2 t1 = cmul(jw, d1);
+                gdg_c2 xa; xa.re = 0.5 * (s1.re - t1.re); xa.im = 0.5 * (s1.im - t1.im);
+                /* W_F^{M-k} = -conj(W_F^k)  =>  j W_F^{M-k} = conj(jW) */
+                const gdg_c2 s2 = cadd(zb, cconj(za)), d2 = csub(zb, cconj(za));
+                const gdg_c2 t2 = cmul(cconj(jw), d2);
+                gdg_c2 xb; xb.re = 0.5 * (s2.re - t2.re); xb.im = 0.5 * (s2.im - t2.im);
+                gdg_c2 ha, hb; ha.re = GDG_LDG(H + 2 * k); ha.im = GDG_LDG(H + 2 * k + 1);
+                hb.re = GDG_LDG(H + 2 * k2); hb.im = GDG_LDG(H + 2 * k2 + 1);
+                const gdg_c2 ya = cmul(xa, ha), yb = cmul(xb, hb);
+                /* Z'[k] = 0.5((Ya + conj Yb) + j (Ya - conj Yb) conj(W_F^k)) */
+                const gdg_c2 e1 = cadd(ya, cconj(yb)), o1 = cmul(csub(ya, cconj(yb)), cconj(wk));
+                gdg_c2 ra; ra.re = 0.5 * (e1.re - o1.im); ra.im = 0.5 * (e1.im + o1.re);
+                gdg_c2 wk2; wk2.re = -wk.re; wk2.im = wk.im;               /* W_F^{M-k} */
+                const gdg_c2 e2 = cadd(yb, cconj(ya)), o2 = cmul(csub(yb, cconj(ya)), cconj(wk2));
+                gdg_c2 rb; rb.re = 0.5 * (e2.re - o2.im); rb.im = 0.5 * (e2.im + o2.re);
+                cst(Z, p1, ra);
+                if (p2 != p1) cst(Z, p2, rb);
+            }
+        }
+    GDG_THREADS_END
+    fft_dit_inv(cx, R, tw, M, logM, nb);
+    /* overlap-add, clamp, new tail */
+    const double scale = 1.0 / (double)M;
+    GDG_THREADS_BEGIN
+        for (int k = tid; k < n; k += GDG_NT) {
+            const int j = k / ns, r = k - j * ns;
+            double pre = scale * R[j * F + r];
+            if (j == 0) pre += tail[r];
+            else { pre += scale * R[(j - 1) * F + ns + r]; if (j == 1) pre += tail[ns + r]; }
+            S[k] = clamp1(pre);
+        }
+    GDG_THREADS_END
+    /* tail' = (y_last + tail_in)[ns:F] shifted to 0, then zeros (filter.go:494-503); for nb >= 2 the
+     * running tail beyond ns is zero, so only the single-block case adds the old tail.  Staged in R
+     * in place (each thread rewrites the cell it read) so no tail[] cell is read after being written. */
+    GDG_THREADS_BEGIN
+        for (int q = tid; q < F - ns; q += GDG_NT) {
+            double v = scale * R[(nb - 1) * F + ns + q];
+            if (nb == 1) v += tail[ns + q];
+            R[(nb - 1) * F + ns + q] = v;
+        }
+    GDG_THREADS_END
+    GDG_THREADS_BEGIN
+        for (int q = tid; q < F; q += GDG_NT) tail[q] = q < F - ns ? R[(nb - 1) * F + ns + q] : 0.0;
+    GDG_THREADS_END
+    cx.cur = R; cx.alt = R + GDG_MAX_N;
+    GDG_THREADS_BEGIN
+        for (int k = tid; k < n; k += GDG_NT) cx.cur[sw(k)] = S[k];
+    GDG_THREADS_END
+}
+
+#endif /* GDG_STAGES2_CUH */

@@ -1,0 +1,164 @@
+/*
+ * gdg.h - C ABI of libgdg: the B200-native effects-chain engine behind
+ * go-dsp-guitar's signal.Chain / effects.Unit / spatializer.Spatializer /
+ * tuner.Tuner interfaces.  Plain pointers and sizes only; this is what a cgo
+ * wrapper binds.  Each entry point names the reference
+ * interface it replaces (paths relative to the go-dsp-guitar tree).
+ *
+ * Conventions
+ *   - every function that can fail returns 0 on success / a negative value on
+ *     failure (or NULL for constructors); gdg_last_error() then returns the
+ *     message, using the reference's own error strings where it has one
+ *     (effects/effects.go:165-312, signal/signal.go:59-337);
+ *   - audio buffers are float64, one contiguous array per channel (the
+ *     reference's []float64); block lengths must be powers of two <= 8192
+ *     (controller/controller.go:36 BLOCK_SIZE; filter.Process is only safe for
+ *     powers of two, filter/filter.go:372-455) - other sizes are REJECTED, where
+ *     the reference would panic or silently misbehave;
+ *   - there is NO CPU fallback: without a CUDA device gdg_init() fails and every
+ *     processing call fails.
+ */
+#ifndef GDG_H
+#define GDG_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GDG_VERSION "0.1.0"
+
+/* unit type codes: effects/effects.go:21-43 (UNIT_SIGNALGENERATOR .. UNIT_CABINET) */
+enum {
+    GDG_SIGNALGENERATOR = 0, GDG_NOISEGATE, GDG_BANDPASS, GDG_AUTOWAH, GDG_AUTOYOY, GDG_COMPRESSOR, GDG_OCTAVER,
+    GDG_EXCESS, GDG_FUZZ, GDG_OVERDRIVE, GDG_DISTORTION, GDG_TONESTACK, GDG_CHORUS, GDG_FLANGER, GDG_PHASER,
+    GDG_TREMOLO, GDG_RINGMODULATOR, GDG_DELAY, GDG_REVERB, GDG_POWERAMP, GDG_CABINET
+};
+/* parameter types: effects/effects.go:12-16 */
+enum { GDG_PARAMETER_TYPE_INVALID = 0, GDG_PARAMETER_TYPE_DISCRETE = 1, GDG_PARAMETER_TYPE_NUMERIC = 2 };
+
+typedef struct gdg_irbank gdg_irbank;           /* filter.ImpulseResponses   filter/filter.go:79-82  */
+typedef struct gdg_chain gdg_chain;             /* signal.Chain              signal/signal.go:21-36  */
+typedef struct gdg_spatializer gdg_spatializer; /* spatializer.Spatializer   spatializer/spatializer.go:30-41 */
+typedef struct gdg_tuner gdg_tuner;             /* tuner.Tuner               tuner/tuner.go:62-65    */
+
+/* ---- runtime ----------------------------------------------------------------- */
+/* Select the CUDA device (one process per GPU) and upload the constant tables.  Called
+ * implicitly (device = current CUDA device) by the first constructor if omitted. */
+int gdg_init(int device);
+const char *gdg_last_error(void);
+const char *gdg_backend_name(void);
+const char *gdg_version(void);
+/* number of kernels launched so far (for bench.py's "gpu_launches") */
+uint64_t gdg_launch_count(void);
+/* page-locked host memory a caller can hand to gdg_process_batch for zero-staging copies */
+void *gdg_pinned_alloc(size_t bytes);
+void gdg_pinned_free(void *p);
+/* the library's CUDA stream (cudaStream_t) for callers that own device buffers */
+void *gdg_stream(void);
+int gdg_synchronize(void);
+
+/* effects.UnitTypes() / effects.ParameterTypes(): effects/effects.go:521-568 */
+int gdg_unit_type_count(void);
+const char *gdg_unit_type_name(int unit_type);
+
+/* ---- impulse responses: filter.Import  filter/filter.go:704-802 ------------------ */
+/* index.json ([{"Name","Path","Compensation"}...]); WAV paths are resolved relative to the
+ * current working directory like the reference (os.ReadFile(wavePath)).  Unreadable or
+ * non-mono files are skipped with a warning on stdout, like the reference. */
+gdg_irbank *gdg_irbank_import(const char *index_json_path);
+gdg_irbank *gdg_irbank_create(void);
+void gdg_irbank_destroy(gdg_irbank *bank);
+/* one descriptor's worth of filter.Import: resample to the 7 supported rates (filter/filter.go:25-33,766-780) */
+int gdg_irbank_add(gdg_irbank *bank, const char *name, int32_t compensation_db,
+                   const double *samples, size_t n, uint32_t source_rate);
+/* one response at exactly one rate (what filter.FromCoefficients-style synthetic IRs need) */
+int gdg_irbank_add_raw(gdg_irbank *bank, const char *name, int32_t compensation_db,
+                       const double *samples, size_t n, uint32_t rate);
+size_t gdg_irbank_name_count(const gdg_irbank *bank);         /* ImpulseResponses.Names() filter.go:681-699 */
+const char *gdg_irbank_name(const gdg_irbank *bank, size_t i);
+
+/* ---- signal.Chain  signal/signal.go ------------------------------------------------ */
+gdg_chain *gdg_chain_create(gdg_irbank *bank);                /* signal.CreateChain            signal.go:419  */
+void gdg_chain_destroy(gdg_chain *chain);
+int gdg_chain_append_unit(gdg_chain *chain, int unit_type);   /* AppendUnit -> id | -1 (starts BYPASSED) signal.go:52-86 */
+int gdg_chain_remove_unit(gdg_chain *chain, int id);          /* RemoveUnit                    signal.go:91-111 */
+int gdg_chain_move_up(gdg_chain *chain, int id);              /* MoveUp                        signal.go:116-136 */
+int gdg_chain_move_down(gdg_chain *chain, int id);            /* MoveDown                      signal.go:141-162 */
+int gdg_chain_unit_type(gdg_chain *chain, int id);            /* UnitType -> type | -1         signal.go:167-185 */
+int gdg_chain_set_bypass(gdg_chain *chain, int id, int bypass);           /* SetBypass        signal.go:190-218 */
+int gdg_chain_get_bypass(gdg_chain *chain, int id, int *bypass);          /* GetBypass        signal.go:223-240 */
+int gdg_chain_set_discrete_value(gdg_chain *chain, int id, const char *name, const char *value);   /* signal.go:245-263, effects.go:127-172 */
+int gdg_chain_get_discrete_value(gdg_chain *chain, int id, const char *name, const char **value);  /* signal.go:268-286 */
+int gdg_chain_set_numeric_value(gdg_chain *chain, int id, const char *name, int32_t value);        /* signal.go:291-308, effects.go:266-317 */
+int gdg_chain_get_numeric_value(gdg_chain *chain, int id, const char *name, int32_t *value);       /* signal.go:313-330 */
+int gdg_chain_length(gdg_chain *chain);                       /* Length                        signal.go:352-358 */
+/* Parameters(id): effects.Parameter (effects/effects.go:69-78), flattened */
+int gdg_chain_parameter_count(gdg_chain *chain, int id);
+typedef struct {
+    const char *name;
+    int32_t type;                 /* GDG_PARAMETER_TYPE_* */
+    const char *physical_unit;
+    int32_t minimum, maximum, numeric_value;
+    int32_t discrete_value_index;
+    int32_t discrete_value_count;
+} gdg_parameter;
+int gdg_chain_parameter(gdg_chain *chain, int id, int index, gdg_parameter *out);
+const char *gdg_chain_parameter_discrete_value(gdg_chain *chain, int id, int index, int value_index);
+
+/* Chain.Process(in, out []float64, sampleRate uint32)  signal.go:361-414.
+ * HOST buffers, synchronous: H2D, fused segment kernel(s), D2H.  The JACK-path drop-in. */
+int gdg_chain_process(gdg_chain *chain, const double *in, double *out, size_t n, uint32_t sample_rate);
+
+/* The per-block fan-out of controller.process (controller/controller.go:2682-2705): all chains,
+ * one block.  HOST buffers (in[c], out[c] point to n doubles each; pinned and/or contiguous
+ * buffers are detected and copied without staging). */
+int gdg_process_batch(gdg_chain *const *chains, size_t channels, const double *const *in, double *const *out,
+                      size_t n, uint32_t sample_rate);
+/* Same with DEVICE-resident planar buffers: channel c at d_in + c*stride.  Asynchronous on `stream`
+ * (NULL = gdg_stream()). */
+int gdg_process_batch_device(gdg_chain *const *chains, size_t channels, const double *d_in, double *d_out,
+                             size_t stride, size_t n, uint32_t sample_rate, void *stream);
+
+/* ---- spatializer.Spatializer  spatializer/spatializer.go ---------------------------- */
+gdg_spatializer *gdg_spatializer_create(uint32_t input_channels);          /* Create           :436-469 */
+void gdg_spatializer_destroy(gdg_spatializer *s);
+int gdg_spatializer_set_azimuth(gdg_spatializer *s, uint32_t channel, double azimuth);    /* :340-355 */
+int gdg_spatializer_get_azimuth(gdg_spatializer *s, uint32_t channel, double *azimuth);   /* :63-78   */
+int gdg_spatializer_set_distance(gdg_spatializer *s, uint32_t channel, double distance);  /* :360-383 */
+int gdg_spatializer_get_distance(gdg_spatializer *s, uint32_t channel, double *distance); /* :83-98   */
+int gdg_spatializer_set_level(gdg_spatializer *s, uint32_t channel, double level);        /* :388-413 */
+int gdg_spatializer_get_level(gdg_spatializer *s, uint32_t channel, double *level);       /* :103-118 */
+uint32_t gdg_spatializer_input_count(gdg_spatializer *s);                                 /* :123-125 */
+uint32_t gdg_spatializer_output_count(gdg_spatializer *s);                                /* :130-132 */
+int gdg_spatializer_set_sample_rate(gdg_spatializer *s, uint32_t rate);                   /* :418-431 */
+/* Process(inputBuffers, auxInputBuffer|nil, outputBuffers[2])  :140-335  (HOST buffers) */
+int gdg_spatializer_process(gdg_spatializer *s, const double *const *in, uint32_t n_in, const double *aux,
+                            double *const *out, uint32_t n_out, size_t n);
+/* DEVICE buffers.  `accumulate` != 0 adds onto d_out (used for the multi-GPU partial sums);
+ * channel c at d_in + c*stride, outputs d_out (left) and d_out + out_stride (right). */
+int gdg_spatializer_process_device(gdg_spatializer *s, const double *d_in, size_t stride, const double *d_aux,
+                                   double *d_out, size_t out_stride, size_t n, int accumulate, void *stream);
+
+/* ---- tuner.Tuner  tuner/tuner.go ---------------------------------------------------- */
+gdg_tuner *gdg_tuner_create(void);                                                        /* Create  :592-607 */
+void gdg_tuner_destroy(gdg_tuner *t);
+int gdg_tuner_process(gdg_tuner *t, const double *samples, size_t n, uint32_t sample_rate);        /* Process :582-587 (HOST) */
+int gdg_tuner_process_device(gdg_tuner *t, const double *d_samples, size_t n, uint32_t sample_rate, void *stream);
+typedef struct { int8_t cents; double frequency; const char *note; } gdg_tuner_result;    /* tuner.Result :27-43 */
+int gdg_tuner_analyze(gdg_tuner *t, gdg_tuner_result *result);                            /* Analyze :379-577 */
+
+/* ---- controller.process mirror (controller/controller.go:2648-2783) ------------------- */
+/* tuner feed (channel tuner_channel, or -1) -> chains -> spatializer into out[C], out[C+1].
+ * HOST buffers; n_out must be >= channels (+2 when spat != NULL).  Metronome/level meters are
+ * the caller's business (out of scope). */
+int gdg_controller_process(gdg_chain *const *chains, uint32_t channels, gdg_tuner *tuner, int tuner_channel,
+                           gdg_spatializer *spat, const double *const *in, double *const *out, uint32_t n_out,
+                           size_t n, uint32_t sample_rate);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,94 @@
+/*
+ * emu_backend.cpp - TEST-ONLY host build of the device side of libgdg.
+ *
+ * Compiles the very same stage source (go-dsp-guitar_b200/csrc/gdg_interp.cuh)
+ * with GDG_HOST_EMU, where a "phase" is a loop over the CTA's thread ids, and
+ * implements gdg_backend.h with plain host memory.  Linked with the unmodified
+ * gdg_host.cpp it yields tests/emu/libgdg_emu.so, which lets the CPU test suite
+ * (-m "not gpu") check the host logic AND the parallel reformulation of every
+ * unit (scans, rounds, tiles, FFT) against the oracle without a GPU.
+ *
+ * It is never shipped, never loaded by the product package, and is not a
+ * fallback: go-dsp-guitar_b200/libgdg.so contains only the CUDA backend and
+ * refuses to start without a B200-class device.
+ */
+#define GDG_HOST_EMU 1
+#include <atomic>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../go-dsp-guitar_b200/csrc/gdg_backend.h"
+#include "../../go-dsp-guitar_b200/csrc/gdg_interp.cuh"
+
+static std::string t_err;
+static std::vector<double> g_tw;
+static std::atomic<uint64_t> g_launches{0};
+
+const char *gdgb_error(void) { return t_err.c_str(); }
+const char *gdgb_name(void) { return "host-emulation (tests only)"; }
+int gdgb_init(int) { return 0; }
+int gdgb_device(void) { return -1; }
+int gdgb_sm_count(void) { return 0; }
+void *gdgb_stream(void) { return nullptr; }
+uint64_t gdgb_launch_count(void) { return g_launches.load(); }
+void *gdgb_alloc(size_t bytes) { return calloc(1, bytes ? bytes : 8); }
+void gdgb_free(void *p) { free(p); }
+int gdgb_zero(void *p, size_t bytes) { memset(p, 0, bytes); return 0; }
+int gdgb_upload(void *d, const void *s, size_t b) { memcpy(d, s, b); return 0; }
+int gdgb_download(void *d, const void *s, size_t b) { memcpy(d, s, b); return 0; }
+int gdgb_copy(void *d, const void *s, size_t b) { memmove(d, s, b); return 0; }
+int gdgb_sync(void) { return 0; }
+void *gdgb_pinned_alloc(size_t bytes) { return malloc(bytes ? bytes : 8); }
+void gdgb_pinned_free(void *p) { free(p); }
+int gdgb_is_pinned(const void *) { return 0; }
+
+int gdgb_set_tables(const double *aa2, const double *aa4, const double *lz2, const double *lz4, const double *tw)
+{
+    memcpy(c_aa2, aa2, sizeof(double) * 80);
+    memcpy(c_aa4, aa4, sizeof(double) * 160);
+    memcpy(c_lz2, lz2, sizeof(double) * 6);
+    memcpy(c_lz4, lz4, sizeof(double) * 18);
+    g_tw.assign(tw, tw + GDG_MAX_FFT);
+    return 0;
+}
+
+int gdgb_launch_chains(const gdg_chain_desc *const *descs, int channels, const double *in, double *out, long stride, int n, void *)
+{
+    std::vector<double> smem(GDG_SMEM_DOUBLES);
+    for (int c = 0; c < channels; c++) {
+        const double *src = in + (long)c * stride;
+        double *dst = out + (long)c * stride;
+        if (!descs[c]) { if (src != dst) memcpy(dst, src, sizeof(double) * n); continue; }
+        run_chain(smem.data(), descs[c], src, dst, n, g_tw.data());
+    }
+    g_launches++;
+    return 0;
+}
+
+int gdgb_launch_spatializer(const gdg_spat_channel *ch, int C, const double *in, long stride, const double *hist_in,
+                            double *hist_out, int hs, const double *aux, double *outL, double *outR, int n, int accumulate, void *)
+{
+    for (int j = 0; j < n; j++) spat_frame(ch, C, in, stride, hist_in, hs, aux, outL, outR, j, accumulate);
+    for (int c = 0; c < C; c++)
+        for (int i = 0; i < hs; i++) {
+            const long src = (long)i + n - hs;
+            hist_out[(long)c * hs + i] = src >= 0 ? in[(long)c * stride + src] : hist_in[(long)c * hs + i + n];
+        }
+    g_launches += 2;
+    return 0;
+}
+
+int gdgb_autocorrelate(const double *ring, int n_ring, int pos, double *w, int F, void *)
+{
+    const int M = F / 2;
+    int logM = 0;
+    while ((1 << logM) < M) logM++;
+    for (int i = 0; i < F; i++) ac_load_body(ring, n_ring, pos, w, i);
+    for (int h = M / 2; h >= 1; h >>= 1) for (int b = 0; b < M / 2; b++) ac_dif_body(w, h, b);
+    for (int k = 0; k <= M / 2; k++) ac_power_body(w, M, logM, k);
+    for (int h = 1; h <= M / 2; h <<= 1) for (int b = 0; b < M / 2; b++) ac_dit_body(w, h, b);
+    for (int i = 0; i < F; i++) w[i] *= 1.0 / (double)M;
+    return 0;
+}
