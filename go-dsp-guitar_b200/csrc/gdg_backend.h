@@ -25,7 +25,8 @@ void gdgb_free(void *p);
 int gdgb_zero(void *p, size_t bytes);
 int gdgb_upload(void *dst, const void *src, size_t bytes);      /* host -> device, stream ordered */
 int gdgb_download(void *dst, const void *src, size_t bytes);    /* device -> host, synchronises */
-int gdgb_copy(void *dst, const void *src, size_t bytes);        /* device -> device */
+int gdgb_copy(void *dst, const void *src, size_t bytes);        /* device -> device, library stream */
+int gdgb_copy_on(void *dst, const void *src, size_t bytes, void *stream);
 int gdgb_sync(void);
 void *gdgb_pinned_alloc(size_t bytes);
 void gdgb_pinned_free(void *p);

@@ -1217,20 +1217,21 @@ gdg_tuner *gdg_tuner_create(void)
 }
 void gdg_tuner_destroy(gdg_tuner *t) { delete t; }
 /* circular.Enqueue (circular/circular.go:33-71) on the device ring */
-int gdg_tuner_process_device(gdg_tuner *t, const double *d, size_t n, uint32_t rate, void *)
+int gdg_tuner_process_device(gdg_tuner *t, const double *d, size_t n, uint32_t rate, void *stream)
 {
     if (ensure_init()) return -1;
     if (!t || (!d && n)) return fail("gdg_tuner_process_device: bad argument");
     const size_t N = gdg_tuner::N;
+    void *st = stream ? stream : gdgb_stream();
     int rc = 0;
-    if (n >= N) { rc = gdgb_copy(t->d_ring, d + (n - N), N * sizeof(double)); t->pos = 0; }
+    if (n >= N) { rc = gdgb_copy_on(t->d_ring, d + (n - N), N * sizeof(double), st); t->pos = 0; }
     else if (n > 0) {
         const size_t inc = (size_t)t->pos + n;
-        if (inc < N) { rc = gdgb_copy(t->d_ring + t->pos, d, n * sizeof(double)); t->pos = (int)inc; }
+        if (inc < N) { rc = gdgb_copy_on(t->d_ring + t->pos, d, n * sizeof(double), st); t->pos = (int)inc; }
         else {
             const size_t head = inc - N, tail = N - (size_t)t->pos;
-            rc = gdgb_copy(t->d_ring + t->pos, d, tail * sizeof(double));
-            if (!rc && head) rc = gdgb_copy(t->d_ring, d + tail, head * sizeof(double));
+            rc = gdgb_copy_on(t->d_ring + t->pos, d, tail * sizeof(double), st);
+            if (!rc && head) rc = gdgb_copy_on(t->d_ring, d + tail, head * sizeof(double), st);
             t->pos = (int)head;
         }
     }

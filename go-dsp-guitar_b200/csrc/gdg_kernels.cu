@@ -133,6 +133,7 @@ int gdgb_download(void *dst, const void *src, size_t bytes)
     return 0;
 }
 int gdgb_copy(void *dst, const void *src, size_t bytes) { if (bytes) CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, g_stream)); return 0; }
+int gdgb_copy_on(void *dst, const void *src, size_t bytes, void *stream) { if (bytes) CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream)); return 0; }
 int gdgb_sync(void) { if (g_stream) CU(cudaStreamSynchronize(g_stream)); return 0; }
 void *gdgb_pinned_alloc(size_t bytes) { void *p = nullptr; if (cudaMallocHost(&p, bytes ? bytes : 8) != cudaSuccess) return nullptr; return p; }
 void gdgb_pinned_free(void *p) { if (p) cudaFreeHost(p); }

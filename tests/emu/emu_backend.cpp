@@ -39,6 +39,7 @@ int gdgb_zero(void *p, size_t bytes) { memset(p, 0, bytes); return 0; }
 int gdgb_upload(void *d, const void *s, size_t b) { memcpy(d, s, b); return 0; }
 int gdgb_download(void *d, const void *s, size_t b) { memcpy(d, s, b); return 0; }
 int gdgb_copy(void *d, const void *s, size_t b) { memmove(d, s, b); return 0; }
+int gdgb_copy_on(void *d, const void *s, size_t b, void *) { memmove(d, s, b); return 0; }
 int gdgb_sync(void) { return 0; }
 void *gdgb_pinned_alloc(size_t bytes) { return malloc(bytes ? bytes : 8); }
 void gdgb_pinned_free(void *p) { free(p); }
