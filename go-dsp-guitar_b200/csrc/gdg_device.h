@@ -56,9 +56,10 @@ typedef struct {
 #define GDG_OS_ST_CCV 1
 #define GDG_OS_ST_UP2 2            /* 8 words: last 8 inputs of the x2 up-sampler (oversampling.go:91-93) */
 #define GDG_OS_ST_UP4 10           /* 8 words: x4                                                          */
-#define GDG_OS_ST_Z2 18            /* 76 words: last L-1 oversampled samples entering the x2 decimator     */
-#define GDG_OS_ST_Z4 94            /* 154 words: x4                                                        */
-#define GDG_OS_ST_WORDS 248
+#define GDG_OS_ST_Z2 18            /* 2 x 41 words: per polyphase branch, the last 41 oversampled samples
+                                      entering the x2 decimator (its 77-tap history, de-interleaved)      */
+#define GDG_OS_ST_Z4 100           /* 4 x 41 words: x4 (155-tap history)                                   */
+#define GDG_OS_ST_WORDS 264
 
 /* delay-type units: word 0 = phase / envelope, word 1 = ring write position, ring from word 2 */
 #define GDG_RING_ST_POS 1

@@ -10,21 +10,9 @@
 
 #include "gdg_stages2.cuh"
 
-/* shared-memory carve-up (doubles) */
-#define GDG_SMEM_R 0
-#define GDG_SMEM_S (2 * GDG_MAX_N)
-#define GDG_SMEM_SCANB (GDG_SMEM_S + GDG_MAX_N)
-#define GDG_SMEM_SCANA (GDG_SMEM_SCANB + GDG_SCAN_LANES * GDG_NT)
-#define GDG_SMEM_SEG (GDG_SMEM_SCANA + GDG_NT)
-#define GDG_SMEM_MISC (GDG_SMEM_SEG + 3 * GDG_SCAN_LANES * GDG_NSEG)
-#define GDG_SMEM_DOUBLES (GDG_SMEM_MISC + 64)
-#define GDG_SMEM_BYTES (GDG_SMEM_DOUBLES * 8)
-
-GDG_DEVI void ctx_init(gdg_ctx &cx, double *smem, int n)
+GDG_DEVI void ctx_init(gdg_ctx &cx, int n)
 {
-    cx.R = smem + GDG_SMEM_R; cx.cur = cx.R; cx.alt = cx.R + GDG_MAX_N;
-    cx.S = smem + GDG_SMEM_S; cx.scanB = smem + GDG_SMEM_SCANB; cx.scanA = smem + GDG_SMEM_SCANA;
-    cx.seg = smem + GDG_SMEM_SEG; cx.misc = smem + GDG_SMEM_MISC; cx.n = n;
+    cx.cur_off = GDG_SMEM_R; cx.alt_off = GDG_SMEM_R + GDG_MAX_N; cx.n = n;
 }
 
 GDG_DEV void run_unit(gdg_ctx &cx, const gdg_unit_desc &d, const double *tw)
@@ -56,14 +44,19 @@ GDG_DEV void run_unit(gdg_ctx &cx, const gdg_unit_desc &d, const double *tw)
 GDG_DEV void run_chain(double *smem, const gdg_chain_desc *cd, const double *in, double *out, int n, const double *tw)
 {
     gdg_ctx cx;
-    ctx_init(cx, smem, n);
+#if !defined(__CUDACC__) || defined(GDG_HOST_EMU)
+    gdg_smem = smem;
+#else
+    (void)smem;
+#endif
+    ctx_init(cx, n);
     GDG_THREADS_BEGIN
-        for (int k = tid; k < n; k += GDG_NT) cx.cur[sw(k)] = in[k];
+        for (int k = tid; k < n; k += GDG_NT) SM_CUR(cx)[sw(k)] = in[k];
     GDG_THREADS_END
     const int ns = cd->nslots;
     for (int s = 0; s < ns; s++) run_unit(cx, cd->slot[s], tw);
     GDG_THREADS_BEGIN
-        for (int k = tid; k < n; k += GDG_NT) out[k] = cx.cur[sw(k)];
+        for (int k = tid; k < n; k += GDG_NT) out[k] = SM_CUR(cx)[sw(k)];
     GDG_THREADS_END
 }
 

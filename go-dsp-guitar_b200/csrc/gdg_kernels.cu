@@ -31,7 +31,6 @@ static int cu_fail(const char *what, cudaError_t e)
 __global__ void __launch_bounds__(GDG_NT, 1)
 k_chain(const gdg_chain_desc *const *descs, const double *in, double *out, long stride, int n, const double *tw)
 {
-    extern __shared__ __align__(16) double smem[];
     const int c = blockIdx.x;
     const gdg_chain_desc *cd = descs[c];
     const double *src = in + (long)c * stride;
@@ -40,7 +39,7 @@ k_chain(const gdg_chain_desc *const *descs, const double *in, double *out, long 
         if (src != dst) for (int k = threadIdx.x; k < n; k += GDG_NT) dst[k] = src[k];
         return;
     }
-    run_chain(smem, cd, src, dst, n, tw);
+    run_chain(gdg_smem, cd, src, dst, n, tw);
 }
 
 __global__ void k_spat(const gdg_spat_channel *ch, int C, const double *in, long stride, const double *hist, int hs,

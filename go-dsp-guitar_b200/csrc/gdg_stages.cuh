@@ -42,15 +42,25 @@
 #define GDG_DEVI __device__ __forceinline__
 #define GDG_THREADS_BEGIN { const int tid = (int)threadIdx.x;
 #define GDG_THREADS_END } __syncthreads();
+#define GDG_THREADS_END_NOSYNC }
 #define GDG_CONST __constant__
 #define GDG_LDG(p) __ldg(p)
+/* thread-private value that stays in a register across phases */
+#define GDG_REG(type, name) type name
+#define GDG_REGA(type, name, cnt) type name[cnt]
+#define R(name) name
 #else
 #define GDG_DEV static
 #define GDG_DEVI static inline
 #define GDG_THREADS_BEGIN for (int tid = 0; tid < GDG_NT; ++tid) {
 #define GDG_THREADS_END }
+#define GDG_THREADS_END_NOSYNC }
 #define GDG_CONST static
 #define GDG_LDG(p) (*(p))
+/* host emulation: one slot per emulated thread */
+#define GDG_REG(type, name) type name##_r[GDG_NT]
+#define GDG_REGA(type, name, cnt) type name##_r[GDG_NT][cnt]
+#define R(name) name##_r[tid]
 #endif
 
 #define GDG_PI 3.14159265358979323846
@@ -63,18 +73,37 @@ GDG_CONST double c_aa4[160];           /* 155-tap x4 anti-aliasing FIR (oversamp
 GDG_CONST double c_lz2[1][6];          /* Lanczos-3 weights of the fractional phases, x2 (resample.go:10-66) */
 GDG_CONST double c_lz4[3][6];          /* ... x4: phase p/4, taps q: L(2 - q + p/4) */
 
-/* ---- execution context: shared-memory carve-up ------------------------------ */
+/* ---- execution context: shared-memory carve-up (offsets in doubles) -----------
+ * Everything is addressed off the CTA's one dynamic shared array so that the
+ * compiler emits LDS/STS (not generic loads) in the separately compiled stages. */
+#define GDG_SMEM_R 0                                         /* 2*GDG_MAX_N: bufA | bufB; also the FFT workspace */
+#define GDG_SMEM_S (2 * GDG_MAX_N)                           /* GDG_MAX_N scratch */
+#define GDG_SMEM_SCANB (GDG_SMEM_S + GDG_MAX_N)              /* GDG_SCAN_LANES * GDG_NT staging */
+#define GDG_SMEM_SCANA (GDG_SMEM_SCANB + GDG_SCAN_LANES * GDG_NT)
+#define GDG_SMEM_SEG (GDG_SMEM_SCANA + GDG_NT)               /* warp totals of the scans */
+#define GDG_SMEM_MISC (GDG_SMEM_SEG + 3 * GDG_SCAN_LANES * GDG_NSEG)
+#define GDG_SMEM_DOUBLES (GDG_SMEM_MISC + 64)
+#define GDG_SMEM_BYTES (GDG_SMEM_DOUBLES * 8)
+
+#if defined(__CUDACC__) && !defined(GDG_HOST_EMU)
+extern __shared__ __align__(16) double gdg_smem[];
+#else
+static double *gdg_smem;                                     /* host emulation: set by run_chain */
+#endif
+
 struct gdg_ctx {
-    double *R;        /* 2*GDG_MAX_N doubles: bufA = R, bufB = R + GDG_MAX_N; also the FFT workspace */
-    double *cur;      /* current block (swizzled layout), R or R + GDG_MAX_N */
-    double *alt;      /* the other half */
-    double *S;        /* GDG_MAX_N doubles scratch */
-    double *scanB;    /* GDG_SCAN_LANES * GDG_NT */
-    double *scanA;    /* GDG_NT */
-    double *seg;      /* 3 * GDG_SCAN_LANES * GDG_NSEG */
-    double *misc;     /* 64 */
+    int cur_off;      /* current block (swizzled layout): GDG_SMEM_R or GDG_SMEM_R + GDG_MAX_N */
+    int alt_off;      /* the other half */
     int n;
 };
+#define SM_R (gdg_smem + GDG_SMEM_R)
+#define SM_S (gdg_smem + GDG_SMEM_S)
+#define SM_SCANB (gdg_smem + GDG_SMEM_SCANB)
+#define SM_SCANA (gdg_smem + GDG_SMEM_SCANA)
+#define SM_SEG (gdg_smem + GDG_SMEM_SEG)
+#define SM_MISC (gdg_smem + GDG_SMEM_MISC)
+#define SM_CUR(cx) (gdg_smem + (cx).cur_off)
+#define SM_ALT(cx) (gdg_smem + (cx).alt_off)
 
 /* XOR swizzle of the block buffers: a thread that walks its own 16-sample chunk
  * (stride-16 across the warp) and a warp that reads 32 consecutive samples are
@@ -87,7 +116,7 @@ GDG_DEVI int imax(int a, int b) { return a > b ? a : b; }
 GDG_DEVI long long st_geti(const double *st, int k) { return ((const long long *)st)[k]; }
 GDG_DEVI void st_seti(double *st, int k, long long v) { ((long long *)st)[k] = v; }
 GDG_DEVI int chunk_len(int n) { return (n + GDG_NT - 1) / GDG_NT; }
-GDG_DEVI void swap_bufs(gdg_ctx &cx) { double *t = cx.cur; cx.cur = cx.alt; cx.alt = t; }
+GDG_DEVI void swap_bufs(gdg_ctx &cx) { const int t = cx.cur_off; cx.cur_off = cx.alt_off; cx.alt_off = t; }
 
 GDG_DEVI double pow_int(double a, int k)
 {
@@ -109,77 +138,64 @@ GDG_DEVI double follow_A(int mode, double d_inv, double d)
 }
 
 /* --------------------------------------------------------------------------
- * Block scan of per-chunk recurrence summaries.
- *   chunk t maps carry c to   affine: A_t c + B_t     maxplus: max(A_t c, B_t)
- * In : scanB[lane*NT + t] = B_t (zero-state response of chunk t),
- *      A_t = a_full for complete chunks, a_last for the trailing partial chunk,
- *            or scanA[t] when vary != 0 (lane 0 only).
- * Out: scanB[lane*NT + t] = carry entering chunk t (chunk 0 gets init[lane]).
- * Two-level serial scan (32-chunk segments): three phases.
+ * Block scan of per-chunk recurrence maps held in registers.
+ *   chunk t maps its carry c to   affine: a_t c + b_t     maxplus: max(a_t c, b_t)
+ * Every thread passes the map of its own chunk (identity a=1, b=0 for an empty
+ * chunk; all maxplus operands are >= 0) and receives the carry entering its chunk;
+ * chunk 0 receives init.  K independent recurrences are scanned together.
+ * Device: inclusive warp scan with shuffles, warp totals through shared memory,
+ * serial prefix over the <= 15 preceding warps.  Host emulation: plain serial scan.
  * -------------------------------------------------------------------------- */
-struct gdg_scan_par { double a_full[GDG_SCAN_LANES], a_last[GDG_SCAN_LANES], init[GDG_SCAN_LANES]; };
-
 GDG_DEVI double scan_apply(int maxplus, double a, double c, double b)
 {
-    double v = a * c;
+    const double v = a * c;
     if (maxplus) return v > b ? v : b;
     return v + b;
 }
 
-GDG_DEV void block_scan(gdg_ctx &cx, int lanes, int maxplus, int vary, const gdg_scan_par &sp, int n, int S)
+#if defined(__CUDACC__) && !defined(GDG_HOST_EMU)
+template <int K>
+GDG_DEVI void scan_regs(gdg_ctx &cx, int maxplus, double (&a)[K], double (&b)[K], const double *init, double (&cin)[K])
 {
-    const int nfull = n / S;                 /* complete chunks */
-    const int nch = (n + S - 1) / S;         /* chunks in use   */
-    double *segA = cx.seg, *segB = cx.seg + GDG_SCAN_LANES * GDG_NSEG, *segV = cx.seg + 2 * GDG_SCAN_LANES * GDG_NSEG;
-    GDG_THREADS_BEGIN
-        if (tid < lanes * GDG_NSEG) {
-            const int lane = tid / GDG_NSEG, g = tid % GDG_NSEG;
-            double accA = 1.0, accB = 0.0;
-            for (int k = 0; k < 32; k++) {
-                const int idx = g * 32 + k;
-                if (idx < nch) {
-                    const double a = vary ? cx.scanA[idx] : (idx < nfull ? sp.a_full[lane] : sp.a_last[lane]);
-                    const double b = cx.scanB[lane * GDG_NT + idx];
-                    accB = scan_apply(maxplus, a, accB, b);
-                    accA *= a;
-                }
-            }
-            segA[lane * GDG_NSEG + g] = accA;
-            segB[lane * GDG_NSEG + g] = accB;
+    const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+#pragma unroll
+        for (int j = 0; j < K; j++) {
+            const double au = __shfl_up_sync(0xffffffffu, a[j], off), bu = __shfl_up_sync(0xffffffffu, b[j], off);
+            if (lane >= off) { b[j] = scan_apply(maxplus, a[j], bu, b[j]); a[j] *= au; }
         }
-    GDG_THREADS_END
-    GDG_THREADS_BEGIN
-        if (tid < lanes) {
-            double v = sp.init[tid];
-            for (int g = 0; g < GDG_NSEG; g++) {
-                segV[tid * GDG_NSEG + g] = v;
-                v = scan_apply(maxplus, segA[tid * GDG_NSEG + g], v, segB[tid * GDG_NSEG + g]);
-            }
-        }
-    GDG_THREADS_END
-    GDG_THREADS_BEGIN
-        if (tid < lanes * GDG_NSEG) {
-            const int lane = tid / GDG_NSEG, g = tid % GDG_NSEG;
-            double c = segV[lane * GDG_NSEG + g];
-            for (int k = 0; k < 32; k++) {
-                const int idx = g * 32 + k;
-                if (idx < nch) {
-                    const double a = vary ? cx.scanA[idx] : (idx < nfull ? sp.a_full[lane] : sp.a_last[lane]);
-                    const double b = cx.scanB[lane * GDG_NT + idx];
-                    cx.scanB[lane * GDG_NT + idx] = c;
-                    c = scan_apply(maxplus, a, c, b);
-                }
-            }
-        }
-    GDG_THREADS_END
+    }
+    double *ws = SM_SEG;                                   /* [K][NSEG][2] */
+    if (lane == 31) {
+#pragma unroll
+        for (int j = 0; j < K; j++) { ws[(j * GDG_NSEG + warp) * 2] = a[j]; ws[(j * GDG_NSEG + warp) * 2 + 1] = b[j]; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < K; j++) {
+        double c = init[j];
+        for (int w = 0; w < warp; w++) c = scan_apply(maxplus, ws[(j * GDG_NSEG + w) * 2], c, ws[(j * GDG_NSEG + w) * 2 + 1]);
+        double ae = __shfl_up_sync(0xffffffffu, a[j], 1), be = __shfl_up_sync(0xffffffffu, b[j], 1);
+        if (lane == 0) { ae = 1.0; be = 0.0; }
+        cin[j] = scan_apply(maxplus, ae, c, be);
+    }
+    __syncthreads();
 }
+#define GDG_SCAN(K, cx, maxplus, a, b, init, cin) scan_regs<K>(cx, maxplus, a, b, init, cin)
+#else
+template <int K>
+static void scan_regs_host(int maxplus, double (*a)[K], double (*b)[K], const double *init, double (*cin)[K])
+{
+    for (int j = 0; j < K; j++) {
+        double c = init[j];
+        for (int t = 0; t < GDG_NT; t++) { cin[t][j] = c; c = scan_apply(maxplus, a[t][j], c, b[t][j]); }
+    }
+}
+#define GDG_SCAN(K, cx, maxplus, a, b, init, cin) scan_regs_host<K>(maxplus, a##_r, b##_r, init, cin##_r)
+#endif
 
-GDG_DEVI void scan_par_const(gdg_scan_par &sp, int lane, double a_step, int n, int S, double init)
-{
-    sp.a_full[lane] = pow_int(a_step, S);
-    sp.a_last[lane] = pow_int(a_step, n % S);
-    sp.init[lane] = init;
-}
+GDG_DEVI double chunk_A(double a_step, int len, int S, double a_full) { return len == S ? a_full : pow_int(a_step, len); }
 
 /* History rings of the delay-type units.  The reference keeps the last `hs`
  * inputs oldest-first and memmoves them every block (e.g. chorus.go:119-129);
@@ -223,12 +239,12 @@ GDG_DEV void ring_push(gdg_ctx &cx, const double *blk, double *st, int hs)
  *   i[0] bypass-like flag (threshold_open < threshold_close), i[1] holdSamples
  *   p[0] facOpen p[1] facClose        st: [0] gateOpen (i64) [1] onHoldSince (i64)
  * "since" at sample k = k - (index of the last sample above the close threshold)
- * -> max-scan; gate = type of the last open/close event -> last-event scan.
+ * -> max-scan; gate = type of the last open/close event -> last-event (max) scan.
  * ========================================================================== */
 GDG_DEV void stage_noisegate(gdg_ctx &cx, const gdg_unit_desc &d)
 {
     const int n = cx.n, S = chunk_len(n);
-    double *x = cx.cur, *st = d.st;
+    double *x = SM_CUR(cx), *st = d.st;
     if (d.i[0]) {                                   /* levelOpen < levelClose: copy, force open */
         GDG_THREADS_BEGIN
             if (tid == 0) { st_seti(st, 0, 1); st_seti(st, 1, 0); }
@@ -239,18 +255,20 @@ GDG_DEV void stage_noisegate(gdg_ctx &cx, const gdg_unit_desc &d)
     const unsigned long long hold = (unsigned long long)(unsigned int)d.i[1];
     const unsigned long long since0 = (unsigned long long)st_geti(st, 1);
     const int open0 = (int)st_geti(st, 0);
-    /* P1: last close-threshold crossing per chunk (as index+1, 0 = none) */
+    const double zero[1] = {0.0};
+    GDG_REGA(double, a, 1); GDG_REGA(double, b, 1); GDG_REGA(double, lcin, 1); GDG_REGA(double, evin, 1);
+    /* last close-threshold crossing per chunk (as index+1, 0 = none) */
     GDG_THREADS_BEGIN
         const int k0 = tid * S, k1 = imin(n, k0 + S);
         double last = 0.0;
         for (int k = k0; k < k1; k++) if (fabs(x[sw(k)]) > facClose) last = (double)(k + 1);
-        cx.scanB[tid] = last;
-    GDG_THREADS_END
-    { gdg_scan_par sp; sp.a_full[0] = 1.0; sp.a_last[0] = 1.0; sp.init[0] = 0.0; block_scan(cx, 1, 1, 0, sp, n, S); }
-    /* P2: gate events per chunk: 0 none, 1 open, 2 close (close wins on the same sample) -> last event */
+        R(a)[0] = 1.0; R(b)[0] = last;
+    GDG_THREADS_END_NOSYNC
+    GDG_SCAN(1, cx, 1, a, b, zero, lcin);
+    /* gate events per chunk: 1 open, 2 close (close wins on the same sample) -> code of the last event */
     GDG_THREADS_BEGIN
         const int k0 = tid * S, k1 = imin(n, k0 + S);
-        long long lc = (long long)cx.scanB[tid];            /* last crossing index+1 before the chunk */
+        long long lc = (long long)R(lcin)[0];
         double ev = 0.0;
         for (int k = k0; k < k1; k++) {
             const double amp = fabs(x[sw(k)]);
@@ -260,27 +278,13 @@ GDG_DEV void stage_noisegate(gdg_ctx &cx, const gdg_unit_desc &d)
             if (amp > facOpen) ev = 1.0;
             if (since >= hold) ev = 2.0;
         }
-        cx.scanB[GDG_NT + tid] = ev;                          /* lane 1 */
-    GDG_THREADS_END
-    /* last-event scan over chunks: serial two-level is overkill - it is "last nonzero": use maxplus on (t+1)*4+ev */
-    GDG_THREADS_BEGIN
-        const double ev = cx.scanB[GDG_NT + tid];
-        cx.scanB[2 * GDG_NT + tid] = ev > 0.0 ? (double)((tid + 1) * 4) + ev : 0.0;   /* lane 2 */
-    GDG_THREADS_END
-    {
-        /* scan lane 2 with max: shift arrays so block_scan (lane-major) sees it as lane 0 of a 1-lane scan */
-        GDG_THREADS_BEGIN
-            cx.scanA[tid] = cx.scanB[tid];                    /* keep the close-crossing carry */
-            cx.scanB[tid] = cx.scanB[2 * GDG_NT + tid];
-        GDG_THREADS_END
-        gdg_scan_par sp; sp.a_full[0] = 1.0; sp.a_last[0] = 1.0; sp.init[0] = 0.0;
-        block_scan(cx, 1, 1, 0, sp, n, S);
-    }
-    /* P3: replay */
+        R(a)[0] = 1.0; R(b)[0] = ev > 0.0 ? (double)((tid + 1) * 4) + ev : 0.0;
+    GDG_THREADS_END_NOSYNC
+    GDG_SCAN(1, cx, 1, a, b, zero, evin);
     GDG_THREADS_BEGIN
         const int k0 = tid * S, k1 = imin(n, k0 + S);
-        long long lc = (long long)cx.scanA[tid];
-        const long long code = (long long)cx.scanB[tid];
+        long long lc = (long long)R(lcin)[0];
+        const long long code = (long long)R(evin)[0];
         int open = code > 0 ? ((code & 3) == 1) : open0;
         unsigned long long since = 0;
         for (int k = k0; k < k1; k++) {
@@ -308,17 +312,20 @@ GDG_DEV void stage_compressor(gdg_ctx &cx, const gdg_unit_desc &d)
 {
     const int n = cx.n, S = chunk_len(n), mode = d.i[0];
     const double dinv = d.p[0], dd = d.p[1], target = d.p[2], limit = d.p[3];
-    double *x = cx.cur, *st = d.st;
+    double *x = SM_CUR(cx), *st = d.st;
+    const double astep = follow_A(mode, dinv, dd), afull = pow_int(astep, S);
+    const double init[1] = {st[0]};
+    GDG_REGA(double, a, 1); GDG_REGA(double, b, 1); GDG_REGA(double, cin, 1);
     GDG_THREADS_BEGIN
         const int k0 = tid * S, k1 = imin(n, k0 + S);
         double e = 0.0;
         for (int k = k0; k < k1; k++) e = follow_step(mode, e, fabs(x[sw(k)]), dinv, dd);
-        cx.scanB[tid] = e;
-    GDG_THREADS_END
-    { gdg_scan_par sp; scan_par_const(sp, 0, follow_A(mode, dinv, dd), n, S, st[0]); block_scan(cx, 1, mode == GDG_FOLLOW_ENVELOPE, 0, sp, n, S); }
+        R(a)[0] = k0 < n ? chunk_A(astep, k1 - k0, S, afull) : 1.0; R(b)[0] = k0 < n ? e : 0.0;
+    GDG_THREADS_END_NOSYNC
+    GDG_SCAN(1, cx, mode == GDG_FOLLOW_ENVELOPE, a, b, init, cin);
     GDG_THREADS_BEGIN
         const int k0 = tid * S, k1 = imin(n, k0 + S);
-        double e = cx.scanB[tid];
+        double e = R(cin)[0];
         for (int k = k0; k < k1; k++) {
             const double s = x[sw(k)];
             e = follow_step(mode, e, fabs(s), dinv, dd);
@@ -338,8 +345,10 @@ GDG_DEV void stage_compressor(gdg_ctx &cx, const gdg_unit_desc &d)
 GDG_DEV void stage_tonestack(gdg_ctx &cx, const gdg_unit_desc &d)
 {
     const int n = cx.n, S = chunk_len(n);
-    double *x = cx.cur, *st = d.st;
-    /* P1: HP zero-state responses (4 lanes) */
+    double *x = SM_CUR(cx), *st = d.st;
+    double ahf[4], alf[4], inith[4], initl[4];
+    for (int j = 0; j < 4; j++) { ahf[j] = pow_int(1.0 - d.p[j], S); alf[j] = pow_int(1.0 - d.p[4 + j], S); inith[j] = st[j]; initl[j] = st[4 + j]; }
+    GDG_REGA(double, a, 4); GDG_REGA(double, b, 4); GDG_REGA(double, hin, 4); GDG_REGA(double, lin, 4);
     GDG_THREADS_BEGIN
         const int k0 = tid * S, k1 = imin(n, k0 + S);
         double h[4] = {0.0, 0.0, 0.0, 0.0};
@@ -347,14 +356,13 @@ GDG_DEV void stage_tonestack(gdg_ctx &cx, const gdg_unit_desc &d)
             const double s = x[sw(k)];
             for (int j = 0; j < 4; j++) h[j] += (s - h[j]) * d.p[j];
         }
-        for (int j = 0; j < 4; j++) cx.scanB[j * GDG_NT + tid] = h[j];
-    GDG_THREADS_END
-    { gdg_scan_par sp; for (int j = 0; j < 4; j++) scan_par_const(sp, j, 1.0 - d.p[j], n, S, st[j]); block_scan(cx, 4, 0, 0, sp, n, S); }
-    /* P2: replay HP, LP zero-state responses; keep the HP carries in S[0..4*NT) */
+        for (int j = 0; j < 4; j++) { R(a)[j] = k0 < n ? chunk_A(1.0 - d.p[j], k1 - k0, S, ahf[j]) : 1.0; R(b)[j] = k0 < n ? h[j] : 0.0; }
+    GDG_THREADS_END_NOSYNC
+    GDG_SCAN(4, cx, 0, a, b, inith, hin);
     GDG_THREADS_BEGIN
         const int k0 = tid * S, k1 = imin(n, k0 + S);
         double h[4], l[4] = {0.0, 0.0, 0.0, 0.0};
-        for (int j = 0; j < 4; j++) { h[j] = cx.scanB[j * GDG_NT + tid]; cx.S[j * GDG_NT + tid] = h[j]; }
+        for (int j = 0; j < 4; j++) h[j] = R(hin)[j];
         for (int k = k0; k < k1; k++) {
             const double s = x[sw(k)];
             for (int j = 0; j < 4; j++) {
@@ -364,14 +372,13 @@ GDG_DEV void stage_tonestack(gdg_ctx &cx, const gdg_unit_desc &d)
                 l[j] += diff * d.p[4 + j];
             }
         }
-        for (int j = 0; j < 4; j++) cx.scanB[j * GDG_NT + tid] = l[j];
-    GDG_THREADS_END
-    { gdg_scan_par sp; for (int j = 0; j < 4; j++) scan_par_const(sp, j, 1.0 - d.p[4 + j], n, S, st[4 + j]); block_scan(cx, 4, 0, 0, sp, n, S); }
-    /* P3: replay both, emit */
+        for (int j = 0; j < 4; j++) { R(a)[j] = k0 < n ? chunk_A(1.0 - d.p[4 + j], k1 - k0, S, alf[j]) : 1.0; R(b)[j] = k0 < n ? l[j] : 0.0; }
+    GDG_THREADS_END_NOSYNC
+    GDG_SCAN(4, cx, 0, a, b, initl, lin);
     GDG_THREADS_BEGIN
         const int k0 = tid * S, k1 = imin(n, k0 + S);
         double h[4], l[4];
-        for (int j = 0; j < 4; j++) { h[j] = cx.S[j * GDG_NT + tid]; l[j] = cx.scanB[j * GDG_NT + tid]; }
+        for (int j = 0; j < 4; j++) { h[j] = R(hin)[j]; l[j] = R(lin)[j]; }
         for (int k = k0; k < k1; k++) {
             const double s = x[sw(k)];
             double sum = 0.0;
@@ -393,7 +400,8 @@ GDG_DEV void stage_tonestack(gdg_ctx &cx, const gdg_unit_desc &d)
  * cabinet  (effects/cabinet.go:27-162): 3 cascaded one-pole high-passes
  * (out = x - v_old) then 4 cascaded low-passes (out = v_old), clamp.
  *   p[0..6] k of the 7 sections; st[0..6] cap voltages
- * The replay of section s also accumulates the zero-state response of section s+1.
+ * Every pass is chunk-local; the replay of section s also accumulates the
+ * zero-state response of section s+1, so a section costs one scan + one pass.
  * ========================================================================== */
 GDG_DEVI double onepole_out(int highpass, double xin, double &v, double k)
 {
@@ -406,29 +414,38 @@ GDG_DEVI double onepole_out(int highpass, double xin, double &v, double k)
 GDG_DEV void stage_cascade(gdg_ctx &cx, const gdg_unit_desc &d, int nsec, int nhp)
 {
     const int n = cx.n, S = chunk_len(n);
-    double *x = cx.cur, *st = d.st;
+    double *x = SM_CUR(cx), *st = d.st;
+    GDG_REGA(double, a, 1); GDG_REGA(double, b, 1); GDG_REGA(double, cin, 1);
     GDG_THREADS_BEGIN
         const int k0 = tid * S, k1 = imin(n, k0 + S);
         double v = 0.0;
         for (int k = k0; k < k1; k++) v += (x[sw(k)] - v) * d.p[0];
-        cx.scanB[tid] = v;
-    GDG_THREADS_END
+        R(b)[0] = k0 < n ? v : 0.0;
+    GDG_THREADS_END_NOSYNC
     for (int s = 0; s < nsec; s++) {
-        { gdg_scan_par sp; scan_par_const(sp, 0, 1.0 - d.p[s], n, S, st[s]); block_scan(cx, 1, 0, 0, sp, n, S); }
+        const double astep = 1.0 - d.p[s], afull = pow_int(astep, S);
+        const double init[1] = {st[s]};
+        GDG_THREADS_BEGIN
+            const int k0 = tid * S, k1 = imin(n, k0 + S);
+            R(a)[0] = k0 < n ? chunk_A(astep, k1 - k0, S, afull) : 1.0;
+        GDG_THREADS_END_NOSYNC
+        GDG_SCAN(1, cx, 0, a, b, init, cin);
         const int last = (s == nsec - 1);
         GDG_THREADS_BEGIN
             const int k0 = tid * S, k1 = imin(n, k0 + S);
-            double v = cx.scanB[tid], w = 0.0;
+            double v = R(cin)[0], w = 0.0;
             const double kk = d.p[s], kn = last ? 0.0 : d.p[s + 1];
             for (int k = k0; k < k1; k++) {
                 double y = onepole_out(s < nhp, x[sw(k)], v, kk);
                 if (last) y = clamp1(y); else w += (y - w) * kn;
                 x[sw(k)] = y;
             }
-            cx.scanB[tid] = w;
+            R(b)[0] = k0 < n ? w : 0.0;
             if (k0 < n && k1 == n) st[s] = v;
-        GDG_THREADS_END
+        GDG_THREADS_END_NOSYNC
     }
+    GDG_THREADS_BEGIN
+    GDG_THREADS_END
 }
 
 /* ==========================================================================
@@ -440,34 +457,33 @@ GDG_DEV void stage_bandpass(gdg_ctx &cx, const gdg_unit_desc &d)
 {
     const int n = cx.n, S = chunk_len(n), half = d.i[0];
     const double ka = d.p[0], kb = d.p[1];
-    double *x = cx.cur, *st = d.st;
+    const double aaf = pow_int(1.0 - ka, S), abf = pow_int(1.0 - kb, S);
+    double *x = SM_CUR(cx), *st = d.st;
+    GDG_REGA(double, a, 1); GDG_REGA(double, b, 1); GDG_REGA(double, hin, 1); GDG_REGA(double, lin, 1);
     for (int j = 0; j < half; j++) {
+        const double inith[1] = {st[j]}, initl[1] = {st[4 + j]};
         GDG_THREADS_BEGIN
             const int k0 = tid * S, k1 = imin(n, k0 + S);
             double h = 0.0;
             for (int k = k0; k < k1; k++) h += (x[sw(k)] - h) * ka;
-            cx.scanB[tid] = h;
-        GDG_THREADS_END
-        { gdg_scan_par sp; scan_par_const(sp, 0, 1.0 - ka, n, S, st[j]); block_scan(cx, 1, 0, 0, sp, n, S); }
+            R(a)[0] = k0 < n ? chunk_A(1.0 - ka, k1 - k0, S, aaf) : 1.0; R(b)[0] = k0 < n ? h : 0.0;
+        GDG_THREADS_END_NOSYNC
+        GDG_SCAN(1, cx, 0, a, b, inith, hin);
         GDG_THREADS_BEGIN
             const int k0 = tid * S, k1 = imin(n, k0 + S);
-            double h = cx.scanB[tid], l = 0.0;
-            cx.scanA[tid] = h;
+            double h = R(hin)[0], l = 0.0;
             for (int k = k0; k < k1; k++) {
                 double diff = x[sw(k)] - h;
                 h += diff * ka;
                 diff -= l;
                 l += diff * kb;
             }
-            cx.scanB[tid] = l;
-        GDG_THREADS_END
-        GDG_THREADS_BEGIN
-            cx.S[tid] = cx.scanA[tid];            /* HP carries survive the next scan (which may use scanA) */
-        GDG_THREADS_END
-        { gdg_scan_par sp; scan_par_const(sp, 0, 1.0 - kb, n, S, st[4 + j]); block_scan(cx, 1, 0, 0, sp, n, S); }
+            R(a)[0] = k0 < n ? chunk_A(1.0 - kb, k1 - k0, S, abf) : 1.0; R(b)[0] = k0 < n ? l : 0.0;
+        GDG_THREADS_END_NOSYNC
+        GDG_SCAN(1, cx, 0, a, b, initl, lin);
         GDG_THREADS_BEGIN
             const int k0 = tid * S, k1 = imin(n, k0 + S);
-            double h = cx.S[tid], l = cx.scanB[tid];
+            double h = R(hin)[0], l = R(lin)[0];
             for (int k = k0; k < k1; k++) {
                 double diff = x[sw(k)] - h;
                 h += diff * ka;
@@ -477,8 +493,10 @@ GDG_DEV void stage_bandpass(gdg_ctx &cx, const gdg_unit_desc &d)
                 x[sw(k)] = clamp1(iv);
             }
             if (k0 < n && k1 == n) { st[j] = h; st[4 + j] = l; }
-        GDG_THREADS_END
+        GDG_THREADS_END_NOSYNC
     }
+    GDG_THREADS_BEGIN
+    GDG_THREADS_END
 }
 
 /* ==========================================================================
@@ -504,7 +522,7 @@ GDG_DEVI void tremolo_at(long long i, int att0, unsigned long long s0, unsigned 
 GDG_DEV void stage_tremolo(gdg_ctx &cx, const gdg_unit_desc &d)
 {
     const int n = cx.n;
-    double *x = cx.cur, *st = d.st;
+    double *x = SM_CUR(cx), *st = d.st;
     const unsigned long long lenA = (unsigned int)d.i[0], lenU = (unsigned int)d.i[1];
     const double fac = d.p[0];
     GDG_THREADS_BEGIN
@@ -531,7 +549,7 @@ GDG_DEV void stage_tremolo(gdg_ctx &cx, const gdg_unit_desc &d)
 GDG_DEV void stage_ringmod(gdg_ctx &cx, const gdg_unit_desc &d)
 {
     const int n = cx.n;
-    double *x = cx.cur, *st = d.st;
+    double *x = SM_CUR(cx), *st = d.st;
     const double frac = d.p[0];
     GDG_THREADS_BEGIN
         const double phase = st[0];
@@ -558,7 +576,7 @@ GDG_DEVI unsigned long long lcg_pow(unsigned long long e)
 GDG_DEV void stage_siggen(gdg_ctx &cx, const gdg_unit_desc &d)
 {
     const int n = cx.n, S = chunk_len(n), type = d.i[0];
-    double *x = cx.cur, *st = d.st;
+    double *x = SM_CUR(cx), *st = d.st;
     const double fin = d.p[0], fsig = d.p[1], inc = d.p[2];
     if (type == 4) {
         GDG_THREADS_BEGIN
@@ -571,11 +589,11 @@ GDG_DEV void stage_siggen(gdg_ctx &cx, const gdg_unit_desc &d)
                     const double r = (double)xs / (double)(m - 1);
                     x[sw(k)] = (fin * x[sw(k)]) + (fsig * (1.0 - (2.0 * r)));
                 }
-                if (k1 == n) cx.misc[0] = (double)xs;
+                if (k1 == n) SM_MISC[0] = (double)xs;
             }
         GDG_THREADS_END
         GDG_THREADS_BEGIN
-            if (tid == 0 && n > 0) st_seti(st, 1, (long long)cx.misc[0]);
+            if (tid == 0 && n > 0) st_seti(st, 1, (long long)SM_MISC[0]);
         GDG_THREADS_END
         return;
     }
@@ -615,7 +633,7 @@ GDG_DEV void stage_delay(gdg_ctx &cx, const gdg_unit_desc &d)
 {
     const int n = cx.n, ds = d.i[0];
     const double fb = d.p[0], lvl = d.p[1];
-    double *x = cx.cur, *y = cx.alt, *st = d.st;
+    double *x = SM_CUR(cx), *y = SM_ALT(cx), *st = d.st;
     GDG_THREADS_BEGIN
         const int pos = (int)st_geti(st, GDG_RING_ST_POS);
         const double *ring = st + GDG_RING_ST_DATA;
@@ -634,18 +652,23 @@ GDG_DEV void stage_chorus(gdg_ctx &cx, const gdg_unit_desc &d)
 {
     const int n = cx.n, hs = d.i[0];
     const double depth = d.p[0], ang = d.p[1], sr = d.p[2];
-    double *x = cx.cur, *y = cx.alt, *st = d.st;
+    double *x = SM_CUR(cx), *y = SM_ALT(cx), *st = d.st;
     GDG_THREADS_BEGIN
         const int pos = (int)st_geti(st, GDG_RING_ST_POS);
         const double *ring = st + GDG_RING_ST_DATA;
         const double prev = st[0];
+        /* the five voices sit at fixed offsets 0.4*pi*j from the zero phase: one sincos per sample and the
+         * angle-addition formula instead of five fmod + sin (differs from chorus.go:75-79 by ~1 ulp of the
+         * sine, i.e. ~1e-13 samples of delay - far inside the 1e-9 budget) */
+        double cj[5], sj[5];
+        for (int j = 0; j < 5; j++) { sj[j] = sin((0.4 * GDG_PI) * (double)j); cj[j] = cos((0.4 * GDG_PI) * (double)j); }
         for (int k = tid; k < n; k += GDG_NT) {
             const double t = (double)k / sr;
             const double zero_phase = fmod(prev + (ang * t), GDG_TWO_PI);
+            const double s0 = sin(zero_phase), c0 = cos(zero_phase);
             double eff = 0.0;
             for (int j = 0; j < 5; j++) {
-                const double phase = fmod(zero_phase + ((0.4 * GDG_PI) * (double)j), GDG_TWO_PI);
-                const double offset = depth * sin(phase);
+                const double offset = depth * ((s0 * cj[j]) + (c0 * sj[j]));
                 const double dsmp = (0.001 * (40.0 + offset)) * sr;
                 eff += 0.2 * frac_delay_read(x, ring, hs, pos, k, dsmp);
             }
@@ -665,7 +688,7 @@ GDG_DEV void stage_flanger(gdg_ctx &cx, const gdg_unit_desc &d)
 {
     const int n = cx.n, hs = d.i[0];
     const double depth = d.p[0], ang = d.p[1], sr = d.p[2], sr_inv = d.p[3], wa = d.p[4], wb = d.p[5];
-    double *x = cx.cur, *y = cx.alt, *st = d.st;
+    double *x = SM_CUR(cx), *y = SM_ALT(cx), *st = d.st;
     GDG_THREADS_BEGIN
         const int pos = (int)st_geti(st, GDG_RING_ST_POS);
         const double *ring = st + GDG_RING_ST_DATA;
@@ -692,19 +715,22 @@ GDG_DEV void stage_autoyoy(gdg_ctx &cx, const gdg_unit_desc &d)
 {
     const int n = cx.n, S = chunk_len(n), hs = d.i[0], mode = d.i[1];
     const double dinv = d.p[0], dd = d.p[1];
-    double *x = cx.cur, *y = cx.alt, *st = d.st;
+    double *x = SM_CUR(cx), *y = SM_ALT(cx), *st = d.st;
+    const double astep = follow_A(mode, dinv, dd), afull = pow_int(astep, S);
+    const double init[1] = {st[0]};
+    GDG_REGA(double, a, 1); GDG_REGA(double, b, 1); GDG_REGA(double, cin, 1);
     GDG_THREADS_BEGIN
         const int k0 = tid * S, k1 = imin(n, k0 + S);
         double e = 0.0;
         for (int k = k0; k < k1; k++) e = follow_step(mode, e, fabs(x[sw(k)]), dinv, dd);
-        cx.scanB[tid] = e;
-    GDG_THREADS_END
-    { gdg_scan_par sp; scan_par_const(sp, 0, follow_A(mode, dinv, dd), n, S, st[0]); block_scan(cx, 1, mode == GDG_FOLLOW_ENVELOPE, 0, sp, n, S); }
+        R(a)[0] = k0 < n ? chunk_A(astep, k1 - k0, S, afull) : 1.0; R(b)[0] = k0 < n ? e : 0.0;
+    GDG_THREADS_END_NOSYNC
+    GDG_SCAN(1, cx, mode == GDG_FOLLOW_ENVELOPE, a, b, init, cin);
     GDG_THREADS_BEGIN
         const int k0 = tid * S, k1 = imin(n, k0 + S);
         const int pos = (int)st_geti(st, GDG_RING_ST_POS);
         const double *ring = st + GDG_RING_ST_DATA;
-        double e = cx.scanB[tid];
+        double e = R(cin)[0];
         for (int k = k0; k < k1; k++) {
             const double s = x[sw(k)];
             e = follow_step(mode, e, fabs(s), dinv, dd);
@@ -716,10 +742,7 @@ GDG_DEV void stage_autoyoy(gdg_ctx &cx, const gdg_unit_desc &d)
             const double dsmp = (0.01 * dfac) * d.p[7];
             y[sw(k)] = (0.5 * s) + (0.5 * frac_delay_read(x, ring, hs, pos, k, dsmp));
         }
-        if (k0 < n && k1 == n) cx.misc[0] = e;
-    GDG_THREADS_END
-    GDG_THREADS_BEGIN
-        if (tid == 0 && n > 0) st[0] = cx.misc[0];
+        if (k0 < n && k1 == n) st[0] = e;
     GDG_THREADS_END
     ring_push(cx, x, st, hs);
     swap_bufs(cx);

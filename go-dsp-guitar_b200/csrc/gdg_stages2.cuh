@@ -19,15 +19,26 @@
  *   overdrive: p[2] driveFac p[3] cleanFac
  *
  * Up-sampling (oversampling.go:54-115 + resample.go:148-176): emitted sample
- * M = f*j + p of the block equals in[j-4] for p == 0 and
- * sum_{q<6} in[j-6+q] * L(2 - q + p/f) otherwise (4-sample look-ahead latency;
+ * M = f*j + ph of the block equals in[j-4] for ph == 0 and
+ * sum_{q<6} in[j-6+q] * L(2 - q + ph/f) otherwise (4-sample look-ahead latency;
  * the last 8 inputs are carried).  Decimation (oversampling.go:126-184 via
  * filter.go:342-515): out[i] = 0.94406 * clamp(sum_k h[k] z[f i - k]) - the
  * reference filters (and clamps) all f*N samples and keeps every f-th; only the
- * kept ones are computed here, as a direct FIR over the carried z history.
+ * kept ones are computed here, as a direct POLYPHASE FIR: with k = f q + p,
+ *   y[i] = sum_p sum_{q<39} h[f q + p] * z_p[i - q],   z_p[m] = z[f m - p]
+ * (both designs are zero-padded to f*39 taps).  The oversampled signal is kept
+ * de-interleaved per phase in shared memory (tile of <= 1024 base samples + a
+ * halo of 41); warp w computes phase p = w mod f of GDG_FIR_R consecutive outputs
+ * per thread with a register sliding window and the taps as constant-bank
+ * immediates; the f partial sums are combined in phase order.
  * ========================================================================== */
-#define GDG_ZHALO 160                       /* >= L-1 = 154, multiple of 8 */
-GDG_DEVI int zp(int q) { return q + (q >> 3); }   /* padded layout: chunks of 8 start in distinct banks */
+#define GDG_FIR_Q 39                         /* taps per polyphase branch */
+#define GDG_ZH 40                            /* halo length per phase (>= Q-1), multiple of 8 */
+#define GDG_ZPS 1200                         /* doubles reserved per phase array: pz(GDG_ZH + GDG_OS_TILE + 1) <= 1200 */
+#define GDG_OS_Z2 GDG_OS_ST_Z2
+GDG_DEVI int pz(int m) { return m + (m >> 3); }      /* one pad per 8: stride-8/9 access patterns spread over banks */
+/* location of oversampled sample (tile-local base index jl, sub-phase ph) in the per-phase arrays */
+GDG_DEVI int zloc(int f, int jl, int ph) { return ph == 0 ? pz(GDG_ZH + jl) : (f - ph) * GDG_ZPS + pz(GDG_ZH + jl + 1); }
 
 GDG_DEVI double nl_pointwise(int type, const gdg_unit_desc &d, double s)
 {
@@ -51,135 +62,175 @@ GDG_DEVI double nl_pointwise(int type, const gdg_unit_desc &d, double s)
     return d.p[1] * pre;
 }
 
-/* fuzz.go:52-105 on `cnt` consecutive samples held (padded layout) at z[zp(q0..)]: three passes + two scans */
-GDG_DEV void fuzz_run(gdg_ctx &cx, const gdg_unit_desc &d, double *z, int q0, int cnt, int padded)
+/* fuzz.go:52-105 over `cnt` consecutive samples: follower scan, coupling-capacitor scan, in place.
+ * f == 1: samples are x[sw(k)]; f > 1: sample k = f*jl + ph of the tile lives at z[zloc(f, jl, ph)]. */
+GDG_DEVI int fz_addr(int f, int k) { if (f == 1) return sw(k); const int jl = k / f; return zloc(f, jl, k - jl * f); }
+
+GDG_DEV void fuzz_run(gdg_ctx &cx, const gdg_unit_desc &d, double *z, int cnt, int f)
 {
     const int S = chunk_len(cnt), mode = d.i[1];
     const double gain = d.p[0], lvl = d.p[1], bias = d.p[2], ff = d.p[3], ffi = d.p[4], dinv = d.p[5], dd = d.p[6];
     double *st = d.st;
+    const double astep = follow_A(mode, dinv, dd), afull = pow_int(astep, S), cstep = 1.0 - dd, cfull = pow_int(cstep, S);
+    const double inite[1] = {st[GDG_OS_ST_ENV]}, initc[1] = {st[GDG_OS_ST_CCV]};
+    GDG_REGA(double, a, 1); GDG_REGA(double, b, 1); GDG_REGA(double, ein, 1); GDG_REGA(double, cin, 1);
     GDG_THREADS_BEGIN
         const int k0 = tid * S, k1 = imin(cnt, k0 + S);
         double e = 0.0;
-        for (int k = k0; k < k1; k++) { const int a = padded ? zp(q0 + k) : sw(k); e = follow_step(mode, e, fabs(z[a]), dinv, dd); }
-        cx.scanB[tid] = e;
-    GDG_THREADS_END
-    { gdg_scan_par sp; scan_par_const(sp, 0, follow_A(mode, dinv, dd), cnt, S, st[GDG_OS_ST_ENV]);
-      block_scan(cx, 1, mode == GDG_FOLLOW_ENVELOPE, 0, sp, cnt, S); }
+        for (int k = k0; k < k1; k++) e = follow_step(mode, e, fabs(z[fz_addr(f, k)]), dinv, dd);
+        R(a)[0] = k0 < cnt ? chunk_A(astep, k1 - k0, S, afull) : 1.0; R(b)[0] = k0 < cnt ? e : 0.0;
+    GDG_THREADS_END_NOSYNC
+    GDG_SCAN(1, cx, mode == GDG_FOLLOW_ENVELOPE, a, b, inite, ein);
     GDG_THREADS_BEGIN
         const int k0 = tid * S, k1 = imin(cnt, k0 + S);
-        double e = cx.scanB[tid], c = 0.0;
-        cx.scanA[tid] = e;
+        double e = R(ein)[0], c = 0.0;
         for (int k = k0; k < k1; k++) {
-            const int a = padded ? zp(q0 + k) : sw(k);
-            const double s = z[a];
+            const double s = z[fz_addr(f, k)];
             e = follow_step(mode, e, fabs(s), dinv, dd);
             double pre = clamp1(gain * (s - (bias * e)));
             pre = (ff * pre) + (ffi * s);
             c += (pre - c) * dd;
         }
-        cx.scanB[tid] = c;
-        if (k0 < cnt && k1 == cnt) cx.misc[0] = e;
-    GDG_THREADS_END
-    GDG_THREADS_BEGIN
-        cx.scanB[GDG_NT + tid] = cx.scanA[tid];          /* follower carries -> lane 1 (untouched by a 1-lane scan) */
-    GDG_THREADS_END
-    { gdg_scan_par sp; scan_par_const(sp, 0, 1.0 - dd, cnt, S, st[GDG_OS_ST_CCV]); block_scan(cx, 1, 0, 0, sp, cnt, S); }
+        R(a)[0] = k0 < cnt ? chunk_A(cstep, k1 - k0, S, cfull) : 1.0; R(b)[0] = k0 < cnt ? c : 0.0;
+    GDG_THREADS_END_NOSYNC
+    GDG_SCAN(1, cx, 0, a, b, initc, cin);
     GDG_THREADS_BEGIN
         const int k0 = tid * S, k1 = imin(cnt, k0 + S);
-        double e = cx.scanB[GDG_NT + tid], c = cx.scanB[tid];
+        double e = R(ein)[0], c = R(cin)[0];
         for (int k = k0; k < k1; k++) {
-            const int a = padded ? zp(q0 + k) : sw(k);
-            const double s = z[a];
+            const int ad = fz_addr(f, k);
+            const double s = z[ad];
             e = follow_step(mode, e, fabs(s), dinv, dd);
             double pre = clamp1(gain * (s - (bias * e)));
             pre = (ff * pre) + (ffi * s);
             const double diff = pre - c;
             c += diff * dd;
             pre -= c;
-            z[a] = lvl * clamp1(pre);
+            z[ad] = lvl * clamp1(pre);
         }
-        if (k0 < cnt && k1 == cnt) { st[GDG_OS_ST_ENV] = cx.misc[0]; st[GDG_OS_ST_CCV] = c; }
+        if (k0 < cnt && k1 == cnt) { st[GDG_OS_ST_ENV] = e; st[GDG_OS_ST_CCV] = c; }
     GDG_THREADS_END
+}
+
+/* one polyphase branch (compile-time phase P) of GDG_FIR_R-consecutive outputs starting at i0: partial sums */
+template <int F, int P, int RR>
+GDG_DEVI void fir_branch(const double *zp, int i0, double (&acc)[RR])
+{
+    const double *hh = F == 2 ? c_aa2 : c_aa4;
+    double win[RR];
+#pragma unroll
+    for (int r = 0; r < RR; r++) { win[r] = zp[pz(GDG_ZH + i0 + r)]; acc[r] = 0.0; }
+#pragma unroll
+    for (int q = 0; q < GDG_FIR_Q; q++) {
+        const double hq = hh[F * q + P];
+#pragma unroll
+        for (int r = 0; r < RR; r++) acc[r] += hq * win[r];
+        if (q + 1 < GDG_FIR_Q) {
+#pragma unroll
+            for (int r = RR - 1; r > 0; r--) win[r] = win[r - 1];
+            win[0] = zp[pz(GDG_ZH + i0 - (q + 1))];
+        }
+    }
+}
+
+template <int F>
+GDG_DEV void oversampled_tiles(gdg_ctx &cx, const gdg_unit_desc &d)
+{
+    constexpr int RR = 2 * F;                   /* outputs per thread: (T/RR) * F threads cover the tile */
+    const int n = cx.n, type = d.type;
+    double *x = SM_CUR(cx), *y = SM_ALT(cx), *z = SM_S, *st = d.st;
+    double *uph = st + (F == 2 ? GDG_OS_ST_UP2 : GDG_OS_ST_UP4);
+    double *zh = st + (F == 2 ? GDG_OS_ST_Z2 : GDG_OS_ST_Z4);
+    double *part = z + F * GDG_ZPS;             /* partial sums of phases 1..F-1: (F-1) * GDG_OS_TILE */
+    const int T = imin(n, GDG_OS_TILE);
+    /* carried oversampled history: per phase GDG_ZH + 1 samples */
+    GDG_THREADS_BEGIN
+        for (int q = tid; q < F * (GDG_ZH + 1); q += GDG_NT) { const int p = q / (GDG_ZH + 1), m = q - p * (GDG_ZH + 1); z[p * GDG_ZPS + pz(m)] = zh[q]; }
+    GDG_THREADS_END
+    for (int t0 = 0; t0 < n; t0 += T) {
+        const int Tt = imin(T, n - t0);
+        /* up-sample (+ stateless nonlinearity) */
+        GDG_THREADS_BEGIN
+            for (int jl = tid; jl < Tt; jl += GDG_NT) {
+                const int j = t0 + jl;
+                double xs[6];
+#pragma unroll
+                for (int q = 0; q < 6; q++) { const int idx = j - 6 + q; xs[q] = idx >= 0 ? x[sw(idx)] : uph[8 + idx]; }
+#pragma unroll
+                for (int ph = 0; ph < F; ph++) {
+                    double u;
+                    if (ph == 0) u = xs[2];                                   /* in[j-4] */
+                    else {
+                        u = 0.0;
+#pragma unroll
+                        for (int q = 0; q < 6; q++) u += xs[q] * (F == 2 ? c_lz2[0][q] : c_lz4[ph - 1][q]);
+                    }
+                    if (type != GDG_UNIT_FUZZ) u = nl_pointwise(type, d, u);
+                    z[zloc(F, jl, ph)] = u;
+                }
+            }
+        GDG_THREADS_END
+        if (type == GDG_UNIT_FUZZ) fuzz_run(cx, d, z, F * Tt, F);
+        /* polyphase FIR partial sums: warp-uniform phase */
+        GDG_THREADS_BEGIN
+            const int warp = tid >> 5, p = warp % F;
+            const int grp = (warp / F) * 32 + (tid & 31);                     /* output group of this thread */
+            const int i0 = grp * RR;
+            if (i0 < Tt) {
+                double acc[RR];
+                const double *zp = z + p * GDG_ZPS;
+                if (F == 2) { if (p == 0) fir_branch<F, 0, RR>(zp, i0, acc); else fir_branch<F, 1, RR>(zp, i0, acc); }
+                else {
+                    if (p == 0) fir_branch<F, 0, RR>(zp, i0, acc);
+                    else if (p == 1) fir_branch<F, 1 % F, RR>(zp, i0, acc);
+                    else if (p == 2) fir_branch<F, 2 % F, RR>(zp, i0, acc);
+                    else fir_branch<F, 3 % F, RR>(zp, i0, acc);
+                }
+#pragma unroll
+                for (int r = 0; r < RR; r++)
+                    if (i0 + r < Tt) { if (p == 0) y[sw(t0 + i0 + r)] = acc[r]; else part[(p - 1) * GDG_OS_TILE + i0 + r] = acc[r]; }
+            }
+        GDG_THREADS_END
+        /* combine in phase order, clamp, -0.5 dB; stage the halo for the next tile */
+        GDG_THREADS_BEGIN
+            for (int i = tid; i < Tt; i += GDG_NT) {
+                double acc = y[sw(t0 + i)];
+#pragma unroll
+                for (int p = 1; p < F; p++) acc += part[(p - 1) * GDG_OS_TILE + i];
+                y[sw(t0 + i)] = 0.9440608762859234 * clamp1(acc);
+            }
+            for (int q = tid; q < F * (GDG_ZH + 1); q += GDG_NT) {
+                const int p = q / (GDG_ZH + 1), m = q - p * (GDG_ZH + 1);
+                SM_SCANB[q] = z[p * GDG_ZPS + pz(m + Tt)];
+            }
+        GDG_THREADS_END
+        GDG_THREADS_BEGIN
+            for (int q = tid; q < F * (GDG_ZH + 1); q += GDG_NT) { const int p = q / (GDG_ZH + 1), m = q - p * (GDG_ZH + 1); z[p * GDG_ZPS + pz(m)] = SM_SCANB[q]; }
+        GDG_THREADS_END
+    }
+    /* carry: oversampled history and the last 8 inputs (oversampling.go:91-93) */
+    GDG_THREADS_BEGIN
+        for (int q = tid; q < F * (GDG_ZH + 1); q += GDG_NT) { const int p = q / (GDG_ZH + 1), m = q - p * (GDG_ZH + 1); zh[q] = z[p * GDG_ZPS + pz(m)]; }
+        if (tid < 8) SM_MISC[8 + tid] = (n - 8 + tid) >= 0 ? x[sw(n - 8 + tid)] : uph[tid + n];
+    GDG_THREADS_END
+    GDG_THREADS_BEGIN
+        if (tid < 8) uph[tid] = SM_MISC[8 + tid];
+    GDG_THREADS_END
+    swap_bufs(cx);
 }
 
 GDG_DEV void stage_oversampled(gdg_ctx &cx, const gdg_unit_desc &d)
 {
     const int n = cx.n, f = d.i[0], type = d.type;
-    double *x = cx.cur, *st = d.st;
+    double *x = SM_CUR(cx);
     if (f <= 1) {
-        if (type == GDG_UNIT_FUZZ) { fuzz_run(cx, d, x, 0, n, 0); return; }
+        if (type == GDG_UNIT_FUZZ) { fuzz_run(cx, d, x, n, 1); return; }
         GDG_THREADS_BEGIN
             for (int k = tid; k < n; k += GDG_NT) x[sw(k)] = nl_pointwise(type, d, x[sw(k)]);
         GDG_THREADS_END
         return;
     }
-    const int L = f == 2 ? 77 : 155;
-    const double *h = f == 2 ? c_aa2 : c_aa4;
-    double *uph = st + (f == 2 ? GDG_OS_ST_UP2 : GDG_OS_ST_UP4);
-    double *zh = st + (f == 2 ? GDG_OS_ST_Z2 : GDG_OS_ST_Z4);
-    double *y = cx.alt, *z = cx.S;
-    const int T = imin(n, GDG_OS_TILE);
-    /* load the z history into the halo: logical q in [GDG_ZHALO-(L-1), GDG_ZHALO) */
-    GDG_THREADS_BEGIN
-        if (tid < GDG_ZHALO) z[zp(tid)] = tid >= GDG_ZHALO - (L - 1) ? zh[tid - (GDG_ZHALO - (L - 1))] : 0.0;
-    GDG_THREADS_END
-    for (int t0 = 0; t0 < n; t0 += T) {
-        const int Tt = imin(T, n - t0), cnt = f * Tt;
-        /* up-sample (+ stateless nonlinearity) */
-        GDG_THREADS_BEGIN
-            for (int m = tid; m < cnt; m += GDG_NT) {
-                const int M = f * t0 + m, jj = M / f, p = M - jj * f;
-                double u;
-                if (p == 0) {
-                    const int idx = jj - 4;
-                    u = idx >= 0 ? x[sw(idx)] : uph[8 + idx];
-                } else {
-                    const double *w = f == 2 ? c_lz2[0] : c_lz4[p - 1];
-                    u = 0.0;
-                    for (int q = 0; q < 6; q++) {
-                        const int idx = jj - 6 + q;
-                        const double s = idx >= 0 ? x[sw(idx)] : uph[8 + idx];
-                        u += s * w[q];
-                    }
-                }
-                if (type != GDG_UNIT_FUZZ) u = nl_pointwise(type, d, u);
-                z[zp(GDG_ZHALO + m)] = u;
-            }
-        GDG_THREADS_END
-        if (type == GDG_UNIT_FUZZ) fuzz_run(cx, d, z, GDG_ZHALO, cnt, 1);
-        /* decimate: two adjacent outputs per thread share one pass over the z window */
-        GDG_THREADS_BEGIN
-            for (int i = 2 * tid; i < Tt; i += 2 * GDG_NT) {
-                const int two = (i + 1 < Tt);
-                const int qtop = GDG_ZHALO + f * (i + 1);           /* newest sample used by output i+1 */
-                double acc0 = 0.0, acc1 = 0.0;
-                for (int k = 0; k < L + f; k++) {
-                    const int q = qtop - k;
-                    const double zv = (two || k >= f) ? z[zp(q)] : 0.0;
-                    if (k < L) acc1 += h[k] * zv;
-                    if (k >= f) acc0 += h[k - f] * zv;
-                }
-                y[sw(t0 + i)] = 0.9440608762859234 * clamp1(acc0);
-                if (two) y[sw(t0 + i + 1)] = 0.9440608762859234 * clamp1(acc1);
-            }
-        GDG_THREADS_END
-        /* slide the window: halo <- last GDG_ZHALO samples (through scanB as staging) */
-        GDG_THREADS_BEGIN
-            if (tid < GDG_ZHALO) cx.scanB[tid] = z[zp(tid + cnt)];
-        GDG_THREADS_END
-        GDG_THREADS_BEGIN
-            if (tid < GDG_ZHALO) z[zp(tid)] = cx.scanB[tid];
-        GDG_THREADS_END
-    }
-    /* carry: z history and the last 8 inputs (oversampling.go:91-93) */
-    GDG_THREADS_BEGIN
-        if (tid < L - 1) zh[tid] = z[zp(GDG_ZHALO - (L - 1) + tid)];
-        if (tid < 8) cx.misc[8 + tid] = (n - 8 + tid) >= 0 ? x[sw(n - 8 + tid)] : uph[tid + n];
-    GDG_THREADS_END
-    GDG_THREADS_BEGIN
-        if (tid < 8) uph[tid] = cx.misc[8 + tid];
-    GDG_THREADS_END
-    swap_bufs(cx);
+    if (f == 2) oversampled_tiles<2>(cx, d); else oversampled_tiles<4>(cx, d);
 }
 
 /* ==========================================================================
@@ -193,20 +244,22 @@ GDG_DEV void stage_octaver(gdg_ctx &cx, const gdg_unit_desc &d)
 {
     const int n = cx.n, S = chunk_len(n), mode = d.i[0];
     const double dinv = d.p[0], dd = d.p[1], fUp = d.p[2], fClean = d.p[3], fDist = d.p[4], fD1 = d.p[5], fD2 = d.p[6], fH = d.p[7];
-    double *x = cx.cur, *st = d.st;
-    double *envc = cx.S, *first = cx.S + GDG_NT, *last = cx.S + 2 * GDG_NT, *flips = cx.S + 3 * GDG_NT,
-           *polin = cx.S + 4 * GDG_NT, *regin = cx.S + 5 * GDG_NT;
+    double *x = SM_CUR(cx), *st = d.st;
+    double *first = SM_S + GDG_NT, *last = SM_S + 2 * GDG_NT, *flips = SM_S + 3 * GDG_NT,
+           *polin = SM_S + 4 * GDG_NT, *regin = SM_S + 5 * GDG_NT;
+    const double astep = follow_A(mode, dinv, dd), afull = pow_int(astep, S), cstep = 1.0 - dd, cfull = pow_int(cstep, S);
+    const double inite[1] = {st[2]}, initc[1] = {st[3]};
+    GDG_REGA(double, a, 1); GDG_REGA(double, b, 1); GDG_REGA(double, ein, 1); GDG_REGA(double, cin, 1);
     GDG_THREADS_BEGIN
         const int k0 = tid * S, k1 = imin(n, k0 + S);
         double e = 0.0;
         for (int k = k0; k < k1; k++) e = follow_step(mode, e, fabs(x[sw(k)]), dinv, dd);
-        cx.scanB[tid] = e;
-    GDG_THREADS_END
-    { gdg_scan_par sp; scan_par_const(sp, 0, follow_A(mode, dinv, dd), n, S, st[2]); block_scan(cx, 1, mode == GDG_FOLLOW_ENVELOPE, 0, sp, n, S); }
+        R(a)[0] = k0 < n ? chunk_A(astep, k1 - k0, S, afull) : 1.0; R(b)[0] = k0 < n ? e : 0.0;
+    GDG_THREADS_END_NOSYNC
+    GDG_SCAN(1, cx, mode == GDG_FOLLOW_ENVELOPE, a, b, inite, ein);
     GDG_THREADS_BEGIN
         const int k0 = tid * S, k1 = imin(n, k0 + S);
-        double e = cx.scanB[tid], fs = 0.0, ls = 0.0, fl = 0.0;
-        envc[tid] = e;
+        double e = R(ein)[0], fs = 0.0, ls = 0.0, fl = 0.0;
         for (int k = k0; k < k1; k++) {
             const double s = x[sw(k)], sa = fabs(s);
             e = follow_step(mode, e, sa, dinv, dd);
@@ -217,7 +270,7 @@ GDG_DEV void stage_octaver(gdg_ctx &cx, const gdg_unit_desc &d)
             }
         }
         first[tid] = fs; last[tid] = ls; flips[tid] = fl;
-        if (k0 < n && k1 == n) cx.misc[0] = e;
+        if (k0 < n && k1 == n) SM_MISC[0] = e;
     GDG_THREADS_END
     GDG_THREADS_BEGIN
         if (tid == 0) {                                /* serial combine over the chunk summaries */
@@ -231,13 +284,13 @@ GDG_DEV void stage_octaver(gdg_ctx &cx, const gdg_unit_desc &d)
                     pol = last[t];
                 }
             }
-            cx.misc[1] = pol; cx.misc[2] = (double)(reg & 7);
+            SM_MISC[1] = pol; SM_MISC[2] = (double)(reg & 7);
         }
     GDG_THREADS_END
     /* pre-coupling signal -> alt, coupling zero-state response */
     GDG_THREADS_BEGIN
         const int k0 = tid * S, k1 = imin(n, k0 + S);
-        double e = envc[tid], pol = polin[tid], c = 0.0;
+        double e = R(ein)[0], pol = polin[tid], c = 0.0;
         long long reg = (long long)regin[tid];
         for (int k = k0; k < k1; k++) {
             const double s = x[sw(k)], sa = fabs(s);
@@ -250,22 +303,22 @@ GDG_DEV void stage_octaver(gdg_ctx &cx, const gdg_unit_desc &d)
             pre += fDist * (sign * e);
             pre += fD1 * (fd * e);
             pre += fD2 * (sd * e);
-            cx.alt[sw(k)] = pre;
+            SM_ALT(cx)[sw(k)] = pre;
             c += (pre - c) * dd;
         }
-        cx.scanB[tid] = c;
-    GDG_THREADS_END
-    { gdg_scan_par sp; scan_par_const(sp, 0, 1.0 - dd, n, S, st[3]); block_scan(cx, 1, 0, 0, sp, n, S); }
+        R(a)[0] = k0 < n ? chunk_A(cstep, k1 - k0, S, cfull) : 1.0; R(b)[0] = k0 < n ? c : 0.0;
+    GDG_THREADS_END_NOSYNC
+    GDG_SCAN(1, cx, 0, a, b, initc, cin);
     GDG_THREADS_BEGIN
         const int k0 = tid * S, k1 = imin(n, k0 + S);
-        double c = cx.scanB[tid];
+        double c = R(cin)[0];
         for (int k = k0; k < k1; k++) {
-            double pre = cx.alt[sw(k)];
+            double pre = SM_ALT(cx)[sw(k)];
             c += (pre - c) * dd;
             pre -= c;
             x[sw(k)] = clamp1(pre);
         }
-        if (k0 < n && k1 == n) { st[0] = cx.misc[1]; st_seti(st, 1, (long long)cx.misc[2]); st[2] = cx.misc[0]; st[3] = c; }
+        if (k0 < n && k1 == n) { st[0] = SM_MISC[1]; st_seti(st, 1, (long long)SM_MISC[2]); st[2] = SM_MISC[0]; st[3] = c; }
     GDG_THREADS_END
 }
 
@@ -280,17 +333,21 @@ GDG_DEV void stage_autowah(gdg_ctx &cx, const gdg_unit_desc &d)
 {
     const int n = cx.n, S = chunk_len(n), mode = d.i[0];
     const double dinv = d.p[0], dd = d.p[1];
-    double *x = cx.cur, *kv = cx.alt, *st = d.st;
+    double *x = SM_CUR(cx), *kv = SM_ALT(cx), *st = d.st;
+    const double astep = follow_A(mode, dinv, dd), afull = pow_int(astep, S);
+    const double inite[1] = {st[0]};
+    GDG_REGA(double, a, 1); GDG_REGA(double, b, 1); GDG_REGA(double, ein, 1); GDG_REGA(double, hin, 1); GDG_REGA(double, lin, 1);
+    GDG_REG(double, aprod);
     GDG_THREADS_BEGIN
         const int k0 = tid * S, k1 = imin(n, k0 + S);
         double e = 0.0;
         for (int k = k0; k < k1; k++) e = follow_step(mode, e, fabs(x[sw(k)]), dinv, dd);
-        cx.scanB[tid] = e;
-    GDG_THREADS_END
-    { gdg_scan_par sp; scan_par_const(sp, 0, follow_A(mode, dinv, dd), n, S, st[0]); block_scan(cx, 1, mode == GDG_FOLLOW_ENVELOPE, 0, sp, n, S); }
+        R(a)[0] = k0 < n ? chunk_A(astep, k1 - k0, S, afull) : 1.0; R(b)[0] = k0 < n ? e : 0.0;
+    GDG_THREADS_END_NOSYNC
+    GDG_SCAN(1, cx, mode == GDG_FOLLOW_ENVELOPE, a, b, inite, ein);
     GDG_THREADS_BEGIN
         const int k0 = tid * S, k1 = imin(n, k0 + S);
-        double e = cx.scanB[tid];
+        double e = R(ein)[0], ap = 1.0;
         for (int k = k0; k < k1; k++) {
             e = follow_step(mode, e, fabs(x[sw(k)]), dinv, dd);
             const double level = 20.0 * log10(e);
@@ -298,23 +355,25 @@ GDG_DEV void stage_autowah(gdg_ctx &cx, const gdg_unit_desc &d)
             if (level <= d.p[2]) freq = d.p[4];
             else if (level >= d.p[3]) freq = d.p[5];
             else freq = d.p[4] + (d.p[6] * (level - d.p[2]));
-            kv[sw(k)] = 1.0 - exp(-freq / d.p[7]);
+            const double kk = 1.0 - exp(-freq / d.p[7]);
+            kv[sw(k)] = kk;
+            ap *= (1.0 - kk);
         }
-        if (k0 < n && k1 == n) cx.misc[0] = e;
-    GDG_THREADS_END
+        R(aprod) = ap;                                  /* product of (1 - k) over the chunk: the A of every section */
+        if (k0 < n && k1 == n) st[0] = e;
+    GDG_THREADS_END_NOSYNC
     for (int j = 0; j < 8; j++) {
-        /* HP zero-state + chunk coefficient product */
+        const double inith[1] = {st[1 + j]}, initl[1] = {st[9 + j]};
         GDG_THREADS_BEGIN
             const int k0 = tid * S, k1 = imin(n, k0 + S);
-            double h = 0.0, a = 1.0;
-            for (int k = k0; k < k1; k++) { const double kk = kv[sw(k)]; h += (x[sw(k)] - h) * kk; a *= (1.0 - kk); }
-            cx.scanB[tid] = h; cx.scanA[tid] = a;
-        GDG_THREADS_END
-        { gdg_scan_par sp; sp.init[0] = st[1 + j]; sp.a_full[0] = sp.a_last[0] = 1.0; block_scan(cx, 1, 0, 1, sp, n, S); }
+            double h = 0.0;
+            for (int k = k0; k < k1; k++) h += (x[sw(k)] - h) * kv[sw(k)];
+            R(a)[0] = R(aprod); R(b)[0] = h;
+        GDG_THREADS_END_NOSYNC
+        GDG_SCAN(1, cx, 0, a, b, inith, hin);
         GDG_THREADS_BEGIN
             const int k0 = tid * S, k1 = imin(n, k0 + S);
-            double h = cx.scanB[tid], l = 0.0;
-            cx.S[tid] = h;
+            double h = R(hin)[0], l = 0.0;
             for (int k = k0; k < k1; k++) {
                 const double kk = kv[sw(k)];
                 double diff = x[sw(k)] - h;
@@ -322,12 +381,12 @@ GDG_DEV void stage_autowah(gdg_ctx &cx, const gdg_unit_desc &d)
                 diff -= l;
                 l += diff * kk;
             }
-            cx.scanB[tid] = l;                       /* scanA still holds prod(1-k) of the chunk */
-        GDG_THREADS_END
-        { gdg_scan_par sp; sp.init[0] = st[9 + j]; sp.a_full[0] = sp.a_last[0] = 1.0; block_scan(cx, 1, 0, 1, sp, n, S); }
+            R(a)[0] = R(aprod); R(b)[0] = l;
+        GDG_THREADS_END_NOSYNC
+        GDG_SCAN(1, cx, 0, a, b, initl, lin);
         GDG_THREADS_BEGIN
             const int k0 = tid * S, k1 = imin(n, k0 + S);
-            double h = cx.S[tid], l = cx.scanB[tid];
+            double h = R(hin)[0], l = R(lin)[0];
             for (int k = k0; k < k1; k++) {
                 const double kk = kv[sw(k)];
                 double diff = x[sw(k)] - h;
@@ -336,9 +395,11 @@ GDG_DEV void stage_autowah(gdg_ctx &cx, const gdg_unit_desc &d)
                 l += diff * kk;
                 x[sw(k)] = (j == 7) ? clamp1(d.p[8] * l) : l;
             }
-            if (k0 < n && k1 == n) { st[1 + j] = h; st[9 + j] = l; if (j == 7) st[0] = cx.misc[0]; }
-        GDG_THREADS_END
+            if (k0 < n && k1 == n) { st[1 + j] = h; st[9 + j] = l; }
+        GDG_THREADS_END_NOSYNC
     }
+    GDG_THREADS_BEGIN
+    GDG_THREADS_END
 }
 
 /* ==========================================================================
@@ -352,7 +413,7 @@ GDG_DEV void stage_autowah(gdg_ctx &cx, const gdg_unit_desc &d)
 GDG_DEV void stage_reverb(gdg_ctx &cx, const gdg_unit_desc &d)
 {
     const int n = cx.n, hs = d.i[0];
-    double *x = cx.cur, *line = cx.alt, *w = cx.S, *st = d.st;
+    double *x = SM_CUR(cx), *line = SM_ALT(cx), *w = SM_S, *st = d.st;
     double *lring = st + GDG_RV_ST_DATA;
     const double g = d.p[6];
     GDG_THREADS_BEGIN
@@ -485,7 +546,7 @@ GDG_DEV void fft_dit_inv(gdg_ctx &cx, double *R, const double *tw, int M, int lo
 GDG_DEV void stage_poweramp(gdg_ctx &cx, const gdg_unit_desc &d, const double *tw)
 {
     const int n = cx.n, L = d.i[0];
-    double *x = cx.cur;
+    double *x = SM_CUR(cx);
     if (L <= 0) {                                              /* filter.go:366-367 / poweramp.go:210-214 */
         GDG_THREADS_BEGIN
             for (int k = tid; k < n; k += GDG_NT) x[sw(k)] = 0.0;
@@ -495,7 +556,7 @@ GDG_DEV void stage_poweramp(gdg_ctx &cx, const gdg_unit_desc &d, const double *t
     const int F = d.i[1], M = F / 2, logM = d.i[2], B = M;       /* B samples per block = M complex points * ... */
     const int nb = n <= B ? 1 : n / B;                           /* n and B are powers of two */
     const int ns = n <= B ? n : B;                               /* samples per block */
-    double *R = cx.R, *S = cx.S, *tail = d.st;
+    double *R = SM_R, *S = SM_S, *tail = d.st;
     const double *H = d.aux;
     /* stage the block in plain layout, then spread: block j -> R[j*F .. j*F + ns), zero padded to F */
     GDG_THREADS_BEGIN
@@ -573,9 +634,9 @@ GDG_DEV void stage_poweramp(gdg_ctx &cx, const gdg_unit_desc &d, const double *t
     GDG_THREADS_BEGIN
         for (int q = tid; q < F; q += GDG_NT) tail[q] = q < F - ns ? R[(nb - 1) * F + ns + q] : 0.0;
     GDG_THREADS_END
-    cx.cur = R; cx.alt = R + GDG_MAX_N;
+    cx.cur_off = GDG_SMEM_R; cx.alt_off = GDG_SMEM_R + GDG_MAX_N;
     GDG_THREADS_BEGIN
-        for (int k = tid; k < n; k += GDG_NT) cx.cur[sw(k)] = S[k];
+        for (int k = tid; k < n; k += GDG_NT) SM_CUR(cx)[sw(k)] = S[k];
     GDG_THREADS_END
 }
 
