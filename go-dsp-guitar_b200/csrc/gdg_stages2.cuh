@@ -504,43 +504,147 @@ GDG_DEVI int brev(int v, int bits)
     return bits ? (int)(r >> (32 - bits)) : 0;
 }
 
-/* forward: decimation in frequency, natural in -> bit-reversed out; nseg transforms of M complex points */
-GDG_DEV void fft_dif(gdg_ctx &cx, double *R, const double *tw, int M, int logM, int nseg)
+/* complex storage swizzle (16-byte units): every pass - unit stride, stride 8, large strides - touches each
+ * 128-byte bank row at most 4 times per warp, the minimum for 32 x 16 B */
+GDG_DEVI int cz(int i) { return i ^ ((i >> 3) & 7); }
+
+/* W_16^idx times a (idx compile-time after unrolling); conj selects conj(W) */
+GDG_DEVI gdg_c2 mul_w16(gdg_c2 a, int idx, int conj)
 {
-    (void)logM;
-    const int total = nseg * (M / 2);
-    for (int h = M / 2; h >= 1; h >>= 1) {
-        const int tstep = (GDG_MAX_FFT / 2) / h;              /* W_{2h}^pos = tw[pos * MAXFFT/(2h)] */
-        GDG_THREADS_BEGIN
-            for (int b = tid; b < total; b += GDG_NT) {
-                const int seg = b / (M / 2), r = b - seg * (M / 2);
-                const int grp = r / h, pos = r - grp * h;
-                const int i0 = seg * M + grp * 2 * h + pos, i1 = i0 + h;
-                const gdg_c2 a = cld(R, i0), c = cld(R, i1);
-                cst(R, i0, cadd(a, c));
-                cst(R, i1, cmul(csub(a, c), twd(tw, pos * tstep)));
-            }
-        GDG_THREADS_END
+    const double h = 0.70710678118654752440;
+    gdg_c2 r;
+    switch (idx) {
+    case 0: return a;
+    case 4: if (!conj) { r.re = a.im; r.im = -a.re; } else { r.re = -a.im; r.im = a.re; } return r;
+    case 2: if (!conj) { r.re = h * (a.re + a.im); r.im = h * (a.im - a.re); } else { r.re = h * (a.re - a.im); r.im = h * (a.im + a.re); } return r;
+    case 6: if (!conj) { r.re = h * (a.im - a.re); r.im = -h * (a.re + a.im); } else { r.re = -h * (a.re + a.im); r.im = h * (a.re - a.im); } return r;
+    default: {
+        /* cos/sin(pi/8), cos/sin(3pi/8): W_16^1 = (c1,-s1), W_16^3 = (s1,-c1), W_16^5 = (-s1,-c1), W_16^7 = (-c1,-s1) */
+        const double c1 = 0.92387953251128675613, s1 = 0.38268343236508977173;
+        gdg_c2 w;
+        w.re = idx == 1 ? c1 : (idx == 3 ? s1 : (idx == 5 ? -s1 : -c1));
+        w.im = idx == 1 ? -s1 : (idx == 3 ? -c1 : (idx == 5 ? -c1 : -s1));
+        if (conj) w.im = -w.im;
+        return cmul(a, w); }
     }
 }
-/* inverse: decimation in time, bit-reversed in -> natural out (unnormalised, conjugate twiddles) */
-GDG_DEV void fft_dit_inv(gdg_ctx &cx, double *R, const double *tw, int M, int logM, int nseg)
+/* in-register radix-2 networks over RR points */
+template <int RR>
+GDG_DEVI void dif_net(gdg_c2 (&v)[RR])
 {
-    (void)logM;
-    const int total = nseg * (M / 2);
-    for (int h = 1; h <= M / 2; h <<= 1) {
-        const int tstep = (GDG_MAX_FFT / 2) / h;
-        GDG_THREADS_BEGIN
-            for (int b = tid; b < total; b += GDG_NT) {
-                const int seg = b / (M / 2), r = b - seg * (M / 2);
-                const int grp = r / h, pos = r - grp * h;
-                const int i0 = seg * M + grp * 2 * h + pos, i1 = i0 + h;
-                const gdg_c2 a = cld(R, i0), t = cmul(cld(R, i1), cconj(twd(tw, pos * tstep)));
-                cst(R, i0, cadd(a, t));
-                cst(R, i1, csub(a, t));
+#pragma unroll
+    for (int half = RR / 2; half >= 1; half >>= 1)
+#pragma unroll
+        for (int g = 0; g < RR; g += 2 * half)
+#pragma unroll
+            for (int pos = 0; pos < half; pos++) {
+                const gdg_c2 a = v[g + pos], c = v[g + pos + half];
+                v[g + pos] = cadd(a, c);
+                v[g + pos + half] = mul_w16(csub(a, c), pos * (8 / half), 0);
             }
-        GDG_THREADS_END
+}
+template <int RR>
+GDG_DEVI void dit_net_inv(gdg_c2 (&v)[RR])
+{
+#pragma unroll
+    for (int half = 1; half <= RR / 2; half <<= 1)
+#pragma unroll
+        for (int g = 0; g < RR; g += 2 * half)
+#pragma unroll
+            for (int pos = 0; pos < half; pos++) {
+                const gdg_c2 a = v[g + pos], t = mul_w16(v[g + pos + half], pos * (8 / half), 1);
+                v[g + pos] = cadd(a, t);
+                v[g + pos + half] = csub(a, t);
+            }
+}
+GDG_DEVI gdg_c2 tw_full(const double *tw, int idx)          /* exp(-2 pi i idx / GDG_MAX_FFT), idx in [0, GDG_MAX_FFT) */
+{
+    gdg_c2 r;
+    if (idx >= GDG_MAX_FFT / 2) { r = twd(tw, idx - GDG_MAX_FFT / 2); r.re = -r.re; r.im = -r.im; }
+    else r = twd(tw, idx);
+    return r;
+}
+template <int RR> GDG_DEVI int brev_small(int k)
+{
+    int r = 0;
+#pragma unroll
+    for (int bit = 1, rb = RR >> 1; bit < RR; bit <<= 1, rb >>= 1) if (k & bit) r |= rb;
+    return r;
+}
+/* powers w^1 .. w^(RR-1) with multiplication depth <= log2(RR) */
+template <int RR>
+GDG_DEVI void tw_powers(gdg_c2 w1, gdg_c2 (&pw)[RR])
+{
+    pw[0].re = 1.0; pw[0].im = 0.0; pw[1] = w1;
+#pragma unroll
+    for (int q = 2; q < RR; q++) {
+        const int hb = q >= 8 ? 8 : (q >= 4 ? 4 : 2);       /* highest power of two <= q */
+        pw[q] = (q == hb) ? cmul(pw[hb / 2], pw[hb / 2]) : cmul(pw[hb], pw[q - hb]);
     }
+}
+
+/* One radix-RR pass of span L = 2^logL over nseg transforms of M = 2^logM complex points held (swizzled) in D.
+ * Forward (inverse == 0): decimation in frequency: RR-point DFT of the points j + k L/RR, then slot k (which
+ * holds output brev(k)) times W_L^(j brev(k)); natural in -> bit-reversed out over all passes.
+ * Inverse: the mirror image with conjugate twiddles (bit-reversed in -> natural out), unnormalised. */
+template <int RR>
+GDG_DEV void fft_pass(double *D, const double *tw, int logM, int nseg, int logL, int inverse)
+{
+    constexpr int LOGR = RR == 16 ? 4 : (RR == 8 ? 3 : (RR == 4 ? 2 : 1));
+    const int logS = logL - LOGR;                              /* stride L/RR */
+    const int nb = nseg << (logM - LOGR);
+    const int tshift = 14 - logL;                              /* W_L^e = tw[e << tshift], GDG_MAX_FFT = 2^14 */
+    GDG_THREADS_BEGIN
+        for (int b = tid; b < nb; b += GDG_NT) {
+            const int seg = b >> (logM - LOGR), rb = b & ((1 << (logM - LOGR)) - 1);
+            const int blk = rb >> logS, j = rb & ((1 << logS) - 1);
+            const int base = (seg << logM) + (blk << logL) + j;
+            gdg_c2 v[RR], pw[RR];
+#pragma unroll
+            for (int k = 0; k < RR; k++) v[k] = cld(D, cz(base + (k << logS)));
+            gdg_c2 w1 = tw_full(tw, j << tshift);
+            if (inverse) w1.im = -w1.im;
+            tw_powers<RR>(w1, pw);
+            if (!inverse) {
+                dif_net<RR>(v);
+#pragma unroll
+                for (int k = 1; k < RR; k++) v[k] = cmul(v[k], pw[brev_small<RR>(k)]);
+            } else {
+#pragma unroll
+                for (int k = 1; k < RR; k++) v[k] = cmul(v[k], pw[brev_small<RR>(k)]);
+                dit_net_inv<RR>(v);
+            }
+#pragma unroll
+            for (int k = 0; k < RR; k++) cst(D, cz(base + (k << logS)), v[k]);
+        }
+    GDG_THREADS_END
+}
+GDG_DEVI void fft_pass_any(double *D, const double *tw, int logM, int nseg, int logL, int r, int inverse, gdg_ctx &cx)
+{
+    (void)cx;
+    if (r == 4) fft_pass<16>(D, tw, logM, nseg, logL, inverse);
+    else if (r == 3) fft_pass<8>(D, tw, logM, nseg, logL, inverse);
+    else if (r == 2) fft_pass<4>(D, tw, logM, nseg, logL, inverse);
+    else fft_pass<2>(D, tw, logM, nseg, logL, inverse);
+}
+/* radix plan: ceil(logM / 4) passes of radix 16 / 8 / 4 / 2, the larger radices first (13 -> 4+3+3+3, 12 -> 4+4+4) */
+GDG_DEVI int fft_plan(int logM, int (&r)[8])
+{
+    const int np = (logM + 3) / 4;
+    for (int i = 0; i < np; i++) r[i] = logM / np + (i < logM % np ? 1 : 0);
+    return np;
+}
+GDG_DEV void fft_forward(gdg_ctx &cx, double *D, const double *tw, int logM, int nseg)
+{
+    int r[8]; const int np = fft_plan(logM, r);
+    int logL = logM;
+    for (int i = 0; i < np; i++) { fft_pass_any(D, tw, logM, nseg, logL, r[i], 0, cx); logL -= r[i]; }
+}
+GDG_DEV void fft_inverse(gdg_ctx &cx, double *D, const double *tw, int logM, int nseg)
+{
+    int r[8]; const int np = fft_plan(logM, r);
+    int logL = 0;
+    for (int i = np - 1; i >= 0; i--) { logL += r[i]; fft_pass_any(D, tw, logM, nseg, logL, r[i], 1, cx); }
 }
 
 GDG_DEV void stage_poweramp(gdg_ctx &cx, const gdg_unit_desc &d, const double *tw)
@@ -553,91 +657,104 @@ GDG_DEV void stage_poweramp(gdg_ctx &cx, const gdg_unit_desc &d, const double *t
         GDG_THREADS_END
         return;
     }
-    const int F = d.i[1], M = F / 2, logM = d.i[2], B = M;       /* B samples per block = M complex points * ... */
+    const int F = d.i[1], M = F / 2, logM = d.i[2], B = M;
     const int nb = n <= B ? 1 : n / B;                           /* n and B are powers of two */
     const int ns = n <= B ? n : B;                               /* samples per block */
-    double *R = SM_R, *S = SM_S, *tail = d.st;
+    const int total = nb * M;                                    /* complex points in flight (<= GDG_MAX_N) */
+    const int per = (total + GDG_NT - 1) / GDG_NT;               /* <= 16 */
+    double *D = SM_R, *tail = d.st;
     const double *H = d.aux;
-    /* stage the block in plain layout, then spread: block j -> R[j*F .. j*F + ns), zero padded to F */
+    GDG_REGA(double, buf, 32);
+    /* pack: block j -> complex points (x[j ns + 2c], x[j ns + 2c + 1]), c < ns/2, zero padded to M; through
+     * registers because the destination overlays the source */
     GDG_THREADS_BEGIN
-        for (int k = tid; k < n; k += GDG_NT) S[k] = x[sw(k)];
-    GDG_THREADS_END
-    GDG_THREADS_BEGIN
-        for (int q = tid; q < nb * F; q += GDG_NT) {
-            const int j = q / F, r = q - j * F;
-            R[q] = r < ns ? S[j * ns + r] : 0.0;
+        for (int r = 0; r < per; r++) {
+            const int g = tid + r * GDG_NT;
+            double re = 0.0, im = 0.0;
+            if (g < total) {
+                const int j = g >> logM, c = g & (M - 1);
+                if (2 * c < ns) { re = x[sw(j * ns + 2 * c)]; im = (2 * c + 1 < ns) ? x[sw(j * ns + 2 * c + 1)] : 0.0; }
+            }
+            R(buf)[2 * r] = re; R(buf)[2 * r + 1] = im;
         }
     GDG_THREADS_END
-    fft_dif(cx, R, tw, M, logM, nb);
+    GDG_THREADS_BEGIN
+        for (int r = 0; r < per; r++) {
+            const int g = tid + r * GDG_NT;
+            if (g < total) { gdg_c2 v; v.re = R(buf)[2 * r]; v.im = R(buf)[2 * r + 1]; cst(D, cz(g), v); }
+        }
+    GDG_THREADS_END
+    fft_forward(cx, D, tw, logM, nb);
     /* split (fft.go:801-818) * H (filter.go:459) * inverse split (fft.go:899-955), on bit-reversed storage */
     const int fstep = GDG_MAX_FFT / F;                            /* W_F^k = tw[k * MAXFFT/F] */
     GDG_THREADS_BEGIN
         for (int b = tid; b < nb * (M / 2 + 1); b += GDG_NT) {
             const int seg = b / (M / 2 + 1), k = b - seg * (M / 2 + 1);
-            double *Z = R + seg * F;
+            const int zb = seg * M;
             if (k == 0) {
-                const gdg_c2 z0 = cld(Z, 0);
+                const gdg_c2 z0 = cld(D, cz(zb));
                 const double x0 = z0.re + z0.im, xm = z0.re - z0.im;     /* X[0], X[M] (real) */
                 const double y0 = x0 * GDG_LDG(H + 0), ym = xm * GDG_LDG(H + 2 * M);  /* real(dc), real(nyquist) of the product */
                 gdg_c2 o; o.re = 0.5 * (y0 + ym); o.im = 0.5 * (y0 - ym);
-                cst(Z, 0, o);
+                cst(D, cz(zb), o);
             } else {
                 const int k2 = M - k;
-                const int p1 = brev(k, logM), p2 = brev(k2, logM);
-                const gdg_c2 za = cld(Z, p1), zb = cld(Z, p2);
+                const int p1 = cz(zb + brev(k, logM)), p2 = cz(zb + brev(k2, logM));
+                const gdg_c2 za = cld(D, p1), zbv = cld(D, p2);
                 const gdg_c2 wk = twd(tw, k * fstep);
                 gdg_c2 jw; jw.re = -wk.im; jw.im = wk.re;                 /* j * W_F^k */
-                /* X[k] = 0.5((Za + conj Zb) - jW (Za - conj Zb));  X[M-k] = conj of the same with roles swapped */
-                const gdg_c2 s1 = cadd(za, cconj(zb)), d1 = csub(za, cconj(zb));
+                const gdg_c2 s1 = cadd(za, cconj(zbv)), d1 = csub(za, cconj(zbv));
                 const gdg_c2 t1 = cmul(jw, d1);
                 gdg_c2 xa; xa.re = 0.5 * (s1.re - t1.re); xa.im = 0.5 * (s1.im - t1.im);
-                /* W_F^{M-k} = -conj(W_F^k)  =>  j W_F^{M-k} = conj(jW) */
-                const gdg_c2 s2 = cadd(zb, cconj(za)), d2 = csub(zb, cconj(za));
-                const gdg_c2 t2 = cmul(cconj(jw), d2);
+                const gdg_c2 s2 = cadd(zbv, cconj(za)), d2 = csub(zbv, cconj(za));
+                const gdg_c2 t2 = cmul(cconj(jw), d2);                    /* j W_F^(M-k) = conj(j W_F^k) */
                 gdg_c2 xb; xb.re = 0.5 * (s2.re - t2.re); xb.im = 0.5 * (s2.im - t2.im);
                 gdg_c2 ha, hb; ha.re = GDG_LDG(H + 2 * k); ha.im = GDG_LDG(H + 2 * k + 1);
                 hb.re = GDG_LDG(H + 2 * k2); hb.im = GDG_LDG(H + 2 * k2 + 1);
                 const gdg_c2 ya = cmul(xa, ha), yb = cmul(xb, hb);
-                /* Z'[k] = 0.5((Ya + conj Yb) + j (Ya - conj Yb) conj(W_F^k)) */
                 const gdg_c2 e1 = cadd(ya, cconj(yb)), o1 = cmul(csub(ya, cconj(yb)), cconj(wk));
                 gdg_c2 ra; ra.re = 0.5 * (e1.re - o1.im); ra.im = 0.5 * (e1.im + o1.re);
-                gdg_c2 wk2; wk2.re = -wk.re; wk2.im = wk.im;               /* W_F^{M-k} */
+                gdg_c2 wk2; wk2.re = -wk.re; wk2.im = wk.im;               /* W_F^(M-k) */
                 const gdg_c2 e2 = cadd(yb, cconj(ya)), o2 = cmul(csub(yb, cconj(ya)), cconj(wk2));
                 gdg_c2 rb; rb.re = 0.5 * (e2.re - o2.im); rb.im = 0.5 * (e2.im + o2.re);
-                cst(Z, p1, ra);
-                if (p2 != p1) cst(Z, p2, rb);
+                cst(D, p1, ra);
+                if (p2 != p1) cst(D, p2, rb);
             }
         }
     GDG_THREADS_END
-    fft_dit_inv(cx, R, tw, M, logM, nb);
-    /* overlap-add, clamp, new tail */
+    fft_inverse(cx, D, tw, logM, nb);
+    /* real sample r of block j = component (r & 1) of complex point r >> 1 */
+#define GDG_YR(j, r) D[2 * cz((j) * M + ((r) >> 1)) + ((r) & 1)]
     const double scale = 1.0 / (double)M;
+    const int per_out = (n + GDG_NT - 1) / GDG_NT;               /* <= 16 */
+    /* overlap-add + clamp into registers; running tail staged in place (filter.go:473-503): for nb >= 2 the
+     * tail beyond ns is zero, so only the single-block case adds the old tail */
     GDG_THREADS_BEGIN
-        for (int k = tid; k < n; k += GDG_NT) {
-            const int j = k / ns, r = k - j * ns;
-            double pre = scale * R[j * F + r];
-            if (j == 0) pre += tail[r];
-            else { pre += scale * R[(j - 1) * F + ns + r]; if (j == 1) pre += tail[ns + r]; }
-            S[k] = clamp1(pre);
+        for (int r = 0; r < per_out; r++) {
+            const int k = tid + r * GDG_NT;
+            if (k < n) {
+                const int j = k / ns, q = k - j * ns;
+                double pre = scale * GDG_YR(j, q);
+                if (j == 0) pre += tail[q];
+                else { pre += scale * GDG_YR(j - 1, ns + q); if (j == 1) pre += tail[ns + q]; }
+                R(buf)[r] = clamp1(pre);
+            }
         }
-    GDG_THREADS_END
-    /* tail' = (y_last + tail_in)[ns:F] shifted to 0, then zeros (filter.go:494-503); for nb >= 2 the
-     * running tail beyond ns is zero, so only the single-block case adds the old tail.  Staged in R
-     * in place (each thread rewrites the cell it read) so no tail[] cell is read after being written. */
-    GDG_THREADS_BEGIN
         for (int q = tid; q < F - ns; q += GDG_NT) {
-            double v = scale * R[(nb - 1) * F + ns + q];
+            double v = scale * GDG_YR(nb - 1, ns + q);
             if (nb == 1) v += tail[ns + q];
-            R[(nb - 1) * F + ns + q] = v;
+            GDG_YR(nb - 1, ns + q) = v;
         }
-    GDG_THREADS_END
-    GDG_THREADS_BEGIN
-        for (int q = tid; q < F; q += GDG_NT) tail[q] = q < F - ns ? R[(nb - 1) * F + ns + q] : 0.0;
     GDG_THREADS_END
     cx.cur_off = GDG_SMEM_R; cx.alt_off = GDG_SMEM_R + GDG_MAX_N;
     GDG_THREADS_BEGIN
-        for (int k = tid; k < n; k += GDG_NT) SM_CUR(cx)[sw(k)] = S[k];
+        for (int q = tid; q < F; q += GDG_NT) tail[q] = q < F - ns ? GDG_YR(nb - 1, ns + q) : 0.0;
     GDG_THREADS_END
+    GDG_THREADS_BEGIN
+        double *out = SM_CUR(cx);
+        for (int r = 0; r < per_out; r++) { const int k = tid + r * GDG_NT; if (k < n) out[sw(k)] = R(buf)[r]; }
+    GDG_THREADS_END
+#undef GDG_YR
 }
 
 #endif /* GDG_STAGES2_CUH */
