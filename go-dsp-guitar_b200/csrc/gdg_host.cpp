@@ -499,7 +499,7 @@ int Unit::prepare(uint32_t rate)
                 if (!pa_spec) return backend_fail("filter spectrum upload failed");
                 /* a recompiled filter is a NEW filter object in the reference: fresh (zero) overlap tail */
                 if (d_st) { gdgb_free(d_st); d_st = nullptr; }
-                if (ensure_state((size_t)pa_spec->F, pa_spec->F)) return -1;
+                if (ensure_state((size_t)pa_spec->F + 1, pa_spec->F)) return -1;   /* tail[F] + zero-run word */
                 pa_new_filter = false;
             }
             d.i[1] = pa_spec->F; d.i[2] = pa_spec->logM; d.aux = pa_spec->d_H;

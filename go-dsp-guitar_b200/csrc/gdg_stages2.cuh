@@ -62,53 +62,61 @@ GDG_DEVI double nl_pointwise(int type, const gdg_unit_desc &d, double s)
     return d.p[1] * pre;
 }
 
-/* fuzz.go:52-105 over `cnt` consecutive samples: follower scan, coupling-capacitor scan, in place.
- * f == 1: samples are x[sw(k)]; f > 1: sample k = f*jl + ph of the tile lives at z[zloc(f, jl, ph)]. */
-GDG_DEVI int fz_addr(int f, int k) { if (f == 1) return sw(k); const int jl = k / f; return zloc(f, jl, k - jl * f); }
+/* fuzz.go:52-105 over the F*nb oversampled samples of nb base samples (F == 1: the block itself): follower
+ * scan, coupling-capacitor scan, in place.  Thread chunk = Sb consecutive base samples = F*Sb consecutive
+ * oversampled samples, visited in time order (base jl, sub-phase ph). */
+template <int F> GDG_DEVI int fz_loc(int jl, int ph) { return F == 1 ? sw(jl) : zloc(F, jl, ph); }
 
-GDG_DEV void fuzz_run(gdg_ctx &cx, const gdg_unit_desc &d, double *z, int cnt, int f)
+template <int F>
+GDG_DEV void fuzz_run(gdg_ctx &cx, const gdg_unit_desc &d, double *z, int nbase)
 {
-    const int S = chunk_len(cnt), mode = d.i[1];
+    const int Sb = chunk_len(nbase), mode = d.i[1];
     const double gain = d.p[0], lvl = d.p[1], bias = d.p[2], ff = d.p[3], ffi = d.p[4], dinv = d.p[5], dd = d.p[6];
     double *st = d.st;
-    const double astep = follow_A(mode, dinv, dd), afull = pow_int(astep, S), cstep = 1.0 - dd, cfull = pow_int(cstep, S);
+    const double astep = follow_A(mode, dinv, dd), afull = pow_int(astep, F * Sb), cstep = 1.0 - dd, cfull = pow_int(cstep, F * Sb);
     const double inite[1] = {st[GDG_OS_ST_ENV]}, initc[1] = {st[GDG_OS_ST_CCV]};
     GDG_REGA(double, a, 1); GDG_REGA(double, b, 1); GDG_REGA(double, ein, 1); GDG_REGA(double, cin, 1);
     GDG_THREADS_BEGIN
-        const int k0 = tid * S, k1 = imin(cnt, k0 + S);
+        const int j0 = tid * Sb, j1 = imin(nbase, j0 + Sb);
         double e = 0.0;
-        for (int k = k0; k < k1; k++) e = follow_step(mode, e, fabs(z[fz_addr(f, k)]), dinv, dd);
-        R(a)[0] = k0 < cnt ? chunk_A(astep, k1 - k0, S, afull) : 1.0; R(b)[0] = k0 < cnt ? e : 0.0;
+        for (int jl = j0; jl < j1; jl++)
+#pragma unroll
+            for (int ph = 0; ph < F; ph++) e = follow_step(mode, e, fabs(z[fz_loc<F>(jl, ph)]), dinv, dd);
+        R(a)[0] = j0 < nbase ? chunk_A(astep, F * (j1 - j0), F * Sb, afull) : 1.0; R(b)[0] = j0 < nbase ? e : 0.0;
     GDG_THREADS_END_NOSYNC
     GDG_SCAN(1, cx, mode == GDG_FOLLOW_ENVELOPE, a, b, inite, ein);
     GDG_THREADS_BEGIN
-        const int k0 = tid * S, k1 = imin(cnt, k0 + S);
+        const int j0 = tid * Sb, j1 = imin(nbase, j0 + Sb);
         double e = R(ein)[0], c = 0.0;
-        for (int k = k0; k < k1; k++) {
-            const double s = z[fz_addr(f, k)];
-            e = follow_step(mode, e, fabs(s), dinv, dd);
-            double pre = clamp1(gain * (s - (bias * e)));
-            pre = (ff * pre) + (ffi * s);
-            c += (pre - c) * dd;
-        }
-        R(a)[0] = k0 < cnt ? chunk_A(cstep, k1 - k0, S, cfull) : 1.0; R(b)[0] = k0 < cnt ? c : 0.0;
+        for (int jl = j0; jl < j1; jl++)
+#pragma unroll
+            for (int ph = 0; ph < F; ph++) {
+                const double s = z[fz_loc<F>(jl, ph)];
+                e = follow_step(mode, e, fabs(s), dinv, dd);
+                double pre = clamp1(gain * (s - (bias * e)));
+                pre = (ff * pre) + (ffi * s);
+                c += (pre - c) * dd;
+            }
+        R(a)[0] = j0 < nbase ? chunk_A(cstep, F * (j1 - j0), F * Sb, cfull) : 1.0; R(b)[0] = j0 < nbase ? c : 0.0;
     GDG_THREADS_END_NOSYNC
     GDG_SCAN(1, cx, 0, a, b, initc, cin);
     GDG_THREADS_BEGIN
-        const int k0 = tid * S, k1 = imin(cnt, k0 + S);
+        const int j0 = tid * Sb, j1 = imin(nbase, j0 + Sb);
         double e = R(ein)[0], c = R(cin)[0];
-        for (int k = k0; k < k1; k++) {
-            const int ad = fz_addr(f, k);
-            const double s = z[ad];
-            e = follow_step(mode, e, fabs(s), dinv, dd);
-            double pre = clamp1(gain * (s - (bias * e)));
-            pre = (ff * pre) + (ffi * s);
-            const double diff = pre - c;
-            c += diff * dd;
-            pre -= c;
-            z[ad] = lvl * clamp1(pre);
-        }
-        if (k0 < cnt && k1 == cnt) { st[GDG_OS_ST_ENV] = e; st[GDG_OS_ST_CCV] = c; }
+        for (int jl = j0; jl < j1; jl++)
+#pragma unroll
+            for (int ph = 0; ph < F; ph++) {
+                const int ad = fz_loc<F>(jl, ph);
+                const double s = z[ad];
+                e = follow_step(mode, e, fabs(s), dinv, dd);
+                double pre = clamp1(gain * (s - (bias * e)));
+                pre = (ff * pre) + (ffi * s);
+                const double diff = pre - c;
+                c += diff * dd;
+                pre -= c;
+                z[ad] = lvl * clamp1(pre);
+            }
+        if (j0 < nbase && j1 == nbase) { st[GDG_OS_ST_ENV] = e; st[GDG_OS_ST_CCV] = c; }
     GDG_THREADS_END
 }
 
@@ -154,8 +162,14 @@ GDG_DEV void oversampled_tiles(gdg_ctx &cx, const gdg_unit_desc &d)
             for (int jl = tid; jl < Tt; jl += GDG_NT) {
                 const int j = t0 + jl;
                 double xs[6];
+                if (j >= 6) {
 #pragma unroll
-                for (int q = 0; q < 6; q++) { const int idx = j - 6 + q; xs[q] = idx >= 0 ? x[sw(idx)] : uph[8 + idx]; }
+                    for (int q = 0; q < 6; q++) xs[q] = x[sw(j - 6 + q)];
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 6; q++) { const int idx = j - 6 + q; xs[q] = idx >= 0 ? x[sw(idx)] : uph[8 + idx]; }
+                }
+                const int m0 = pz(GDG_ZH + jl), m1 = pz(GDG_ZH + jl + 1);
 #pragma unroll
                 for (int ph = 0; ph < F; ph++) {
                     double u;
@@ -166,11 +180,11 @@ GDG_DEV void oversampled_tiles(gdg_ctx &cx, const gdg_unit_desc &d)
                         for (int q = 0; q < 6; q++) u += xs[q] * (F == 2 ? c_lz2[0][q] : c_lz4[ph - 1][q]);
                     }
                     if (type != GDG_UNIT_FUZZ) u = nl_pointwise(type, d, u);
-                    z[zloc(F, jl, ph)] = u;
+                    if (ph == 0) z[m0] = u; else z[(F - ph) * GDG_ZPS + m1] = u;
                 }
             }
         GDG_THREADS_END
-        if (type == GDG_UNIT_FUZZ) fuzz_run(cx, d, z, F * Tt, F);
+        if (type == GDG_UNIT_FUZZ) fuzz_run<F>(cx, d, z, Tt);
         /* polyphase FIR partial sums: warp-uniform phase */
         GDG_THREADS_BEGIN
             const int warp = tid >> 5, p = warp % F;
@@ -188,7 +202,7 @@ GDG_DEV void oversampled_tiles(gdg_ctx &cx, const gdg_unit_desc &d)
                 }
 #pragma unroll
                 for (int r = 0; r < RR; r++)
-                    if (i0 + r < Tt) { if (p == 0) y[sw(t0 + i0 + r)] = acc[r]; else part[(p - 1) * GDG_OS_TILE + i0 + r] = acc[r]; }
+                    if (i0 + r < Tt) { if (p == 0) y[sw(t0 + i0 + r)] = acc[r]; else part[(p - 1) * GDG_OS_TILE + sw(i0 + r)] = acc[r]; }
             }
         GDG_THREADS_END
         /* combine in phase order, clamp, -0.5 dB; stage the halo for the next tile */
@@ -196,16 +210,13 @@ GDG_DEV void oversampled_tiles(gdg_ctx &cx, const gdg_unit_desc &d)
             for (int i = tid; i < Tt; i += GDG_NT) {
                 double acc = y[sw(t0 + i)];
 #pragma unroll
-                for (int p = 1; p < F; p++) acc += part[(p - 1) * GDG_OS_TILE + i];
+                for (int p = 1; p < F; p++) acc += part[(p - 1) * GDG_OS_TILE + sw(i)];
                 y[sw(t0 + i)] = 0.9440608762859234 * clamp1(acc);
             }
-            for (int q = tid; q < F * (GDG_ZH + 1); q += GDG_NT) {
-                const int p = q / (GDG_ZH + 1), m = q - p * (GDG_ZH + 1);
-                SM_SCANB[q] = z[p * GDG_ZPS + pz(m + Tt)];
-            }
+            if (tid < F * 64) { const int p = tid >> 6, m = tid & 63; if (m <= GDG_ZH) SM_SCANB[tid] = z[p * GDG_ZPS + pz(m + Tt)]; }
         GDG_THREADS_END
         GDG_THREADS_BEGIN
-            for (int q = tid; q < F * (GDG_ZH + 1); q += GDG_NT) { const int p = q / (GDG_ZH + 1), m = q - p * (GDG_ZH + 1); z[p * GDG_ZPS + pz(m)] = SM_SCANB[q]; }
+            if (tid < F * 64) { const int p = tid >> 6, m = tid & 63; if (m <= GDG_ZH) z[p * GDG_ZPS + pz(m)] = SM_SCANB[tid]; }
         GDG_THREADS_END
     }
     /* carry: oversampled history and the last 8 inputs (oversampling.go:91-93) */
@@ -224,7 +235,7 @@ GDG_DEV void stage_oversampled(gdg_ctx &cx, const gdg_unit_desc &d)
     const int n = cx.n, f = d.i[0], type = d.type;
     double *x = SM_CUR(cx);
     if (f <= 1) {
-        if (type == GDG_UNIT_FUZZ) { fuzz_run(cx, d, x, n, 1); return; }
+        if (type == GDG_UNIT_FUZZ) { fuzz_run<1>(cx, d, x, n); return; }
         GDG_THREADS_BEGIN
             for (int k = tid; k < n; k += GDG_NT) x[sw(k)] = nl_pointwise(type, d, x[sw(k)]);
         GDG_THREADS_END
@@ -588,12 +599,12 @@ GDG_DEVI void tw_powers(gdg_c2 w1, gdg_c2 (&pw)[RR])
  * holds output brev(k)) times W_L^(j brev(k)); natural in -> bit-reversed out over all passes.
  * Inverse: the mirror image with conjugate twiddles (bit-reversed in -> natural out), unnormalised. */
 template <int RR>
-GDG_DEV void fft_pass(double *D, const double *tw, int logM, int nseg, int logL, int inverse)
+GDG_DEV void fft_pass(double *D, const double *tws, int logM, int nseg, int logL, int inverse)
 {
     constexpr int LOGR = RR == 16 ? 4 : (RR == 8 ? 3 : (RR == 4 ? 2 : 1));
     const int logS = logL - LOGR;                              /* stride L/RR */
     const int nb = nseg << (logM - LOGR);
-    const int tshift = 14 - logL;                              /* W_L^e = tw[e << tshift], GDG_MAX_FFT = 2^14 */
+    const int tshift = 13 - logL;                              /* W_L^j = tws[j << tshift]: shared table exp(-2 pi i k / 8192), k < 1024 */
     GDG_THREADS_BEGIN
         for (int b = tid; b < nb; b += GDG_NT) {
             const int seg = b >> (logM - LOGR), rb = b & ((1 << (logM - LOGR)) - 1);
@@ -602,7 +613,7 @@ GDG_DEV void fft_pass(double *D, const double *tw, int logM, int nseg, int logL,
             gdg_c2 v[RR], pw[RR];
 #pragma unroll
             for (int k = 0; k < RR; k++) v[k] = cld(D, cz(base + (k << logS)));
-            gdg_c2 w1 = tw_full(tw, j << tshift);
+            gdg_c2 w1 = cld(tws, j << tshift);
             if (inverse) w1.im = -w1.im;
             tw_powers<RR>(w1, pw);
             if (!inverse) {
@@ -647,6 +658,7 @@ GDG_DEV void fft_inverse(gdg_ctx &cx, double *D, const double *tw, int logM, int
     for (int i = np - 1; i >= 0; i--) { logL += r[i]; fft_pass_any(D, tw, logM, nseg, logL, r[i], 1, cx); }
 }
 
+/* power_amp state: tail[F] followed by one word = number of trailing tail cells known to be zero */
 GDG_DEV void stage_poweramp(gdg_ctx &cx, const gdg_unit_desc &d, const double *tw)
 {
     const int n = cx.n, L = d.i[0];
@@ -663,10 +675,15 @@ GDG_DEV void stage_poweramp(gdg_ctx &cx, const gdg_unit_desc &d, const double *t
     const int total = nb * M;                                    /* complex points in flight (<= GDG_MAX_N) */
     const int per = (total + GDG_NT - 1) / GDG_NT;               /* <= 16 */
     double *D = SM_R, *tail = d.st;
+    double *tws = SM_SCANB;                                      /* 1024 complex: exp(-2 pi i k / 8192) for the passes */
+    double *wc = SM_SCANA, *wf = SM_SCANA + 130;                 /* W_F^(64 a), a <= 64 and W_F^b, b < 64 for the split */
+    double *tl = SM_S;                                           /* prefetched overlap tail (plain layout) */
     const double *H = d.aux;
+    const int zlen = (int)st_geti(tail, F);                      /* trailing zeros guaranteed in tail[] */
+    const int fstep = GDG_MAX_FFT / F;                           /* W_F^k = tw[k * MAXFFT/F] */
     GDG_REGA(double, buf, 32);
     /* pack: block j -> complex points (x[j ns + 2c], x[j ns + 2c + 1]), c < ns/2, zero padded to M; through
-     * registers because the destination overlays the source */
+     * registers because the destination overlays the source.  Also fetch twiddles and the overlap tail. */
     GDG_THREADS_BEGIN
         for (int r = 0; r < per; r++) {
             const int g = tid + r * GDG_NT;
@@ -677,6 +694,11 @@ GDG_DEV void stage_poweramp(gdg_ctx &cx, const gdg_unit_desc &d, const double *t
             }
             R(buf)[2 * r] = re; R(buf)[2 * r + 1] = im;
         }
+        for (int k = tid; k < 1024; k += GDG_NT) { const gdg_c2 w = twd(tw, 2 * k); cst(tws, k, w); }
+        if (tid < 65) cst(wc, tid, tw_full(tw, imin(64 * tid * fstep, GDG_MAX_FFT - 1) ));
+        if (tid >= 128 && tid < 192) cst(wf, tid - 128, twd(tw, (tid - 128) * fstep));
+        /* overlap cells [0, ns) are always needed: fetch them now, hidden behind the transform */
+        for (int q = tid; q < ns; q += GDG_NT) tl[q] = q < F - zlen ? tail[q] : 0.0;
     GDG_THREADS_END
     GDG_THREADS_BEGIN
         for (int r = 0; r < per; r++) {
@@ -684,10 +706,10 @@ GDG_DEV void stage_poweramp(gdg_ctx &cx, const gdg_unit_desc &d, const double *t
             if (g < total) { gdg_c2 v; v.re = R(buf)[2 * r]; v.im = R(buf)[2 * r + 1]; cst(D, cz(g), v); }
         }
     GDG_THREADS_END
-    fft_forward(cx, D, tw, logM, nb);
+    fft_forward(cx, D, tws, logM, nb);
     /* split (fft.go:801-818) * H (filter.go:459) * inverse split (fft.go:899-955), on bit-reversed storage */
-    const int fstep = GDG_MAX_FFT / F;                            /* W_F^k = tw[k * MAXFFT/F] */
     GDG_THREADS_BEGIN
+#pragma unroll 2
         for (int b = tid; b < nb * (M / 2 + 1); b += GDG_NT) {
             const int seg = b / (M / 2 + 1), k = b - seg * (M / 2 + 1);
             const int zb = seg * M;
@@ -699,9 +721,11 @@ GDG_DEV void stage_poweramp(gdg_ctx &cx, const gdg_unit_desc &d, const double *t
                 cst(D, cz(zb), o);
             } else {
                 const int k2 = M - k;
+                gdg_c2 ha, hb; ha.re = GDG_LDG(H + 2 * k); ha.im = GDG_LDG(H + 2 * k + 1);
+                hb.re = GDG_LDG(H + 2 * k2); hb.im = GDG_LDG(H + 2 * k2 + 1);
                 const int p1 = cz(zb + brev(k, logM)), p2 = cz(zb + brev(k2, logM));
                 const gdg_c2 za = cld(D, p1), zbv = cld(D, p2);
-                const gdg_c2 wk = twd(tw, k * fstep);
+                const gdg_c2 wk = cmul(cld(wc, k >> 6), cld(wf, k & 63));  /* W_F^k = W_F^(64 a) W_F^b */
                 gdg_c2 jw; jw.re = -wk.im; jw.im = wk.re;                 /* j * W_F^k */
                 const gdg_c2 s1 = cadd(za, cconj(zbv)), d1 = csub(za, cconj(zbv));
                 const gdg_c2 t1 = cmul(jw, d1);
@@ -709,8 +733,6 @@ GDG_DEV void stage_poweramp(gdg_ctx &cx, const gdg_unit_desc &d, const double *t
                 const gdg_c2 s2 = cadd(zbv, cconj(za)), d2 = csub(zbv, cconj(za));
                 const gdg_c2 t2 = cmul(cconj(jw), d2);                    /* j W_F^(M-k) = conj(j W_F^k) */
                 gdg_c2 xb; xb.re = 0.5 * (s2.re - t2.re); xb.im = 0.5 * (s2.im - t2.im);
-                gdg_c2 ha, hb; ha.re = GDG_LDG(H + 2 * k); ha.im = GDG_LDG(H + 2 * k + 1);
-                hb.re = GDG_LDG(H + 2 * k2); hb.im = GDG_LDG(H + 2 * k2 + 1);
                 const gdg_c2 ya = cmul(xa, ha), yb = cmul(xb, hb);
                 const gdg_c2 e1 = cadd(ya, cconj(yb)), o1 = cmul(csub(ya, cconj(yb)), cconj(wk));
                 gdg_c2 ra; ra.re = 0.5 * (e1.re - o1.im); ra.im = 0.5 * (e1.im + o1.re);
@@ -722,35 +744,36 @@ GDG_DEV void stage_poweramp(gdg_ctx &cx, const gdg_unit_desc &d, const double *t
             }
         }
     GDG_THREADS_END
-    fft_inverse(cx, D, tw, logM, nb);
+    fft_inverse(cx, D, tws, logM, nb);
     /* real sample r of block j = component (r & 1) of complex point r >> 1 */
 #define GDG_YR(j, r) D[2 * cz((j) * M + ((r) >> 1)) + ((r) & 1)]
     const double scale = 1.0 / (double)M;
     const int per_out = (n + GDG_NT - 1) / GDG_NT;               /* <= 16 */
     /* overlap-add + clamp into registers; running tail staged in place (filter.go:473-503): for nb >= 2 the
-     * tail beyond ns is zero, so only the single-block case adds the old tail */
+     * tail beyond ns is zero after the first block, so only the single-block case adds the old tail there.
+     * Cells of tail[] known to be zero (the zero-run word) are neither read nor rewritten. */
     GDG_THREADS_BEGIN
         for (int r = 0; r < per_out; r++) {
             const int k = tid + r * GDG_NT;
             if (k < n) {
                 const int j = k / ns, q = k - j * ns;
                 double pre = scale * GDG_YR(j, q);
-                if (j == 0) pre += tail[q];
-                else { pre += scale * GDG_YR(j - 1, ns + q); if (j == 1) pre += tail[ns + q]; }
+                if (j == 0) pre += tl[q];
+                else { pre += scale * GDG_YR(j - 1, ns + q); if (j == 1 && ns + q < F - zlen) pre += tail[ns + q]; }
                 R(buf)[r] = clamp1(pre);
             }
         }
         for (int q = tid; q < F - ns; q += GDG_NT) {
             double v = scale * GDG_YR(nb - 1, ns + q);
-            if (nb == 1) v += tail[ns + q];
+            if (nb == 1 && ns + q < F - zlen) v += tail[ns + q];
             GDG_YR(nb - 1, ns + q) = v;
         }
     GDG_THREADS_END
     cx.cur_off = GDG_SMEM_R; cx.alt_off = GDG_SMEM_R + GDG_MAX_N;
     GDG_THREADS_BEGIN
-        for (int q = tid; q < F; q += GDG_NT) tail[q] = q < F - ns ? GDG_YR(nb - 1, ns + q) : 0.0;
-    GDG_THREADS_END
-    GDG_THREADS_BEGIN
+        for (int q = tid; q < F - ns; q += GDG_NT) tail[q] = GDG_YR(nb - 1, ns + q);
+        for (int q = F - ns + tid; q < F - zlen; q += GDG_NT) tail[q] = 0.0;
+        if (tid == 0) st_seti(tail, F, ns);
         double *out = SM_CUR(cx);
         for (int r = 0; r < per_out; r++) { const int k = tid + r * GDG_NT; if (k < n) out[sw(k)] = R(buf)[r]; }
     GDG_THREADS_END
