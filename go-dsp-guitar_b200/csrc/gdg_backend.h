@@ -28,6 +28,15 @@ int gdgb_download(void *dst, const void *src, size_t bytes);    /* device -> hos
 int gdgb_copy(void *dst, const void *src, size_t bytes);        /* device -> device, library stream */
 int gdgb_copy_on(void *dst, const void *src, size_t bytes, void *stream);
 int gdgb_sync(void);
+/* copy/compute overlap for the host-buffer entry points: stream 0 = compute (== gdgb_stream()), 1 = H2D, 2 = D2H;
+ * a small pool of events orders them.  Copies are truly asynchronous only for page-locked host memory. */
+#define GDGB_EVENTS 64
+void *gdgb_stream_handle(int stream);
+int gdgb_h2d_async(void *dst, const void *src, size_t bytes, int stream);
+int gdgb_d2h_async(void *dst, const void *src, size_t bytes, int stream);
+int gdgb_record(int event, int stream);
+int gdgb_wait(int stream, int event);
+int gdgb_sync_stream(int stream);
 void *gdgb_pinned_alloc(size_t bytes);
 void gdgb_pinned_free(void *p);
 int gdgb_is_pinned(const void *p);

@@ -624,17 +624,15 @@ struct Batch {
     std::vector<std::vector<const gdg_chain_desc *>> h_ptrs;     /* [round][channel] */
     std::vector<const gdg_chain_desc **> d_ptrs;
     double *d_in = nullptr, *d_out = nullptr; size_t cap = 0;    /* device staging for host-buffer calls */
-    double *h_stage = nullptr; size_t h_cap = 0;                 /* pinned staging */
-    ~Batch() { for (auto p : d_ptrs) gdgb_free((void *)p); if (d_in) gdgb_free(d_in); if (d_out) gdgb_free(d_out); if (h_stage) gdgb_pinned_free(h_stage); }
+    double *h_stage = nullptr, *h_stage2 = nullptr; size_t h_cap = 0;   /* pinned staging (in / out) for pageable callers */
+    ~Batch() { for (auto p : d_ptrs) gdgb_free((void *)p); if (d_in) gdgb_free(d_in); if (d_out) gdgb_free(d_out); if (h_stage) gdgb_pinned_free(h_stage); if (h_stage2) gdgb_pinned_free(h_stage2); }
 };
 std::mutex g_batch_mutex;
 std::unique_ptr<Batch> g_batch;
 
-int run_batch_device(gdg_chain *const *chains, size_t C, const double *d_in, double *d_out, size_t stride, size_t n,
-                     uint32_t rate, void *stream)
+/* bring descriptors + pointer tables of the batch up to date; returns the number of segment rounds or -1 */
+int prepare_batch(gdg_chain *const *chains, size_t C, uint32_t rate, void *stream)
 {
-    if (check_block(n)) return -1;
-    std::lock_guard<std::mutex> lk(g_batch_mutex);
     if (!g_batch || g_batch->chains.size() != C || !std::equal(g_batch->chains.begin(), g_batch->chains.end(), chains)) {
         g_batch.reset(new Batch());
         g_batch->chains.assign(chains, chains + C);
@@ -647,31 +645,51 @@ int run_batch_device(gdg_chain *const *chains, size_t C, const double *d_in, dou
         if (r < 0) return -1;
         nseg[c] = r; rounds = std::max(rounds, (size_t)r);
     }
-    bool ptr_changed = b.h_ptrs.size() != rounds;
-    std::vector<std::vector<const gdg_chain_desc *>> ptrs(rounds, std::vector<const gdg_chain_desc *>(C, nullptr));
-    for (size_t r = 0; r < rounds; r++)
-        for (size_t c = 0; c < C; c++) if ((int)r < nseg[c]) ptrs[r][c] = chains[c]->d_desc[r];
-    if (!ptr_changed) for (size_t r = 0; r < rounds; r++) if (ptrs[r] != b.h_ptrs[r]) { ptr_changed = true; break; }
-    if (ptr_changed) {
-        for (auto p : b.d_ptrs) gdgb_free((void *)p);
-        b.d_ptrs.clear();
-        for (size_t r = 0; r < rounds; r++) {
-            const gdg_chain_desc **dp = (const gdg_chain_desc **)gdgb_alloc(C * sizeof(void *));
-            if (!dp || gdgb_upload((void *)dp, ptrs[r].data(), C * sizeof(void *))) return backend_fail("descriptor table upload failed");
-            b.d_ptrs.push_back(dp);
-        }
-        b.h_ptrs = ptrs;
-    }
-    /* descriptor / state uploads run on the library stream: order a foreign stream after them */
-    bool touched = ptr_changed;
+    bool touched = false;
     for (size_t c = 0; c < C; c++) if (chains[c]->uploaded) { touched = true; chains[c]->uploaded = false; }
-    if (touched && stream != gdgb_stream() && gdgb_sync()) return backend_fail("synchronize failed");
-    for (size_t r = 0; r < rounds; r++) {
+    if (touched || b.h_ptrs.size() != rounds) {          /* pointer tables only change when some chain changed */
+        std::vector<std::vector<const gdg_chain_desc *>> ptrs(rounds, std::vector<const gdg_chain_desc *>(C, nullptr));
+        for (size_t r = 0; r < rounds; r++)
+            for (size_t c = 0; c < C; c++) if ((int)r < nseg[c]) ptrs[r][c] = chains[c]->d_desc[r];
+        if (ptrs != b.h_ptrs) {
+            for (auto p : b.d_ptrs) gdgb_free((void *)p);
+            b.d_ptrs.clear();
+            for (size_t r = 0; r < rounds; r++) {
+                const gdg_chain_desc **dp = (const gdg_chain_desc **)gdgb_alloc(C * sizeof(void *));
+                if (!dp || gdgb_upload((void *)dp, ptrs[r].data(), C * sizeof(void *))) return backend_fail("descriptor table upload failed");
+                b.d_ptrs.push_back(dp);
+            }
+            b.h_ptrs = ptrs;
+        }
+        /* descriptor / state uploads run on the library stream: order a foreign stream after them */
+        if (stream != gdgb_stream() && gdgb_sync()) return backend_fail("synchronize failed");
+    }
+    return (int)rounds;
+}
+/* launch channels [c0, c0 + cnt) of the prepared batch */
+int launch_batch(size_t c0, size_t cnt, int rounds, const double *d_in, double *d_out, size_t stride, size_t n, void *stream)
+{
+    Batch &b = *g_batch;
+    for (int r = 0; r < rounds; r++) {
         const double *src = r == 0 ? d_in : d_out;
-        if (gdgb_launch_chains(b.d_ptrs[r], (int)C, src, d_out, (long)stride, (int)n, stream)) return backend_fail("chain kernel launch failed");
+        if (gdgb_launch_chains(b.d_ptrs[r] + c0, (int)cnt, src + c0 * stride, d_out + c0 * stride, (long)stride, (int)n, stream))
+            return backend_fail("chain kernel launch failed");
     }
     return 0;
 }
+int run_batch_device(gdg_chain *const *chains, size_t C, const double *d_in, double *d_out, size_t stride, size_t n,
+                     uint32_t rate, void *stream)
+{
+    if (check_block(n)) return -1;
+    std::lock_guard<std::mutex> lk(g_batch_mutex);
+    const int rounds = prepare_batch(chains, C, rate, stream);
+    if (rounds < 0) return -1;
+    return launch_batch(0, C, rounds, d_in, d_out, stride, n, stream);
+}
+
+/* Host-buffer pipeline: channels are cut into groups; H2D of group g+1, the kernel of group g and D2H of
+ * group g-1 overlap on three streams.  `extra_out` rows (spatializer master) follow the channel rows. */
+int pipeline_groups(size_t C) { return C >= 256 ? 8 : (C >= 32 ? 4 : 1); }
 
 bool contiguous(const double *const *p, size_t C, size_t n)
 {
@@ -692,21 +710,54 @@ int stage_buffers(Batch &b, size_t words)
     return 0;
 }
 
-/* host [C][n] (array of pointers) -> device planar */
-int upload_channels(const double *const *in, size_t C, size_t n, double *d_dst)
+/* host rows [c0, c0+cnt) (array of pointers) -> device planar, asynchronously on `stream_id` */
+int upload_rows(Batch &b, const double *const *in, size_t c0, size_t cnt, size_t n, double *d_dst, int stream_id)
+{
+    const size_t bytes = n * sizeof(double);
+    if (contiguous(in + c0, cnt, n) && gdgb_is_pinned(in[c0]))
+        return gdgb_h2d_async(d_dst + c0 * n, in[c0], cnt * bytes, stream_id) ? backend_fail("upload failed") : 0;
+    /* pageable / scattered rows: gather into the library's pinned staging, then one copy */
+    for (size_t c = c0; c < c0 + cnt; c++) memcpy(b.h_stage + c * n, in[c], bytes);
+    return gdgb_h2d_async(d_dst + c0 * n, b.h_stage + c0 * n, cnt * bytes, stream_id) ? backend_fail("upload failed") : 0;
+}
+/* device planar rows -> host rows; returns 1 if the data still sits in the pinned staging (scatter after sync) */
+int download_rows(Batch &b, double *const *out, size_t c0, size_t cnt, size_t n, const double *d_src, int stream_id)
+{
+    const size_t bytes = n * sizeof(double);
+    if (contiguous((const double *const *)out + c0, cnt, n) && gdgb_is_pinned(out[c0]))
+        return gdgb_d2h_async(out[c0], d_src + c0 * n, cnt * bytes, stream_id) ? backend_fail("download failed") : 0;
+    if (gdgb_d2h_async(b.h_stage2 + c0 * n, d_src + c0 * n, cnt * bytes, stream_id)) return backend_fail("download failed");
+    return 1;
+}
+int ensure_host_stage(Batch &b, size_t words)
+{
+    if (b.h_cap < words) {
+        if (b.h_stage) gdgb_pinned_free(b.h_stage);
+        if (b.h_stage2) gdgb_pinned_free(b.h_stage2);
+        b.h_stage = (double *)gdgb_pinned_alloc(words * sizeof(double));
+        b.h_stage2 = (double *)gdgb_pinned_alloc(words * sizeof(double));
+        if (!b.h_stage || !b.h_stage2) return backend_fail("pinned staging allocation failed");
+        b.h_cap = words;
+    }
+    return 0;
+}
+
+int upload_simple(const double *const *in, size_t C, size_t n, double *d_dst)
 {
     if (contiguous(in, C, n)) return gdgb_upload(d_dst, in[0], C * n * sizeof(double)) ? backend_fail("upload failed") : 0;
-    for (size_t c = 0; c < C; c++)
-        if (gdgb_upload(d_dst + c * n, in[c], n * sizeof(double))) return backend_fail("upload failed");
+    for (size_t c = 0; c < C; c++) if (gdgb_upload(d_dst + c * n, in[c], n * sizeof(double))) return backend_fail("upload failed");
     return 0;
 }
-int download_channels(double *const *out, size_t C, size_t n, const double *d_src)
+int download_simple(double *const *out, size_t C, size_t n, const double *d_src)
 {
     if (contiguous((const double *const *)out, C, n)) return gdgb_download(out[0], d_src, C * n * sizeof(double)) ? backend_fail("download failed") : 0;
-    for (size_t c = 0; c < C; c++)
-        if (gdgb_download(out[c], d_src + c * n, n * sizeof(double))) return backend_fail("download failed");
+    for (size_t c = 0; c < C; c++) if (gdgb_download(out[c], d_src + c * n, n * sizeof(double))) return backend_fail("download failed");
     return 0;
 }
+
+/* the whole host-buffer block: upload -> (tuner feed) -> chains -> (spatializer) -> download, pipelined */
+int host_block(gdg_chain *const *chains, size_t C, gdg_tuner *tuner, int tuner_channel, gdg_spatializer *spat,
+               const double *const *in, double *const *out, size_t n_out_rows, size_t n, uint32_t rate);
 
 } // namespace
 
@@ -770,6 +821,56 @@ struct gdg_tuner {
     std::vector<double> corr;
     ~gdg_tuner() { gdgb_free(d_ring); gdgb_free(d_work); gdgb_free(d_block); }
 };
+
+namespace {
+int host_block(gdg_chain *const *chains, size_t C, gdg_tuner *tuner, int tuner_channel, gdg_spatializer *spat,
+               const double *const *in, double *const *out, size_t n_out_rows, size_t n, uint32_t rate)
+{
+    std::lock_guard<std::mutex> lk(g_batch_mutex);
+    const int rounds = prepare_batch(chains, C, rate, gdgb_stream());
+    if (rounds < 0) return -1;
+    Batch &b = *g_batch;
+    if (stage_buffers(b, (C + 2) * n)) return -1;
+    const bool in_direct = contiguous(in, C, n) && gdgb_is_pinned(in[0]);
+    const bool out_direct = contiguous((const double *const *)out, n_out_rows, n) && gdgb_is_pinned(out[0]);
+    if ((!in_direct || !out_direct) && ensure_host_stage(b, (C + 2) * n)) return -1;
+    const int G = pipeline_groups(C);
+    const size_t per = (C + G - 1) / G;
+    void *s0 = gdgb_stream_handle(0);
+    std::vector<std::pair<size_t, size_t>> staged;
+    for (int g = 0; g < G; g++) {
+        const size_t c0 = (size_t)g * per;
+        if (c0 >= C) break;
+        const size_t cnt = std::min(per, C - c0);
+        if (upload_rows(b, in, c0, cnt, n, b.d_in, 1)) return -1;
+        if (gdgb_record(g, 1)) return backend_fail("event record failed");
+    }
+    for (int g = 0; g < G; g++) {
+        const size_t c0 = (size_t)g * per;
+        if (c0 >= C) break;
+        const size_t cnt = std::min(per, C - c0);
+        if (gdgb_wait(0, g)) return backend_fail("stream wait failed");
+        if (tuner && tuner_channel >= 0 && (size_t)tuner_channel >= c0 && (size_t)tuner_channel < c0 + cnt)
+            if (gdg_tuner_process_device(tuner, b.d_in + (size_t)tuner_channel * n, n, rate, s0)) return -1;   /* controller.go:2668-2672 */
+        if (launch_batch(c0, cnt, rounds, b.d_in, b.d_out, n, n, s0)) return -1;                               /* controller.go:2682-2705 */
+        if (gdgb_record(16 + g, 0) || gdgb_wait(2, 16 + g)) return backend_fail("event failed");
+        const int r = download_rows(b, out, c0, cnt, n, b.d_out, 2);
+        if (r < 0) return -1;
+        if (r == 1) staged.push_back({c0, cnt});
+    }
+    if (spat) {                                                                                                 /* controller.go:2761 */
+        if (gdg_spatializer_process_device(spat, b.d_out, n, nullptr, b.d_out + C * n, n, n, 0, s0)) return -1;
+        if (gdgb_record(40, 0) || gdgb_wait(2, 40)) return backend_fail("event failed");
+        const int r = download_rows(b, out, C, 2, n, b.d_out, 2);
+        if (r < 0) return -1;
+        if (r == 1) staged.push_back({C, 2});
+    }
+    if (gdgb_sync_stream(2)) return backend_fail("synchronize failed");
+    for (auto &sg : staged)
+        for (size_t c = sg.first; c < sg.first + sg.second; c++) memcpy(out[c], b.h_stage2 + c * n, n * sizeof(double));
+    return 0;
+}
+} // namespace
 
 /* ================================================================================ */
 /* C ABI                                                                             */
@@ -1105,17 +1206,7 @@ int gdg_process_batch(gdg_chain *const *chains, size_t C, const double *const *i
     if (ensure_init()) return -1;
     if (!chains || !C || !in || !out) return fail("gdg_process_batch: bad argument");
     if (check_block(n)) return -1;
-    {   /* make sure the batch object (and its staging) matches */
-        std::lock_guard<std::mutex> lk(g_batch_mutex);
-        if (!g_batch || g_batch->chains.size() != C || !std::equal(g_batch->chains.begin(), g_batch->chains.end(), chains)) {
-            g_batch.reset(new Batch()); g_batch->chains.assign(chains, chains + C);
-        }
-        if (stage_buffers(*g_batch, C * n)) return -1;
-    }
-    Batch &b = *g_batch;
-    if (upload_channels(in, C, n, b.d_in)) return -1;
-    if (run_batch_device(chains, C, b.d_in, b.d_out, n, n, rate, gdgb_stream())) return -1;
-    return download_channels(out, C, n, b.d_out);
+    return host_block(chains, C, nullptr, -1, nullptr, in, out, C, n, rate);
 }
 
 int gdg_chain_process(gdg_chain *c, const double *in, double *out, size_t n, uint32_t rate)
@@ -1199,10 +1290,10 @@ int gdg_spatializer_process(gdg_spatializer *s, const double *const *in, uint32_
         if (!s->d_in || !s->d_out || !s->d_aux) return backend_fail("spatializer staging allocation failed");
         s->cap_n = n;
     }
-    if (upload_channels(in, s->count, n, s->d_in)) return -1;
+    if (upload_simple(in, s->count, n, s->d_in)) return -1;
     if (aux && gdgb_upload(s->d_aux, aux, n * sizeof(double))) return backend_fail("upload failed");
     if (gdg_spatializer_process_device(s, s->d_in, n, aux ? s->d_aux : nullptr, s->d_out, n, n, 0, nullptr)) return -1;
-    return download_channels(out, 2, n, s->d_out);
+    return download_simple(out, 2, n, s->d_out);
 }
 
 /* ---- tuner ---- */
@@ -1297,21 +1388,8 @@ int gdg_controller_process(gdg_chain *const *chains, uint32_t C, gdg_tuner *tune
     if (!chains || !C || !in || !out) return fail("gdg_controller_process: bad argument");
     if (check_block(n)) return -1;
     if (n_out < C) return 0;                                /* controller.go:2682: nothing happens */
-    {
-        std::lock_guard<std::mutex> lk(g_batch_mutex);
-        if (!g_batch || g_batch->chains.size() != C || !std::equal(g_batch->chains.begin(), g_batch->chains.end(), chains)) {
-            g_batch.reset(new Batch()); g_batch->chains.assign(chains, chains + C);
-        }
-        if (stage_buffers(*g_batch, ((size_t)C + 2) * n)) return -1;
-    }
-    Batch &b = *g_batch;
-    if (upload_channels(in, C, n, b.d_in)) return -1;
-    if (tuner && tuner_channel >= 0 && (uint32_t)tuner_channel < C)
-        if (gdg_tuner_process_device(tuner, b.d_in + (size_t)tuner_channel * n, n, rate, nullptr)) return -1;
-    if (run_batch_device(chains, C, b.d_in, b.d_out, n, n, rate, gdgb_stream())) return -1;
     const bool do_spat = spat && n_out >= C + 2 && spat->count == C;
-    if (do_spat && gdg_spatializer_process_device(spat, b.d_out, n, nullptr, b.d_out + (size_t)C * n, n, n, 0, nullptr)) return -1;
-    return download_channels(out, (size_t)C + (do_spat ? 2 : 0), n, b.d_out);
+    return host_block(chains, C, tuner, tuner_channel, do_spat ? spat : nullptr, in, out, (size_t)C + (do_spat ? 2 : 0), n, rate);
 }
 
 } /* extern "C" */

@@ -16,7 +16,8 @@
 
 static thread_local std::string t_err;
 static int g_device = -1, g_sms = 0;
-static cudaStream_t g_stream = nullptr;
+static cudaStream_t g_stream = nullptr, g_copy_streams[2] = {nullptr, nullptr};
+static cudaEvent_t g_events[GDGB_EVENTS];
 static double *g_d_tw = nullptr;
 static std::atomic<uint64_t> g_launches{0};
 
@@ -108,6 +109,8 @@ int gdgb_init(int device)
     if (prop.major < 10) { t_err = std::string("device '") + prop.name + "' is not a Blackwell (sm_100a) GPU"; return -1; }
     g_device = device; g_sms = prop.multiProcessorCount;
     CU(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) CU(cudaStreamCreateWithFlags(&g_copy_streams[i], cudaStreamNonBlocking));
+    for (int i = 0; i < GDGB_EVENTS; i++) CU(cudaEventCreateWithFlags(&g_events[i], cudaEventDisableTiming));
     CU(cudaFuncSetAttribute(k_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, GDG_SMEM_BYTES));
     return 0;
 }
@@ -134,6 +137,13 @@ int gdgb_download(void *dst, const void *src, size_t bytes)
 int gdgb_copy(void *dst, const void *src, size_t bytes) { if (bytes) CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, g_stream)); return 0; }
 int gdgb_copy_on(void *dst, const void *src, size_t bytes, void *stream) { if (bytes) CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream)); return 0; }
 int gdgb_sync(void) { if (g_stream) CU(cudaStreamSynchronize(g_stream)); return 0; }
+static cudaStream_t stream_of(int s) { return s == 0 ? g_stream : g_copy_streams[(s - 1) & 1]; }
+void *gdgb_stream_handle(int s) { return (void *)stream_of(s); }
+int gdgb_h2d_async(void *dst, const void *src, size_t bytes, int s) { if (bytes) CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream_of(s))); return 0; }
+int gdgb_d2h_async(void *dst, const void *src, size_t bytes, int s) { if (bytes) CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, stream_of(s))); return 0; }
+int gdgb_record(int ev, int s) { CU(cudaEventRecord(g_events[ev % GDGB_EVENTS], stream_of(s))); return 0; }
+int gdgb_wait(int s, int ev) { CU(cudaStreamWaitEvent(stream_of(s), g_events[ev % GDGB_EVENTS], 0)); return 0; }
+int gdgb_sync_stream(int s) { CU(cudaStreamSynchronize(stream_of(s))); return 0; }
 void *gdgb_pinned_alloc(size_t bytes) { void *p = nullptr; if (cudaMallocHost(&p, bytes ? bytes : 8) != cudaSuccess) return nullptr; return p; }
 void gdgb_pinned_free(void *p) { if (p) cudaFreeHost(p); }
 int gdgb_is_pinned(const void *p)

@@ -41,6 +41,12 @@ int gdgb_download(void *d, const void *s, size_t b) { memcpy(d, s, b); return 0;
 int gdgb_copy(void *d, const void *s, size_t b) { memmove(d, s, b); return 0; }
 int gdgb_copy_on(void *d, const void *s, size_t b, void *) { memmove(d, s, b); return 0; }
 int gdgb_sync(void) { return 0; }
+void *gdgb_stream_handle(int) { return nullptr; }
+int gdgb_h2d_async(void *d, const void *s, size_t b, int) { memcpy(d, s, b); return 0; }
+int gdgb_d2h_async(void *d, const void *s, size_t b, int) { memcpy(d, s, b); return 0; }
+int gdgb_record(int, int) { return 0; }
+int gdgb_wait(int, int) { return 0; }
+int gdgb_sync_stream(int) { return 0; }
 void *gdgb_pinned_alloc(size_t bytes) { return malloc(bytes ? bytes : 8); }
 void gdgb_pinned_free(void *p) { free(p); }
 int gdgb_is_pinned(const void *) { return 0; }
