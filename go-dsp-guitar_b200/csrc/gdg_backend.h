@@ -53,7 +53,8 @@ int gdgb_launch_chains(const gdg_chain_desc *const *d_descs, int channels, const
 /* spatializer: out[2][n] (+)= sum over channels; hist_in/hist_out: [C][hs] double-buffered history */
 int gdgb_launch_spatializer(const gdg_spat_channel *d_ch, int channels, const double *d_in, long stride,
                             const double *d_hist_in, double *d_hist_out, int hs, const double *d_aux,
-                            double *d_outL, double *d_outR, int n, int accumulate, void *stream);
+                            double *d_outL, double *d_outR, int n, int accumulate, double *d_partials, void *stream);
+/* d_partials: 2 * ceil(channels / 32) * n doubles of scratch, needed when channels > 32 */
 
 /* tuner: autocorrelation of `ring` (n_ring samples, oldest at `pos`) zero-padded to fft_size (power of two):
  * d_work: 2*fft_size doubles; result corr[0..fft_size) left in d_work */

@@ -481,7 +481,7 @@ int Unit::prepare(uint32_t rate)
         int hs = 0; size_t total = GDG_RV_ST_DATA;
         for (int j = 0; j < 4; j++) { d.i[1 + j] = (int32_t)(uint32_t)std::round(tt[j] * sr); d.p[2 + j] = tc[j]; hs = std::max(hs, d.i[1 + j]); }
         d.i[0] = hs; total += (size_t)hs; d.i[8] = (int32_t)total;
-        for (int a = 0; a < 3; a++) { d.i[5 + a] = (int)std::round(ap[a] * sr); total += (size_t)(2 * std::max(0, d.i[5 + a] - 1)); }
+        for (int a = 0; a < 3; a++) { d.i[5 + a] = (int)std::round(ap[a] * sr); total += (size_t)std::max(0, d.i[5 + a] - 1); }
         if (ensure_state(total, (long)rate)) return -1;   /* reverb.go:199-262: rebuilt when the rate changes */
         break; }
     case GDG_UNIT_POWERAMP: {
@@ -689,7 +689,14 @@ int run_batch_device(gdg_chain *const *chains, size_t C, const double *d_in, dou
 
 /* Host-buffer pipeline: channels are cut into groups; H2D of group g+1, the kernel of group g and D2H of
  * group g-1 overlap on three streams.  `extra_out` rows (spatializer master) follow the channel rows. */
-int pipeline_groups(size_t C) { return C >= 256 ? 8 : (C >= 32 ? 4 : 1); }
+size_t pipeline_group_size(size_t C)
+{
+    if (C < 64) return C;
+    size_t per = (C + 3) / 4;                                  /* about four groups ... */
+    const size_t sms = (size_t)std::max(1, gdgb_sm_count());
+    if (per > sms) per = ((per + sms - 1) / sms) * sms;        /* ... each a whole number of one-CTA-per-SM waves */
+    return per;
+}
 
 bool contiguous(const double *const *p, size_t C, size_t n)
 {
@@ -769,7 +776,8 @@ struct gdg_spatializer {
     int hs; bool dirty = true; int flip = 0;
     gdg_spat_channel *d_ch = nullptr; double *d_hist[2] = {nullptr, nullptr};
     double *d_in = nullptr, *d_out = nullptr, *d_aux = nullptr; size_t cap_n = 0;
-    ~gdg_spatializer() { gdgb_free(d_ch); gdgb_free(d_hist[0]); gdgb_free(d_hist[1]); gdgb_free(d_in); gdgb_free(d_out); gdgb_free(d_aux); }
+    double *d_part = nullptr; size_t part_n = 0;          /* partial sums of 32-channel groups */
+    ~gdg_spatializer() { gdgb_free(d_part); gdgb_free(d_ch); gdgb_free(d_hist[0]); gdgb_free(d_hist[1]); gdgb_free(d_in); gdgb_free(d_out); gdgb_free(d_aux); }
 
     int alloc_hist(uint32_t rate)
     {
@@ -834,8 +842,8 @@ int host_block(gdg_chain *const *chains, size_t C, gdg_tuner *tuner, int tuner_c
     const bool in_direct = contiguous(in, C, n) && gdgb_is_pinned(in[0]);
     const bool out_direct = contiguous((const double *const *)out, n_out_rows, n) && gdgb_is_pinned(out[0]);
     if ((!in_direct || !out_direct) && ensure_host_stage(b, (C + 2) * n)) return -1;
-    const int G = pipeline_groups(C);
-    const size_t per = (C + G - 1) / G;
+    const size_t per = pipeline_group_size(C);
+    const int G = (int)((C + per - 1) / per);
     void *s0 = gdgb_stream_handle(0);
     std::vector<std::pair<size_t, size_t>> staged;
     for (int g = 0; g < G; g++) {
@@ -1270,8 +1278,15 @@ int gdg_spatializer_process_device(gdg_spatializer *s, const double *d_in, size_
     if (!s || !d_in || !d_out) return fail("gdg_spatializer_process_device: bad argument");
     if (n == 0 || n > (size_t)1 << 24) return fail("gdg_spatializer_process_device: bad block length");
     if (s->dirty) { if (s->upload_channels()) return -1; if (stream && stream != gdgb_stream() && gdgb_sync()) return backend_fail("synchronize failed"); }
+    if (s->count > 32 && s->part_n < n) {
+        gdgb_sync(); gdgb_free(s->d_part);
+        s->d_part = (double *)gdgb_alloc(2 * ((size_t)(s->count + 31) / 32) * n * sizeof(double));
+        if (!s->d_part) return backend_fail("spatializer scratch allocation failed");
+        s->part_n = n;
+        if (stream && stream != gdgb_stream() && gdgb_sync()) return backend_fail("synchronize failed");
+    }
     if (gdgb_launch_spatializer(s->d_ch, (int)s->count, d_in, (long)stride, s->d_hist[s->flip], s->d_hist[s->flip ^ 1], s->hs,
-                                d_aux, d_out, d_out + out_stride, (int)n, accumulate, stream ? stream : gdgb_stream()))
+                                d_aux, d_out, d_out + out_stride, (int)n, accumulate, s->d_part, stream ? stream : gdgb_stream()))
         return backend_fail("spatializer kernel launch failed");
     s->flip ^= 1;
     return 0;

@@ -68,11 +68,12 @@ GDG_DEV void run_chain(double *smem, const gdg_chain_desc *cd, const double *in,
  * possible because other CTAs still read the history -> the history update is
  * its own kernel (spat_push).
  * -------------------------------------------------------------------------- */
-GDG_DEVI void spat_frame(const gdg_spat_channel *ch, int C, const double *in, long stride, const double *hist, int hs,
-                         const double *aux, double *outL, double *outR, int j, int accumulate)
+#define GDG_SPAT_GROUP 32          /* channels mixed by one thread before the partial sums are combined */
+/* channels [c0, c1) of frame j accumulated in ascending order onto (l, r) */
+GDG_DEVI void spat_accumulate(const gdg_spat_channel *ch, int c0, int c1, const double *in, long stride, const double *hist, int hs,
+                              int j, double &l, double &r)
 {
-    double l = accumulate ? outL[j] : 0.0, r = accumulate ? outR[j] : 0.0;
-    for (int c = 0; c < C; c++) {
+    for (int c = c0; c < c1; c++) {
         const gdg_spat_channel &p = ch[c];
         const double *x = in + (long)c * stride;
         const double cur = x[j];
@@ -89,10 +90,32 @@ GDG_DEVI void spat_frame(const gdg_spat_channel *ch, int C, const double *in, lo
             else { l += p.fac_left * cur; r += p.fac_right * dsmp; }
         }
     }
+}
+/* single pass (C <= GDG_SPAT_GROUP): exactly the reference's accumulation order (channels ascending, then aux) */
+GDG_DEVI void spat_frame(const gdg_spat_channel *ch, int C, const double *in, long stride, const double *hist, int hs,
+                         const double *aux, double *outL, double *outR, int j, int accumulate)
+{
+    double l = accumulate ? outL[j] : 0.0, r = accumulate ? outR[j] : 0.0;
+    spat_accumulate(ch, 0, C, in, stride, hist, hs, j, l, r);
     if (aux) { l += aux[j]; r += aux[j]; }
     outL[j] = l; outR[j] = r;
 }
-
+/* two passes for many channels: group g -> part[(2 g + {0,1}) * n + j]; then the groups are summed in ascending order */
+GDG_DEVI void spat_partial(const gdg_spat_channel *ch, int C, const double *in, long stride, const double *hist, int hs,
+                           double *part, int n, int g, int j)
+{
+    double l = 0.0, r = 0.0;
+    const int c0 = g * GDG_SPAT_GROUP, c1 = imin(C, c0 + GDG_SPAT_GROUP);
+    spat_accumulate(ch, c0, c1, in, stride, hist, hs, j, l, r);
+    part[(long)(2 * g) * n + j] = l; part[(long)(2 * g + 1) * n + j] = r;
+}
+GDG_DEVI void spat_combine(const double *part, int groups, const double *aux, double *outL, double *outR, int n, int j, int accumulate)
+{
+    double l = accumulate ? outL[j] : 0.0, r = accumulate ? outR[j] : 0.0;
+    for (int g = 0; g < groups; g++) { l += part[(long)(2 * g) * n + j]; r += part[(long)(2 * g + 1) * n + j]; }
+    if (aux) { l += aux[j]; r += aux[j]; }
+    outL[j] = l; outR[j] = r;
+}
 
 /* --------------------------------------------------------------------------
  * tuner autocorrelation (tuner/tuner.go:379-446): real FFT of size F through a

@@ -49,6 +49,16 @@ __global__ void k_spat(const gdg_spat_channel *ch, int C, const double *in, long
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j < n) spat_frame(ch, C, in, stride, hist, hs, aux, outL, outR, j, accumulate);
 }
+__global__ void k_spat_partial(const gdg_spat_channel *ch, int C, const double *in, long stride, const double *hist, int hs, double *part, int n)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) spat_partial(ch, C, in, stride, hist, hs, part, n, blockIdx.y, j);
+}
+__global__ void k_spat_combine(const double *part, int groups, const double *aux, double *outL, double *outR, int n, int accumulate)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) spat_combine(part, groups, aux, outL, outR, n, j, accumulate);
+}
 /* history <- last hs samples of (history ++ block): spatializer.go:316-331 */
 __global__ void k_spat_push(int C, const double *in, long stride, const double *hist_in, double *hist_out, int hs, int n)
 {
@@ -175,11 +185,19 @@ int gdgb_launch_chains(const gdg_chain_desc *const *d_descs, int channels, const
 
 int gdgb_launch_spatializer(const gdg_spat_channel *d_ch, int channels, const double *d_in, long stride,
                             const double *d_hist_in, double *d_hist_out, int hs, const double *d_aux,
-                            double *d_outL, double *d_outR, int n, int accumulate, void *stream)
+                            double *d_outL, double *d_outR, int n, int accumulate, double *d_partials, void *stream)
 {
     cudaStream_t s = (cudaStream_t)stream;
-    k_spat<<<(n + 255) / 256, 256, 0, s>>>(d_ch, channels, d_in, stride, d_hist_in, hs, d_aux, d_outL, d_outR, n, accumulate);
-    g_launches++;
+    if (channels <= GDG_SPAT_GROUP || !d_partials) {
+        k_spat<<<(n + 255) / 256, 256, 0, s>>>(d_ch, channels, d_in, stride, d_hist_in, hs, d_aux, d_outL, d_outR, n, accumulate);
+        g_launches++;
+    } else {
+        const int groups = (channels + GDG_SPAT_GROUP - 1) / GDG_SPAT_GROUP;
+        dim3 grid((n + 127) / 128, groups);
+        k_spat_partial<<<grid, 128, 0, s>>>(d_ch, channels, d_in, stride, d_hist_in, hs, d_partials, n);
+        k_spat_combine<<<(n + 127) / 128, 128, 0, s>>>(d_partials, groups, d_aux, d_outL, d_outR, n, accumulate);
+        g_launches += 2;
+    }
     CU(cudaGetLastError());
     if (channels > 0 && hs > 0) {
         dim3 grid((hs + 127) / 128, channels);

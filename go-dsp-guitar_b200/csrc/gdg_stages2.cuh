@@ -415,22 +415,30 @@ GDG_DEV void stage_autowah(gdg_ctx &cx, const gdg_unit_desc &d)
 
 /* ==========================================================================
  * reverb  (effects/reverb.go:41-60 all-pass, 65-116 delay line, 179-338 Process)
- *   i[0] line ring size (max tap) i[1..4] taps i[5..7] all-pass delays D (device ring: 2*(D-1) slots)
+ *   i[0] line ring size (max tap) i[1..4] taps i[5..7] all-pass delays D
  *   i[8] offset of the first all-pass ring inside st (line ring starts at GDG_RV_ST_DATA)
  *   p[0] dryFrac p[1] halfWetFrac p[2..5] tap coefficients p[6] all-pass feedback
- * All-pass: pre[i] = x[i] - g*pre[i-(D-1)], out[i] = g*pre[i] + pre[i-(D-1)] with the
- * pre ring in global memory -> rounds of D-1 independent samples.
+ * All-pass (reverb.go:51-56: the read pointer runs one slot ahead of the write pointer in a ring of D):
+ *   pre[i] = x[i] - g*pre[i-lag],  out[i] = g*pre[i] + pre[i-lag],  lag = D-1.
+ * The block's pre sequence lives in shared memory (P): P[k] first holds the carried history
+ * pre[k-lag] (k < lag, fetched from the global ring before the rounds start) and is overwritten
+ * by pre[k]; rounds of <= lag samples are independent.  Only the last `lag` values go back to
+ * the global ring (a true ring of `lag` slots with its write position).
+ * out = clamp((dry x + hw line) + hw wet): the dry/line part is folded first, which differs from
+ * reverb.go:318-319 "(dry x) + hw (line + wet)" by one rounding (~1e-16).
  * ========================================================================== */
 GDG_DEV void stage_reverb(gdg_ctx &cx, const gdg_unit_desc &d)
 {
     const int n = cx.n, hs = d.i[0];
-    double *x = SM_CUR(cx), *line = SM_ALT(cx), *w = SM_S, *st = d.st;
+    double *x = SM_CUR(cx), *w = SM_ALT(cx), *P = SM_S, *st = d.st;
     double *lring = st + GDG_RV_ST_DATA;
     const double g = d.p[6];
+    /* delay line taps -> w */
     GDG_THREADS_BEGIN
         const int pos = (int)st_geti(st, GDG_RV_ST_LINEPOS);
         for (int k = tid; k < n; k += GDG_NT) {
             double pre = 0.0;
+#pragma unroll
             for (int j = 0; j < 4; j++) {
                 const int idx = k - d.i[1 + j];
                 double cs = 0.0;
@@ -438,50 +446,50 @@ GDG_DEV void stage_reverb(gdg_ctx &cx, const gdg_unit_desc &d)
                 else if (idx >= -hs) cs = ring_get(lring, hs, pos, hs + idx);
                 pre += d.p[2 + j] * cs;
             }
-            line[sw(k)] = pre;
             w[sw(k)] = pre;
         }
     GDG_THREADS_END
-    /* push the dry block into the line ring */
+    /* push the dry block into the line ring, then fold dry + line */
     GDG_THREADS_BEGIN
         const int pos = (int)st_geti(st, GDG_RV_ST_LINEPOS);
-        if (n >= hs) { for (int q = tid; q < hs; q += GDG_NT) lring[q] = x[sw(n - hs + q)]; }
-        else { for (int k = tid; k < n; k += GDG_NT) { int p = pos + k; if (p >= hs) p -= hs; lring[p] = x[sw(k)]; } }
-    GDG_THREADS_END
-    GDG_THREADS_BEGIN
-        if (tid == 0) { const int pos = (int)st_geti(st, GDG_RV_ST_LINEPOS); st_seti(st, GDG_RV_ST_LINEPOS, n >= hs ? 0 : (pos + n) % hs); }
+        for (int k = tid; k < n; k += GDG_NT) {
+            const double xv = x[sw(k)];
+            if (n >= hs) { if (k >= n - hs) lring[k - (n - hs)] = xv; }
+            else { int p = pos + k; if (p >= hs) p -= hs; lring[p] = xv; }
+            x[sw(k)] = (d.p[0] * xv) + (d.p[1] * w[sw(k)]);
+        }
     GDG_THREADS_END
     int off = d.i[8];
     for (int a = 0; a < 3; a++) {
-        /* pre[i] = x[i] - g*pre[i-lag], out[i] = g*pre[i] + pre[i-lag], lag = D-1 (reverb.go:51-56: the read
-         * pointer runs one slot ahead of the write pointer in a ring of D).  The device ring has 2*lag slots
-         * indexed by time, so the slots written in a round of <= lag samples are disjoint from the slots read. */
-        const int D = d.i[5 + a], lag = D - 1, Dr = 2 * lag;
+        const int D = d.i[5 + a], lag = D - 1;
         double *ring = st + off;
-        off += Dr;
+        off += lag > 0 ? lag : 0;
         if (lag <= 0) continue;                              /* not reachable: D >= 100 for every supported rate */
-        const int w0 = (int)st_geti(st, GDG_RV_ST_APPTR + a);
+        const int w0 = (int)st_geti(st, GDG_RV_ST_APPTR + a);   /* ring slot of the oldest carried value */
+        const int nh = imin(lag, n);
+        GDG_THREADS_BEGIN
+            if (a == 0 && tid == 0) { const int pos = (int)st_geti(st, GDG_RV_ST_LINEPOS); st_seti(st, GDG_RV_ST_LINEPOS, n >= hs ? 0 : (pos + n) % hs); }
+            for (int k = tid; k < nh; k += GDG_NT) { int p = w0 + k; if (p >= lag) p -= lag; P[k] = ring[p]; }
+        GDG_THREADS_END
         for (int r0 = 0; r0 < n; r0 += lag) {
             const int r1 = imin(n, r0 + lag);
             GDG_THREADS_BEGIN
                 for (int k = r0 + tid; k < r1; k += GDG_NT) {
-                    const int pw = (w0 + k) % Dr;
-                    int pr = pw - lag;
-                    if (pr < 0) pr += Dr;
-                    const double dl = ring[pr];
+                    const double dl = k < lag ? P[k] : P[k - lag];
                     const double pre = w[sw(k)] - (g * dl);
-                    ring[pw] = pre;
+                    P[k] = pre;
                     w[sw(k)] = (g * pre) + dl;
                 }
             GDG_THREADS_END
         }
+        /* carry the last `lag` pre values: ring slot (w0 + k) % lag <- pre[k] for k >= n - lag */
         GDG_THREADS_BEGIN
-            if (tid == 0) st_seti(st, GDG_RV_ST_APPTR + a, (w0 + n) % Dr);
+            for (int k = imax(0, n - lag) + tid; k < n; k += GDG_NT) ring[(w0 + k) % lag] = P[k];
+            if (tid == 0) st_seti(st, GDG_RV_ST_APPTR + a, (w0 + n) % lag);
         GDG_THREADS_END
     }
     GDG_THREADS_BEGIN
-        for (int k = tid; k < n; k += GDG_NT)
-            x[sw(k)] = clamp1((d.p[0] * x[sw(k)]) + (d.p[1] * (line[sw(k)] + w[sw(k)])));
+        for (int k = tid; k < n; k += GDG_NT) x[sw(k)] = clamp1(x[sw(k)] + (d.p[1] * w[sw(k)]));
     GDG_THREADS_END
 }
 

@@ -75,9 +75,15 @@ int gdgb_launch_chains(const gdg_chain_desc *const *descs, int channels, const d
 }
 
 int gdgb_launch_spatializer(const gdg_spat_channel *ch, int C, const double *in, long stride, const double *hist_in,
-                            double *hist_out, int hs, const double *aux, double *outL, double *outR, int n, int accumulate, void *)
+                            double *hist_out, int hs, const double *aux, double *outL, double *outR, int n, int accumulate, double *part, void *)
 {
-    for (int j = 0; j < n; j++) spat_frame(ch, C, in, stride, hist_in, hs, aux, outL, outR, j, accumulate);
+    if (C <= GDG_SPAT_GROUP || !part) {
+        for (int j = 0; j < n; j++) spat_frame(ch, C, in, stride, hist_in, hs, aux, outL, outR, j, accumulate);
+    } else {
+        const int groups = (C + GDG_SPAT_GROUP - 1) / GDG_SPAT_GROUP;
+        for (int g = 0; g < groups; g++) for (int j = 0; j < n; j++) spat_partial(ch, C, in, stride, hist_in, hs, part, n, g, j);
+        for (int j = 0; j < n; j++) spat_combine(part, groups, aux, outL, outR, n, j, accumulate);
+    }
     for (int c = 0; c < C; c++)
         for (int i = 0; i < hs; i++) {
             const long src = (long)i + n - hs;

@@ -274,6 +274,21 @@ def test_spatializer_parity(lib, fs, n):
         assert common.rms(ya - yb) <= 1e-12, k
 
 
+def test_spatializer_many_channels_group_partials(lib):
+    """More than 32 channels: 32-channel group partial sums combined in ascending order (not the strictly
+    sequential order of spatializer.go:170-308): differences are rounding-level."""
+    C, fs, n = 70, 192000, 2048
+    a, b = orc.Spatializer(C), gdg.Spatializer(C, lib=lib)
+    for c in range(C):
+        for s_ in (a, b):
+            s_.set_azimuth(c, -80.0 + 160.0 * c / (C - 1)); s_.set_distance(c, 0.3 + 0.1 * (c % 17)); s_.set_level(c, 0.2 + 0.01 * c)
+    a.set_sample_rate(fs); b.set_sample_rate(fs)
+    x = np.stack([common.synth_fast(c, fs, 3 * n) for c in range(C)])
+    for k in range(3):
+        ya, yb = a.process(x[:, k * n:(k + 1) * n]), b.process(x[:, k * n:(k + 1) * n])
+        assert common.rms(ya - yb) <= 1e-12 and np.abs(ya).max() > 1.0
+
+
 def test_spatializer_default_position_is_plain_sum(lib):
     s = gdg.Spatializer(3, lib=lib)
     x = np.stack([common.synth_fast(c, 96000, 512) for c in range(3)])
