@@ -45,6 +45,9 @@
 #define GDG_THREADS_END_NOSYNC }
 #define GDG_CONST __constant__
 #define GDG_LDG(p) __ldg(p)
+/* coherent load from GLOBAL memory (unit state): tells the compiler the address space, so that the loads can be
+ * hoisted over shared-memory stores and batched */
+#define GDG_LDST(p) __ldcg(p)
 /* thread-private value that stays in a register across phases */
 #define GDG_REG(type, name) type name
 #define GDG_REGA(type, name, cnt) type name[cnt]
@@ -57,6 +60,7 @@
 #define GDG_THREADS_END_NOSYNC }
 #define GDG_CONST static
 #define GDG_LDG(p) (*(p))
+#define GDG_LDST(p) (*(p))
 /* host emulation: one slot per emulated thread */
 #define GDG_REG(type, name) type name##_r[GDG_NT]
 #define GDG_REGA(type, name, cnt) type name##_r[GDG_NT][cnt]
@@ -204,7 +208,7 @@ GDG_DEVI double ring_get(const double *ring, int hs, int pos, int q)
 {
     int p = pos + q;
     if (p >= hs) p -= hs;
-    return ring[p];
+    return GDG_LDST(ring + p);
 }
 /* x[idx] for idx in [-hs, n): block sample or history */
 GDG_DEVI double hist_or_block(const double *blk, const double *ring, int hs, int pos, int idx)
@@ -637,6 +641,7 @@ GDG_DEV void stage_delay(gdg_ctx &cx, const gdg_unit_desc &d)
     GDG_THREADS_BEGIN
         const int pos = (int)st_geti(st, GDG_RING_ST_POS);
         const double *ring = st + GDG_RING_ST_DATA;
+        #pragma unroll 4
         for (int k = tid; k < n; k += GDG_NT) {
             const double dl = hist_or_block(x, ring, ds, pos, k - ds);
             y[sw(k)] = clamp1(lvl * (x[sw(k)] + (fb * dl)));
@@ -662,6 +667,7 @@ GDG_DEV void stage_chorus(gdg_ctx &cx, const gdg_unit_desc &d)
          * sine, i.e. ~1e-13 samples of delay - far inside the 1e-9 budget) */
         double cj[5], sj[5];
         for (int j = 0; j < 5; j++) { sj[j] = sin((0.4 * GDG_PI) * (double)j); cj[j] = cos((0.4 * GDG_PI) * (double)j); }
+        #pragma unroll 4
         for (int k = tid; k < n; k += GDG_NT) {
             const double t = (double)k / sr;
             const double zero_phase = fmod(prev + (ang * t), GDG_TWO_PI);
@@ -693,6 +699,7 @@ GDG_DEV void stage_flanger(gdg_ctx &cx, const gdg_unit_desc &d)
         const int pos = (int)st_geti(st, GDG_RING_ST_POS);
         const double *ring = st + GDG_RING_ST_DATA;
         const double prev = st[0];
+        #pragma unroll 4
         for (int k = tid; k < n; k += GDG_NT) {
             const double t = (double)k * sr_inv;
             const double phase = fmod(prev + (ang * t), GDG_TWO_PI);

@@ -436,6 +436,7 @@ GDG_DEV void stage_reverb(gdg_ctx &cx, const gdg_unit_desc &d)
     /* delay line taps -> w */
     GDG_THREADS_BEGIN
         const int pos = (int)st_geti(st, GDG_RV_ST_LINEPOS);
+#pragma unroll 4
         for (int k = tid; k < n; k += GDG_NT) {
             double pre = 0.0;
 #pragma unroll
@@ -469,7 +470,8 @@ GDG_DEV void stage_reverb(gdg_ctx &cx, const gdg_unit_desc &d)
         const int nh = imin(lag, n);
         GDG_THREADS_BEGIN
             if (a == 0 && tid == 0) { const int pos = (int)st_geti(st, GDG_RV_ST_LINEPOS); st_seti(st, GDG_RV_ST_LINEPOS, n >= hs ? 0 : (pos + n) % hs); }
-            for (int k = tid; k < nh; k += GDG_NT) { int p = w0 + k; if (p >= lag) p -= lag; P[k] = ring[p]; }
+#pragma unroll 4
+            for (int k = tid; k < nh; k += GDG_NT) { int p = w0 + k; if (p >= lag) p -= lag; P[k] = GDG_LDST(ring + p); }
         GDG_THREADS_END
         for (int r0 = 0; r0 < n; r0 += lag) {
             const int r1 = imin(n, r0 + lag);
@@ -706,7 +708,8 @@ GDG_DEV void stage_poweramp(gdg_ctx &cx, const gdg_unit_desc &d, const double *t
         if (tid < 65) cst(wc, tid, tw_full(tw, imin(64 * tid * fstep, GDG_MAX_FFT - 1) ));
         if (tid >= 128 && tid < 192) cst(wf, tid - 128, twd(tw, (tid - 128) * fstep));
         /* overlap cells [0, ns) are always needed: fetch them now, hidden behind the transform */
-        for (int q = tid; q < ns; q += GDG_NT) tl[q] = q < F - zlen ? tail[q] : 0.0;
+#pragma unroll 4
+        for (int q = tid; q < ns; q += GDG_NT) tl[q] = q < F - zlen ? GDG_LDST(tail + q) : 0.0;
     GDG_THREADS_END
     GDG_THREADS_BEGIN
         for (int r = 0; r < per; r++) {
