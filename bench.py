@@ -50,6 +50,15 @@ METRIC = "Msamples/sec full 12-stage chain @192kHz 4xOS"
 WORKLOAD = "cfg5: %d-ch/GPU CHAIN12 (4xOS, 8192-tap IR, spatializer), 192 kHz, block 8192"
 
 
+def kchain_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one k_chain launch from the committed ncu capture."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "kchain_traffic.json")) as f:
+            return float(json.load(f)["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -324,7 +333,8 @@ def main():
             "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": C * N * 8, "d2h_bytes_per_step": (C + 2) * N * 8, "api": e2e_api},
             "gpu_launches": int(round(launches_per_step * args.steps)), "gpu_launches_per_step": launches_per_step,
             "roofline": {"kernel": "k_chain (fused 12-unit segment, one CTA per channel)", "bound": "hbm", "achieved": achieved,
-                         "peak": hbm_peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+                         "peak": hbm_peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": kchain_traffic() if C == 1024 else None,
+                         "traffic_note": "bytes per launch from the committed ncu capture (profiles/kchain_traffic.json); ~1 MB of unit state per channel-block (delay/reverb/chorus rings, FFT tail) on top of the 134 MB of audio",
                          "ms_per_launch": ms_k, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_SAMPLE * C * N,
                          "note": "FP64-pipe-bound by construction (~136 FLOP/B, SURVEY.md 8d); see fp64",
                          "fp64": {"achieved_tflops": tfl, "peak_tflops": FP64_PEAK_TFLOPS, "frac": tfl / FP64_PEAK_TFLOPS,
