@@ -275,31 +275,25 @@ def main():
     for k in range(2):
         h_in[k].copy_(ring_in[k])
     torch.cuda.synchronize()
-    if world == 1:
-        import ctypes as Ct
-        handles = (Ct.c_void_p * C)(*[c_._h for c_ in chains])
-        ptrs_in = [(Ct.c_void_p * C)(*[h_in[k].data_ptr() + 8 * N * c for c in range(C)]) for k in range(2)]
-        ptrs_out = [(Ct.c_void_p * (C + 2))(*[h_out[k].data_ptr() + 8 * N * c for c in range(C + 2)]) for k in range(2)]
+    import ctypes as Ct
+    handles = (Ct.c_void_p * C)(*[c_._h for c_ in chains])
+    ptrs_in = [(Ct.c_void_p * C)(*[h_in[k].data_ptr() + 8 * N * c for c in range(C)]) for k in range(2)]
+    ptrs_out = [(Ct.c_void_p * (C + 2))(*[h_out[k].data_ptr() + 8 * N * c for c in range(C + 2)]) for k in range(2)]
+    d_master = torch.empty((2, N), device=dev, dtype=torch.float64)
 
-        def step_e2e(k):
-            rc = lib.gdg_controller_process(handles, C, tuner._h, 0, spat._h, ptrs_in[k % 2], ptrs_out[k % 2], C + 2, N, FS)
-            if rc < 0:
-                raise RuntimeError(lib.gdg_last_error().decode())
-        e2e_api = "gdg_controller_process (host buffers, one C-ABI call per block)"
-    else:
-        d_in = torch.empty((C, N), device=dev, dtype=torch.float64)
-        d_out = torch.empty((C + 2, N), device=dev, dtype=torch.float64)
-
-        def step_e2e(k):
-            d_in.copy_(h_in[k % 2], non_blocking=True)
-            if tuner is not None:
-                tuner.process_device(d_in.data_ptr(), N, FS, sh)
-            runner.process_device(d_in.data_ptr(), d_out.data_ptr(), N, N, FS, sh)
-            spat.process_device(d_out.data_ptr(), N, d_out.data_ptr() + 8 * C * N, N, N, None, False, sh)
-            dist.reduce(d_out[C:], dst=0, op=dist.ReduceOp.SUM)
-            h_out[k % 2].copy_(d_out, non_blocking=True)
+    def step_e2e(k):
+        # one C-ABI call on HOST buffers: H2D, tuner feed, chains, spatializer (this rank's partial master), D2H - pipelined inside
+        rc = lib.gdg_controller_process(handles, C, tuner._h if tuner is not None else None, 0 if tuner is not None else -1,
+                                        spat._h, ptrs_in[k % 2], ptrs_out[k % 2], C + 2, N, FS)
+        if rc < 0:
+            raise RuntimeError(lib.gdg_last_error().decode())
+        if world > 1:                                            # the one exchange step: sum the partial masters onto rank 0
+            d_master.copy_(h_out[k % 2][C:], non_blocking=True)
+            dist.reduce(d_master, dst=0, op=dist.ReduceOp.SUM)
+            if rank == 0:
+                h_out[k % 2][C:].copy_(d_master, non_blocking=True)
             stream.synchronize()
-        e2e_api = "pinned H2D + gdg_process_batch_device + gdg_spatializer_process_device + NCCL reduce + D2H"
+    e2e_api = "gdg_controller_process (host buffers, one C-ABI call per block)" + (" + NCCL reduce of the [2][8192] master" if world > 1 else "")
     barrier()
     t0 = time.perf_counter()
     for k in range(max(1, args.warmup // 2)):

@@ -206,7 +206,7 @@ namespace {
 /* ------------------------------------------------------------------------ */
 /* compiled power-amp filters: device spectrum shared between chains           */
 /* ------------------------------------------------------------------------ */
-struct DeviceSpectrum { double *d_H = nullptr; int L = 0, F = 0, logM = 0; ~DeviceSpectrum() { if (d_H) gdgb_free(d_H); } };
+struct DeviceSpectrum { double *d_H = nullptr; int L = 0, F = 0, logM = 0, K = 1; ~DeviceSpectrum() { if (d_H) gdgb_free(d_H); } };
 std::mutex g_spec_mutex;
 std::map<std::string, std::weak_ptr<DeviceSpectrum>> g_spec_cache;
 
@@ -214,19 +214,28 @@ std::shared_ptr<DeviceSpectrum> make_spectrum(const std::vector<double> &coeffs)
 {
     const int L = (int)coeffs.size();
     uint32_t e = 0;
-    const uint64_t B = next_pow2((uint64_t)L, &e);
+    uint64_t B = next_pow2((uint64_t)L, &e);
+    int K = 1;
+    if (2 * B > GDG_MAX_FFT) {                               /* longer than 8192 taps: partitions of GDG_MAX_FFT/2 taps */
+        B = GDG_MAX_FFT / 2; e = 13;
+        K = (int)((L + (int)B - 1) / (int)B);
+    }
     const int F = (int)(2 * B);
     std::string key((const char *)coeffs.data(), coeffs.size() * sizeof(double));
     std::lock_guard<std::mutex> lk(g_spec_mutex);
     auto it = g_spec_cache.find(key);
     if (it != g_spec_cache.end()) if (auto sp = it->second.lock()) return sp;
     auto sp = std::make_shared<DeviceSpectrum>();
-    sp->L = L; sp->F = F; sp->logM = (int)e;               /* M = F/2 = B = 2^e */
-    std::vector<double> padded((size_t)F, 0.0);
-    std::copy(coeffs.begin(), coeffs.end(), padded.begin());
-    std::vector<cplx> H = real_spectrum(padded);            /* filter.go:395-401 */
-    std::vector<double> packed(2 * ((size_t)F / 2 + 1));
-    for (int k = 0; k <= F / 2; k++) { packed[2 * k] = H[(size_t)k].real(); packed[2 * k + 1] = H[(size_t)k].imag(); }
+    sp->L = L; sp->F = F; sp->logM = (int)e; sp->K = K;     /* M = F/2 = B = 2^e */
+    const size_t bins = (size_t)F / 2 + 1;
+    std::vector<double> packed(2 * bins * (size_t)K);
+    for (int p = 0; p < K; p++) {
+        std::vector<double> padded((size_t)F, 0.0);
+        const size_t lo = (size_t)p * B, hi = std::min((size_t)L, lo + (size_t)B);
+        std::copy(coeffs.begin() + lo, coeffs.begin() + hi, padded.begin());
+        std::vector<cplx> H = real_spectrum(padded);        /* filter.go:395-401 */
+        for (size_t k = 0; k < bins; k++) { packed[2 * (p * bins + k)] = H[k].real(); packed[2 * (p * bins + k) + 1] = H[k].imag(); }
+    }
     sp->d_H = (double *)gdgb_alloc(packed.size() * sizeof(double));
     if (!sp->d_H || gdgb_upload(sp->d_H, packed.data(), packed.size() * sizeof(double))) return nullptr;
     g_spec_cache[key] = sp;
@@ -297,7 +306,7 @@ struct Unit {
     int os_factor() const { std::string o = disc("oversampling"); return o == "2" ? 2 : (o == "4" ? 4 : 1); }
 
     int compile_poweramp(uint32_t rate);
-    int prepare(uint32_t rate);
+    int prepare(uint32_t rate, size_t n);
 };
 
 /* effects/poweramp.go:25-127 compile */
@@ -326,13 +335,15 @@ int Unit::compile_poweramp(uint32_t rate)
 }
 
 /* Resolve parameters -> descriptor (what each Process body recomputes per block in the reference). */
-int Unit::prepare(uint32_t rate)
+int Unit::prepare(uint32_t rate, size_t n)
 {
     if (type == GDG_UNIT_POWERAMP && rate != pa_rate) {     /* poweramp.go:187-199 */
         pa_rate = rate;
         compile_poweramp(rate);
         dirty = true;
     }
+    if (type == GDG_UNIT_POWERAMP && pa_spec && pa_spec->K > 1 && n != GDG_MAX_N)
+        return fail("power_amp: a %d-tap filter runs as a partitioned convolution that is only supported for blocks of %d samples (got %zu)", pa_spec->L, GDG_MAX_N, n);
     if (valid && !dirty && cached_rate == rate) return 0;
     gdg_unit_desc d; memset(&d, 0, sizeof d);
     d.type = type;
@@ -490,18 +501,17 @@ int Unit::prepare(uint32_t rate)
         d.i[0] = L;
         if (L > 0) {
             if (pa_new_filter || !pa_spec) {
-                uint32_t e = 0;
-                const uint64_t B = next_pow2((uint64_t)L, &e);
-                if (2 * B > GDG_MAX_FFT)
-                    return fail("power_amp: compiled filter has %d taps; filters beyond %d taps (FFT > %d) are not supported by the "
-                                "shared-memory convolution yet - choose filter_order <= %d", L, GDG_MAX_FFT / 2, GDG_MAX_FFT, GDG_MAX_FFT / 2);
                 pa_spec = make_spectrum(pa_filter.coeffs);
                 if (!pa_spec) return backend_fail("filter spectrum upload failed");
                 /* a recompiled filter is a NEW filter object in the reference: fresh (zero) overlap tail */
-                if (d_st) { gdgb_free(d_st); d_st = nullptr; }
-                if (ensure_state((size_t)pa_spec->F + 1, pa_spec->F)) return -1;   /* tail[F] + zero-run word */
+                if (d_st) { gdgb_sync(); gdgb_free(d_st); d_st = nullptr; }
+                const size_t words = (size_t)pa_spec->F + 2 + (pa_spec->K > 1 ? (size_t)pa_spec->K * (pa_spec->F + 2) : 0);
+                if (ensure_state(words, pa_spec->F)) return -1;   /* tail[F], zero-run word, slot word, spectrum delay line */
                 pa_new_filter = false;
             }
+            d.i[3] = pa_spec->K; d.i[4] = pa_spec->F + 2;
+            if (pa_spec->K > 1 && n != GDG_MAX_N)
+                return fail("power_amp: a %d-tap filter runs as a partitioned convolution that is only supported for blocks of %d samples (got %zu)", pa_spec->L, GDG_MAX_N, n);
             d.i[1] = pa_spec->F; d.i[2] = pa_spec->logM; d.aux = pa_spec->d_H;
         }
         break; }
@@ -584,12 +594,12 @@ struct gdg_chain {
     ~gdg_chain() { for (auto p : d_desc) gdgb_free(p); if (d_in) gdgb_free(d_in); if (d_out) gdgb_free(d_out); }
 
     /* bring the device descriptors up to date; returns number of segments or -1 */
-    int prepare(uint32_t rate)
+    int prepare(uint32_t rate, size_t n)
     {
         bool changed = topo_dirty;
         std::vector<Unit *> active;
         for (auto &s : slots) if (!s.bypass) {
-            int r = s.unit->prepare(rate);
+            int r = s.unit->prepare(rate, n);
             if (r < 0) return -1;
             if (r > 0) changed = true;
             active.push_back(s.unit.get());
@@ -631,7 +641,7 @@ std::mutex g_batch_mutex;
 std::unique_ptr<Batch> g_batch;
 
 /* bring descriptors + pointer tables of the batch up to date; returns the number of segment rounds or -1 */
-int prepare_batch(gdg_chain *const *chains, size_t C, uint32_t rate, void *stream)
+int prepare_batch(gdg_chain *const *chains, size_t C, uint32_t rate, size_t n, void *stream)
 {
     if (!g_batch || g_batch->chains.size() != C || !std::equal(g_batch->chains.begin(), g_batch->chains.end(), chains)) {
         g_batch.reset(new Batch());
@@ -641,7 +651,7 @@ int prepare_batch(gdg_chain *const *chains, size_t C, uint32_t rate, void *strea
     size_t rounds = 1;
     std::vector<int> nseg(C);
     for (size_t c = 0; c < C; c++) {
-        const int r = chains[c]->prepare(rate);
+        const int r = chains[c]->prepare(rate, n);
         if (r < 0) return -1;
         nseg[c] = r; rounds = std::max(rounds, (size_t)r);
     }
@@ -682,7 +692,7 @@ int run_batch_device(gdg_chain *const *chains, size_t C, const double *d_in, dou
 {
     if (check_block(n)) return -1;
     std::lock_guard<std::mutex> lk(g_batch_mutex);
-    const int rounds = prepare_batch(chains, C, rate, stream);
+    const int rounds = prepare_batch(chains, C, rate, n, stream);
     if (rounds < 0) return -1;
     return launch_batch(0, C, rounds, d_in, d_out, stride, n, stream);
 }
@@ -835,7 +845,7 @@ int host_block(gdg_chain *const *chains, size_t C, gdg_tuner *tuner, int tuner_c
                const double *const *in, double *const *out, size_t n_out_rows, size_t n, uint32_t rate)
 {
     std::lock_guard<std::mutex> lk(g_batch_mutex);
-    const int rounds = prepare_batch(chains, C, rate, gdgb_stream());
+    const int rounds = prepare_batch(chains, C, rate, n, gdgb_stream());
     if (rounds < 0) return -1;
     Batch &b = *g_batch;
     if (stage_buffers(b, (C + 2) * n)) return -1;

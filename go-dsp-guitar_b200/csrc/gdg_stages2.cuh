@@ -498,9 +498,13 @@ GDG_DEV void stage_reverb(gdg_ctx &cx, const gdg_unit_desc &d)
 /* ==========================================================================
  * power_amp: FFT overlap-add FIR  (effects/poweramp.go:186-216 -> filter/filter.go:342-515)
  *   i[0] L (taps; 0 = empty filter -> zeros, -1 = no filter compiled -> zeros)
- *   i[1] F (real FFT size = 2*nextPow2(L) <= GDG_MAX_FFT)   i[2] log2(F/2)
- *   aux: H[k], k = 0..F/2 (interleaved re,im) = first half of RealFourier(zero-padded h)
- *   st: tail[F]
+ *   i[1] F (real FFT size = 2*nextPow2(L), capped at GDG_MAX_FFT)   i[2] log2(F/2)
+ *   i[3] K partitions (1 unless L > GDG_MAX_FFT/2)   i[4] word offset of the spectrum delay line in st
+ *   aux: H_p[k], p < K, k = 0..F/2 (interleaved re,im) = first half of RealFourier(zero-padded partition p of h)
+ *   st: tail[F], zero-run word, [K > 1: current slot word, then K x (F/2 + 1) complex input spectra]
+ * Filters longer than 8192 taps run as a uniformly partitioned convolution (block = partition = 8192):
+ * y_t = IFFT(sum_p X_(t-p) H_p) - the same linear convolution the reference evaluates with one
+ * 2*nextPow2(L)-point FFT per 8192-sample hop (filter.go:372-455), then the same overlap-add and clamp.
  * Blocks of B = F/2 samples (filter.go:372-388): out = clamp(y[0:ns] + tail[0:ns]),
  * tail <- (y + tail)[ns:F] shifted, zero-filled.  All nb = ceil(n/B) block FFTs sit in
  * R side by side (2B doubles each) and are transformed together.
@@ -690,6 +694,10 @@ GDG_DEV void stage_poweramp(gdg_ctx &cx, const gdg_unit_desc &d, const double *t
     double *tl = SM_S;                                           /* prefetched overlap tail (plain layout) */
     const double *H = d.aux;
     const int zlen = (int)st_geti(tail, F);                      /* trailing zeros guaranteed in tail[] */
+    const int K = d.i[3] > 1 ? d.i[3] : 1;                       /* partitions */
+    double *fdl = d.st + d.i[4];                                 /* K x (M + 1) complex input spectra, slot ring */
+    const int slot = K > 1 ? (int)st_geti(tail, F + 1) : 0;
+    const long hstride = 2L * (M + 1);
     const int fstep = GDG_MAX_FFT / F;                           /* W_F^k = tw[k * MAXFFT/F] */
     GDG_REGA(double, buf, 32);
     /* pack: block j -> complex points (x[j ns + 2c], x[j ns + 2c + 1]), c < ns/2, zero padded to M; through
@@ -727,7 +735,15 @@ GDG_DEV void stage_poweramp(gdg_ctx &cx, const gdg_unit_desc &d, const double *t
             if (k == 0) {
                 const gdg_c2 z0 = cld(D, cz(zb));
                 const double x0 = z0.re + z0.im, xm = z0.re - z0.im;     /* X[0], X[M] (real) */
-                const double y0 = x0 * GDG_LDG(H + 0), ym = xm * GDG_LDG(H + 2 * M);  /* real(dc), real(nyquist) of the product */
+                double y0 = x0 * GDG_LDG(H + 0), ym = xm * GDG_LDG(H + 2 * M);  /* real(dc), real(nyquist) of the product */
+                if (K > 1) {
+                    for (int p = 1; p < K; p++) {
+                        const double *X = fdl + (long)((slot - p + K) % K) * hstride, *Hp = H + (long)p * hstride;
+                        y0 += GDG_LDST(X + 0) * GDG_LDG(Hp + 0); ym += GDG_LDST(X + 2 * M) * GDG_LDG(Hp + 2 * M);
+                    }
+                    double *Xc = fdl + (long)slot * hstride;
+                    Xc[0] = x0; Xc[1] = 0.0; Xc[2 * M] = xm; Xc[2 * M + 1] = 0.0;
+                }
                 gdg_c2 o; o.re = 0.5 * (y0 + ym); o.im = 0.5 * (y0 - ym);
                 cst(D, cz(zb), o);
             } else {
@@ -744,7 +760,19 @@ GDG_DEV void stage_poweramp(gdg_ctx &cx, const gdg_unit_desc &d, const double *t
                 const gdg_c2 s2 = cadd(zbv, cconj(za)), d2 = csub(zbv, cconj(za));
                 const gdg_c2 t2 = cmul(cconj(jw), d2);                    /* j W_F^(M-k) = conj(j W_F^k) */
                 gdg_c2 xb; xb.re = 0.5 * (s2.re - t2.re); xb.im = 0.5 * (s2.im - t2.im);
-                const gdg_c2 ya = cmul(xa, ha), yb = cmul(xb, hb);
+                gdg_c2 ya = cmul(xa, ha), yb = cmul(xb, hb);
+                if (K > 1) {
+                    for (int p = 1; p < K; p++) {
+                        const double *X = fdl + (long)((slot - p + K) % K) * hstride, *Hp = H + (long)p * hstride;
+                        gdg_c2 xp, hp;
+                        xp.re = GDG_LDST(X + 2 * k); xp.im = GDG_LDST(X + 2 * k + 1); hp.re = GDG_LDG(Hp + 2 * k); hp.im = GDG_LDG(Hp + 2 * k + 1);
+                        ya = cadd(ya, cmul(xp, hp));
+                        xp.re = GDG_LDST(X + 2 * k2); xp.im = GDG_LDST(X + 2 * k2 + 1); hp.re = GDG_LDG(Hp + 2 * k2); hp.im = GDG_LDG(Hp + 2 * k2 + 1);
+                        yb = cadd(yb, cmul(xp, hp));
+                    }
+                    double *Xc = fdl + (long)slot * hstride;
+                    Xc[2 * k] = xa.re; Xc[2 * k + 1] = xa.im; Xc[2 * k2] = xb.re; Xc[2 * k2 + 1] = xb.im;
+                }
                 const gdg_c2 e1 = cadd(ya, cconj(yb)), o1 = cmul(csub(ya, cconj(yb)), cconj(wk));
                 gdg_c2 ra; ra.re = 0.5 * (e1.re - o1.im); ra.im = 0.5 * (e1.im + o1.re);
                 gdg_c2 wk2; wk2.re = -wk.re; wk2.im = wk.im;               /* W_F^(M-k) */
@@ -784,7 +812,7 @@ GDG_DEV void stage_poweramp(gdg_ctx &cx, const gdg_unit_desc &d, const double *t
     GDG_THREADS_BEGIN
         for (int q = tid; q < F - ns; q += GDG_NT) tail[q] = GDG_YR(nb - 1, ns + q);
         for (int q = F - ns + tid; q < F - zlen; q += GDG_NT) tail[q] = 0.0;
-        if (tid == 0) st_seti(tail, F, ns);
+        if (tid == 0) { st_seti(tail, F, ns); if (K > 1) st_seti(tail, F + 1, (slot + 1) % K); }
         double *out = SM_CUR(cx);
         for (int r = 0; r < per_out; r++) { const int k = tid + r * GDG_NT; if (k < n) out[sw(k)] = R(buf)[r]; }
     GDG_THREADS_END

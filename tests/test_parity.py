@@ -176,9 +176,11 @@ def test_poweramp_mix_of_filters_and_none(lib):
         assert np.array_equal(y, np.zeros(4096)) and np.array_equal(a2.process(x[:4096], 96000), y)
 
 
-@pytest.mark.parametrize("L", [256, 1024, 8192])
+@pytest.mark.parametrize("L", [256, 1024, 8192, 16384, 20000, 65536])
 def test_ir_sweep_synthetic(lib, L):
-    """BASELINE.json config 3 (the part that fits the shared-memory FFT): synthetic IRs, 192 kHz."""
+    """BASELINE.json config 3: synthetic IRs of 256 .. 65536 taps at 192 kHz, block 8192.  Up to 8192 taps the
+    whole FFT sits in shared memory; longer filters run as a uniformly partitioned convolution, which must still
+    equal the reference's single 2*nextPow2(L) FFT per hop (filter.go:372-455)."""
     banks = common.make_banks(lib, with_fixture=False, synthetic=[("syn", L, 192000)])
     spec = [("power_amp", {}, {"filter_1": "syn"})]
     a, b = common.make_chain_pair(lib, spec, banks)
@@ -186,11 +188,20 @@ def test_ir_sweep_synthetic(lib, L):
     common.compare_stream(a, b, x, 8192, 192000, label="sweep L=%d" % L)
 
 
-def test_too_long_filter_is_rejected_loudly(lib):
+def test_long_filter_with_short_block_is_rejected_loudly(lib):
     banks = common.make_banks(lib, with_fixture=False, synthetic=[("syn", 20000, 192000)])
     c = common.build_chain(gdg.Chain(banks[1], lib=lib), [("power_amp", {}, {"filter_1": "syn"})])
-    with pytest.raises(gdg.GdgError, match="not supported"):
-        c.process(np.zeros(8192), 192000)
+    with pytest.raises(gdg.GdgError, match="only supported for blocks of 8192"):
+        c.process(np.zeros(1024), 192000)
+
+
+def test_default_filter_order_with_long_bank_response(lib):
+    """filter_order left at its default (1048576): "Guitar: Custom BP" is 15359 taps at 192 kHz -> 2 partitions."""
+    banks = common.make_banks(lib)
+    spec = [("power_amp", {"level_1": -3}, {"filter_1": "Guitar: Custom BP"})]
+    a, b = common.make_chain_pair(lib, spec, banks)
+    x = common.synth_fast(8, 192000, 5 * 8192) * 2.0
+    common.compare_stream(a, b, x, 8192, 192000, label="custom-bp-default-order")
 
 
 # ---- the canonical 12-stage chain ------------------------------------------------------------------
