@@ -34,7 +34,8 @@
  * ========================================================================== */
 #define GDG_FIR_Q 39                         /* taps per polyphase branch */
 #define GDG_ZH 40                            /* halo length per phase (>= Q-1), multiple of 8 */
-#define GDG_ZPS 1200                         /* doubles reserved per phase array: pz(GDG_ZH + GDG_OS_TILE + 1) <= 1200 */
+#define GDG_ZPS 1204                         /* doubles reserved per phase array: pz(GDG_ZH + GDG_OS_TILE + 1) = 1198; == 4 (mod 16) so that
+                                                the F phase arrays start in different banks */
 #define GDG_OS_Z2 GDG_OS_ST_Z2
 GDG_DEVI int pz(int m) { return m + (m >> 3); }      /* one pad per 8: stride-8/9 access patterns spread over banks */
 /* location of oversampled sample (tile-local base index jl, sub-phase ph) in the per-phase arrays */
@@ -120,17 +121,17 @@ GDG_DEV void fuzz_run(gdg_ctx &cx, const gdg_unit_desc &d, double *z, int nbase)
     GDG_THREADS_END
 }
 
-/* one polyphase branch (compile-time phase P) of GDG_FIR_R-consecutive outputs starting at i0: partial sums */
-template <int F, int P, int RR>
-GDG_DEVI void fir_branch(const double *zp, int i0, double (&acc)[RR])
+/* One polyphase branch p of RR consecutive outputs starting at i0: register sliding window over z_p, taps
+ * h[F q + p] from the shared-memory copy hs (lanes of one phase read the same address: broadcast). */
+template <int F, int RR>
+GDG_DEVI void fir_branch(const double *zp, const double *hs, int p, int i0, double (&acc)[RR])
 {
-    const double *hh = F == 2 ? c_aa2 : c_aa4;
     double win[RR];
 #pragma unroll
     for (int r = 0; r < RR; r++) { win[r] = zp[pz(GDG_ZH + i0 + r)]; acc[r] = 0.0; }
 #pragma unroll
     for (int q = 0; q < GDG_FIR_Q; q++) {
-        const double hq = hh[F * q + P];
+        const double hq = hs[F * q + p];
 #pragma unroll
         for (int r = 0; r < RR; r++) acc[r] += hq * win[r];
         if (q + 1 < GDG_FIR_Q) {
@@ -141,89 +142,113 @@ GDG_DEVI void fir_branch(const double *zp, int i0, double (&acc)[RR])
     }
 }
 
+/* up-sampled + shaped samples of base sample j (tile-local jl) into the per-phase arrays */
+template <int F>
+GDG_DEVI void os_produce(const gdg_unit_desc &d, int type, const double *x, const double *uph, double *z, int j, int jl)
+{
+    double xs[6];
+    if (j >= 6) {
+#pragma unroll
+        for (int q = 0; q < 6; q++) xs[q] = x[sw(j - 6 + q)];
+    } else {
+#pragma unroll
+        for (int q = 0; q < 6; q++) { const int idx = j - 6 + q; xs[q] = idx >= 0 ? x[sw(idx)] : uph[8 + idx]; }
+    }
+    const int m0 = pz(GDG_ZH + jl), m1 = pz(GDG_ZH + jl + 1);
+#pragma unroll
+    for (int ph = 0; ph < F; ph++) {
+        double u;
+        if (ph == 0) u = xs[2];                                   /* in[j-4] */
+        else {
+            u = 0.0;
+#pragma unroll
+            for (int q = 0; q < 6; q++) u += xs[q] * (F == 2 ? c_lz2[0][q] : c_lz4[ph - 1][q]);
+        }
+        if (type != GDG_UNIT_FUZZ) u = nl_pointwise(type, d, u);
+        if (ph == 0) z[m0] = u; else z[(F - ph) * GDG_ZPS + m1] = u;
+    }
+}
+
 template <int F>
 GDG_DEV void oversampled_tiles(gdg_ctx &cx, const gdg_unit_desc &d)
 {
-    constexpr int RR = 2 * F;                   /* outputs per thread: (T/RR) * F threads cover the tile */
+    constexpr int RR = 2 * F;                   /* outputs per thread group; F lanes (one per phase) share a group */
     const int n = cx.n, type = d.type;
     double *x = SM_CUR(cx), *y = SM_ALT(cx), *z = SM_S, *st = d.st;
     double *uph = st + (F == 2 ? GDG_OS_ST_UP2 : GDG_OS_ST_UP4);
     double *zh = st + (F == 2 ? GDG_OS_ST_Z2 : GDG_OS_ST_Z4);
-    double *part = z + F * GDG_ZPS;             /* partial sums of phases 1..F-1: (F-1) * GDG_OS_TILE */
+    double *hs = SM_SCANB + 1024;               /* F * 39 taps */
     const int T = imin(n, GDG_OS_TILE);
-    /* carried oversampled history: per phase GDG_ZH + 1 samples */
+    const int stateless = type != GDG_UNIT_FUZZ;
+    /* carried oversampled history: per phase GDG_ZH + 1 samples; taps to shared memory */
     GDG_THREADS_BEGIN
-        for (int q = tid; q < F * (GDG_ZH + 1); q += GDG_NT) { const int p = q / (GDG_ZH + 1), m = q - p * (GDG_ZH + 1); z[p * GDG_ZPS + pz(m)] = zh[q]; }
+        if (tid < F * 64) { const int p = tid >> 6, m = tid & 63; if (m <= GDG_ZH) z[p * GDG_ZPS + pz(m)] = zh[p * (GDG_ZH + 1) + m]; }
+        if (tid < F * GDG_FIR_Q) hs[tid] = F == 2 ? c_aa2[tid] : c_aa4[tid];
     GDG_THREADS_END
     for (int t0 = 0; t0 < n; t0 += T) {
         const int Tt = imin(T, n - t0);
-        /* up-sample (+ stateless nonlinearity) */
+        /* up-sample (+ stateless nonlinearity).  From the second tile on, a stateless unit simply recomputes the
+         * GDG_ZH-sample halo from the block instead of carrying it over from the previous tile. */
         GDG_THREADS_BEGIN
-            for (int jl = tid; jl < Tt; jl += GDG_NT) {
-                const int j = t0 + jl;
-                double xs[6];
-                if (j >= 6) {
-#pragma unroll
-                    for (int q = 0; q < 6; q++) xs[q] = x[sw(j - 6 + q)];
-                } else {
-#pragma unroll
-                    for (int q = 0; q < 6; q++) { const int idx = j - 6 + q; xs[q] = idx >= 0 ? x[sw(idx)] : uph[8 + idx]; }
-                }
-                const int m0 = pz(GDG_ZH + jl), m1 = pz(GDG_ZH + jl + 1);
-#pragma unroll
-                for (int ph = 0; ph < F; ph++) {
-                    double u;
-                    if (ph == 0) u = xs[2];                                   /* in[j-4] */
-                    else {
-                        u = 0.0;
-#pragma unroll
-                        for (int q = 0; q < 6; q++) u += xs[q] * (F == 2 ? c_lz2[0][q] : c_lz4[ph - 1][q]);
-                    }
-                    if (type != GDG_UNIT_FUZZ) u = nl_pointwise(type, d, u);
-                    if (ph == 0) z[m0] = u; else z[(F - ph) * GDG_ZPS + m1] = u;
-                }
-            }
+            const int jlo = (stateless && t0 > 0) ? -GDG_ZH : 0;      /* entries >= ZH - 38 are all the FIR reads */
+            for (int jl = jlo + tid; jl < Tt; jl += GDG_NT) os_produce<F>(d, type, x, uph, z, t0 + jl, jl);
         GDG_THREADS_END
-        if (type == GDG_UNIT_FUZZ) fuzz_run<F>(cx, d, z, Tt);
-        /* polyphase FIR partial sums: warp-uniform phase */
+        if (!stateless) fuzz_run<F>(cx, d, z, Tt);
+        /* polyphase FIR: lane = (group, phase); the F partial sums meet through shuffles (phase order 0+1, 2+3) */
         GDG_THREADS_BEGIN
-            const int warp = tid >> 5, p = warp % F;
-            const int grp = (warp / F) * 32 + (tid & 31);                     /* output group of this thread */
-            const int i0 = grp * RR;
-            if (i0 < Tt) {
+            const int p = tid % F, grp = tid / F;
+            for (int base = 0; base < Tt; base += (GDG_NT / F) * RR) {      /* trip count uniform over the CTA (shuffles below) */
+                const int i0 = base + grp * RR;
                 double acc[RR];
-                const double *zp = z + p * GDG_ZPS;
-                if (F == 2) { if (p == 0) fir_branch<F, 0, RR>(zp, i0, acc); else fir_branch<F, 1, RR>(zp, i0, acc); }
+                if (i0 < Tt) fir_branch<F, RR>(z + p * GDG_ZPS, hs, p, i0, acc);
                 else {
-                    if (p == 0) fir_branch<F, 0, RR>(zp, i0, acc);
-                    else if (p == 1) fir_branch<F, 1 % F, RR>(zp, i0, acc);
-                    else if (p == 2) fir_branch<F, 2 % F, RR>(zp, i0, acc);
-                    else fir_branch<F, 3 % F, RR>(zp, i0, acc);
+#pragma unroll
+                    for (int r = 0; r < RR; r++) acc[r] = 0.0;
                 }
+#if defined(__CUDACC__) && !defined(GDG_HOST_EMU)
 #pragma unroll
-                for (int r = 0; r < RR; r++)
-                    if (i0 + r < Tt) { if (p == 0) y[sw(t0 + i0 + r)] = acc[r]; else part[(p - 1) * GDG_OS_TILE + sw(i0 + r)] = acc[r]; }
+                for (int r = 0; r < RR; r++) {
+                    acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], 1);
+                    if (F == 4) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], 2);
+                }
+                if (p == 0) {
+#pragma unroll
+                    for (int r = 0; r < RR; r++) if (i0 + r < Tt) y[sw(t0 + i0 + r)] = 0.9440608762859234 * clamp1(acc[r]);
+                }
+#else
+                /* host emulation: lanes run one after another - accumulate the phases through the output cells */
+#pragma unroll
+                for (int r = 0; r < RR; r++) if (i0 + r < Tt) {
+                    double &cell = y[sw(t0 + i0 + r)];
+                    if (F == 2) { cell = p == 0 ? acc[r] : 0.9440608762859234 * clamp1(cell + acc[r]); }
+                    else {
+                        double *tmp = SM_SCANA;                   /* (a0 + a1) + (a2 + a3), like the shuffle tree */
+                        if (p == 0) tmp[r] = acc[r];
+                        else if (p == 1) tmp[r] += acc[r];
+                        else if (p == 2) tmp[8 + r] = acc[r];
+                        else cell = 0.9440608762859234 * clamp1(tmp[r] + (tmp[8 + r] + acc[r]));
+                    }
+                }
+#endif
             }
         GDG_THREADS_END
-        /* combine in phase order, clamp, -0.5 dB; stage the halo for the next tile */
-        GDG_THREADS_BEGIN
-            for (int i = tid; i < Tt; i += GDG_NT) {
-                double acc = y[sw(t0 + i)];
-#pragma unroll
-                for (int p = 1; p < F; p++) acc += part[(p - 1) * GDG_OS_TILE + sw(i)];
-                y[sw(t0 + i)] = 0.9440608762859234 * clamp1(acc);
-            }
-            if (tid < F * 64) { const int p = tid >> 6, m = tid & 63; if (m <= GDG_ZH) SM_SCANB[tid] = z[p * GDG_ZPS + pz(m + Tt)]; }
-        GDG_THREADS_END
-        GDG_THREADS_BEGIN
-            if (tid < F * 64) { const int p = tid >> 6, m = tid & 63; if (m <= GDG_ZH) z[p * GDG_ZPS + pz(m)] = SM_SCANB[tid]; }
-        GDG_THREADS_END
+        if (!stateless && t0 + Tt < n) {
+            /* stateful unit: carry the halo (last GDG_ZH + 1 entries of every phase) to the front */
+            GDG_THREADS_BEGIN
+                if (tid < F * 64) { const int p = tid >> 6, m = tid & 63; if (m <= GDG_ZH) SM_SCANB[tid] = z[p * GDG_ZPS + pz(m + Tt)]; }
+            GDG_THREADS_END
+            GDG_THREADS_BEGIN
+                if (tid < F * 64) { const int p = tid >> 6, m = tid & 63; if (m <= GDG_ZH) z[p * GDG_ZPS + pz(m)] = SM_SCANB[tid]; }
+            GDG_THREADS_END
+        }
+        if (t0 + Tt >= n) {
+            /* carry: oversampled history (entries Tt .. Tt + GDG_ZH of the last tile) and the last 8 inputs (oversampling.go:91-93) */
+            GDG_THREADS_BEGIN
+                if (tid < F * 64) { const int p = tid >> 6, m = tid & 63; if (m <= GDG_ZH) zh[p * (GDG_ZH + 1) + m] = z[p * GDG_ZPS + pz(m + Tt)]; }
+                if (tid < 8) SM_MISC[8 + tid] = (n - 8 + tid) >= 0 ? x[sw(n - 8 + tid)] : uph[tid + n];
+            GDG_THREADS_END
+        }
     }
-    /* carry: oversampled history and the last 8 inputs (oversampling.go:91-93) */
-    GDG_THREADS_BEGIN
-        for (int q = tid; q < F * (GDG_ZH + 1); q += GDG_NT) { const int p = q / (GDG_ZH + 1), m = q - p * (GDG_ZH + 1); zh[q] = z[p * GDG_ZPS + pz(m)]; }
-        if (tid < 8) SM_MISC[8 + tid] = (n - 8 + tid) >= 0 ? x[sw(n - 8 + tid)] : uph[tid + n];
-    GDG_THREADS_END
     GDG_THREADS_BEGIN
         if (tid < 8) uph[tid] = SM_MISC[8 + tid];
     GDG_THREADS_END
