@@ -34,8 +34,7 @@
  * ========================================================================== */
 #define GDG_FIR_Q 39                         /* taps per polyphase branch */
 #define GDG_ZH 40                            /* halo length per phase (>= Q-1), multiple of 8 */
-#define GDG_ZPS 1204                         /* doubles reserved per phase array: pz(GDG_ZH + GDG_OS_TILE + 1) = 1198; == 4 (mod 16) so that
-                                                the F phase arrays start in different banks */
+#define GDG_ZPS 1200                         /* doubles reserved per phase array: pz(GDG_ZH + GDG_OS_TILE + 1) = 1198 */
 #define GDG_OS_Z2 GDG_OS_ST_Z2
 GDG_DEVI int pz(int m) { return m + (m >> 3); }      /* one pad per 8: stride-8/9 access patterns spread over banks */
 /* location of oversampled sample (tile-local base index jl, sub-phase ph) in the per-phase arrays */
@@ -121,17 +120,18 @@ GDG_DEV void fuzz_run(gdg_ctx &cx, const gdg_unit_desc &d, double *z, int nbase)
     GDG_THREADS_END
 }
 
-/* One polyphase branch p of RR consecutive outputs starting at i0: register sliding window over z_p, taps
- * h[F q + p] from the shared-memory copy hs (lanes of one phase read the same address: broadcast). */
-template <int F, int RR>
-GDG_DEVI void fir_branch(const double *zp, const double *hs, int p, int i0, double (&acc)[RR])
+/* One polyphase branch (compile-time phase P) of RR consecutive outputs starting at i0: register sliding window
+ * over z_p, taps h[F q + P] as constant-bank operands (uniform across the warp). */
+template <int F, int P, int RR>
+GDG_DEVI void fir_branch(const double *zp, int i0, double (&acc)[RR])
 {
+    const double *hh = F == 2 ? c_aa2 : c_aa4;
     double win[RR];
 #pragma unroll
     for (int r = 0; r < RR; r++) { win[r] = zp[pz(GDG_ZH + i0 + r)]; acc[r] = 0.0; }
 #pragma unroll
     for (int q = 0; q < GDG_FIR_Q; q++) {
-        const double hq = hs[F * q + p];
+        const double hq = hh[F * q + P];
 #pragma unroll
         for (int r = 0; r < RR; r++) acc[r] += hq * win[r];
         if (q + 1 < GDG_FIR_Q) {
@@ -177,13 +177,12 @@ GDG_DEV void oversampled_tiles(gdg_ctx &cx, const gdg_unit_desc &d)
     double *x = SM_CUR(cx), *y = SM_ALT(cx), *z = SM_S, *st = d.st;
     double *uph = st + (F == 2 ? GDG_OS_ST_UP2 : GDG_OS_ST_UP4);
     double *zh = st + (F == 2 ? GDG_OS_ST_Z2 : GDG_OS_ST_Z4);
-    double *hs = SM_SCANB + 1024;               /* F * 39 taps */
+    double *part = z + F * GDG_ZPS;             /* partial sums of phases 1..F-1: (F-1) * GDG_OS_TILE */
     const int T = imin(n, GDG_OS_TILE);
     const int stateless = type != GDG_UNIT_FUZZ;
     /* carried oversampled history: per phase GDG_ZH + 1 samples; taps to shared memory */
     GDG_THREADS_BEGIN
         if (tid < F * 64) { const int p = tid >> 6, m = tid & 63; if (m <= GDG_ZH) z[p * GDG_ZPS + pz(m)] = zh[p * (GDG_ZH + 1) + m]; }
-        if (tid < F * GDG_FIR_Q) hs[tid] = F == 2 ? c_aa2[tid] : c_aa4[tid];
     GDG_THREADS_END
     for (int t0 = 0; t0 < n; t0 += T) {
         const int Tt = imin(T, n - t0);
@@ -194,44 +193,34 @@ GDG_DEV void oversampled_tiles(gdg_ctx &cx, const gdg_unit_desc &d)
             for (int jl = jlo + tid; jl < Tt; jl += GDG_NT) os_produce<F>(d, type, x, uph, z, t0 + jl, jl);
         GDG_THREADS_END
         if (!stateless) fuzz_run<F>(cx, d, z, Tt);
-        /* polyphase FIR: lane = (group, phase); the F partial sums meet through shuffles (phase order 0+1, 2+3) */
+        /* polyphase FIR partial sums: warp w computes phase w % F (taps warp-uniform) of RR outputs per thread */
         GDG_THREADS_BEGIN
-            const int p = tid % F, grp = tid / F;
-            for (int base = 0; base < Tt; base += (GDG_NT / F) * RR) {      /* trip count uniform over the CTA (shuffles below) */
-                const int i0 = base + grp * RR;
+            const int warp = tid >> 5, p = warp % F;
+            const int i0 = ((warp / F) * 32 + (tid & 31)) * RR;
+            if (i0 < Tt) {
                 double acc[RR];
-                if (i0 < Tt) fir_branch<F, RR>(z + p * GDG_ZPS, hs, p, i0, acc);
+                const double *zp = z + p * GDG_ZPS;
+                if (F == 2) { if (p == 0) fir_branch<F, 0, RR>(zp, i0, acc); else fir_branch<F, 1, RR>(zp, i0, acc); }
                 else {
-#pragma unroll
-                    for (int r = 0; r < RR; r++) acc[r] = 0.0;
+                    if (p == 0) fir_branch<F, 0, RR>(zp, i0, acc);
+                    else if (p == 1) fir_branch<F, 1 % F, RR>(zp, i0, acc);
+                    else if (p == 2) fir_branch<F, 2 % F, RR>(zp, i0, acc);
+                    else fir_branch<F, 3 % F, RR>(zp, i0, acc);
                 }
-#if defined(__CUDACC__) && !defined(GDG_HOST_EMU)
 #pragma unroll
-                for (int r = 0; r < RR; r++) {
-                    acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], 1);
-                    if (F == 4) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], 2);
-                }
-                if (p == 0) {
-#pragma unroll
-                    for (int r = 0; r < RR; r++) if (i0 + r < Tt) y[sw(t0 + i0 + r)] = 0.9440608762859234 * clamp1(acc[r]);
-                }
-#else
-                /* host emulation: lanes run one after another - accumulate the phases through the output cells */
-#pragma unroll
-                for (int r = 0; r < RR; r++) if (i0 + r < Tt) {
-                    double &cell = y[sw(t0 + i0 + r)];
-                    if (F == 2) { cell = p == 0 ? acc[r] : 0.9440608762859234 * clamp1(cell + acc[r]); }
-                    else {
-                        double *tmp = SM_SCANA;                   /* (a0 + a1) + (a2 + a3), like the shuffle tree */
-                        if (p == 0) tmp[r] = acc[r];
-                        else if (p == 1) tmp[r] += acc[r];
-                        else if (p == 2) tmp[8 + r] = acc[r];
-                        else cell = 0.9440608762859234 * clamp1(tmp[r] + (tmp[8 + r] + acc[r]));
-                    }
-                }
-#endif
+                for (int r = 0; r < RR; r++)
+                    if (i0 + r < Tt) { if (p == 0) y[sw(t0 + i0 + r)] = acc[r]; else part[(p - 1) * GDG_OS_TILE + sw(i0 + r)] = acc[r]; }
             }
         GDG_THREADS_END
+        /* combine in phase order, clamp, -0.5 dB */
+        GDG_THREADS_BEGIN
+            for (int i = tid; i < Tt; i += GDG_NT) {
+                double acc = y[sw(t0 + i)];
+#pragma unroll
+                for (int p = 1; p < F; p++) acc += part[(p - 1) * GDG_OS_TILE + sw(i)];
+                y[sw(t0 + i)] = 0.9440608762859234 * clamp1(acc);
+            }
+        GDG_THREADS_END_NOSYNC
         if (!stateless && t0 + Tt < n) {
             /* stateful unit: carry the halo (last GDG_ZH + 1 entries of every phase) to the front */
             GDG_THREADS_BEGIN
