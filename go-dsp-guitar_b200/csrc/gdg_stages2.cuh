@@ -186,11 +186,10 @@ GDG_DEV void oversampled_tiles(gdg_ctx &cx, const gdg_unit_desc &d)
     GDG_THREADS_END
     for (int t0 = 0; t0 < n; t0 += T) {
         const int Tt = imin(T, n - t0);
-        /* up-sample (+ stateless nonlinearity).  From the second tile on, a stateless unit simply recomputes the
-         * GDG_ZH-sample halo from the block instead of carrying it over from the previous tile. */
+        /* up-sample (+ stateless nonlinearity); exactly two base samples per thread for a full tile.  (Recomputing
+         * the halo instead of carrying it was measured slower: 1065 items do not divide over 512 threads.) */
         GDG_THREADS_BEGIN
-            const int jlo = (stateless && t0 > 0) ? -GDG_ZH : 0;      /* entries >= ZH - 38 are all the FIR reads */
-            for (int jl = jlo + tid; jl < Tt; jl += GDG_NT) os_produce<F>(d, type, x, uph, z, t0 + jl, jl);
+            for (int jl = tid; jl < Tt; jl += GDG_NT) os_produce<F>(d, type, x, uph, z, t0 + jl, jl);
         GDG_THREADS_END
         if (!stateless) fuzz_run<F>(cx, d, z, Tt);
         /* polyphase FIR partial sums: warp w computes phase w % F (taps warp-uniform) of RR outputs per thread */
@@ -221,8 +220,8 @@ GDG_DEV void oversampled_tiles(gdg_ctx &cx, const gdg_unit_desc &d)
                 y[sw(t0 + i)] = 0.9440608762859234 * clamp1(acc);
             }
         GDG_THREADS_END_NOSYNC
-        if (!stateless && t0 + Tt < n) {
-            /* stateful unit: carry the halo (last GDG_ZH + 1 entries of every phase) to the front */
+        if (t0 + Tt < n) {
+            /* carry the halo (last GDG_ZH + 1 entries of every phase) to the front */
             GDG_THREADS_BEGIN
                 if (tid < F * 64) { const int p = tid >> 6, m = tid & 63; if (m <= GDG_ZH) SM_SCANB[tid] = z[p * GDG_ZPS + pz(m + Tt)]; }
             GDG_THREADS_END
