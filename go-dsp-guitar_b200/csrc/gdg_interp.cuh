@@ -54,7 +54,12 @@ GDG_DEV void run_chain(double *smem, const gdg_chain_desc *cd, const double *in,
         for (int k = tid; k < n; k += GDG_NT) SM_CUR(cx)[sw(k)] = in[k];
     GDG_THREADS_END
     const int ns = cd->nslots;
-    for (int s = 0; s < ns; s++) run_unit(cx, cd->slot[s], tw);
+    for (int s = 0; s < ns; s++) {
+        GDG_THREADS_BEGIN
+            if (tid < (int)(sizeof(gdg_unit_desc) / 4)) ((int *)(gdg_smem + GDG_SMEM_DESC))[tid] = ((const int *)&cd->slot[s])[tid];
+        GDG_THREADS_END
+        run_unit(cx, GDG_DESC, tw);
+    }
     GDG_THREADS_BEGIN
         for (int k = tid; k < n; k += GDG_NT) out[k] = SM_CUR(cx)[sw(k)];
     GDG_THREADS_END

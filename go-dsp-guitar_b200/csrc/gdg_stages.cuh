@@ -86,7 +86,8 @@ GDG_CONST double c_lz4[3][6];          /* ... x4: phase p/4, taps q: L(2 - q + p
 #define GDG_SMEM_SCANA (GDG_SMEM_SCANB + GDG_SCAN_LANES * GDG_NT)
 #define GDG_SMEM_SEG (GDG_SMEM_SCANA + GDG_NT)               /* warp totals of the scans */
 #define GDG_SMEM_MISC (GDG_SMEM_SEG + 3 * GDG_SCAN_LANES * GDG_NSEG)
-#define GDG_SMEM_DOUBLES (GDG_SMEM_MISC + 64)
+#define GDG_SMEM_DESC (GDG_SMEM_MISC + 64)                    /* the running unit's descriptor (24 doubles) */
+#define GDG_SMEM_DOUBLES (GDG_SMEM_DESC + 24)
 #define GDG_SMEM_BYTES (GDG_SMEM_DOUBLES * 8)
 
 #if defined(__CUDACC__) && !defined(GDG_HOST_EMU)
@@ -106,6 +107,9 @@ struct gdg_ctx {
 #define SM_SCANA (gdg_smem + GDG_SMEM_SCANA)
 #define SM_SEG (gdg_smem + GDG_SMEM_SEG)
 #define SM_MISC (gdg_smem + GDG_SMEM_MISC)
+/* the unit descriptor is staged in shared memory by run_chain: parameter reads inside the stages are LDS, not
+ * global loads that the compiler may not hoist over stores */
+#define GDG_DESC (*(const gdg_unit_desc *)(gdg_smem + GDG_SMEM_DESC))
 #define SM_CUR(cx) (gdg_smem + (cx).cur_off)
 #define SM_ALT(cx) (gdg_smem + (cx).alt_off)
 
@@ -245,8 +249,9 @@ GDG_DEV void ring_push(gdg_ctx &cx, const double *blk, double *st, int hs)
  * "since" at sample k = k - (index of the last sample above the close threshold)
  * -> max-scan; gate = type of the last open/close event -> last-event (max) scan.
  * ========================================================================== */
-GDG_DEV void stage_noisegate(gdg_ctx &cx, const gdg_unit_desc &d)
+GDG_DEV void stage_noisegate(gdg_ctx &cx, const gdg_unit_desc &d_global)
 {
+    const gdg_unit_desc &d = GDG_DESC; (void)d_global;
     const int n = cx.n, S = chunk_len(n);
     double *x = SM_CUR(cx), *st = d.st;
     if (d.i[0]) {                                   /* levelOpen < levelClose: copy, force open */
@@ -312,8 +317,9 @@ GDG_DEV void stage_noisegate(gdg_ctx &cx, const gdg_unit_desc &d)
  * compressor  (effects/compressor.go:18-84)
  *   i[0] follow mode; p[0] dInv p[1] d p[2] targetFac p[3] limitFac; st[0] envelope
  * ========================================================================== */
-GDG_DEV void stage_compressor(gdg_ctx &cx, const gdg_unit_desc &d)
+GDG_DEV void stage_compressor(gdg_ctx &cx, const gdg_unit_desc &d_global)
 {
+    const gdg_unit_desc &d = GDG_DESC; (void)d_global;
     const int n = cx.n, S = chunk_len(n), mode = d.i[0];
     const double dinv = d.p[0], dd = d.p[1], target = d.p[2], limit = d.p[3];
     double *x = SM_CUR(cx), *st = d.st;
@@ -346,8 +352,9 @@ GDG_DEV void stage_compressor(gdg_ctx &cx, const gdg_unit_desc &d)
  * LP output taken BEFORE its update, weighted sum, clamp.
  *   p[0..3] HP k, p[4..7] LP k, p[8..11] band factors; st[0..3] hcv, st[4..7] lcv
  * ========================================================================== */
-GDG_DEV void stage_tonestack(gdg_ctx &cx, const gdg_unit_desc &d)
+GDG_DEV void stage_tonestack(gdg_ctx &cx, const gdg_unit_desc &d_global)
 {
+    const gdg_unit_desc &d = GDG_DESC; (void)d_global;
     const int n = cx.n, S = chunk_len(n);
     double *x = SM_CUR(cx), *st = d.st;
     double ahf[4], alf[4], inith[4], initl[4];
@@ -415,8 +422,9 @@ GDG_DEVI double onepole_out(int highpass, double xin, double &v, double k)
     return out;
 }
 
-GDG_DEV void stage_cascade(gdg_ctx &cx, const gdg_unit_desc &d, int nsec, int nhp)
+GDG_DEV void stage_cascade(gdg_ctx &cx, const gdg_unit_desc &d_global, int nsec, int nhp)
 {
+    const gdg_unit_desc &d = GDG_DESC; (void)d_global;
     const int n = cx.n, S = chunk_len(n);
     double *x = SM_CUR(cx), *st = d.st;
     GDG_REGA(double, a, 1); GDG_REGA(double, b, 1); GDG_REGA(double, cin, 1);
@@ -457,8 +465,9 @@ GDG_DEV void stage_cascade(gdg_ctx &cx, const gdg_unit_desc &d, int nsec, int nh
  * output (pre-update value) is clamped between pairs.
  *   i[0] halfOrder; p[0] HP k, p[1] LP k; st[0..3] hcv, st[4..7] lcv
  * ========================================================================== */
-GDG_DEV void stage_bandpass(gdg_ctx &cx, const gdg_unit_desc &d)
+GDG_DEV void stage_bandpass(gdg_ctx &cx, const gdg_unit_desc &d_global)
 {
+    const gdg_unit_desc &d = GDG_DESC; (void)d_global;
     const int n = cx.n, S = chunk_len(n), half = d.i[0];
     const double ka = d.p[0], kb = d.p[1];
     const double aaf = pow_int(1.0 - ka, S), abf = pow_int(1.0 - kb, S);
@@ -523,8 +532,9 @@ GDG_DEVI void tremolo_at(long long i, int att0, unsigned long long s0, unsigned 
     if (m < dFirst) { att = !att0; since = m; }
     else { att = att0; since = m - dFirst; }
 }
-GDG_DEV void stage_tremolo(gdg_ctx &cx, const gdg_unit_desc &d)
+GDG_DEV void stage_tremolo(gdg_ctx &cx, const gdg_unit_desc &d_global)
 {
+    const gdg_unit_desc &d = GDG_DESC; (void)d_global;
     const int n = cx.n;
     double *x = SM_CUR(cx), *st = d.st;
     const unsigned long long lenA = (unsigned int)d.i[0], lenU = (unsigned int)d.i[1];
@@ -550,8 +560,9 @@ GDG_DEV void stage_tremolo(gdg_ctx &cx, const gdg_unit_desc &d)
 }
 
 /* ring_modulator (effects/ringmodulator.go:18-47): p[0] phaseFraction; st[0] phase */
-GDG_DEV void stage_ringmod(gdg_ctx &cx, const gdg_unit_desc &d)
+GDG_DEV void stage_ringmod(gdg_ctx &cx, const gdg_unit_desc &d_global)
 {
+    const gdg_unit_desc &d = GDG_DESC; (void)d_global;
     const int n = cx.n;
     double *x = SM_CUR(cx), *st = d.st;
     const double frac = d.p[0];
@@ -577,8 +588,9 @@ GDG_DEVI unsigned long long lcg_pow(unsigned long long e)
     while (e) { if (e & 1) r = (r * b) % m; b = (b * b) % m; e >>= 1; }
     return r;
 }
-GDG_DEV void stage_siggen(gdg_ctx &cx, const gdg_unit_desc &d)
+GDG_DEV void stage_siggen(gdg_ctx &cx, const gdg_unit_desc &d_global)
 {
+    const gdg_unit_desc &d = GDG_DESC; (void)d_global;
     const int n = cx.n, S = chunk_len(n), type = d.i[0];
     double *x = SM_CUR(cx), *st = d.st;
     const double fin = d.p[0], fsig = d.p[1], inc = d.p[2];
@@ -633,8 +645,9 @@ GDG_DEVI double frac_delay_read(const double *blk, const double *ring, int hs, i
 }
 
 /* delay (effects/delay.go:17-91): i[0] delaySamples (= ring size); p[0] feedbackFac p[1] levelFac */
-GDG_DEV void stage_delay(gdg_ctx &cx, const gdg_unit_desc &d)
+GDG_DEV void stage_delay(gdg_ctx &cx, const gdg_unit_desc &d_global)
 {
+    const gdg_unit_desc &d = GDG_DESC; (void)d_global;
     const int n = cx.n, ds = d.i[0];
     const double fb = d.p[0], lvl = d.p[1];
     double *x = SM_CUR(cx), *y = SM_ALT(cx), *st = d.st;
@@ -653,8 +666,9 @@ GDG_DEV void stage_delay(gdg_ctx &cx, const gdg_unit_desc &d)
 
 /* chorus (effects/chorus.go:19-130): i[0] ring size; p[0] depth p[1] angularSpeed p[2] sampleRate
  * st[0] previousPhase (advanced by the RING length per call, chorus.go:114-117) */
-GDG_DEV void stage_chorus(gdg_ctx &cx, const gdg_unit_desc &d)
+GDG_DEV void stage_chorus(gdg_ctx &cx, const gdg_unit_desc &d_global)
 {
+    const gdg_unit_desc &d = GDG_DESC; (void)d_global;
     const int n = cx.n, hs = d.i[0];
     const double depth = d.p[0], ang = d.p[1], sr = d.p[2];
     double *x = SM_CUR(cx), *y = SM_ALT(cx), *st = d.st;
@@ -690,8 +704,9 @@ GDG_DEV void stage_chorus(gdg_ctx &cx, const gdg_unit_desc &d)
 
 /* flanger / phaser (effects/flanger.go:19-117, phaser.go:19-125)
  *   i[0] ring size; p[0] depth p[1] angularSpeed p[2] sampleRate p[3] 1/sampleRate p[4] dry weight p[5] wet weight */
-GDG_DEV void stage_flanger(gdg_ctx &cx, const gdg_unit_desc &d)
+GDG_DEV void stage_flanger(gdg_ctx &cx, const gdg_unit_desc &d_global)
 {
+    const gdg_unit_desc &d = GDG_DESC; (void)d_global;
     const int n = cx.n, hs = d.i[0];
     const double depth = d.p[0], ang = d.p[1], sr = d.p[2], sr_inv = d.p[3], wa = d.p[4], wb = d.p[5];
     double *x = SM_CUR(cx), *y = SM_ALT(cx), *st = d.st;
@@ -718,8 +733,9 @@ GDG_DEV void stage_flanger(gdg_ctx &cx, const gdg_unit_desc &d)
 /* auto_yoy (effects/autoyoy.go:19-156)
  *   i[0] ring size i[1] follow; p[0] dInv p[1] d p[2] levelA p[3] levelB p[4] depthA p[5] depthB p[6] slope p[7] sampleRate
  *   st[0] envelope */
-GDG_DEV void stage_autoyoy(gdg_ctx &cx, const gdg_unit_desc &d)
+GDG_DEV void stage_autoyoy(gdg_ctx &cx, const gdg_unit_desc &d_global)
 {
+    const gdg_unit_desc &d = GDG_DESC; (void)d_global;
     const int n = cx.n, S = chunk_len(n), hs = d.i[0], mode = d.i[1];
     const double dinv = d.p[0], dd = d.p[1];
     double *x = SM_CUR(cx), *y = SM_ALT(cx), *st = d.st;

@@ -68,8 +68,9 @@ GDG_DEVI double nl_pointwise(int type, const gdg_unit_desc &d, double s)
 template <int F> GDG_DEVI int fz_loc(int jl, int ph) { return F == 1 ? sw(jl) : zloc(F, jl, ph); }
 
 template <int F>
-GDG_DEV void fuzz_run(gdg_ctx &cx, const gdg_unit_desc &d, double *z, int nbase)
+GDG_DEV void fuzz_run(gdg_ctx &cx, const gdg_unit_desc &d_global, double *z, int nbase)
 {
+    const gdg_unit_desc &d = GDG_DESC; (void)d_global;
     const int Sb = chunk_len(nbase), mode = d.i[1];
     const double gain = d.p[0], lvl = d.p[1], bias = d.p[2], ff = d.p[3], ffi = d.p[4], dinv = d.p[5], dd = d.p[6];
     double *st = d.st;
@@ -170,8 +171,9 @@ GDG_DEVI void os_produce(const gdg_unit_desc &d, int type, const double *x, cons
 }
 
 template <int F>
-GDG_DEV void oversampled_tiles(gdg_ctx &cx, const gdg_unit_desc &d)
+GDG_DEV void oversampled_tiles(gdg_ctx &cx, const gdg_unit_desc &d_global)
 {
+    const gdg_unit_desc &d = GDG_DESC; (void)d_global;
     constexpr int RR = 2 * F;                   /* outputs per thread group; F lanes (one per phase) share a group */
     const int n = cx.n, type = d.type;
     double *x = SM_CUR(cx), *y = SM_ALT(cx), *z = SM_S, *st = d.st;
@@ -278,8 +280,9 @@ GDG_DEVI void os_produce_at(const gdg_unit_desc &d, int type, const double *x, c
 }
 
 template <int F>
-GDG_DEV void oversampled_pipe(gdg_ctx &cx, const gdg_unit_desc &d)
+GDG_DEV void oversampled_pipe(gdg_ctx &cx, const gdg_unit_desc &d_global)
 {
+    const gdg_unit_desc &d = GDG_DESC; (void)d_global;
     constexpr int RR = 2 * F;
     constexpr int HALF = GDG_NT / 2;
     const int n = cx.n, type = d.type;
@@ -361,8 +364,9 @@ GDG_DEV void oversampled_pipe(gdg_ctx &cx, const gdg_unit_desc &d)
     swap_bufs(cx);
 }
 
-GDG_DEV void stage_oversampled(gdg_ctx &cx, const gdg_unit_desc &d)
+GDG_DEV void stage_oversampled(gdg_ctx &cx, const gdg_unit_desc &d_global)
 {
+    const gdg_unit_desc &d = GDG_DESC; (void)d_global;
     const int n = cx.n, f = d.i[0], type = d.type;
     double *x = SM_CUR(cx);
     if (f <= 1) {
@@ -383,8 +387,9 @@ GDG_DEV void stage_oversampled(gdg_ctx &cx, const gdg_unit_desc &d)
  * polarity after a sample = sign of the last "candidate" (nonzero sample above the
  * hysteresis level); the register counts sign changes between successive candidates.
  * ========================================================================== */
-GDG_DEV void stage_octaver(gdg_ctx &cx, const gdg_unit_desc &d)
+GDG_DEV void stage_octaver(gdg_ctx &cx, const gdg_unit_desc &d_global)
 {
+    const gdg_unit_desc &d = GDG_DESC; (void)d_global;
     const int n = cx.n, S = chunk_len(n), mode = d.i[0];
     const double dinv = d.p[0], dd = d.p[1], fUp = d.p[2], fClean = d.p[3], fDist = d.p[4], fD1 = d.p[5], fD2 = d.p[6], fH = d.p[7];
     double *x = SM_CUR(cx), *st = d.st;
@@ -472,8 +477,9 @@ GDG_DEV void stage_octaver(gdg_ctx &cx, const gdg_unit_desc &d)
  * k[n] = 1 - exp(-f(env[n])/fs) is stored in alt; the 8 HP/LP pairs are affine
  * recurrences with that time-varying coefficient (the NEW lp value feeds the next pair).
  * ========================================================================== */
-GDG_DEV void stage_autowah(gdg_ctx &cx, const gdg_unit_desc &d)
+GDG_DEV void stage_autowah(gdg_ctx &cx, const gdg_unit_desc &d_global)
 {
+    const gdg_unit_desc &d = GDG_DESC; (void)d_global;
     const int n = cx.n, S = chunk_len(n), mode = d.i[0];
     const double dinv = d.p[0], dd = d.p[1];
     double *x = SM_CUR(cx), *kv = SM_ALT(cx), *st = d.st;
@@ -559,8 +565,9 @@ GDG_DEV void stage_autowah(gdg_ctx &cx, const gdg_unit_desc &d)
  * out = clamp((dry x + hw line) + hw wet): the dry/line part is folded first, which differs from
  * reverb.go:318-319 "(dry x) + hw (line + wet)" by one rounding (~1e-16).
  * ========================================================================== */
-GDG_DEV void stage_reverb(gdg_ctx &cx, const gdg_unit_desc &d)
+GDG_DEV void stage_reverb(gdg_ctx &cx, const gdg_unit_desc &d_global)
 {
+    const gdg_unit_desc &d = GDG_DESC; (void)d_global;
     const int n = cx.n, hs = d.i[0];
     double *x = SM_CUR(cx), *w = SM_ALT(cx), *P = SM_S, *st = d.st;
     double *lring = st + GDG_RV_ST_DATA;
@@ -805,8 +812,9 @@ GDG_DEV void fft_inverse(gdg_ctx &cx, double *D, const double *tw, int logM, int
 }
 
 /* power_amp state: tail[F] followed by one word = number of trailing tail cells known to be zero */
-GDG_DEV void stage_poweramp(gdg_ctx &cx, const gdg_unit_desc &d, const double *tw)
+GDG_DEV void stage_poweramp(gdg_ctx &cx, const gdg_unit_desc &d_global, const double *tw)
 {
+    const gdg_unit_desc &d = GDG_DESC; (void)d_global;
     const int n = cx.n, L = d.i[0];
     double *x = SM_CUR(cx);
     if (L <= 0) {                                              /* filter.go:366-367 / poweramp.go:210-214 */
