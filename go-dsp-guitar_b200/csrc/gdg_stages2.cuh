@@ -57,7 +57,8 @@ GDG_DEVI double nl_pointwise(int type, const gdg_unit_desc &d, double s)
     const int section = (int)(0.5 * floor(ap + 1.0));
     const int odd = (section % 2) != 0;
     const int inverted = odd != (exceeded && negative);
-    const double ex = fmod(ap + 1.0, 2.0);
+    const double tt = ap + 1.0;
+    const double ex = tt - 2.0 * floor(0.5 * tt);          /* == fmod(tt, 2.0) exactly (tt >= 1, all steps exact in binary64) */
     if (exceeded) pre = inverted ? 1.0 - ex : ex - 1.0;
     return d.p[1] * pre;
 }
@@ -245,125 +246,6 @@ GDG_DEV void oversampled_tiles(gdg_ctx &cx, const gdg_unit_desc &d_global)
     swap_bufs(cx);
 }
 
-/* --------------------------------------------------------------------------
- * Stateless units (excess / overdrive / distortion): the same computation as oversampled_tiles, software-
- * pipelined over half-size tiles with WARP SPECIALISATION: in every step warps 0-7 run the FP64-bound polyphase
- * FIR of tile s while warps 8-15 combine tile s-1, carry the halo and up-sample + shape tile s+1 into the other
- * z buffer.  One barrier per 512 base samples instead of five per 1024.
- * -------------------------------------------------------------------------- */
-#define GDG_PT 512                           /* base samples per pipeline tile */
-#define GDG_PZS 624                          /* doubles per phase array: pz(GDG_ZH + GDG_PT + 1) = 622 */
-template <int F>
-GDG_DEVI void os_produce_at(const gdg_unit_desc &d, int type, const double *x, const double *uph, double *z, int j, int jl)
-{
-    double xs[6];
-    if (j >= 6) {
-#pragma unroll
-        for (int q = 0; q < 6; q++) xs[q] = x[sw(j - 6 + q)];
-    } else {
-#pragma unroll
-        for (int q = 0; q < 6; q++) { const int idx = j - 6 + q; xs[q] = idx >= 0 ? x[sw(idx)] : uph[8 + idx]; }
-    }
-    const int m0 = pz(GDG_ZH + jl), m1 = pz(GDG_ZH + jl + 1);
-#pragma unroll
-    for (int ph = 0; ph < F; ph++) {
-        double u;
-        if (ph == 0) u = xs[2];
-        else {
-            u = 0.0;
-#pragma unroll
-            for (int q = 0; q < 6; q++) u += xs[q] * (F == 2 ? c_lz2[0][q] : c_lz4[ph - 1][q]);
-        }
-        u = nl_pointwise(type, d, u);
-        if (ph == 0) z[m0] = u; else z[(F - ph) * GDG_PZS + m1] = u;
-    }
-}
-
-template <int F>
-GDG_DEV void oversampled_pipe(gdg_ctx &cx, const gdg_unit_desc &d_global)
-{
-    const gdg_unit_desc &d = GDG_DESC; (void)d_global;
-    constexpr int RR = 2 * F;
-    constexpr int HALF = GDG_NT / 2;
-    const int n = cx.n, type = d.type;
-    double *x = SM_CUR(cx), *y = SM_ALT(cx), *st = d.st;
-    double *uph = st + (F == 2 ? GDG_OS_ST_UP2 : GDG_OS_ST_UP4);
-    double *zh = st + (F == 2 ? GDG_OS_ST_Z2 : GDG_OS_ST_Z4);
-    double *zb0 = SM_S, *zb1 = SM_S + F * GDG_PZS;                 /* two z buffers of F phase arrays */
-    double *pt0 = SM_S + 2 * F * GDG_PZS, *pt1 = pt0 + (F - 1) * GDG_PT;   /* two partial-sum buffers */
-    const int T = imin(n, GDG_PT), nt = (n + T - 1) / T;
-    /* prologue: carried history into buffer 0, then tile 0 */
-    GDG_THREADS_BEGIN
-        if (tid < F * 64) { const int p = tid >> 6, m = tid & 63; if (m <= GDG_ZH) zb0[p * GDG_PZS + pz(m)] = zh[p * (GDG_ZH + 1) + m]; }
-    GDG_THREADS_END
-    GDG_THREADS_BEGIN
-        for (int jl = tid; jl < T; jl += GDG_NT) os_produce_at<F>(d, type, x, uph, zb0, jl, jl);
-    GDG_THREADS_END
-    for (int s = 0; s < nt; s++) {
-        const int t0 = s * T, Tt = imin(T, n - t0);
-        double *zc = (s & 1) ? zb1 : zb0, *zn = (s & 1) ? zb0 : zb1;
-        double *pc = (s & 1) ? pt1 : pt0, *pp = (s & 1) ? pt0 : pt1;
-        GDG_THREADS_BEGIN
-            if (tid < HALF) {
-                /* FIR of tile s: warp w -> phase w % F, 32 output groups per warp */
-                const int warp = tid >> 5, p = warp % F;
-                const int i0 = ((warp / F) * 32 + (tid & 31)) * RR;
-                if (i0 < Tt) {
-                    double acc[RR];
-                    const double *zp = zc + p * GDG_PZS;
-                    if (F == 2) { if (p == 0) fir_branch<F, 0, RR>(zp, i0, acc); else fir_branch<F, 1, RR>(zp, i0, acc); }
-                    else {
-                        if (p == 0) fir_branch<F, 0, RR>(zp, i0, acc);
-                        else if (p == 1) fir_branch<F, 1 % F, RR>(zp, i0, acc);
-                        else if (p == 2) fir_branch<F, 2 % F, RR>(zp, i0, acc);
-                        else fir_branch<F, 3 % F, RR>(zp, i0, acc);
-                    }
-#pragma unroll
-                    for (int r = 0; r < RR; r++)
-                        if (i0 + r < Tt) { if (p == 0) y[sw(t0 + i0 + r)] = acc[r]; else pc[(p - 1) * GDG_PT + sw(i0 + r)] = acc[r]; }
-                }
-            } else {
-                const int tb = tid - HALF;
-                if (s > 0) {                                    /* combine tile s-1 (always a full tile) */
-                    for (int i = tb; i < T; i += HALF) {
-                        double acc = y[sw(t0 - T + i)];
-#pragma unroll
-                        for (int p = 1; p < F; p++) acc += pp[(p - 1) * GDG_PT + sw(i)];
-                        y[sw(t0 - T + i)] = 0.9440608762859234 * clamp1(acc);
-                    }
-                }
-                if (s + 1 < nt) {                               /* halo, then tile s+1 into the other buffer */
-                    if (tb < F * 64) {
-                        const int p = tb >> 6, m = tb & 63;
-                        if (m < GDG_ZH || (m == GDG_ZH && p > 0)) zn[p * GDG_PZS + pz(m)] = zc[p * GDG_PZS + pz(m + Tt)];
-                    }
-                    const int Tn = imin(T, n - (t0 + T));
-                    for (int jl = tb; jl < Tn; jl += HALF) os_produce_at<F>(d, type, x, uph, zn, t0 + T + jl, jl);
-                }
-            }
-        GDG_THREADS_END
-    }
-    /* epilogue: combine the last tile; carry the oversampled history and the last 8 inputs */
-    {
-        const int t0 = (nt - 1) * T, Tt = n - t0;
-        double *zc = ((nt - 1) & 1) ? zb1 : zb0, *pc = ((nt - 1) & 1) ? pt1 : pt0;
-        GDG_THREADS_BEGIN
-            for (int i = tid; i < Tt; i += GDG_NT) {
-                double acc = y[sw(t0 + i)];
-#pragma unroll
-                for (int p = 1; p < F; p++) acc += pc[(p - 1) * GDG_PT + sw(i)];
-                y[sw(t0 + i)] = 0.9440608762859234 * clamp1(acc);
-            }
-            if (tid < F * 64) { const int p = tid >> 6, m = tid & 63; if (m <= GDG_ZH) zh[p * (GDG_ZH + 1) + m] = zc[p * GDG_PZS + pz(m + Tt)]; }
-            if (tid < 8) SM_MISC[8 + tid] = (n - 8 + tid) >= 0 ? x[sw(n - 8 + tid)] : uph[tid + n];
-        GDG_THREADS_END
-    }
-    GDG_THREADS_BEGIN
-        if (tid < 8) uph[tid] = SM_MISC[8 + tid];
-    GDG_THREADS_END
-    swap_bufs(cx);
-}
-
 GDG_DEV void stage_oversampled(gdg_ctx &cx, const gdg_unit_desc &d_global)
 {
     const gdg_unit_desc &d = GDG_DESC; (void)d_global;
@@ -376,8 +258,9 @@ GDG_DEV void stage_oversampled(gdg_ctx &cx, const gdg_unit_desc &d_global)
         GDG_THREADS_END
         return;
     }
-    if (type == GDG_UNIT_FUZZ) { if (f == 2) oversampled_tiles<2>(cx, d); else oversampled_tiles<4>(cx, d); }
-    else { if (f == 2) oversampled_pipe<2>(cx, d); else oversampled_pipe<4>(cx, d); }
+    /* (a warp-specialised variant - FIR warps / produce warps, one barrier per 512 samples - was measured and was
+     * not faster on B200: distortion 0.257 vs 0.253 ms, overdrive 0.455 vs 0.360 ms per 1024-channel block) */
+    if (f == 2) oversampled_tiles<2>(cx, d); else oversampled_tiles<4>(cx, d);
 }
 
 /* ==========================================================================
