@@ -591,7 +591,8 @@ struct gdg_chain {
     bool topo_dirty = true;
     bool uploaded = false;                                      /* set when prepare() touched device memory */
     double *d_in = nullptr, *d_out = nullptr; size_t d_n = 0;   /* single-channel staging for gdg_chain_process */
-    ~gdg_chain() { for (auto p : d_desc) gdgb_free(p); if (d_in) gdgb_free(d_in); if (d_out) gdgb_free(d_out); }
+    const gdg_chain_desc **d_self = nullptr; size_t self_rounds = 0;   /* one-entry pointer tables (one per segment round) */
+    ~gdg_chain() { for (auto p : d_desc) gdgb_free(p); if (d_in) gdgb_free(d_in); if (d_out) gdgb_free(d_out); gdgb_free((void *)d_self); }
 
     /* bring the device descriptors up to date; returns number of segments or -1 */
     int prepare(uint32_t rate, size_t n)
@@ -1242,8 +1243,19 @@ int gdg_chain_process(gdg_chain *c, const double *in, double *out, size_t n, uin
         c->d_n = n;
     }
     if (gdgb_upload(c->d_in, in, n * sizeof(double))) return backend_fail("upload failed");
-    gdg_chain *one[1] = {c};
-    if (run_batch_device(one, 1, c->d_in, c->d_out, n, n, rate, gdgb_stream())) return -1;
+    /* single chain (the JACK path calls Chain.Process per channel): its own pointer table, no batch cache churn */
+    const int rounds = c->prepare(rate, n);
+    if (rounds < 0) return -1;
+    if (c->self_rounds != (size_t)rounds) {                /* descriptor addresses are stable; only their number can change */
+        gdgb_sync(); gdgb_free((void *)c->d_self);
+        c->d_self = (const gdg_chain_desc **)gdgb_alloc((size_t)rounds * sizeof(void *));
+        std::vector<const gdg_chain_desc *> ptrs(c->d_desc.begin(), c->d_desc.begin() + rounds);
+        if (!c->d_self || gdgb_upload((void *)c->d_self, ptrs.data(), ptrs.size() * sizeof(void *))) return backend_fail("descriptor table upload failed");
+        c->self_rounds = (size_t)rounds;
+    }
+    for (int r = 0; r < rounds; r++)
+        if (gdgb_launch_chains(c->d_self + r, 1, r == 0 ? c->d_in : c->d_out, c->d_out, (long)n, (int)n, gdgb_stream()))
+            return backend_fail("chain kernel launch failed");
     return gdgb_download(out, c->d_out, n * sizeof(double)) ? backend_fail("download failed") : 0;
 }
 

@@ -1,0 +1,113 @@
+"""Edge cases of the hot path on both backends: tiny blocks, every supported sample rate, long streams,
+chain edits with live state, state isolation between chains, scattered host buffers."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import common
+from common import gdg, orc
+
+BACKENDS = [pytest.param("emu", id="emu"), pytest.param("cuda", id="cuda", marks=pytest.mark.gpu)]
+
+
+@pytest.fixture(params=BACKENDS)
+def lib(request):
+    return common.backend_lib(request.param)
+
+
+MIXED = [("compressor", {}, {}), ("overdrive", {"gain": 18}, {"oversampling": "4"}), ("fuzz", {"gain": 10}, {"oversampling": "2"}),
+         ("tone_stack", {}, {}), ("chorus", {}, {}), ("delay", {"delay_time": 3}, {}), ("reverb", {}, {}),
+         ("power_amp", {}, {"filter_order": "512", "filter_1": None}), ("cabinet", {}, {})]
+
+
+@pytest.mark.parametrize("n", [1, 2, 4, 8, 16, 32, 128, 512])
+def test_tiny_and_small_blocks(lib, n):
+    """Block lengths below the CTA width (JACK periods go down to 64; the oracle accepts any power of two)."""
+    banks = common.make_banks(lib)
+    a, b = common.make_chain_pair(lib, MIXED, banks, ir_name="Guitar: British Vintage (Neutral)")
+    fs = 48000
+    x = common.synth_fast(2, fs, 24 * n + 0) * 1.5
+    common.compare_stream(a, b, x, n, fs, label="n=%d" % n)
+
+
+@pytest.mark.parametrize("fs", [22050, 32000, 44100, 48000, 88200, 96000, 192000])
+def test_every_supported_sample_rate(lib, fs):
+    """filter.go:25-33: the seven rates the IR bank is resampled to."""
+    banks = common.make_banks(lib)
+    a, b = common.make_chain_pair(lib, MIXED, banks, ir_name="PA: ISP 2-way (Low)")
+    x = common.synth_fast(4, fs, 4 * 2048)
+    common.compare_stream(a, b, x, 2048, fs, label="fs=%d" % fs)
+
+
+def test_long_stream_does_not_drift(lib):
+    """60 consecutive blocks: the parallel scans must not accumulate error against the sequential reference."""
+    fs, n = 96000, 1024
+    banks = common.make_banks(lib)
+    a, b = common.make_chain_pair(lib, common.CHAIN12, banks, ir_name="Guitar: American Vintage (Center)")
+    x = common.synth_fast(6, fs, 60 * n)
+    worst = common.compare_stream(a, b, x, n, fs, label="drift")
+    assert worst <= common.TOL_RMS
+
+
+def test_chain_edits_keep_unit_state(lib):
+    """RemoveUnit / MoveUp / MoveDown / SetBypass move live units around: their DSP state travels with them
+    (signal.go:91-162 operate on the slot slice; the unit objects are untouched)."""
+    fs, n = 96000, 2048
+    spec = [("delay", {"delay_time": 10}, {}), ("reverb", {}, {}), ("tone_stack", {}, {}), ("overdrive", {"gain": 12}, {"oversampling": "2"})]
+    a, b = common.make_chain_pair(lib, spec)
+    x = common.synth_fast(7, fs, 12 * n)
+    for blk in range(12):
+        for ch in (a, b):
+            if blk == 2: ch.move_up(3)              # overdrive before tone_stack
+            if blk == 4: ch.set_bypass(1, True)     # reverb off (keeps its tails for later)
+            if blk == 6: ch.remove_unit(0)          # delay gone
+            if blk == 7: ch.set_bypass(0, False)    # reverb back on with its old state
+            if blk == 9: ch.move_down(0)
+            if blk == 10:
+                i = ch.append_unit("cabinet"); ch.set_bypass(i, False)
+        ya, yb = a.process(x[blk * n:(blk + 1) * n], fs), b.process(x[blk * n:(blk + 1) * n], fs)
+        assert common.rms(ya - yb) <= common.TOL_RMS, blk
+    assert [a.unit_type(i) for i in range(a.length())] == [b.unit_type(i) for i in range(b.length())]
+
+
+def test_chains_do_not_share_state(lib):
+    """Two chains over one bank, processed alternately and in one batch, behave like two independent oracle chains."""
+    fs, n = 96000, 2048
+    banks = common.make_banks(lib)
+    pairs = [common.make_chain_pair(lib, common.CHAIN12, banks, ir_name=nm) for nm in ("Guitar: Custom BP", "PA: HC 4-way (Mid)")]
+    x = [common.synth_fast(c, fs, 6 * n) for c in range(2)]
+    for k in range(6):
+        if k % 2:      # alternately: one batched call ...
+            out = gdg.process_batch([p[1] for p in pairs], np.stack([x[c][k * n:(k + 1) * n] for c in range(2)]), fs)
+        else:          # ... or two single-channel calls in swapped order
+            out = [None, None]
+            for c in (1, 0):
+                out[c] = pairs[c][1].process(x[c][k * n:(k + 1) * n], fs)
+        for c in range(2):
+            ref = pairs[c][0].process(x[c][k * n:(k + 1) * n], fs)
+            assert common.rms(ref - out[c]) <= common.TOL_RMS, (k, c)
+
+
+def test_scattered_host_buffers(lib):
+    """gdg_process_batch with non-contiguous, unpinned row pointers (the Go [][]float64 case)."""
+    fs, n, Cn = 48000, 1024, 5
+    chains_o = [common.build_chain(orc.Chain(), [("distortion", {"gain": 9 + c}, {})]) for c in range(Cn)]
+    chains_p = [common.build_chain(gdg.Chain(lib=lib), [("distortion", {"gain": 9 + c}, {})]) for c in range(Cn)]
+    rows_in = [np.ascontiguousarray(common.synth_fast(c, fs, n)) for c in range(Cn)]          # separate allocations
+    rows_out = [np.zeros(n) for _ in range(Cn)]
+    hs = (C.c_void_p * Cn)(*[c._h for c in chains_p])
+    ip = (C.c_void_p * Cn)(*[r.ctypes.data for r in reversed(rows_in)])                       # deliberately not ascending
+    op = (C.c_void_p * Cn)(*[r.ctypes.data for r in reversed(rows_out)])
+    assert lib.gdg_process_batch(hs, Cn, ip, op, n, fs) == 0, lib.gdg_last_error()
+    for c in range(Cn):
+        ref = chains_o[c].process(rows_in[Cn - 1 - c], fs)
+        assert np.array_equal(ref, rows_out[Cn - 1 - c])
+
+
+def test_length_mismatch_and_null_arguments(lib):
+    c = gdg.Chain(lib=lib)
+    assert lib.gdg_chain_process(c._h, None, None, 64, 48000) < 0
+    assert lib.gdg_process_batch(None, 0, None, None, 64, 48000) < 0
+    assert lib.gdg_chain_set_bypass(None, 0, 1) < 0
+    assert b"NULL" in lib.gdg_last_error()
