@@ -26,7 +26,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-DEFAULT_LIBRARY = os.path.join(HERE, "libgdg.so")
+DEFAULT_LIBRARY = os.environ.get("GDG_LIBRARY") or os.path.join(HERE, "libgdg.so")   # GDG_LIBRARY: development override
 
 UNIT_TYPES = ["signal_generator", "noise_gate", "bandpass", "auto_wah", "auto_yoy", "compressor", "octaver",
               "excess", "fuzz", "overdrive", "distortion", "tone_stack", "chorus", "flanger", "phaser", "tremolo",

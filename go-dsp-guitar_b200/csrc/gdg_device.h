@@ -15,7 +15,9 @@
 
 #include <stdint.h>
 
+#ifndef GDG_NT
 #define GDG_NT 512              /* threads per CTA                                   */
+#endif
 #define GDG_MAX_N 8192          /* max block length (controller.go:36 BLOCK_SIZE)    */
 #define GDG_MAX_FFT 16384       /* max real FFT size held in shared memory (2*MAX_N) */
 #define GDG_MAX_SLOTS 24        /* non-bypassed units per fused segment              */

@@ -52,6 +52,7 @@ GDG_DEV void run_chain(double *smem, const gdg_chain_desc *cd, const double *in,
     ctx_init(cx, n);
     GDG_THREADS_BEGIN
         for (int k = tid; k < n; k += GDG_NT) SM_CUR(cx)[sw(k)] = in[k];
+        for (int k = tid; k < 1024; k += GDG_NT) { SM_TWS[2 * k] = GDG_LDG(tw + 4 * k); SM_TWS[2 * k + 1] = GDG_LDG(tw + 4 * k + 1); }   /* exp(-2 pi i k / 8192) */
     GDG_THREADS_END
     const int ns = cd->nslots;
     for (int s = 0; s < ns; s++) {

@@ -82,9 +82,10 @@ GDG_CONST double c_lz4[3][6];          /* ... x4: phase p/4, taps q: L(2 - q + p
  * compiler emits LDS/STS (not generic loads) in the separately compiled stages. */
 #define GDG_SMEM_R 0                                         /* 2*GDG_MAX_N: bufA | bufB; also the FFT workspace */
 #define GDG_SMEM_S (2 * GDG_MAX_N)                           /* GDG_MAX_N scratch */
-#define GDG_SMEM_SCANB (GDG_SMEM_S + GDG_MAX_N)              /* GDG_SCAN_LANES * GDG_NT staging */
-#define GDG_SMEM_SCANA (GDG_SMEM_SCANB + GDG_SCAN_LANES * GDG_NT)
-#define GDG_SMEM_SEG (GDG_SMEM_SCANA + GDG_NT)               /* warp totals of the scans */
+#define GDG_SMEM_TWS (GDG_SMEM_S + GDG_MAX_N)                /* 1024 complex: exp(-2 pi i k / 8192), loaded once per launch */
+#define GDG_SMEM_SCANB (GDG_SMEM_TWS + 2048)                 /* 256 doubles staging */
+#define GDG_SMEM_SCANA (GDG_SMEM_SCANB + 256)                /* 512 doubles: split twiddles / staging */
+#define GDG_SMEM_SEG (GDG_SMEM_SCANA + 512)                  /* warp totals of the scans */
 #define GDG_SMEM_MISC (GDG_SMEM_SEG + 3 * GDG_SCAN_LANES * GDG_NSEG)
 #define GDG_SMEM_DESC (GDG_SMEM_MISC + 64)                    /* the running unit's descriptor (24 doubles) */
 #define GDG_SMEM_DOUBLES (GDG_SMEM_DESC + 24)
@@ -103,6 +104,7 @@ struct gdg_ctx {
 };
 #define SM_R (gdg_smem + GDG_SMEM_R)
 #define SM_S (gdg_smem + GDG_SMEM_S)
+#define SM_TWS (gdg_smem + GDG_SMEM_TWS)
 #define SM_SCANB (gdg_smem + GDG_SMEM_SCANB)
 #define SM_SCANA (gdg_smem + GDG_SMEM_SCANA)
 #define SM_SEG (gdg_smem + GDG_SMEM_SEG)
@@ -217,7 +219,14 @@ GDG_DEVI double ring_get(const double *ring, int hs, int pos, int q)
 /* x[idx] for idx in [-hs, n): block sample or history */
 GDG_DEVI double hist_or_block(const double *blk, const double *ring, int hs, int pos, int idx)
 {
-    return idx >= 0 ? blk[sw(idx)] : ring_get(ring, hs, pos, hs + idx);
+    /* both loads are issued unconditionally on clamped (valid) addresses so that the compiler can batch the
+     * global loads of an unrolled loop instead of branching around each of them */
+    int p = pos + hs + (idx < 0 ? idx : -1);
+    if (p >= hs) p -= hs;
+    if (p < 0) p = 0;
+    const double hv = hs > 0 ? GDG_LDST(ring + p) : 0.0;
+    const double bv = blk[sw(idx < 0 ? 0 : idx)];
+    return idx >= 0 ? bv : hv;
 }
 /* push the block into the ring (one phase), returns nothing; new pos written by thread 0 */
 GDG_DEV void ring_push(gdg_ctx &cx, const double *blk, double *st, int hs)

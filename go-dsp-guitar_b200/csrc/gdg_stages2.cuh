@@ -458,17 +458,19 @@ GDG_DEV void stage_reverb(gdg_ctx &cx, const gdg_unit_desc &d_global)
     /* delay line taps -> w */
     GDG_THREADS_BEGIN
         const int pos = (int)st_geti(st, GDG_RV_ST_LINEPOS);
+        const int t0 = d.i[1], t1 = d.i[2], t2 = d.i[3], t3 = d.i[4];
+        const double c0 = d.p[2], c1 = d.p[3], c2 = d.p[4], c3 = d.p[5];
 #pragma unroll 4
         for (int k = tid; k < n; k += GDG_NT) {
+            /* taps beyond the ring (idx < -hs) read zero; loads are unconditional on clamped addresses */
+            const int i0 = k - t0, i1 = k - t1, i2 = k - t2, i3 = k - t3;
+            const double v0 = hist_or_block(x, lring, hs, pos, i0 < -hs ? -hs : i0), v1 = hist_or_block(x, lring, hs, pos, i1 < -hs ? -hs : i1);
+            const double v2 = hist_or_block(x, lring, hs, pos, i2 < -hs ? -hs : i2), v3 = hist_or_block(x, lring, hs, pos, i3 < -hs ? -hs : i3);
             double pre = 0.0;
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const int idx = k - d.i[1 + j];
-                double cs = 0.0;
-                if (idx >= 0) cs = x[sw(idx)];
-                else if (idx >= -hs) cs = ring_get(lring, hs, pos, hs + idx);
-                pre += d.p[2 + j] * cs;
-            }
+            pre += c0 * (i0 < -hs ? 0.0 : v0);
+            pre += c1 * (i1 < -hs ? 0.0 : v1);
+            pre += c2 * (i2 < -hs ? 0.0 : v2);
+            pre += c3 * (i3 < -hs ? 0.0 : v3);
             w[sw(k)] = pre;
         }
     GDG_THREADS_END
@@ -712,7 +714,7 @@ GDG_DEV void stage_poweramp(gdg_ctx &cx, const gdg_unit_desc &d_global, const do
     const int total = nb * M;                                    /* complex points in flight (<= GDG_MAX_N) */
     const int per = (total + GDG_NT - 1) / GDG_NT;               /* <= 16 */
     double *D = SM_R, *tail = d.st;
-    double *tws = SM_SCANB;                                      /* 1024 complex: exp(-2 pi i k / 8192) for the passes */
+    const double *tws = SM_TWS;                                  /* 1024 complex: exp(-2 pi i k / 8192), loaded by run_chain */
     double *wc = SM_SCANA, *wf = SM_SCANA + 130;                 /* W_F^(64 a), a <= 64 and W_F^b, b < 64 for the split */
     double *tl = SM_S;                                           /* prefetched overlap tail (plain layout) */
     const double *H = d.aux;
@@ -735,7 +737,6 @@ GDG_DEV void stage_poweramp(gdg_ctx &cx, const gdg_unit_desc &d_global, const do
             }
             R(buf)[2 * r] = re; R(buf)[2 * r + 1] = im;
         }
-        for (int k = tid; k < 1024; k += GDG_NT) { const gdg_c2 w = twd(tw, 2 * k); cst(tws, k, w); }
         if (tid < 65) cst(wc, tid, tw_full(tw, imin(64 * tid * fstep, GDG_MAX_FFT - 1) ));
         if (tid >= 128 && tid < 192) cst(wf, tid - 128, twd(tw, (tid - 128) * fstep));
         /* overlap cells [0, ns) are always needed: fetch them now, hidden behind the transform */
@@ -751,11 +752,10 @@ GDG_DEV void stage_poweramp(gdg_ctx &cx, const gdg_unit_desc &d_global, const do
     fft_forward(cx, D, tws, logM, nb);
     /* split (fft.go:801-818) * H (filter.go:459) * inverse split (fft.go:899-955), on bit-reversed storage */
     GDG_THREADS_BEGIN
-#pragma unroll 2
-        for (int b = tid; b < nb * (M / 2 + 1); b += GDG_NT) {
-            const int seg = b / (M / 2 + 1), k = b - seg * (M / 2 + 1);
-            const int zb = seg * M;
-            if (k == 0) {
+        /* bins 0 and M (both real) of every block: one thread per block */
+        if (tid < nb) {
+            const int zb = tid * M;
+            {
                 const gdg_c2 z0 = cld(D, cz(zb));
                 const double x0 = z0.re + z0.im, xm = z0.re - z0.im;     /* X[0], X[M] (real) */
                 double y0 = x0 * GDG_LDG(H + 0), ym = xm * GDG_LDG(H + 2 * M);  /* real(dc), real(nyquist) of the product */
@@ -769,7 +769,13 @@ GDG_DEV void stage_poweramp(gdg_ctx &cx, const gdg_unit_desc &d_global, const do
                 }
                 gdg_c2 o; o.re = 0.5 * (y0 + ym); o.im = 0.5 * (y0 - ym);
                 cst(D, cz(zb), o);
-            } else {
+            }
+        }
+#pragma unroll 4
+        for (int b = tid; b < nb * (M / 2); b += GDG_NT) {
+            const int seg = b / (M / 2), k = 1 + (b - seg * (M / 2));
+            const int zb = seg * M;
+            {
                 const int k2 = M - k;
                 gdg_c2 ha, hb; ha.re = GDG_LDG(H + 2 * k); ha.im = GDG_LDG(H + 2 * k + 1);
                 hb.re = GDG_LDG(H + 2 * k2); hb.im = GDG_LDG(H + 2 * k2 + 1);
