@@ -219,8 +219,12 @@ GDG_DEVI double ring_get(const double *ring, int hs, int pos, int q)
 /* x[idx] for idx in [-hs, n): block sample or history */
 GDG_DEVI double hist_or_block(const double *blk, const double *ring, int hs, int pos, int idx)
 {
-    /* both loads are issued unconditionally on clamped (valid) addresses so that the compiler can batch the
-     * global loads of an unrolled loop instead of branching around each of them */
+    return idx >= 0 ? blk[sw(idx)] : ring_get(ring, hs, pos, hs + idx);
+}
+/* same, for units that read mostly from the ring (delay, reverb line): both loads are issued unconditionally on
+ * clamped (valid) addresses so that the global loads of an unrolled loop are batched instead of branched around */
+GDG_DEVI double hist_or_block_nb(const double *blk, const double *ring, int hs, int pos, int idx)
+{
     int p = pos + hs + (idx < 0 ? idx : -1);
     if (p >= hs) p -= hs;
     if (p < 0) p = 0;
@@ -665,7 +669,7 @@ GDG_DEV void stage_delay(gdg_ctx &cx, const gdg_unit_desc &d_global)
         const double *ring = st + GDG_RING_ST_DATA;
         #pragma unroll 4
         for (int k = tid; k < n; k += GDG_NT) {
-            const double dl = hist_or_block(x, ring, ds, pos, k - ds);
+            const double dl = hist_or_block_nb(x, ring, ds, pos, k - ds);
             y[sw(k)] = clamp1(lvl * (x[sw(k)] + (fb * dl)));
         }
     GDG_THREADS_END

@@ -464,8 +464,8 @@ GDG_DEV void stage_reverb(gdg_ctx &cx, const gdg_unit_desc &d_global)
         for (int k = tid; k < n; k += GDG_NT) {
             /* taps beyond the ring (idx < -hs) read zero; loads are unconditional on clamped addresses */
             const int i0 = k - t0, i1 = k - t1, i2 = k - t2, i3 = k - t3;
-            const double v0 = hist_or_block(x, lring, hs, pos, i0 < -hs ? -hs : i0), v1 = hist_or_block(x, lring, hs, pos, i1 < -hs ? -hs : i1);
-            const double v2 = hist_or_block(x, lring, hs, pos, i2 < -hs ? -hs : i2), v3 = hist_or_block(x, lring, hs, pos, i3 < -hs ? -hs : i3);
+            const double v0 = hist_or_block_nb(x, lring, hs, pos, i0 < -hs ? -hs : i0), v1 = hist_or_block_nb(x, lring, hs, pos, i1 < -hs ? -hs : i1);
+            const double v2 = hist_or_block_nb(x, lring, hs, pos, i2 < -hs ? -hs : i2), v3 = hist_or_block_nb(x, lring, hs, pos, i3 < -hs ? -hs : i3);
             double pre = 0.0;
             pre += c0 * (i0 < -hs ? 0.0 : v0);
             pre += c1 * (i1 < -hs ? 0.0 : v1);
