@@ -452,6 +452,7 @@ int Unit::prepare(uint32_t rate, size_t n)
         depth = depth < 0.0 ? 0.0 : (depth > 10.0 ? 10.0 : depth);
         const int hs = (int)std::floor((0.05 * sr) + 0.5);
         d.i[0] = hs; d.p[0] = depth; d.p[1] = GDG_MATH_PI_THOUSANDTH * (double)num("speed"); d.p[2] = sr;
+        for (int j = 1; j < 5; j++) { d.p[2 + j] = std::cos(GDG_MATH_TWO_PI_FIFTH * (double)j); d.p[6 + j] = std::sin(GDG_MATH_TWO_PI_FIFTH * (double)j); }
         if (ensure_state(2 + (size_t)hs, hs, 1)) return -1;
         break; }
     case GDG_UNIT_FLANGER: case GDG_UNIT_PHASER: {

@@ -241,8 +241,10 @@ GDG_DEV void ring_push(gdg_ctx &cx, const double *blk, double *st, int hs)
         const int pos = (int)st_geti(st, GDG_RING_ST_POS);
         if (hs > 0) {
             if (n >= hs) {
+#pragma unroll 1
                 for (int q = tid; q < hs; q += GDG_NT) ring[q] = blk[sw(n - hs + q)];
             } else {
+#pragma unroll 1
                 for (int k = tid; k < n; k += GDG_NT) { int p = pos + k; if (p >= hs) p -= hs; ring[p] = blk[sw(k)]; }
             }
         }
@@ -283,6 +285,7 @@ GDG_DEV void stage_noisegate(gdg_ctx &cx, const gdg_unit_desc &d_global)
     GDG_THREADS_BEGIN
         const int k0 = tid * S, k1 = imin(n, k0 + S);
         double last = 0.0;
+#pragma unroll 1
         for (int k = k0; k < k1; k++) if (fabs(x[sw(k)]) > facClose) last = (double)(k + 1);
         R(a)[0] = 1.0; R(b)[0] = last;
     GDG_THREADS_END_NOSYNC
@@ -292,6 +295,7 @@ GDG_DEV void stage_noisegate(gdg_ctx &cx, const gdg_unit_desc &d_global)
         const int k0 = tid * S, k1 = imin(n, k0 + S);
         long long lc = (long long)R(lcin)[0];
         double ev = 0.0;
+#pragma unroll 1
         for (int k = k0; k < k1; k++) {
             const double amp = fabs(x[sw(k)]);
             if (amp > facClose) lc = k + 1;
@@ -309,6 +313,7 @@ GDG_DEV void stage_noisegate(gdg_ctx &cx, const gdg_unit_desc &d_global)
         const long long code = (long long)R(evin)[0];
         int open = code > 0 ? ((code & 3) == 1) : open0;
         unsigned long long since = 0;
+#pragma unroll 1
         for (int k = k0; k < k1; k++) {
             const double s = x[sw(k)];
             const double amp = fabs(s);
@@ -342,6 +347,7 @@ GDG_DEV void stage_compressor(gdg_ctx &cx, const gdg_unit_desc &d_global)
     GDG_THREADS_BEGIN
         const int k0 = tid * S, k1 = imin(n, k0 + S);
         double e = 0.0;
+#pragma unroll 1
         for (int k = k0; k < k1; k++) e = follow_step(mode, e, fabs(x[sw(k)]), dinv, dd);
         R(a)[0] = k0 < n ? chunk_A(astep, k1 - k0, S, afull) : 1.0; R(b)[0] = k0 < n ? e : 0.0;
     GDG_THREADS_END_NOSYNC
@@ -349,6 +355,7 @@ GDG_DEV void stage_compressor(gdg_ctx &cx, const gdg_unit_desc &d_global)
     GDG_THREADS_BEGIN
         const int k0 = tid * S, k1 = imin(n, k0 + S);
         double e = R(cin)[0];
+#pragma unroll 1
         for (int k = k0; k < k1; k++) {
             const double s = x[sw(k)];
             e = follow_step(mode, e, fabs(s), dinv, dd);
@@ -376,6 +383,7 @@ GDG_DEV void stage_tonestack(gdg_ctx &cx, const gdg_unit_desc &d_global)
     GDG_THREADS_BEGIN
         const int k0 = tid * S, k1 = imin(n, k0 + S);
         double h[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 1
         for (int k = k0; k < k1; k++) {
             const double s = x[sw(k)];
             for (int j = 0; j < 4; j++) h[j] += (s - h[j]) * d.p[j];
@@ -387,6 +395,7 @@ GDG_DEV void stage_tonestack(gdg_ctx &cx, const gdg_unit_desc &d_global)
         const int k0 = tid * S, k1 = imin(n, k0 + S);
         double h[4], l[4] = {0.0, 0.0, 0.0, 0.0};
         for (int j = 0; j < 4; j++) h[j] = R(hin)[j];
+#pragma unroll 1
         for (int k = k0; k < k1; k++) {
             const double s = x[sw(k)];
             for (int j = 0; j < 4; j++) {
@@ -403,6 +412,7 @@ GDG_DEV void stage_tonestack(gdg_ctx &cx, const gdg_unit_desc &d_global)
         const int k0 = tid * S, k1 = imin(n, k0 + S);
         double h[4], l[4];
         for (int j = 0; j < 4; j++) { h[j] = R(hin)[j]; l[j] = R(lin)[j]; }
+#pragma unroll 1
         for (int k = k0; k < k1; k++) {
             const double s = x[sw(k)];
             double sum = 0.0;
@@ -444,6 +454,7 @@ GDG_DEV void stage_cascade(gdg_ctx &cx, const gdg_unit_desc &d_global, int nsec,
     GDG_THREADS_BEGIN
         const int k0 = tid * S, k1 = imin(n, k0 + S);
         double v = 0.0;
+#pragma unroll 1
         for (int k = k0; k < k1; k++) v += (x[sw(k)] - v) * d.p[0];
         R(b)[0] = k0 < n ? v : 0.0;
     GDG_THREADS_END_NOSYNC
@@ -460,6 +471,7 @@ GDG_DEV void stage_cascade(gdg_ctx &cx, const gdg_unit_desc &d_global, int nsec,
             const int k0 = tid * S, k1 = imin(n, k0 + S);
             double v = R(cin)[0], w = 0.0;
             const double kk = d.p[s], kn = last ? 0.0 : d.p[s + 1];
+#pragma unroll 1
             for (int k = k0; k < k1; k++) {
                 double y = onepole_out(s < nhp, x[sw(k)], v, kk);
                 if (last) y = clamp1(y); else w += (y - w) * kn;
@@ -491,6 +503,7 @@ GDG_DEV void stage_bandpass(gdg_ctx &cx, const gdg_unit_desc &d_global)
         GDG_THREADS_BEGIN
             const int k0 = tid * S, k1 = imin(n, k0 + S);
             double h = 0.0;
+#pragma unroll 1
             for (int k = k0; k < k1; k++) h += (x[sw(k)] - h) * ka;
             R(a)[0] = k0 < n ? chunk_A(1.0 - ka, k1 - k0, S, aaf) : 1.0; R(b)[0] = k0 < n ? h : 0.0;
         GDG_THREADS_END_NOSYNC
@@ -498,6 +511,7 @@ GDG_DEV void stage_bandpass(gdg_ctx &cx, const gdg_unit_desc &d_global)
         GDG_THREADS_BEGIN
             const int k0 = tid * S, k1 = imin(n, k0 + S);
             double h = R(hin)[0], l = 0.0;
+#pragma unroll 1
             for (int k = k0; k < k1; k++) {
                 double diff = x[sw(k)] - h;
                 h += diff * ka;
@@ -510,6 +524,7 @@ GDG_DEV void stage_bandpass(gdg_ctx &cx, const gdg_unit_desc &d_global)
         GDG_THREADS_BEGIN
             const int k0 = tid * S, k1 = imin(n, k0 + S);
             double h = R(hin)[0], l = R(lin)[0];
+#pragma unroll 1
             for (int k = k0; k < k1; k++) {
                 double diff = x[sw(k)] - h;
                 h += diff * ka;
@@ -555,6 +570,7 @@ GDG_DEV void stage_tremolo(gdg_ctx &cx, const gdg_unit_desc &d_global)
     GDG_THREADS_BEGIN
         const int att0 = (int)st_geti(st, 0);
         const unsigned long long s0 = (unsigned long long)st_geti(st, 1) & 0xffffffffull;
+#pragma unroll 1
         for (int k = tid; k < n; k += GDG_NT) {
             int att; unsigned long long since;
             tremolo_at(k, att0, s0, lenA, lenU, att, since);
@@ -581,6 +597,7 @@ GDG_DEV void stage_ringmod(gdg_ctx &cx, const gdg_unit_desc &d_global)
     const double frac = d.p[0];
     GDG_THREADS_BEGIN
         const double phase = st[0];
+#pragma unroll 1
         for (int k = tid; k < n; k += GDG_NT) {
             const double cp = fmod(phase + ((double)k * frac), GDG_TWO_PI);
             x[sw(k)] = sin(cp) * x[sw(k)];
@@ -613,6 +630,7 @@ GDG_DEV void stage_siggen(gdg_ctx &cx, const gdg_unit_desc &d_global)
             const unsigned long long m = 2147483647ull;
             if (k0 < n) {
                 unsigned long long xs = ((unsigned long long)st_geti(st, 1) * lcg_pow((unsigned long long)k0)) % m;
+#pragma unroll 1
                 for (int k = k0; k < k1; k++) {
                     xs = (16807ull * xs) % m;
                     const double r = (double)xs / (double)(m - 1);
@@ -629,6 +647,7 @@ GDG_DEV void stage_siggen(gdg_ctx &cx, const gdg_unit_desc &d_global)
     GDG_THREADS_BEGIN
         const double phase = st[0];
         const double two_over_pi = 2.0 / GDG_PI;
+#pragma unroll 1
         for (int k = tid; k < n; k += GDG_NT) {
             const double cp = fmod(phase + ((double)k * inc), GDG_TWO_PI);
             double sig;
@@ -677,7 +696,7 @@ GDG_DEV void stage_delay(gdg_ctx &cx, const gdg_unit_desc &d_global)
     swap_bufs(cx);
 }
 
-/* chorus (effects/chorus.go:19-130): i[0] ring size; p[0] depth p[1] angularSpeed p[2] sampleRate
+/* chorus (effects/chorus.go:19-130): i[0] ring size; p[0] depth p[1] angularSpeed p[2] sampleRate p[3..6] cos(0.4 pi j), p[7..10] sin(0.4 pi j), j = 1..4
  * st[0] previousPhase (advanced by the RING length per call, chorus.go:114-117) */
 GDG_DEV void stage_chorus(gdg_ctx &cx, const gdg_unit_desc &d_global)
 {
@@ -692,9 +711,10 @@ GDG_DEV void stage_chorus(gdg_ctx &cx, const gdg_unit_desc &d_global)
         /* the five voices sit at fixed offsets 0.4*pi*j from the zero phase: one sincos per sample and the
          * angle-addition formula instead of five fmod + sin (differs from chorus.go:75-79 by ~1 ulp of the
          * sine, i.e. ~1e-13 samples of delay - far inside the 1e-9 budget) */
-        double cj[5], sj[5];
-        for (int j = 0; j < 5; j++) { sj[j] = sin((0.4 * GDG_PI) * (double)j); cj[j] = cos((0.4 * GDG_PI) * (double)j); }
-        #pragma unroll 4
+        double cj[5], sj[5];                           /* cos / sin of the voice offsets 0.4*pi*j (p[3..10], host-computed) */
+        cj[0] = 1.0; sj[0] = 0.0;
+        for (int j = 1; j < 5; j++) { cj[j] = d.p[2 + j]; sj[j] = d.p[6 + j]; }
+#pragma unroll 1
         for (int k = tid; k < n; k += GDG_NT) {
             const double t = (double)k / sr;
             const double zero_phase = fmod(prev + (ang * t), GDG_TWO_PI);
@@ -727,7 +747,7 @@ GDG_DEV void stage_flanger(gdg_ctx &cx, const gdg_unit_desc &d_global)
         const int pos = (int)st_geti(st, GDG_RING_ST_POS);
         const double *ring = st + GDG_RING_ST_DATA;
         const double prev = st[0];
-        #pragma unroll 4
+#pragma unroll 1
         for (int k = tid; k < n; k += GDG_NT) {
             const double t = (double)k * sr_inv;
             const double phase = fmod(prev + (ang * t), GDG_TWO_PI);
@@ -758,6 +778,7 @@ GDG_DEV void stage_autoyoy(gdg_ctx &cx, const gdg_unit_desc &d_global)
     GDG_THREADS_BEGIN
         const int k0 = tid * S, k1 = imin(n, k0 + S);
         double e = 0.0;
+#pragma unroll 1
         for (int k = k0; k < k1; k++) e = follow_step(mode, e, fabs(x[sw(k)]), dinv, dd);
         R(a)[0] = k0 < n ? chunk_A(astep, k1 - k0, S, afull) : 1.0; R(b)[0] = k0 < n ? e : 0.0;
     GDG_THREADS_END_NOSYNC
@@ -767,6 +788,7 @@ GDG_DEV void stage_autoyoy(gdg_ctx &cx, const gdg_unit_desc &d_global)
         const int pos = (int)st_geti(st, GDG_RING_ST_POS);
         const double *ring = st + GDG_RING_ST_DATA;
         double e = R(cin)[0];
+#pragma unroll 1
         for (int k = k0; k < k1; k++) {
             const double s = x[sw(k)];
             e = follow_step(mode, e, fabs(s), dinv, dd);

@@ -81,6 +81,7 @@ GDG_DEV void fuzz_run(gdg_ctx &cx, const gdg_unit_desc &d_global, double *z, int
     GDG_THREADS_BEGIN
         const int j0 = tid * Sb, j1 = imin(nbase, j0 + Sb);
         double e = 0.0;
+#pragma unroll 1
         for (int jl = j0; jl < j1; jl++)
 #pragma unroll
             for (int ph = 0; ph < F; ph++) e = follow_step(mode, e, fabs(z[fz_loc<F>(jl, ph)]), dinv, dd);
@@ -90,6 +91,7 @@ GDG_DEV void fuzz_run(gdg_ctx &cx, const gdg_unit_desc &d_global, double *z, int
     GDG_THREADS_BEGIN
         const int j0 = tid * Sb, j1 = imin(nbase, j0 + Sb);
         double e = R(ein)[0], c = 0.0;
+#pragma unroll 1
         for (int jl = j0; jl < j1; jl++)
 #pragma unroll
             for (int ph = 0; ph < F; ph++) {
@@ -105,6 +107,7 @@ GDG_DEV void fuzz_run(gdg_ctx &cx, const gdg_unit_desc &d_global, double *z, int
     GDG_THREADS_BEGIN
         const int j0 = tid * Sb, j1 = imin(nbase, j0 + Sb);
         double e = R(ein)[0], c = R(cin)[0];
+#pragma unroll 1
         for (int jl = j0; jl < j1; jl++)
 #pragma unroll
             for (int ph = 0; ph < F; ph++) {
@@ -192,6 +195,7 @@ GDG_DEV void oversampled_tiles(gdg_ctx &cx, const gdg_unit_desc &d_global)
         /* up-sample (+ stateless nonlinearity); exactly two base samples per thread for a full tile.  (Recomputing
          * the halo instead of carrying it was measured slower: 1065 items do not divide over 512 threads.) */
         GDG_THREADS_BEGIN
+#pragma unroll 1
             for (int jl = tid; jl < Tt; jl += GDG_NT) os_produce<F>(d, type, x, uph, z, t0 + jl, jl);
         GDG_THREADS_END
         if (!stateless) fuzz_run<F>(cx, d, z, Tt);
@@ -254,6 +258,7 @@ GDG_DEV void stage_oversampled(gdg_ctx &cx, const gdg_unit_desc &d_global)
     if (f <= 1) {
         if (type == GDG_UNIT_FUZZ) { fuzz_run<1>(cx, d, x, n); return; }
         GDG_THREADS_BEGIN
+#pragma unroll 1
             for (int k = tid; k < n; k += GDG_NT) x[sw(k)] = nl_pointwise(type, d, x[sw(k)]);
         GDG_THREADS_END
         return;
@@ -284,6 +289,7 @@ GDG_DEV void stage_octaver(gdg_ctx &cx, const gdg_unit_desc &d_global)
     GDG_THREADS_BEGIN
         const int k0 = tid * S, k1 = imin(n, k0 + S);
         double e = 0.0;
+#pragma unroll 1
         for (int k = k0; k < k1; k++) e = follow_step(mode, e, fabs(x[sw(k)]), dinv, dd);
         R(a)[0] = k0 < n ? chunk_A(astep, k1 - k0, S, afull) : 1.0; R(b)[0] = k0 < n ? e : 0.0;
     GDG_THREADS_END_NOSYNC
@@ -291,6 +297,7 @@ GDG_DEV void stage_octaver(gdg_ctx &cx, const gdg_unit_desc &d_global)
     GDG_THREADS_BEGIN
         const int k0 = tid * S, k1 = imin(n, k0 + S);
         double e = R(ein)[0], fs = 0.0, ls = 0.0, fl = 0.0;
+#pragma unroll 1
         for (int k = k0; k < k1; k++) {
             const double s = x[sw(k)], sa = fabs(s);
             e = follow_step(mode, e, sa, dinv, dd);
@@ -323,6 +330,7 @@ GDG_DEV void stage_octaver(gdg_ctx &cx, const gdg_unit_desc &d_global)
         const int k0 = tid * S, k1 = imin(n, k0 + S);
         double e = R(ein)[0], pol = polin[tid], c = 0.0;
         long long reg = (long long)regin[tid];
+#pragma unroll 1
         for (int k = k0; k < k1; k++) {
             const double s = x[sw(k)], sa = fabs(s);
             e = follow_step(mode, e, sa, dinv, dd);
@@ -343,6 +351,7 @@ GDG_DEV void stage_octaver(gdg_ctx &cx, const gdg_unit_desc &d_global)
     GDG_THREADS_BEGIN
         const int k0 = tid * S, k1 = imin(n, k0 + S);
         double c = R(cin)[0];
+#pragma unroll 1
         for (int k = k0; k < k1; k++) {
             double pre = SM_ALT(cx)[sw(k)];
             c += (pre - c) * dd;
@@ -373,6 +382,7 @@ GDG_DEV void stage_autowah(gdg_ctx &cx, const gdg_unit_desc &d_global)
     GDG_THREADS_BEGIN
         const int k0 = tid * S, k1 = imin(n, k0 + S);
         double e = 0.0;
+#pragma unroll 1
         for (int k = k0; k < k1; k++) e = follow_step(mode, e, fabs(x[sw(k)]), dinv, dd);
         R(a)[0] = k0 < n ? chunk_A(astep, k1 - k0, S, afull) : 1.0; R(b)[0] = k0 < n ? e : 0.0;
     GDG_THREADS_END_NOSYNC
@@ -380,6 +390,7 @@ GDG_DEV void stage_autowah(gdg_ctx &cx, const gdg_unit_desc &d_global)
     GDG_THREADS_BEGIN
         const int k0 = tid * S, k1 = imin(n, k0 + S);
         double e = R(ein)[0], ap = 1.0;
+#pragma unroll 1
         for (int k = k0; k < k1; k++) {
             e = follow_step(mode, e, fabs(x[sw(k)]), dinv, dd);
             const double level = 20.0 * log10(e);
@@ -399,6 +410,7 @@ GDG_DEV void stage_autowah(gdg_ctx &cx, const gdg_unit_desc &d_global)
         GDG_THREADS_BEGIN
             const int k0 = tid * S, k1 = imin(n, k0 + S);
             double h = 0.0;
+#pragma unroll 1
             for (int k = k0; k < k1; k++) h += (x[sw(k)] - h) * kv[sw(k)];
             R(a)[0] = R(aprod); R(b)[0] = h;
         GDG_THREADS_END_NOSYNC
@@ -406,6 +418,7 @@ GDG_DEV void stage_autowah(gdg_ctx &cx, const gdg_unit_desc &d_global)
         GDG_THREADS_BEGIN
             const int k0 = tid * S, k1 = imin(n, k0 + S);
             double h = R(hin)[0], l = 0.0;
+#pragma unroll 1
             for (int k = k0; k < k1; k++) {
                 const double kk = kv[sw(k)];
                 double diff = x[sw(k)] - h;
@@ -419,6 +432,7 @@ GDG_DEV void stage_autowah(gdg_ctx &cx, const gdg_unit_desc &d_global)
         GDG_THREADS_BEGIN
             const int k0 = tid * S, k1 = imin(n, k0 + S);
             double h = R(hin)[0], l = R(lin)[0];
+#pragma unroll 1
             for (int k = k0; k < k1; k++) {
                 const double kk = kv[sw(k)];
                 double diff = x[sw(k)] - h;
@@ -477,6 +491,7 @@ GDG_DEV void stage_reverb(gdg_ctx &cx, const gdg_unit_desc &d_global)
     /* push the dry block into the line ring, then fold dry + line */
     GDG_THREADS_BEGIN
         const int pos = (int)st_geti(st, GDG_RV_ST_LINEPOS);
+#pragma unroll 1
         for (int k = tid; k < n; k += GDG_NT) {
             const double xv = x[sw(k)];
             if (n >= hs) { if (k >= n - hs) lring[k - (n - hs)] = xv; }
@@ -500,6 +515,7 @@ GDG_DEV void stage_reverb(gdg_ctx &cx, const gdg_unit_desc &d_global)
         for (int r0 = 0; r0 < n; r0 += lag) {
             const int r1 = imin(n, r0 + lag);
             GDG_THREADS_BEGIN
+#pragma unroll 1
                 for (int k = r0 + tid; k < r1; k += GDG_NT) {
                     const double dl = k < lag ? P[k] : P[k - lag];
                     const double pre = w[sw(k)] - (g * dl);
@@ -515,6 +531,7 @@ GDG_DEV void stage_reverb(gdg_ctx &cx, const gdg_unit_desc &d_global)
         GDG_THREADS_END
     }
     GDG_THREADS_BEGIN
+#pragma unroll 1
         for (int k = tid; k < n; k += GDG_NT) x[sw(k)] = clamp1(x[sw(k)] + (d.p[1] * w[sw(k)]));
     GDG_THREADS_END
 }
@@ -644,6 +661,7 @@ GDG_DEV void fft_pass(double *D, const double *tws, int logM, int nseg, int logL
     const int nb = nseg << (logM - LOGR);
     const int tshift = 13 - logL;                              /* W_L^j = tws[j << tshift]: shared table exp(-2 pi i k / 8192), k < 1024 */
     GDG_THREADS_BEGIN
+#pragma unroll 1
         for (int b = tid; b < nb; b += GDG_NT) {
             const int seg = b >> (logM - LOGR), rb = b & ((1 << (logM - LOGR)) - 1);
             const int blk = rb >> logS, j = rb & ((1 << logS) - 1);
@@ -704,6 +722,7 @@ GDG_DEV void stage_poweramp(gdg_ctx &cx, const gdg_unit_desc &d_global, const do
     double *x = SM_CUR(cx);
     if (L <= 0) {                                              /* filter.go:366-367 / poweramp.go:210-214 */
         GDG_THREADS_BEGIN
+#pragma unroll 1
             for (int k = tid; k < n; k += GDG_NT) x[sw(k)] = 0.0;
         GDG_THREADS_END
         return;
@@ -831,6 +850,7 @@ GDG_DEV void stage_poweramp(gdg_ctx &cx, const gdg_unit_desc &d_global, const do
                 R(buf)[r] = clamp1(pre);
             }
         }
+#pragma unroll 1
         for (int q = tid; q < F - ns; q += GDG_NT) {
             double v = scale * GDG_YR(nb - 1, ns + q);
             if (nb == 1 && ns + q < F - zlen) v += tail[ns + q];
@@ -839,6 +859,7 @@ GDG_DEV void stage_poweramp(gdg_ctx &cx, const gdg_unit_desc &d_global, const do
     GDG_THREADS_END
     cx.cur_off = GDG_SMEM_R; cx.alt_off = GDG_SMEM_R + GDG_MAX_N;
     GDG_THREADS_BEGIN
+#pragma unroll 1
         for (int q = tid; q < F - ns; q += GDG_NT) tail[q] = GDG_YR(nb - 1, ns + q);
         for (int q = F - ns + tid; q < F - zlen; q += GDG_NT) tail[q] = 0.0;
         if (tid == 0) { st_seti(tail, F, ns); if (K > 1) st_seti(tail, F + 1, (slot + 1) % K); }
