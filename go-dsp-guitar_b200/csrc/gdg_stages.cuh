@@ -128,10 +128,11 @@ GDG_DEVI void st_seti(double *st, int k, long long v) { ((long long *)st)[k] = v
 GDG_DEVI int chunk_len(int n) { return (n + GDG_NT - 1) / GDG_NT; }
 GDG_DEVI void swap_bufs(gdg_ctx &cx) { const int t = cx.cur_off; cx.cur_off = cx.alt_off; cx.alt_off = t; }
 
-GDG_DEVI double pow_int(double a, int k)
+GDG_DEVI double pow_int(double a, int k)          /* a^k by binary exponentiation (k >= 0) */
 {
     double r = 1.0;
-    for (int i = 0; i < k; i++) r *= a;
+#pragma unroll 1
+    while (k > 0) { if (k & 1) r *= a; a *= a; k >>= 1; }
     return r;
 }
 

@@ -192,9 +192,11 @@ GDG_DEV void oversampled_tiles(gdg_ctx &cx, const gdg_unit_desc &d_global)
     GDG_THREADS_END
     for (int t0 = 0; t0 < n; t0 += T) {
         const int Tt = imin(T, n - t0);
-        /* up-sample (+ stateless nonlinearity); exactly two base samples per thread for a full tile.  (Recomputing
-         * the halo instead of carrying it was measured slower: 1065 items do not divide over 512 threads.) */
+        /* up-sample (+ stateless nonlinearity): two base samples per thread for a full tile; the same phase lands the
+         * halo staged by the previous tile (cells m <= GDG_ZH; this tile writes cells m >= GDG_ZH, and (phase 0,
+         * m = GDG_ZH) is this tile's own sample, which the staging skips) */
         GDG_THREADS_BEGIN
+            if (t0 > 0 && tid < F * 64) { const int p = tid >> 6, m = tid & 63; if (m < GDG_ZH || (m == GDG_ZH && p > 0)) z[p * GDG_ZPS + pz(m)] = SM_SCANB[tid]; }
 #pragma unroll 1
             for (int jl = tid; jl < Tt; jl += GDG_NT) os_produce<F>(d, type, x, uph, z, t0 + jl, jl);
         GDG_THREADS_END
@@ -218,24 +220,17 @@ GDG_DEV void oversampled_tiles(gdg_ctx &cx, const gdg_unit_desc &d_global)
                     if (i0 + r < Tt) { if (p == 0) y[sw(t0 + i0 + r)] = acc[r]; else part[(p - 1) * GDG_OS_TILE + sw(i0 + r)] = acc[r]; }
             }
         GDG_THREADS_END
-        /* combine in phase order, clamp, -0.5 dB */
+        /* combine in phase order, clamp, -0.5 dB; stage the halo (last GDG_ZH + 1 cells of every phase) for the next tile */
         GDG_THREADS_BEGIN
+#pragma unroll 1
             for (int i = tid; i < Tt; i += GDG_NT) {
                 double acc = y[sw(t0 + i)];
 #pragma unroll
                 for (int p = 1; p < F; p++) acc += part[(p - 1) * GDG_OS_TILE + sw(i)];
                 y[sw(t0 + i)] = 0.9440608762859234 * clamp1(acc);
             }
-        GDG_THREADS_END_NOSYNC
-        if (t0 + Tt < n) {
-            /* carry the halo (last GDG_ZH + 1 entries of every phase) to the front */
-            GDG_THREADS_BEGIN
-                if (tid < F * 64) { const int p = tid >> 6, m = tid & 63; if (m <= GDG_ZH) SM_SCANB[tid] = z[p * GDG_ZPS + pz(m + Tt)]; }
-            GDG_THREADS_END
-            GDG_THREADS_BEGIN
-                if (tid < F * 64) { const int p = tid >> 6, m = tid & 63; if (m <= GDG_ZH) z[p * GDG_ZPS + pz(m)] = SM_SCANB[tid]; }
-            GDG_THREADS_END
-        }
+            if (t0 + Tt < n && tid < F * 64) { const int p = tid >> 6, m = tid & 63; if (m <= GDG_ZH) SM_SCANB[tid] = z[p * GDG_ZPS + pz(m + Tt)]; }
+        GDG_THREADS_END
         if (t0 + Tt >= n) {
             /* carry: oversampled history (entries Tt .. Tt + GDG_ZH of the last tile) and the last 8 inputs (oversampling.go:91-93) */
             GDG_THREADS_BEGIN
@@ -790,7 +785,7 @@ GDG_DEV void stage_poweramp(gdg_ctx &cx, const gdg_unit_desc &d_global, const do
                 cst(D, cz(zb), o);
             }
         }
-#pragma unroll 4
+#pragma unroll 2
         for (int b = tid; b < nb * (M / 2); b += GDG_NT) {
             const int seg = b / (M / 2), k = 1 + (b - seg * (M / 2));
             const int zb = seg * M;

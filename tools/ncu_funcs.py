@@ -39,3 +39,21 @@ def dem(n):
 for f, n in agg.most_common(25):
     top = ", ".join("%s %d%%" % (k, 100 * v / max(1, sum(stalls[f].values()))) for k, v in stalls[f].most_common(4))
     print("%5.1f%%  %-46s %s" % (100.0 * n / tot, dem(f)[:46], top))
+
+# optional: hot 128-instruction windows inside one function (argv[3] = substring of its name)
+if len(sys.argv) > 3:
+    want = sys.argv[3]
+    for a, sz, nm in funcs:
+        if want in dem(nm):
+            i0, i1 = a // 16, (a + sz) // 16
+            ftot = sum(int(rows[i][iS] or 0) for i in range(i0, min(i1, len(rows))))
+            print("---- %s: %d instructions, %d samples" % (dem(nm), i1 - i0, ftot))
+            iSrc = hdr.index("Source")
+            for s0 in range(i0, i1, 128):
+                blk = rows[s0:min(s0 + 128, i1)]
+                smp = sum(int(r[iS] or 0) for r in blk)
+                mix = collections.Counter(r[iSrc].split()[0].split(".")[0] for r in blk if r[iSrc].strip())
+                st = collections.Counter()
+                for r in blk:
+                    for c in stall_cols: st[hdr[c][6:]] += int(float(r[c] or 0))
+                print("%5.1f%% +%5d %s | %s" % (100.0 * smp / max(1, ftot), s0 - i0, dict(mix.most_common(5)), ", ".join("%s %d%%" % (k, 100 * v / max(1, sum(st.values()))) for k, v in st.most_common(3))))
