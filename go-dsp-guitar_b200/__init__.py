@@ -90,6 +90,11 @@ ABI = {
     "gdg_chain_process": (_int, [_vp, _vp, _vp, _sz, _u32]),
     "gdg_process_batch": (_int, [_vp, _sz, _vp, _vp, _sz, _u32]),
     "gdg_process_batch_device": (_int, [_vp, _sz, _vp, _vp, _sz, _sz, _u32, _vp]),
+    "gdg_format_bytes_per_sample": (_sz, [_int]),
+    "gdg_process_batch_encoded": (_int, [_vp, _sz, _vp, _int, _vp, _int, _sz, _u32]),
+    "gdg_process_batch_device_encoded": (_int, [_vp, _sz, _vp, _int, _sz, _vp, _int, _sz, _sz, _u32, _vp]),
+    "gdg_resample_time_length": (_sz, [_sz, _u32, _u32]),
+    "gdg_resample_time": (C.c_long, [_vp, _sz, _u32, _u32, _vp, _sz]),
     "gdg_spatializer_create": (_vp, [_u32]),
     "gdg_spatializer_destroy": (None, [_vp]),
     "gdg_spatializer_set_azimuth": (_int, [_vp, _u32, _dbl]),
@@ -296,6 +301,35 @@ def process_batch(chains, inputs, sample_rate):
     if lib.gdg_process_batch(_handles(chains), c, ip, op, n, sample_rate) < 0:
         raise GdgError(lib.gdg_last_error().decode())
     return out
+
+
+FORMATS = ["PCM8", "PCM16", "PCM24", "PCM32", "IEEE32", "IEEE64"]          # wave/wave.go:737-838
+
+
+def process_batch_encoded(chains, rows, in_format, out_format, n, sample_rate):
+    """gdg_process_batch_encoded: rows = list of bytes-like (one channel's payload each); returns list of bytes."""
+    lib = chains[0]._lib
+    fi, fo = FORMATS.index(in_format), FORMATS.index(out_format)
+    ins = [np.frombuffer(bytes(r), dtype=np.uint8).copy() for r in rows]
+    outs = [np.zeros(n * lib.gdg_format_bytes_per_sample(fo), dtype=np.uint8) for _ in rows]
+    c = len(rows)
+    ip = (C.c_void_p * c)(*[a.ctypes.data for a in ins])
+    op = (C.c_void_p * c)(*[a.ctypes.data for a in outs])
+    if lib.gdg_process_batch_encoded(_handles(chains), c, ip, fi, op, fo, n, sample_rate) < 0:
+        raise GdgError(lib.gdg_last_error().decode())
+    return [o.tobytes() for o in outs]
+
+
+def resample_time(x, source_rate, target_rate, lib=None):
+    """resample.Time (resample/resample.go:72-103) on the device."""
+    lib = lib if lib is not None else load()
+    x = _f64(x)
+    n = lib.gdg_resample_time_length(len(x), source_rate, target_rate)
+    out = np.zeros(n)
+    r = lib.gdg_resample_time(_ptr(x), len(x), source_rate, target_rate, _ptr(out), n)
+    if r < 0:
+        raise GdgError(lib.gdg_last_error().decode())
+    return out[:r]
 
 
 class BatchRunner:

@@ -46,9 +46,11 @@ int gdgb_set_tables(const double *aa2, const double *aa4, const double *lz2, con
                     const double *twiddles /* GDG_MAX_FFT/2 complex */);
 
 /* fused chain segment: CTA c runs descs[c] (NULL -> pass-through copy when in != out, else nothing)
- * on in + c*stride -> out + c*stride */
-int gdgb_launch_chains(const gdg_chain_desc *const *d_descs, int channels, const double *d_in, double *d_out,
-                       long stride, int n, void *stream);
+ * on in + c*in_stride_bytes -> out + c*out_stride_bytes; samples are decoded / encoded per GDG_FMT_* */
+int gdgb_launch_chains(const gdg_chain_desc *const *d_descs, int channels, const void *d_in, long in_stride_bytes, int in_fmt,
+                       void *d_out, long out_stride_bytes, int out_fmt, int n, void *stream);
+/* resample.Time on device: d_out[i], i < out_len */
+int gdgb_resample_time(const double *d_in, long n, double dx, double *d_out, long out_len, void *stream);
 
 /* spatializer: out[2][n] (+)= sum over channels; hist_in/hist_out: [C][hs] double-buffered history */
 int gdgb_launch_spatializer(const gdg_spat_channel *d_ch, int channels, const double *d_in, long stride,

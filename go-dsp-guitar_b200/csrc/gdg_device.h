@@ -35,6 +35,9 @@ enum {
     GDG_UNIT_CABINET, GDG_UNIT_COUNT
 };
 
+/* sample formats of the encoded entry points == the (format, bit depth) pairs of wave/wave.go:737-838 */
+enum { GDG_FMT_PCM8 = 0, GDG_FMT_PCM16, GDG_FMT_PCM24, GDG_FMT_PCM32, GDG_FMT_IEEE32, GDG_FMT_IEEE64 };
+
 /* follower modes (compressor.go:44-58 and friends) */
 enum { GDG_FOLLOW_ENVELOPE = 0, GDG_FOLLOW_LEVEL = 1, GDG_FOLLOW_OTHER = 2 };
 

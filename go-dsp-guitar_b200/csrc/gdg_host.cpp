@@ -678,16 +678,26 @@ int prepare_batch(gdg_chain *const *chains, size_t C, uint32_t rate, size_t n, v
     }
     return (int)rounds;
 }
-/* launch channels [c0, c0 + cnt) of the prepared batch */
-int launch_batch(size_t c0, size_t cnt, int rounds, const double *d_in, double *d_out, size_t stride, size_t n, void *stream)
+size_t fmt_bytes(int fmt) { static const size_t b[6] = {1, 2, 3, 4, 4, 8}; return (fmt >= 0 && fmt < 6) ? b[fmt] : 0; }
+
+/* launch channels [c0, c0 + cnt) of the prepared batch; strides in bytes, samples in the given formats */
+int launch_batch_fmt(size_t c0, size_t cnt, int rounds, const void *d_in, size_t in_stride, int in_fmt,
+                     void *d_out, size_t out_stride, int out_fmt, size_t n, void *stream)
 {
     Batch &b = *g_batch;
+    if (rounds > 1 && (in_fmt != GDG_FMT_IEEE64 || out_fmt != GDG_FMT_IEEE64))
+        return fail("encoded sample formats need chains of at most %d active units (one fused segment)", GDG_MAX_SLOTS);
     for (int r = 0; r < rounds; r++) {
-        const double *src = r == 0 ? d_in : d_out;
-        if (gdgb_launch_chains(b.d_ptrs[r] + c0, (int)cnt, src + c0 * stride, d_out + c0 * stride, (long)stride, (int)n, stream))
+        const unsigned char *src = r == 0 ? (const unsigned char *)d_in + c0 * in_stride : (const unsigned char *)d_out + c0 * out_stride;
+        if (gdgb_launch_chains(b.d_ptrs[r] + c0, (int)cnt, src, (long)(r == 0 ? in_stride : out_stride), r == 0 ? in_fmt : out_fmt,
+                               (unsigned char *)d_out + c0 * out_stride, (long)out_stride, out_fmt, (int)n, stream))
             return backend_fail("chain kernel launch failed");
     }
     return 0;
+}
+int launch_batch(size_t c0, size_t cnt, int rounds, const double *d_in, double *d_out, size_t stride, size_t n, void *stream)
+{
+    return launch_batch_fmt(c0, cnt, rounds, d_in, stride * sizeof(double), GDG_FMT_IEEE64, d_out, stride * sizeof(double), GDG_FMT_IEEE64, n, stream);
 }
 int run_batch_device(gdg_chain *const *chains, size_t C, const double *d_in, double *d_out, size_t stride, size_t n,
                      uint32_t rate, void *stream)
@@ -732,22 +742,28 @@ int stage_buffers(Batch &b, size_t words)
 }
 
 /* host rows [c0, c0+cnt) (array of pointers) -> device planar, asynchronously on `stream_id` */
-int upload_rows(Batch &b, const double *const *in, size_t c0, size_t cnt, size_t n, double *d_dst, int stream_id)
+bool contiguous_bytes(const void *const *p, size_t C, size_t row_bytes)
 {
-    const size_t bytes = n * sizeof(double);
-    if (contiguous(in + c0, cnt, n) && gdgb_is_pinned(in[c0]))
-        return gdgb_h2d_async(d_dst + c0 * n, in[c0], cnt * bytes, stream_id) ? backend_fail("upload failed") : 0;
+    for (size_t c = 1; c < C; c++) if ((const char *)p[c] != (const char *)p[0] + c * row_bytes) return false;
+    return true;
+}
+/* rows are `bytes` long (n samples of the batch's input format) */
+int upload_rows(Batch &b, const void *const *in, size_t c0, size_t cnt, size_t bytes, void *d_dst, int stream_id)
+{
+    char *dst = (char *)d_dst, *hs = (char *)b.h_stage;
+    if (contiguous_bytes(in + c0, cnt, bytes) && gdgb_is_pinned(in[c0]))
+        return gdgb_h2d_async(dst + c0 * bytes, in[c0], cnt * bytes, stream_id) ? backend_fail("upload failed") : 0;
     /* pageable / scattered rows: gather into the library's pinned staging, then one copy */
-    for (size_t c = c0; c < c0 + cnt; c++) memcpy(b.h_stage + c * n, in[c], bytes);
-    return gdgb_h2d_async(d_dst + c0 * n, b.h_stage + c0 * n, cnt * bytes, stream_id) ? backend_fail("upload failed") : 0;
+    for (size_t c = c0; c < c0 + cnt; c++) memcpy(hs + c * bytes, in[c], bytes);
+    return gdgb_h2d_async(dst + c0 * bytes, hs + c0 * bytes, cnt * bytes, stream_id) ? backend_fail("upload failed") : 0;
 }
 /* device planar rows -> host rows; returns 1 if the data still sits in the pinned staging (scatter after sync) */
-int download_rows(Batch &b, double *const *out, size_t c0, size_t cnt, size_t n, const double *d_src, int stream_id)
+int download_rows(Batch &b, void *const *out, size_t c0, size_t cnt, size_t bytes, const void *d_src, int stream_id)
 {
-    const size_t bytes = n * sizeof(double);
-    if (contiguous((const double *const *)out + c0, cnt, n) && gdgb_is_pinned(out[c0]))
-        return gdgb_d2h_async(out[c0], d_src + c0 * n, cnt * bytes, stream_id) ? backend_fail("download failed") : 0;
-    if (gdgb_d2h_async(b.h_stage2 + c0 * n, d_src + c0 * n, cnt * bytes, stream_id)) return backend_fail("download failed");
+    const char *src = (const char *)d_src;
+    if (contiguous_bytes((const void *const *)out + c0, cnt, bytes) && gdgb_is_pinned(out[c0]))
+        return gdgb_d2h_async(out[c0], src + c0 * bytes, cnt * bytes, stream_id) ? backend_fail("download failed") : 0;
+    if (gdgb_d2h_async((char *)b.h_stage2 + c0 * bytes, src + c0 * bytes, cnt * bytes, stream_id)) return backend_fail("download failed");
     return 1;
 }
 int ensure_host_stage(Batch &b, size_t words)
@@ -778,7 +794,7 @@ int download_simple(double *const *out, size_t C, size_t n, const double *d_src)
 
 /* the whole host-buffer block: upload -> (tuner feed) -> chains -> (spatializer) -> download, pipelined */
 int host_block(gdg_chain *const *chains, size_t C, gdg_tuner *tuner, int tuner_channel, gdg_spatializer *spat,
-               const double *const *in, double *const *out, size_t n_out_rows, size_t n, uint32_t rate);
+               const void *const *in, int in_fmt, void *const *out, int out_fmt, size_t n_out_rows, size_t n, uint32_t rate);
 
 } // namespace
 
@@ -845,16 +861,18 @@ struct gdg_tuner {
 };
 
 namespace {
+/* in_fmt / out_fmt: sample formats of the host rows (tuner and spatializer need float64 rows) */
 int host_block(gdg_chain *const *chains, size_t C, gdg_tuner *tuner, int tuner_channel, gdg_spatializer *spat,
-               const double *const *in, double *const *out, size_t n_out_rows, size_t n, uint32_t rate)
+               const void *const *in, int in_fmt, void *const *out, int out_fmt, size_t n_out_rows, size_t n, uint32_t rate)
 {
     std::lock_guard<std::mutex> lk(g_batch_mutex);
     const int rounds = prepare_batch(chains, C, rate, n, gdgb_stream());
     if (rounds < 0) return -1;
     Batch &b = *g_batch;
+    const size_t ib = n * fmt_bytes(in_fmt), ob = n * fmt_bytes(out_fmt);      /* bytes per row */
     if (stage_buffers(b, (C + 2) * n)) return -1;
-    const bool in_direct = contiguous(in, C, n) && gdgb_is_pinned(in[0]);
-    const bool out_direct = contiguous((const double *const *)out, n_out_rows, n) && gdgb_is_pinned(out[0]);
+    const bool in_direct = contiguous_bytes(in, C, ib) && gdgb_is_pinned(in[0]);
+    const bool out_direct = contiguous_bytes((const void *const *)out, n_out_rows, ob) && gdgb_is_pinned(out[0]);
     if ((!in_direct || !out_direct) && ensure_host_stage(b, (C + 2) * n)) return -1;
     const size_t per = pipeline_group_size(C);
     const int G = (int)((C + per - 1) / per);
@@ -864,32 +882,32 @@ int host_block(gdg_chain *const *chains, size_t C, gdg_tuner *tuner, int tuner_c
         const size_t c0 = (size_t)g * per;
         if (c0 >= C) break;
         const size_t cnt = std::min(per, C - c0);
-        if (upload_rows(b, in, c0, cnt, n, b.d_in, 1)) return -1;
-        if (gdgb_record(g, 1)) return backend_fail("event record failed");
+        if (upload_rows(b, in, c0, cnt, ib, b.d_in, 1)) return -1;
+        if (gdgb_record(g % 16, 1)) return backend_fail("event record failed");
     }
     for (int g = 0; g < G; g++) {
         const size_t c0 = (size_t)g * per;
         if (c0 >= C) break;
         const size_t cnt = std::min(per, C - c0);
-        if (gdgb_wait(0, g)) return backend_fail("stream wait failed");
+        if (gdgb_wait(0, g % 16)) return backend_fail("stream wait failed");
         if (tuner && tuner_channel >= 0 && (size_t)tuner_channel >= c0 && (size_t)tuner_channel < c0 + cnt)
             if (gdg_tuner_process_device(tuner, b.d_in + (size_t)tuner_channel * n, n, rate, s0)) return -1;   /* controller.go:2668-2672 */
-        if (launch_batch(c0, cnt, rounds, b.d_in, b.d_out, n, n, s0)) return -1;                               /* controller.go:2682-2705 */
-        if (gdgb_record(16 + g, 0) || gdgb_wait(2, 16 + g)) return backend_fail("event failed");
-        const int r = download_rows(b, out, c0, cnt, n, b.d_out, 2);
+        if (launch_batch_fmt(c0, cnt, rounds, b.d_in, ib, in_fmt, b.d_out, ob, out_fmt, n, s0)) return -1;       /* controller.go:2682-2705 */
+        if (gdgb_record(16 + g % 16, 0) || gdgb_wait(2, 16 + g % 16)) return backend_fail("event failed");
+        const int r = download_rows(b, out, c0, cnt, ob, b.d_out, 2);
         if (r < 0) return -1;
         if (r == 1) staged.push_back({c0, cnt});
     }
     if (spat) {                                                                                                 /* controller.go:2761 */
         if (gdg_spatializer_process_device(spat, b.d_out, n, nullptr, b.d_out + C * n, n, n, 0, s0)) return -1;
         if (gdgb_record(40, 0) || gdgb_wait(2, 40)) return backend_fail("event failed");
-        const int r = download_rows(b, out, C, 2, n, b.d_out, 2);
+        const int r = download_rows(b, out, C, 2, ob, b.d_out, 2);
         if (r < 0) return -1;
         if (r == 1) staged.push_back({C, 2});
     }
     if (gdgb_sync_stream(2)) return backend_fail("synchronize failed");
     for (auto &sg : staged)
-        for (size_t c = sg.first; c < sg.first + sg.second; c++) memcpy(out[c], b.h_stage2 + c * n, n * sizeof(double));
+        for (size_t c = sg.first; c < sg.first + sg.second; c++) memcpy(out[c], (char *)b.h_stage2 + c * ob, ob);
     return 0;
 }
 } // namespace
@@ -1228,7 +1246,7 @@ int gdg_process_batch(gdg_chain *const *chains, size_t C, const double *const *i
     if (ensure_init()) return -1;
     if (!chains || !C || !in || !out) return fail("gdg_process_batch: bad argument");
     if (check_block(n)) return -1;
-    return host_block(chains, C, nullptr, -1, nullptr, in, out, C, n, rate);
+    return host_block(chains, C, nullptr, -1, nullptr, (const void *const *)in, GDG_FMT_IEEE64, (void *const *)out, GDG_FMT_IEEE64, C, n, rate);
 }
 
 int gdg_chain_process(gdg_chain *c, const double *in, double *out, size_t n, uint32_t rate)
@@ -1255,7 +1273,8 @@ int gdg_chain_process(gdg_chain *c, const double *in, double *out, size_t n, uin
         c->self_rounds = (size_t)rounds;
     }
     for (int r = 0; r < rounds; r++)
-        if (gdgb_launch_chains(c->d_self + r, 1, r == 0 ? c->d_in : c->d_out, c->d_out, (long)n, (int)n, gdgb_stream()))
+        if (gdgb_launch_chains(c->d_self + r, 1, r == 0 ? c->d_in : c->d_out, (long)(n * sizeof(double)), GDG_FMT_IEEE64, c->d_out,
+                               (long)(n * sizeof(double)), GDG_FMT_IEEE64, (int)n, gdgb_stream()))
             return backend_fail("chain kernel launch failed");
     return gdgb_download(out, c->d_out, n * sizeof(double)) ? backend_fail("download failed") : 0;
 }
@@ -1420,6 +1439,57 @@ int gdg_tuner_analyze(gdg_tuner *t, gdg_tuner_result *res)
     return 0;
 }
 
+/* ---- encoded batch (wave/wave.go sample formats fused into the kernel's load / store) ---- */
+size_t gdg_format_bytes_per_sample(int format) { return fmt_bytes(format); }
+int gdg_process_batch_encoded(gdg_chain *const *chains, size_t C, const void *const *in, int in_format, void *const *out, int out_format,
+                              size_t n, uint32_t rate)
+{
+    if (ensure_init()) return -1;
+    if (!chains || !C || !in || !out) return fail("gdg_process_batch_encoded: bad argument");
+    if (!fmt_bytes(in_format) || !fmt_bytes(out_format)) return fail("Unknown sample format: %#04x", fmt_bytes(in_format) ? out_format : in_format);
+    if (check_block(n)) return -1;
+    return host_block(chains, C, nullptr, -1, nullptr, in, in_format, out, out_format, C, n, rate);
+}
+int gdg_process_batch_device_encoded(gdg_chain *const *chains, size_t C, const void *d_in, int in_format, size_t in_stride_bytes,
+                                     void *d_out, int out_format, size_t out_stride_bytes, size_t n, uint32_t rate, void *stream)
+{
+    if (ensure_init()) return -1;
+    if (!chains || !C || !d_in || !d_out) return fail("gdg_process_batch_device_encoded: bad argument");
+    if (!fmt_bytes(in_format) || !fmt_bytes(out_format)) return fail("Unknown sample format: %#04x", fmt_bytes(in_format) ? out_format : in_format);
+    if (in_stride_bytes < n * fmt_bytes(in_format) || out_stride_bytes < n * fmt_bytes(out_format)) return fail("gdg_process_batch_device_encoded: stride too small");
+    if (check_block(n)) return -1;
+    std::lock_guard<std::mutex> lk(g_batch_mutex);
+    void *st = stream ? stream : gdgb_stream();
+    const int rounds = prepare_batch(chains, C, rate, n, st);
+    if (rounds < 0) return -1;
+    return launch_batch_fmt(0, C, rounds, d_in, in_stride_bytes, in_format, d_out, out_stride_bytes, out_format, n, st);
+}
+
+/* ---- resample.Time (resample/resample.go:72-103) ---- */
+size_t gdg_resample_time_length(size_t n, uint32_t src, uint32_t dst)
+{
+    if (!src) return 0;
+    const double lf = (double)n * ((double)dst / (double)src);
+    const double fl = std::floor(lf);
+    long len = (long)fl;
+    if (fl == lf) len--;
+    return len < 0 ? 0 : (size_t)len;
+}
+long gdg_resample_time(const double *in, size_t n, uint32_t src, uint32_t dst, double *out, size_t out_capacity)
+{
+    if (ensure_init()) return -1;
+    if ((!in && n) || !out || !src || !dst) return fail("gdg_resample_time: bad argument");
+    const size_t len = gdg_resample_time_length(n, src, dst);
+    if (out_capacity < len) return fail("gdg_resample_time: output buffer holds %zu samples, %zu needed", out_capacity, len);
+    double *d_in = (double *)gdgb_alloc(std::max<size_t>(1, n) * sizeof(double)), *d_out = (double *)gdgb_alloc(std::max<size_t>(1, len) * sizeof(double));
+    int rc = (!d_in || !d_out) ? backend_fail("allocation failed") : 0;
+    if (!rc && n && gdgb_upload(d_in, in, n * sizeof(double))) rc = backend_fail("upload failed");
+    if (!rc && gdgb_resample_time(d_in, (long)n, (double)src / (double)dst, d_out, (long)len, gdgb_stream())) rc = backend_fail("resample kernel launch failed");
+    if (!rc && gdgb_download(out, d_out, len * sizeof(double))) rc = backend_fail("download failed");
+    gdgb_sync(); gdgb_free(d_in); gdgb_free(d_out);
+    return rc ? -1 : (long)len;
+}
+
 /* ---- controller.process mirror ---- */
 int gdg_controller_process(gdg_chain *const *chains, uint32_t C, gdg_tuner *tuner, int tuner_channel, gdg_spatializer *spat,
                            const double *const *in, double *const *out, uint32_t n_out, size_t n, uint32_t rate)
@@ -1429,7 +1499,8 @@ int gdg_controller_process(gdg_chain *const *chains, uint32_t C, gdg_tuner *tune
     if (check_block(n)) return -1;
     if (n_out < C) return 0;                                /* controller.go:2682: nothing happens */
     const bool do_spat = spat && n_out >= C + 2 && spat->count == C;
-    return host_block(chains, C, tuner, tuner_channel, do_spat ? spat : nullptr, in, out, (size_t)C + (do_spat ? 2 : 0), n, rate);
+    return host_block(chains, C, tuner, tuner_channel, do_spat ? spat : nullptr, (const void *const *)in, GDG_FMT_IEEE64, (void *const *)out,
+                      GDG_FMT_IEEE64, (size_t)C + (do_spat ? 2 : 0), n, rate);
 }
 
 } /* extern "C" */

@@ -10,6 +10,77 @@
 
 #include "gdg_stages2.cuh"
 
+/* --------------------------------------------------------------------------
+ * Sample codecs of wave/wave.go (bytesToSamples / samplesToBytes, wave.go:275-732) as the load / store
+ * prologue and epilogue of the chain kernel: formats GDG_FMT_* of gdg_device.h, little-endian payload.
+ * Every step is an exactly rounded IEEE operation, so the bytes equal the reference's for equal float64 input.
+ * -------------------------------------------------------------------------- */
+GDG_DEVI int fmt_bytes(int fmt) { return fmt == GDG_FMT_PCM8 ? 1 : (fmt == GDG_FMT_PCM16 ? 2 : (fmt == GDG_FMT_PCM24 ? 3 : (fmt == GDG_FMT_IEEE64 ? 8 : 4))); }
+GDG_DEVI double decode_sample(int fmt, const unsigned char *p, int k)
+{
+    switch (fmt) {
+    case GDG_FMT_PCM8: {                                     /* wave.go:316-342 */
+        const double r = (1.0 / 127.0) * (double)((int)p[k] - 128);
+        return r < -1.0 ? -1.0 : (r > 1.0 ? 1.0 : r); }
+    case GDG_FMT_PCM16: {                                    /* wave.go:400-428 */
+        const int v = (int)(short)((unsigned)p[2 * k] | ((unsigned)p[2 * k + 1] << 8));
+        return (2.0 / 65535.0) * (double)v; }
+    case GDG_FMT_PCM24: {                                    /* wave.go:483-531 */
+        const unsigned w = (unsigned)p[3 * k] | ((unsigned)p[3 * k + 1] << 8) | ((unsigned)p[3 * k + 2] << 16);
+        int v = (int)w;
+        if (w & 0x00800000u) v = -8388608 + (v & 0x007fffff);
+        return (2.0 / 16777215.0) * (double)v; }
+    case GDG_FMT_PCM32: {                                    /* wave.go:589-617 */
+        const unsigned w = (unsigned)p[4 * k] | ((unsigned)p[4 * k + 1] << 8) | ((unsigned)p[4 * k + 2] << 16) | ((unsigned)p[4 * k + 3] << 24);
+        return (2.0 / 4294967295.0) * (double)(int)w; }
+    case GDG_FMT_IEEE32: return (double)((const float *)p)[k];           /* wave.go:662-689 */
+    default: return ((const double *)p)[k];                              /* wave.go:714-732 */
+    }
+}
+GDG_DEVI void encode_sample(int fmt, unsigned char *p, int k, double s)
+{
+    if (fmt == GDG_FMT_IEEE64) { ((double *)p)[k] = s; return; }         /* wave.go:694-709: no clamp */
+    s = s < -1.0 ? -1.0 : (s > 1.0 ? 1.0 : s);
+    switch (fmt) {
+    case GDG_FMT_PCM8: {                                     /* wave.go:275-311 */
+        const int res = (int)(short)(127.0 * s) + 128;
+        p[k] = (unsigned char)(res < 0 ? 0 : (res > 255 ? 255 : res)); break; }
+    case GDG_FMT_PCM16: {                                    /* wave.go:347-395 */
+        int t = (int)((0.5 * 65535.0) * s);
+        t = t > 32767 ? 32767 : (t < -32768 ? -32768 : t);
+        p[2 * k] = (unsigned char)(t & 0xff); p[2 * k + 1] = (unsigned char)((t >> 8) & 0xff); break; }
+    case GDG_FMT_PCM24: {                                    /* wave.go:433-478 */
+        int t = (int)((0.5 * 16777215.0) * s);
+        t = t > 8388607 ? 8388607 : (t < -8388608 ? -8388608 : t);
+        p[3 * k] = (unsigned char)(t & 0xff); p[3 * k + 1] = (unsigned char)((t >> 8) & 0xff); p[3 * k + 2] = (unsigned char)((t >> 16) & 0xff); break; }
+    case GDG_FMT_PCM32: {                                    /* wave.go:536-584 */
+        long long t = (long long)((0.5 * 4294967295.0) * s);
+        t = t > 2147483647LL ? 2147483647LL : (t < -2147483648LL ? -2147483648LL : t);
+        const unsigned u = (unsigned)(int)t;
+        p[4 * k] = (unsigned char)(u & 0xff); p[4 * k + 1] = (unsigned char)((u >> 8) & 0xff);
+        p[4 * k + 2] = (unsigned char)((u >> 16) & 0xff); p[4 * k + 3] = (unsigned char)(u >> 24); break; }
+    default: ((float *)p)[k] = (float)s; break;              /* IEEE32, wave.go:622-657 */
+    }
+}
+
+/* resample.Time (resample/resample.go:72-103): out[i] = Lanczos-3 interpolation of the input at i * src/dst */
+GDG_DEVI double resample_time_body(const double *in, long n, double dx, long i)
+{
+    const double x = (double)i * dx;
+    const long idx = (long)floor(x);
+    double sum = 0.0;
+    for (long t = idx - 2; t < idx + 4; t++)
+        if (t >= 0 && t < n) {
+            const double df = x - (double)t;
+            double kv;
+            if (df == 0.0) kv = 1.0;
+            else if (-3.0 < df && df < 3.0) { const double pix = GDG_PI * df; kv = (3.0 * (sin(pix) * sin(pix / 3.0))) / (pix * pix); }
+            else kv = 0.0;
+            sum += in[t] * kv;
+        }
+    return sum;
+}
+
 GDG_DEVI void ctx_init(gdg_ctx &cx, int n)
 {
     cx.cur_off = GDG_SMEM_R; cx.alt_off = GDG_SMEM_R + GDG_MAX_N; cx.n = n;
@@ -41,7 +112,7 @@ GDG_DEV void run_unit(gdg_ctx &cx, const gdg_unit_desc &d, const double *tw)
 }
 
 /* one channel, one block: load -> every slot -> store */
-GDG_DEV void run_chain(double *smem, const gdg_chain_desc *cd, const double *in, double *out, int n, const double *tw)
+GDG_DEV void run_chain(double *smem, const gdg_chain_desc *cd, const void *in, int in_fmt, void *out, int out_fmt, int n, const double *tw)
 {
     gdg_ctx cx;
 #if !defined(__CUDACC__) || defined(GDG_HOST_EMU)
@@ -51,7 +122,8 @@ GDG_DEV void run_chain(double *smem, const gdg_chain_desc *cd, const double *in,
 #endif
     ctx_init(cx, n);
     GDG_THREADS_BEGIN
-        for (int k = tid; k < n; k += GDG_NT) SM_CUR(cx)[sw(k)] = in[k];
+        if (in_fmt == GDG_FMT_IEEE64) { for (int k = tid; k < n; k += GDG_NT) SM_CUR(cx)[sw(k)] = ((const double *)in)[k]; }
+        else { for (int k = tid; k < n; k += GDG_NT) SM_CUR(cx)[sw(k)] = decode_sample(in_fmt, (const unsigned char *)in, k); }
         for (int k = tid; k < 1024; k += GDG_NT) { SM_TWS[2 * k] = GDG_LDG(tw + 4 * k); SM_TWS[2 * k + 1] = GDG_LDG(tw + 4 * k + 1); }   /* exp(-2 pi i k / 8192) */
     GDG_THREADS_END
     const int ns = cd->nslots;
@@ -62,7 +134,8 @@ GDG_DEV void run_chain(double *smem, const gdg_chain_desc *cd, const double *in,
         run_unit(cx, GDG_DESC, tw);
     }
     GDG_THREADS_BEGIN
-        for (int k = tid; k < n; k += GDG_NT) out[k] = SM_CUR(cx)[sw(k)];
+        if (out_fmt == GDG_FMT_IEEE64) { for (int k = tid; k < n; k += GDG_NT) ((double *)out)[k] = SM_CUR(cx)[sw(k)]; }
+        else { for (int k = tid; k < n; k += GDG_NT) encode_sample(out_fmt, (unsigned char *)out, k, SM_CUR(cx)[sw(k)]); }
     GDG_THREADS_END
 }
 

@@ -30,17 +30,23 @@ static int cu_fail(const char *what, cudaError_t e)
 
 /* ---- kernels ------------------------------------------------------------------- */
 __global__ void __launch_bounds__(GDG_NT, 1)
-k_chain(const gdg_chain_desc *const *descs, const double *in, double *out, long stride, int n, const double *tw)
+k_chain(const gdg_chain_desc *const *descs, const unsigned char *in, long in_stride, int in_fmt, unsigned char *out, long out_stride,
+        int out_fmt, int n, const double *tw)
 {
     const int c = blockIdx.x;
     const gdg_chain_desc *cd = descs[c];
-    const double *src = in + (long)c * stride;
-    double *dst = out + (long)c * stride;
-    if (cd == nullptr) {                                   /* no segment in this round: pass through */
-        if (src != dst) for (int k = threadIdx.x; k < n; k += GDG_NT) dst[k] = src[k];
+    const unsigned char *src = in + (long)c * in_stride;
+    unsigned char *dst = out + (long)c * out_stride;
+    if (cd == nullptr) {                                   /* no segment in this round: pass through (float64 rounds only) */
+        if (src != dst) for (int k = threadIdx.x; k < n; k += GDG_NT) ((double *)dst)[k] = ((const double *)src)[k];
         return;
     }
-    run_chain(gdg_smem, cd, src, dst, n, tw);
+    run_chain(gdg_smem, cd, src, in_fmt, dst, out_fmt, n, tw);
+}
+__global__ void k_resample_time(const double *in, long n, double dx, double *out, long out_len)
+{
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < out_len) out[i] = resample_time_body(in, n, dx, i);
 }
 
 __global__ void k_spat(const gdg_spat_channel *ch, int C, const double *in, long stride, const double *hist, int hs,
@@ -174,12 +180,22 @@ int gdgb_set_tables(const double *aa2, const double *aa4, const double *lz2, con
     return 0;
 }
 
-int gdgb_launch_chains(const gdg_chain_desc *const *d_descs, int channels, const double *d_in, double *d_out,
-                       long stride, int n, void *stream)
+int gdgb_launch_chains(const gdg_chain_desc *const *d_descs, int channels, const void *d_in, long in_stride_bytes, int in_fmt,
+                       void *d_out, long out_stride_bytes, int out_fmt, int n, void *stream)
 {
-    k_chain<<<channels, GDG_NT, GDG_SMEM_BYTES, (cudaStream_t)stream>>>(d_descs, d_in, d_out, stride, n, g_d_tw);
+    k_chain<<<channels, GDG_NT, GDG_SMEM_BYTES, (cudaStream_t)stream>>>(d_descs, (const unsigned char *)d_in, in_stride_bytes, in_fmt,
+                                                                      (unsigned char *)d_out, out_stride_bytes, out_fmt, n, g_d_tw);
     g_launches++;
     CU(cudaGetLastError());
+    return 0;
+}
+int gdgb_resample_time(const double *d_in, long n, double dx, double *d_out, long out_len, void *stream)
+{
+    if (out_len > 0) {
+        k_resample_time<<<(unsigned)((out_len + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_in, n, dx, d_out, out_len);
+        g_launches++;
+        CU(cudaGetLastError());
+    }
     return 0;
 }
 

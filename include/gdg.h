@@ -122,6 +122,23 @@ int gdg_process_batch(gdg_chain *const *chains, size_t channels, const double *c
 int gdg_process_batch_device(gdg_chain *const *chains, size_t channels, const double *d_in, double *d_out,
                              size_t stride, size_t n, uint32_t sample_rate, void *stream);
 
+/* ---- "next" rows of the path: the steps either side of the block loop ----------------
+ * Sample formats == the (format, bit depth) pairs of wave.samplesToBytes / bytesToSamples (wave/wave.go:737-838). */
+enum { GDG_FORMAT_PCM8 = 0, GDG_FORMAT_PCM16, GDG_FORMAT_PCM24, GDG_FORMAT_PCM32, GDG_FORMAT_IEEE32, GDG_FORMAT_IEEE64 };
+size_t gdg_format_bytes_per_sample(int format);
+/* gdg_process_batch with the sample codecs of wave/wave.go:275-732 fused into the kernel's load and store: row c of `in`
+ * holds n little-endian samples of in_format (the data-chunk payload of one channel), row c of `out` receives n samples of
+ * out_format.  Replaces wave.Channel.Floats() -> process -> Channel.WriteFloats()/File.Bytes() of the batch path
+ * (controller/controller.go:2908-3143) for one block; chains of at most one fused segment (24 active units). */
+int gdg_process_batch_encoded(gdg_chain *const *chains, size_t channels, const void *const *in, int in_format,
+                              void *const *out, int out_format, size_t n, uint32_t sample_rate);
+int gdg_process_batch_device_encoded(gdg_chain *const *chains, size_t channels, const void *d_in, int in_format, size_t in_stride_bytes,
+                                     void *d_out, int out_format, size_t out_stride_bytes, size_t n, uint32_t sample_rate, void *stream);
+/* resample.Time (resample/resample.go:72-103): the batch path's input rate conversion (controller.go:2991-3003).
+ * Returns the number of samples written (== gdg_resample_time_length) or -1. */
+size_t gdg_resample_time_length(size_t n, uint32_t source_rate, uint32_t target_rate);
+long gdg_resample_time(const double *in, size_t n, uint32_t source_rate, uint32_t target_rate, double *out, size_t out_capacity);
+
 /* ---- spatializer.Spatializer  spatializer/spatializer.go ---------------------------- */
 gdg_spatializer *gdg_spatializer_create(uint32_t input_channels);          /* Create           :436-469 */
 void gdg_spatializer_destroy(gdg_spatializer *s);

@@ -62,9 +62,14 @@ void orc_circular_enqueue(orc_circular *c, const double *elems, size_t n);
 size_t orc_circular_length(const orc_circular *c);
 int orc_circular_retrieve(const orc_circular *c, double *buf, size_t n);
 
-/* ---- wave/wave.go (PCM16 codec only) ------------------------------------- */
+/* ---- wave/wave.go sample codecs --------------------------------------------- */
 void orc_wave_pcm16_decode(const int16_t *pcm, size_t n, double *out);  /* wave.go:400-428 */
 void orc_wave_pcm16_encode(const double *samples, size_t n, int16_t *out); /* wave.go:347-379 */
+/* formats: bytesToSamples / samplesToBytes (wave.go:737-838): little-endian payload bytes */
+enum { ORC_FMT_PCM8 = 0, ORC_FMT_PCM16, ORC_FMT_PCM24, ORC_FMT_PCM32, ORC_FMT_IEEE32, ORC_FMT_IEEE64 };
+size_t orc_wave_bytes_per_sample(int fmt);
+int orc_wave_decode(int fmt, const unsigned char *data, size_t n_samples, double *out);   /* wave.go:316-342,400-428,483-531,589-617,662-689,714-732 */
+int orc_wave_encode(int fmt, const double *samples, size_t n_samples, unsigned char *out); /* wave.go:275-311,347-395,433-478,536-584,622-657,694-709 */
 
 /* ---- filter/filter.go ---------------------------------------------------- */
 typedef struct orc_filter orc_filter;

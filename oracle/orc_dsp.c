@@ -372,6 +372,101 @@ void orc_wave_pcm16_encode(const double *samples, size_t n, int16_t *out)
     }
 }
 
+/* all six sample formats of wave.go, on the data-chunk payload (little endian) */
+size_t orc_wave_bytes_per_sample(int fmt)
+{
+    static const size_t b[6] = {1, 2, 3, 4, 4, 8};
+    return (fmt >= 0 && fmt < 6) ? b[fmt] : 0;
+}
+int orc_wave_decode(int fmt, const unsigned char *d, size_t n, double *out)
+{
+    switch (fmt) {
+    case ORC_FMT_PCM8: {                                     /* wave.go:316-342 */
+        const double scale = 1.0 / 127.0;
+        for (size_t i = 0; i < n; i++) {
+            const int16_t temp = (int16_t)((int16_t)d[i] + (-128));
+            const double r = scale * (double)temp;
+            out[i] = r < -1.0 ? -1.0 : (r > 1.0 ? 1.0 : r);
+        }
+        return 0; }
+    case ORC_FMT_PCM16: {                                    /* wave.go:400-428 */
+        const double scaling = 2.0 / (32767.0 - (-32768.0));
+        for (size_t i = 0; i < n; i++) { const int16_t v = (int16_t)((uint16_t)d[2 * i] | ((uint16_t)d[2 * i + 1] << 8)); out[i] = scaling * (double)v; }
+        return 0; }
+    case ORC_FMT_PCM24: {                                    /* wave.go:483-531 */
+        const double scaling = 2.0 / (8388607.0 - (-8388608.0));
+        for (size_t i = 0; i < n; i++) {
+            const uint32_t w = (uint32_t)d[3 * i] | ((uint32_t)d[3 * i + 1] << 8) | ((uint32_t)d[3 * i + 2] << 16);
+            int32_t v = (int32_t)w;
+            if (w & 0x00800000u) v = -8388608 + (v & 0x007fffff);
+            out[i] = scaling * (double)v;
+        }
+        return 0; }
+    case ORC_FMT_PCM32: {                                    /* wave.go:589-617 */
+        const double scaling = 2.0 / (2147483647.0 - (-2147483648.0));
+        for (size_t i = 0; i < n; i++) {
+            const uint32_t w = (uint32_t)d[4 * i] | ((uint32_t)d[4 * i + 1] << 8) | ((uint32_t)d[4 * i + 2] << 16) | ((uint32_t)d[4 * i + 3] << 24);
+            out[i] = scaling * (double)(int32_t)w;
+        }
+        return 0; }
+    case ORC_FMT_IEEE32:                                     /* wave.go:662-689 */
+        for (size_t i = 0; i < n; i++) { float f; memcpy(&f, d + 4 * i, 4); out[i] = (double)f; }
+        return 0;
+    case ORC_FMT_IEEE64:                                     /* wave.go:714-732 */
+        memcpy(out, d, 8 * n);
+        return 0;
+    }
+    return -1;
+}
+static double wave_clamp(double s) { return s < -1.0 ? -1.0 : (s > 1.0 ? 1.0 : s); }
+int orc_wave_encode(int fmt, const double *x, size_t n, unsigned char *o)
+{
+    switch (fmt) {
+    case ORC_FMT_PCM8:                                       /* wave.go:275-311 */
+        for (size_t i = 0; i < n; i++) {
+            const int16_t temp = (int16_t)(127.0 * wave_clamp(x[i]));
+            const int res = (int)temp - (-128);
+            o[i] = res < 0 ? 0 : (res > 255 ? 255 : (unsigned char)res);
+        }
+        return 0;
+    case ORC_FMT_PCM16: {                                    /* wave.go:347-395 */
+        const double scale = 0.5 * 65535.0;
+        for (size_t i = 0; i < n; i++) {
+            int32_t t = (int32_t)(scale * wave_clamp(x[i]));
+            if (t > 32767) t = 32767; else if (t < -32768) t = -32768;
+            const uint16_t u = (uint16_t)(int16_t)t;
+            o[2 * i] = (unsigned char)(u & 0xff); o[2 * i + 1] = (unsigned char)(u >> 8);
+        }
+        return 0; }
+    case ORC_FMT_PCM24: {                                    /* wave.go:433-478 */
+        const double scale = 0.5 * 16777215.0;
+        for (size_t i = 0; i < n; i++) {
+            int32_t t = (int32_t)(scale * wave_clamp(x[i]));
+            if (t > 8388607) t = 8388607; else if (t < -8388608) t = -8388608;
+            const uint32_t u = (uint32_t)t;
+            o[3 * i] = (unsigned char)(u & 0xff); o[3 * i + 1] = (unsigned char)((u >> 8) & 0xff); o[3 * i + 2] = (unsigned char)((u >> 16) & 0xff);
+        }
+        return 0; }
+    case ORC_FMT_PCM32: {                                    /* wave.go:536-584 */
+        const double scale = 0.5 * 4294967295.0;
+        for (size_t i = 0; i < n; i++) {
+            int64_t t = (int64_t)(scale * wave_clamp(x[i]));
+            if (t > 2147483647LL) t = 2147483647LL; else if (t < -2147483648LL) t = -2147483648LL;
+            const uint32_t u = (uint32_t)(int32_t)t;
+            o[4 * i] = (unsigned char)(u & 0xff); o[4 * i + 1] = (unsigned char)((u >> 8) & 0xff);
+            o[4 * i + 2] = (unsigned char)((u >> 16) & 0xff); o[4 * i + 3] = (unsigned char)(u >> 24);
+        }
+        return 0; }
+    case ORC_FMT_IEEE32:                                     /* wave.go:622-657 */
+        for (size_t i = 0; i < n; i++) { const float f = (float)wave_clamp(x[i]); memcpy(o + 4 * i, &f, 4); }
+        return 0;
+    case ORC_FMT_IEEE64:                                     /* wave.go:694-709: no clamp */
+        memcpy(o, x, 8 * n);
+        return 0;
+    }
+    return -1;
+}
+
 /* ======================================================================== */
 /* filter/filter.go                                                          */
 /* ======================================================================== */

@@ -53,6 +53,9 @@ def lib():
             "orc_circular_retrieve": (C.c_int, [vp, vp, sz]),
             "orc_wave_pcm16_decode": (None, [vp, sz, vp]),
             "orc_wave_pcm16_encode": (None, [vp, sz, vp]),
+            "orc_wave_bytes_per_sample": (sz, [C.c_int]),
+            "orc_wave_decode": (C.c_int, [C.c_int, vp, sz, vp]),
+            "orc_wave_encode": (C.c_int, [C.c_int, vp, sz, vp]),
             "orc_filter_from_coefficients": (vp, [vp, sz, u32]),
             "orc_filter_destroy": (None, [vp]),
             "orc_filter_length": (sz, [vp]),
@@ -242,6 +245,32 @@ def pcm16_encode(x):
     x = _f64(x)
     out = np.zeros(len(x), dtype=np.int16)
     lib().orc_wave_pcm16_encode(_p(x), len(x), _p(out))
+    return out
+
+
+WAVE_FORMATS = ["PCM8", "PCM16", "PCM24", "PCM32", "IEEE32", "IEEE64"]      # wave.go:737-838
+
+
+def wave_bytes_per_sample(fmt):
+    return lib().orc_wave_bytes_per_sample(WAVE_FORMATS.index(fmt) if isinstance(fmt, str) else fmt)
+
+
+def wave_decode(fmt, data):
+    f = WAVE_FORMATS.index(fmt) if isinstance(fmt, str) else fmt
+    d = np.ascontiguousarray(np.frombuffer(bytes(data), dtype=np.uint8))
+    n = len(d) // wave_bytes_per_sample(f)
+    out = np.zeros(n)
+    if lib().orc_wave_decode(f, _p(d), n, _p(out)):
+        raise OracleError("unknown sample format")
+    return out
+
+
+def wave_encode(fmt, x):
+    f = WAVE_FORMATS.index(fmt) if isinstance(fmt, str) else fmt
+    x = _f64(x)
+    out = np.zeros(len(x) * wave_bytes_per_sample(f), dtype=np.uint8)
+    if lib().orc_wave_encode(f, _p(x), len(x), _p(out)):
+        raise OracleError("unknown sample format")
     return out
 
 

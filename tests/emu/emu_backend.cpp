@@ -61,15 +61,22 @@ int gdgb_set_tables(const double *aa2, const double *aa4, const double *lz2, con
     return 0;
 }
 
-int gdgb_launch_chains(const gdg_chain_desc *const *descs, int channels, const double *in, double *out, long stride, int n, void *)
+int gdgb_launch_chains(const gdg_chain_desc *const *descs, int channels, const void *in, long in_stride, int in_fmt,
+                       void *out, long out_stride, int out_fmt, int n, void *)
 {
     std::vector<double> smem(GDG_SMEM_DOUBLES);
     for (int c = 0; c < channels; c++) {
-        const double *src = in + (long)c * stride;
-        double *dst = out + (long)c * stride;
+        const unsigned char *src = (const unsigned char *)in + (long)c * in_stride;
+        unsigned char *dst = (unsigned char *)out + (long)c * out_stride;
         if (!descs[c]) { if (src != dst) memcpy(dst, src, sizeof(double) * n); continue; }
-        run_chain(smem.data(), descs[c], src, dst, n, g_tw.data());
+        run_chain(smem.data(), descs[c], src, in_fmt, dst, out_fmt, n, g_tw.data());
     }
+    g_launches++;
+    return 0;
+}
+int gdgb_resample_time(const double *in, long n, double dx, double *out, long out_len, void *)
+{
+    for (long i = 0; i < out_len; i++) out[i] = resample_time_body(in, n, dx, i);
     g_launches++;
     return 0;
 }

@@ -11,6 +11,9 @@ What it reads (and nothing else):
     functions of the reference's ``*_test.go`` files -> ``reference_goldens.json``
       fft/fft_test.go, oversampling/oversampling_test.go, resample/resample_test.go,
       random/random_test.go, circular/circular_test.go
+  * wave/wave_test.go: per sample format the export vector (samples -> expected WAV bytes; only the data chunk
+    payload is kept) and the import vector (WAV bytes -> expected samples, with the test's tolerance)
+    -> ``wave_goldens.json``
   * the 24 impulse-response WAVs named by ``ir/index.json`` (16-bit PCM mono,
     96 kHz) -> ``ir_bank.npz`` holding the raw int16 frames + names + dB
     compensation (data fixtures for power-amp parity, SURVEY.md §2 "ir/")
@@ -125,6 +128,33 @@ def main():
         print(rel, {fn: list(v) for fn, v in goldens[rel].items()})
     with open(os.path.join(HERE, "reference_goldens.json"), "w") as f:
         json.dump(goldens, f, indent=0)
+
+    # --- wave codec vectors (wave/wave_test.go) ---
+    wsrc = strip_comments(open(os.path.join(REF, "wave/wave_test.go")).read())
+    wf = split_functions(wsrc)
+    wave = {}
+    for fmt in ["PCM8", "PCM16", "PCM24", "PCM32", "IEEE32", "IEEE64"]:
+        exp, imp = wf["TestExport%sMono" % fmt], wf["TestImport%sMono" % fmt]
+        tobytes = lambda body, name: [int(x, 16) for x in re.findall(r"0x[0-9a-fA-F]{2}", re.search(name + r" := \[\]byte\{(.*?)\}", body, re.S).group(1))]
+        samples = extract_literals(exp)["samples"]
+        out = tobytes(exp, "expectedOutput")
+        buf = tobytes(imp, "buf")
+        expected = extract_literals(imp)["expectedSamples"]
+        tol = float(re.search(r"areSlicesClose\(samples, expectedSamples, ([0-9.e+-]+)\)", imp).group(1))
+
+        def payload(b):
+            pos = 12
+            while pos + 8 <= len(b):
+                cid, size = bytes(b[pos:pos + 4]), struct.unpack("<I", bytes(b[pos + 4:pos + 8]))[0]
+                if cid == b"data":
+                    return b[pos + 8:pos + 8 + size]
+                pos += 8 + size + (size & 1)
+            raise ValueError("no data chunk")
+        wave[fmt] = {"export_samples": samples, "export_data": payload(out), "import_data": payload(buf),
+                     "import_samples": expected, "import_tolerance": tol}
+        print("wave", fmt, len(samples), len(wave[fmt]["export_data"]), tol)
+    with open(os.path.join(HERE, "wave_goldens.json"), "w") as f:
+        json.dump(wave, f)
 
     # --- impulse-response bank (data fixtures) ---
     index = json.load(open(os.path.join(REF, "ir/index.json")))
