@@ -308,6 +308,31 @@ def main():
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     e2e_value = samples_per_step * args.steps / float(dt.item()) / 1e6
 
+    # ---- extra (not the headline): the same chains fed with PCM16 payloads, codecs fused into the kernel ----
+    extras = {}
+    try:
+        p_in = torch.empty((C, N), dtype=torch.int16).pin_memory()
+        p_out = torch.empty((C, N), dtype=torch.int16).pin_memory()
+        p_in.copy_((ring_in[0] * 32767.0).clamp(-32768, 32767).to(torch.int16))
+        pi = (Ct.c_void_p * C)(*[p_in.data_ptr() + 2 * N * c for c in range(C)])
+        po = (Ct.c_void_p * C)(*[p_out.data_ptr() + 2 * N * c for c in range(C)])
+        for _ in range(2):
+            if lib.gdg_process_batch_encoded(handles, C, pi, 1, po, 1, N, FS) < 0:
+                raise RuntimeError(lib.gdg_last_error().decode())
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            lib.gdg_process_batch_encoded(handles, C, pi, 1, po, 1, N, FS)
+        barrier()
+        dtp = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dtp, op=dist.ReduceOp.MAX)
+        extras["e2e_pcm16_payload"] = {"value": samples_per_step * args.steps / float(dtp.item()) / 1e6, "unit": "Msamples/s",
+                                       "api": "gdg_process_batch_encoded (PCM16 in / PCM16 out, chains only: no tuner / spatializer)",
+                                       "h2d_bytes_per_step": 2 * C * N, "d2h_bytes_per_step": 2 * C * N}
+    except Exception as e:                                        # never let an extra break the contract line
+        extras["e2e_pcm16_payload"] = {"error": str(e)}
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
@@ -333,7 +358,7 @@ def main():
                          "note": "FP64-pipe-bound by construction (~136 FLOP/B, SURVEY.md 8d); see fp64",
                          "fp64": {"achieved_tflops": tfl, "peak_tflops": FP64_PEAK_TFLOPS, "frac": tfl / FP64_PEAK_TFLOPS,
                                   "flop_per_sample": ALGO_FLOP_PER_SAMPLE, "peak_kind": "measured (tools/fp64_peak.cu)"}},
-            "cpu_baseline": cpu_baseline}))
+            "cpu_baseline": cpu_baseline, "extras": extras}))
     if world > 1:
         dist.destroy_process_group()
 
