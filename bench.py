@@ -13,10 +13,12 @@ A step = one audio block of every channel through tuner feed -> chains ->
 spatializer (-> NCCL reduce of the [2][8192] master when N > 1).
   value : Msamples/s with the inputs resident in HBM (a ring of distinct blocks larger
           than L2), CUDA events on the launching stream, max over ranks.
-  e2e   : the same through host buffers (pinned), H2D of the block and D2H of every
-          channel's output + master inside the timed region.  At N=1 this is the single
-          C-ABI call gdg_controller_process(); at N>1 the same steps are issued
-          separately so that the NCCL reduce can sit between spatializer and D2H.
+  e2e   : the same through host buffers (pinned), H2D of every block and D2H of every
+          channel's output + master inside the timed region, through the C-ABI pair
+          gdg_controller_submit() / gdg_controller_wait() with two blocks in flight (the
+          batch loop's natural double buffering); e2e.synchronous_call is the blocking
+          one-call-per-block gdg_controller_process().  At N>1 the NCCL reduce of the
+          stereo master follows each block's wait.
   roofline : the fused chain kernel (k_chain) against the measured HBM copy bandwidth
           (16 algorithmic bytes per sample) - and, because this path is FP64-pipe-bound
           by construction, against the measured FP64 FMA rate as well.
@@ -281,32 +283,55 @@ def main():
     ptrs_out = [(Ct.c_void_p * (C + 2))(*[h_out[k].data_ptr() + 8 * N * c for c in range(C + 2)]) for k in range(2)]
     d_master = torch.empty((2, N), device=dev, dtype=torch.float64)
 
-    def step_e2e(k):
-        # one C-ABI call on HOST buffers: H2D, tuner feed, chains, spatializer (this rank's partial master), D2H - pipelined inside
-        rc = lib.gdg_controller_process(handles, C, tuner._h if tuner is not None else None, 0 if tuner is not None else -1,
-                                        spat._h, ptrs_in[k % 2], ptrs_out[k % 2], C + 2, N, FS)
-        if rc < 0:
-            raise RuntimeError(lib.gdg_last_error().decode())
-        if world > 1:                                            # the one exchange step: sum the partial masters onto rank 0
+    tun_h, tun_ch = (tuner._h if tuner is not None else None), (0 if tuner is not None else -1)
+
+    def finish_block(k):                                         # the one exchange step: sum the partial masters onto rank 0
+        if world > 1:
             d_master.copy_(h_out[k % 2][C:], non_blocking=True)
             dist.reduce(d_master, dst=0, op=dist.ReduceOp.SUM)
             if rank == 0:
                 h_out[k % 2][C:].copy_(d_master, non_blocking=True)
             stream.synchronize()
-    e2e_api = "gdg_controller_process (host buffers, one C-ABI call per block)" + (" + NCCL reduce of the [2][8192] master" if world > 1 else "")
-    barrier()
-    t0 = time.perf_counter()
-    for k in range(max(1, args.warmup // 2)):
-        step_e2e(k)
-    barrier()
-    t0 = time.perf_counter()
-    for k in range(args.steps):
-        step_e2e(k)
-    barrier()
-    dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-    e2e_value = samples_per_step * args.steps / float(dt.item()) / 1e6
+
+    def step_sync(k):
+        # one C-ABI call on HOST buffers: H2D, tuner feed, chains, spatializer (this rank's partial master), D2H - pipelined inside
+        rc = lib.gdg_controller_process(handles, C, tun_h, tun_ch, spat._h, ptrs_in[k % 2], ptrs_out[k % 2], C + 2, N, FS)
+        if rc < 0:
+            raise RuntimeError(lib.gdg_last_error().decode())
+        finish_block(k)
+
+    def run_pipelined(steps):
+        # the batch loop of controller.go:2991-3106 with two blocks in flight: block k+1 is submitted (its H2D starts) before
+        # block k is waited for (its D2H finishes); every block's inputs go up and every block's outputs come back in the loop
+        prev = None
+        for k in range(steps):
+            t = lib.gdg_controller_submit(handles, C, tun_h, tun_ch, spat._h, None, ptrs_in[k % 2], ptrs_out[k % 2], C + 2, N, FS)
+            if t < 0:
+                raise RuntimeError(lib.gdg_last_error().decode())
+            if prev is not None:
+                if lib.gdg_controller_wait(prev[0]) < 0:
+                    raise RuntimeError(lib.gdg_last_error().decode())
+                finish_block(prev[1])
+            prev = (t, k)
+        if lib.gdg_controller_wait(prev[0]) < 0:
+            raise RuntimeError(lib.gdg_last_error().decode())
+        finish_block(prev[1])
+
+    def wall(fn):
+        barrier()
+        t0 = time.perf_counter()
+        fn()
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        return float(dt.item())
+    e2e_api = ("gdg_controller_submit / gdg_controller_wait on pinned host buffers: one submit per block, two blocks in flight"
+               + (" + NCCL reduce of the [2][8192] master" if world > 1 else ""))
+    wall(lambda: [step_sync(k) for k in range(max(1, args.warmup // 2))])
+    e2e_sync = samples_per_step * args.steps / wall(lambda: [step_sync(k) for k in range(args.steps)]) / 1e6
+    run_pipelined(2)
+    e2e_value = samples_per_step * args.steps / wall(lambda: run_pipelined(args.steps)) / 1e6
 
     # ---- extra (not the headline): the same chains fed with PCM16 payloads, codecs fused into the kernel ----
     extras = {}
@@ -333,6 +358,31 @@ def main():
     except Exception as e:                                        # never let an extra break the contract line
         extras["e2e_pcm16_payload"] = {"error": str(e)}
 
+    # ---- extra: the headline e2e call with the level meter of controller.go:2653-2781 fed on the device ----
+    try:
+        meter = gdg.Meter(2 * C + 3, lib=lib)
+        meter.set_enabled(True)
+
+        def step_metered(k):
+            if lib.gdg_controller_process_metered(handles, C, tuner._h if tuner is not None else None, 0 if tuner is not None else -1,
+                                                  spat._h, meter._h, ptrs_in[k % 2], ptrs_out[k % 2], C + 2, N, FS) < 0:
+                raise RuntimeError(lib.gdg_last_error().decode())
+        for k in range(2):
+            step_metered(k)
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(args.steps):
+            step_metered(k)
+        barrier()
+        dtm = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dtm, op=dist.ReduceOp.MAX)
+        extras["e2e_with_level_meter"] = {"value": samples_per_step * args.steps / float(dtm.item()) / 1e6, "unit": "Msamples/s",
+                                          "api": "gdg_controller_process_metered (%d meter channels: inputs, outputs, master)" % (2 * C + 3),
+                                          "input_0_level_peak_db": list(meter.analyze(0)), "master_left_level_peak_db": list(meter.analyze(2 * C + 1))}
+    except Exception as e:
+        extras["e2e_with_level_meter"] = {"error": str(e)}
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
@@ -349,7 +399,8 @@ def main():
                        "cache": "inputs larger than L2: ring of %d distinct in/out block sets (%.0f MB) cycled" % (RING_BLOCKS, RING_BLOCKS * (2 * C + 2) * N * 8 / 1e6),
                        "parallelism": "channels sharded %d-way, NCCL reduce of the stereo master" % world},
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": C * N * 8, "d2h_bytes_per_step": (C + 2) * N * 8, "api": e2e_api},
+            "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": C * N * 8, "d2h_bytes_per_step": (C + 2) * N * 8, "api": e2e_api,
+                    "synchronous_call": {"value": e2e_sync, "unit": "Msamples/s", "api": "gdg_controller_process (one blocking C-ABI call per block)"}},
             "gpu_launches": int(round(launches_per_step * args.steps)), "gpu_launches_per_step": launches_per_step,
             "roofline": {"kernel": "k_chain (fused 12-unit segment, one CTA per channel)", "bound": "hbm", "achieved": achieved,
                          "peak": hbm_peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": kchain_traffic() if C == 1024 else None,

@@ -113,7 +113,20 @@ ABI = {
     "gdg_tuner_process": (_int, [_vp, _vp, _sz, _u32]),
     "gdg_tuner_process_device": (_int, [_vp, _vp, _sz, _u32, _vp]),
     "gdg_tuner_analyze": (_int, [_vp, C.POINTER(_TunerResult)]),
+    "gdg_meter_create": (_vp, [_u32, _vp]),
+    "gdg_meter_destroy": (None, [_vp]),
+    "gdg_meter_channel_count": (_u32, [_vp]),
+    "gdg_meter_channel_name": (_cp, [_vp, _u32]),
+    "gdg_meter_enabled": (_int, [_vp]),
+    "gdg_meter_set_enabled": (_int, [_vp, _int]),
+    "gdg_meter_process": (_int, [_vp, _vp, _u32, _sz, _u32]),
+    "gdg_meter_process_device": (_int, [_vp, _u32, _vp, _sz, _u32, _sz, _u32, _vp]),
+    "gdg_meter_analyze": (_int, [_vp, _u32, C.POINTER(_i32), C.POINTER(_i32)]),
+    "gdg_meter_state": (_int, [_vp, _u32, C.POINTER(_dbl), C.POINTER(_dbl), C.POINTER(C.c_uint64)]),
     "gdg_controller_process": (_int, [_vp, _u32, _vp, _int, _vp, _vp, _vp, _u32, _sz, _u32]),
+    "gdg_controller_process_metered": (_int, [_vp, _u32, _vp, _int, _vp, _vp, _vp, _vp, _u32, _sz, _u32]),
+    "gdg_controller_submit": (_int, [_vp, _u32, _vp, _int, _vp, _vp, _vp, _vp, _u32, _sz, _u32]),
+    "gdg_controller_wait": (_int, [_int]),
 }
 
 _LIBS = {}
@@ -437,7 +450,66 @@ class Tuner(_Base):
         return {"cents": r.cents, "frequency": r.frequency, "note": r.note.decode()}
 
 
-def controller_process(chains, tuner, tuner_channel, spat, inputs, sample_rate):
+class Meter(_Base):
+    """level.Meter (level/level.go:57-65)."""
+
+    def __init__(self, channels, names=None, lib=None):
+        super().__init__(lib)
+        if names is not None and len(names) != channels:     # level.go:325-326
+            raise GdgError("Failed to create channel meter. Requested channel meter for %d channels, but provided %d channel names."
+                           % (channels, len(names)))
+        arr = None
+        if names is not None:
+            self._names = [nm.encode() for nm in names]
+            arr = (C.c_char_p * max(channels, 1))(*self._names)
+        self._h = self._lib.gdg_meter_create(channels, arr)
+        if not self._h:
+            raise self._err()
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._lib.gdg_meter_destroy(self._h)
+
+    def channel_count(self):
+        return self._lib.gdg_meter_channel_count(self._h)
+
+    def channel_name(self, channel):
+        r = self._lib.gdg_meter_channel_name(self._h, channel)
+        if r is None:
+            raise self._err()
+        return r.decode()
+
+    def enabled(self):
+        return bool(self._lib.gdg_meter_enabled(self._h))
+
+    def set_enabled(self, value):
+        self._check(self._lib.gdg_meter_set_enabled(self._h, 1 if value else 0))
+
+    def process(self, buffers, sample_rate):
+        """buffers: one equally long array (or None) per channel."""
+        rows = [None if b is None else _f64(b) for b in buffers]
+        k = len(rows)
+        n = max([len(r) for r in rows if r is not None], default=0)
+        if any(r is not None and len(r) != n for r in rows):
+            raise GdgError("gdg_meter_process: buffers of one call must have the same length")
+        bp = (C.c_void_p * max(k, 1))(*[None if r is None else r.ctypes.data for r in rows])
+        self._check(self._lib.gdg_meter_process(self._h, bp, k, n, sample_rate))
+
+    def process_device(self, first_channel, d_rows_ptr, stride, rows, n, sample_rate, stream=None):
+        self._check(self._lib.gdg_meter_process_device(self._h, first_channel, d_rows_ptr, stride, rows, n, sample_rate, stream))
+
+    def analyze(self, channel):
+        lv, pk = _i32(), _i32()
+        self._check(self._lib.gdg_meter_analyze(self._h, channel, C.byref(lv), C.byref(pk)))
+        return lv.value, pk.value
+
+    def state(self, channel):
+        c, p, q = _dbl(), _dbl(), C.c_uint64()
+        self._check(self._lib.gdg_meter_state(self._h, channel, C.byref(c), C.byref(p), C.byref(q)))
+        return c.value, p.value, q.value
+
+
+def controller_process(chains, tuner, tuner_channel, spat, inputs, sample_rate, meter=None):
     """controller.process (controller.go:2648-2783) with host buffers: returns out[C (+2)][n]."""
     lib = chains[0]._lib
     x = _f64(inputs)
@@ -446,8 +518,31 @@ def controller_process(chains, tuner, tuner_channel, spat, inputs, sample_rate):
     out = np.zeros((n_out, n))
     ip = (C.c_void_p * c)(*[x[i].ctypes.data for i in range(c)])
     op = (C.c_void_p * n_out)(*[out[i].ctypes.data for i in range(n_out)])
-    rc = lib.gdg_controller_process(_handles(chains), c, tuner._h if tuner else None, tuner_channel,
-                                    spat._h if spat else None, ip, op, n_out, n, sample_rate)
+    rc = lib.gdg_controller_process_metered(_handles(chains), c, tuner._h if tuner else None, tuner_channel,
+                                            spat._h if spat else None, meter._h if meter else None, ip, op, n_out, n, sample_rate)
     if rc < 0:
         raise GdgError(lib.gdg_last_error().decode())
     return out
+
+
+def controller_submit(chains, tuner, tuner_channel, spat, inputs, outputs, sample_rate, meter=None):
+    """gdg_controller_submit: enqueue one block without waiting.  `inputs` [C][n] and `outputs` [C (+2)][n] are caller-owned
+    C-contiguous float64 arrays that must stay alive (inputs untouched) until controller_wait(ticket).  Returns the ticket."""
+    lib = chains[0]._lib
+    if inputs.dtype != np.float64 or outputs.dtype != np.float64 or not inputs.flags.c_contiguous or not outputs.flags.c_contiguous:
+        raise GdgError("controller_submit needs C-contiguous float64 arrays")
+    c, n = inputs.shape
+    n_out = outputs.shape[0]
+    ip = (C.c_void_p * c)(*[inputs[i].ctypes.data for i in range(c)])
+    op = (C.c_void_p * n_out)(*[outputs[i].ctypes.data for i in range(n_out)])
+    t = lib.gdg_controller_submit(_handles(chains), c, tuner._h if tuner else None, tuner_channel, spat._h if spat else None,
+                                  meter._h if meter else None, ip, op, n_out, n, sample_rate)
+    if t < 0:
+        raise GdgError(lib.gdg_last_error().decode())
+    return t
+
+
+def controller_wait(ticket, lib=None):
+    lib = lib if lib is not None else load()
+    if lib.gdg_controller_wait(ticket) < 0:
+        raise GdgError(lib.gdg_last_error().decode())

@@ -37,6 +37,7 @@ int gdgb_d2h_async(void *dst, const void *src, size_t bytes, int stream);
 int gdgb_record(int event, int stream);
 int gdgb_wait(int stream, int event);
 int gdgb_sync_stream(int stream);
+int gdgb_sync_event(int event);                 /* host waits for the last record of `event` */
 void *gdgb_pinned_alloc(size_t bytes);
 void gdgb_pinned_free(void *p);
 int gdgb_is_pinned(const void *p);
@@ -49,6 +50,9 @@ int gdgb_set_tables(const double *aa2, const double *aa4, const double *lz2, con
  * on in + c*in_stride_bytes -> out + c*out_stride_bytes; samples are decoded / encoded per GDG_FMT_* */
 int gdgb_launch_chains(const gdg_chain_desc *const *d_descs, int channels, const void *d_in, long in_stride_bytes, int in_fmt,
                        void *d_out, long out_stride_bytes, int out_fmt, int n, void *stream);
+/* level meter (level/level.go:147-208): row c = d_in + c*stride (n samples) updates the 4-word state d_state + 4*c
+ * {cur, peak, counter (int64), unused}; f = decay factor per sample, hold = peak hold time in samples */
+int gdgb_launch_meter(const double *d_in, long stride, int channels, long n, double f, long long hold, double *d_state, void *stream);
 /* resample.Time on device: d_out[i], i < out_len */
 int gdgb_resample_time(const double *d_in, long n, double dx, double *d_out, long out_len, void *stream);
 

@@ -18,11 +18,19 @@
 #ifndef GDG_NT
 #define GDG_NT 512              /* threads per CTA                                   */
 #endif
-#define GDG_MAX_N 8192          /* max block length (controller.go:36 BLOCK_SIZE)    */
-#define GDG_MAX_FFT 16384       /* max real FFT size held in shared memory (2*MAX_N) */
+#ifndef GDG_LOG_MAX_N
+#define GDG_LOG_MAX_N 13
+#endif
+#define GDG_MAX_N (1 << GDG_LOG_MAX_N)   /* max block length per CTA pass: 8192 (controller.go:36 BLOCK_SIZE) */
+#define GDG_MAX_FFT (2 * GDG_MAX_N)      /* max real FFT size held in shared memory            */
+#ifndef GDG_MIN_CTAS
+#define GDG_MIN_CTAS 1          /* resident CTAs per SM the chain kernel is compiled for */
+#endif
 #define GDG_MAX_SLOTS 24        /* non-bypassed units per fused segment              */
 #define GDG_SCAN_LANES 4        /* independent recurrences scanned together          */
-#define GDG_OS_TILE 1024        /* base-rate samples per oversampling tile           */
+#ifndef GDG_OS_TILE
+#define GDG_OS_TILE (GDG_MAX_N / 8)      /* base-rate samples per oversampling tile            */
+#endif
 #define GDG_NP 12               /* double parameters per unit                        */
 #define GDG_NI 10               /* int parameters per unit                           */
 

@@ -217,7 +217,7 @@ std::shared_ptr<DeviceSpectrum> make_spectrum(const std::vector<double> &coeffs)
     uint64_t B = next_pow2((uint64_t)L, &e);
     int K = 1;
     if (2 * B > GDG_MAX_FFT) {                               /* longer than 8192 taps: partitions of GDG_MAX_FFT/2 taps */
-        B = GDG_MAX_FFT / 2; e = 13;
+        B = GDG_MAX_FFT / 2; e = GDG_LOG_MAX_N;
         K = (int)((L + (int)B - 1) / (int)B);
     }
     const int F = (int)(2 * B);
@@ -635,9 +635,19 @@ struct Batch {
     std::vector<gdg_chain *> chains;
     std::vector<std::vector<const gdg_chain_desc *>> h_ptrs;     /* [round][channel] */
     std::vector<const gdg_chain_desc **> d_ptrs;
-    double *d_in = nullptr, *d_out = nullptr; size_t cap = 0;    /* device staging for host-buffer calls */
-    double *h_stage = nullptr, *h_stage2 = nullptr; size_t h_cap = 0;   /* pinned staging (in / out) for pageable callers */
-    ~Batch() { for (auto p : d_ptrs) gdgb_free((void *)p); if (d_in) gdgb_free(d_in); if (d_out) gdgb_free(d_out); if (h_stage) gdgb_pinned_free(h_stage); if (h_stage2) gdgb_pinned_free(h_stage2); }
+    /* two staging slots: block k+1 can be submitted (its upload overlapping block k's kernels and download) before
+     * block k is waited for; the synchronous entry points use whichever slot is free */
+    struct Slot {
+        double *d_in = nullptr, *d_out = nullptr; size_t cap = 0;    /* device staging for host-buffer calls */
+        double *h_stage = nullptr, *h_stage2 = nullptr; size_t h_cap = 0;   /* pinned staging (in / out) for pageable callers */
+        bool busy = false;                                           /* submitted, not yet waited for */
+        std::vector<std::pair<size_t, size_t>> staged;               /* output rows still in h_stage2 */
+        std::vector<void *> out; size_t ob = 0;
+    } slot[2];
+    ~Batch() {
+        for (auto p : d_ptrs) gdgb_free((void *)p);
+        for (auto &sl : slot) { if (sl.d_in) gdgb_free(sl.d_in); if (sl.d_out) gdgb_free(sl.d_out); if (sl.h_stage) gdgb_pinned_free(sl.h_stage); if (sl.h_stage2) gdgb_pinned_free(sl.h_stage2); }
+    }
 };
 std::mutex g_batch_mutex;
 std::unique_ptr<Batch> g_batch;
@@ -646,6 +656,8 @@ std::unique_ptr<Batch> g_batch;
 int prepare_batch(gdg_chain *const *chains, size_t C, uint32_t rate, size_t n, void *stream)
 {
     if (!g_batch || g_batch->chains.size() != C || !std::equal(g_batch->chains.begin(), g_batch->chains.end(), chains)) {
+        if (g_batch && (g_batch->slot[0].busy || g_batch->slot[1].busy))
+            return fail("a submitted block of another chain set is still in flight: gdg_controller_wait() for it first");
         g_batch.reset(new Batch());
         g_batch->chains.assign(chains, chains + C);
     }
@@ -728,7 +740,7 @@ bool contiguous(const double *const *p, size_t C, size_t n)
     return true;
 }
 
-int stage_buffers(Batch &b, size_t words)
+int stage_buffers(Batch::Slot &b, size_t words)
 {
     if (b.cap < words) {
         if (b.d_in) gdgb_free(b.d_in);
@@ -748,7 +760,7 @@ bool contiguous_bytes(const void *const *p, size_t C, size_t row_bytes)
     return true;
 }
 /* rows are `bytes` long (n samples of the batch's input format) */
-int upload_rows(Batch &b, const void *const *in, size_t c0, size_t cnt, size_t bytes, void *d_dst, int stream_id)
+int upload_rows(Batch::Slot &b, const void *const *in, size_t c0, size_t cnt, size_t bytes, void *d_dst, int stream_id)
 {
     char *dst = (char *)d_dst, *hs = (char *)b.h_stage;
     if (contiguous_bytes(in + c0, cnt, bytes) && gdgb_is_pinned(in[c0]))
@@ -758,7 +770,7 @@ int upload_rows(Batch &b, const void *const *in, size_t c0, size_t cnt, size_t b
     return gdgb_h2d_async(dst + c0 * bytes, hs + c0 * bytes, cnt * bytes, stream_id) ? backend_fail("upload failed") : 0;
 }
 /* device planar rows -> host rows; returns 1 if the data still sits in the pinned staging (scatter after sync) */
-int download_rows(Batch &b, void *const *out, size_t c0, size_t cnt, size_t bytes, const void *d_src, int stream_id)
+int download_rows(Batch::Slot &b, void *const *out, size_t c0, size_t cnt, size_t bytes, const void *d_src, int stream_id)
 {
     const char *src = (const char *)d_src;
     if (contiguous_bytes((const void *const *)out + c0, cnt, bytes) && gdgb_is_pinned(out[c0]))
@@ -766,7 +778,7 @@ int download_rows(Batch &b, void *const *out, size_t c0, size_t cnt, size_t byte
     if (gdgb_d2h_async((char *)b.h_stage2 + c0 * bytes, src + c0 * bytes, cnt * bytes, stream_id)) return backend_fail("download failed");
     return 1;
 }
-int ensure_host_stage(Batch &b, size_t words)
+int ensure_host_stage(Batch::Slot &b, size_t words)
 {
     if (b.h_cap < words) {
         if (b.h_stage) gdgb_pinned_free(b.h_stage);
@@ -793,7 +805,7 @@ int download_simple(double *const *out, size_t C, size_t n, const double *d_src)
 }
 
 /* the whole host-buffer block: upload -> (tuner feed) -> chains -> (spatializer) -> download, pipelined */
-int host_block(gdg_chain *const *chains, size_t C, gdg_tuner *tuner, int tuner_channel, gdg_spatializer *spat,
+int host_block(gdg_chain *const *chains, size_t C, gdg_tuner *tuner, int tuner_channel, gdg_spatializer *spat, struct gdg_meter *meter,
                const void *const *in, int in_fmt, void *const *out, int out_fmt, size_t n_out_rows, size_t n, uint32_t rate);
 
 } // namespace
@@ -860,15 +872,39 @@ struct gdg_tuner {
     ~gdg_tuner() { gdgb_free(d_ring); gdgb_free(d_work); gdgb_free(d_block); }
 };
 
+/* ---- level meter ---------------------------------------------------------------- */
+struct gdg_meter {
+    std::vector<std::string> names;
+    uint32_t count = 0;
+    bool enabled = false;                                 /* level.go:383-386: created disabled */
+    double *d_state = nullptr;                            /* [count][4]: cur, peak, counter, unused */
+    double *d_stage = nullptr; size_t stage_cap = 0;      /* rows of the host entry point */
+    ~gdg_meter() { gdgb_free(d_state); gdgb_free(d_stage); }
+};
+
 namespace {
-/* in_fmt / out_fmt: sample formats of the host rows (tuner and spatializer need float64 rows) */
-int host_block(gdg_chain *const *chains, size_t C, gdg_tuner *tuner, int tuner_channel, gdg_spatializer *spat,
-               const void *const *in, int in_fmt, void *const *out, int out_fmt, size_t n_out_rows, size_t n, uint32_t rate)
+int meter_rows(gdg_meter *m, uint32_t first, const double *d_rows, size_t stride, uint32_t rows, size_t n, uint32_t rate, void *stream)
 {
-    std::lock_guard<std::mutex> lk(g_batch_mutex);
+    if (!m->enabled || !rows || !n) return 0;             /* level.go:156: disabled channels do nothing */
+    const double sr = (double)rate;
+    const long long hold = (long long)(uint64_t)(2.0 * sr);                  /* level.go:163 */
+    const double f = std::pow(10.0, -1.0 / (1.7 * sr));                       /* level.go:164-165 */
+    if (gdgb_launch_meter(d_rows, (long)stride, (int)rows, (long)n, f, hold, m->d_state + 4 * (size_t)first, stream ? stream : gdgb_stream()))
+        return backend_fail("level meter launch failed");
+    return 0;
+}
+
+/* Enqueue one block on staging slot `si` (caller holds g_batch_mutex): uploads on stream 1, kernels on stream 0, downloads
+ * on stream 2, one SM wave of channels per pipeline group.  Nothing here waits for the device.
+ * in_fmt / out_fmt: sample formats of the host rows (tuner, spatializer and level meter need float64 rows).
+ * Event ids: slot*28 + {0..7 uploads, 8..15 kernels, 16 spatializer, 17 all downloads}. */
+int block_submit(int si, gdg_chain *const *chains, size_t C, gdg_tuner *tuner, int tuner_channel, gdg_spatializer *spat, gdg_meter *meter,
+                 const void *const *in, int in_fmt, void *const *out, int out_fmt, size_t n_out_rows, size_t n, uint32_t rate)
+{
     const int rounds = prepare_batch(chains, C, rate, n, gdgb_stream());
     if (rounds < 0) return -1;
-    Batch &b = *g_batch;
+    Batch::Slot &b = g_batch->slot[si];
+    const int ev = si * 28;
     const size_t ib = n * fmt_bytes(in_fmt), ob = n * fmt_bytes(out_fmt);      /* bytes per row */
     if (stage_buffers(b, (C + 2) * n)) return -1;
     const bool in_direct = contiguous_bytes(in, C, ib) && gdgb_is_pinned(in[0]);
@@ -877,38 +913,68 @@ int host_block(gdg_chain *const *chains, size_t C, gdg_tuner *tuner, int tuner_c
     const size_t per = pipeline_group_size(C);
     const int G = (int)((C + per - 1) / per);
     void *s0 = gdgb_stream_handle(0);
-    std::vector<std::pair<size_t, size_t>> staged;
+    b.staged.clear(); b.out.assign(out, out + n_out_rows); b.ob = ob;
     for (int g = 0; g < G; g++) {
         const size_t c0 = (size_t)g * per;
         if (c0 >= C) break;
         const size_t cnt = std::min(per, C - c0);
         if (upload_rows(b, in, c0, cnt, ib, b.d_in, 1)) return -1;
-        if (gdgb_record(g % 16, 1)) return backend_fail("event record failed");
+        if (gdgb_record(ev + g % 8, 1)) return backend_fail("event record failed");
     }
     for (int g = 0; g < G; g++) {
         const size_t c0 = (size_t)g * per;
         if (c0 >= C) break;
         const size_t cnt = std::min(per, C - c0);
-        if (gdgb_wait(0, g % 16)) return backend_fail("stream wait failed");
+        if (gdgb_wait(0, ev + g % 8)) return backend_fail("stream wait failed");
         if (tuner && tuner_channel >= 0 && (size_t)tuner_channel >= c0 && (size_t)tuner_channel < c0 + cnt)
             if (gdg_tuner_process_device(tuner, b.d_in + (size_t)tuner_channel * n, n, rate, s0)) return -1;   /* controller.go:2668-2672 */
+        if (meter && meter_rows(meter, (uint32_t)c0, b.d_in + c0 * n, n, (uint32_t)cnt, n, rate, s0)) return -1;      /* controller.go:2710-2714: inputs */
         if (launch_batch_fmt(c0, cnt, rounds, b.d_in, ib, in_fmt, b.d_out, ob, out_fmt, n, s0)) return -1;       /* controller.go:2682-2705 */
-        if (gdgb_record(16 + g % 16, 0) || gdgb_wait(2, 16 + g % 16)) return backend_fail("event failed");
+        if (meter && meter_rows(meter, (uint32_t)(C + c0), b.d_out + c0 * n, n, (uint32_t)cnt, n, rate, s0)) return -1;   /* outputs */
+        if (gdgb_record(ev + 8 + g % 8, 0) || gdgb_wait(2, ev + 8 + g % 8)) return backend_fail("event failed");
         const int r = download_rows(b, out, c0, cnt, ob, b.d_out, 2);
         if (r < 0) return -1;
-        if (r == 1) staged.push_back({c0, cnt});
+        if (r == 1) b.staged.push_back({c0, cnt});
     }
     if (spat) {                                                                                                 /* controller.go:2761 */
         if (gdg_spatializer_process_device(spat, b.d_out, n, nullptr, b.d_out + C * n, n, n, 0, s0)) return -1;
-        if (gdgb_record(40, 0) || gdgb_wait(2, 40)) return backend_fail("event failed");
+        if (meter && meter_rows(meter, (uint32_t)(2 * C + 1), b.d_out + C * n, n, 2, n, rate, s0)) return -1;    /* controller.go:2768-2770: master */
+        if (gdgb_record(ev + 16, 0) || gdgb_wait(2, ev + 16)) return backend_fail("event failed");
         const int r = download_rows(b, out, C, 2, ob, b.d_out, 2);
         if (r < 0) return -1;
-        if (r == 1) staged.push_back({C, 2});
+        if (r == 1) b.staged.push_back({C, 2});
     }
-    if (gdgb_sync_stream(2)) return backend_fail("synchronize failed");
-    for (auto &sg : staged)
-        for (size_t c = sg.first; c < sg.first + sg.second; c++) memcpy(out[c], (char *)b.h_stage2 + c * ob, ob);
+    if (gdgb_record(ev + 17, 2)) return backend_fail("event record failed");
+    b.busy = true;
     return 0;
+}
+/* the host waits for slot `si`'s downloads and scatters rows that went through the pinned staging */
+int block_wait(int si)
+{
+    Batch::Slot &b = g_batch->slot[si];
+    b.busy = false;
+    if (gdgb_sync_event(si * 28 + 17)) return backend_fail("synchronize failed");
+    for (auto &sg : b.staged)
+        for (size_t c = sg.first; c < sg.first + sg.second; c++) memcpy(b.out[c], (char *)b.h_stage2 + c * b.ob, b.ob);
+    b.staged.clear();
+    return 0;
+}
+int free_slot()
+{
+    if (!g_batch) return 0;
+    return !g_batch->slot[0].busy ? 0 : (!g_batch->slot[1].busy ? 1 : -1);
+}
+int host_block(gdg_chain *const *chains, size_t C, gdg_tuner *tuner, int tuner_channel, gdg_spatializer *spat, gdg_meter *meter,
+               const void *const *in, int in_fmt, void *const *out, int out_fmt, size_t n_out_rows, size_t n, uint32_t rate)
+{
+    std::lock_guard<std::mutex> lk(g_batch_mutex);
+    const int si = free_slot();
+    if (si < 0) return fail("two submitted blocks are in flight: gdg_controller_wait() for one first");
+    if (block_submit(si, chains, C, tuner, tuner_channel, spat, meter, in, in_fmt, out, out_fmt, n_out_rows, n, rate)) {
+        if (g_batch) { gdgb_sync(); g_batch->slot[si].busy = false; }
+        return -1;
+    }
+    return block_wait(si);
 }
 } // namespace
 
@@ -1246,7 +1312,7 @@ int gdg_process_batch(gdg_chain *const *chains, size_t C, const double *const *i
     if (ensure_init()) return -1;
     if (!chains || !C || !in || !out) return fail("gdg_process_batch: bad argument");
     if (check_block(n)) return -1;
-    return host_block(chains, C, nullptr, -1, nullptr, (const void *const *)in, GDG_FMT_IEEE64, (void *const *)out, GDG_FMT_IEEE64, C, n, rate);
+    return host_block(chains, C, nullptr, -1, nullptr, nullptr, (const void *const *)in, GDG_FMT_IEEE64, (void *const *)out, GDG_FMT_IEEE64, C, n, rate);
 }
 
 int gdg_chain_process(gdg_chain *c, const double *in, double *out, size_t n, uint32_t rate)
@@ -1448,7 +1514,7 @@ int gdg_process_batch_encoded(gdg_chain *const *chains, size_t C, const void *co
     if (!chains || !C || !in || !out) return fail("gdg_process_batch_encoded: bad argument");
     if (!fmt_bytes(in_format) || !fmt_bytes(out_format)) return fail("Unknown sample format: %#04x", fmt_bytes(in_format) ? out_format : in_format);
     if (check_block(n)) return -1;
-    return host_block(chains, C, nullptr, -1, nullptr, in, in_format, out, out_format, C, n, rate);
+    return host_block(chains, C, nullptr, -1, nullptr, nullptr, in, in_format, out, out_format, C, n, rate);
 }
 int gdg_process_batch_device_encoded(gdg_chain *const *chains, size_t C, const void *d_in, int in_format, size_t in_stride_bytes,
                                      void *d_out, int out_format, size_t out_stride_bytes, size_t n, uint32_t rate, void *stream)
@@ -1490,17 +1556,134 @@ long gdg_resample_time(const double *in, size_t n, uint32_t src, uint32_t dst, d
     return rc ? -1 : (long)len;
 }
 
+/* ---- level.Meter ---- */
+gdg_meter *gdg_meter_create(uint32_t channels, const char *const *names)
+{
+    if (ensure_init()) return nullptr;
+    gdg_meter *m = new gdg_meter();
+    m->count = channels;
+    for (uint32_t c = 0; c < channels; c++) m->names.push_back(names && names[c] ? names[c] : "");
+    m->d_state = (double *)gdgb_alloc(std::max<size_t>(1, channels) * 4 * sizeof(double));
+    if (!m->d_state) { backend_fail("level meter allocation failed"); delete m; return nullptr; }
+    return m;
+}
+void gdg_meter_destroy(gdg_meter *m) { delete m; }
+uint32_t gdg_meter_channel_count(gdg_meter *m) { return m ? m->count : 0; }
+const char *gdg_meter_channel_name(gdg_meter *m, uint32_t channel)
+{
+    if (!m) { fail("gdg_meter_channel_name: bad argument"); return nullptr; }
+    if (channel >= m->count) { fail("Requested name of channel %u, but level meter only has %u channels.", channel, m->count); return nullptr; }
+    return m->names[channel].c_str();
+}
+int gdg_meter_enabled(gdg_meter *m) { return m && m->enabled ? 1 : 0; }
+int gdg_meter_set_enabled(gdg_meter *m, int value)
+{
+    if (ensure_init()) return -1;
+    if (!m) return fail("gdg_meter_set_enabled: bad argument");
+    const bool v = value != 0;
+    if (v != m->enabled) {
+        if (!v && gdgb_zero(m->d_state, std::max<size_t>(1, m->count) * 4 * sizeof(double))) return backend_fail("level meter reset failed");   /* level.go:226-230 */
+        m->enabled = v;
+    }
+    return 0;
+}
+int gdg_meter_process_device(gdg_meter *m, uint32_t first_channel, const double *d_rows, size_t stride, uint32_t rows, size_t n,
+                             uint32_t rate, void *stream)
+{
+    if (ensure_init()) return -1;
+    if (!m || (!d_rows && rows && n) || !rate) return fail("gdg_meter_process_device: bad argument");
+    if ((uint64_t)first_channel + rows > m->count) return fail("gdg_meter_process_device: channels %u..%u exceed the meter's %u channels", first_channel, first_channel + rows, m->count);
+    return meter_rows(m, first_channel, d_rows, stride, rows, n, rate, stream);
+}
+int gdg_meter_process(gdg_meter *m, const double *const *bufs, uint32_t nbufs, size_t n, uint32_t rate)
+{
+    if (ensure_init()) return -1;
+    if (!m || (!bufs && nbufs)) return fail("gdg_meter_process: bad argument");
+    if (nbufs != m->count) return fail("Number of input buffers (%u) does not match number of channels (%u) for this level meter.", nbufs, m->count);   /* level.go:311-312 */
+    if (!m->enabled || !n || !nbufs) return 0;
+    if (!rate) return fail("gdg_meter_process: bad sample rate");
+    const size_t need = (size_t)nbufs * n;
+    if (m->stage_cap < need) { gdgb_free(m->d_stage); m->d_stage = (double *)gdgb_alloc(need * sizeof(double)); m->stage_cap = m->d_stage ? need : 0; if (!m->d_stage) return backend_fail("level meter staging allocation failed"); }
+    /* rows that are NULL (a nil buffer in the reference: zero samples) are skipped; runs of present rows go up together */
+    uint32_t c = 0;
+    while (c < nbufs) {
+        if (!bufs[c]) { c++; continue; }
+        uint32_t e = c;
+        while (e < nbufs && bufs[e]) { if (gdgb_upload(m->d_stage + (size_t)e * n, bufs[e], n * sizeof(double))) return backend_fail("upload failed"); e++; }
+        if (meter_rows(m, c, m->d_stage + (size_t)c * n, n, e - c, n, rate, nullptr)) return -1;
+        c = e;
+    }
+    return 0;
+}
+int gdg_meter_state(gdg_meter *m, uint32_t channel, double *cur, double *peak, uint64_t *counter)
+{
+    if (ensure_init()) return -1;
+    if (!m) return fail("gdg_meter_state: bad argument");
+    if (channel >= m->count) return fail("Requested analysis for channel %u, but level meter only has %u channels.", channel, m->count);
+    double w[4];
+    if (gdgb_sync_stream(0) || gdgb_download(w, m->d_state + 4 * (size_t)channel, sizeof(w))) return backend_fail("download failed");
+    if (cur) *cur = w[0];
+    if (peak) *peak = w[1];
+    if (counter) memcpy(counter, &w[2], sizeof(uint64_t));
+    return 0;
+}
+/* level.go:95-137: 20 log10, NaN / below -200 dB -> -200, round half away from zero */
+int gdg_meter_analyze(gdg_meter *m, uint32_t channel, int32_t *level, int32_t *peak)
+{
+    double c = 0.0, p = 0.0;
+    if (gdg_meter_state(m, channel, &c, &p, nullptr)) return -1;
+    auto db = [](double v) { double l = 20.0 * std::log10(v); if (std::isnan(l) || l < -200.0) l = -200.0; return (int32_t)std::round(l); };
+    if (level) *level = db(c);
+    if (peak) *peak = db(p);
+    return 0;
+}
+
 /* ---- controller.process mirror ---- */
-int gdg_controller_process(gdg_chain *const *chains, uint32_t C, gdg_tuner *tuner, int tuner_channel, gdg_spatializer *spat,
-                           const double *const *in, double *const *out, uint32_t n_out, size_t n, uint32_t rate)
+int gdg_controller_process_metered(gdg_chain *const *chains, uint32_t C, gdg_tuner *tuner, int tuner_channel, gdg_spatializer *spat,
+                                   gdg_meter *meter, const double *const *in, double *const *out, uint32_t n_out, size_t n, uint32_t rate)
 {
     if (ensure_init()) return -1;
     if (!chains || !C || !in || !out) return fail("gdg_controller_process: bad argument");
     if (check_block(n)) return -1;
+    if (meter && meter->count != 2 * C + 3)
+        return fail("gdg_controller_process: the level meter has %u channels, %u inputs need %u (inputs, outputs, metronome, master L/R: controller.go:2710-2771)", meter->count, C, 2 * C + 3);
     if (n_out < C) return 0;                                /* controller.go:2682: nothing happens */
     const bool do_spat = spat && n_out >= C + 2 && spat->count == C;
-    return host_block(chains, C, tuner, tuner_channel, do_spat ? spat : nullptr, (const void *const *)in, GDG_FMT_IEEE64, (void *const *)out,
-                      GDG_FMT_IEEE64, (size_t)C + (do_spat ? 2 : 0), n, rate);
+    return host_block(chains, C, tuner, tuner_channel, do_spat ? spat : nullptr, meter && meter->enabled ? meter : nullptr, (const void *const *)in,
+                      GDG_FMT_IEEE64, (void *const *)out, GDG_FMT_IEEE64, (size_t)C + (do_spat ? 2 : 0), n, rate);
+}
+/* the same block, submitted without waiting: returns a ticket (0 or 1) for gdg_controller_wait */
+int gdg_controller_submit(gdg_chain *const *chains, uint32_t C, gdg_tuner *tuner, int tuner_channel, gdg_spatializer *spat,
+                          gdg_meter *meter, const double *const *in, double *const *out, uint32_t n_out, size_t n, uint32_t rate)
+{
+    if (ensure_init()) return -1;
+    if (!chains || !C || !in || !out) return fail("gdg_controller_submit: bad argument");
+    if (check_block(n)) return -1;
+    if (meter && meter->count != 2 * C + 3)
+        return fail("gdg_controller_submit: the level meter has %u channels, %u inputs need %u (inputs, outputs, metronome, master L/R: controller.go:2710-2771)", meter->count, C, 2 * C + 3);
+    if (n_out < C) return fail("gdg_controller_submit: %u output rows for %u channels", n_out, C);
+    const bool do_spat = spat && n_out >= C + 2 && spat->count == C;
+    std::lock_guard<std::mutex> lk(g_batch_mutex);
+    const int si = free_slot();
+    if (si < 0) return fail("two submitted blocks are in flight: gdg_controller_wait() for one first");
+    if (block_submit(si, chains, C, tuner, tuner_channel, do_spat ? spat : nullptr, meter && meter->enabled ? meter : nullptr, (const void *const *)in,
+                     GDG_FMT_IEEE64, (void *const *)out, GDG_FMT_IEEE64, (size_t)C + (do_spat ? 2 : 0), n, rate)) {
+        if (g_batch) { gdgb_sync(); g_batch->slot[si].busy = false; }
+        return -1;
+    }
+    return si;
+}
+int gdg_controller_wait(int ticket)
+{
+    if (ensure_init()) return -1;
+    std::lock_guard<std::mutex> lk(g_batch_mutex);
+    if (ticket < 0 || ticket > 1 || !g_batch || !g_batch->slot[ticket].busy) return fail("gdg_controller_wait: ticket %d is not in flight", ticket);
+    return block_wait(ticket);
+}
+int gdg_controller_process(gdg_chain *const *chains, uint32_t C, gdg_tuner *tuner, int tuner_channel, gdg_spatializer *spat,
+                           const double *const *in, double *const *out, uint32_t n_out, size_t n, uint32_t rate)
+{
+    return gdg_controller_process_metered(chains, C, tuner, tuner_channel, spat, nullptr, in, out, n_out, n, rate);
 }
 
 } /* extern "C" */

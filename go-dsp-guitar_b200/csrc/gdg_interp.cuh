@@ -81,6 +81,122 @@ GDG_DEVI double resample_time_body(const double *in, long n, double dx, long i)
     return sum;
 }
 
+/* --------------------------------------------------------------------------
+ * level meter (level/level.go:147-208): per channel and sample
+ *     cur *= f;  if counter > hold: peak *= f else counter++;
+ *     if |s| > cur: cur = |s|;  if |s| >= peak: peak = |s|, counter = 0
+ * with f = 10^(-1/(1.7 fs)) and hold = 2 fs samples.  One CTA per channel walks the buffer in
+ * segments of GDG_METER_SEG <= hold samples (a thread owns 16 consecutive samples):
+ *   cur  : max-times reduction  cur' = max(cur f^len, max_t e_t f^(len - end_t)),  e_t the thread's exact local run;
+ *   peak : a segment shorter than the hold time can decay the peak only BEFORE its first reset, so
+ *          j* = first j with |s_j| >= peak f^(decays up to j)   (min-reduction),
+ *          after j* the peak is the running maximum: peak' = max_{j >= j*} |s_j|, counter' = len-1 - (last index of it);
+ *          without a reset peak' = peak f^(decays), counter' advances to at most hold + 1.
+ * Powers f^k are formed by squaring instead of k successive products: the state agrees with the reference to a
+ * few 1e-15 relative (the dB read-out, level.go:95-137, is integer).  Segments longer than the hold time
+ * (sample rates below GDG_METER_SEG/2 Hz) are walked by one thread with the literal loop.
+ * state words: st[0] cur, st[1] peak, st[2] counter (int64).  red: 4*GDG_NT + 8 doubles of shared scratch.
+ * -------------------------------------------------------------------------- */
+#define GDG_METER_SPT 16
+#define GDG_METER_SEG (GDG_NT * GDG_METER_SPT)
+#define GDG_METER_RED (4 * GDG_NT + 8)
+GDG_DEV void meter_segment(double *red, const double *x, int len, double f, long long hold, double *st)
+{
+    double *r_cur = red, *r_m = red + GDG_NT, *r_j = red + 2 * GDG_NT, *r_l = red + 3 * GDG_NT, *res = red + 4 * GDG_NT;
+    GDG_REGA(double, v, GDG_METER_SPT);
+    if ((long long)len > hold) {                                   /* not reachable for fs >= 4096 Hz */
+        GDG_THREADS_BEGIN
+            if (tid == 0) {
+                double cur = st[0], peak = st[1]; long long cnt = st_geti(st, 2);
+                for (int j = 0; j < len; j++) {
+                    cur *= f;
+                    if (cnt > hold) peak *= f; else cnt++;
+                    const double a = fabs(x[j]);
+                    if (a > cur) cur = a;
+                    if (a >= peak) { peak = a; cnt = 0; }
+                }
+                st[0] = cur; st[1] = peak; st_seti(st, 2, cnt);
+            }
+        GDG_THREADS_END
+        return;
+    }
+    const double c0 = st[0], p0 = st[1];
+    const long long q0 = st_geti(st, 2);
+    const int grace = q0 <= hold ? (int)(hold + 1 - q0 < (long long)len ? hold + 1 - q0 : (long long)len) : 0;   /* samples that only count */
+    GDG_THREADS_BEGIN
+        const int k0 = tid * GDG_METER_SPT, cnt = imax(0, imin(GDG_METER_SPT, len - k0));
+        double e = 0.0, thr = p0 * pow_int(f, imax(0, k0 - grace));
+        int jf = len;                                               /* first reset this chunk would cause, if none came earlier */
+#pragma unroll
+        for (int r = 0; r < GDG_METER_SPT; r++) {
+            const int j = k0 + r;
+            const double a = r < cnt ? fabs(x[j]) : 0.0;
+            R(v)[r] = a;
+            if (r < cnt) {
+                e *= f; if (a > e) e = a;
+                if (j >= grace) thr *= f;
+                if (jf == len && a >= thr) jf = j;
+            }
+        }
+        r_cur[tid] = cnt > 0 ? e * pow_int(f, len - (k0 + cnt)) : 0.0;
+        r_j[tid] = (double)jf;
+    GDG_THREADS_END
+    GDG_THREADS_BEGIN
+        if (tid < 32) {
+            double m = 0.0, j = (double)len;
+            for (int q = tid * (GDG_NT / 32); q < (tid + 1) * (GDG_NT / 32); q++) { if (r_cur[q] > m) m = r_cur[q]; if (r_j[q] < j) j = r_j[q]; }
+            r_m[tid] = m; r_l[tid] = j;
+        }
+    GDG_THREADS_END
+    GDG_THREADS_BEGIN
+        if (tid == 0) {
+            double m = 0.0, j = (double)len;
+            for (int q = 0; q < 32; q++) { if (r_m[q] > m) m = r_m[q]; if (r_l[q] < j) j = r_l[q]; }
+            res[1] = m; res[2] = j;
+        }
+    GDG_THREADS_END
+    const int jstar = (int)res[2];
+    const double curmax = res[1];
+    GDG_THREADS_BEGIN
+        const int k0 = tid * GDG_METER_SPT, cnt = imax(0, imin(GDG_METER_SPT, len - k0));
+        double m = -1.0; int li = -1;
+#pragma unroll
+        for (int r = 0; r < GDG_METER_SPT; r++) {
+            const int j = k0 + r;
+            if (r < cnt && j >= jstar && R(v)[r] >= m) { m = R(v)[r]; li = j; }
+        }
+        r_cur[tid] = m; r_j[tid] = (double)li;
+    GDG_THREADS_END
+    GDG_THREADS_BEGIN
+        if (tid < 32) {
+            double m = -1.0, l = -1.0;
+            for (int q = tid * (GDG_NT / 32); q < (tid + 1) * (GDG_NT / 32); q++) if (r_cur[q] > m || (r_cur[q] == m && r_j[q] > l)) { m = r_cur[q]; l = r_j[q]; }
+            r_m[tid] = m; r_l[tid] = l;
+        }
+    GDG_THREADS_END
+    GDG_THREADS_BEGIN
+        if (tid == 0) {
+            double m = -1.0, l = -1.0;
+            for (int q = 0; q < 32; q++) if (r_m[q] > m || (r_m[q] == m && r_l[q] > l)) { m = r_m[q]; l = r_l[q]; }
+            const double cdec = c0 * pow_int(f, len);
+            st[0] = curmax > cdec ? curmax : cdec;
+            if (jstar < len) { st[1] = m; st_seti(st, 2, (long long)(len - 1) - (long long)l); }
+            else {
+                st[1] = p0 * pow_int(f, len - grace);
+                st_seti(st, 2, q0 <= hold ? q0 + (long long)grace : q0);
+            }
+        }
+    GDG_THREADS_END
+}
+
+GDG_DEV void meter_channel(double *red, const double *x, long n, double f, long long hold, double *st)
+{
+    for (long o = 0; o < n; o += GDG_METER_SEG) {
+        const long len = n - o < (long)GDG_METER_SEG ? n - o : (long)GDG_METER_SEG;
+        meter_segment(red, x + o, (int)len, f, hold, st);
+    }
+}
+
 GDG_DEVI void ctx_init(gdg_ctx &cx, int n)
 {
     cx.cur_off = GDG_SMEM_R; cx.alt_off = GDG_SMEM_R + GDG_MAX_N; cx.n = n;
@@ -124,12 +240,15 @@ GDG_DEV void run_chain(double *smem, const gdg_chain_desc *cd, const void *in, i
     GDG_THREADS_BEGIN
         if (in_fmt == GDG_FMT_IEEE64) { for (int k = tid; k < n; k += GDG_NT) SM_CUR(cx)[sw(k)] = ((const double *)in)[k]; }
         else { for (int k = tid; k < n; k += GDG_NT) SM_CUR(cx)[sw(k)] = decode_sample(in_fmt, (const unsigned char *)in, k); }
-        for (int k = tid; k < 1024; k += GDG_NT) { SM_TWS[2 * k] = GDG_LDG(tw + 4 * k); SM_TWS[2 * k + 1] = GDG_LDG(tw + 4 * k + 1); }   /* exp(-2 pi i k / 8192) */
+        for (int k = tid; k < GDG_MAX_N / 8; k += GDG_NT) { SM_TWS[2 * k] = GDG_LDG(tw + 4 * k); SM_TWS[2 * k + 1] = GDG_LDG(tw + 4 * k + 1); }   /* exp(-2 pi i k / 8192) */
+        /* the chain descriptor rides along with the input load: no global round trip between units */
+        for (int k = tid; k < (int)(sizeof(gdg_chain_desc) / 4); k += GDG_NT) ((int *)(gdg_smem + GDG_SMEM_CHAIN))[k] = ((const int *)cd)[k];
     GDG_THREADS_END
-    const int ns = cd->nslots;
+    const gdg_chain_desc *scd = (const gdg_chain_desc *)(gdg_smem + GDG_SMEM_CHAIN);
+    const int ns = scd->nslots;
     for (int s = 0; s < ns; s++) {
         GDG_THREADS_BEGIN
-            if (tid < (int)(sizeof(gdg_unit_desc) / 4)) ((int *)(gdg_smem + GDG_SMEM_DESC))[tid] = ((const int *)&cd->slot[s])[tid];
+            if (tid < (int)(sizeof(gdg_unit_desc) / 4)) ((int *)(gdg_smem + GDG_SMEM_DESC))[tid] = ((const int *)&scd->slot[s])[tid];
         GDG_THREADS_END
         run_unit(cx, GDG_DESC, tw);
     }

@@ -29,7 +29,7 @@ static int cu_fail(const char *what, cudaError_t e)
 #define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cu_fail(#call, e_); } while (0)
 
 /* ---- kernels ------------------------------------------------------------------- */
-__global__ void __launch_bounds__(GDG_NT, 1)
+__global__ void __launch_bounds__(GDG_NT, GDG_MIN_CTAS)
 k_chain(const gdg_chain_desc *const *descs, const unsigned char *in, long in_stride, int in_fmt, unsigned char *out, long out_stride,
         int out_fmt, int n, const double *tw)
 {
@@ -42,6 +42,12 @@ k_chain(const gdg_chain_desc *const *descs, const unsigned char *in, long in_str
         return;
     }
     run_chain(gdg_smem, cd, src, in_fmt, dst, out_fmt, n, tw);
+}
+/* level meter: CTA c meters row c of d_in into state words d_state + 4*c */
+__global__ void __launch_bounds__(GDG_NT) k_meter(const double *in, long stride, long n, double f, long long hold, double *state)
+{
+    __shared__ double red[GDG_METER_RED];
+    meter_channel(red, in + (long)blockIdx.x * stride, n, f, hold, state + 4 * (long)blockIdx.x);
 }
 __global__ void k_resample_time(const double *in, long n, double dx, double *out, long out_len)
 {
@@ -160,6 +166,7 @@ int gdgb_d2h_async(void *dst, const void *src, size_t bytes, int s) { if (bytes)
 int gdgb_record(int ev, int s) { CU(cudaEventRecord(g_events[ev % GDGB_EVENTS], stream_of(s))); return 0; }
 int gdgb_wait(int s, int ev) { CU(cudaStreamWaitEvent(stream_of(s), g_events[ev % GDGB_EVENTS], 0)); return 0; }
 int gdgb_sync_stream(int s) { CU(cudaStreamSynchronize(stream_of(s))); return 0; }
+int gdgb_sync_event(int ev) { CU(cudaEventSynchronize(g_events[ev % GDGB_EVENTS])); return 0; }
 void *gdgb_pinned_alloc(size_t bytes) { void *p = nullptr; if (cudaMallocHost(&p, bytes ? bytes : 8) != cudaSuccess) return nullptr; return p; }
 void gdgb_pinned_free(void *p) { if (p) cudaFreeHost(p); }
 int gdgb_is_pinned(const void *p)
@@ -187,6 +194,15 @@ int gdgb_launch_chains(const gdg_chain_desc *const *d_descs, int channels, const
                                                                       (unsigned char *)d_out, out_stride_bytes, out_fmt, n, g_d_tw);
     g_launches++;
     CU(cudaGetLastError());
+    return 0;
+}
+int gdgb_launch_meter(const double *d_in, long stride, int channels, long n, double f, long long hold, double *d_state, void *stream)
+{
+    if (channels > 0 && n > 0) {
+        k_meter<<<channels, GDG_NT, 0, (cudaStream_t)stream>>>(d_in, stride, n, f, hold, d_state);
+        g_launches++;
+        CU(cudaGetLastError());
+    }
     return 0;
 }
 int gdgb_resample_time(const double *d_in, long n, double dx, double *d_out, long out_len, void *stream)

@@ -83,12 +83,13 @@ GDG_CONST double c_lz4[3][6];          /* ... x4: phase p/4, taps q: L(2 - q + p
 #define GDG_SMEM_R 0                                         /* 2*GDG_MAX_N: bufA | bufB; also the FFT workspace */
 #define GDG_SMEM_S (2 * GDG_MAX_N)                           /* GDG_MAX_N scratch */
 #define GDG_SMEM_TWS (GDG_SMEM_S + GDG_MAX_N)                /* 1024 complex: exp(-2 pi i k / 8192), loaded once per launch */
-#define GDG_SMEM_SCANB (GDG_SMEM_TWS + 2048)                 /* 256 doubles staging */
+#define GDG_SMEM_SCANB (GDG_SMEM_TWS + GDG_MAX_N / 4)                 /* 256 doubles staging */
 #define GDG_SMEM_SCANA (GDG_SMEM_SCANB + 256)                /* 512 doubles: split twiddles / staging */
 #define GDG_SMEM_SEG (GDG_SMEM_SCANA + 512)                  /* warp totals of the scans */
 #define GDG_SMEM_MISC (GDG_SMEM_SEG + 3 * GDG_SCAN_LANES * GDG_NSEG)
 #define GDG_SMEM_DESC (GDG_SMEM_MISC + 64)                    /* the running unit's descriptor (24 doubles) */
-#define GDG_SMEM_DOUBLES (GDG_SMEM_DESC + 24)
+#define GDG_SMEM_CHAIN (GDG_SMEM_DESC + 24)                  /* the whole chain descriptor, staged once per launch */
+#define GDG_SMEM_DOUBLES (GDG_SMEM_CHAIN + (int)((sizeof(gdg_chain_desc) + 7) / 8))
 #define GDG_SMEM_BYTES (GDG_SMEM_DOUBLES * 8)
 
 #if defined(__CUDACC__) && !defined(GDG_HOST_EMU)

@@ -34,7 +34,7 @@
  * ========================================================================== */
 #define GDG_FIR_Q 39                         /* taps per polyphase branch */
 #define GDG_ZH 40                            /* halo length per phase (>= Q-1), multiple of 8 */
-#define GDG_ZPS 1200                         /* doubles reserved per phase array: pz(GDG_ZH + GDG_OS_TILE + 1) = 1198 */
+#define GDG_ZPS (((GDG_ZH + GDG_OS_TILE + 1) * 9) / 8 + 8)   /* doubles reserved per phase array >= pz(GDG_ZH + GDG_OS_TILE + 1) + 1 */
 #define GDG_OS_Z2 GDG_OS_ST_Z2
 GDG_DEVI int pz(int m) { return m + (m >> 3); }      /* one pad per 8: stride-8/9 access patterns spread over banks */
 /* location of oversampled sample (tile-local base index jl, sub-phase ph) in the per-phase arrays */
@@ -654,7 +654,7 @@ GDG_DEV void fft_pass(double *D, const double *tws, int logM, int nseg, int logL
     constexpr int LOGR = RR == 16 ? 4 : (RR == 8 ? 3 : (RR == 4 ? 2 : 1));
     const int logS = logL - LOGR;                              /* stride L/RR */
     const int nb = nseg << (logM - LOGR);
-    const int tshift = 13 - logL;                              /* W_L^j = tws[j << tshift]: shared table exp(-2 pi i k / 8192), k < 1024 */
+    const int tshift = GDG_LOG_MAX_N - logL;                              /* W_L^j = tws[j << tshift]: shared table exp(-2 pi i k / 8192), k < 1024 */
     GDG_THREADS_BEGIN
 #pragma unroll 1
         for (int b = tid; b < nb; b += GDG_NT) {

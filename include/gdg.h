@@ -43,6 +43,7 @@ typedef struct gdg_irbank gdg_irbank;           /* filter.ImpulseResponses   fil
 typedef struct gdg_chain gdg_chain;             /* signal.Chain              signal/signal.go:21-36  */
 typedef struct gdg_spatializer gdg_spatializer; /* spatializer.Spatializer   spatializer/spatializer.go:30-41 */
 typedef struct gdg_tuner gdg_tuner;             /* tuner.Tuner               tuner/tuner.go:62-65    */
+typedef struct gdg_meter gdg_meter;             /* level.Meter               level/level.go:48-65    */
 
 /* ---- runtime ----------------------------------------------------------------- */
 /* Select the CUDA device (one process per GPU) and upload the constant tables.  Called
@@ -167,13 +168,45 @@ int gdg_tuner_process_device(gdg_tuner *t, const double *d_samples, size_t n, ui
 typedef struct { int8_t cents; double frequency; const char *note; } gdg_tuner_result;    /* tuner.Result :27-43 */
 int gdg_tuner_analyze(gdg_tuner *t, gdg_tuner_result *result);                            /* Analyze :379-577 */
 
+/* ---- level.Meter  level/level.go ------------------------------------------------------ */
+/* CreateMeter(numChannels, names) :318-399 (names may be NULL: empty names); created disabled */
+gdg_meter *gdg_meter_create(uint32_t channels, const char *const *names);
+void gdg_meter_destroy(gdg_meter *m);
+uint32_t gdg_meter_channel_count(gdg_meter *m);                                           /* ChannelCount :260-265 */
+const char *gdg_meter_channel_name(gdg_meter *m, uint32_t channel);                       /* ChannelName  :270-287 (NULL + error when out of range) */
+int gdg_meter_enabled(gdg_meter *m);                                                      /* Enabled      :292-297 */
+int gdg_meter_set_enabled(gdg_meter *m, int value);                                       /* SetEnabled   :333-356 (disabling clears the state, :214-237) */
+/* Process(buffers, sampleRate) :302-328 -> channelMeter.process :147-208.  HOST buffers, one per channel (a NULL row is a
+ * nil buffer: no samples); fails when n_buffers != channel count; a disabled meter does nothing. */
+int gdg_meter_process(gdg_meter *m, const double *const *buffers, uint32_t n_buffers, size_t n, uint32_t sample_rate);
+/* DEVICE rows: `rows` consecutive meter channels from first_channel, row r at d_rows + r*stride */
+int gdg_meter_process_device(gdg_meter *m, uint32_t first_channel, const double *d_rows, size_t stride, uint32_t rows, size_t n,
+                             uint32_t sample_rate, void *stream);
+int gdg_meter_analyze(gdg_meter *m, uint32_t channel, int32_t *level, int32_t *peak);    /* Analyze :242-255 -> :95-137 (dB, rounded) */
+/* the raw state of one channel meter (currentValue, peakValue, sampleCounter: level.go:37-44); for tests and persistence */
+int gdg_meter_state(gdg_meter *m, uint32_t channel, double *current_value, double *peak_value, uint64_t *sample_counter);
+
 /* ---- controller.process mirror (controller/controller.go:2648-2783) ------------------- */
 /* tuner feed (channel tuner_channel, or -1) -> chains -> spatializer into out[C], out[C+1].
- * HOST buffers; n_out must be >= channels (+2 when spat != NULL).  Metronome/level meters are
+ * HOST buffers; n_out must be >= channels (+2 when spat != NULL).  The metronome is
  * the caller's business (out of scope). */
 int gdg_controller_process(gdg_chain *const *chains, uint32_t channels, gdg_tuner *tuner, int tuner_channel,
                            gdg_spatializer *spat, const double *const *in, double *const *out, uint32_t n_out,
                            size_t n, uint32_t sample_rate);
+/* the same with the level meter of controller.go:2653-2781 fed on the device: meter channels [0,C) inputs, [C,2C) chain
+ * outputs, 2C the metronome port (not fed here), 2C+1 / 2C+2 master left / right; meter may be NULL */
+int gdg_controller_process_metered(gdg_chain *const *chains, uint32_t channels, gdg_tuner *tuner, int tuner_channel,
+                                   gdg_spatializer *spat, gdg_meter *meter, const double *const *in, double *const *out,
+                                   uint32_t n_out, size_t n, uint32_t sample_rate);
+/* The same block WITHOUT waiting for it: returns a ticket (0 or 1, at most two blocks in flight) or -1.  The rows of `in`
+ * must stay untouched and the rows of `out` are undefined until gdg_controller_wait(ticket) returns.  Blocks run in
+ * submission order (unit state carries from one to the next), so a batch loop - controller.go:2991-3106 walks the file
+ * block by block - submits block k+1 before it waits for block k: the upload of k+1 and the download of k overlap the
+ * kernels.  Pinned, contiguous rows (gdg_pinned_alloc) make both copies truly asynchronous. */
+int gdg_controller_submit(gdg_chain *const *chains, uint32_t channels, gdg_tuner *tuner, int tuner_channel,
+                          gdg_spatializer *spat, gdg_meter *meter, const double *const *in, double *const *out,
+                          uint32_t n_out, size_t n, uint32_t sample_rate);
+int gdg_controller_wait(int ticket);
 
 #ifdef __cplusplus
 }

@@ -141,6 +141,17 @@ void orc_tuner_destroy(orc_tuner *t);
 void orc_tuner_process(orc_tuner *t, const double *samples, size_t n, uint32_t sample_rate);
 int orc_tuner_analyze(orc_tuner *t, orc_tuner_result *res);
 
+/* ---- level/level.go ---------------------------------------------------------- */
+typedef struct orc_meter orc_meter;
+orc_meter *orc_meter_create(uint32_t channels);
+void orc_meter_destroy(orc_meter *m);
+uint32_t orc_meter_channel_count(const orc_meter *m);
+int orc_meter_enabled(const orc_meter *m);
+void orc_meter_set_enabled(orc_meter *m, int value);
+int orc_meter_process(orc_meter *m, const double *const *bufs, const size_t *lens, uint32_t n_bufs, uint32_t sample_rate);
+int orc_meter_analyze(const orc_meter *m, uint32_t channel, int32_t *level, int32_t *peak);
+int orc_meter_state(const orc_meter *m, uint32_t channel, double *cur, double *peak, uint64_t *counter);
+
 /* ---- controller.process mirror (controller/controller.go:2648-2783) -------
  * One block over C chains: tuner feed (channel tuner_channel or -1), chains,
  * spatializer (may be NULL) into out[C], out[C+1]; no metronome (zeros).      */

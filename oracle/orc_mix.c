@@ -211,6 +211,81 @@ int orc_tuner_analyze(orc_tuner *t, orc_tuner_result *res)
 }
 
 /* ======================================================================== */
+/* level/level.go: level meter (peak programme meter with 2 s peak hold)      */
+/* ======================================================================== */
+typedef struct { double cur, peak; uint64_t counter; int enabled; } orc_meter_channel;
+struct orc_meter { uint32_t count; int enabled; orc_meter_channel *ch; };
+
+orc_meter *orc_meter_create(uint32_t channels)          /* level.go:318-399: all channels disabled, state zero */
+{
+    orc_meter *m = (orc_meter *)calloc(1, sizeof(*m));
+    m->count = channels;
+    m->ch = (orc_meter_channel *)calloc(channels ? channels : 1, sizeof(orc_meter_channel));
+    return m;
+}
+void orc_meter_destroy(orc_meter *m) { if (m) { free(m->ch); free(m); } }
+uint32_t orc_meter_channel_count(const orc_meter *m) { return m->count; }
+int orc_meter_enabled(const orc_meter *m) { return m->enabled; }
+void orc_meter_set_enabled(orc_meter *m, int value)      /* level.go:333-356 -> 214-237 */
+{
+    value = value != 0;
+    if (value == m->enabled) return;
+    for (uint32_t c = 0; c < m->count; c++) {
+        orc_meter_channel *k = &m->ch[c];
+        if (value != k->enabled) {
+            if (!value) { k->cur = 0.0; k->peak = 0.0; k->counter = 0; }
+            k->enabled = value;
+        }
+    }
+    m->enabled = value;
+}
+/* level.go:147-208 */
+static void meter_channel_process(orc_meter_channel *k, const double *buf, size_t n, uint32_t rate)
+{
+    if (!k->enabled) return;
+    double cur = k->cur, peak = k->peak;
+    uint64_t counter = k->counter;
+    const double sr = (double)rate;
+    const uint64_t hold = (uint64_t)(2.0 * sr);
+    const double f = pow(10.0, -1.0 / (1.7 * sr));
+    for (size_t i = 0; i < n; i++) {
+        cur *= f;
+        if (counter > hold) peak *= f; else counter++;
+        const double a = fabs(buf[i]);
+        if (a > cur) cur = a;
+        if (a >= peak) { peak = a; counter = 0; }
+    }
+    k->cur = cur; k->peak = peak; k->counter = counter;
+}
+/* level.go:302-328: -1 when the number of buffers differs from the channel count; lens[c] samples in bufs[c] (NULL: none) */
+int orc_meter_process(orc_meter *m, const double *const *bufs, const size_t *lens, uint32_t n_bufs, uint32_t rate)
+{
+    if (n_bufs != m->count) return -1;
+    for (uint32_t c = 0; c < n_bufs; c++)
+        if (bufs[c]) meter_channel_process(&m->ch[c], bufs[c], lens[c], rate);
+    return 0;
+}
+static int32_t meter_db(double v)                       /* level.go:70-73, 95-137 */
+{
+    double l = 20.0 * log10(v);
+    if (isnan(l) || l < -200.0) l = -200.0;
+    return (int32_t)round(l);
+}
+int orc_meter_analyze(const orc_meter *m, uint32_t channel, int32_t *level, int32_t *peak)   /* level.go:242-255 */
+{
+    if (channel >= m->count) return -1;
+    *level = meter_db(m->ch[channel].cur);
+    *peak = meter_db(m->ch[channel].peak);
+    return 0;
+}
+int orc_meter_state(const orc_meter *m, uint32_t channel, double *cur, double *peak, uint64_t *counter)
+{
+    if (channel >= m->count) return -1;
+    *cur = m->ch[channel].cur; *peak = m->ch[channel].peak; *counter = m->ch[channel].counter;
+    return 0;
+}
+
+/* ======================================================================== */
 /* controller/controller.go:2648-2783 process (metronome = zeros, no meters)  */
 /* ======================================================================== */
 void orc_controller_process(orc_chain *const *chains, uint32_t n_ch, orc_tuner *tuner, int tuner_channel,

@@ -102,6 +102,14 @@ def lib():
             "orc_tuner_destroy": (None, [vp]),
             "orc_tuner_process": (None, [vp, vp, sz, u32]),
             "orc_tuner_analyze": (C.c_int, [vp, vp]),
+            "orc_meter_create": (vp, [u32]),
+            "orc_meter_destroy": (None, [vp]),
+            "orc_meter_channel_count": (u32, [vp]),
+            "orc_meter_enabled": (C.c_int, [vp]),
+            "orc_meter_set_enabled": (None, [vp, C.c_int]),
+            "orc_meter_process": (C.c_int, [vp, vp, vp, u32, u32]),
+            "orc_meter_analyze": (C.c_int, [vp, u32, vp, vp]),
+            "orc_meter_state": (C.c_int, [vp, u32, vp, vp, vp]),
             "orc_controller_process": (None, [vp, u32, vp, C.c_int, vp, vp, vp, u32, sz, u32]),
         }
         for name, (res, args) in sig.items():
@@ -500,6 +508,44 @@ class Tuner:
         if lib().orc_tuner_analyze(self._h, C.byref(r)):
             raise OracleError("analyze")
         return {"cents": r.cents, "frequency": r.frequency, "note": r.note.decode()}
+
+
+# ---- level meter (level/level.go) --------------------------------------------------------
+class Meter:
+    def __init__(self, channels):
+        self._h = lib().orc_meter_create(channels)
+        self.count = channels
+
+    def __del__(self):
+        lib().orc_meter_destroy(self._h)
+
+    @property
+    def enabled(self):
+        return bool(lib().orc_meter_enabled(self._h))
+
+    def set_enabled(self, value):
+        lib().orc_meter_set_enabled(self._h, 1 if value else 0)
+
+    def process(self, buffers, rate):
+        """buffers: one array (or None) per channel, lengths may differ."""
+        rows = [None if b is None else _f64(b) for b in buffers]
+        k = len(rows)
+        bp = (C.c_void_p * max(k, 1))(*[None if r is None else r.ctypes.data for r in rows])
+        ln = (C.c_size_t * max(k, 1))(*[0 if r is None else len(r) for r in rows])
+        if lib().orc_meter_process(self._h, bp, ln, k, rate):
+            raise OracleError("Number of input buffers (%d) does not match number of channels (%d) for this level meter." % (k, self.count))
+
+    def analyze(self, channel):
+        lv, pk = C.c_int32(), C.c_int32()
+        if lib().orc_meter_analyze(self._h, channel, C.byref(lv), C.byref(pk)):
+            raise OracleError("Requested analysis for channel %d, but level meter only has %d channels." % (channel, self.count))
+        return lv.value, pk.value
+
+    def state(self, channel):
+        c, p, q = C.c_double(), C.c_double(), C.c_uint64()
+        if lib().orc_meter_state(self._h, channel, C.byref(c), C.byref(p), C.byref(q)):
+            raise OracleError("channel")
+        return c.value, p.value, q.value
 
 
 def controller_process(chains, tuner, tuner_channel, spat, inputs, sample_rate):

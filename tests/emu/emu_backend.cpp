@@ -47,6 +47,7 @@ int gdgb_d2h_async(void *d, const void *s, size_t b, int) { memcpy(d, s, b); ret
 int gdgb_record(int, int) { return 0; }
 int gdgb_wait(int, int) { return 0; }
 int gdgb_sync_stream(int) { return 0; }
+int gdgb_sync_event(int) { return 0; }
 void *gdgb_pinned_alloc(size_t bytes) { return malloc(bytes ? bytes : 8); }
 void gdgb_pinned_free(void *p) { free(p); }
 int gdgb_is_pinned(const void *) { return 0; }
@@ -72,6 +73,13 @@ int gdgb_launch_chains(const gdg_chain_desc *const *descs, int channels, const v
         run_chain(smem.data(), descs[c], src, in_fmt, dst, out_fmt, n, g_tw.data());
     }
     g_launches++;
+    return 0;
+}
+int gdgb_launch_meter(const double *in, long stride, int channels, long n, double f, long long hold, double *state, void *)
+{
+    std::vector<double> red(GDG_METER_RED);
+    for (int c = 0; c < channels; c++) meter_channel(red.data(), in + (long)c * stride, n, f, hold, state + 4 * (long)c);
+    if (channels > 0 && n > 0) g_launches++;
     return 0;
 }
 int gdgb_resample_time(const double *in, long n, double dx, double *out, long out_len, void *)

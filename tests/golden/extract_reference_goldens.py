@@ -186,6 +186,21 @@ def main():
                             sample_rate=np.array(fmt[2], dtype=np.uint32))
         print("tuner", note, fmt[2], len(x))
 
+    # --- level meter: level/level_test.go TestMeters feeds one second of a 1 Hz sine (amplitude 1 and 0.5) at
+    #     96 kHz in ONE Process call and expects integer dB read-outs before and after SetEnabled(false) ---
+    lsrc = strip_comments(open(os.path.join(REF, "level/level_test.go")).read())
+    rate = int(re.search(r"DEFAULT_SAMPLE_RATE\s*=\s*(\d+)", lsrc).group(1))
+    lv = [int(v) for v in re.findall(r"expectedLevel := int32\((-?\d+)\)", lsrc)]
+    pk = [int(v) for v in re.findall(r"expectedPeak := int32\((-?\d+)\)", lsrc)]
+    assert len(lv) == 4 and len(pk) == 4 and "0.5 * elemA" in lsrc and "TWO_PI * t" in lsrc, (lv, pk)
+    level = {"source": "level/level_test.go", "sample_rate": rate, "samples": rate, "signal": "sin(2 pi i / sample_rate)",
+             "amplitudes": [1.0, 0.5],
+             "enabled": {"level": lv[0:2], "peak": pk[0:2]},
+             "after_disable": {"level": lv[2:4], "peak": pk[2:4]}}
+    with open(os.path.join(HERE, "level_goldens.json"), "w") as f:
+        json.dump(level, f, indent=1)
+    print("level:", level["enabled"], level["after_disable"])
+
 
 if __name__ == "__main__":
     sys.exit(main())

@@ -115,3 +115,169 @@ def test_resample_time_matches_oracle(lib, src, dst):
     assert len(a) == len(b) == lib.gdg_resample_time_length(len(x), src, dst)
     assert common.rms(a - b) <= common.TOL_RMS
     assert len(gdg.resample_time(np.zeros(0), src, dst, lib)) == 0
+
+
+# ---- level.Meter -----------------------------------------------------------
+METER_RTOL = 1e-10          # state (currentValue / peakValue) relative tolerance: powers by squaring vs. successive products
+
+
+def _meter_pair(lib, channels):
+    m, o = gdg.Meter(channels, lib=lib), orc.Meter(channels)
+    assert not m.enabled() and not o.enabled                 # level.go:383-386
+    return m, o
+
+
+def _assert_meters_agree(m, o, channels, exact=False):
+    for c in range(channels):
+        (mc, mp, mq), (oc, op, oq) = m.state(c), o.state(c)
+        assert mq == oq, (c, mq, oq)
+        if exact:
+            assert (mc, mp) == (oc, op)
+        else:
+            assert abs(mc - oc) <= METER_RTOL * abs(oc) and abs(mp - op) <= METER_RTOL * abs(op), (c, mc, oc, mp, op)
+        assert m.analyze(c) == o.analyze(c)
+
+
+def test_meter_reference_vector(lib):
+    """level/level_test.go TestMeters: one second of a 1 Hz sine in one Process call."""
+    g = json.load(open(os.path.join(common.GOLD, "level_goldens.json")))
+    fs, n = g["sample_rate"], g["samples"]
+    t = np.arange(n, dtype=np.float64) / float(fs)
+    sig = np.sin((2.0 * np.pi) * t)
+    m = gdg.Meter(2, ["channel_a", "channel_b"], lib=lib)
+    assert m.channel_count() == 2 and m.channel_name(0) == "channel_a" and m.channel_name(1) == "channel_b"
+    with pytest.raises(gdg.GdgError, match="level meter only has 2 channels"):
+        m.channel_name(2)
+    m.set_enabled(True)
+    m.process([a * sig for a in g["amplitudes"]], fs)
+    for c in range(2):
+        assert m.analyze(c) == (g["enabled"]["level"][c], g["enabled"]["peak"][c])
+    m.set_enabled(False)                                      # clears the state (level.go:226-230)
+    for c in range(2):
+        assert m.analyze(c) == (g["after_disable"]["level"][c], g["after_disable"]["peak"][c])
+
+
+@pytest.mark.parametrize("fs", [22050, 96000, 192000])
+def test_meter_streams_like_the_reference(lib, fs):
+    """blocks of many lengths (one sample .. several segments), bursts, ties, silence, and decays that run past the
+    2 s hold time: state and read-outs follow the oracle's literal per-sample loop."""
+    rng = np.random.default_rng(fs)
+    ch = 4
+    m, o = _meter_pair(lib, ch)
+    m.set_enabled(True); o.set_enabled(True)
+    total = 0
+    for k, n in enumerate([8192, 1, 64, 1000, 8192, 8193, 20000, 4096, 512] + [8192] * (3 * fs // 8192 + 2)):
+        t = (total + np.arange(n)) / fs
+        env = np.exp(-3.0 * t)                                 # decays through the hold time
+        rows = [env * rng.uniform(-1, 1, n),
+                0.25 * np.sign(np.sin(2 * np.pi * 50 * t)),    # constant magnitude: every sample ties the peak (>=)
+                np.zeros(n) if k % 3 else 1e-3 * rng.standard_normal(n),
+                (env * np.sin(2 * np.pi * 440 * t)) * (1.0 if k < 6 else 0.0)]
+        if k == 4:
+            rows[3] = rows[3].copy(); rows[3][n // 2] = 0.9    # a new maximum in the middle of a block
+        m.process(rows, fs); o.process(rows, fs)
+        total += n
+        if k < 12 or k % 5 == 0:
+            _assert_meters_agree(m, o, ch)
+    _assert_meters_agree(m, o, ch)
+    assert o.state(3)[2] > 2 * fs                            # the hold time did expire in the test
+
+
+def test_meter_enable_disable_and_argument_errors(lib):
+    rng = np.random.default_rng(3)
+    m, o = _meter_pair(lib, 3)
+    rows = [rng.uniform(-1, 1, 2048) for _ in range(3)]
+    m.process(rows, 48000); o.process(rows, 48000)           # disabled: nothing happens
+    _assert_meters_agree(m, o, 3, exact=True)
+    assert m.state(0) == (0.0, 0.0, 0) and m.analyze(0) == (-200, -200)
+    m.set_enabled(True); o.set_enabled(True)
+    assert m.enabled()
+    rows[1] = None                                            # a nil buffer: that channel sees no samples
+    m.process(rows, 48000); o.process(rows, 48000)
+    _assert_meters_agree(m, o, 3)
+    assert m.state(1) == (0.0, 0.0, 0)
+    with pytest.raises(gdg.GdgError, match=r"Number of input buffers \(2\) does not match number of channels \(3\)"):
+        m.process(rows[:2], 48000)
+    with pytest.raises(gdg.GdgError, match="only has 3 channels"):
+        m.analyze(3)
+    m.set_enabled(False); o.set_enabled(False)
+    _assert_meters_agree(m, o, 3, exact=True)
+    with pytest.raises(gdg.GdgError, match="provided 1 channel names"):
+        gdg.Meter(2, ["only_one"], lib=lib)
+
+
+def test_meter_low_rate_literal_path(lib):
+    """a segment longer than the hold time (sample rates below 4096 Hz) is walked sample by sample: bit-exact"""
+    rng = np.random.default_rng(11)
+    m, o = _meter_pair(lib, 2)
+    m.set_enabled(True); o.set_enabled(True)
+    for n in [8192, 3000, 8192]:
+        rows = [np.exp(-np.arange(n) / 500.0) * rng.uniform(-1, 1, n), rng.uniform(-1, 1, n) * (np.arange(n) < 10)]
+        m.process(rows, 1000); o.process(rows, 1000)
+    _assert_meters_agree(m, o, 2, exact=True)
+    assert o.state(1)[2] > 2000
+
+
+def test_controller_process_feeds_the_meter(lib):
+    """controller.go:2710-2781: inputs, chain outputs and the master pair reach the meter (port layout 2C+3)."""
+    fs, n, C = 48000, 1024, 5
+    gc, oc = [], []
+    for c in range(C):
+        a, b = common.make_chain_pair(lib, [("overdrive", {"gain": 5 + c}, {}), ("delay", {"delay_time": 10}, {})])
+        oc.append(a); gc.append(b)
+    gs, os_ = gdg.Spatializer(C, lib=lib), orc.Spatializer(C)
+    for c in range(C):
+        gs.set_azimuth(c, -60.0 + 30.0 * c); os_.set_azimuth(c, -60.0 + 30.0 * c)
+    m, o = _meter_pair(lib, 2 * C + 3)
+    m.set_enabled(True); o.set_enabled(True)
+    for blk in range(3):
+        x = np.stack([common.synth_fast(c, fs, 4 * n, 1)[blk * n:(blk + 1) * n] for c in range(C)])
+        got = gdg.controller_process(gc, None, -1, gs, x, fs, meter=m)
+        ref = orc.controller_process(oc, None, -1, os_, x, fs)
+        assert np.max(np.abs(got - ref)) < 1e-9
+        o.process(list(x) + list(ref[:C]) + [None] + list(ref[C:]), fs)
+    _assert_meters_agree(m, o, 2 * C + 3)
+    assert m.analyze(0)[0] > -60 and m.analyze(2 * C + 1)[0] > -60 and m.analyze(2 * C) == (-200, -200)
+    with pytest.raises(gdg.GdgError, match="level meter has 4 channels"):
+        gdg.controller_process(gc, None, -1, gs, x, fs, meter=gdg.Meter(4, lib=lib))
+
+
+# ---- submit / wait: two blocks in flight --------------------------------------------------------------
+def test_controller_submit_wait_pipeline_matches_sequential(lib):
+    """gdg_controller_submit / gdg_controller_wait: block k+1 is submitted before block k is waited for; outputs, tuner
+    and meter state are those of the sequential reference loop (controller.go:2991-3106 walks blocks in order)."""
+    fs, n, C, blocks = 96000, 2048, 6, 6
+    spec = [("compressor", {}, {}), ("overdrive", {"gain": 12}, {"oversampling": "2"}), ("chorus", {}, {}), ("delay", {"delay_time": 30}, {})]
+    oc, gc = zip(*[common.make_chain_pair(lib, spec) for _ in range(C)])
+    gs, os_ = gdg.Spatializer(C, lib=lib), orc.Spatializer(C)
+    gt, ot = gdg.Tuner(lib=lib), orc.Tuner()
+    m, o = _meter_pair(lib, 2 * C + 3)
+    m.set_enabled(True); o.set_enabled(True)
+    x = np.stack([common.synth_fast(c, fs, blocks * n, 2) for c in range(C)])
+    xin = [np.ascontiguousarray(x[:, k * n:(k + 1) * n]) for k in range(blocks)]
+    outs = [np.zeros((C + 2, n)) for _ in range(blocks)]
+    tickets = []
+    for k in range(blocks):
+        tickets.append(gdg.controller_submit(list(gc), gt, 1, gs, xin[k], outs[k], fs, meter=m))
+        if k >= 1:
+            gdg.controller_wait(tickets[k - 1], lib)
+    with pytest.raises(gdg.GdgError, match="not in flight"):
+        gdg.controller_wait(tickets[0], lib)                  # already waited for
+    gdg.controller_wait(tickets[-1], lib)
+    for k in range(blocks):
+        ref = orc.controller_process(list(oc), ot, 1, os_, xin[k], fs)
+        o.process(list(xin[k]) + list(ref[:C]) + [None] + list(ref[C:]), fs)
+        for c in range(C + 2):
+            assert common.rms(ref[c] - outs[k][c]) <= common.TOL_RMS, (k, c)
+    _assert_meters_agree(m, o, 2 * C + 3)
+    assert gt.analyze()["note"] == ot.analyze()["note"]
+    # a third submit without a wait is refused, and the synchronous call still works afterwards
+    t0 = gdg.controller_submit(list(gc), None, -1, gs, xin[0], outs[0], fs)
+    t1 = gdg.controller_submit(list(gc), None, -1, gs, xin[1], outs[1], fs)
+    assert {t0, t1} == {0, 1}
+    with pytest.raises(gdg.GdgError, match="two submitted blocks are in flight"):
+        gdg.controller_submit(list(gc), None, -1, gs, xin[2], outs[2], fs)
+    with pytest.raises(gdg.GdgError, match="two submitted blocks are in flight"):
+        gdg.controller_process(list(gc), None, -1, gs, xin[2], fs)
+    gdg.controller_wait(t0, lib); gdg.controller_wait(t1, lib)
+    assert gdg.controller_process(list(gc), None, -1, gs, xin[2], fs).shape == (C + 2, n)

@@ -196,3 +196,23 @@ def test_wave_codecs(fmt):
     if fmt == "PCM16":
         pcm = np.frombuffer(bytes(g["import_data"]), dtype="<i2")
         assert np.array_equal(orc.pcm16_decode(pcm), dec)
+
+
+def test_level_meter_matches_reference_test():
+    """level/level_test.go TestMeters: -3 / 0 dB and -9 / -6 dB for a 1 Hz sine of amplitude 1 and 0.5, -200 once disabled."""
+    import json
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "level_goldens.json")))
+    fs, n = g["sample_rate"], g["samples"]
+    sig = np.sin((2.0 * np.pi) * (np.arange(n, dtype=np.float64) / float(fs)))
+    m = orc.Meter(2)
+    m.process([sig, 0.5 * sig], fs)                           # created disabled (level.go:383): nothing happens
+    assert [m.analyze(c) for c in range(2)] == [(-200, -200)] * 2
+    m.set_enabled(True)
+    m.process([a * sig for a in g["amplitudes"]], fs)
+    assert [m.analyze(c)[0] for c in range(2)] == g["enabled"]["level"]
+    assert [m.analyze(c)[1] for c in range(2)] == g["enabled"]["peak"]
+    m.set_enabled(False)
+    assert [m.analyze(c)[0] for c in range(2)] == g["after_disable"]["level"]
+    assert [m.analyze(c)[1] for c in range(2)] == g["after_disable"]["peak"]
+    with pytest.raises(orc.OracleError):
+        m.process([sig], fs)                                  # level.go:311-312: buffer count mismatch

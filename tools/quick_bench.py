@@ -8,7 +8,7 @@ import common
 from common import gdg
 
 lib = common.backend_lib("cuda")
-C = int(os.environ.get("GDG_C", "1024")); n = 8192; fs = 192000
+C = int(os.environ.get("GDG_C", "1024")); n = int(os.environ.get("GDG_N", "8192")); fs = 192000
 banks = common.make_banks(lib, synthetic=[("syn8192", 8192, fs)])
 x = torch.tensor(np.stack([common.synth_fast(c % 64, fs, n) for c in range(64)]), device="cuda").repeat(C // 64 + 1, 1)[:C].contiguous()
 y = torch.empty_like(x)
@@ -28,10 +28,13 @@ def timeit(name, spec, ir=None, reps=5):
     ms = e0.elapsed_time(e1) / reps
     res[name] = ms
     print("%-28s %8.3f ms/block  %9.1f Msamples/s" % (name, ms, C * n / ms / 1e3), flush=True)
+only = os.environ.get("GDG_ONLY", "").split(",") if os.environ.get("GDG_ONLY") else None
 timeit("empty", [])
 for u, nn, dd in common.CHAIN12:
+    if only and u not in only: continue
     timeit(u, [(u, nn, dd)], "syn8192")
 for u in ["signal_generator", "bandpass", "auto_wah", "auto_yoy", "octaver", "flanger", "phaser", "tremolo", "ring_modulator"]:
+    if only and u not in only: continue
     timeit(u, [(u, {}, {})])
 timeit("CHAIN12", common.CHAIN12, "syn8192")
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
