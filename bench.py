@@ -188,6 +188,22 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device - the product has no CPU path")
     torch.cuda.set_device(local)
+    # run this rank's host thread (and first-touch its pinned buffers) on the CPUs next to its GPU: the e2e path moves
+    # 134 MB per block per GPU over PCIe and a rank on the far socket pays for it at N = 8
+    all_cpus = os.sched_getaffinity(0)
+    numa_note = "unbound"
+    if os.environ.get("GDG_BENCH_NUMA", "1") != "0":
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(local)
+            words = pynvml.nvmlDeviceGetCpuAffinity(h, (max(all_cpus) // 64) + 1)
+            near = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1} & all_cpus
+            if near:
+                os.sched_setaffinity(0, near)
+                numa_note = "%d CPUs near GPU %d" % (len(near), local)
+        except Exception as e:                                   # affinity is an optimisation, never a requirement
+            numa_note = "unbound (%s)" % type(e).__name__
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -385,6 +401,7 @@ def main():
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        os.sched_setaffinity(0, all_cpus)                        # the CPU baseline gets every host core
         cores = os.cpu_count() or 1
         v, secs = time_oracle(cores, 4)
         cpu_baseline = {"value": v, "unit": "Msamples/s", "cores": cores, "kind": "port",
@@ -399,7 +416,7 @@ def main():
                        "cache": "inputs larger than L2: ring of %d distinct in/out block sets (%.0f MB) cycled" % (RING_BLOCKS, RING_BLOCKS * (2 * C + 2) * N * 8 / 1e6),
                        "parallelism": "channels sharded %d-way, NCCL reduce of the stereo master" % world},
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": C * N * 8, "d2h_bytes_per_step": (C + 2) * N * 8, "api": e2e_api,
+            "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": C * N * 8, "d2h_bytes_per_step": (C + 2) * N * 8, "api": e2e_api, "host_affinity": numa_note,
                     "synchronous_call": {"value": e2e_sync, "unit": "Msamples/s", "api": "gdg_controller_process (one blocking C-ABI call per block)"}},
             "gpu_launches": int(round(launches_per_step * args.steps)), "gpu_launches_per_step": launches_per_step,
             "roofline": {"kernel": "k_chain (fused 12-unit segment, one CTA per channel)", "bound": "hbm", "achieved": achieved,
