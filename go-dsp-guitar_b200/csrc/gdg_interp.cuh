@@ -230,13 +230,15 @@ GDG_DEV void run_unit(gdg_ctx &cx, const gdg_unit_desc &d, const double *tw)
 /* one channel, one block: load -> every slot -> store */
 GDG_DEV void run_chain(double *smem, const gdg_chain_desc *cd, const void *in, int in_fmt, void *out, int out_fmt, int n, const double *tw)
 {
-    gdg_ctx cx;
 #if !defined(__CUDACC__) || defined(GDG_HOST_EMU)
     gdg_smem = smem;
 #else
     (void)smem;
 #endif
+    gdg_ctx &cx = *(gdg_ctx *)(gdg_smem + GDG_SMEM_CTX);        /* every thread writes the same three words */
     ctx_init(cx, n);
+    GDG_THREADS_BEGIN
+    GDG_THREADS_END
     GDG_THREADS_BEGIN
         if (in_fmt == GDG_FMT_IEEE64) { for (int k = tid; k < n; k += GDG_NT) SM_CUR(cx)[sw(k)] = ((const double *)in)[k]; }
         else { for (int k = tid; k < n; k += GDG_NT) SM_CUR(cx)[sw(k)] = decode_sample(in_fmt, (const unsigned char *)in, k); }

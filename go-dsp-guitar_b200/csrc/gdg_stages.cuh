@@ -88,7 +88,8 @@ GDG_CONST double c_lz4[3][6];          /* ... x4: phase p/4, taps q: L(2 - q + p
 #define GDG_SMEM_SEG (GDG_SMEM_SCANA + 512)                  /* warp totals of the scans */
 #define GDG_SMEM_MISC (GDG_SMEM_SEG + 3 * GDG_SCAN_LANES * GDG_NSEG)
 #define GDG_SMEM_DESC (GDG_SMEM_MISC + 64)                    /* the running unit's descriptor (24 doubles) */
-#define GDG_SMEM_CHAIN (GDG_SMEM_DESC + 24)                  /* the whole chain descriptor, staged once per launch */
+#define GDG_SMEM_CTX (GDG_SMEM_DESC + 24)                    /* gdg_ctx of the running block (2 doubles) */
+#define GDG_SMEM_CHAIN (GDG_SMEM_CTX + 2)                    /* the whole chain descriptor, staged once per launch */
 #define GDG_SMEM_DOUBLES (GDG_SMEM_CHAIN + (int)((sizeof(gdg_chain_desc) + 7) / 8))
 #define GDG_SMEM_BYTES (GDG_SMEM_DOUBLES * 8)
 
@@ -127,7 +128,15 @@ GDG_DEVI int imax(int a, int b) { return a > b ? a : b; }
 GDG_DEVI long long st_geti(const double *st, int k) { return ((const long long *)st)[k]; }
 GDG_DEVI void st_seti(double *st, int k, long long v) { ((long long *)st)[k] = v; }
 GDG_DEVI int chunk_len(int n) { return (n + GDG_NT - 1) / GDG_NT; }
-GDG_DEVI void swap_bufs(gdg_ctx &cx) { const int t = cx.cur_off; cx.cur_off = cx.alt_off; cx.alt_off = t; }
+/* the context lives in shared memory (a private copy passed by reference to the non-inlined stages would sit in
+ * local memory, and there is next to no L1 left beside the 220 KB carve-out): one thread flips it between barriers.
+ * Every stage ends with a barrier before it swaps, so no thread still reads the old orientation. */
+GDG_DEVI void swap_bufs(gdg_ctx &cx)
+{
+    GDG_THREADS_BEGIN
+        if (tid == 0) { const int t = cx.cur_off; cx.cur_off = cx.alt_off; cx.alt_off = t; }
+    GDG_THREADS_END
+}
 
 GDG_DEVI double pow_int(double a, int k)          /* a^k by binary exponentiation (k >= 0) */
 {

@@ -690,23 +690,20 @@ GDG_DEVI void fft_pass_any(double *D, const double *tw, int logM, int nseg, int 
     else fft_pass<2>(D, tw, logM, nseg, logL, inverse);
 }
 /* radix plan: ceil(logM / 4) passes of radix 16 / 8 / 4 / 2, the larger radices first (13 -> 4+3+3+3, 12 -> 4+4+4) */
-GDG_DEVI int fft_plan(int logM, int (&r)[8])
-{
-    const int np = (logM + 3) / 4;
-    for (int i = 0; i < np; i++) r[i] = logM / np + (i < logM % np ? 1 : 0);
-    return np;
-}
+GDG_DEVI int fft_plan_radix(int logM, int np, int i) { return logM / np + (i < logM % np ? 1 : 0); }
 GDG_DEV void fft_forward(gdg_ctx &cx, double *D, const double *tw, int logM, int nseg)
 {
-    int r[8]; const int np = fft_plan(logM, r);
+    const int np = (logM + 3) / 4;
     int logL = logM;
-    for (int i = 0; i < np; i++) { fft_pass_any(D, tw, logM, nseg, logL, r[i], 0, cx); logL -= r[i]; }
+#pragma unroll 1
+    for (int i = 0; i < np; i++) { const int r = fft_plan_radix(logM, np, i); fft_pass_any(D, tw, logM, nseg, logL, r, 0, cx); logL -= r; }
 }
 GDG_DEV void fft_inverse(gdg_ctx &cx, double *D, const double *tw, int logM, int nseg)
 {
-    int r[8]; const int np = fft_plan(logM, r);
+    const int np = (logM + 3) / 4;
     int logL = 0;
-    for (int i = np - 1; i >= 0; i--) { logL += r[i]; fft_pass_any(D, tw, logM, nseg, logL, r[i], 1, cx); }
+#pragma unroll 1
+    for (int i = np - 1; i >= 0; i--) { const int r = fft_plan_radix(logM, np, i); logL += r; fft_pass_any(D, tw, logM, nseg, logL, r, 1, cx); }
 }
 
 /* power_amp state: tail[F] followed by one word = number of trailing tail cells known to be zero */
@@ -741,8 +738,10 @@ GDG_DEV void stage_poweramp(gdg_ctx &cx, const gdg_unit_desc &d_global, const do
     GDG_REGA(double, buf, 32);
     /* pack: block j -> complex points (x[j ns + 2c], x[j ns + 2c + 1]), c < ns/2, zero padded to M; through
      * registers because the destination overlays the source.  Also fetch twiddles and the overlap tail. */
+    constexpr int PER_MAX = GDG_MAX_N / GDG_NT;                  /* static trip counts keep buf[] in registers */
     GDG_THREADS_BEGIN
-        for (int r = 0; r < per; r++) {
+#pragma unroll
+        for (int r = 0; r < PER_MAX; r++) {
             const int g = tid + r * GDG_NT;
             double re = 0.0, im = 0.0;
             if (g < total) {
@@ -758,7 +757,8 @@ GDG_DEV void stage_poweramp(gdg_ctx &cx, const gdg_unit_desc &d_global, const do
         for (int q = tid; q < ns; q += GDG_NT) tl[q] = q < F - zlen ? GDG_LDST(tail + q) : 0.0;
     GDG_THREADS_END
     GDG_THREADS_BEGIN
-        for (int r = 0; r < per; r++) {
+#pragma unroll
+        for (int r = 0; r < PER_MAX; r++) {
             const int g = tid + r * GDG_NT;
             if (g < total) { gdg_c2 v; v.re = R(buf)[2 * r]; v.im = R(buf)[2 * r + 1]; cst(D, cz(g), v); }
         }
@@ -831,18 +831,19 @@ GDG_DEV void stage_poweramp(gdg_ctx &cx, const gdg_unit_desc &d_global, const do
 #define GDG_YR(j, r) D[2 * cz((j) * M + ((r) >> 1)) + ((r) & 1)]
     const double scale = 1.0 / (double)M;
     const int per_out = (n + GDG_NT - 1) / GDG_NT;               /* <= 16 */
-    /* overlap-add + clamp into registers; running tail staged in place (filter.go:473-503): for nb >= 2 the
+    /* overlap-add + clamp, staged in S (the output buffer overlays the FFT workspace); running tail staged in place (filter.go:473-503): for nb >= 2 the
      * tail beyond ns is zero after the first block, so only the single-block case adds the old tail there.
      * Cells of tail[] known to be zero (the zero-run word) are neither read nor rewritten. */
     GDG_THREADS_BEGIN
-        for (int r = 0; r < per_out; r++) {
+#pragma unroll
+        for (int r = 0; r < PER_MAX; r++) {
             const int k = tid + r * GDG_NT;
             if (k < n) {
                 const int j = k / ns, q = k - j * ns;
                 double pre = scale * GDG_YR(j, q);
                 if (j == 0) pre += tl[q];
                 else { pre += scale * GDG_YR(j - 1, ns + q); if (j == 1 && ns + q < F - zlen) pre += tail[ns + q]; }
-                R(buf)[r] = clamp1(pre);
+                tl[k] = clamp1(pre);                                 /* staged in S: cell k is read (j == 0) and written by this thread only */
             }
         }
 #pragma unroll 1
@@ -859,7 +860,8 @@ GDG_DEV void stage_poweramp(gdg_ctx &cx, const gdg_unit_desc &d_global, const do
         for (int q = F - ns + tid; q < F - zlen; q += GDG_NT) tail[q] = 0.0;
         if (tid == 0) { st_seti(tail, F, ns); if (K > 1) st_seti(tail, F + 1, (slot + 1) % K); }
         double *out = SM_CUR(cx);
-        for (int r = 0; r < per_out; r++) { const int k = tid + r * GDG_NT; if (k < n) out[sw(k)] = R(buf)[r]; }
+#pragma unroll
+        for (int r = 0; r < PER_MAX; r++) { const int k = tid + r * GDG_NT; if (k < n) out[sw(k)] = tl[k]; }
     GDG_THREADS_END
 #undef GDG_YR
 }
