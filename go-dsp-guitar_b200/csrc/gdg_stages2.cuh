@@ -178,7 +178,7 @@ template <int F>
 GDG_DEV void oversampled_tiles(gdg_ctx &cx, const gdg_unit_desc &d_global)
 {
     const gdg_unit_desc &d = GDG_DESC; (void)d_global;
-    constexpr int RR = 2 * F;                   /* outputs per thread group; F lanes (one per phase) share a group */
+    constexpr int RR = (2 * F * 512) / GDG_NT;  /* outputs per thread: GDG_NT / F threads of one phase cover a tile of GDG_OS_TILE outputs */
     const int n = cx.n, type = d.type;
     double *x = SM_CUR(cx), *y = SM_ALT(cx), *z = SM_S, *st = d.st;
     double *uph = st + (F == 2 ? GDG_OS_ST_UP2 : GDG_OS_ST_UP4);
