@@ -40,7 +40,7 @@
 #if defined(__CUDACC__) && !defined(GDG_HOST_EMU)
 #define GDG_DEV __device__ __noinline__
 #define GDG_DEVI __device__ __forceinline__
-#define GDG_THREADS_BEGIN { const int tid = (int)threadIdx.x;
+#define GDG_THREADS_BEGIN { const int tid = (int)threadIdx.x; (void)tid;
 #define GDG_THREADS_END } __syncthreads();
 #define GDG_THREADS_END_NOSYNC }
 #define GDG_CONST __constant__

@@ -723,7 +723,6 @@ GDG_DEV void stage_poweramp(gdg_ctx &cx, const gdg_unit_desc &d_global, const do
     const int nb = n <= B ? 1 : n / B;                           /* n and B are powers of two */
     const int ns = n <= B ? n : B;                               /* samples per block */
     const int total = nb * M;                                    /* complex points in flight (<= GDG_MAX_N) */
-    const int per = (total + GDG_NT - 1) / GDG_NT;               /* <= 16 */
     double *D = SM_R, *tail = d.st;
     const double *tws = SM_TWS;                                  /* 1024 complex: exp(-2 pi i k / 8192), loaded by run_chain */
     double *wc = SM_SCANA, *wf = SM_SCANA + 130;                 /* W_F^(64 a), a <= 64 and W_F^b, b < 64 for the split */
@@ -830,7 +829,6 @@ GDG_DEV void stage_poweramp(gdg_ctx &cx, const gdg_unit_desc &d_global, const do
     /* real sample r of block j = component (r & 1) of complex point r >> 1 */
 #define GDG_YR(j, r) D[2 * cz((j) * M + ((r) >> 1)) + ((r) & 1)]
     const double scale = 1.0 / (double)M;
-    const int per_out = (n + GDG_NT - 1) / GDG_NT;               /* <= 16 */
     /* overlap-add + clamp, staged in S (the output buffer overlays the FFT workspace); running tail staged in place (filter.go:473-503): for nb >= 2 the
      * tail beyond ns is zero after the first block, so only the single-block case adds the old tail there.
      * Cells of tail[] known to be zero (the zero-run word) are neither read nor rewritten. */
