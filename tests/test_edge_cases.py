@@ -111,3 +111,29 @@ def test_length_mismatch_and_null_arguments(lib):
     assert lib.gdg_process_batch(None, 0, None, None, 64, 48000) < 0
     assert lib.gdg_chain_set_bypass(None, 0, 1) < 0
     assert b"NULL" in lib.gdg_last_error()
+
+
+SIGNALS = ["silence", "dc_full_scale", "overdriven_square", "impulse", "denormal", "nyquist", "step_after_silence"]
+
+
+@pytest.mark.parametrize("kind", SIGNALS)
+def test_extreme_finite_signals(lib, kind):
+    """Signals at the edges of the float64 sample range (the reference clamps to [-1, 1] in most units and never checks
+    its input): silence, DC at full scale, a square wave five times over full scale, one impulse, denormals, the Nyquist
+    tone, and silence followed by a step - through every unit type in one chain and through CHAIN12's oversampled core."""
+    fs, n, blocks = 96000, 2048, 5
+    t = np.arange(blocks * n)
+    x = {"silence": np.zeros(blocks * n),
+         "dc_full_scale": np.ones(blocks * n),
+         "overdriven_square": 5.0 * np.sign(np.sin(2 * np.pi * 997.0 * t / fs) + 1e-12),
+         "impulse": (t == 3 * n // 2).astype(np.float64),
+         "denormal": 1e-310 * np.sign(np.sin(2 * np.pi * 440.0 * t / fs) + 1e-12),
+         "nyquist": np.where(t % 2 == 0, 1.0, -1.0) * 0.9,
+         "step_after_silence": (t >= 2 * n + 17).astype(np.float64) * -0.75}[kind]
+    banks = common.make_banks(lib)
+    a, b = common.make_chain_pair(lib, MIXED, banks, ir_name="Guitar: British Vintage (Neutral)")
+    common.compare_stream(a, b, x, n, fs, label=kind)
+    every = [(u, {}, ({"oversampling": "2"} if u in ("excess", "fuzz", "overdrive", "distortion") else {})) for u in gdg.UNIT_TYPES]
+    every[19] = ("power_amp", {}, {"filter_order": "2048", "filter_1": "Guitar: British Modern (Center)"})
+    a, b = common.make_chain_pair(lib, every, banks)
+    common.compare_stream(a, b, x, n, fs, label=kind + "/all21")
