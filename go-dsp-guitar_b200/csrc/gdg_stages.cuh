@@ -48,6 +48,13 @@
 /* coherent load from GLOBAL memory (unit state): tells the compiler the address space, so that the loads can be
  * hoisted over shared-memory stores and batched */
 #define GDG_LDST(p) __ldcg(p)
+/* 8-byte global -> shared copy that does not pass through registers (LDGSTS): the issuing thread does not wait for it
+ * until async_wait(); a thread only ever reads back cells it requested itself, so no barrier is involved */
+static __device__ __forceinline__ void async_copy8(double *smem_dst, const double *gsrc)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+static __device__ __forceinline__ void async_wait() { asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory"); }
 /* thread-private value that stays in a register across phases */
 #define GDG_REG(type, name) type name
 #define GDG_REGA(type, name, cnt) type name[cnt]
@@ -61,6 +68,8 @@
 #define GDG_CONST static
 #define GDG_LDG(p) (*(p))
 #define GDG_LDST(p) (*(p))
+static inline void async_copy8(double *dst, const double *src) { *dst = *src; }
+static inline void async_wait() {}
 /* host emulation: one slot per emulated thread */
 #define GDG_REG(type, name) type name##_r[GDG_NT]
 #define GDG_REGA(type, name, cnt) type name##_r[GDG_NT][cnt]

@@ -734,34 +734,29 @@ GDG_DEV void stage_poweramp(gdg_ctx &cx, const gdg_unit_desc &d_global, const do
     const int slot = K > 1 ? (int)st_geti(tail, F + 1) : 0;
     const long hstride = 2L * (M + 1);
     const int fstep = GDG_MAX_FFT / F;                           /* W_F^k = tw[k * MAXFFT/F] */
-    GDG_REGA(double, buf, 32);
-    /* pack: block j -> complex points (x[j ns + 2c], x[j ns + 2c + 1]), c < ns/2, zero padded to M; through
-     * registers because the destination overlays the source.  Also fetch twiddles and the overlap tail. */
-    constexpr int PER_MAX = GDG_MAX_N / GDG_NT;                  /* static trip counts keep buf[] in registers */
+    /* pack: block j -> complex points (x[j ns + 2c], x[j ns + 2c + 1]), c < ns/2, zero padded to M.  The destination
+     * overlays the source, so the block first moves to S in plain order; the split twiddles are set up on the way. */
     GDG_THREADS_BEGIN
-#pragma unroll
-        for (int r = 0; r < PER_MAX; r++) {
-            const int g = tid + r * GDG_NT;
-            double re = 0.0, im = 0.0;
-            if (g < total) {
-                const int j = g >> logM, c = g & (M - 1);
-                if (2 * c < ns) { re = x[sw(j * ns + 2 * c)]; im = (2 * c + 1 < ns) ? x[sw(j * ns + 2 * c + 1)] : 0.0; }
-            }
-            R(buf)[2 * r] = re; R(buf)[2 * r + 1] = im;
-        }
+#pragma unroll 4
+        for (int k = tid; k < n; k += GDG_NT) tl[k] = x[sw(k)];
         if (tid < 65) cst(wc, tid, tw_full(tw, imin(64 * tid * fstep, GDG_MAX_FFT - 1) ));
         if (tid >= 128 && tid < 192) cst(wf, tid - 128, twd(tw, (tid - 128) * fstep));
-        /* overlap cells [0, ns) are always needed: fetch them now, hidden behind the transform */
-#pragma unroll 4
-        for (int q = tid; q < ns; q += GDG_NT) tl[q] = q < F - zlen ? GDG_LDST(tail + q) : 0.0;
     GDG_THREADS_END
     GDG_THREADS_BEGIN
-#pragma unroll
-        for (int r = 0; r < PER_MAX; r++) {
-            const int g = tid + r * GDG_NT;
-            if (g < total) { gdg_c2 v; v.re = R(buf)[2 * r]; v.im = R(buf)[2 * r + 1]; cst(D, cz(g), v); }
+#pragma unroll 2
+        for (int g = tid; g < total; g += GDG_NT) {
+            const int j = g >> logM, c = g & (M - 1);
+            gdg_c2 v; v.re = 0.0; v.im = 0.0;
+            if (2 * c < ns) { v.re = tl[j * ns + 2 * c]; v.im = (2 * c + 1 < ns) ? tl[j * ns + 2 * c + 1] : 0.0; }
+            cst(D, cz(g), v);
         }
     GDG_THREADS_END
+    /* overlap cells [0, ns) of the tail are needed after the inverse transform: request them now (asynchronous copies
+     * straight into S, no thread waits here); cells known to be zero are not read */
+    GDG_THREADS_BEGIN
+#pragma unroll 4
+        for (int q = tid; q < ns; q += GDG_NT) { if (q < F - zlen) async_copy8(tl + q, tail + q); else tl[q] = 0.0; }
+    GDG_THREADS_END_NOSYNC
     fft_forward(cx, D, tws, logM, nb);
     /* split (fft.go:801-818) * H (filter.go:459) * inverse split (fft.go:899-955), on bit-reversed storage */
     GDG_THREADS_BEGIN
@@ -833,10 +828,10 @@ GDG_DEV void stage_poweramp(gdg_ctx &cx, const gdg_unit_desc &d_global, const do
      * tail beyond ns is zero after the first block, so only the single-block case adds the old tail there.
      * Cells of tail[] known to be zero (the zero-run word) are neither read nor rewritten. */
     GDG_THREADS_BEGIN
-#pragma unroll
-        for (int r = 0; r < PER_MAX; r++) {
-            const int k = tid + r * GDG_NT;
-            if (k < n) {
+        async_wait();                                            /* this thread's tail cells are in S now */
+#pragma unroll 2
+        for (int k = tid; k < n; k += GDG_NT) {
+            {
                 const int j = k / ns, q = k - j * ns;
                 double pre = scale * GDG_YR(j, q);
                 if (j == 0) pre += tl[q];
@@ -858,8 +853,8 @@ GDG_DEV void stage_poweramp(gdg_ctx &cx, const gdg_unit_desc &d_global, const do
         for (int q = F - ns + tid; q < F - zlen; q += GDG_NT) tail[q] = 0.0;
         if (tid == 0) { st_seti(tail, F, ns); if (K > 1) st_seti(tail, F + 1, (slot + 1) % K); }
         double *out = SM_CUR(cx);
-#pragma unroll
-        for (int r = 0; r < PER_MAX; r++) { const int k = tid + r * GDG_NT; if (k < n) out[sw(k)] = tl[k]; }
+#pragma unroll 4
+        for (int k = tid; k < n; k += GDG_NT) out[sw(k)] = tl[k];
     GDG_THREADS_END
 #undef GDG_YR
 }
