@@ -137,3 +137,28 @@ def test_extreme_finite_signals(lib, kind):
     every[19] = ("power_amp", {}, {"filter_order": "2048", "filter_1": "Guitar: British Modern (Center)"})
     a, b = common.make_chain_pair(lib, every, banks)
     common.compare_stream(a, b, x, n, fs, label=kind + "/all21")
+
+
+def test_chain_longer_than_one_fused_segment(lib):
+    """The chain kernel fuses up to 24 active units per launch; signal.Chain has no length limit (signal.go:64-86), so a
+    longer chain runs as consecutive segments with the block round-tripping through HBM between them - same result, and
+    a batch may mix short and long chains.  Encoded payloads are limited to one segment and say so."""
+    fs, n = 96000, 2048
+    unit_cycle = ["tone_stack", "delay", "compressor", "tremolo", "bandpass", "overdrive", "chorus", "noise_gate", "reverb", "cabinet"]
+    long_spec = [(unit_cycle[k % len(unit_cycle)], ({"delay_time": 3 + k} if unit_cycle[k % len(unit_cycle)] == "delay" else {}), {}) for k in range(53)]
+    short_spec = long_spec[:5]
+    pairs = [common.make_chain_pair(lib, long_spec), common.make_chain_pair(lib, short_spec), common.make_chain_pair(lib, long_spec[:25])]
+    x = np.stack([common.synth_fast(c, fs, 3 * n, 5) for c in range(3)])
+    for k in range(3):
+        blk = x[:, k * n:(k + 1) * n]
+        ref = np.stack([p[0].process(blk[c], fs) for c, p in enumerate(pairs)])
+        got = gdg.process_batch([p[1] for p in pairs], blk, fs)
+        for c in range(3):
+            assert common.rms(ref[c] - got[c]) <= common.TOL_RMS, (k, c)
+    # a bypassed unit does not count towards the segment length
+    for i in range(25, 53):
+        pairs[0][0].set_bypass(i, True); pairs[0][1].set_bypass(i, True)
+    blk = x[0, :n]
+    assert common.rms(pairs[0][0].process(blk, fs) - pairs[0][1].process(blk, fs)) <= common.TOL_RMS
+    with pytest.raises(gdg.GdgError, match="segment"):
+        gdg.process_batch_encoded([pairs[2][1]], [np.zeros(n, dtype="<i2").tobytes()], "PCM16", "PCM16", n, fs)
