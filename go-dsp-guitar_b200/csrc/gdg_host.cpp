@@ -1516,6 +1516,23 @@ int gdg_process_batch_encoded(gdg_chain *const *chains, size_t C, const void *co
     if (check_block(n)) return -1;
     return host_block(chains, C, nullptr, -1, nullptr, nullptr, in, in_format, out, out_format, C, n, rate);
 }
+/* the same without waiting: ticket for gdg_controller_wait (two blocks in flight, like gdg_controller_submit) */
+int gdg_process_batch_encoded_submit(gdg_chain *const *chains, size_t C, const void *const *in, int in_format, void *const *out,
+                                     int out_format, size_t n, uint32_t rate)
+{
+    if (ensure_init()) return -1;
+    if (!chains || !C || !in || !out) return fail("gdg_process_batch_encoded_submit: bad argument");
+    if (!fmt_bytes(in_format) || !fmt_bytes(out_format)) return fail("Unknown sample format: %#04x", fmt_bytes(in_format) ? out_format : in_format);
+    if (check_block(n)) return -1;
+    std::lock_guard<std::mutex> lk(g_batch_mutex);
+    const int si = free_slot();
+    if (si < 0) return fail("two submitted blocks are in flight: gdg_controller_wait() for one first");
+    if (block_submit(si, chains, C, nullptr, -1, nullptr, nullptr, in, in_format, out, out_format, C, n, rate)) {
+        if (g_batch) { gdgb_sync(); g_batch->slot[si].busy = false; }
+        return -1;
+    }
+    return si;
+}
 int gdg_process_batch_device_encoded(gdg_chain *const *chains, size_t C, const void *d_in, int in_format, size_t in_stride_bytes,
                                      void *d_out, int out_format, size_t out_stride_bytes, size_t n, uint32_t rate, void *stream)
 {

@@ -133,6 +133,9 @@ size_t gdg_format_bytes_per_sample(int format);
  * (controller/controller.go:2908-3143) for one block; chains of at most one fused segment (24 active units). */
 int gdg_process_batch_encoded(gdg_chain *const *chains, size_t channels, const void *const *in, int in_format,
                               void *const *out, int out_format, size_t n, uint32_t sample_rate);
+/* the same block submitted without waiting: returns a ticket for gdg_controller_wait() (see gdg_controller_submit below) */
+int gdg_process_batch_encoded_submit(gdg_chain *const *chains, size_t channels, const void *const *in, int in_format,
+                                     void *const *out, int out_format, size_t n, uint32_t sample_rate);
 int gdg_process_batch_device_encoded(gdg_chain *const *chains, size_t channels, const void *d_in, int in_format, size_t in_stride_bytes,
                                      void *d_out, int out_format, size_t out_stride_bytes, size_t n, uint32_t sample_rate, void *stream);
 /* resample.Time (resample/resample.go:72-103): the batch path's input rate conversion (controller.go:2991-3003).

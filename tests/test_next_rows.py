@@ -281,3 +281,29 @@ def test_controller_submit_wait_pipeline_matches_sequential(lib):
         gdg.controller_process(list(gc), None, -1, gs, xin[2], fs)
     gdg.controller_wait(t0, lib); gdg.controller_wait(t1, lib)
     assert gdg.controller_process(list(gc), None, -1, gs, xin[2], fs).shape == (C + 2, n)
+
+
+def test_encoded_submit_wait(lib):
+    """gdg_process_batch_encoded_submit: PCM16 blocks with two in flight give the bytes of the blocking call."""
+    import ctypes as Ct
+    fs, n, C, blocks = 48000, 1024, 3, 4
+    spec = [("overdrive", {"gain": 9}, {"oversampling": "2"}), ("tone_stack", {}, {}), ("delay", {"delay_time": 5}, {})]
+    ref_chains = [common.make_chain_pair(lib, spec)[1] for _ in range(C)]
+    chains = [common.make_chain_pair(lib, spec)[1] for _ in range(C)]
+    x = [(np.stack([common.synth_fast(c, fs, blocks * n, 7)[k * n:(k + 1) * n] for c in range(C)]) * 20000).astype("<i2") for k in range(blocks)]
+    want = [gdg.process_batch_encoded(ref_chains, [r.tobytes() for r in x[k]], "PCM16", "PCM16", n, fs) for k in range(blocks)]
+    outs = [np.zeros((C, n), dtype="<i2") for _ in range(blocks)]
+    handles = (Ct.c_void_p * C)(*[c._h for c in chains])
+    tickets = []
+    for k in range(blocks):
+        ip = (Ct.c_void_p * C)(*[x[k][c].ctypes.data for c in range(C)])
+        op = (Ct.c_void_p * C)(*[outs[k][c].ctypes.data for c in range(C)])
+        t = lib.gdg_process_batch_encoded_submit(handles, C, ip, 1, op, 1, n, fs)
+        assert t >= 0, lib.gdg_last_error()
+        tickets.append(t)
+        if k >= 1:
+            assert lib.gdg_controller_wait(tickets[k - 1]) == 0
+    assert lib.gdg_controller_wait(tickets[-1]) == 0
+    for k in range(blocks):
+        for c in range(C):
+            assert outs[k][c].tobytes() == bytes(want[k][c]), (k, c)
