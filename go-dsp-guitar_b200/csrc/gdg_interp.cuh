@@ -235,9 +235,9 @@ GDG_DEV void run_chain(double *smem, const gdg_chain_desc *cd, const void *in, i
 #else
     (void)smem;
 #endif
-    gdg_ctx &cx = *(gdg_ctx *)(gdg_smem + GDG_SMEM_CTX);        /* every thread writes the same three words */
-    ctx_init(cx, n);
+    gdg_ctx &cx = *(gdg_ctx *)(gdg_smem + GDG_SMEM_CTX);
     GDG_THREADS_BEGIN
+        if (tid == 0) ctx_init(cx, n);
     GDG_THREADS_END
     GDG_THREADS_BEGIN
         if (in_fmt == GDG_FMT_IEEE64) { for (int k = tid; k < n; k += GDG_NT) SM_CUR(cx)[sw(k)] = ((const double *)in)[k]; }

@@ -845,8 +845,8 @@ GDG_DEV void stage_poweramp(gdg_ctx &cx, const gdg_unit_desc &d_global, const do
             if (nb == 1 && ns + q < F - zlen) v += tail[ns + q];
             GDG_YR(nb - 1, ns + q) = v;
         }
+        if (tid == 0) { cx.cur_off = GDG_SMEM_R; cx.alt_off = GDG_SMEM_R + GDG_MAX_N; }   /* the output goes to the first half of R */
     GDG_THREADS_END
-    cx.cur_off = GDG_SMEM_R; cx.alt_off = GDG_SMEM_R + GDG_MAX_N;
     GDG_THREADS_BEGIN
 #pragma unroll 1
         for (int q = tid; q < F - ns; q += GDG_NT) tail[q] = GDG_YR(nb - 1, ns + q);
