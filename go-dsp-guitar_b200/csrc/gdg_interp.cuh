@@ -235,28 +235,15 @@ GDG_DEV void run_chain(double *smem, const gdg_chain_desc *cd, const void *in, i
 #else
     (void)smem;
 #endif
-    gdg_ctx &cx = *(gdg_ctx *)(gdg_smem + GDG_SMEM_CTX);
-    GDG_THREADS_BEGIN
-        if (tid == 0) ctx_init(cx, n);
-    GDG_THREADS_END
-#if defined(__CUDACC__) && !defined(GDG_HOST_EMU)
     /* float64 rows come in as ONE bulk asynchronous copy (TMA, cp.async.bulk -> UBLKCP) into S, signalled through an
      * mbarrier, while the threads fetch the twiddles and the chain descriptor; then S is folded into the swizzled block
      * layout.  Needs 16-byte aligned rows of a multiple of 16 bytes; anything else takes the per-thread loop. */
-    const bool bulk_in = in_fmt == GDG_FMT_IEEE64 && ((n * 8) % 16) == 0 && (((unsigned long long)in) & 15ull) == 0;
-    const unsigned mbar = (unsigned)__cvta_generic_to_shared(SM_MISC + 32);
-    if (bulk_in) {
-        if (threadIdx.x == 0) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(mbar));
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mbar), "r"((unsigned)(n * 8)) : "memory");
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         :: "r"((unsigned)__cvta_generic_to_shared(SM_S)), "l"(in), "r"((unsigned)(n * 8)), "r"(mbar) : "memory");
-        }
-    }
-#else
-    const bool bulk_in = false;
-#endif
+    const bool bulk_in = GDG_HAVE_BULK && in_fmt == GDG_FMT_IEEE64 && ((n * 8) % 16) == 0 && (((unsigned long long)in) & 15ull) == 0;
+    double *mbar = SM_MISC + 32;
+    gdg_ctx &cx = *(gdg_ctx *)(gdg_smem + GDG_SMEM_CTX);
+    GDG_THREADS_BEGIN
+        if (tid == 0) { ctx_init(cx, n); if (bulk_in) bulk_load(mbar, SM_S, in, (unsigned)(n * 8)); }
+    GDG_THREADS_END
     GDG_THREADS_BEGIN
         if (!bulk_in) {
             if (in_fmt == GDG_FMT_IEEE64) { for (int k = tid; k < n; k += GDG_NT) SM_CUR(cx)[sw(k)] = ((const double *)in)[k]; }
@@ -265,13 +252,11 @@ GDG_DEV void run_chain(double *smem, const gdg_chain_desc *cd, const void *in, i
         for (int k = tid; k < GDG_MAX_N / 8; k += GDG_NT) { SM_TWS[2 * k] = GDG_LDG(tw + 4 * k); SM_TWS[2 * k + 1] = GDG_LDG(tw + 4 * k + 1); }   /* exp(-2 pi i k / 8192) */
         /* the chain descriptor rides along with the input load: no global round trip between units */
         for (int k = tid; k < (int)(sizeof(gdg_chain_desc) / 4); k += GDG_NT) ((int *)(gdg_smem + GDG_SMEM_CHAIN))[k] = ((const int *)cd)[k];
-#if defined(__CUDACC__) && !defined(GDG_HOST_EMU)
         if (bulk_in) {
-            asm volatile("{\n\t.reg .pred p;\n\tGDG_WAIT_IN:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t@!p bra GDG_WAIT_IN;\n\t}" :: "r"(mbar) : "memory");
+            bulk_wait(mbar);
 #pragma unroll 4
             for (int k = tid; k < n; k += GDG_NT) SM_CUR(cx)[sw(k)] = SM_S[k];
         }
-#endif
     GDG_THREADS_END
     const gdg_chain_desc *scd = (const gdg_chain_desc *)(gdg_smem + GDG_SMEM_CHAIN);
     const int ns = scd->nslots;

@@ -55,6 +55,24 @@ static __device__ __forceinline__ void async_copy8(double *smem_dst, const doubl
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
 }
 static __device__ __forceinline__ void async_wait() { asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory"); }
+/* Bulk asynchronous copy global -> shared (TMA engine, UBLKCP) signalled through an mbarrier word in shared memory.
+ * ONE thread calls bulk_load(); a __syncthreads() must separate that call from the first bulk_wait() of any other
+ * thread (the barrier word is initialised by the issuing thread).  src, dst and bytes are multiples of 16. */
+static __device__ __forceinline__ void bulk_load(double *mbar_word, double *smem_dst, const void *gsrc, unsigned bytes)
+{
+    const unsigned mbar = (unsigned)__cvta_generic_to_shared(mbar_word);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(mbar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mbar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc), "r"(bytes), "r"(mbar) : "memory");
+}
+static __device__ __forceinline__ void bulk_wait(double *mbar_word)
+{
+    const unsigned mbar = (unsigned)__cvta_generic_to_shared(mbar_word);
+    asm volatile("{\n\t.reg .pred p;\n\tGDG_BULK_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t@!p bra GDG_BULK_WAIT;\n\t}" :: "r"(mbar) : "memory");
+}
+#define GDG_HAVE_BULK 1
 /* thread-private value that stays in a register across phases */
 #define GDG_REG(type, name) type name
 #define GDG_REGA(type, name, cnt) type name[cnt]
@@ -70,6 +88,9 @@ static __device__ __forceinline__ void async_wait() { asm volatile("cp.async.com
 #define GDG_LDST(p) (*(p))
 static inline void async_copy8(double *dst, const double *src) { *dst = *src; }
 static inline void async_wait() {}
+static inline void bulk_load(double *, double *dst, const void *src, unsigned bytes) { memcpy(dst, src, bytes); }
+static inline void bulk_wait(double *) {}
+#define GDG_HAVE_BULK 0
 /* host emulation: one slot per emulated thread */
 #define GDG_REG(type, name) type name##_r[GDG_NT]
 #define GDG_REGA(type, name, cnt) type name##_r[GDG_NT][cnt]

@@ -751,11 +751,19 @@ GDG_DEV void stage_poweramp(gdg_ctx &cx, const gdg_unit_desc &d_global, const do
             cst(D, cz(g), v);
         }
     GDG_THREADS_END
-    /* overlap cells [0, ns) of the tail are needed after the inverse transform: request them now (asynchronous copies
-     * straight into S, no thread waits here); cells known to be zero are not read */
+    /* overlap cells [0, ns) of the tail are needed after the inverse transform: request them now - one bulk asynchronous
+     * copy straight into S (nobody waits here; the transform's barriers separate this from the wait below); cells known
+     * to be zero are not read */
+    const int tl_live = imax(0, imin(ns, F - zlen));            /* cells of tail[0, ns) that may be non-zero */
+    const bool tl_bulk = GDG_HAVE_BULK && tl_live > 0 && (tl_live & 1) == 0;
+    double *mbar = SM_MISC + 32;
     GDG_THREADS_BEGIN
+        if (tl_bulk) { if (tid == 0) bulk_load(mbar, tl, tail, (unsigned)(tl_live * 8)); }
+        else {
 #pragma unroll 4
-        for (int q = tid; q < ns; q += GDG_NT) { if (q < F - zlen) async_copy8(tl + q, tail + q); else tl[q] = 0.0; }
+            for (int q = tid; q < tl_live; q += GDG_NT) async_copy8(tl + q, tail + q);
+        }
+        for (int q = tl_live + tid; q < ns; q += GDG_NT) tl[q] = 0.0;
     GDG_THREADS_END_NOSYNC
     fft_forward(cx, D, tws, logM, nb);
     /* split (fft.go:801-818) * H (filter.go:459) * inverse split (fft.go:899-955), on bit-reversed storage */
@@ -828,7 +836,7 @@ GDG_DEV void stage_poweramp(gdg_ctx &cx, const gdg_unit_desc &d_global, const do
      * tail beyond ns is zero after the first block, so only the single-block case adds the old tail there.
      * Cells of tail[] known to be zero (the zero-run word) are neither read nor rewritten. */
     GDG_THREADS_BEGIN
-        async_wait();                                            /* this thread's tail cells are in S now */
+        if (tl_bulk) bulk_wait(mbar); else async_wait();           /* the tail cells are in S now */
 #pragma unroll 2
         for (int k = tid; k < n; k += GDG_NT) {
             {
