@@ -235,14 +235,15 @@ GDG_DEV void run_chain(double *smem, const gdg_chain_desc *cd, const void *in, i
 #else
     (void)smem;
 #endif
-    /* float64 rows come in as ONE bulk asynchronous copy (TMA, cp.async.bulk -> UBLKCP) into S, signalled through an
+    /* input rows (float64 or an encoded payload) come in as ONE bulk asynchronous copy (TMA, cp.async.bulk -> UBLKCP) into S, signalled through an
      * mbarrier, while the threads fetch the twiddles and the chain descriptor; then S is folded into the swizzled block
      * layout.  Needs 16-byte aligned rows of a multiple of 16 bytes; anything else takes the per-thread loop. */
-    const bool bulk_in = GDG_HAVE_BULK && in_fmt == GDG_FMT_IEEE64 && ((n * 8) % 16) == 0 && (((unsigned long long)in) & 15ull) == 0;
+    const unsigned in_bytes = (unsigned)(n * fmt_bytes(in_fmt));
+    const bool bulk_in = GDG_HAVE_BULK && (in_bytes % 16) == 0 && (((unsigned long long)in) & 15ull) == 0;
     double *mbar = SM_MISC + 32;
     gdg_ctx &cx = *(gdg_ctx *)(gdg_smem + GDG_SMEM_CTX);
     GDG_THREADS_BEGIN
-        if (tid == 0) { ctx_init(cx, n); if (bulk_in) bulk_load(mbar, SM_S, in, (unsigned)(n * 8)); }
+        if (tid == 0) { ctx_init(cx, n); if (bulk_in) bulk_load(mbar, SM_S, in, in_bytes); }
     GDG_THREADS_END
     GDG_THREADS_BEGIN
         if (!bulk_in) {
@@ -254,8 +255,13 @@ GDG_DEV void run_chain(double *smem, const gdg_chain_desc *cd, const void *in, i
         for (int k = tid; k < (int)(sizeof(gdg_chain_desc) / 4); k += GDG_NT) ((int *)(gdg_smem + GDG_SMEM_CHAIN))[k] = ((const int *)cd)[k];
         if (bulk_in) {
             bulk_wait(mbar);
+            if (in_fmt == GDG_FMT_IEEE64) {
 #pragma unroll 4
-            for (int k = tid; k < n; k += GDG_NT) SM_CUR(cx)[sw(k)] = SM_S[k];
+                for (int k = tid; k < n; k += GDG_NT) SM_CUR(cx)[sw(k)] = SM_S[k];
+            } else {                                               /* encoded payload: decode out of shared memory */
+#pragma unroll 4
+                for (int k = tid; k < n; k += GDG_NT) SM_CUR(cx)[sw(k)] = decode_sample(in_fmt, (const unsigned char *)SM_S, k);
+            }
         }
     GDG_THREADS_END
     const gdg_chain_desc *scd = (const gdg_chain_desc *)(gdg_smem + GDG_SMEM_CHAIN);
