@@ -346,3 +346,24 @@ def test_controller_process_config4(lib):
         for c in range(C + 2):
             assert common.rms(ya[c] - yb[c]) <= common.TOL_RMS, (k, c)
     assert ta.analyze()["note"] == tb.analyze()["note"]
+
+
+@pytest.mark.parametrize("unit", [u for u in gdg.UNIT_TYPES if u != "power_amp"])
+def test_parameter_extremes(lib, unit):
+    """Each numeric parameter at its minimum and at its maximum (others default), each discrete parameter at each of its
+    values: the ranges the reference's setters accept (effects.go:287-320) all reach the kernels."""
+    fs, n = 96000, 2048
+    probe = gdg.Chain(lib=lib)
+    i = probe.append_unit(unit)
+    params = probe.parameters(i)
+    x = common.synth_fast(11, fs, 3 * n) * 1.2
+    variants = []
+    for p in params:
+        if p["DiscreteValues"]:
+            variants += [({}, {p["Name"]: v}) for v in p["DiscreteValues"]]
+        else:
+            variants += [({p["Name"]: p["Minimum"]}, {}), ({p["Name"]: p["Maximum"]}, {})]
+    assert variants
+    for numeric, discrete in variants:
+        a, b = common.make_chain_pair(lib, [(unit, numeric, discrete)])
+        common.compare_stream(a, b, x, n, fs, label="%s %s %s" % (unit, numeric, discrete))
