@@ -174,6 +174,19 @@ GDG_DEVI void os_produce(const gdg_unit_desc &d, int type, const double *x, cons
     }
 }
 
+/* finish a tile: y[t0 + i] = 0.944.. * clamp(sum of the f branch sums in branch order), i < cnt (oversampling.go:150-177) */
+template <int F>
+GDG_DEVI void os_combine(double *y, const double *part, int t0, int cnt, int tid)
+{
+#pragma unroll 1
+    for (int i = tid; i < cnt; i += GDG_NT) {
+        double acc = y[sw(t0 + i)];
+#pragma unroll
+        for (int p = 1; p < F; p++) acc += part[(p - 1) * GDG_OS_TILE + sw(i)];
+        y[sw(t0 + i)] = 0.9440608762859234 * clamp1(acc);
+    }
+}
+
 template <int F>
 GDG_DEV void oversampled_tiles(gdg_ctx &cx, const gdg_unit_desc &d_global)
 {
@@ -192,16 +205,19 @@ GDG_DEV void oversampled_tiles(gdg_ctx &cx, const gdg_unit_desc &d_global)
     GDG_THREADS_END
     for (int t0 = 0; t0 < n; t0 += T) {
         const int Tt = imin(T, n - t0);
-        /* up-sample (+ stateless nonlinearity): two base samples per thread for a full tile; the same phase lands the
-         * halo staged by the previous tile (cells m <= GDG_ZH; this tile writes cells m >= GDG_ZH, and (phase 0,
-         * m = GDG_ZH) is this tile's own sample, which the staging skips) */
+        /* up-sample (+ stateless nonlinearity): two base samples per thread for a full tile.  The same phase lands the
+         * halo stashed by the previous tile (cells m <= GDG_ZH; this tile writes cells m >= GDG_ZH, and (phase 0,
+         * m = GDG_ZH) is this tile's own sample, which the landing skips) and finishes the PREVIOUS tile: partial sums
+         * combined in phase order, clamp, -0.5 dB (its latency hides behind the up-sampling; one barrier fewer per tile) */
         GDG_THREADS_BEGIN
             if (t0 > 0 && tid < F * 64) { const int p = tid >> 6, m = tid & 63; if (m < GDG_ZH || (m == GDG_ZH && p > 0)) z[p * GDG_ZPS + pz(m)] = SM_SCANB[tid]; }
 #pragma unroll 1
             for (int jl = tid; jl < Tt; jl += GDG_NT) os_produce<F>(d, type, x, uph, z, t0 + jl, jl);
+            if (t0 > 0) os_combine<F>(y, part, t0 - T, T, tid);
         GDG_THREADS_END
         if (!stateless) fuzz_run<F>(cx, d, z, Tt);
-        /* polyphase FIR partial sums: warp w computes phase w % F (taps warp-uniform) of RR outputs per thread */
+        /* polyphase FIR partial sums: warp w computes phase w % F (taps warp-uniform) of RR outputs per thread; then the
+         * last GDG_ZH + 1 cells of every phase are stashed for the next tile (z is read-only in this phase) */
         GDG_THREADS_BEGIN
             const int warp = tid >> 5, p = warp % F;
             const int i0 = ((warp / F) * 32 + (tid & 31)) * RR;
@@ -219,21 +235,13 @@ GDG_DEV void oversampled_tiles(gdg_ctx &cx, const gdg_unit_desc &d_global)
                 for (int r = 0; r < RR; r++)
                     if (i0 + r < Tt) { if (p == 0) y[sw(t0 + i0 + r)] = acc[r]; else part[(p - 1) * GDG_OS_TILE + sw(i0 + r)] = acc[r]; }
             }
-        GDG_THREADS_END
-        /* combine in phase order, clamp, -0.5 dB; stage the halo (last GDG_ZH + 1 cells of every phase) for the next tile */
-        GDG_THREADS_BEGIN
-#pragma unroll 1
-            for (int i = tid; i < Tt; i += GDG_NT) {
-                double acc = y[sw(t0 + i)];
-#pragma unroll
-                for (int p = 1; p < F; p++) acc += part[(p - 1) * GDG_OS_TILE + sw(i)];
-                y[sw(t0 + i)] = 0.9440608762859234 * clamp1(acc);
-            }
-            if (t0 + Tt < n && tid < F * 64) { const int p = tid >> 6, m = tid & 63; if (m <= GDG_ZH) SM_SCANB[tid] = z[p * GDG_ZPS + pz(m + Tt)]; }
+            if (t0 + Tt < n && tid < F * 64) { const int pp = tid >> 6, m = tid & 63; if (m <= GDG_ZH) SM_SCANB[tid] = z[pp * GDG_ZPS + pz(m + Tt)]; }
         GDG_THREADS_END
         if (t0 + Tt >= n) {
-            /* carry: oversampled history (entries Tt .. Tt + GDG_ZH of the last tile) and the last 8 inputs (oversampling.go:91-93) */
+            /* last tile: finish it, and carry the oversampled history (entries Tt .. Tt + GDG_ZH) and the last 8 inputs
+             * (oversampling.go:91-93) */
             GDG_THREADS_BEGIN
+                os_combine<F>(y, part, t0, Tt, tid);
                 if (tid < F * 64) { const int p = tid >> 6, m = tid & 63; if (m <= GDG_ZH) zh[p * (GDG_ZH + 1) + m] = z[p * GDG_ZPS + pz(m + Tt)]; }
                 if (tid < 8) SM_MISC[8 + tid] = (n - 8 + tid) >= 0 ? x[sw(n - 8 + tid)] : uph[tid + n];
             GDG_THREADS_END
