@@ -382,6 +382,31 @@ def main():
     except Exception as e:                                        # never let an extra break the contract line
         extras["e2e_pcm16_payload"] = {"error": str(e)}
 
+    # ---- extra: the WHOLE controller step (tuner feed, chains, spatializer -> master) on PCM16 rows, two blocks in flight ----
+    try:
+        q_out = [torch.empty((C + 2, N), dtype=torch.int16).pin_memory() for _ in range(2)]
+        qo = [(Ct.c_void_p * (C + 2))(*[q_out[k].data_ptr() + 2 * N * c for c in range(C + 2)]) for k in range(2)]
+        qi = [pi, pi2]
+
+        def run_full_pcm(steps):
+            prev = None
+            for k in range(steps):
+                t = lib.gdg_controller_submit_encoded(handles, C, tun_h, tun_ch, spat._h, None, qi[k % 2], 1, qo[k % 2], 1, C + 2, N, FS)
+                if t < 0:
+                    raise RuntimeError(lib.gdg_last_error().decode())
+                if prev is not None and lib.gdg_controller_wait(prev) < 0:
+                    raise RuntimeError(lib.gdg_last_error().decode())
+                prev = t
+            if lib.gdg_controller_wait(prev) < 0:
+                raise RuntimeError(lib.gdg_last_error().decode())
+        run_full_pcm(2)
+        dtq = wall(lambda: run_full_pcm(args.steps))
+        extras["e2e_pcm16_controller"] = {"value": samples_per_step * args.steps / dtq / 1e6, "unit": "Msamples/s",
+                                          "api": "gdg_controller_submit_encoded / gdg_controller_wait (PCM16 rows in and out, tuner feed + chains + spatializer; this rank's partial master, no NCCL reduce)",
+                                          "h2d_bytes_per_step": 2 * C * N, "d2h_bytes_per_step": 2 * (C + 2) * N}
+    except Exception as e:
+        extras["e2e_pcm16_controller"] = {"error": str(e)}
+
     # ---- extra: the headline e2e call with the level meter of controller.go:2653-2781 fed on the device ----
     try:
         meter = gdg.Meter(2 * C + 3, lib=lib)

@@ -127,6 +127,7 @@ ABI = {
     "gdg_controller_process_metered": (_int, [_vp, _u32, _vp, _int, _vp, _vp, _vp, _vp, _u32, _sz, _u32]),
     "gdg_controller_submit": (_int, [_vp, _u32, _vp, _int, _vp, _vp, _vp, _vp, _u32, _sz, _u32]),
     "gdg_controller_wait": (_int, [_int]),
+    "gdg_controller_submit_encoded": (_int, [_vp, _u32, _vp, _int, _vp, _vp, _vp, _int, _vp, _int, _u32, _sz, _u32]),
     "gdg_process_batch_encoded_submit": (_int, [_vp, _sz, _vp, _int, _vp, _int, _sz, _u32]),
 }
 

@@ -53,6 +53,8 @@ int gdgb_launch_chains(const gdg_chain_desc *const *d_descs, int channels, const
 /* level meter (level/level.go:147-208): row c = d_in + c*stride (n samples) updates the 4-word state d_state + 4*c
  * {cur, peak, counter (int64), unused}; f = decay factor per sample, hold = peak hold time in samples */
 int gdgb_launch_meter(const double *d_in, long stride, int channels, long n, double f, long long hold, double *d_state, void *stream);
+/* planar rows from one sample format (GDG_FMT_*) to another: the wave.go codecs outside the chain kernel */
+int gdgb_convert_rows(const void *d_in, long in_stride_bytes, int in_fmt, void *d_out, long out_stride_bytes, int out_fmt, int rows, int n, void *stream);
 /* resample.Time on device: d_out[i], i < out_len */
 int gdgb_resample_time(const double *d_in, long n, double dx, double *d_out, long out_len, void *stream);
 

@@ -639,6 +639,7 @@ struct Batch {
      * block k is waited for; the synchronous entry points use whichever slot is free */
     struct Slot {
         double *d_in = nullptr, *d_out = nullptr; size_t cap = 0;    /* device staging for host-buffer calls */
+        double *d_enc_in = nullptr, *d_enc_out = nullptr; size_t enc_cap = 0;   /* encoded rows of the full controller path */
         double *h_stage = nullptr, *h_stage2 = nullptr; size_t h_cap = 0;   /* pinned staging (in / out) for pageable callers */
         bool busy = false;                                           /* submitted, not yet waited for */
         std::vector<std::pair<size_t, size_t>> staged;               /* output rows still in h_stage2 */
@@ -646,7 +647,7 @@ struct Batch {
     } slot[2];
     ~Batch() {
         for (auto p : d_ptrs) gdgb_free((void *)p);
-        for (auto &sl : slot) { if (sl.d_in) gdgb_free(sl.d_in); if (sl.d_out) gdgb_free(sl.d_out); if (sl.h_stage) gdgb_pinned_free(sl.h_stage); if (sl.h_stage2) gdgb_pinned_free(sl.h_stage2); }
+        for (auto &sl : slot) { if (sl.d_in) gdgb_free(sl.d_in); if (sl.d_out) gdgb_free(sl.d_out); if (sl.d_enc_in) gdgb_free(sl.d_enc_in); if (sl.d_enc_out) gdgb_free(sl.d_enc_out); if (sl.h_stage) gdgb_pinned_free(sl.h_stage); if (sl.h_stage2) gdgb_pinned_free(sl.h_stage2); }
     }
 };
 std::mutex g_batch_mutex;
@@ -905,8 +906,23 @@ int block_submit(int si, gdg_chain *const *chains, size_t C, gdg_tuner *tuner, i
     if (rounds < 0) return -1;
     Batch::Slot &b = g_batch->slot[si];
     const int ev = si * 28;
-    const size_t ib = n * fmt_bytes(in_fmt), ob = n * fmt_bytes(out_fmt);      /* bytes per row */
+    const size_t ib = n * fmt_bytes(in_fmt), ob = n * fmt_bytes(out_fmt);      /* bytes per host row */
+    /* tuner, spatializer and meter read float64 rows: with encoded host rows and any of them present the payload is
+     * converted by a small kernel on either side of the float64 path instead of inside the chain kernel */
+    const bool recode = (tuner || spat || meter) && (in_fmt != GDG_FMT_IEEE64 || out_fmt != GDG_FMT_IEEE64);
+    const int kin = recode ? GDG_FMT_IEEE64 : in_fmt, kout = recode ? GDG_FMT_IEEE64 : out_fmt;   /* formats the chain kernel sees */
+    const size_t kib = n * fmt_bytes(kin), kob = n * fmt_bytes(kout);
     if (stage_buffers(b, (C + 2) * n)) return -1;
+    if (recode && b.enc_cap < (C + 2) * n) {
+        if (b.d_enc_in) gdgb_free(b.d_enc_in);
+        if (b.d_enc_out) gdgb_free(b.d_enc_out);
+        b.d_enc_in = (double *)gdgb_alloc((C + 2) * n * sizeof(double));
+        b.d_enc_out = (double *)gdgb_alloc((C + 2) * n * sizeof(double));
+        if (!b.d_enc_in || !b.d_enc_out) return backend_fail("device staging allocation failed");
+        b.enc_cap = (C + 2) * n;
+    }
+    void *up_dst = recode ? (void *)b.d_enc_in : (void *)b.d_in;
+    const void *down_src = recode ? (const void *)b.d_enc_out : (const void *)b.d_out;
     const bool in_direct = contiguous_bytes(in, C, ib) && gdgb_is_pinned(in[0]);
     const bool out_direct = contiguous_bytes((const void *const *)out, n_out_rows, ob) && gdgb_is_pinned(out[0]);
     if ((!in_direct || !out_direct) && ensure_host_stage(b, (C + 2) * n)) return -1;
@@ -918,7 +934,7 @@ int block_submit(int si, gdg_chain *const *chains, size_t C, gdg_tuner *tuner, i
         const size_t c0 = (size_t)g * per;
         if (c0 >= C) break;
         const size_t cnt = std::min(per, C - c0);
-        if (upload_rows(b, in, c0, cnt, ib, b.d_in, 1)) return -1;
+        if (upload_rows(b, in, c0, cnt, ib, up_dst, 1)) return -1;
         if (gdgb_record(ev + g % 8, 1)) return backend_fail("event record failed");
     }
     for (int g = 0; g < G; g++) {
@@ -926,21 +942,27 @@ int block_submit(int si, gdg_chain *const *chains, size_t C, gdg_tuner *tuner, i
         if (c0 >= C) break;
         const size_t cnt = std::min(per, C - c0);
         if (gdgb_wait(0, ev + g % 8)) return backend_fail("stream wait failed");
+        if (recode && gdgb_convert_rows((const char *)b.d_enc_in + c0 * ib, (long)ib, in_fmt, b.d_in + c0 * n, (long)(n * sizeof(double)), GDG_FMT_IEEE64, (int)cnt, (int)n, s0))
+            return backend_fail("payload decode failed");
         if (tuner && tuner_channel >= 0 && (size_t)tuner_channel >= c0 && (size_t)tuner_channel < c0 + cnt)
             if (gdg_tuner_process_device(tuner, b.d_in + (size_t)tuner_channel * n, n, rate, s0)) return -1;   /* controller.go:2668-2672 */
         if (meter && meter_rows(meter, (uint32_t)c0, b.d_in + c0 * n, n, (uint32_t)cnt, n, rate, s0)) return -1;      /* controller.go:2710-2714: inputs */
-        if (launch_batch_fmt(c0, cnt, rounds, b.d_in, ib, in_fmt, b.d_out, ob, out_fmt, n, s0)) return -1;       /* controller.go:2682-2705 */
+        if (launch_batch_fmt(c0, cnt, rounds, b.d_in, kib, kin, b.d_out, kob, kout, n, s0)) return -1;           /* controller.go:2682-2705 */
         if (meter && meter_rows(meter, (uint32_t)(C + c0), b.d_out + c0 * n, n, (uint32_t)cnt, n, rate, s0)) return -1;   /* outputs */
+        if (recode && gdgb_convert_rows(b.d_out + c0 * n, (long)(n * sizeof(double)), GDG_FMT_IEEE64, (char *)b.d_enc_out + c0 * ob, (long)ob, out_fmt, (int)cnt, (int)n, s0))
+            return backend_fail("payload encode failed");
         if (gdgb_record(ev + 8 + g % 8, 0) || gdgb_wait(2, ev + 8 + g % 8)) return backend_fail("event failed");
-        const int r = download_rows(b, out, c0, cnt, ob, b.d_out, 2);
+        const int r = download_rows(b, out, c0, cnt, ob, down_src, 2);
         if (r < 0) return -1;
         if (r == 1) b.staged.push_back({c0, cnt});
     }
     if (spat) {                                                                                                 /* controller.go:2761 */
         if (gdg_spatializer_process_device(spat, b.d_out, n, nullptr, b.d_out + C * n, n, n, 0, s0)) return -1;
         if (meter && meter_rows(meter, (uint32_t)(2 * C + 1), b.d_out + C * n, n, 2, n, rate, s0)) return -1;    /* controller.go:2768-2770: master */
+        if (recode && gdgb_convert_rows(b.d_out + C * n, (long)(n * sizeof(double)), GDG_FMT_IEEE64, (char *)b.d_enc_out + C * ob, (long)ob, out_fmt, 2, (int)n, s0))
+            return backend_fail("payload encode failed");
         if (gdgb_record(ev + 16, 0) || gdgb_wait(2, ev + 16)) return backend_fail("event failed");
-        const int r = download_rows(b, out, C, 2, ob, b.d_out, 2);
+        const int r = download_rows(b, out, C, 2, ob, down_src, 2);
         if (r < 0) return -1;
         if (r == 1) b.staged.push_back({C, 2});
     }
@@ -1685,6 +1707,30 @@ int gdg_controller_submit(gdg_chain *const *chains, uint32_t C, gdg_tuner *tuner
     if (si < 0) return fail("two submitted blocks are in flight: gdg_controller_wait() for one first");
     if (block_submit(si, chains, C, tuner, tuner_channel, do_spat ? spat : nullptr, meter && meter->enabled ? meter : nullptr, (const void *const *)in,
                      GDG_FMT_IEEE64, (void *const *)out, GDG_FMT_IEEE64, (size_t)C + (do_spat ? 2 : 0), n, rate)) {
+        if (g_batch) { gdgb_sync(); g_batch->slot[si].busy = false; }
+        return -1;
+    }
+    return si;
+}
+/* gdg_controller_submit with encoded host rows (wave.go sample formats): the payload is decoded / encoded on the device,
+ * tuner, spatializer and meter see float64 */
+int gdg_controller_submit_encoded(gdg_chain *const *chains, uint32_t C, gdg_tuner *tuner, int tuner_channel, gdg_spatializer *spat,
+                                  gdg_meter *meter, const void *const *in, int in_format, void *const *out, int out_format,
+                                  uint32_t n_out, size_t n, uint32_t rate)
+{
+    if (ensure_init()) return -1;
+    if (!chains || !C || !in || !out) return fail("gdg_controller_submit_encoded: bad argument");
+    if (!fmt_bytes(in_format) || !fmt_bytes(out_format)) return fail("Unknown sample format: %#04x", fmt_bytes(in_format) ? out_format : in_format);
+    if (check_block(n)) return -1;
+    if (meter && meter->count != 2 * C + 3)
+        return fail("gdg_controller_submit_encoded: the level meter has %u channels, %u inputs need %u (inputs, outputs, metronome, master L/R: controller.go:2710-2771)", meter->count, C, 2 * C + 3);
+    if (n_out < C) return fail("gdg_controller_submit_encoded: %u output rows for %u channels", n_out, C);
+    const bool do_spat = spat && n_out >= C + 2 && spat->count == C;
+    std::lock_guard<std::mutex> lk(g_batch_mutex);
+    const int si = free_slot();
+    if (si < 0) return fail("two submitted blocks are in flight: gdg_controller_wait() for one first");
+    if (block_submit(si, chains, C, tuner, tuner_channel, do_spat ? spat : nullptr, meter && meter->enabled ? meter : nullptr, in, in_format, out,
+                     out_format, (size_t)C + (do_spat ? 2 : 0), n, rate)) {
         if (g_batch) { gdgb_sync(); g_batch->slot[si].busy = false; }
         return -1;
     }

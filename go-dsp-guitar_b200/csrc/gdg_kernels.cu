@@ -49,6 +49,13 @@ __global__ void __launch_bounds__(GDG_NT) k_meter(const double *in, long stride,
     __shared__ double red[GDG_METER_RED];
     meter_channel(red, in + (long)blockIdx.x * stride, n, f, hold, state + 4 * (long)blockIdx.x);
 }
+/* sample-format conversion of planar rows (wave.go codecs): row r of `in` (in_fmt) -> row r of `out` (out_fmt) */
+__global__ void k_convert_rows(const unsigned char *in, long in_stride, int in_fmt, unsigned char *out, long out_stride, int out_fmt, int n)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const long r = blockIdx.y;
+    if (k < n) encode_sample(out_fmt, out + r * out_stride, k, decode_sample(in_fmt, in + r * in_stride, k));
+}
 __global__ void k_resample_time(const double *in, long n, double dx, double *out, long out_len)
 {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -200,6 +207,16 @@ int gdgb_launch_meter(const double *d_in, long stride, int channels, long n, dou
 {
     if (channels > 0 && n > 0) {
         k_meter<<<channels, GDG_NT, 0, (cudaStream_t)stream>>>(d_in, stride, n, f, hold, d_state);
+        g_launches++;
+        CU(cudaGetLastError());
+    }
+    return 0;
+}
+int gdgb_convert_rows(const void *d_in, long in_stride_bytes, int in_fmt, void *d_out, long out_stride_bytes, int out_fmt, int rows, int n, void *stream)
+{
+    if (rows > 0 && n > 0) {
+        dim3 grid((unsigned)((n + 255) / 256), (unsigned)rows);
+        k_convert_rows<<<grid, 256, 0, (cudaStream_t)stream>>>((const unsigned char *)d_in, in_stride_bytes, in_fmt, (unsigned char *)d_out, out_stride_bytes, out_fmt, n);
         g_launches++;
         CU(cudaGetLastError());
     }

@@ -210,6 +210,12 @@ int gdg_controller_submit(gdg_chain *const *chains, uint32_t channels, gdg_tuner
                           gdg_spatializer *spat, gdg_meter *meter, const double *const *in, double *const *out,
                           uint32_t n_out, size_t n, uint32_t sample_rate);
 int gdg_controller_wait(int ticket);
+/* gdg_controller_submit on ENCODED host rows (the data-chunk payload of wave/wave.go's formats, GDG_FORMAT_*): rows are
+ * decoded to float64 on the device, tuner feed / chains / spatializer / meter run as above, the C (+2) output rows come
+ * back encoded - the whole of controller.go:2908-3143 for one block without a float64 ever crossing PCIe. */
+int gdg_controller_submit_encoded(gdg_chain *const *chains, uint32_t channels, gdg_tuner *tuner, int tuner_channel,
+                                  gdg_spatializer *spat, gdg_meter *meter, const void *const *in, int in_format,
+                                  void *const *out, int out_format, uint32_t n_out, size_t n, uint32_t sample_rate);
 
 #ifdef __cplusplus
 }

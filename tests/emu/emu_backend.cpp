@@ -82,6 +82,14 @@ int gdgb_launch_meter(const double *in, long stride, int channels, long n, doubl
     if (channels > 0 && n > 0) g_launches++;
     return 0;
 }
+int gdgb_convert_rows(const void *in, long in_stride, int in_fmt, void *out, long out_stride, int out_fmt, int rows, int n, void *)
+{
+    for (int r = 0; r < rows; r++)
+        for (int k = 0; k < n; k++)
+            encode_sample(out_fmt, (unsigned char *)out + (long)r * out_stride, k, decode_sample(in_fmt, (const unsigned char *)in + (long)r * in_stride, k));
+    if (rows > 0 && n > 0) g_launches++;
+    return 0;
+}
 int gdgb_resample_time(const double *in, long n, double dx, double *out, long out_len, void *)
 {
     for (long i = 0; i < out_len; i++) out[i] = resample_time_body(in, n, dx, i);
