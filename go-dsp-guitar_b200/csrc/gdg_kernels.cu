@@ -151,6 +151,8 @@ void *gdgb_alloc(size_t bytes)
     cudaError_t e = cudaMalloc(&p, bytes);
     if (e != cudaSuccess) { cu_fail("cudaMalloc", e); return nullptr; }
     e = cudaMemsetAsync(p, 0, bytes, g_stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(g_stream);   /* the buffer may next be touched from another stream (uploads
+                                                                  * run on their own): the zero fill must have landed by then */
     if (e != cudaSuccess) { cu_fail("cudaMemsetAsync", e); cudaFree(p); return nullptr; }
     return p;
 }
