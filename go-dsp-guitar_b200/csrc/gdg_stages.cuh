@@ -48,6 +48,9 @@
 /* coherent load from GLOBAL memory (unit state): tells the compiler the address space, so that the loads can be
  * hoisted over shared-memory stores and batched */
 #define GDG_LDST(p) __ldcg(p)
+/* c + a*b with BOTH roundings, as the reference computes it (no FMA contraction): used where the result feeds a
+ * discontinuity (phase wrap, square / sawtooth edge) or is carried as state, so that it stays bit-identical */
+#define GDG_MULADD_RN(a, b, c) __dadd_rn(__dmul_rn((a), (b)), (c))
 /* 8-byte global -> shared copy that does not pass through registers (LDGSTS): the issuing thread does not wait for it
  * until async_wait(); a thread only ever reads back cells it requested itself, so no barrier is involved */
 static __device__ __forceinline__ void async_copy8(double *smem_dst, const double *gsrc)
@@ -86,6 +89,7 @@ static __device__ __forceinline__ void bulk_wait(double *mbar_word)
 #define GDG_CONST static
 #define GDG_LDG(p) (*(p))
 #define GDG_LDST(p) (*(p))
+#define GDG_MULADD_RN(a, b, c) (((a) * (b)) + (c))          /* the emulation is built with -ffp-contract=off */
 static inline void async_copy8(double *dst, const double *src) { *dst = *src; }
 static inline void async_wait() {}
 static inline void bulk_load(double *, double *dst, const void *src, unsigned bytes) { memcpy(dst, src, bytes); }
@@ -640,12 +644,12 @@ GDG_DEV void stage_ringmod(gdg_ctx &cx, const gdg_unit_desc &d_global)
         const double phase = st[0];
 #pragma unroll 1
         for (int k = tid; k < n; k += GDG_NT) {
-            const double cp = fmod(phase + ((double)k * frac), GDG_TWO_PI);
+            const double cp = fmod(GDG_MULADD_RN((double)k, frac, phase), GDG_TWO_PI);
             x[sw(k)] = sin(cp) * x[sw(k)];
         }
     GDG_THREADS_END
     GDG_THREADS_BEGIN
-        if (tid == 0) st[0] = fmod(st[0] + ((double)n * frac), GDG_TWO_PI);
+        if (tid == 0) st[0] = fmod(GDG_MULADD_RN((double)n, frac, st[0]), GDG_TWO_PI);
     GDG_THREADS_END
 }
 
@@ -690,7 +694,7 @@ GDG_DEV void stage_siggen(gdg_ctx &cx, const gdg_unit_desc &d_global)
         const double two_over_pi = 2.0 / GDG_PI;
 #pragma unroll 1
         for (int k = tid; k < n; k += GDG_NT) {
-            const double cp = fmod(phase + ((double)k * inc), GDG_TWO_PI);
+            const double cp = fmod(GDG_MULADD_RN((double)k, inc, phase), GDG_TWO_PI);
             double sig;
             if (type == 0) sig = sin(cp);
             else if (type == 1) sig = cp < GDG_PI ? (two_over_pi * cp) - 1.0 : 3.0 - (two_over_pi * cp);
@@ -700,7 +704,7 @@ GDG_DEV void stage_siggen(gdg_ctx &cx, const gdg_unit_desc &d_global)
         }
     GDG_THREADS_END
     GDG_THREADS_BEGIN
-        if (tid == 0) { double ph = st[0] + (double)n * inc; st[0] = fmod(ph, GDG_TWO_PI); }
+        if (tid == 0) { const double ph = GDG_MULADD_RN((double)n, inc, st[0]); st[0] = fmod(ph, GDG_TWO_PI); }
     GDG_THREADS_END
 }
 
@@ -758,7 +762,7 @@ GDG_DEV void stage_chorus(gdg_ctx &cx, const gdg_unit_desc &d_global)
 #pragma unroll 1
         for (int k = tid; k < n; k += GDG_NT) {
             const double t = (double)k / sr;
-            const double zero_phase = fmod(prev + (ang * t), GDG_TWO_PI);
+            const double zero_phase = fmod(GDG_MULADD_RN(ang, t, prev), GDG_TWO_PI);
             const double s0 = sin(zero_phase), c0 = cos(zero_phase);
             double eff = 0.0;
             for (int j = 0; j < 5; j++) {
@@ -770,7 +774,7 @@ GDG_DEV void stage_chorus(gdg_ctx &cx, const gdg_unit_desc &d_global)
         }
     GDG_THREADS_END
     GDG_THREADS_BEGIN
-        if (tid == 0) st[0] = fmod(st[0] + (ang * ((double)hs / sr)), GDG_TWO_PI);
+        if (tid == 0) st[0] = fmod(GDG_MULADD_RN(ang, (double)hs / sr, st[0]), GDG_TWO_PI);
     GDG_THREADS_END
     ring_push(cx, x, st, hs);
     swap_bufs(cx);
@@ -791,14 +795,14 @@ GDG_DEV void stage_flanger(gdg_ctx &cx, const gdg_unit_desc &d_global)
 #pragma unroll 1
         for (int k = tid; k < n; k += GDG_NT) {
             const double t = (double)k * sr_inv;
-            const double phase = fmod(prev + (ang * t), GDG_TWO_PI);
+            const double phase = fmod(GDG_MULADD_RN(ang, t, prev), GDG_TWO_PI);
             const double offset = depth * sin(phase);
             const double dsmp = (0.001 * (depth + offset)) * sr;
             y[sw(k)] = (wa * x[sw(k)]) + (wb * frac_delay_read(x, ring, hs, pos, k, dsmp));
         }
     GDG_THREADS_END
     GDG_THREADS_BEGIN
-        if (tid == 0) st[0] = fmod(st[0] + (ang * ((double)hs * sr_inv)), GDG_TWO_PI);
+        if (tid == 0) st[0] = fmod(GDG_MULADD_RN(ang, (double)hs * sr_inv, st[0]), GDG_TWO_PI);
     GDG_THREADS_END
     ring_push(cx, x, st, hs);
     swap_bufs(cx);
