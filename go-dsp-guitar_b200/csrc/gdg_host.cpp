@@ -264,6 +264,7 @@ struct Unit {
     gdg_irbank *bank = nullptr;
     /* device state */
     double *d_st = nullptr; size_t st_words = 0; long st_key = -1;
+    size_t os_last_n[2] = {0, 0};                          /* block length last seen by the x2 / x4 oversampler */
     /* cached descriptor */
     gdg_unit_desc desc; bool dirty = true; uint32_t cached_rate = 0; bool valid = false;
     /* power amp */
@@ -344,6 +345,19 @@ int Unit::prepare(uint32_t rate, size_t n)
     }
     if (type == GDG_UNIT_POWERAMP && pa_spec && pa_spec->K > 1 && n != GDG_MAX_N)
         return fail("power_amp: a %d-tap filter runs as a partitioned convolution that is only supported for blocks of %d samples (got %zu)", pa_spec->L, GDG_MAX_N, n);
+    if (type == GDG_UNIT_EXCESS || type == GDG_UNIT_FUZZ || type == GDG_UNIT_OVERDRIVE || type == GDG_UNIT_DISTORTION) {
+        /* oversampling.go:74-84: the up-sampler's input buffer (N + 8, its first 8 cells = the last 8 inputs) is re-made,
+         * i.e. zeroed, whenever the block length differs from the one it was made for; the anti-aliasing filter's
+         * overlap tail does not depend on N and survives.  Each unit owns one x2 and one x4 oversampler
+         * (e.g. overdrive.go:150-151), each with its own history. */
+        const int f = os_factor();
+        if (f > 1) {
+            size_t &last = os_last_n[f == 2 ? 0 : 1];
+            if (last && last != n && d_st && gdgb_zero(d_st + (f == 2 ? GDG_OS_ST_UP2 : GDG_OS_ST_UP4), 8 * sizeof(double)))
+                return backend_fail("state reset failed");
+            last = n;
+        }
+    }
     if (valid && !dirty && cached_rate == rate) return 0;
     gdg_unit_desc d; memset(&d, 0, sizeof d);
     d.type = type;

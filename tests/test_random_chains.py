@@ -62,3 +62,91 @@ def test_random_chain_streams_like_the_oracle(lib, seed):
     blocks = 3 if n >= 2048 else 6
     x = common.synth_fast(seed, fs, blocks * n, seed) * float(rng.choice([0.1, 1.0, 1.7]))
     common.compare_stream(a, b, x, n, fs, label="seed %d fs %d n %d %s" % (seed, fs, n, [s[0] for s in spec]))
+
+
+def _random_params(rng, schema, u, n, ir_names):
+    numeric, discrete = {}, {}
+    for p in schema[u]:
+        if rng.random() < 0.5:
+            continue
+        if p["DiscreteValues"]:
+            vals = p["DiscreteValues"]
+            if u == "power_amp" and p["Name"] == "filter_order":
+                vals = [v for v in vals if int(v) <= 8192]
+            if u == "power_amp" and p["Name"].startswith("filter_") and p["Name"] != "filter_order":
+                vals = ["- NONE -"] + [str(x) for x in rng.choice(ir_names, 2)]
+            discrete[p["Name"]] = str(rng.choice(vals))
+        else:
+            numeric[p["Name"]] = int(rng.integers(int(p["Minimum"]), int(p["Maximum"]) + 1))
+    if u == "power_amp" and "filter_order" not in discrete:
+        discrete["filter_order"] = "4096"
+    return numeric, discrete
+
+
+CONTINUOUS = [u for u in gdg.UNIT_TYPES if u not in ("noise_gate", "octaver")]
+
+
+@pytest.mark.parametrize("seed", range(int(__import__("os").environ.get("GDG_RANDOM_EDITS", "24"))))
+def test_random_edit_sequences(lib, seed):
+    """A live chain is edited between blocks the way the web UI drives signal.Chain (append / remove / move / bypass /
+    parameter changes, a new block length, a new sample rate): unit state has to travel, reset or be rebuilt exactly
+    where the reference does it (signal.go:52-218, each unit's Process head, poweramp.go:132-181)."""
+    rng = np.random.default_rng(5000 + seed)
+    schema = _schema(lib)
+    banks = common.make_banks(lib)
+    ir_names = list(np.load(common.GOLD + "/ir_bank.npz")["names"])
+    a, b = orc.Chain(banks[0]), gdg.Chain(banks[1], lib=lib)
+    fs, n = int(rng.choice(RATES)), int(rng.choice([256, 1024, 2048]))
+
+    def both(fn):
+        ra, rb = fn(a), fn(b)
+        return ra, rb
+
+    def append():
+        u = str(rng.choice(CONTINUOUS))
+        ia, ib = both(lambda c: c.append_unit(u))
+        assert ia == ib
+        numeric, discrete = _random_params(rng, schema, u, n, ir_names)
+        for k, v in discrete.items():
+            both(lambda c: c.set_discrete_value(ia, k, v))
+        for k, v in numeric.items():
+            both(lambda c: c.set_numeric_value(ia, k, v))
+        both(lambda c: c.set_bypass(ia, False))
+        kinds.append(u)
+
+    kinds = []
+    for _ in range(int(rng.integers(2, 6))):
+        append()
+    pos = 0
+    x = common.synth_fast(seed, 48000, 40 * 2048, seed)      # just a long varied signal; the rate label is what changes
+    for step in range(14):
+        op = rng.choice(["none", "param", "bypass", "move_up", "move_down", "remove", "append", "block", "rate"],
+                        p=[0.15, 0.25, 0.1, 0.08, 0.08, 0.08, 0.1, 0.08, 0.08])
+        L = len(kinds)
+        if op == "param" and L:
+            i = int(rng.integers(L))
+            numeric, discrete = _random_params(rng, schema, kinds[i], n, ir_names)
+            for k, v in discrete.items():
+                both(lambda c: c.set_discrete_value(i, k, v))
+            for k, v in numeric.items():
+                both(lambda c: c.set_numeric_value(i, k, v))
+        elif op == "bypass" and L:
+            i = int(rng.integers(L)); v = bool(rng.integers(2))
+            both(lambda c: c.set_bypass(i, v))
+        elif op == "move_up" and L > 1:
+            i = int(rng.integers(1, L)); both(lambda c: c.move_up(i)); kinds[i - 1], kinds[i] = kinds[i], kinds[i - 1]
+        elif op == "move_down" and L > 1:
+            i = int(rng.integers(0, L - 1)); both(lambda c: c.move_down(i)); kinds[i + 1], kinds[i] = kinds[i], kinds[i + 1]
+        elif op == "remove" and L > 1:
+            i = int(rng.integers(L)); both(lambda c: c.remove_unit(i)); kinds.pop(i)
+        elif op == "append" and L < 9:
+            append()
+        elif op == "block":
+            n = int(rng.choice([64, 256, 1024, 2048, 4096]))
+        elif op == "rate":
+            fs = int(rng.choice(RATES))
+        blk = x[pos:pos + n]; pos += n
+        ya, yb = a.process(blk, fs), b.process(blk, fs)
+        assert a.length() == b.length() == len(kinds)
+        e = common.rms(ya - yb)
+        assert np.all(np.isfinite(yb)) and e <= common.TOL_RMS, "seed %d step %d after %s: rms %.3e, chain %s, n %d fs %d" % (seed, step, op, e, kinds, n, fs)
