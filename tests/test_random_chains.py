@@ -52,12 +52,14 @@ def test_random_chain_streams_like_the_oracle(lib, seed):
         if u == "power_amp" and "filter_order" not in discrete:
             discrete["filter_order"] = "8192" if n != 8192 else "65536"                 # the default (1048576) needs n = 8192
         spec.append((u, numeric, discrete))
-    # discontinuous units (gate open/close, octaver polarity flips with hysteresis) amplify a 1e-18 difference of their
+    # discontinuous units (gate open/close, octaver polarity flips with hysteresis, auto_yoy's clamp edges) amplify a 1e-18 difference of their
     # input into a different decision - between Go and any restatement too.  Like CHAIN12 the random chains
     # keep them where their input is bit-identical: gates first, then at most one octaver, then everything else.
+    # auto_yoy belongs here too: where its delay is clamped to a whole number of samples both interpolation weights are 1
+    # (autoyoy.go:124-140), a hair off it they are (1, 0) - the output jumps by a whole sample at the clamp edge.
     gates = [u for u in spec if u[0] == "noise_gate"]
-    octs = [u for u in spec if u[0] == "octaver"][:1]
-    spec = gates + octs + [u for u in spec if u[0] not in ("noise_gate", "octaver")]
+    octs = [u for u in spec if u[0] in ("octaver", "auto_yoy")][:1]
+    spec = gates + octs + [u for u in spec if u[0] not in ("noise_gate", "octaver", "auto_yoy")]
     a, b = common.make_chain_pair(lib, spec, banks)
     blocks = 3 if n >= 2048 else 6
     x = common.synth_fast(seed, fs, blocks * n, seed) * float(rng.choice([0.1, 1.0, 1.7]))
@@ -83,7 +85,7 @@ def _random_params(rng, schema, u, n, ir_names):
     return numeric, discrete
 
 
-CONTINUOUS = [u for u in gdg.UNIT_TYPES if u not in ("noise_gate", "octaver")]
+CONTINUOUS = [u for u in gdg.UNIT_TYPES if u not in ("noise_gate", "octaver", "auto_yoy")]
 
 
 @pytest.mark.parametrize("seed", range(int(__import__("os").environ.get("GDG_RANDOM_EDITS", "24"))))
@@ -150,3 +152,105 @@ def test_random_edit_sequences(lib, seed):
         assert a.length() == b.length() == len(kinds)
         e = common.rms(ya - yb)
         assert np.all(np.isfinite(yb)) and e <= common.TOL_RMS, "seed %d step %d after %s: rms %.3e, chain %s, n %d fs %d" % (seed, step, op, e, kinds, n, fs)
+
+
+@pytest.mark.parametrize("seed", range(int(__import__("os").environ.get("GDG_RANDOM_MIX", "16"))))
+def test_random_spatializer_and_power_amp_sessions(lib, seed):
+    """Spatializer positions / levels and the power amp's eight filter slots change between blocks, block length and rate
+    too: the mix-down keeps its inter-aural history, the power amp recompiles with a fresh overlap tail
+    (poweramp.go:132-181) exactly when the reference does."""
+    rng = np.random.default_rng(9000 + seed)
+    banks = common.make_banks(lib)
+    ir_names = [str(x) for x in np.load(common.GOLD + "/ir_bank.npz")["names"]]
+    C = int(rng.integers(1, 41))
+    sa, sb = orc.Spatializer(C), gdg.Spatializer(C, lib=lib)
+    a, b = common.make_chain_pair(lib, [("power_amp", {}, {"filter_order": "2048"})], banks)
+    fs, n = int(rng.choice(RATES)), int(rng.choice([256, 1024, 4096]))
+    x = np.stack([common.synth_fast(c, 48000, 12 * 4096, seed) for c in range(min(C, 6))])
+    pos = 0
+    for step in range(10):
+        for _ in range(int(rng.integers(0, 4))):
+            c, what = int(rng.integers(C)), rng.choice(["az", "dist", "level"])
+            v = float(rng.uniform(-90, 90)) if what == "az" else (float(rng.uniform(0.0, 10.0)) if what == "dist" else float(rng.uniform(0.0, 1.0)))
+            for s in (sa, sb):
+                {"az": s.set_azimuth, "dist": s.set_distance, "level": s.set_level}[what](c, v)
+        r = rng.random()
+        if r < 0.2:
+            fs = int(rng.choice(RATES)); sa.set_sample_rate(fs); sb.set_sample_rate(fs)
+        elif r < 0.4:
+            n = int(rng.choice([64, 256, 1024, 4096]))
+        elif r < 0.8:
+            k = int(rng.integers(1, 9))
+            what = rng.choice(["filter", "level", "order"])
+            for ch in (a, b):
+                if what == "filter":
+                    ch.set_discrete_value(0, "filter_%d" % k, str(rng.choice(["- NONE -"] + ir_names)) if ch is a else last)
+                elif what == "level":
+                    ch.set_numeric_value(0, "level_%d" % k, int(rng.integers(-60, 1)) if ch is a else last)
+                else:
+                    ch.set_discrete_value(0, "filter_order", str(rng.choice(["64", "512", "2048", "8192"])) if ch is a else last)
+                last = ch.get_discrete_value(0, "filter_%d" % k) if what == "filter" else (ch.get_numeric_value(0, "level_%d" % k) if what == "level" else ch.get_discrete_value(0, "filter_order"))
+        blk = np.stack([x[c % x.shape[0], pos:pos + n] * (1.0 + 0.1 * (c // x.shape[0])) for c in range(C)]); pos += n
+        aux = 0.05 * x[0, pos:pos + n] if rng.random() < 0.3 else None
+        ya, yb = sa.process(blk, aux), sb.process(blk, aux)
+        scale = max(1.0, float(np.max(np.abs(ya))))
+        assert np.max(np.abs(ya - yb)) <= 1e-11 * scale, (seed, step, C, n, fs)
+        pa, pb = a.process(blk[0], fs), b.process(blk[0], fs)
+        assert common.rms(pa - pb) <= common.TOL_RMS, (seed, step, n, fs)
+
+
+@pytest.mark.parametrize("seed", range(int(__import__("os").environ.get("GDG_RANDOM_SESSIONS", "10"))))
+def test_random_controller_sessions(lib, seed):
+    """controller.process as a whole on random batches: 1..9 channels whose chains differ in length (so the batch mixes
+    segment rounds), bypass toggles and tuner-channel changes between blocks, tuner read-outs at random moments, the level
+    meter on, blocking calls and submit / wait pairs interleaved."""
+    rng = np.random.default_rng(13000 + seed)
+    schema = _schema(lib)
+    banks = common.make_banks(lib)
+    ir_names = list(np.load(common.GOLD + "/ir_bank.npz")["names"])
+    C = int(rng.integers(1, 10))
+    fs, n = int(rng.choice([44100, 48000, 96000, 192000])), int(rng.choice([256, 1024, 2048]))
+    oc, gc = [], []
+    for c in range(C):
+        spec = []
+        for _ in range(int(rng.choice([1, 3, 6, 27]))):
+            u = str(rng.choice([k for k in CONTINUOUS if k != "power_amp"]))
+            numeric, discrete = _random_params(rng, schema, u, n, ir_names)
+            spec.append((u, numeric, discrete))
+        a, b = common.make_chain_pair(lib, spec, banks)
+        oc.append(a); gc.append(b)
+    sa, sb = orc.Spatializer(C), gdg.Spatializer(C, lib=lib)
+    ta, tb = orc.Tuner(), gdg.Tuner(lib=lib)
+    ma, mb = orc.Meter(2 * C + 3), gdg.Meter(2 * C + 3, lib=lib)
+    ma.set_enabled(True); mb.set_enabled(True)
+    x = np.stack([common.synth_fast(c, fs, 10 * n, seed) for c in range(C)])
+    tch = int(rng.integers(-1, C))
+    pending = None
+    for k in range(10):
+        if rng.random() < 0.3:
+            c = int(rng.integers(C)); i = int(rng.integers(oc[c].length())); v = bool(rng.integers(2))
+            oc[c].set_bypass(i, v); gc[c].set_bypass(i, v)
+        if rng.random() < 0.2:
+            tch = int(rng.integers(-1, C))
+        blk = np.ascontiguousarray(x[:, k * n:(k + 1) * n])
+        ref = orc.controller_process(oc, ta, tch, sa, blk, fs)
+        ma.process(list(blk) + list(ref[:C]) + [None] + list(ref[C:]), fs)
+        if rng.random() < 0.5:
+            got = gdg.controller_process(gc, tb, tch, sb, blk, fs, meter=mb)
+        else:
+            got = np.zeros((C + 2, n))
+            t = gdg.controller_submit(gc, tb, tch, sb, blk, got, fs, meter=mb)
+            gdg.controller_wait(t, lib)
+        for c in range(C):
+            assert common.rms(ref[c] - got[c]) <= common.TOL_RMS, (seed, k, c)
+        # the master pair sums the channels (default positions: plain sum): its error is bounded by the channels' own
+        scale = max(1.0, float(np.max(np.abs(ref[C:]))))
+        bound = 2.0 * sum(float(np.max(np.abs(ref[c] - got[c]))) for c in range(C)) + 1e-11 * scale
+        assert np.max(np.abs(ref[C:] - got[C:])) <= bound, (seed, k)
+        if rng.random() < 0.3:
+            ra, rb = ta.analyze(), tb.analyze()
+            assert ra["note"] == rb["note"] and ra["cents"] == rb["cents"] and abs(ra["frequency"] - rb["frequency"]) <= 1e-6 * abs(ra["frequency"]), (seed, k, ra, rb)
+    for c in range(2 * C + 3):
+        assert ma.analyze(c) == mb.analyze(c), (seed, c)
+        if c < C:                                                # input rows are bit-identical: so is the hold counter; on the
+            assert ma.state(c) == pytest.approx(mb.state(c), rel=1e-10) and ma.state(c)[2] == mb.state(c)[2], (seed, c)   # output rows a 1e-16 difference can move the last ">= peak" sample
