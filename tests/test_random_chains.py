@@ -254,3 +254,32 @@ def test_random_controller_sessions(lib, seed):
         assert ma.analyze(c) == mb.analyze(c), (seed, c)
         if c < C:                                                # input rows are bit-identical: so is the hold counter; on the
             assert ma.state(c) == pytest.approx(mb.state(c), rel=1e-10) and ma.state(c)[2] == mb.state(c)[2], (seed, c)   # output rows a 1e-16 difference can move the last ">= peak" sample
+
+
+@pytest.mark.parametrize("seed", range(int(__import__("os").environ.get("GDG_RANDOM_LONGIR", "6"))))
+def test_random_long_filter_sessions(lib, seed):
+    """Blocks of 8192 with composite power-amp filters of up to 65536 taps (the partitioned-convolution path: spectrum delay
+    line, slot ring) while filters, levels and the order change between blocks and other units sit around the power amp."""
+    rng = np.random.default_rng(17000 + seed)
+    fs, n = int(rng.choice([96000, 192000])), 8192
+    ob, pb = common.make_banks(lib, synthetic=[("long_a", 30000, fs), ("long_b", 65536, fs), ("mid", 9000, fs)])
+    names = ["long_a", "long_b", "mid", "- NONE -"] + [str(v) for v in np.load(common.GOLD + "/ir_bank.npz")["names"][:3]]
+    spec = [("compressor", {}, {}), ("power_amp", {}, {"filter_order": "65536", "filter_1": "long_a"}), ("delay", {"delay_time": 20}, {})]
+    a, b = common.make_chain_pair(lib, spec, (ob, pb))
+    x = common.synth_fast(seed, fs, 8 * n, seed)
+    for k in range(8):
+        r = rng.random()
+        if r < 0.25:
+            slot, name = int(rng.integers(1, 9)), str(rng.choice(names))
+            a.set_discrete_value(1, "filter_%d" % slot, name); b.set_discrete_value(1, "filter_%d" % slot, name)
+        elif r < 0.4:
+            slot, lv = int(rng.integers(1, 9)), int(rng.integers(-30, 1))
+            a.set_numeric_value(1, "level_%d" % slot, lv); b.set_numeric_value(1, "level_%d" % slot, lv)
+        elif r < 0.55:
+            order = str(rng.choice(["4096", "16384", "32768", "65536"]))
+            a.set_discrete_value(1, "filter_order", order); b.set_discrete_value(1, "filter_order", order)
+        elif r < 0.65:
+            v = bool(rng.integers(2)); a.set_bypass(1, v); b.set_bypass(1, v)
+        blk = x[k * n:(k + 1) * n]
+        ya, yb = a.process(blk, fs), b.process(blk, fs)
+        assert np.all(np.isfinite(yb)) and common.rms(ya - yb) <= common.TOL_RMS, (seed, k, common.rms(ya - yb))
