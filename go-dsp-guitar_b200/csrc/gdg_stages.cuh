@@ -261,10 +261,12 @@ GDG_DEVI double ring_get(const double *ring, int hs, int pos, int q)
     if (p >= hs) p -= hs;
     return GDG_LDST(ring + p);
 }
-/* x[idx] for idx in [-hs, n): block sample or history */
+/* x[idx] for idx in [-hs, n): block sample or history.  An index below -hs (flanger / phaser at 22.05 / 44.1 / 88.2 kHz,
+ * depth 100: delay 0.002 fs against a history of round(0.002 fs) samples - the reference panics there, flanger.go:80-84)
+ * reads the OLDEST history sample: defined behaviour shared with the oracle, never outside the ring. */
 GDG_DEVI double hist_or_block(const double *blk, const double *ring, int hs, int pos, int idx)
 {
-    return idx >= 0 ? blk[sw(idx)] : ring_get(ring, hs, pos, hs + idx);
+    return idx >= 0 ? blk[sw(idx)] : ring_get(ring, hs, pos, idx < -hs ? 0 : hs + idx);
 }
 /* same, for units that read mostly from the ring (delay, reverb line): both loads are issued unconditionally on
  * clamped (valid) addresses so that the global loads of an unrolled loop are batched instead of branched around */

@@ -153,9 +153,15 @@ static void history_push(double *buffer, int size, const double *in, int n)
         memcpy(buffer, in + (-boundary), sizeof(double) * size);
     }
 }
+/* x[idx] for idx in [-hsize, n).  DELIBERATE DIFFERENCE: flanger / phaser at 22050, 44100 and 88200 Hz with depth 100
+ * ask for idx = -hsize - 1 (delay 0.002 fs = 44.1 / 88.2 / 176.4 samples against a history of round(0.002 fs)); the
+ * reference panics there (flanger.go:80-84: buffer[-1]).  The oracle and the product read the OLDEST history sample
+ * instead (index clamped to -hsize) and never touch memory outside the history. */
 static inline double delayed(const double *in, const double *hist, int hsize, int idx)
 {
-    return idx >= 0 ? in[idx] : hist[hsize + idx];
+    if (idx >= 0) return in[idx];
+    if (idx < -hsize) idx = -hsize;
+    return hsize > 0 ? hist[hsize + idx] : 0.0;
 }
 
 /* ---- signalgenerator.go:20-153 ------------------------------------------- */

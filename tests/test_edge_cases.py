@@ -132,11 +132,11 @@ def test_extreme_finite_signals(lib, kind):
          "step_after_silence": (t >= 2 * n + 17).astype(np.float64) * -0.75}[kind]
     banks = common.make_banks(lib)
     a, b = common.make_chain_pair(lib, MIXED, banks, ir_name="Guitar: British Vintage (Neutral)")
-    common.compare_stream(a, b, x, n, fs, label=kind)
+    common.compare_stream(a, b, x, n, fs, label=kind, expect_signal=kind not in ("silence", "denormal"))
     every = [(u, {}, ({"oversampling": "2"} if u in ("excess", "fuzz", "overdrive", "distortion") else {})) for u in gdg.UNIT_TYPES]
     every[19] = ("power_amp", {}, {"filter_order": "2048", "filter_1": "Guitar: British Modern (Center)"})
     a, b = common.make_chain_pair(lib, every, banks)
-    common.compare_stream(a, b, x, n, fs, label=kind + "/all21")
+    common.compare_stream(a, b, x, n, fs, label=kind + "/all21", expect_signal=kind != "silence")
 
 
 def test_chain_longer_than_one_fused_segment(lib):
@@ -162,3 +162,15 @@ def test_chain_longer_than_one_fused_segment(lib):
     assert common.rms(pairs[0][0].process(blk, fs) - pairs[0][1].process(blk, fs)) <= common.TOL_RMS
     with pytest.raises(gdg.GdgError, match="segment"):
         gdg.process_batch_encoded([pairs[2][1]], [np.zeros(n, dtype="<i2").tobytes()], "PCM16", "PCM16", n, fs)
+
+
+@pytest.mark.parametrize("unit", ["flanger", "phaser"])
+@pytest.mark.parametrize("fs,n", [(22050, 32), (44100, 64), (88200, 128)])
+def test_flanger_phaser_full_depth_history_edge(lib, unit, fs, n):
+    """depth 100 at 22.05 / 44.1 / 88.2 kHz: the delay reaches 0.002 fs = history + a fraction, so the late tap of the first
+    samples of a block asks for one sample BEFORE the history (the reference panics, flanger.go:80-84).  Product and oracle
+    read the oldest history sample there (tests/test_oracle_crosscheck.py pins that choice against the literal restatement);
+    600 blocks shorter than the history, speed 37: the LFO passes sin(phase) > 0.9955 at a block start many times."""
+    a, b = common.make_chain_pair(lib, [(unit, {"depth": 100, "speed": 37}, {})])
+    x = common.synth_fast(11, fs, 600 * n)
+    common.compare_stream(a, b, x, n, fs, label="%s depth 100 @%d" % (unit, fs))

@@ -74,6 +74,13 @@ UNIT_CASES = [
 ]
 
 
+def _silent_by_design(case):
+    """parameter corners whose correct output is silence on a short stream: a gate that never holds or never opens (threshold 0 dB, input below full scale), a 100 % wet reverb
+    before its first tap (192 ms), a power amp without a filter"""
+    u, n, d = case
+    return (u == "noise_gate" and (n.get("hold_time", 1) == 0 or n.get("threshold_open") == 0)) or (u == "reverb" and n.get("mix") == 100) or u == "power_amp"
+
+
 def _id(case):
     u, n, d = case
     return u + ("-" + "-".join("%s=%s" % kv for kv in list(n.items()) + list(d.items())) if (n or d) else "")
@@ -86,7 +93,7 @@ def test_unit_parity(lib, case):
         a, b = common.make_chain_pair(lib, [case])
         x = common.synth_fast(3, fs, 6 * n, seed=n)
         x *= 1.6                                            # drive the clamps and thresholds
-        common.compare_stream(a, b, x, n, fs, label="%s n=%d fs=%d" % (_id(case), n, fs))
+        common.compare_stream(a, b, x, n, fs, label="%s n=%d fs=%d" % (_id(case), n, fs), expect_signal=not _silent_by_design(case))
 
 
 def test_bit_exact_units(lib):
@@ -366,4 +373,4 @@ def test_parameter_extremes(lib, unit):
     assert variants
     for numeric, discrete in variants:
         a, b = common.make_chain_pair(lib, [(unit, numeric, discrete)])
-        common.compare_stream(a, b, x, n, fs, label="%s %s %s" % (unit, numeric, discrete))
+        common.compare_stream(a, b, x, n, fs, label="%s %s %s" % (unit, numeric, discrete), expect_signal=not _silent_by_design((unit, numeric, discrete)))

@@ -63,7 +63,8 @@ def test_random_chain_streams_like_the_oracle(lib, seed):
     a, b = common.make_chain_pair(lib, spec, banks)
     blocks = 3 if n >= 2048 else 6
     x = common.synth_fast(seed, fs, blocks * n, seed) * float(rng.choice([0.1, 1.0, 1.7]))
-    common.compare_stream(a, b, x, n, fs, label="seed %d fs %d n %d %s" % (seed, fs, n, [s[0] for s in spec]))
+    # a random chain may be silent by construction (a power amp without a filter, a gate that never opens): not asserted here
+    common.compare_stream(a, b, x, n, fs, label="seed %d fs %d n %d %s" % (seed, fs, n, [s[0] for s in spec]), expect_signal=False)
 
 
 def _random_params(rng, schema, u, n, ir_names):
