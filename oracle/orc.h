@@ -12,9 +12,13 @@
  * resample/resample_test.go, random/random_test.go, circular/circular_test.go and
  * tuner/tuner_test.go (+ tuner/samples/ WAV tails) - see tests/test_oracle_goldens.py.
  * Units, chain driver, IR algebra and spatializer have NO tests in the reference
- * (SURVEY.md 8c): for those rows the oracle itself is the pin ("parity unpinned
- * by the reference"), cross-checked by an independent numpy restatement in
- * tests/test_oracle_crosscheck.py.
+ * ("parity unpinned by the reference").  For those rows the pin is
+ * (ii) a second restatement written independently from the Go sources in Python
+ * (tests/goref.py, parameter tables extracted from the Go Parameter{} literals),
+ * diffed against this oracle at <= 1e-12 per unit / parameter corner / CHAIN12 /
+ * Reduce-Normalize-Multiply-Add / filter.Import / spatializer, and (iii) analytic
+ * closed forms (distortion = clamp, ECC83 = tanh(g x / 2), excess = triangle fold,
+ * ...): tests/test_oracle_crosscheck.py, part of the CPU suite.
  *
  * The Go toolchain is absent from the build image, so the reference itself can
  * not be executed; math.Sin/Exp/Atan/Pow/Log10 are replaced by glibc libm
