@@ -26,7 +26,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-DEFAULT_LIBRARY = os.environ.get("GDG_LIBRARY") or os.path.join(HERE, "libgdg.so")   # GDG_LIBRARY: development override
+DEFAULT_LIBRARY = os.path.join(HERE, "libgdg.so")      # the in-tree CUDA build; no environment override (no CPU path is reachable from here)
 
 UNIT_TYPES = ["signal_generator", "noise_gate", "bandpass", "auto_wah", "auto_yoy", "compressor", "octaver",
               "excess", "fuzz", "overdrive", "distortion", "tone_stack", "chorus", "flanger", "phaser", "tremolo",
@@ -128,15 +128,19 @@ ABI = {
     "gdg_controller_submit": (_int, [_vp, _u32, _vp, _int, _vp, _vp, _vp, _vp, _u32, _sz, _u32]),
     "gdg_controller_wait": (_int, [_int]),
     "gdg_controller_submit_encoded": (_int, [_vp, _u32, _vp, _int, _vp, _vp, _vp, _int, _vp, _int, _u32, _sz, _u32]),
+    "gdg_controller_process_aux": (_int, [_vp, _u32, _vp, _int, _vp, _vp, _vp, _vp, _int, _vp, _u32, _sz, _u32]),
+    "gdg_controller_submit_aux": (_int, [_vp, _u32, _vp, _int, _vp, _vp, _vp, _vp, _int, _vp, _u32, _sz, _u32]),
     "gdg_process_batch_encoded_submit": (_int, [_vp, _sz, _vp, _int, _vp, _int, _sz, _u32]),
 }
 
 _LIBS = {}
 
 
-def load(path=None):
+def load(path=None, _test_backend=False):
     """dlopen libgdg (default: the in-tree CUDA build) and bind the ABI.  Fails loudly if the
-    library is missing - there is no Python / CPU fallback for any processing call."""
+    library is missing - there is no Python / CPU fallback for any processing call.  Any library whose
+    gdg_backend_name() is not the CUDA backend is REFUSED unless the caller is the test suite
+    (tests/common.py passes _test_backend=True for tests/emu/libgdg_emu.so)."""
     path = os.path.abspath(path or DEFAULT_LIBRARY)
     if path not in _LIBS:
         if not os.path.exists(path):
@@ -147,6 +151,9 @@ def load(path=None):
             fn = getattr(lib, name)
             fn.restype = res
             fn.argtypes = args
+        backend = lib.gdg_backend_name().decode()
+        if not backend.startswith("cuda:") and not _test_backend:
+            raise GdgError("%s is not the CUDA product library (backend '%s'): refused - there is no CPU path" % (path, backend))
         _LIBS[path] = lib
     return _LIBS[path]
 
@@ -511,8 +518,9 @@ class Meter(_Base):
         return c.value, p.value, q.value
 
 
-def controller_process(chains, tuner, tuner_channel, spat, inputs, sample_rate, meter=None):
-    """controller.process (controller.go:2648-2783) with host buffers: returns out[C (+2)][n]."""
+def controller_process(chains, tuner, tuner_channel, spat, inputs, sample_rate, meter=None, metronome=None, metronome_to_master=True):
+    """controller.process (controller.go:2648-2783) with host buffers: returns out[C (+2)][n].  `metronome`: the row the
+    metronome wrote for this block (controller.go:2724-2738), mixed into the master when metronome_to_master."""
     lib = chains[0]._lib
     x = _f64(inputs)
     c, n = x.shape
@@ -520,8 +528,13 @@ def controller_process(chains, tuner, tuner_channel, spat, inputs, sample_rate, 
     out = np.zeros((n_out, n))
     ip = (C.c_void_p * c)(*[x[i].ctypes.data for i in range(c)])
     op = (C.c_void_p * n_out)(*[out[i].ctypes.data for i in range(n_out)])
-    rc = lib.gdg_controller_process_metered(_handles(chains), c, tuner._h if tuner else None, tuner_channel,
-                                            spat._h if spat else None, meter._h if meter else None, ip, op, n_out, n, sample_rate)
+    if metronome is not None:
+        m = _f64(metronome)
+        rc = lib.gdg_controller_process_aux(_handles(chains), c, tuner._h if tuner else None, tuner_channel, spat._h if spat else None,
+                                            meter._h if meter else None, ip, _ptr(m), 1 if metronome_to_master else 0, op, n_out, n, sample_rate)
+    else:
+        rc = lib.gdg_controller_process_metered(_handles(chains), c, tuner._h if tuner else None, tuner_channel,
+                                                spat._h if spat else None, meter._h if meter else None, ip, op, n_out, n, sample_rate)
     if rc < 0:
         raise GdgError(lib.gdg_last_error().decode())
     return out

@@ -27,6 +27,7 @@
 #include <map>
 #include <memory>
 #include <mutex>
+#include <shared_mutex>
 #include <string>
 #include <vector>
 
@@ -41,6 +42,17 @@ int fail(const char *fmt, ...)
     return -1;
 }
 int backend_fail(const char *what) { return fail("%s: %s", what, gdgb_error()); }
+
+/* The reference guards every unit's parameters and every chain's slot list with an RWMutex (effects/effects.go:98,
+ * signal/signal.go:45): web-UI goroutines edit chains while the audio callback runs.  Here ONE reader/writer lock plays
+ * both roles: every processing entry point holds it SHARED from "resolve descriptors" to "kernels enqueued", every
+ * mutator (append / remove / move / bypass / set_*) and every getter that walks the parameter vectors holds it
+ * EXCLUSIVE resp. SHARED.  A mutator therefore never sees a half-prepared block, RemoveUnit cannot free device state that
+ * a not-yet-enqueued launch still references (it synchronises the stream after taking the lock), and parameter changes
+ * take effect at the next block boundary, as in the reference. */
+std::shared_mutex g_edit_mutex;
+typedef std::unique_lock<std::shared_mutex> EditLock;
+typedef std::shared_lock<std::shared_mutex> ProcessLock;
 
 std::once_flag g_init_once;
 int g_init_status = -1;
@@ -730,6 +742,7 @@ int run_batch_device(gdg_chain *const *chains, size_t C, const double *d_in, dou
                      uint32_t rate, void *stream)
 {
     if (check_block(n)) return -1;
+    ProcessLock el(g_edit_mutex);
     std::lock_guard<std::mutex> lk(g_batch_mutex);
     const int rounds = prepare_batch(chains, C, rate, n, stream);
     if (rounds < 0) return -1;
@@ -821,7 +834,8 @@ int download_simple(double *const *out, size_t C, size_t n, const double *d_src)
 
 /* the whole host-buffer block: upload -> (tuner feed) -> chains -> (spatializer) -> download, pipelined */
 int host_block(gdg_chain *const *chains, size_t C, gdg_tuner *tuner, int tuner_channel, gdg_spatializer *spat, struct gdg_meter *meter,
-               const void *const *in, int in_fmt, void *const *out, int out_fmt, size_t n_out_rows, size_t n, uint32_t rate);
+               const void *const *in, int in_fmt, void *const *out, int out_fmt, size_t n_out_rows, size_t n, uint32_t rate,
+               const double *metronome = nullptr, bool metro_master = false);
 
 } // namespace
 
@@ -909,12 +923,17 @@ int meter_rows(gdg_meter *m, uint32_t first, const double *d_rows, size_t stride
     return 0;
 }
 
-/* Enqueue one block on staging slot `si` (caller holds g_batch_mutex): uploads on stream 1, kernels on stream 0, downloads
- * on stream 2, one SM wave of channels per pipeline group.  Nothing here waits for the device.
+/* Enqueue one block on staging slot `si` (caller holds g_edit_mutex shared and g_batch_mutex): uploads on stream 1, kernels on
+ * stream 0, downloads on stream 2, one SM wave of channels per pipeline group, everything of a group enqueued before the next
+ * group is touched (an event is recorded and waited for within the same iteration, so the small id pool never aliases).
+ * Nothing here waits for the device.
  * in_fmt / out_fmt: sample formats of the host rows (tuner, spatializer and level meter need float64 rows).
- * Event ids: slot*28 + {0..7 uploads, 8..15 kernels, 16 spatializer, 17 all downloads}. */
+ * metronome: host row of n float64 samples = the metronome's output buffer of this block (controller.go:2724-2738), or NULL;
+ * it feeds meter channel 2C and, when `metro_master`, the spatializer's aux input (controller.go:2746-2761).
+ * Event ids: slot*28 + {0..7 uploads, 8..15 kernels, 16 spatializer, 17 all downloads, 18 metronome upload}. */
 int block_submit(int si, gdg_chain *const *chains, size_t C, gdg_tuner *tuner, int tuner_channel, gdg_spatializer *spat, gdg_meter *meter,
-                 const void *const *in, int in_fmt, void *const *out, int out_fmt, size_t n_out_rows, size_t n, uint32_t rate)
+                 const void *const *in, int in_fmt, void *const *out, int out_fmt, size_t n_out_rows, size_t n, uint32_t rate,
+                 const double *metronome = nullptr, bool metro_master = false)
 {
     const int rounds = prepare_batch(chains, C, rate, n, gdgb_stream());
     if (rounds < 0) return -1;
@@ -926,7 +945,7 @@ int block_submit(int si, gdg_chain *const *chains, size_t C, gdg_tuner *tuner, i
     const bool recode = (tuner || spat || meter) && (in_fmt != GDG_FMT_IEEE64 || out_fmt != GDG_FMT_IEEE64);
     const int kin = recode ? GDG_FMT_IEEE64 : in_fmt, kout = recode ? GDG_FMT_IEEE64 : out_fmt;   /* formats the chain kernel sees */
     const size_t kib = n * fmt_bytes(kin), kob = n * fmt_bytes(kout);
-    if (stage_buffers(b, (C + 2) * n)) return -1;
+    if (stage_buffers(b, (C + 3) * n)) return -1;                             /* C channel rows + master L/R + metronome */
     if (recode && b.enc_cap < (C + 2) * n) {
         if (b.d_enc_in) gdgb_free(b.d_enc_in);
         if (b.d_enc_out) gdgb_free(b.d_enc_out);
@@ -944,18 +963,17 @@ int block_submit(int si, gdg_chain *const *chains, size_t C, gdg_tuner *tuner, i
     const int G = (int)((C + per - 1) / per);
     void *s0 = gdgb_stream_handle(0);
     b.staged.clear(); b.out.assign(out, out + n_out_rows); b.ob = ob;
-    for (int g = 0; g < G; g++) {
-        const size_t c0 = (size_t)g * per;
-        if (c0 >= C) break;
-        const size_t cnt = std::min(per, C - c0);
-        if (upload_rows(b, in, c0, cnt, ib, up_dst, 1)) return -1;
-        if (gdgb_record(ev + g % 8, 1)) return backend_fail("event record failed");
+    double *d_metro = nullptr;
+    if (metronome && (spat || meter)) {                                        /* the metronome row rides on the upload stream */
+        d_metro = b.d_in + (C + 2) * n;
+        if (gdgb_h2d_async(d_metro, metronome, n * sizeof(double), 1) || gdgb_record(ev + 18, 1)) return backend_fail("metronome upload failed");
     }
     for (int g = 0; g < G; g++) {
         const size_t c0 = (size_t)g * per;
         if (c0 >= C) break;
         const size_t cnt = std::min(per, C - c0);
-        if (gdgb_wait(0, ev + g % 8)) return backend_fail("stream wait failed");
+        if (upload_rows(b, in, c0, cnt, ib, up_dst, 1)) return -1;
+        if (gdgb_record(ev + g % 8, 1) || gdgb_wait(0, ev + g % 8)) return backend_fail("event failed");
         if (recode && gdgb_convert_rows((const char *)b.d_enc_in + c0 * ib, (long)ib, in_fmt, b.d_in + c0 * n, (long)(n * sizeof(double)), GDG_FMT_IEEE64, (int)cnt, (int)n, s0))
             return backend_fail("payload decode failed");
         if (tuner && tuner_channel >= 0 && (size_t)tuner_channel >= c0 && (size_t)tuner_channel < c0 + cnt)
@@ -970,8 +988,10 @@ int block_submit(int si, gdg_chain *const *chains, size_t C, gdg_tuner *tuner, i
         if (r < 0) return -1;
         if (r == 1) b.staged.push_back({c0, cnt});
     }
+    if (d_metro && gdgb_wait(0, ev + 18)) return backend_fail("stream wait failed");
+    if (d_metro && meter && meter_rows(meter, (uint32_t)(2 * C), d_metro, n, 1, n, rate, s0)) return -1;        /* controller.go:2735-2738: the metronome port */
     if (spat) {                                                                                                 /* controller.go:2761 */
-        if (gdg_spatializer_process_device(spat, b.d_out, n, nullptr, b.d_out + C * n, n, n, 0, s0)) return -1;
+        if (gdg_spatializer_process_device(spat, b.d_out, n, (d_metro && metro_master) ? d_metro : nullptr, b.d_out + C * n, n, n, 0, s0)) return -1;
         if (meter && meter_rows(meter, (uint32_t)(2 * C + 1), b.d_out + C * n, n, 2, n, rate, s0)) return -1;    /* controller.go:2768-2770: master */
         if (recode && gdgb_convert_rows(b.d_out + C * n, (long)(n * sizeof(double)), GDG_FMT_IEEE64, (char *)b.d_enc_out + C * ob, (long)ob, out_fmt, 2, (int)n, s0))
             return backend_fail("payload encode failed");
@@ -1001,12 +1021,14 @@ int free_slot()
     return !g_batch->slot[0].busy ? 0 : (!g_batch->slot[1].busy ? 1 : -1);
 }
 int host_block(gdg_chain *const *chains, size_t C, gdg_tuner *tuner, int tuner_channel, gdg_spatializer *spat, gdg_meter *meter,
-               const void *const *in, int in_fmt, void *const *out, int out_fmt, size_t n_out_rows, size_t n, uint32_t rate)
+               const void *const *in, int in_fmt, void *const *out, int out_fmt, size_t n_out_rows, size_t n, uint32_t rate,
+               const double *metronome, bool metro_master)
 {
+    ProcessLock el(g_edit_mutex);
     std::lock_guard<std::mutex> lk(g_batch_mutex);
     const int si = free_slot();
     if (si < 0) return fail("two submitted blocks are in flight: gdg_controller_wait() for one first");
-    if (block_submit(si, chains, C, tuner, tuner_channel, spat, meter, in, in_fmt, out, out_fmt, n_out_rows, n, rate)) {
+    if (block_submit(si, chains, C, tuner, tuner_channel, spat, meter, in, in_fmt, out, out_fmt, n_out_rows, n, rate, metronome, metro_master)) {
         if (g_batch) { gdgb_sync(); g_batch->slot[si].busy = false; }
         return -1;
     }
@@ -1139,7 +1161,36 @@ static bool parse_index(const std::string &s, std::vector<Descriptor> &out)
         ws(); if (i < s.size() && s[i] == ',') i++;
     }
 }
-/* mono PCM16 (wave.go:400-428) and IEEE float64 (wave.go:714-732) payloads */
+/* the six payload formats of wave.bytesToSamples (wave/wave.go:790-838): LPCM 8 / 16 / 24 / 32 bit (wave.go:316-342, 400-428,
+ * 483-531, 589-617) and IEEE 32 / 64 bit (wave.go:662-689, 714-732); same arithmetic as the device codecs (gdg_interp.cuh) */
+static bool decode_payload(int fmt, int bits, const unsigned char *p, size_t bytes, std::vector<double> &out)
+{
+    if (fmt == 1 && bits == 8) {
+        out.resize(bytes);
+        for (size_t i = 0; i < bytes; i++) { const double r = (1.0 / 127.0) * (double)((int)p[i] - 128); out[i] = r < -1.0 ? -1.0 : (r > 1.0 ? 1.0 : r); }
+    } else if (fmt == 1 && bits == 16) {
+        out.resize(bytes / 2);
+        for (size_t i = 0; i < out.size(); i++) { int16_t v; memcpy(&v, p + 2 * i, 2); out[i] = GDG_PCM16_DECODE_SCALE * (double)v; }
+    } else if (fmt == 1 && bits == 24) {
+        out.resize(bytes / 3);
+        for (size_t i = 0; i < out.size(); i++) {
+            const uint32_t w = (uint32_t)p[3 * i] | ((uint32_t)p[3 * i + 1] << 8) | ((uint32_t)p[3 * i + 2] << 16);
+            int32_t v = (int32_t)w;
+            if (w & 0x00800000u) v = -8388608 + (v & 0x007fffff);
+            out[i] = (2.0 / 16777215.0) * (double)v;
+        }
+    } else if (fmt == 1 && bits == 32) {
+        out.resize(bytes / 4);
+        for (size_t i = 0; i < out.size(); i++) { int32_t v; memcpy(&v, p + 4 * i, 4); out[i] = (2.0 / 4294967295.0) * (double)v; }
+    } else if (fmt == 3 && bits == 32) {
+        out.resize(bytes / 4);
+        for (size_t i = 0; i < out.size(); i++) { float v; memcpy(&v, p + 4 * i, 4); out[i] = (double)v; }
+    } else if (fmt == 3 && bits == 64) {
+        out.resize(bytes / 8);
+        if (!out.empty()) memcpy(out.data(), p, out.size() * 8);
+    } else return false;
+    return true;
+}
 static int parse_wav(const std::vector<unsigned char> &b, std::vector<double> &samples, uint32_t &rate, int &channels, std::string &err)
 {
     if (b.size() < 12 || memcmp(b.data(), "RIFF", 4) || memcmp(b.data() + 8, "WAVE", 4)) { err = "not a RIFF/WAVE file"; return -1; }
@@ -1154,13 +1205,12 @@ static int parse_wav(const std::vector<unsigned char> &b, std::vector<double> &s
             fmt = f; channels = c; rate = r; bits = bp; have_fmt = true;
         } else if (!memcmp(b.data() + pos, "data", 4)) {
             if (!have_fmt) { err = "data chunk before fmt chunk"; return -1; }
-            if (fmt == 1 && bits == 16) {
-                const size_t ns = avail / 2; samples.resize(ns);
-                for (size_t i = 0; i < ns; i++) { int16_t v; memcpy(&v, payload + 2 * i, 2); samples[i] = GDG_PCM16_DECODE_SCALE * (double)v; }
-            } else if (fmt == 3 && bits == 64) {
-                const size_t ns = avail / 8; samples.resize(ns);
-                memcpy(samples.data(), payload, ns * 8);
-            } else { err = "unsupported sample format (only 16-bit PCM and 64-bit IEEE float are read here)"; return -1; }
+            if (!decode_payload(fmt, bits, payload, avail, samples)) { err = "Unknown sample format or bit depth."; return -1; }
+            if (channels > 1) {                                  /* interleaved frames: the caller rejects non-mono files, keep channel 0 */
+                std::vector<double> c0(samples.size() / (size_t)channels);
+                for (size_t i = 0; i < c0.size(); i++) c0[i] = samples[i * (size_t)channels];
+                samples.swap(c0);
+            }
             return 0;
         }
         pos += 8 + (size_t)size + (size & 1);
@@ -1197,6 +1247,7 @@ gdg_chain *gdg_chain_create(gdg_irbank *bank)
 }
 void gdg_chain_destroy(gdg_chain *c)
 {
+    EditLock el(g_edit_mutex);
     std::lock_guard<std::mutex> lk(g_batch_mutex);
     if (g_batch && std::find(g_batch->chains.begin(), g_batch->chains.end(), c) != g_batch->chains.end()) g_batch.reset();
     delete c;
@@ -1204,6 +1255,7 @@ void gdg_chain_destroy(gdg_chain *c)
 #define CHAIN_CHECK(c) if (!(c)) return fail("chain is NULL")
 int gdg_chain_append_unit(gdg_chain *c, int type)
 {
+    EditLock lk(g_edit_mutex);
     if (!c) { fail("chain is NULL"); return -1; }
     Unit *u = create_unit(type, c->bank);
     if (!u) { fail("%s", "Failed to create effects unit."); return -1; }
@@ -1213,6 +1265,7 @@ int gdg_chain_append_unit(gdg_chain *c, int type)
 }
 int gdg_chain_remove_unit(gdg_chain *c, int id)
 {
+    EditLock lk(g_edit_mutex);
     CHAIN_CHECK(c);
     if (id < 0 || id >= (int)c->slots.size()) return fail("Cannot remove unit %d.", id);
     gdgb_sync();
@@ -1221,6 +1274,7 @@ int gdg_chain_remove_unit(gdg_chain *c, int id)
 }
 int gdg_chain_move_up(gdg_chain *c, int id)
 {
+    EditLock lk(g_edit_mutex);
     CHAIN_CHECK(c);
     if (id <= 0 || id >= (int)c->slots.size()) return fail("Cannot move unit %d up.", id);
     std::swap(c->slots[id], c->slots[id - 1]); c->topo_dirty = true;
@@ -1228,6 +1282,7 @@ int gdg_chain_move_up(gdg_chain *c, int id)
 }
 int gdg_chain_move_down(gdg_chain *c, int id)
 {
+    EditLock lk(g_edit_mutex);
     CHAIN_CHECK(c);
     if (id < 0 || id >= (int)c->slots.size() - 1) return fail("Cannot move unit %d down.", id);
     std::swap(c->slots[id], c->slots[id + 1]); c->topo_dirty = true;
@@ -1235,12 +1290,14 @@ int gdg_chain_move_down(gdg_chain *c, int id)
 }
 int gdg_chain_unit_type(gdg_chain *c, int id)
 {
+    ProcessLock lk(g_edit_mutex);
     if (!c) { fail("chain is NULL"); return -1; }
     if (id < 0 || id >= (int)c->slots.size()) { fail("Cannot get unit type: No unit %d.", id); return -1; }
     return c->slots[id].unit->type;
 }
 int gdg_chain_set_bypass(gdg_chain *c, int id, int bypass)
 {
+    EditLock lk(g_edit_mutex);
     CHAIN_CHECK(c);
     if (id < 0 || id >= (int)c->slots.size()) return fail("Cannot %s bypass: No unit %d.", bypass ? "enable" : "disable", id);
     if (c->slots[id].bypass != (bypass != 0)) { c->slots[id].bypass = bypass != 0; c->topo_dirty = true; }
@@ -1248,6 +1305,7 @@ int gdg_chain_set_bypass(gdg_chain *c, int id, int bypass)
 }
 int gdg_chain_get_bypass(gdg_chain *c, int id, int *bypass)
 {
+    ProcessLock lk(g_edit_mutex);
     CHAIN_CHECK(c);
     if (id < 0 || id >= (int)c->slots.size()) return fail("Cannot get bypass value: No unit %d.", id);
     *bypass = c->slots[id].bypass;
@@ -1255,6 +1313,7 @@ int gdg_chain_get_bypass(gdg_chain *c, int id, int *bypass)
 }
 int gdg_chain_set_discrete_value(gdg_chain *c, int id, const char *name, const char *value)
 {
+    EditLock lk(g_edit_mutex);
     CHAIN_CHECK(c);
     if (id < 0 || id >= (int)c->slots.size()) return fail("Cannot set discrete value: No unit %d.", id);
     Unit *u = c->slots[id].unit.get();
@@ -1271,6 +1330,7 @@ int gdg_chain_set_discrete_value(gdg_chain *c, int id, const char *name, const c
 }
 int gdg_chain_get_discrete_value(gdg_chain *c, int id, const char *name, const char **value)
 {
+    ProcessLock lk(g_edit_mutex);
     CHAIN_CHECK(c);
     if (id < 0 || id >= (int)c->slots.size()) return fail("Cannot get discrete value: No unit %d.", id);
     Unit *u = c->slots[id].unit.get();
@@ -1282,6 +1342,7 @@ int gdg_chain_get_discrete_value(gdg_chain *c, int id, const char *name, const c
 }
 int gdg_chain_set_numeric_value(gdg_chain *c, int id, const char *name, int32_t value)
 {
+    EditLock lk(g_edit_mutex);
     CHAIN_CHECK(c);
     if (id < 0 || id >= (int)c->slots.size()) return fail("Cannot set numeric value: No unit %d.", id);
     Unit *u = c->slots[id].unit.get();
@@ -1297,6 +1358,7 @@ int gdg_chain_set_numeric_value(gdg_chain *c, int id, const char *name, int32_t 
 }
 int gdg_chain_get_numeric_value(gdg_chain *c, int id, const char *name, int32_t *value)
 {
+    ProcessLock lk(g_edit_mutex);
     CHAIN_CHECK(c);
     if (id < 0 || id >= (int)c->slots.size()) return fail("Cannot get numeric value: No unit %d.", id);
     Unit *u = c->slots[id].unit.get();
@@ -1306,15 +1368,17 @@ int gdg_chain_get_numeric_value(gdg_chain *c, int id, const char *name, int32_t 
     *value = u->params[idx].num;
     return 0;
 }
-int gdg_chain_length(gdg_chain *c) { return c ? (int)c->slots.size() : 0; }
+int gdg_chain_length(gdg_chain *c) { ProcessLock lk(g_edit_mutex); return c ? (int)c->slots.size() : 0; }
 int gdg_chain_parameter_count(gdg_chain *c, int id)
 {
+    ProcessLock lk(g_edit_mutex);
     if (!c) { fail("chain is NULL"); return -1; }
     if (id < 0 || id >= (int)c->slots.size()) { fail("Cannot get parameters: No unit %d.", id); return -1; }
     return (int)c->slots[id].unit->params.size();
 }
 int gdg_chain_parameter(gdg_chain *c, int id, int index, gdg_parameter *out)
 {
+    ProcessLock lk(g_edit_mutex);
     CHAIN_CHECK(c);
     if (id < 0 || id >= (int)c->slots.size()) return fail("Cannot get parameters: No unit %d.", id);
     Unit *u = c->slots[id].unit.get();
@@ -1357,6 +1421,7 @@ int gdg_chain_process(gdg_chain *c, const double *in, double *out, size_t n, uin
     CHAIN_CHECK(c);
     if (!in || !out) return fail("gdg_chain_process: bad argument");
     if (check_block(n)) return -1;
+    ProcessLock el(g_edit_mutex);
     if (c->d_n < n) {
         gdgb_free(c->d_in); gdgb_free(c->d_out);
         c->d_in = (double *)gdgb_alloc(n * sizeof(double)); c->d_out = (double *)gdgb_alloc(n * sizeof(double));
@@ -1560,6 +1625,7 @@ int gdg_process_batch_encoded_submit(gdg_chain *const *chains, size_t C, const v
     if (!chains || !C || !in || !out) return fail("gdg_process_batch_encoded_submit: bad argument");
     if (!fmt_bytes(in_format) || !fmt_bytes(out_format)) return fail("Unknown sample format: %#04x", fmt_bytes(in_format) ? out_format : in_format);
     if (check_block(n)) return -1;
+    ProcessLock el(g_edit_mutex);
     std::lock_guard<std::mutex> lk(g_batch_mutex);
     const int si = free_slot();
     if (si < 0) return fail("two submitted blocks are in flight: gdg_controller_wait() for one first");
@@ -1577,6 +1643,7 @@ int gdg_process_batch_device_encoded(gdg_chain *const *chains, size_t C, const v
     if (!fmt_bytes(in_format) || !fmt_bytes(out_format)) return fail("Unknown sample format: %#04x", fmt_bytes(in_format) ? out_format : in_format);
     if (in_stride_bytes < n * fmt_bytes(in_format) || out_stride_bytes < n * fmt_bytes(out_format)) return fail("gdg_process_batch_device_encoded: stride too small");
     if (check_block(n)) return -1;
+    ProcessLock el(g_edit_mutex);
     std::lock_guard<std::mutex> lk(g_batch_mutex);
     void *st = stream ? stream : gdgb_stream();
     const int rounds = prepare_batch(chains, C, rate, n, st);
@@ -1692,39 +1759,72 @@ int gdg_meter_analyze(gdg_meter *m, uint32_t channel, int32_t *level, int32_t *p
 }
 
 /* ---- controller.process mirror ---- */
+namespace {
+/* One block of controller.process (controller/controller.go:2648-2783) on HOST rows; `wait` selects the blocking call or the
+ * ticketed submit.  Returns 0 / the ticket, or -1. */
+int controller_block(const char *who, gdg_chain *const *chains, uint32_t C, gdg_tuner *tuner, int tuner_channel, gdg_spatializer *spat,
+                     gdg_meter *meter, const void *const *in, int in_fmt, const double *metronome, int metro_master,
+                     void *const *out, int out_fmt, uint32_t n_out, size_t n, uint32_t rate, bool wait)
+{
+    if (ensure_init()) return -1;
+    if (!chains || !C || !in || !out) return fail("%s: bad argument", who);
+    if (!fmt_bytes(in_fmt) || !fmt_bytes(out_fmt)) return fail("Unknown sample format: %#04x", fmt_bytes(in_fmt) ? out_fmt : in_fmt);
+    if (check_block(n)) return -1;
+    if (meter && meter->count != 2 * C + 3)
+        return fail("%s: the level meter has %u channels, %u inputs need %u (inputs, outputs, metronome, master L/R: controller.go:2710-2771)", who, meter->count, C, 2 * C + 3);
+    if (n_out < C) {
+        /* controller.go:2666-2682: the tuner is fed whatever the number of outputs; the chains only run when nOut >= nIn */
+        if (!wait) return fail("%s: %u output rows for %u channels", who, n_out, C);
+        if (tuner && tuner_channel >= 0 && (uint32_t)tuner_channel < C && in_fmt == GDG_FMT_IEEE64)
+            return gdg_tuner_process(tuner, (const double *)in[tuner_channel], n, rate);
+        return 0;
+    }
+    /* spatializer (and the metronome's way into the master) only with nOut >= nIn + 2 + 1 (controller.go:2650, 2722); callers
+     * that pass no metronome row get the master pair with nIn + 2 rows as before */
+    const bool do_spat = spat && n_out >= C + 2 && spat->count == C;
+    gdg_meter *m = meter && meter->enabled ? meter : nullptr;
+    if (wait)
+        return host_block(chains, C, tuner, tuner_channel, do_spat ? spat : nullptr, m, in, in_fmt, out, out_fmt, (size_t)C + (do_spat ? 2 : 0), n, rate,
+                          metronome, metro_master != 0);
+    ProcessLock el(g_edit_mutex);
+    std::lock_guard<std::mutex> lk(g_batch_mutex);
+    const int si = free_slot();
+    if (si < 0) return fail("two submitted blocks are in flight: gdg_controller_wait() for one first");
+    if (block_submit(si, chains, C, tuner, tuner_channel, do_spat ? spat : nullptr, m, in, in_fmt, out, out_fmt, (size_t)C + (do_spat ? 2 : 0), n, rate,
+                     metronome, metro_master != 0)) {
+        if (g_batch) { gdgb_sync(); g_batch->slot[si].busy = false; }
+        return -1;
+    }
+    return si;
+}
+} // namespace
+
 int gdg_controller_process_metered(gdg_chain *const *chains, uint32_t C, gdg_tuner *tuner, int tuner_channel, gdg_spatializer *spat,
                                    gdg_meter *meter, const double *const *in, double *const *out, uint32_t n_out, size_t n, uint32_t rate)
 {
-    if (ensure_init()) return -1;
-    if (!chains || !C || !in || !out) return fail("gdg_controller_process: bad argument");
-    if (check_block(n)) return -1;
-    if (meter && meter->count != 2 * C + 3)
-        return fail("gdg_controller_process: the level meter has %u channels, %u inputs need %u (inputs, outputs, metronome, master L/R: controller.go:2710-2771)", meter->count, C, 2 * C + 3);
-    if (n_out < C) return 0;                                /* controller.go:2682: nothing happens */
-    const bool do_spat = spat && n_out >= C + 2 && spat->count == C;
-    return host_block(chains, C, tuner, tuner_channel, do_spat ? spat : nullptr, meter && meter->enabled ? meter : nullptr, (const void *const *)in,
-                      GDG_FMT_IEEE64, (void *const *)out, GDG_FMT_IEEE64, (size_t)C + (do_spat ? 2 : 0), n, rate);
+    return controller_block("gdg_controller_process", chains, C, tuner, tuner_channel, spat, meter, (const void *const *)in, GDG_FMT_IEEE64, nullptr, 0,
+                            (void *const *)out, GDG_FMT_IEEE64, n_out, n, rate, true);
+}
+int gdg_controller_process_aux(gdg_chain *const *chains, uint32_t C, gdg_tuner *tuner, int tuner_channel, gdg_spatializer *spat,
+                               gdg_meter *meter, const double *const *in, const double *metronome, int metronome_to_master,
+                               double *const *out, uint32_t n_out, size_t n, uint32_t rate)
+{
+    return controller_block("gdg_controller_process_aux", chains, C, tuner, tuner_channel, spat, meter, (const void *const *)in, GDG_FMT_IEEE64, metronome,
+                            metronome_to_master, (void *const *)out, GDG_FMT_IEEE64, n_out, n, rate, true);
 }
 /* the same block, submitted without waiting: returns a ticket (0 or 1) for gdg_controller_wait */
 int gdg_controller_submit(gdg_chain *const *chains, uint32_t C, gdg_tuner *tuner, int tuner_channel, gdg_spatializer *spat,
                           gdg_meter *meter, const double *const *in, double *const *out, uint32_t n_out, size_t n, uint32_t rate)
 {
-    if (ensure_init()) return -1;
-    if (!chains || !C || !in || !out) return fail("gdg_controller_submit: bad argument");
-    if (check_block(n)) return -1;
-    if (meter && meter->count != 2 * C + 3)
-        return fail("gdg_controller_submit: the level meter has %u channels, %u inputs need %u (inputs, outputs, metronome, master L/R: controller.go:2710-2771)", meter->count, C, 2 * C + 3);
-    if (n_out < C) return fail("gdg_controller_submit: %u output rows for %u channels", n_out, C);
-    const bool do_spat = spat && n_out >= C + 2 && spat->count == C;
-    std::lock_guard<std::mutex> lk(g_batch_mutex);
-    const int si = free_slot();
-    if (si < 0) return fail("two submitted blocks are in flight: gdg_controller_wait() for one first");
-    if (block_submit(si, chains, C, tuner, tuner_channel, do_spat ? spat : nullptr, meter && meter->enabled ? meter : nullptr, (const void *const *)in,
-                     GDG_FMT_IEEE64, (void *const *)out, GDG_FMT_IEEE64, (size_t)C + (do_spat ? 2 : 0), n, rate)) {
-        if (g_batch) { gdgb_sync(); g_batch->slot[si].busy = false; }
-        return -1;
-    }
-    return si;
+    return controller_block("gdg_controller_submit", chains, C, tuner, tuner_channel, spat, meter, (const void *const *)in, GDG_FMT_IEEE64, nullptr, 0,
+                            (void *const *)out, GDG_FMT_IEEE64, n_out, n, rate, false);
+}
+int gdg_controller_submit_aux(gdg_chain *const *chains, uint32_t C, gdg_tuner *tuner, int tuner_channel, gdg_spatializer *spat,
+                              gdg_meter *meter, const double *const *in, const double *metronome, int metronome_to_master,
+                              double *const *out, uint32_t n_out, size_t n, uint32_t rate)
+{
+    return controller_block("gdg_controller_submit_aux", chains, C, tuner, tuner_channel, spat, meter, (const void *const *)in, GDG_FMT_IEEE64, metronome,
+                            metronome_to_master, (void *const *)out, GDG_FMT_IEEE64, n_out, n, rate, false);
 }
 /* gdg_controller_submit with encoded host rows (wave.go sample formats): the payload is decoded / encoded on the device,
  * tuner, spatializer and meter see float64 */
@@ -1732,23 +1832,8 @@ int gdg_controller_submit_encoded(gdg_chain *const *chains, uint32_t C, gdg_tune
                                   gdg_meter *meter, const void *const *in, int in_format, void *const *out, int out_format,
                                   uint32_t n_out, size_t n, uint32_t rate)
 {
-    if (ensure_init()) return -1;
-    if (!chains || !C || !in || !out) return fail("gdg_controller_submit_encoded: bad argument");
-    if (!fmt_bytes(in_format) || !fmt_bytes(out_format)) return fail("Unknown sample format: %#04x", fmt_bytes(in_format) ? out_format : in_format);
-    if (check_block(n)) return -1;
-    if (meter && meter->count != 2 * C + 3)
-        return fail("gdg_controller_submit_encoded: the level meter has %u channels, %u inputs need %u (inputs, outputs, metronome, master L/R: controller.go:2710-2771)", meter->count, C, 2 * C + 3);
-    if (n_out < C) return fail("gdg_controller_submit_encoded: %u output rows for %u channels", n_out, C);
-    const bool do_spat = spat && n_out >= C + 2 && spat->count == C;
-    std::lock_guard<std::mutex> lk(g_batch_mutex);
-    const int si = free_slot();
-    if (si < 0) return fail("two submitted blocks are in flight: gdg_controller_wait() for one first");
-    if (block_submit(si, chains, C, tuner, tuner_channel, do_spat ? spat : nullptr, meter && meter->enabled ? meter : nullptr, in, in_format, out,
-                     out_format, (size_t)C + (do_spat ? 2 : 0), n, rate)) {
-        if (g_batch) { gdgb_sync(); g_batch->slot[si].busy = false; }
-        return -1;
-    }
-    return si;
+    return controller_block("gdg_controller_submit_encoded", chains, C, tuner, tuner_channel, spat, meter, in, in_format, nullptr, 0, out, out_format,
+                            n_out, n, rate, false);
 }
 int gdg_controller_wait(int ticket)
 {

@@ -16,7 +16,13 @@
  *     powers of two, filter/filter.go:372-455) - other sizes are REJECTED, where
  *     the reference would panic or silently misbehave;
  *   - there is NO CPU fallback: without a CUDA device gdg_init() fails and every
- *     processing call fails.
+ *     processing call fails;
+ *   - threading (effects/effects.go:98, signal/signal.go:45: RWMutex per unit / chain): every mutator and getter of a
+ *     chain may be called from any thread while another thread processes blocks - they serialise against the
+ *     "resolve parameters + enqueue kernels" part of the processing calls, a change takes effect at the next block
+ *     boundary.  Processing the SAME chain from two threads at once is not allowed (as in the reference);
+ *     gdg_last_error() is per thread: fetch it on the thread that made the failing call (cgo: runtime.LockOSThread,
+ *     see INTEGRATION.md).
  */
 #ifndef GDG_H
 #define GDG_H
@@ -210,6 +216,17 @@ int gdg_controller_submit(gdg_chain *const *chains, uint32_t channels, gdg_tuner
                           gdg_spatializer *spat, gdg_meter *meter, const double *const *in, double *const *out,
                           uint32_t n_out, size_t n, uint32_t sample_rate);
 int gdg_controller_wait(int ticket);
+/* The same two calls WITH the metronome of controller.go:2722-2761: `metronome` is the host row (n float64 samples) that
+ * metronome.Process just wrote (the reference hands it to the spatializer as auxInputBuffer, spatializer.go:300-308), or NULL
+ * when there is no metronome.  It feeds level-meter channel 2C (controller.go:2735-2738) and - when metronome_to_master is
+ * non-zero (controller.go:2746-2748 metrMasterOutput) - is added to both master channels.  The metronome generator itself
+ * stays on the host (out of scope). */
+int gdg_controller_process_aux(gdg_chain *const *chains, uint32_t channels, gdg_tuner *tuner, int tuner_channel,
+                               gdg_spatializer *spat, gdg_meter *meter, const double *const *in, const double *metronome,
+                               int metronome_to_master, double *const *out, uint32_t n_out, size_t n, uint32_t sample_rate);
+int gdg_controller_submit_aux(gdg_chain *const *chains, uint32_t channels, gdg_tuner *tuner, int tuner_channel,
+                              gdg_spatializer *spat, gdg_meter *meter, const double *const *in, const double *metronome,
+                              int metronome_to_master, double *const *out, uint32_t n_out, size_t n, uint32_t sample_rate);
 /* gdg_controller_submit on ENCODED host rows (the data-chunk payload of wave/wave.go's formats, GDG_FORMAT_*): rows are
  * decoded to float64 on the device, tuner feed / chains / spatializer / meter run as above, the C (+2) output rows come
  * back encoded - the whole of controller.go:2908-3143 for one block without a float64 ever crossing PCIe. */

@@ -31,7 +31,7 @@ def backend_lib(kind):
         if kind == "emu":
             sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
             import build_emu
-            _libs[kind] = gdg.load(build_emu.build())
+            _libs[kind] = gdg.load(build_emu.build(), _test_backend=True)
         elif kind == "cuda":
             lib = gdg.load()                       # fails loudly if libgdg.so is missing
             gdg.init(-1, lib)                      # fails loudly without a B200

@@ -153,6 +153,31 @@ def test_irbank_import_json_and_wav(tmp_path, monkeypatch):
         gdg.IRBank.import_file("nope.json", lib)
 
 
+@pytest.mark.parametrize("fmt", [0, 1, 2, 3, 4, 5])
+def test_irbank_import_every_wave_format(tmp_path, monkeypatch, fmt):
+    """filter.Import reads its files through wave.FromBuffer: all six payload formats of wave.go:790-838 (user impulse
+    responses in 24-bit PCM or float32 are common).  The imported response must equal the oracle's decode of the same bytes."""
+    lib = common.backend_lib("emu")
+    monkeypatch.chdir(tmp_path)
+    rng = np.random.default_rng(fmt)
+    h = rng.uniform(-0.9, 0.9, 257) * np.exp(-np.arange(257) / 40.0)
+    payload = orc.wave_encode(fmt, h).tobytes()
+    bits = [8, 16, 24, 32, 32, 64][fmt]
+    tag = 1 if fmt < 4 else 3
+    with open("ir.wav", "wb") as f:
+        f.write(b"RIFF" + struct.pack("<I", 36 + len(payload)) + b"WAVE")
+        f.write(b"fmt " + struct.pack("<IHHIIHH", 16, tag, 1, 48000, 48000 * bits // 8, bits // 8, bits))
+        f.write(b"data" + struct.pack("<I", len(payload)) + payload)
+    json.dump([{"Name": "user ir", "Path": "ir.wav", "Compensation": -2}], open("index.json", "w"))
+    pb = gdg.IRBank.import_file("index.json", lib)
+    assert pb.names() == ["user ir"]
+    ob = orc.IRBank()
+    ob.add("user ir", -2, orc.wave_decode(fmt, np.frombuffer(payload, dtype=np.uint8)), 48000)
+    a, b = common.make_chain_pair(lib, [("power_amp", {}, {"filter_1": "user ir"})], (ob, pb))
+    x = common.synth_fast(2, 48000, 2 * 1024)
+    common.compare_stream(a, b, x, 1024, 48000, label="import fmt %d" % fmt)
+
+
 def test_parameter_table_matches_reference_source():
     if not os.path.isdir("/root/reference/effects"):
         pytest.skip("reference tree not present (GPU box)")

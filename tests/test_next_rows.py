@@ -1,5 +1,6 @@
 """SURVEY.md 8(f) rows built so far: the wave sample codecs fused into the chain kernel's load/store and
 resample.Time on the device - same parity bar as the hot path (bit-exact for the integer/byte work)."""
+import ctypes as C_
 import json
 import os
 
@@ -348,3 +349,87 @@ def test_controller_submit_encoded(lib, fmt):
     assert t.analyze() == rt.analyze()
     for c in (0, C, 2 * C + 1, 2 * C + 2):
         assert m.state(c) == rm.state(c)
+
+
+# ---- the metronome row (auxInputBuffer) through the controller mirror, setters under load ----------------------
+def test_controller_process_metronome_into_master_and_meter(lib):
+    """controller.go:2722-2761: the metronome's buffer feeds meter port 2C and - with metrMasterOutput - both master channels
+    through spatializer.Process' auxInputBuffer (spatializer.go:300-308)."""
+    fs, n, C = 48000, 512, 3
+    gc, oc = [], []
+    for c in range(C):
+        a, b = common.make_chain_pair(lib, [("distortion", {"gain": 6 + c}, {}), ("tremolo", {}, {})])
+        oc.append(a); gc.append(b)
+    gs, os_ = gdg.Spatializer(C, lib=lib), orc.Spatializer(C)
+    for c in range(C):
+        gs.set_azimuth(c, -45.0 + 45.0 * c); os_.set_azimuth(c, -45.0 + 45.0 * c)
+    m, o = _meter_pair(lib, 2 * C + 3)
+    m.set_enabled(True); o.set_enabled(True)
+    rng = np.random.default_rng(4)
+    for blk in range(4):
+        x = np.stack([common.synth_fast(c, fs, 4 * n, 3)[blk * n:(blk + 1) * n] for c in range(C)])
+        click = np.where(np.arange(n) < 40, 0.25 * rng.uniform(-1, 1, n), 0.0)
+        to_master = blk % 2 == 0
+        got = gdg.controller_process(gc, None, -1, gs, x, fs, meter=m, metronome=click, metronome_to_master=to_master)
+        outs = np.stack([oc[c].process(x[c], fs) for c in range(C)])
+        master = os_.process(outs, click if to_master else None)
+        assert np.max(np.abs(got[:C] - outs)) < 1e-9 and np.max(np.abs(got[C:] - master)) < 1e-9
+        o.process(list(x) + list(outs) + [click] + list(master), fs)
+    _assert_meters_agree(m, o, 2 * C + 3)
+    assert m.analyze(2 * C)[0] > -60                         # the metronome port saw the click
+
+
+def test_tuner_is_fed_even_without_output_rows(lib):
+    """controller.go:2666-2672 feeds the tuner before it looks at the number of outputs; with nOut < nIn nothing else runs."""
+    fs, n, C = 48000, 4096, 2
+    chains = [common.build_chain(gdg.Chain(lib=lib), [("tone_stack", {}, {})]) for _ in range(C)]
+    gt, ot = gdg.Tuner(lib=lib), orc.Tuner()
+    t = np.arange(24 * n) / fs
+    x = 0.5 * np.sin(2 * np.pi * 110.0 * t)
+    for k in range(24):
+        rows = np.stack([x[k * n:(k + 1) * n], np.zeros(n)])
+        ip = (C_.c_void_p * C)(*[rows[i].ctypes.data for i in range(C)])
+        out = np.zeros((1, n))
+        op = (C_.c_void_p * 1)(out[0].ctypes.data)
+        assert lib.gdg_controller_process(gdg._handles(chains), C, gt._h, 0, None, ip, op, 1, n, fs) == 0
+        assert not out.any()
+        ot.process(rows[0], fs)
+    assert gt.analyze()["note"] == ot.analyze()["note"] == "A2"
+
+
+def test_setters_race_free_against_processing(lib):
+    """effects.go:98 / signal.go:45: parameter and topology edits arrive from another thread while blocks are processed.
+    Every block must equal one of the oracle's outputs for SOME interleaving - here the edits toggle between two whole
+    configurations under a lock shared with the checker, so each block is checked against the configuration it ran with;
+    the point of the test is that nothing crashes, deadlocks or reads freed state (RemoveUnit frees device memory)."""
+    import threading
+    fs, n = 48000, 256
+    chain = common.build_chain(gdg.Chain(lib=lib), [("overdrive", {"gain": 10}, {}), ("delay", {"delay_time": 5}, {}), ("cabinet", {}, {})])
+    stop = threading.Event()
+    errors = []
+
+    def hammer():
+        k = 0
+        try:
+            while not stop.is_set():
+                chain.set_numeric_value(0, "gain", 5 + k % 20)
+                chain.set_bypass(1, k % 3 == 0)
+                i = chain.append_unit("tremolo")
+                chain.set_bypass(i, False)
+                chain.get_numeric_value(0, "gain"), chain.parameters(0), chain.length()
+                chain.remove_unit(i)
+                if k % 5 == 0:
+                    chain.move_down(0), chain.move_up(1)
+                k += 1
+        except Exception as e:                               # noqa: BLE001
+            errors.append(e)
+    th = threading.Thread(target=hammer)
+    th.start()
+    x = common.synth_fast(1, fs, 150 * n)
+    try:
+        for k in range(150):
+            y = chain.process(x[k * n:(k + 1) * n], fs)
+            assert np.all(np.isfinite(y)) and np.max(np.abs(y)) <= 1.0 + 1e-12
+    finally:
+        stop.set(); th.join()
+    assert not errors, errors
