@@ -610,17 +610,27 @@ int check_block(size_t n)
 
 /* ---- signal.Chain ----------------------------------------------------------- */
 struct Slot { std::unique_ptr<Unit> unit; bool bypass; };
+/* The active units of a chain are cut into SEGMENTS, each one kernel launch ("round") per block:
+ *   kind 0  block-resident chain kernel (k_chain): up to GDG_MAX_SLOTS units of any type;
+ *   kind 1  oversampled-run kernel (k_os): a maximal run of consecutive excess / fuzz / overdrive / distortion units
+ *           with oversampling "2" or "4" (up to GDG_OSK_MAX_UNITS per launch), streamed tile by tile at four CTAs per SM. */
+enum { SEG_CHAIN = 0, SEG_OS = 1, SEG_KINDS = 2 };
+#define GDG_OSK_MAX_UNITS_HOST 6                /* == GDG_OSK_MAX_UNITS (gdg_os.cuh) */
 struct gdg_chain {
     gdg_irbank *bank;
     std::vector<Slot> slots;
-    /* device descriptors: one per fused segment of <= GDG_MAX_SLOTS active units */
-    std::vector<gdg_chain_desc *> d_desc; std::vector<gdg_chain_desc> h_desc;
+    /* device descriptors: one per segment */
+    std::vector<gdg_chain_desc *> d_desc; std::vector<gdg_chain_desc> h_desc; std::vector<int> seg_kind;
     bool topo_dirty = true;
     bool uploaded = false;                                      /* set when prepare() touched device memory */
     double *d_in = nullptr, *d_out = nullptr; size_t d_n = 0;   /* single-channel staging for gdg_chain_process */
-    const gdg_chain_desc **d_self = nullptr; size_t self_rounds = 0;   /* one-entry pointer tables (one per segment round) */
-    ~gdg_chain() { for (auto p : d_desc) gdgb_free(p); if (d_in) gdgb_free(d_in); if (d_out) gdgb_free(d_out); gdgb_free((void *)d_self); }
+    struct Batch *self = nullptr;                               /* one-chain launch tables of gdg_chain_process */
+    ~gdg_chain();
 
+    static bool is_os(const Unit *u)
+    {
+        return (u->type == GDG_UNIT_EXCESS || u->type == GDG_UNIT_FUZZ || u->type == GDG_UNIT_OVERDRIVE || u->type == GDG_UNIT_DISTORTION) && u->os_factor() > 1;
+    }
     /* bring the device descriptors up to date; returns number of segments or -1 */
     int prepare(uint32_t rate, size_t n)
     {
@@ -632,16 +642,22 @@ struct gdg_chain {
             if (r > 0) changed = true;
             active.push_back(s.unit.get());
         }
-        const size_t nseg = active.empty() ? 1 : (active.size() + GDG_MAX_SLOTS - 1) / GDG_MAX_SLOTS;
-        if (!changed && h_desc.size() == nseg) return (int)nseg;
-        uploaded = true;
-        h_desc.assign(nseg, gdg_chain_desc());
-        for (size_t g = 0; g < nseg; g++) {
-            gdg_chain_desc &cd = h_desc[g];
-            memset(&cd, 0, sizeof cd);
-            for (size_t k = g * GDG_MAX_SLOTS; k < active.size() && k < (g + 1) * GDG_MAX_SLOTS; k++)
-                cd.slot[cd.nslots++] = active[k]->desc;
+        if (!changed && !h_desc.empty()) return (int)h_desc.size();
+        static const bool split_os = !getenv("GDG_NO_OS_KERNEL");     /* development knob: everything through k_chain */
+        std::vector<gdg_chain_desc> segs; std::vector<int> kinds;
+        for (Unit *u : active) {
+            const int kind = (split_os && is_os(u)) ? SEG_OS : SEG_CHAIN;
+            const int cap = kind == SEG_OS ? GDG_OSK_MAX_UNITS_HOST : GDG_MAX_SLOTS;
+            if (segs.empty() || kinds.back() != kind || segs.back().nslots >= cap) {
+                gdg_chain_desc cd; memset(&cd, 0, sizeof cd);
+                segs.push_back(cd); kinds.push_back(kind);
+            }
+            segs.back().slot[segs.back().nslots++] = u->desc;
         }
+        if (segs.empty()) { gdg_chain_desc cd; memset(&cd, 0, sizeof cd); segs.push_back(cd); kinds.push_back(SEG_CHAIN); }   /* pass-through */
+        uploaded = true;
+        h_desc = segs; seg_kind = kinds;
+        const size_t nseg = h_desc.size();
         while (d_desc.size() < nseg) {
             gdg_chain_desc *p = (gdg_chain_desc *)gdgb_alloc(sizeof(gdg_chain_desc));
             if (!p) return backend_fail("descriptor allocation failed");
@@ -656,11 +672,16 @@ struct gdg_chain {
 
 namespace {
 
-/* a batch = ordered list of chains; caches the device array of descriptor pointers per segment round */
+/* a batch = ordered list of chains; caches the device launch tables: per segment round and kernel kind the array of
+ * descriptor pointers (NULL = this channel has no segment of that kind in that round), and the segment count per channel */
+} // namespace
 struct Batch {
     std::vector<gdg_chain *> chains;
-    std::vector<std::vector<const gdg_chain_desc *>> h_ptrs;     /* [round][channel] */
+    std::vector<std::vector<const gdg_chain_desc *>> h_ptrs;     /* [round * SEG_KINDS + kind][channel] */
     std::vector<const gdg_chain_desc **> d_ptrs;
+    std::vector<bool> kind_used;                                 /* [round * SEG_KINDS + kind] */
+    std::vector<int32_t> h_nseg; int32_t *d_nseg = nullptr;
+    double *d_scratch = nullptr; size_t scratch_cap = 0;         /* float64 rows between the rounds of encoded calls */
     /* two staging slots: block k+1 can be submitted (its upload overlapping block k's kernels and download) before
      * block k is waited for; the synchronous entry points use whichever slot is free */
     struct Slot {
@@ -673,24 +694,22 @@ struct Batch {
     } slot[2];
     ~Batch() {
         for (auto p : d_ptrs) gdgb_free((void *)p);
+        gdgb_free(d_nseg); gdgb_free(d_scratch);
         for (auto &sl : slot) { if (sl.d_in) gdgb_free(sl.d_in); if (sl.d_out) gdgb_free(sl.d_out); if (sl.d_enc_in) gdgb_free(sl.d_enc_in); if (sl.d_enc_out) gdgb_free(sl.d_enc_out); if (sl.h_stage) gdgb_pinned_free(sl.h_stage); if (sl.h_stage2) gdgb_pinned_free(sl.h_stage2); }
     }
 };
+namespace {
 std::mutex g_batch_mutex;
 std::unique_ptr<Batch> g_batch;
+} // namespace
+gdg_chain::~gdg_chain() { for (auto p : d_desc) gdgb_free(p); if (d_in) gdgb_free(d_in); if (d_out) gdgb_free(d_out); delete self; }
+namespace {
 
-/* bring descriptors + pointer tables of the batch up to date; returns the number of segment rounds or -1 */
-int prepare_batch(gdg_chain *const *chains, size_t C, uint32_t rate, size_t n, void *stream)
+/* bring descriptors + launch tables of batch `b` up to date; returns the number of segment rounds or -1 */
+int prepare_tables(Batch &b, gdg_chain *const *chains, size_t C, uint32_t rate, size_t n, void *stream)
 {
-    if (!g_batch || g_batch->chains.size() != C || !std::equal(g_batch->chains.begin(), g_batch->chains.end(), chains)) {
-        if (g_batch && (g_batch->slot[0].busy || g_batch->slot[1].busy))
-            return fail("a submitted block of another chain set is still in flight: gdg_controller_wait() for it first");
-        g_batch.reset(new Batch());
-        g_batch->chains.assign(chains, chains + C);
-    }
-    Batch &b = *g_batch;
     size_t rounds = 1;
-    std::vector<int> nseg(C);
+    std::vector<int32_t> nseg(C);
     for (size_t c = 0; c < C; c++) {
         const int r = chains[c]->prepare(rate, n);
         if (r < 0) return -1;
@@ -698,41 +717,81 @@ int prepare_batch(gdg_chain *const *chains, size_t C, uint32_t rate, size_t n, v
     }
     bool touched = false;
     for (size_t c = 0; c < C; c++) if (chains[c]->uploaded) { touched = true; chains[c]->uploaded = false; }
-    if (touched || b.h_ptrs.size() != rounds) {          /* pointer tables only change when some chain changed */
-        std::vector<std::vector<const gdg_chain_desc *>> ptrs(rounds, std::vector<const gdg_chain_desc *>(C, nullptr));
+    if (touched || b.h_ptrs.size() != rounds * SEG_KINDS) {          /* tables only change when some chain changed */
+        std::vector<std::vector<const gdg_chain_desc *>> ptrs(rounds * SEG_KINDS, std::vector<const gdg_chain_desc *>(C, nullptr));
+        std::vector<bool> used(rounds * SEG_KINDS, false);
         for (size_t r = 0; r < rounds; r++)
-            for (size_t c = 0; c < C; c++) if ((int)r < nseg[c]) ptrs[r][c] = chains[c]->d_desc[r];
-        if (ptrs != b.h_ptrs) {
+            for (size_t c = 0; c < C; c++) if ((int)r < nseg[c]) {
+                const size_t t = r * SEG_KINDS + (size_t)chains[c]->seg_kind[r];
+                ptrs[t][c] = chains[c]->d_desc[r]; used[t] = true;
+            }
+        if (ptrs != b.h_ptrs || nseg != b.h_nseg) {
+            gdgb_sync();                                              /* launches still reading the old tables */
             for (auto p : b.d_ptrs) gdgb_free((void *)p);
             b.d_ptrs.clear();
-            for (size_t r = 0; r < rounds; r++) {
+            for (size_t t = 0; t < ptrs.size(); t++) {
                 const gdg_chain_desc **dp = (const gdg_chain_desc **)gdgb_alloc(C * sizeof(void *));
-                if (!dp || gdgb_upload((void *)dp, ptrs[r].data(), C * sizeof(void *))) return backend_fail("descriptor table upload failed");
+                if (!dp || gdgb_upload((void *)dp, ptrs[t].data(), C * sizeof(void *))) return backend_fail("descriptor table upload failed");
                 b.d_ptrs.push_back(dp);
             }
-            b.h_ptrs = ptrs;
+            gdgb_free(b.d_nseg);
+            b.d_nseg = (int32_t *)gdgb_alloc(C * sizeof(int32_t));
+            if (!b.d_nseg || gdgb_upload(b.d_nseg, nseg.data(), C * sizeof(int32_t))) return backend_fail("segment table upload failed");
+            b.h_ptrs = ptrs; b.kind_used = used; b.h_nseg = nseg;
         }
         /* descriptor / state uploads run on the library stream: order a foreign stream after them */
         if (stream != gdgb_stream() && gdgb_sync()) return backend_fail("synchronize failed");
     }
     return (int)rounds;
 }
+int prepare_batch(gdg_chain *const *chains, size_t C, uint32_t rate, size_t n, void *stream)
+{
+    if (!g_batch || g_batch->chains.size() != C || !std::equal(g_batch->chains.begin(), g_batch->chains.end(), chains)) {
+        if (g_batch && (g_batch->slot[0].busy || g_batch->slot[1].busy))
+            return fail("a submitted block of another chain set is still in flight: gdg_controller_wait() for it first");
+        gdgb_sync();
+        g_batch.reset(new Batch());
+        g_batch->chains.assign(chains, chains + C);
+    }
+    return prepare_tables(*g_batch, chains, C, rate, n, stream);
+}
 size_t fmt_bytes(int fmt) { static const size_t b[6] = {1, 2, 3, 4, 4, 8}; return (fmt >= 0 && fmt < 6) ? b[fmt] : 0; }
 
-/* launch channels [c0, c0 + cnt) of the prepared batch; strides in bytes, samples in the given formats */
+/* launch channels [c0, c0 + cnt) of prepared batch `b`; strides in bytes, samples in the given formats.  Round r of channel
+ * c reads the caller's input rows when r == 0 and the float64 rows of the previous round otherwise, and writes the caller's
+ * output rows when it is the channel's LAST segment, float64 rows otherwise.  With float64 I/O the in-between rows are the
+ * output rows themselves; encoded calls with more than one round keep them in a scratch buffer. */
+int launch_tables(Batch &b, size_t c0, size_t cnt, int rounds, const void *d_in, size_t in_stride, int in_fmt,
+                  void *d_out, size_t out_stride, int out_fmt, size_t n, void *stream)
+{
+    unsigned char *mid = (unsigned char *)d_out; size_t mid_stride = out_stride;
+    if (rounds > 1 && out_fmt != GDG_FMT_IEEE64) {
+        const size_t C = b.chains.size();
+        if (b.scratch_cap < C * n) {
+            gdgb_sync(); gdgb_free(b.d_scratch);
+            b.d_scratch = (double *)gdgb_alloc(C * n * sizeof(double));
+            if (!b.d_scratch) return backend_fail("scratch allocation failed");
+            b.scratch_cap = C * n;
+            if (stream != gdgb_stream() && gdgb_sync()) return backend_fail("synchronize failed");
+        }
+        mid = (unsigned char *)b.d_scratch; mid_stride = n * sizeof(double);
+    }
+    for (int r = 0; r < rounds; r++)
+        for (int k = 0; k < SEG_KINDS; k++) {
+            const size_t t = (size_t)r * SEG_KINDS + (size_t)k;
+            if (!b.kind_used[t]) continue;
+            if (gdgb_launch_segments(k, b.d_ptrs[t] + c0, b.d_nseg + c0, r, (int)cnt,
+                                     (const unsigned char *)d_in + c0 * in_stride, (long)in_stride, in_fmt,
+                                     (unsigned char *)d_out + c0 * out_stride, (long)out_stride, out_fmt,
+                                     mid + c0 * mid_stride, (long)mid_stride, (int)n, stream))
+                return backend_fail("chain kernel launch failed");
+        }
+    return 0;
+}
 int launch_batch_fmt(size_t c0, size_t cnt, int rounds, const void *d_in, size_t in_stride, int in_fmt,
                      void *d_out, size_t out_stride, int out_fmt, size_t n, void *stream)
 {
-    Batch &b = *g_batch;
-    if (rounds > 1 && (in_fmt != GDG_FMT_IEEE64 || out_fmt != GDG_FMT_IEEE64))
-        return fail("encoded sample formats need chains of at most %d active units (one fused segment)", GDG_MAX_SLOTS);
-    for (int r = 0; r < rounds; r++) {
-        const unsigned char *src = r == 0 ? (const unsigned char *)d_in + c0 * in_stride : (const unsigned char *)d_out + c0 * out_stride;
-        if (gdgb_launch_chains(b.d_ptrs[r] + c0, (int)cnt, src, (long)(r == 0 ? in_stride : out_stride), r == 0 ? in_fmt : out_fmt,
-                               (unsigned char *)d_out + c0 * out_stride, (long)out_stride, out_fmt, (int)n, stream))
-            return backend_fail("chain kernel launch failed");
-    }
-    return 0;
+    return launch_tables(*g_batch, c0, cnt, rounds, d_in, in_stride, in_fmt, d_out, out_stride, out_fmt, n, stream);
 }
 int launch_batch(size_t c0, size_t cnt, int rounds, const double *d_in, double *d_out, size_t stride, size_t n, void *stream)
 {
@@ -1429,20 +1488,13 @@ int gdg_chain_process(gdg_chain *c, const double *in, double *out, size_t n, uin
         c->d_n = n;
     }
     if (gdgb_upload(c->d_in, in, n * sizeof(double))) return backend_fail("upload failed");
-    /* single chain (the JACK path calls Chain.Process per channel): its own pointer table, no batch cache churn */
-    const int rounds = c->prepare(rate, n);
+    /* single chain (the JACK path calls Chain.Process per channel): its own launch tables, no batch cache churn */
+    if (!c->self) { c->self = new Batch(); c->self->chains.assign(1, c); }
+    gdg_chain *one[1] = {c};
+    const int rounds = prepare_tables(*c->self, one, 1, rate, n, gdgb_stream());
     if (rounds < 0) return -1;
-    if (c->self_rounds != (size_t)rounds) {                /* descriptor addresses are stable; only their number can change */
-        gdgb_sync(); gdgb_free((void *)c->d_self);
-        c->d_self = (const gdg_chain_desc **)gdgb_alloc((size_t)rounds * sizeof(void *));
-        std::vector<const gdg_chain_desc *> ptrs(c->d_desc.begin(), c->d_desc.begin() + rounds);
-        if (!c->d_self || gdgb_upload((void *)c->d_self, ptrs.data(), ptrs.size() * sizeof(void *))) return backend_fail("descriptor table upload failed");
-        c->self_rounds = (size_t)rounds;
-    }
-    for (int r = 0; r < rounds; r++)
-        if (gdgb_launch_chains(c->d_self + r, 1, r == 0 ? c->d_in : c->d_out, (long)(n * sizeof(double)), GDG_FMT_IEEE64, c->d_out,
-                               (long)(n * sizeof(double)), GDG_FMT_IEEE64, (int)n, gdgb_stream()))
-            return backend_fail("chain kernel launch failed");
+    if (launch_tables(*c->self, 0, 1, rounds, c->d_in, n * sizeof(double), GDG_FMT_IEEE64, c->d_out, n * sizeof(double), GDG_FMT_IEEE64, n, gdgb_stream()))
+        return -1;
     return gdgb_download(out, c->d_out, n * sizeof(double)) ? backend_fail("download failed") : 0;
 }
 

@@ -13,6 +13,7 @@
 
 #include "gdg_backend.h"
 #include "gdg_interp.cuh"
+#include "gdg_os.cuh"
 
 static thread_local std::string t_err;
 static int g_device = -1, g_sms = 0;
@@ -29,19 +30,39 @@ static int cu_fail(const char *what, cudaError_t e)
 #define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cu_fail(#call, e_); } while (0)
 
 /* ---- kernels ------------------------------------------------------------------- */
+/* source / destination rows of channel c in segment round `round` (see gdgb_launch_segments) */
+struct gdg_io { const unsigned char *src; unsigned char *dst; int src_fmt, dst_fmt; };
+__device__ __forceinline__ gdg_io segment_io(int c, int round, int nseg, const unsigned char *in, long in_stride, int in_fmt,
+                                             unsigned char *out, long out_stride, int out_fmt, unsigned char *mid, long mid_stride)
+{
+    gdg_io io;
+    const bool first = round == 0, last = round == nseg - 1;
+    io.src = first ? in + (long)c * in_stride : mid + (long)c * mid_stride;
+    io.src_fmt = first ? in_fmt : GDG_FMT_IEEE64;
+    io.dst = last ? out + (long)c * out_stride : mid + (long)c * mid_stride;
+    io.dst_fmt = last ? out_fmt : GDG_FMT_IEEE64;
+    return io;
+}
 __global__ void __launch_bounds__(GDG_NT, GDG_MIN_CTAS)
-k_chain(const gdg_chain_desc *const *descs, const unsigned char *in, long in_stride, int in_fmt, unsigned char *out, long out_stride,
-        int out_fmt, int n, const double *tw)
+k_chain(const gdg_chain_desc *const *descs, const int32_t *nseg, int round, const unsigned char *in, long in_stride, int in_fmt,
+        unsigned char *out, long out_stride, int out_fmt, unsigned char *mid, long mid_stride, int n, const double *tw)
 {
     const int c = blockIdx.x;
     const gdg_chain_desc *cd = descs[c];
-    const unsigned char *src = in + (long)c * in_stride;
-    unsigned char *dst = out + (long)c * out_stride;
-    if (cd == nullptr) {                                   /* no segment in this round: pass through (float64 rounds only) */
-        if (src != dst) for (int k = threadIdx.x; k < n; k += GDG_NT) ((double *)dst)[k] = ((const double *)src)[k];
-        return;
-    }
-    run_chain(gdg_smem, cd, src, in_fmt, dst, out_fmt, n, tw);
+    if (cd == nullptr) return;                             /* this channel's segment of this round runs in the other kernel (or it has none) */
+    const gdg_io io = segment_io(c, round, nseg[c], in, in_stride, in_fmt, out, out_stride, out_fmt, mid, mid_stride);
+    run_chain(gdg_smem, cd, io.src, io.src_fmt, io.dst, io.dst_fmt, n, tw);
+}
+/* a run of consecutive oversampled units, tile by tile, GDG_OSK_CTAS CTAs per SM (gdg_os.cuh) */
+__global__ void __launch_bounds__(GDG_OSK_NT, GDG_OSK_CTAS)
+k_os(const gdg_chain_desc *const *descs, const int32_t *nseg, int round, const unsigned char *in, long in_stride, int in_fmt,
+     unsigned char *out, long out_stride, int out_fmt, unsigned char *mid, long mid_stride, int n)
+{
+    const int c = blockIdx.x;
+    const gdg_chain_desc *cd = descs[c];
+    if (cd == nullptr) return;
+    const gdg_io io = segment_io(c, round, nseg[c], in, in_stride, in_fmt, out, out_stride, out_fmt, mid, mid_stride);
+    run_os(gdg_smem, cd, io.src, io.src_fmt, io.dst, io.dst_fmt, n);
 }
 /* level meter: CTA c meters row c of d_in into state words d_state + 4*c */
 __global__ void __launch_bounds__(GDG_NT) k_meter(const double *in, long stride, long n, double f, long long hold, double *state)
@@ -141,6 +162,8 @@ int gdgb_init(int device)
     for (int i = 0; i < 2; i++) CU(cudaStreamCreateWithFlags(&g_copy_streams[i], cudaStreamNonBlocking));
     for (int i = 0; i < GDGB_EVENTS; i++) CU(cudaEventCreateWithFlags(&g_events[i], cudaEventDisableTiming));
     CU(cudaFuncSetAttribute(k_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, GDG_SMEM_BYTES));
+    CU(cudaFuncSetAttribute(k_os, cudaFuncAttributeMaxDynamicSharedMemorySize, GDG_OSK_SMEM_BYTES));
+    CU(cudaFuncSetAttribute(k_os, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     return 0;
 }
 
@@ -196,11 +219,16 @@ int gdgb_set_tables(const double *aa2, const double *aa4, const double *lz2, con
     return 0;
 }
 
-int gdgb_launch_chains(const gdg_chain_desc *const *d_descs, int channels, const void *d_in, long in_stride_bytes, int in_fmt,
-                       void *d_out, long out_stride_bytes, int out_fmt, int n, void *stream)
+int gdgb_launch_segments(int kind, const gdg_chain_desc *const *d_descs, const int32_t *d_nseg, int round, int channels,
+                         const void *d_in, long in_stride_bytes, int in_fmt, void *d_out, long out_stride_bytes, int out_fmt,
+                         void *d_mid, long mid_stride_bytes, int n, void *stream)
 {
-    k_chain<<<channels, GDG_NT, GDG_SMEM_BYTES, (cudaStream_t)stream>>>(d_descs, (const unsigned char *)d_in, in_stride_bytes, in_fmt,
-                                                                      (unsigned char *)d_out, out_stride_bytes, out_fmt, n, g_d_tw);
+    if (kind == 0)
+        k_chain<<<channels, GDG_NT, GDG_SMEM_BYTES, (cudaStream_t)stream>>>(d_descs, d_nseg, round, (const unsigned char *)d_in, in_stride_bytes, in_fmt,
+                                                                          (unsigned char *)d_out, out_stride_bytes, out_fmt, (unsigned char *)d_mid, mid_stride_bytes, n, g_d_tw);
+    else
+        k_os<<<channels, GDG_OSK_NT, GDG_OSK_SMEM_BYTES, (cudaStream_t)stream>>>(d_descs, d_nseg, round, (const unsigned char *)d_in, in_stride_bytes, in_fmt,
+                                                                               (unsigned char *)d_out, out_stride_bytes, out_fmt, (unsigned char *)d_mid, mid_stride_bytes, n);
     g_launches++;
     CU(cudaGetLastError());
     return 0;

@@ -41,6 +41,7 @@
 #define GDG_DEV __device__ __noinline__
 #define GDG_DEVI __device__ __forceinline__
 #define GDG_THREADS_BEGIN { const int tid = (int)threadIdx.x; (void)tid;
+#define GDG_THREADS_BEGIN_N(NT_) { const int tid = (int)threadIdx.x; (void)tid;       /* CTA of NT_ threads */
 #define GDG_THREADS_END } __syncthreads();
 #define GDG_THREADS_END_NOSYNC }
 #define GDG_CONST __constant__
@@ -84,6 +85,7 @@ static __device__ __forceinline__ void bulk_wait(double *mbar_word)
 #define GDG_DEV static
 #define GDG_DEVI static inline
 #define GDG_THREADS_BEGIN for (int tid = 0; tid < GDG_NT; ++tid) {
+#define GDG_THREADS_BEGIN_N(NT_) for (int tid = 0; tid < (NT_); ++tid) {
 #define GDG_THREADS_END }
 #define GDG_THREADS_END_NOSYNC }
 #define GDG_CONST static
@@ -209,9 +211,10 @@ GDG_DEVI double scan_apply(int maxplus, double a, double c, double b)
 }
 
 #if defined(__CUDACC__) && !defined(GDG_HOST_EMU)
-template <int K>
-GDG_DEVI void scan_regs(gdg_ctx &cx, int maxplus, double (&a)[K], double (&b)[K], const double *init, double (&cin)[K])
+template <int K, int NT = GDG_NT>
+GDG_DEVI void scan_regs(double *ws, int maxplus, double (&a)[K], double (&b)[K], const double *init, double (&cin)[K])
 {
+    constexpr int NSEG = NT / 32;
     const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
@@ -221,33 +224,36 @@ GDG_DEVI void scan_regs(gdg_ctx &cx, int maxplus, double (&a)[K], double (&b)[K]
             if (lane >= off) { b[j] = scan_apply(maxplus, a[j], bu, b[j]); a[j] *= au; }
         }
     }
-    double *ws = SM_SEG;                                   /* [K][NSEG][2] */
+    /* ws: [K][NSEG][2] warp totals in shared memory */
     if (lane == 31) {
 #pragma unroll
-        for (int j = 0; j < K; j++) { ws[(j * GDG_NSEG + warp) * 2] = a[j]; ws[(j * GDG_NSEG + warp) * 2 + 1] = b[j]; }
+        for (int j = 0; j < K; j++) { ws[(j * NSEG + warp) * 2] = a[j]; ws[(j * NSEG + warp) * 2 + 1] = b[j]; }
     }
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < K; j++) {
         double c = init[j];
-        for (int w = 0; w < warp; w++) c = scan_apply(maxplus, ws[(j * GDG_NSEG + w) * 2], c, ws[(j * GDG_NSEG + w) * 2 + 1]);
+        for (int w = 0; w < warp; w++) c = scan_apply(maxplus, ws[(j * NSEG + w) * 2], c, ws[(j * NSEG + w) * 2 + 1]);
         double ae = __shfl_up_sync(0xffffffffu, a[j], 1), be = __shfl_up_sync(0xffffffffu, b[j], 1);
         if (lane == 0) { ae = 1.0; be = 0.0; }
         cin[j] = scan_apply(maxplus, ae, c, be);
     }
     __syncthreads();
 }
-#define GDG_SCAN(K, cx, maxplus, a, b, init, cin) scan_regs<K>(cx, maxplus, a, b, init, cin)
+#define GDG_SCAN(K, cx, maxplus, a, b, init, cin) scan_regs<K>(SM_SEG, maxplus, a, b, init, cin)
+/* the same scan in a CTA of NT threads with its warp totals at `ws` */
+#define GDG_SCAN_N(K, NT, ws, maxplus, a, b, init, cin) scan_regs<K, NT>(ws, maxplus, a, b, init, cin)
 #else
 template <int K>
-static void scan_regs_host(int maxplus, double (*a)[K], double (*b)[K], const double *init, double (*cin)[K])
+static void scan_regs_host(int nt, int maxplus, double (*a)[K], double (*b)[K], const double *init, double (*cin)[K])
 {
     for (int j = 0; j < K; j++) {
         double c = init[j];
-        for (int t = 0; t < GDG_NT; t++) { cin[t][j] = c; c = scan_apply(maxplus, a[t][j], c, b[t][j]); }
+        for (int t = 0; t < nt; t++) { cin[t][j] = c; c = scan_apply(maxplus, a[t][j], c, b[t][j]); }
     }
 }
-#define GDG_SCAN(K, cx, maxplus, a, b, init, cin) scan_regs_host<K>(maxplus, a##_r, b##_r, init, cin##_r)
+#define GDG_SCAN(K, cx, maxplus, a, b, init, cin) scan_regs_host<K>(GDG_NT, maxplus, a##_r, b##_r, init, cin##_r)
+#define GDG_SCAN_N(K, NT, ws, maxplus, a, b, init, cin) scan_regs_host<K>(NT, maxplus, a##_r, b##_r, init, cin##_r)
 #endif
 
 GDG_DEVI double chunk_A(double a_step, int len, int S, double a_full) { return len == S ? a_full : pow_int(a_step, len); }

@@ -38,7 +38,7 @@
 #define GDG_OS_Z2 GDG_OS_ST_Z2
 GDG_DEVI int pz(int m) { return m + (m >> 3); }      /* one pad per 8: stride-8/9 access patterns spread over banks */
 /* location of oversampled sample (tile-local base index jl, sub-phase ph) in the per-phase arrays */
-GDG_DEVI int zloc(int f, int jl, int ph) { return ph == 0 ? pz(GDG_ZH + jl) : (f - ph) * GDG_ZPS + pz(GDG_ZH + jl + 1); }
+GDG_DEVI int zloc(int f, int jl, int ph, int zps = GDG_ZPS) { return ph == 0 ? pz(GDG_ZH + jl) : (f - ph) * zps + pz(GDG_ZH + jl + 1); }
 
 GDG_DEVI double nl_pointwise(int type, const gdg_unit_desc &d, double s)
 {
@@ -66,36 +66,37 @@ GDG_DEVI double nl_pointwise(int type, const gdg_unit_desc &d, double s)
 /* fuzz.go:52-105 over the F*nb oversampled samples of nb base samples (F == 1: the block itself): follower
  * scan, coupling-capacitor scan, in place.  Thread chunk = Sb consecutive base samples = F*Sb consecutive
  * oversampled samples, visited in time order (base jl, sub-phase ph). */
-template <int F> GDG_DEVI int fz_loc(int jl, int ph) { return F == 1 ? sw(jl) : zloc(F, jl, ph); }
+template <int F, int ZPS> GDG_DEVI int fz_loc(int jl, int ph) { return F == 1 ? sw(jl) : zloc(F, jl, ph, ZPS); }
 
-template <int F>
-GDG_DEV void fuzz_run(gdg_ctx &cx, const gdg_unit_desc &d_global, double *z, int nbase)
+/* NT: threads of the CTA; ZPS: doubles per polyphase array of z; d: the unit's descriptor (shared memory); st2: {envelope,
+ * coupling-capacitor voltage} (device state or a shared-memory copy of it); ws: warp totals of the scans */
+template <int F, int NT, int ZPS>
+GDG_DEV void fuzz_run(const gdg_unit_desc &d, double *z, int nbase, double *st2, double *ws)
 {
-    const gdg_unit_desc &d = GDG_DESC; (void)d_global;
-    const int Sb = chunk_len(nbase), mode = d.i[1];
+    const int Sb = (nbase + NT - 1) / NT, mode = d.i[1];
     const double gain = d.p[0], lvl = d.p[1], bias = d.p[2], ff = d.p[3], ffi = d.p[4], dinv = d.p[5], dd = d.p[6];
-    double *st = d.st;
+    double *st = st2; (void)ws;
     const double astep = follow_A(mode, dinv, dd), afull = pow_int(astep, F * Sb), cstep = 1.0 - dd, cfull = pow_int(cstep, F * Sb);
     const double inite[1] = {st[GDG_OS_ST_ENV]}, initc[1] = {st[GDG_OS_ST_CCV]};
     GDG_REGA(double, a, 1); GDG_REGA(double, b, 1); GDG_REGA(double, ein, 1); GDG_REGA(double, cin, 1);
-    GDG_THREADS_BEGIN
+    GDG_THREADS_BEGIN_N(NT)
         const int j0 = tid * Sb, j1 = imin(nbase, j0 + Sb);
         double e = 0.0;
 #pragma unroll 1
         for (int jl = j0; jl < j1; jl++)
 #pragma unroll
-            for (int ph = 0; ph < F; ph++) e = follow_step(mode, e, fabs(z[fz_loc<F>(jl, ph)]), dinv, dd);
+            for (int ph = 0; ph < F; ph++) e = follow_step(mode, e, fabs(z[fz_loc<F, ZPS>(jl, ph)]), dinv, dd);
         R(a)[0] = j0 < nbase ? chunk_A(astep, F * (j1 - j0), F * Sb, afull) : 1.0; R(b)[0] = j0 < nbase ? e : 0.0;
     GDG_THREADS_END_NOSYNC
-    GDG_SCAN(1, cx, mode == GDG_FOLLOW_ENVELOPE, a, b, inite, ein);
-    GDG_THREADS_BEGIN
+    GDG_SCAN_N(1, NT, ws, mode == GDG_FOLLOW_ENVELOPE, a, b, inite, ein);
+    GDG_THREADS_BEGIN_N(NT)
         const int j0 = tid * Sb, j1 = imin(nbase, j0 + Sb);
         double e = R(ein)[0], c = 0.0;
 #pragma unroll 1
         for (int jl = j0; jl < j1; jl++)
 #pragma unroll
             for (int ph = 0; ph < F; ph++) {
-                const double s = z[fz_loc<F>(jl, ph)];
+                const double s = z[fz_loc<F, ZPS>(jl, ph)];
                 e = follow_step(mode, e, fabs(s), dinv, dd);
                 double pre = clamp1(gain * (s - (bias * e)));
                 pre = (ff * pre) + (ffi * s);
@@ -103,15 +104,15 @@ GDG_DEV void fuzz_run(gdg_ctx &cx, const gdg_unit_desc &d_global, double *z, int
             }
         R(a)[0] = j0 < nbase ? chunk_A(cstep, F * (j1 - j0), F * Sb, cfull) : 1.0; R(b)[0] = j0 < nbase ? c : 0.0;
     GDG_THREADS_END_NOSYNC
-    GDG_SCAN(1, cx, 0, a, b, initc, cin);
-    GDG_THREADS_BEGIN
+    GDG_SCAN_N(1, NT, ws, 0, a, b, initc, cin);
+    GDG_THREADS_BEGIN_N(NT)
         const int j0 = tid * Sb, j1 = imin(nbase, j0 + Sb);
         double e = R(ein)[0], c = R(cin)[0];
 #pragma unroll 1
         for (int jl = j0; jl < j1; jl++)
 #pragma unroll
             for (int ph = 0; ph < F; ph++) {
-                const int ad = fz_loc<F>(jl, ph);
+                const int ad = fz_loc<F, ZPS>(jl, ph);
                 const double s = z[ad];
                 e = follow_step(mode, e, fabs(s), dinv, dd);
                 double pre = clamp1(gain * (s - (bias * e)));
@@ -215,7 +216,7 @@ GDG_DEV void oversampled_tiles(gdg_ctx &cx, const gdg_unit_desc &d_global)
             for (int jl = tid; jl < Tt; jl += GDG_NT) os_produce<F>(d, type, x, uph, z, t0 + jl, jl);
             if (t0 > 0) os_combine<F>(y, part, t0 - T, T, tid);
         GDG_THREADS_END
-        if (!stateless) fuzz_run<F>(cx, d, z, Tt);
+        if (!stateless) fuzz_run<F, GDG_NT, GDG_ZPS>(d, z, Tt, st, SM_SEG);
         /* polyphase FIR partial sums: warp w computes phase w % F (taps warp-uniform) of RR outputs per thread; then the
          * last GDG_ZH + 1 cells of every phase are stashed for the next tile (z is read-only in this phase) */
         GDG_THREADS_BEGIN
@@ -259,7 +260,7 @@ GDG_DEV void stage_oversampled(gdg_ctx &cx, const gdg_unit_desc &d_global)
     const int n = cx.n, f = d.i[0], type = d.type;
     double *x = SM_CUR(cx);
     if (f <= 1) {
-        if (type == GDG_UNIT_FUZZ) { fuzz_run<1>(cx, d, x, n); return; }
+        if (type == GDG_UNIT_FUZZ) { fuzz_run<1, GDG_NT, GDG_ZPS>(d, x, n, d.st, SM_SEG); return; }
         GDG_THREADS_BEGIN
 #pragma unroll 1
             for (int k = tid; k < n; k += GDG_NT) x[sw(k)] = nl_pointwise(type, d, x[sw(k)]);

@@ -21,6 +21,7 @@
 
 #include "../../go-dsp-guitar_b200/csrc/gdg_backend.h"
 #include "../../go-dsp-guitar_b200/csrc/gdg_interp.cuh"
+#include "../../go-dsp-guitar_b200/csrc/gdg_os.cuh"
 
 static std::string t_err;
 static std::vector<double> g_tw;
@@ -62,15 +63,19 @@ int gdgb_set_tables(const double *aa2, const double *aa4, const double *lz2, con
     return 0;
 }
 
-int gdgb_launch_chains(const gdg_chain_desc *const *descs, int channels, const void *in, long in_stride, int in_fmt,
-                       void *out, long out_stride, int out_fmt, int n, void *)
+int gdgb_launch_segments(int kind, const gdg_chain_desc *const *descs, const int32_t *nseg, int round, int channels,
+                         const void *in, long in_stride, int in_fmt, void *out, long out_stride, int out_fmt,
+                         void *mid, long mid_stride, int n, void *)
 {
-    std::vector<double> smem(GDG_SMEM_DOUBLES);
+    std::vector<double> smem(kind == 0 ? GDG_SMEM_DOUBLES : GDG_OSK_SMEM_DOUBLES);
     for (int c = 0; c < channels; c++) {
-        const unsigned char *src = (const unsigned char *)in + (long)c * in_stride;
-        unsigned char *dst = (unsigned char *)out + (long)c * out_stride;
-        if (!descs[c]) { if (src != dst) memcpy(dst, src, sizeof(double) * n); continue; }
-        run_chain(smem.data(), descs[c], src, in_fmt, dst, out_fmt, n, g_tw.data());
+        if (!descs[c]) continue;
+        const bool first = round == 0, last = round == nseg[c] - 1;
+        const unsigned char *src = first ? (const unsigned char *)in + (long)c * in_stride : (const unsigned char *)mid + (long)c * mid_stride;
+        unsigned char *dst = last ? (unsigned char *)out + (long)c * out_stride : (unsigned char *)mid + (long)c * mid_stride;
+        const int sf = first ? in_fmt : GDG_FMT_IEEE64, df = last ? out_fmt : GDG_FMT_IEEE64;
+        if (kind == 0) run_chain(smem.data(), descs[c], src, sf, dst, df, n, g_tw.data());
+        else run_os(smem.data(), descs[c], src, sf, dst, df, n);
     }
     g_launches++;
     return 0;

@@ -142,7 +142,7 @@ def test_extreme_finite_signals(lib, kind):
 def test_chain_longer_than_one_fused_segment(lib):
     """The chain kernel fuses up to 24 active units per launch; signal.Chain has no length limit (signal.go:64-86), so a
     longer chain runs as consecutive segments with the block round-tripping through HBM between them - same result, and
-    a batch may mix short and long chains.  Encoded payloads are limited to one segment and say so."""
+    a batch may mix short and long chains; encoded payloads keep float64 rows between the segments."""
     fs, n = 96000, 2048
     unit_cycle = ["tone_stack", "delay", "compressor", "tremolo", "bandpass", "overdrive", "chorus", "noise_gate", "reverb", "cabinet"]
     long_spec = [(unit_cycle[k % len(unit_cycle)], ({"delay_time": 3 + k} if unit_cycle[k % len(unit_cycle)] == "delay" else {}), {}) for k in range(53)]
@@ -160,8 +160,11 @@ def test_chain_longer_than_one_fused_segment(lib):
         pairs[0][0].set_bypass(i, True); pairs[0][1].set_bypass(i, True)
     blk = x[0, :n]
     assert common.rms(pairs[0][0].process(blk, fs) - pairs[0][1].process(blk, fs)) <= common.TOL_RMS
-    with pytest.raises(gdg.GdgError, match="segment"):
-        gdg.process_batch_encoded([pairs[2][1]], [np.zeros(n, dtype="<i2").tobytes()], "PCM16", "PCM16", n, fs)
+    # encoded rows through a multi-segment chain: decoded on the way into the first segment, encoded out of the last one
+    a, b = common.make_chain_pair(lib, long_spec[:30])
+    pcm = (np.random.default_rng(3).standard_normal(n) * 6000).clip(-32768, 32767).astype("<i2").tobytes()
+    got = gdg.process_batch_encoded([b], [pcm], "PCM16", "IEEE64", n, fs)[0]
+    assert common.rms(np.frombuffer(got, dtype=np.float64) - a.process(orc.wave_decode("PCM16", pcm), fs)) <= common.TOL_RMS
 
 
 @pytest.mark.parametrize("unit", ["flanger", "phaser"])

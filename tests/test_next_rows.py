@@ -83,7 +83,7 @@ def test_batch_file_path_pcm16_in_pcm24_out(lib):
     assert mism <= total // 2000
 
 
-def test_encoded_rejects_unknown_format_and_long_chains(lib):
+def test_encoded_rejects_unknown_format_and_runs_long_chains(lib):
     c = gdg.Chain(lib=lib)
     import ctypes as C
     buf = (C.c_char * 64)()
@@ -93,12 +93,14 @@ def test_encoded_rejects_unknown_format_and_long_chains(lib):
     assert lib.gdg_format_bytes_per_sample(2) == 3 and lib.gdg_format_bytes_per_sample(7) == 0
     for _ in range(25):
         i = c.append_unit("distortion"); c.set_bypass(i, False)
-    with pytest.raises(gdg.GdgError, match="one fused segment"):
-        gdg.process_batch_encoded([c], [bytes(16)], "PCM16", "PCM16", 8, 48000)
-    # ... while the float64 entry point handles 25 active units in two segments
+    # 25 active units = two segments: float64 and encoded entry points both handle it (float64 rows between the segments)
     a = common.build_chain(orc.Chain(), [("distortion", {}, {})] * 25)
     x = common.synth_fast(0, 48000, 1024) * 3
     assert np.array_equal(c.process(x, 48000), a.process(x, 48000))
+    pcm = orc.wave_encode("PCM16", x).tobytes()
+    a2 = common.build_chain(orc.Chain(), [("distortion", {}, {})] * 25)
+    got = gdg.process_batch_encoded([c], [pcm], "PCM16", "PCM16", 1024, 48000)[0]
+    assert got == orc.wave_encode("PCM16", a2.process(orc.wave_decode("PCM16", pcm), 48000)).tobytes()
 
 
 # ---- resample.Time -------------------------------------------------------------------------------------
