@@ -815,10 +815,11 @@ size_t pipeline_group_size(size_t C)
     static const long forced = getenv("GDG_PIPE_GROUP") ? atol(getenv("GDG_PIPE_GROUP")) : 0;   /* tuning knob */
     if (forced > 0) return (size_t)forced;
     if (C < 64) return C;
-    /* one CTA-per-SM wave per group: measured best on B200 (e2e 2.27 vs 1.46 Gsamples/s unpipelined, 1024 channels) */
+    /* a group = four CTA-per-SM waves of the chain kernel = one full wave of the oversampled-run kernel (4 CTAs per SM):
+     * smaller groups would run k_os at a quarter of its occupancy */
     const size_t sms = (size_t)std::max(1, gdgb_sm_count());
-    size_t per = C >= 2 * sms ? sms : (C + 1) / 2;
-    return per;
+    const size_t wave = 4 * sms;
+    return C >= wave + wave / 2 ? wave : C;
 }
 
 bool contiguous(const double *const *p, size_t C, size_t n)

@@ -163,6 +163,10 @@ void orc_controller_process(orc_chain *const *chains, uint32_t n_ch, orc_tuner *
                             orc_spatializer *spat, const double *const *in, double *const *out,
                             uint32_t n_out, size_t n, uint32_t sample_rate);
 
+/* ---- measurement driver (orc_bench.c): the CPU baseline of bench.py --------------------------------- */
+double orc_bench_controller(orc_chain *const *chains, uint32_t n_ch, orc_spatializer *spat, const double *x, size_t n, size_t blocks,
+                            uint32_t rate, int threads, int pin);
+
 #ifdef __cplusplus
 }
 #endif

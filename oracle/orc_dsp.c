@@ -11,6 +11,7 @@
 
 #include <complex.h>
 #include <math.h>
+#include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -39,11 +40,15 @@ int orc_fft_next_power_of_two(uint64_t value, uint64_t *pow_out, uint32_t *exp_o
 typedef struct { size_t n; cplx *w; size_t *perm; } fft_table;
 static fft_table g_tables[40];
 
+/* fft.go guards its lazily built global tables with a mutex (fft.go:140-240); so does this */
+static pthread_mutex_t g_tables_mutex = PTHREAD_MUTEX_INITIALIZER;
 static const fft_table *fft_tables(size_t n)
 {
     uint32_t e = 0;
     while (((size_t)1 << e) < n) e++;
     fft_table *t = &g_tables[e];
+    if (__atomic_load_n(&t->n, __ATOMIC_ACQUIRE) == n) return t;
+    pthread_mutex_lock(&g_tables_mutex);
     if (t->n != n) {
         t->w = (cplx *)malloc(sizeof(cplx) * (n ? n : 1));
         t->perm = (size_t *)malloc(sizeof(size_t) * (n ? n : 1));
@@ -55,8 +60,9 @@ static const fft_table *fft_tables(size_t n)
                 if (i & ((size_t)1 << b)) r |= (size_t)1 << (e - 1 - b);
             t->perm[i] = r;
         }
-        t->n = n;
+        __atomic_store_n(&t->n, n, __ATOMIC_RELEASE);
     }
+    pthread_mutex_unlock(&g_tables_mutex);
     return t;
 }
 
@@ -84,10 +90,12 @@ static void inplace_transform(cplx *vec, size_t n)
 {
     if (n <= 1) return;
     const fft_table *t = fft_tables(n);
-    cplx *scrap = (cplx *)malloc(sizeof(cplx) * n);
+    /* the reference keeps this buffer in the transform object and re-makes it only when the size changes (fft.go:528-551
+     * scrapspace); one buffer per thread here - a malloc/free (mmap above 128 KB) per FFT is not part of the algorithm */
+    static __thread cplx *scrap = NULL; static __thread size_t scrap_n = 0;
+    if (scrap_n < n) { free(scrap); scrap = (cplx *)malloc(sizeof(cplx) * n); scrap_n = n; }
     memcpy(scrap, vec, sizeof(cplx) * n);
     for (size_t i = 0; i < n; i++) vec[i] = scrap[t->perm[i]];
-    free(scrap);
     size_t stride = n;
     for (size_t size = 2; size <= n; size <<= 1) {
         stride >>= 1;

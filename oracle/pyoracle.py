@@ -111,6 +111,7 @@ def lib():
             "orc_meter_analyze": (C.c_int, [vp, u32, vp, vp]),
             "orc_meter_state": (C.c_int, [vp, u32, vp, vp, vp]),
             "orc_controller_process": (None, [vp, u32, vp, C.c_int, vp, vp, vp, u32, sz, u32]),
+            "orc_bench_controller": (C.c_double, [vp, u32, vp, vp, sz, sz, u32, C.c_int, C.c_int]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(L, name)
@@ -560,3 +561,13 @@ def controller_process(chains, tuner, tuner_channel, spat, inputs, sample_rate):
     lib().orc_controller_process(ch, c, tuner._h if tuner else None, tuner_channel,
                                  spat._h if spat else None, ip, op, n_out, n, sample_rate)
     return out
+
+
+def bench_controller(chains, spat, x, n, sample_rate, threads, pin=True):
+    """orc_bench_controller: x [C][blocks * n] float64 through the chains (+ spatializer) on a pinned pthread pool;
+    returns the wall time in seconds."""
+    x = _f64(x)
+    c, total = x.shape
+    blocks = total // n
+    ch = (C.c_void_p * c)(*[k._h for k in chains])
+    return lib().orc_bench_controller(ch, c, spat._h if spat else None, _p(x), n, blocks, sample_rate, threads, 1 if pin else 0)
