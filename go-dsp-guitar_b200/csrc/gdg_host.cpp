@@ -222,18 +222,25 @@ struct DeviceSpectrum { double *d_H = nullptr; int L = 0, F = 0, logM = 0, K = 1
 std::mutex g_spec_mutex;
 std::map<std::string, std::weak_ptr<DeviceSpectrum>> g_spec_cache;
 
-std::shared_ptr<DeviceSpectrum> make_spectrum(const std::vector<double> &coeffs)
+/* partition length of the convolution for a filter of L taps processed in blocks of n samples: filters of up to 8192 taps run
+ * as ONE partition of nextPow2(L) taps whatever the block length (the reference's own block size, filter.go:372-388);
+ * longer ones as a uniformly partitioned convolution whose partition = hop = block length (at most 8192), so that the
+ * reference's default filter_order (no reduction: up to 19199 taps at 192 kHz) also works at JACK period sizes. */
+uint64_t partition_length(size_t L, size_t n)
+{
+    const uint64_t B = next_pow2((uint64_t)L);
+    if (2 * B <= GDG_MAX_FFT) return B;
+    return std::min<uint64_t>((uint64_t)n, GDG_MAX_FFT / 2);
+}
+std::shared_ptr<DeviceSpectrum> make_spectrum(const std::vector<double> &coeffs, uint64_t B)
 {
     const int L = (int)coeffs.size();
     uint32_t e = 0;
-    uint64_t B = next_pow2((uint64_t)L, &e);
-    int K = 1;
-    if (2 * B > GDG_MAX_FFT) {                               /* longer than 8192 taps: partitions of GDG_MAX_FFT/2 taps */
-        B = GDG_MAX_FFT / 2; e = GDG_LOG_MAX_N;
-        K = (int)((L + (int)B - 1) / (int)B);
-    }
+    next_pow2(B, &e);
+    const int K = std::max(1, (int)((L + (int)B - 1) / (int)B));
     const int F = (int)(2 * B);
     std::string key((const char *)coeffs.data(), coeffs.size() * sizeof(double));
+    key.append((const char *)&B, sizeof B);
     std::lock_guard<std::mutex> lk(g_spec_mutex);
     auto it = g_spec_cache.find(key);
     if (it != g_spec_cache.end()) if (auto sp = it->second.lock()) return sp;
@@ -355,8 +362,11 @@ int Unit::prepare(uint32_t rate, size_t n)
         compile_poweramp(rate);
         dirty = true;
     }
-    if (type == GDG_UNIT_POWERAMP && pa_spec && pa_spec->K > 1 && n != GDG_MAX_N)
-        return fail("power_amp: a %d-tap filter runs as a partitioned convolution that is only supported for blocks of %d samples (got %zu)", pa_spec->L, GDG_MAX_N, n);
+    if (type == GDG_UNIT_POWERAMP && pa_spec && pa_has_filter && !pa_new_filter && pa_spec->F != (int)(2 * partition_length(pa_filter.coeffs.size(), n))) {
+        /* a filter longer than 8192 taps is partitioned by the block length: a new block length re-partitions it.  DELIBERATE
+         * DIFFERENCE: the overlap tail restarts here, the reference's single big FFT keeps it across block-length changes. */
+        pa_new_filter = true; dirty = true;
+    }
     if (type == GDG_UNIT_EXCESS || type == GDG_UNIT_FUZZ || type == GDG_UNIT_OVERDRIVE || type == GDG_UNIT_DISTORTION) {
         /* oversampling.go:74-84: the up-sampler's input buffer (N + 8, its first 8 cells = the last 8 inputs) is re-made,
          * i.e. zeroed, whenever the block length differs from the one it was made for; the anti-aliasing filter's
@@ -528,7 +538,7 @@ int Unit::prepare(uint32_t rate, size_t n)
         d.i[0] = L;
         if (L > 0) {
             if (pa_new_filter || !pa_spec) {
-                pa_spec = make_spectrum(pa_filter.coeffs);
+                pa_spec = make_spectrum(pa_filter.coeffs, partition_length(pa_filter.coeffs.size(), n));
                 if (!pa_spec) return backend_fail("filter spectrum upload failed");
                 /* a recompiled filter is a NEW filter object in the reference: fresh (zero) overlap tail */
                 if (d_st) { gdgb_sync(); gdgb_free(d_st); d_st = nullptr; }
@@ -537,8 +547,6 @@ int Unit::prepare(uint32_t rate, size_t n)
                 pa_new_filter = false;
             }
             d.i[3] = pa_spec->K; d.i[4] = pa_spec->F + 2;
-            if (pa_spec->K > 1 && n != GDG_MAX_N)
-                return fail("power_amp: a %d-tap filter runs as a partitioned convolution that is only supported for blocks of %d samples (got %zu)", pa_spec->L, GDG_MAX_N, n);
             d.i[1] = pa_spec->F; d.i[2] = pa_spec->logM; d.aux = pa_spec->d_H;
         }
         break; }

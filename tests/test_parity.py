@@ -195,11 +195,32 @@ def test_ir_sweep_synthetic(lib, L):
     common.compare_stream(a, b, x, 8192, 192000, label="sweep L=%d" % L)
 
 
-def test_long_filter_with_short_block_is_rejected_loudly(lib):
-    banks = common.make_banks(lib, with_fixture=False, synthetic=[("syn", 20000, 192000)])
-    c = common.build_chain(gdg.Chain(banks[1], lib=lib), [("power_amp", {}, {"filter_1": "syn"})])
-    with pytest.raises(gdg.GdgError, match="only supported for blocks of 8192"):
-        c.process(np.zeros(1024), 192000)
+@pytest.mark.parametrize("n", [64, 256, 1024, 4096])
+def test_long_filter_at_jack_block_sizes(lib, n):
+    """The reference's default filter_order (1048576: no reduction) leaves 7 of the 24 bank responses above 8192 taps at
+    192 kHz (and one at 96 kHz); the reference convolves them at any JACK period with one 2*nextPow2(L) FFT per block
+    (filter.go:372-455, doc/jack-setup.txt:15-16).  Here they run as a uniformly partitioned convolution whose partition is
+    the block length: same linear convolution, same overlap-add, same clamp."""
+    banks = common.make_banks(lib, synthetic=[("syn20000", 20000, 192000)])
+    for name, fs in (("Guitar: Custom BP", 192000), ("syn20000", 192000), ("PA: HC 4-way (Sub)", 96000)):
+        a, b = common.make_chain_pair(lib, [("power_amp", {"level_1": -3}, {"filter_1": name})], banks)
+        blocks = max(6, 3 * 20000 // n // 4)
+        x = common.synth_fast(5, fs, blocks * n) * 1.5
+        common.compare_stream(a, b, x, n, fs, label="%s n=%d" % (name, n))
+
+
+def test_long_filter_block_length_change_repartitions(lib):
+    """DELIBERATE DIFFERENCE: a new block length re-partitions a filter longer than 8192 taps and restarts its
+    overlap tail; the reference's single FFT keeps the tail.  After the change the product equals a FRESH reference filter
+    fed from that block on; nothing is rejected."""
+    fs = 192000
+    banks = common.make_banks(lib, with_fixture=False, synthetic=[("syn", 20000, fs)])
+    spec = [("power_amp", {}, {"filter_1": "syn"})]
+    a, b = common.make_chain_pair(lib, spec, banks)
+    x = common.synth_fast(2, fs, 4 * 8192)
+    common.compare_stream(a, b, x[:2 * 8192], 8192, fs, label="8192")
+    fresh = common.build_chain(orc.Chain(banks[0]), spec)
+    common.compare_stream(fresh, b, x[2 * 8192:2 * 8192 + 8 * 1024], 1024, fs, label="after the switch to 1024")
 
 
 def test_default_filter_order_with_long_bank_response(lib):
