@@ -128,6 +128,8 @@ ABI = {
     "gdg_controller_submit": (_int, [_vp, _u32, _vp, _int, _vp, _vp, _vp, _vp, _u32, _sz, _u32]),
     "gdg_controller_wait": (_int, [_int]),
     "gdg_controller_submit_encoded": (_int, [_vp, _u32, _vp, _int, _vp, _vp, _vp, _int, _vp, _int, _u32, _sz, _u32]),
+    "gdg_chain_filter_coefficients": (C.c_long, [_vp, _int, _vp, _sz]),
+    "gdg_tuner_analyze_batch": (_int, [_vp, _u32, _vp]),
     "gdg_controller_process_aux": (_int, [_vp, _u32, _vp, _int, _vp, _vp, _vp, _vp, _int, _vp, _u32, _sz, _u32]),
     "gdg_controller_submit_aux": (_int, [_vp, _u32, _vp, _int, _vp, _vp, _vp, _vp, _int, _vp, _u32, _sz, _u32]),
     "gdg_process_batch_encoded_submit": (_int, [_vp, _sz, _vp, _int, _vp, _int, _sz, _u32]),
@@ -300,6 +302,16 @@ class Chain(_Base):
     def length(self):
         return self._lib.gdg_chain_length(self._h)
 
+    def filter_coefficients(self, i):
+        """Filter.Coefficients() of the power amp in slot i (compiled on the device); empty before the first process()."""
+        n = self._lib.gdg_chain_filter_coefficients(self._h, i, None, 0)
+        if n < 0:
+            raise self._err()
+        out = np.zeros(n)
+        if n and self._lib.gdg_chain_filter_coefficients(self._h, i, _ptr(out), n) < 0:
+            raise self._err()
+        return out
+
     def process(self, x, sample_rate):
         """Chain.Process(in, out, sampleRate) with host buffers (signal.go:361-414)."""
         x = _f64(x)
@@ -457,6 +469,17 @@ class Tuner(_Base):
         r = _TunerResult()
         self._check(self._lib.gdg_tuner_analyze(self._h, C.byref(r)))
         return {"cents": r.cents, "frequency": r.frequency, "note": r.note.decode()}
+
+
+def tuner_analyze_batch(tuners):
+    """gdg_tuner_analyze_batch: Analyze for several tuners with ONE batch of device launches."""
+    if not tuners:
+        return []
+    lib = tuners[0]._lib
+    res = (_TunerResult * len(tuners))()
+    if lib.gdg_tuner_analyze_batch(_handles(tuners), len(tuners), res) < 0:
+        raise GdgError(lib.gdg_last_error().decode())
+    return [{"cents": r.cents, "frequency": r.frequency, "note": r.note.decode()} for r in res]
 
 
 class Meter(_Base):

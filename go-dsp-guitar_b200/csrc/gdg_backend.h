@@ -71,6 +71,23 @@ int gdgb_launch_spatializer(const gdg_spat_channel *d_ch, int channels, const do
  * d_work: 2*fft_size doubles; result corr[0..fft_size) left in d_work */
 int gdgb_autocorrelate(const double *d_ring, int n_ring, int pos, double *d_work, int fft_size, void *stream);
 
+/* ---- impulse-response compilation on the device (bodies in gdg_interp.cuh): everything is
+ * stream-ordered, nothing waits for the device ---- */
+/* bins 0..nfft/2 (interleaved re, im) of the real FFT of x zero-padded to nfft (power of two >= 2); d_work: nfft doubles */
+int gdgb_ir_real_spectrum(const double *d_x, long n_x, int nfft, double *d_work, double *d_spec, void *stream);
+/* resample.Frequency (resample.go:109-142) */
+int gdgb_ir_resample_bins(const double *d_spec_in, int bins_in, double *d_spec_out, int bins_out, void *stream);
+/* RealInverseFourier of the Hermitian half d_spec (bins 0..nfft/2), first n_keep samples to d_out; d_work: nfft doubles */
+int gdgb_ir_real_inverse(const double *d_spec, int nfft, double *d_work, double *d_out, long n_keep, void *stream);
+/* *d_ss = sum of x[i]^2 (estimateGain without the root, filter.go:127-138) */
+int gdgb_ir_sum_squares(const double *d_x, long n, double *d_ss, void *stream);
+/* acc[i] += fac * ((comp / sqrt(*d_ss)) * x[i]), i < n: Normalize -> Multiply -> Add of one filter (filter.go:328-336, 270-323, 167-253) */
+int gdgb_ir_scale_add(double *d_acc, const double *d_x, long n, double comp, double fac, const double *d_ss, void *stream);
+/* H_p[k], p < K, k = 0..B: spectra of the K partitions of B taps (real FFT size 2B) of the L-tap filter d_coeffs */
+int gdgb_ir_partition_spectra(const double *d_coeffs, int L, int B, int logB, int K, double *d_H, void *stream);
+/* the tuner's autocorrelation for `count` tuners in one batch of launches: ring / work / pos per tuner */
+int gdgb_autocorrelate_batch(const double *const *d_rings, int n_ring, const int *pos, double *const *d_works, int count, int fft_size, void *stream);
+
 uint64_t gdgb_launch_count(void);               /* kernels launched so far (bench "gpu_launches") */
 
 #endif

@@ -71,35 +71,6 @@ uint64_t next_pow2(uint64_t v, uint32_t *exp_out = nullptr)     /* fft/fft.go:39
     return p;
 }
 
-/* iterative radix-2 complex FFT (forward, unscaled); n power of two */
-void fft_inplace(std::vector<cplx> &a, bool inverse)
-{
-    const size_t n = a.size();
-    for (size_t i = 1, j = 0; i < n; i++) {
-        size_t bit = n >> 1;
-        for (; j & bit; bit >>= 1) j ^= bit;
-        j ^= bit;
-        if (i < j) std::swap(a[i], a[j]);
-    }
-    for (size_t len = 2; len <= n; len <<= 1) {
-        const double ang = (inverse ? 2.0 : -2.0) * GDG_MATH_PI / (double)len;
-        for (size_t i = 0; i < n; i += len)
-            for (size_t k = 0; k < len / 2; k++) {
-                const cplx w(std::cos(ang * (double)k), std::sin(ang * (double)k));
-                const cplx u = a[i + k], v = a[i + k + len / 2] * w;
-                a[i + k] = u + v; a[i + k + len / 2] = u - v;
-            }
-    }
-    if (inverse) for (auto &x : a) x /= (double)n;
-}
-/* full spectrum of a real sequence (what RealFourier yields, fft/fft.go:744-856) */
-std::vector<cplx> real_spectrum(const std::vector<double> &x)
-{
-    std::vector<cplx> a(x.begin(), x.end());
-    if (a.size() > 1) fft_inplace(a, false);
-    return a;
-}
-
 /* resample/resample.go:10-31, 36-66 */
 double lanczos_kernel(double x, double a)
 {
@@ -110,26 +81,15 @@ double lanczos_kernel(double x, double a)
     }
     return 0.0;
 }
-double lanczos_interpolate(const double *s, long n, double x, int a)
+/* output length of resample.Time (resample/resample.go:72-89) */
+size_t resample_time_length(size_t n, uint32_t src, uint32_t dst)
 {
-    const long idx = (long)std::floor(x);
-    double sum = 0.0;
-    for (long i = idx + 1 - a; i < idx + 1 + a; i++)
-        if (i >= 0 && i < n) sum += s[i] * lanczos_kernel(x - (double)i, (double)a);
-    return sum;
-}
-/* resample/resample.go:72-103 Time */
-std::vector<double> resample_time(const std::vector<double> &in, uint32_t src, uint32_t dst)
-{
-    const double lf = (double)in.size() * ((double)dst / (double)src);
+    if (!src) return 0;
+    const double lf = (double)n * ((double)dst / (double)src);
     const double fl = std::floor(lf);
     long len = (long)fl;
     if (fl == lf) len--;
-    if (len < 0) len = 0;
-    std::vector<double> out((size_t)len);
-    const double dx = (double)src / (double)dst;
-    for (long i = 0; i < len; i++) out[(size_t)i] = lanczos_interpolate(in.data(), (long)in.size(), (double)i * dx, 3);
-    return out;
+    return len < 0 ? 0 : (size_t)len;
 }
 
 double db2fac(int32_t db) { return std::pow(10.0, 0.05 * (double)db); }     /* effects.go:389-394 */
@@ -139,66 +99,31 @@ double db2fac(int32_t db) { return std::pow(10.0, 0.05 * (double)db); }     /* e
 /* ------------------------------------------------------------------------ */
 const uint32_t k_sample_rates[7] = {22050, 32000, 44100, 48000, 88200, 96000, 192000};   /* filter.go:25-33 */
 
-struct ImpulseResponse { std::string name; uint32_t rate; double comp; std::vector<double> data; };
-
-struct FilterIR {                    /* the coefficient side of filter.filterStruct */
-    std::vector<double> coeffs; uint32_t rate = 0; double comp = 0.0;
+/* one response at one rate (filter.impulseResponseStruct): the coefficients live on the device, where filter.Import's
+ * resampling produced them and where the power amp compiles them */
+struct ImpulseResponse {
+    std::string name; uint32_t rate; double comp; double *d_data = nullptr; size_t n = 0;
+    ImpulseResponse(std::string nm, uint32_t r, double c, double *d, size_t len) : name(std::move(nm)), rate(r), comp(c), d_data(d), n(len) {}
+    ImpulseResponse(const ImpulseResponse &) = delete;
+    ImpulseResponse(ImpulseResponse &&o) noexcept : name(std::move(o.name)), rate(o.rate), comp(o.comp), d_data(o.d_data), n(o.n) { o.d_data = nullptr; }
+    ~ImpulseResponse() { if (d_data) gdgb_free(d_data); }
 };
-FilterIR ir_multiply(const FilterIR &f, double s)          /* filter.go:270-323 (compensation resets to 0) */
-{
-    FilterIR r; r.rate = f.rate; r.comp = 0.0; r.coeffs.resize(f.coeffs.size());
-    for (size_t i = 0; i < f.coeffs.size(); i++) r.coeffs[i] = s * f.coeffs[i];
-    return r;
-}
-FilterIR ir_normalize(const FilterIR &f)                   /* filter.go:127-138, 328-336 */
-{
-    double sum = 0.0;
-    for (double c : f.coeffs) sum += c * c;
-    return ir_multiply(f, f.comp / std::sqrt(sum));
-}
-FilterIR ir_add(const FilterIR &a, const FilterIR &b)      /* filter.go:167-253 */
-{
-    FilterIR r; r.rate = a.rate; r.comp = 0.0;
-    r.coeffs.assign(std::max(a.coeffs.size(), b.coeffs.size()), 0.0);
-    std::copy(a.coeffs.begin(), a.coeffs.end(), r.coeffs.begin());
-    for (size_t i = 0; i < b.coeffs.size(); i++) r.coeffs[i] += b.coeffs[i];
-    return r;
-}
-FilterIR ir_reduce(const FilterIR &f, uint32_t order)      /* filter.go:520-604 */
-{
-    const uint64_t n = f.coeffs.size();
-    if (n <= (uint64_t)order) return f;
-    const uint64_t n_src = next_pow2(n), n_tgt = next_pow2(order);
-    std::vector<double> padded(n_src, 0.0);
-    std::copy(f.coeffs.begin(), f.coeffs.end(), padded.begin());
-    std::vector<cplx> fr = real_spectrum(padded);
-    const uint32_t pos_src = (uint32_t)(n_src >> 1) + 1, half_tgt = (uint32_t)(n_tgt >> 1), pos_tgt = half_tgt + 1;
-    std::vector<double> re(pos_src), im(pos_src);
-    for (uint32_t i = 0; i < pos_src; i++) { re[i] = fr[i].real(); im[i] = fr[i].imag(); }
-    std::vector<cplx> pos(pos_tgt);
-    const double dx = (double)pos_src / (double)pos_tgt;                      /* resample.go:109-142 Frequency */
-    for (uint32_t i = 0; i < pos_tgt; i++) {
-        const double x = (double)i * dx;
-        pos[i] = cplx(lanczos_interpolate(re.data(), pos_src, x, 3), lanczos_interpolate(im.data(), pos_src, x, 3));
-    }
-    /* RealInverseFourier of [pos | conj mirror] (fft.go:863-990): it symmetrises the bins, keeps only the
-     * real parts of DC and Nyquist, and inverts - equivalent to a complex inverse FFT of the Hermitian
-     * completion with real DC/Nyquist. */
-    std::vector<cplx> full(n_tgt);
-    for (uint32_t i = 0; i < pos_tgt && i < n_tgt; i++) full[i] = pos[i];
-    for (uint32_t i = 1; i < half_tgt; i++) full[n_tgt - i] = std::conj(pos[i]);
-    full[0] = cplx(full[0].real(), 0.0);
-    if (half_tgt > 0) full[half_tgt] = cplx(full[half_tgt].real(), 0.0);
-    fft_inplace(full, true);
-    FilterIR r; r.rate = f.rate; r.comp = f.comp; r.coeffs.resize(order);
-    for (uint32_t i = 0; i < order; i++) r.coeffs[i] = full[i].real();
-    return r;
-}
+
+/* a filter's coefficients on the device (the coefficient side of filter.filterStruct) */
+struct DevFilter {
+    double *d = nullptr; size_t n = 0; bool owned = false;
+    DevFilter() {}
+    DevFilter(const DevFilter &) = delete;
+    DevFilter &operator=(const DevFilter &) = delete;
+    void reset() { if (owned && d) gdgb_free(d); d = nullptr; n = 0; owned = false; }
+    ~DevFilter() { reset(); }
+};
 
 } // namespace
 
 struct gdg_irbank {
     std::vector<ImpulseResponse> responses;
+    uint64_t generation = 0;                               /* bumped by every add: compiled-filter cache key */
     std::vector<std::string> names() const                 /* filter.go:681-699 */
     {
         std::vector<std::string> out;
@@ -219,8 +144,12 @@ namespace {
 /* compiled power-amp filters: device spectrum shared between chains           */
 /* ------------------------------------------------------------------------ */
 struct DeviceSpectrum { double *d_H = nullptr; int L = 0, F = 0, logM = 0, K = 1; ~DeviceSpectrum() { if (d_H) gdgb_free(d_H); } };
+/* a compiled power-amp filter (the composite of poweramp.compile, poweramp.go:25-127): coefficients on the device, shared by
+ * every chain whose recipe (bank, rate, target order, filter names and levels) is the same */
+struct CompiledFilter { double *d = nullptr; int L = 0; std::string key; ~CompiledFilter() { if (d) gdgb_free(d); } };
 std::mutex g_spec_mutex;
 std::map<std::string, std::weak_ptr<DeviceSpectrum>> g_spec_cache;
+std::map<std::string, std::weak_ptr<CompiledFilter>> g_filter_cache;
 
 /* partition length of the convolution for a filter of L taps processed in blocks of n samples: filters of up to 8192 taps run
  * as ONE partition of nextPow2(L) taps whatever the block length (the reference's own block size, filter.go:372-388);
@@ -232,31 +161,24 @@ uint64_t partition_length(size_t L, size_t n)
     if (2 * B <= GDG_MAX_FFT) return B;
     return std::min<uint64_t>((uint64_t)n, GDG_MAX_FFT / 2);
 }
-std::shared_ptr<DeviceSpectrum> make_spectrum(const std::vector<double> &coeffs, uint64_t B)
+/* H of filter.Process (filter.go:395-401) for every partition, built on the device by the chain kernel's own FFT */
+std::shared_ptr<DeviceSpectrum> make_spectrum(const CompiledFilter &flt, uint64_t B)
 {
-    const int L = (int)coeffs.size();
+    const int L = flt.L;
     uint32_t e = 0;
     next_pow2(B, &e);
     const int K = std::max(1, (int)((L + (int)B - 1) / (int)B));
     const int F = (int)(2 * B);
-    std::string key((const char *)coeffs.data(), coeffs.size() * sizeof(double));
-    key.append((const char *)&B, sizeof B);
+    std::string key = flt.key;
+    key.append("|B="); key.append(std::to_string(B));
     std::lock_guard<std::mutex> lk(g_spec_mutex);
     auto it = g_spec_cache.find(key);
     if (it != g_spec_cache.end()) if (auto sp = it->second.lock()) return sp;
     auto sp = std::make_shared<DeviceSpectrum>();
     sp->L = L; sp->F = F; sp->logM = (int)e; sp->K = K;     /* M = F/2 = B = 2^e */
     const size_t bins = (size_t)F / 2 + 1;
-    std::vector<double> packed(2 * bins * (size_t)K);
-    for (int p = 0; p < K; p++) {
-        std::vector<double> padded((size_t)F, 0.0);
-        const size_t lo = (size_t)p * B, hi = std::min((size_t)L, lo + (size_t)B);
-        std::copy(coeffs.begin() + lo, coeffs.begin() + hi, padded.begin());
-        std::vector<cplx> H = real_spectrum(padded);        /* filter.go:395-401 */
-        for (size_t k = 0; k < bins; k++) { packed[2 * (p * bins + k)] = H[k].real(); packed[2 * (p * bins + k) + 1] = H[k].imag(); }
-    }
-    sp->d_H = (double *)gdgb_alloc(packed.size() * sizeof(double));
-    if (!sp->d_H || gdgb_upload(sp->d_H, packed.data(), packed.size() * sizeof(double))) return nullptr;
+    sp->d_H = (double *)gdgb_alloc(2 * bins * (size_t)K * sizeof(double));
+    if (!sp->d_H || gdgb_ir_partition_spectra(flt.d, L, (int)B, (int)e, K, sp->d_H, gdgb_stream())) return nullptr;
     g_spec_cache[key] = sp;
     return sp;
 }
@@ -287,7 +209,7 @@ struct Unit {
     /* cached descriptor */
     gdg_unit_desc desc; bool dirty = true; uint32_t cached_rate = 0; bool valid = false;
     /* power amp */
-    uint32_t pa_rate = 0; bool pa_has_filter = false; FilterIR pa_filter; bool pa_new_filter = false;
+    uint32_t pa_rate = 0; bool pa_has_filter = false; std::shared_ptr<CompiledFilter> pa_filter; bool pa_new_filter = false;
     std::shared_ptr<DeviceSpectrum> pa_spec;
 
     explicit Unit(int t) : type(t) { memset(&desc, 0, sizeof desc); }
@@ -329,12 +251,21 @@ struct Unit {
     int prepare(uint32_t rate, size_t n);
 };
 
-/* effects/poweramp.go:25-127 compile */
+/* effects/poweramp.go:25-127 compile - on the device: per selected response
+ *   Reduce(filter_order)  filter.go:520-604   real FFT -> Lanczos resampling of the positive bins -> inverse -> truncate
+ *   Normalize             filter.go:328-336   scale to compensation / ||h||_2
+ *   Multiply(10^(level/20)), Add into the composite   filter.go:270-323, 167-253
+ * enqueued on the library stream; identical recipes are compiled once and shared. */
 int Unit::compile_poweramp(uint32_t rate)
 {
     if (!bank) return -1;                                   /* "No impulse responses were loaded." */
     const uint32_t target = (uint32_t)strtoul(disc("filter_order").c_str(), nullptr, 10);
-    FilterIR comp; comp.rate = rate;                        /* filter.Empty */
+    struct Term { const ImpulseResponse *ir; double fac; size_t len; };
+    std::vector<Term> terms;
+    char head[96];
+    snprintf(head, sizeof head, "bank=%p/%llu|rate=%u|order=%u|", (void *)bank, (unsigned long long)bank->generation, rate, target);
+    std::string key(head);
+    size_t L = 0;
     for (int i = 0; i < 8; i++) {
         char pf[32], pl[32];
         snprintf(pf, sizeof pf, "filter_%d", i + 1);
@@ -343,14 +274,45 @@ int Unit::compile_poweramp(uint32_t rate)
         if (name != "- NONE -") {
             const ImpulseResponse *ir = bank->find(name, rate);
             if (!ir) return -1;                             /* "Failed to load filter '%s' for sample rate '%d'." */
-            FilterIR f; f.coeffs = ir->data; f.rate = rate; f.comp = ir->comp;
-            if (target > 0) f = ir_reduce(f, target);
-            f = ir_normalize(f);
-            f = ir_multiply(f, db2fac(num(pl)));
-            comp = ir_add(comp, f);
+            const size_t len = (target > 0 && ir->n > (size_t)target) ? (size_t)target : ir->n;     /* Reduce is a no-op for n <= order */
+            terms.push_back(Term{ir, db2fac(num(pl)), len});
+            L = std::max(L, len);
+            key.append(name); key.push_back('\x1f'); key.append(std::to_string(num(pl))); key.push_back(';');
         }
     }
-    pa_filter = comp; pa_has_filter = true; pa_new_filter = true;
+    std::lock_guard<std::mutex> lk(g_spec_mutex);
+    auto it = g_filter_cache.find(key);
+    if (it != g_filter_cache.end()) if (auto sp = it->second.lock()) { pa_filter = sp; pa_has_filter = true; pa_new_filter = true; return 0; }
+    auto sp = std::make_shared<CompiledFilter>();
+    sp->L = (int)L; sp->key = key;
+    sp->d = (double *)gdgb_alloc(std::max<size_t>(1, L) * sizeof(double));     /* filter.Empty: zeros */
+    double *d_ss = (double *)gdgb_alloc(sizeof(double));
+    if (!sp->d || !d_ss) { gdgb_free(d_ss); return backend_fail("filter allocation failed"); }
+    std::vector<double *> temps{d_ss};
+    void *st = gdgb_stream();
+    int rc = 0;
+    for (auto &t : terms) {
+        const double *cur = t.ir->d_data;
+        if (t.len != t.ir->n) {                             /* filter.Reduce */
+            const int n_src = (int)next_pow2(t.ir->n), n_tgt = (int)next_pow2(target);
+            const int pos_src = n_src / 2 + 1, pos_tgt = n_tgt / 2 + 1;
+            double *work = (double *)gdgb_alloc((size_t)std::max(n_src, n_tgt) * sizeof(double));
+            double *spec = (double *)gdgb_alloc(2 * (size_t)pos_src * sizeof(double));
+            double *spec2 = (double *)gdgb_alloc(2 * (size_t)pos_tgt * sizeof(double));
+            double *red = (double *)gdgb_alloc((size_t)target * sizeof(double));
+            temps.push_back(work); temps.push_back(spec); temps.push_back(spec2); temps.push_back(red);
+            if (!work || !spec || !spec2 || !red) { rc = backend_fail("filter allocation failed"); break; }
+            if (gdgb_ir_real_spectrum(cur, (long)t.ir->n, n_src, work, spec, st) || gdgb_ir_resample_bins(spec, pos_src, spec2, pos_tgt, st) ||
+                gdgb_ir_real_inverse(spec2, n_tgt, work, red, (long)target, st)) { rc = backend_fail("filter reduction failed"); break; }
+            cur = red;
+        }
+        if (gdgb_ir_sum_squares(cur, (long)t.len, d_ss, st) || gdgb_ir_scale_add(sp->d, cur, (long)t.len, t.ir->comp, t.fac, d_ss, st)) { rc = backend_fail("filter compilation failed"); break; }
+    }
+    gdgb_sync();                                            /* the scratch buffers go away */
+    for (double *p : temps) gdgb_free(p);
+    if (rc) return -1;
+    g_filter_cache[key] = sp;
+    pa_filter = sp; pa_has_filter = true; pa_new_filter = true;
     return 0;
 }
 
@@ -362,7 +324,7 @@ int Unit::prepare(uint32_t rate, size_t n)
         compile_poweramp(rate);
         dirty = true;
     }
-    if (type == GDG_UNIT_POWERAMP && pa_spec && pa_has_filter && !pa_new_filter && pa_spec->F != (int)(2 * partition_length(pa_filter.coeffs.size(), n))) {
+    if (type == GDG_UNIT_POWERAMP && pa_spec && pa_has_filter && !pa_new_filter && pa_spec->F != (int)(2 * partition_length((size_t)pa_filter->L, n))) {
         /* a filter longer than 8192 taps is partitioned by the block length: a new block length re-partitions it.  DELIBERATE
          * DIFFERENCE: the overlap tail restarts here, the reference's single big FFT keeps it across block-length changes. */
         pa_new_filter = true; dirty = true;
@@ -534,11 +496,11 @@ int Unit::prepare(uint32_t rate, size_t n)
         break; }
     case GDG_UNIT_POWERAMP: {
         if (!pa_has_filter) { d.i[0] = -1; break; }        /* poweramp.go:210-214: zeros */
-        const int L = (int)pa_filter.coeffs.size();
+        const int L = pa_filter->L;
         d.i[0] = L;
         if (L > 0) {
             if (pa_new_filter || !pa_spec) {
-                pa_spec = make_spectrum(pa_filter.coeffs, partition_length(pa_filter.coeffs.size(), n));
+                pa_spec = make_spectrum(*pa_filter, partition_length((size_t)pa_filter->L, n));
                 if (!pa_spec) return backend_fail("filter spectrum upload failed");
                 /* a recompiled filter is a NEW filter object in the reference: fresh (zero) overlap tail */
                 if (d_st) { gdgb_sync(); gdgb_free(d_st); d_st = nullptr; }
@@ -1150,17 +1112,33 @@ gdg_irbank *gdg_irbank_create(void) { return new gdg_irbank(); }
 void gdg_irbank_destroy(gdg_irbank *b) { delete b; }
 int gdg_irbank_add(gdg_irbank *b, const char *name, int32_t comp_db, const double *s, size_t n, uint32_t src_rate)
 {
+    if (ensure_init()) return -1;
     if (!b || !name || (!s && n)) return fail("gdg_irbank_add: bad argument");
     if (src_rate == 0) return fail("gdg_irbank_add: source rate must not be zero");
     const double fac = std::pow(10.0, 0.05 * (double)comp_db);      /* filter.go:742-745 */
-    std::vector<double> in(s, s + n);
-    for (uint32_t r : k_sample_rates) b->responses.push_back(ImpulseResponse{name, r, fac, resample_time(in, src_rate, r)});
-    return 0;
+    /* filter.Import's resample.Time to the seven supported rates (filter.go:766-780) runs on the device; the responses stay there */
+    double *d_src = (double *)gdgb_alloc(std::max<size_t>(1, n) * sizeof(double));
+    if (!d_src || (n && gdgb_upload(d_src, s, n * sizeof(double)))) { gdgb_free(d_src); return backend_fail("impulse response upload failed"); }
+    int rc = 0;
+    for (uint32_t r : k_sample_rates) {
+        const size_t len = resample_time_length(n, src_rate, r);
+        double *d = (double *)gdgb_alloc(std::max<size_t>(1, len) * sizeof(double));
+        if (!d || gdgb_resample_time(d_src, (long)n, (double)src_rate / (double)r, d, (long)len, gdgb_stream())) { gdgb_free(d); rc = backend_fail("impulse response resampling failed"); break; }
+        b->responses.emplace_back(name, r, fac, d, len);
+    }
+    gdgb_sync(); gdgb_free(d_src);
+    b->generation++;
+    return rc;
 }
 int gdg_irbank_add_raw(gdg_irbank *b, const char *name, int32_t comp_db, const double *s, size_t n, uint32_t rate)
 {
+    if (ensure_init()) return -1;
     if (!b || !name || (!s && n)) return fail("gdg_irbank_add_raw: bad argument");
-    b->responses.push_back(ImpulseResponse{name, rate, std::pow(10.0, 0.05 * (double)comp_db), std::vector<double>(s, s + n)});
+    double *d = (double *)gdgb_alloc(std::max<size_t>(1, n) * sizeof(double));
+    if (!d || (n && gdgb_upload(d, s, n * sizeof(double)))) { gdgb_free(d); return backend_fail("impulse response upload failed"); }
+    gdgb_sync();
+    b->responses.emplace_back(name, rate, std::pow(10.0, 0.05 * (double)comp_db), d, n);
+    b->generation++;
     return 0;
 }
 size_t gdg_irbank_name_count(const gdg_irbank *b) { return b ? b->names().size() : 0; }
@@ -1466,6 +1444,21 @@ const char *gdg_chain_parameter_discrete_value(gdg_chain *c, int id, int index, 
     return (vi >= 0 && vi < (int)p.disc.size()) ? p.disc[vi].c_str() : nullptr;
 }
 
+/* Filter.Coefficients() of a power amp's compiled composite filter (filter.go:258-265): for inspection and tests */
+long gdg_chain_filter_coefficients(gdg_chain *c, int id, double *out, size_t capacity)
+{
+    if (ensure_init()) return -1;
+    if (!c) { fail("chain is NULL"); return -1; }
+    ProcessLock lk(g_edit_mutex);
+    if (id < 0 || id >= (int)c->slots.size()) { fail("Cannot get filter coefficients: No unit %d.", id); return -1; }
+    Unit *u = c->slots[id].unit.get();
+    if (u->type != GDG_UNIT_POWERAMP) { fail("Cannot get filter coefficients: Unit %d is not a power amp.", id); return -1; }
+    if (!u->pa_has_filter || !u->pa_filter) return 0;
+    const size_t L = (size_t)u->pa_filter->L;
+    if (out && capacity >= L && L && gdgb_download(out, u->pa_filter->d, L * sizeof(double))) { backend_fail("download failed"); return -1; }
+    return (long)L;
+}
+
 int gdg_process_batch_device(gdg_chain *const *chains, size_t C, const double *d_in, double *d_out, size_t stride,
                              size_t n, uint32_t rate, void *stream)
 {
@@ -1626,18 +1619,15 @@ int gdg_tuner_process(gdg_tuner *t, const double *s, size_t n, uint32_t rate)
     if (n && gdgb_upload(t->d_block, s, n * sizeof(double))) return backend_fail("upload failed");
     return gdg_tuner_process_device(t, t->d_block, n == N ? N : n, rate, nullptr);
 }
-/* tuner.Analyze: tuner/tuner.go:379-577 - the 262144-point autocorrelation runs on the device;
- * the scalar peak pick / note lookup below is the control-plane tail of the call. */
-int gdg_tuner_analyze(gdg_tuner *t, gdg_tuner_result *res)
+/* tuner.Analyze: tuner/tuner.go:379-577 - the 262144-point autocorrelation runs on the device (all tuners of a batch in
+ * one set of launches); the scalar peak pick / note lookup below is the control-plane tail of the call. */
+static int tuner_pick(gdg_tuner *t, gdg_tuner_result *res)
 {
     static const char *names[GDG_TUNER_NOTE_COUNT] = GDG_TUNER_NOTE_NAMES_INIT;
     static const double freqs[GDG_TUNER_NOTE_COUNT] = GDG_TUNER_NOTE_FREQS_INIT;
-    if (ensure_init()) return -1;
-    if (!t || !res) return fail("gdg_tuner_analyze: bad argument");
     const long n = gdg_tuner::N;
     const uint64_t two_n = 2 * (uint64_t)n;
     const int fft_size = (int)next_pow2(two_n);
-    if (gdgb_autocorrelate(t->d_ring, (int)n, t->pos, t->d_work, fft_size, gdgb_stream())) return backend_fail("autocorrelation failed");
     const double sr = (double)t->rate;
     long low = (long)((sr / freqs[GDG_TUNER_NOTE_COUNT - 1]) + 0.5);
     if (low < 0 || (uint64_t)low >= two_n) low = 0;
@@ -1665,6 +1655,26 @@ int gdg_tuner_analyze(gdg_tuner *t, gdg_tuner_result *res)
     res->cents = (std::isinf(cents) || std::isnan(cents)) ? 0 : (int8_t)cents;
     res->frequency = freq; res->note = note;
     return 0;
+}
+int gdg_tuner_analyze_batch(gdg_tuner *const *tuners, uint32_t count, gdg_tuner_result *results)
+{
+    if (ensure_init()) return -1;
+    if ((!tuners || !results) && count) return fail("gdg_tuner_analyze_batch: bad argument");
+    std::vector<const double *> rings(count); std::vector<double *> works(count); std::vector<int> pos(count);
+    for (uint32_t i = 0; i < count; i++) {
+        if (!tuners[i]) return fail("gdg_tuner_analyze_batch: tuner %u is NULL", i);
+        rings[i] = tuners[i]->d_ring; works[i] = tuners[i]->d_work; pos[i] = tuners[i]->pos;
+    }
+    const int fft_size = (int)next_pow2(2 * (uint64_t)gdg_tuner::N);
+    if (count && gdgb_autocorrelate_batch(rings.data(), gdg_tuner::N, pos.data(), works.data(), (int)count, fft_size, gdgb_stream()))
+        return backend_fail("autocorrelation failed");
+    for (uint32_t i = 0; i < count; i++) if (tuner_pick(tuners[i], &results[i])) return -1;
+    return 0;
+}
+int gdg_tuner_analyze(gdg_tuner *t, gdg_tuner_result *res)
+{
+    if (!t || !res) return fail("gdg_tuner_analyze: bad argument");
+    return gdg_tuner_analyze_batch(&t, 1, res);
 }
 
 /* ---- encoded batch (wave/wave.go sample formats fused into the kernel's load / store) ---- */
@@ -1713,15 +1723,7 @@ int gdg_process_batch_device_encoded(gdg_chain *const *chains, size_t C, const v
 }
 
 /* ---- resample.Time (resample/resample.go:72-103) ---- */
-size_t gdg_resample_time_length(size_t n, uint32_t src, uint32_t dst)
-{
-    if (!src) return 0;
-    const double lf = (double)n * ((double)dst / (double)src);
-    const double fl = std::floor(lf);
-    long len = (long)fl;
-    if (fl == lf) len--;
-    return len < 0 ? 0 : (size_t)len;
-}
+size_t gdg_resample_time_length(size_t n, uint32_t src, uint32_t dst) { return resample_time_length(n, src, dst); }
 long gdg_resample_time(const double *in, size_t n, uint32_t src, uint32_t dst, double *out, size_t out_capacity)
 {
     if (ensure_init()) return -1;

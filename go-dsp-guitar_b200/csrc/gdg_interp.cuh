@@ -416,4 +416,112 @@ GDG_DEVI void ac_power_body(double *w, int M, int logM, int k)
     }
 }
 
+/* --------------------------------------------------------------------------
+ * Impulse-response compilation on the device: the per-index bodies of
+ *   filter.Reduce      filter/filter.go:520-604  (RealFourier -> resample.Frequency -> RealInverseFourier -> truncate)
+ *   filter.Normalize   filter/filter.go:127-138, 328-336 ; Multiply :270-323 ; Add :167-253
+ *   the spectrum H of filter.Process (filter.go:395-401), per partition
+ * Real transforms of size n go through a complex transform of M = n/2 points in global memory: the tuner's radix-2
+ * DIF / DIT passes (ac_dif_body / ac_dit_body, natural -> bit-reversed -> natural) plus the split passes below.
+ * -------------------------------------------------------------------------- */
+/* zero-padded copy: w[i] = i < n_x ? x[i] : 0, i < n (n real = n/2 complex points, interleaved) */
+GDG_DEVI void ir_pad_body(const double *x, long n_x, double *w, long i) { w[i] = i < n_x ? x[i] : 0.0; }
+/* forward split: bins X[k], k = 0..M, in natural order from the bit-reversed half-size transform Z (fft.go:801-818, 832-838) */
+GDG_DEVI void ir_split_body(const double *w, int M, int logM, double *spec, int k)
+{
+    if (k == 0 || k == M) {
+        const double zr = w[0], zi = w[1];
+        spec[2 * k] = k == 0 ? zr + zi : zr - zi; spec[2 * k + 1] = 0.0;
+        return;
+    }
+    const int p1 = brev(k, logM), p2 = brev(M - k, logM);
+    const double ar = w[2 * p1], ai = w[2 * p1 + 1], br = w[2 * p2], bi = w[2 * p2 + 1];
+    double s, c;
+    GDG_SINCOSPI(-(double)k / (double)M, &s, &c);               /* W_n^k, n = 2M */
+    const double sr = ar + br, si = ai - bi, dr = ar - br, di = ai + bi;        /* A + conj B, A - conj B */
+    const double jr = -s, ji = c;                                               /* j W */
+    const double tr = jr * dr - ji * di, ti = jr * di + ji * dr;
+    spec[2 * k] = 0.5 * (sr - tr); spec[2 * k + 1] = 0.5 * (si - ti);
+}
+/* resample.Frequency (resample.go:109-142): Lanczos-3 on the real and imaginary parts, bin i of bins_out at x = i bins_in / bins_out */
+GDG_DEVI void ir_resample_bins_body(const double *spec_in, int bins_in, double *spec_out, int bins_out, int i)
+{
+    const double dx = (double)bins_in / (double)bins_out;
+    const double x = (double)i * dx;
+    const long idx = (long)floor(x);
+    double re = 0.0, im = 0.0;
+    for (long t = idx - 2; t < idx + 4; t++)
+        if (t >= 0 && t < bins_in) {
+            const double df = x - (double)t;
+            double kv;
+            if (df == 0.0) kv = 1.0;
+            else if (-3.0 < df && df < 3.0) { const double pix = GDG_PI * df; kv = (3.0 * (sin(pix) * sin(pix / 3.0))) / (pix * pix); }
+            else kv = 0.0;
+            re += spec_in[2 * t] * kv; im += spec_in[2 * t + 1] * kv;
+        }
+    spec_out[2 * i] = re; spec_out[2 * i + 1] = im;
+}
+/* inverse split (fft.go:899-955): half-size complex input Z'[k] at its bit-reversed slot from the Hermitian half Y[0..M]
+ * (only the real parts of Y[0] and Y[M] count, fft.go:908-913) */
+GDG_DEVI void ir_unsplit_body(const double *spec, int M, int logM, double *w, int k)
+{
+    if (k == 0) { const double y0 = spec[0], ym = spec[2 * M]; w[0] = 0.5 * (y0 + ym); w[1] = 0.5 * (y0 - ym); return; }
+    const int k2 = M - k;
+    const double ar = spec[2 * k], ai = spec[2 * k + 1], br = spec[2 * k2], bi = spec[2 * k2 + 1];
+    double s, c;
+    GDG_SINCOSPI(-(double)k / (double)M, &s, &c);
+    const double er = ar + br, ei = ai - bi, orr = ar - br, oi = ai + bi;       /* Ya + conj Yb, Ya - conj Yb */
+    const double pr = orr * c + oi * s, pi = oi * c - orr * s;                  /* (Ya - conj Yb) conj(W) */
+    const int p1 = brev(k, logM);
+    w[2 * p1] = 0.5 * (er - pi); w[2 * p1 + 1] = 0.5 * (ei + pr);               /* 0.5 (even + j odd) */
+}
+/* acc[i] = acc[i] + fac * ((comp / sqrt(ss)) * x[i]): Normalize -> Multiply -> Add of one term, element by element in the
+ * reference's order of operations (filter.go:328-336, 270-323, 209-215) */
+GDG_DEVI void ir_scale_add_body(double *acc, const double *x, double comp, double fac, const double *ss, long i)
+{
+    const double f = comp / sqrt(ss[0]);
+    acc[i] = acc[i] + (fac * (f * x[i]));
+}
+
+/* spectrum of partition p of a filter (filter.go:395-401 per 8192-tap / block-length partition): real FFT of size F = 2B of
+ * h[pB .. pB + B) zero-padded, through the chain kernel's own shared-memory FFT (half-size complex transform, DIF, natural ->
+ * bit-reversed) and a split pass; H: bins 0..B interleaved (re, im).  One CTA (GDG_NT threads) per partition. */
+GDG_DEV void run_partition_spectrum(double *smem, const double *coeffs, int L, int B, int logB, int p, double *H, const double *tw)
+{
+#if !defined(__CUDACC__) || defined(GDG_HOST_EMU)
+    gdg_smem = smem;
+#else
+    (void)smem;
+#endif
+    gdg_ctx &cx = *(gdg_ctx *)(gdg_smem + GDG_SMEM_CTX);
+    const int M = B, F = 2 * B, fstep = GDG_MAX_FFT / F;
+    double *D = SM_R;
+    GDG_THREADS_BEGIN
+        if (tid == 0) ctx_init(cx, B);
+        for (int k = tid; k < GDG_MAX_N / 8; k += GDG_NT) { SM_TWS[2 * k] = GDG_LDG(tw + 4 * k); SM_TWS[2 * k + 1] = GDG_LDG(tw + 4 * k + 1); }
+        for (int c = tid; c < M; c += GDG_NT) {
+            gdg_c2 v; v.re = 0.0; v.im = 0.0;
+            const long i0 = (long)p * B + 2 * c;
+            if (2 * c < B) { v.re = i0 < L ? coeffs[i0] : 0.0; v.im = (2 * c + 1 < B && i0 + 1 < L) ? coeffs[i0 + 1] : 0.0; }
+            cst(D, cz(c), v);
+        }
+    GDG_THREADS_END
+    fft_forward(cx, D, SM_TWS, logB, 1);
+    GDG_THREADS_BEGIN
+        for (int k = tid; k <= M; k += GDG_NT) {
+            double xr, xi;
+            if (k == 0 || k == M) { const gdg_c2 z0 = cld(D, cz(0)); xr = k == 0 ? z0.re + z0.im : z0.re - z0.im; xi = 0.0; }
+            else {
+                const gdg_c2 za = cld(D, cz(brev(k, logB))), zb = cld(D, cz(brev(M - k, logB)));
+                const gdg_c2 wk = tw_full(tw, k * fstep);                         /* W_F^k */
+                gdg_c2 jw; jw.re = -wk.im; jw.im = wk.re;
+                const gdg_c2 s1 = cadd(za, cconj(zb)), d1 = csub(za, cconj(zb));
+                const gdg_c2 t1 = cmul(jw, d1);
+                xr = 0.5 * (s1.re - t1.re); xi = 0.5 * (s1.im - t1.im);
+            }
+            H[2 * k] = xr; H[2 * k + 1] = xi;
+        }
+    GDG_THREADS_END
+}
+
 #endif

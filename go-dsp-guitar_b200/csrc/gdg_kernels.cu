@@ -137,6 +137,81 @@ __global__ void k_scale(double *w, int n, double f)
     if (i < n) w[i] *= f;
 }
 
+/* --- impulse-response compilation (gdg_interp.cuh ir_* bodies) --- */
+__global__ void k_ir_pad(const double *x, long n_x, double *w, long n)
+{
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) ir_pad_body(x, n_x, w, i);
+}
+__global__ void k_ir_split(const double *w, int M, int logM, double *spec)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k <= M) ir_split_body(w, M, logM, spec, k);
+}
+__global__ void k_ir_resample_bins(const double *in, int bins_in, double *out, int bins_out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < bins_out) ir_resample_bins_body(in, bins_in, out, bins_out, i);
+}
+__global__ void k_ir_unsplit(const double *spec, int M, int logM, double *w)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < M) ir_unsplit_body(spec, M, logM, w, k);
+}
+__global__ void k_ir_scale_copy(const double *w, double f, double *out, long n)
+{
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = f * w[i];
+}
+/* one CTA, fixed summation tree: the same bits from run to run */
+__global__ void __launch_bounds__(GDG_NT) k_ir_sum_squares(const double *x, long n, double *ss)
+{
+    __shared__ double red[GDG_NT];
+    double s = 0.0;
+    for (long i = threadIdx.x; i < n; i += GDG_NT) s += x[i] * x[i];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int h = GDG_NT / 2; h >= 1; h >>= 1) { if ((int)threadIdx.x < h) red[threadIdx.x] += red[threadIdx.x + h]; __syncthreads(); }
+    if (threadIdx.x == 0) ss[0] = red[0];
+}
+__global__ void k_ir_scale_add(double *acc, const double *x, long n, double comp, double fac, const double *ss)
+{
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) ir_scale_add_body(acc, x, comp, fac, ss, i);
+}
+__global__ void __launch_bounds__(GDG_NT, GDG_MIN_CTAS)
+k_ir_partition_spectra(const double *coeffs, int L, int B, int logB, double *H, const double *tw)
+{
+    run_partition_spectrum(gdg_smem, coeffs, L, B, logB, blockIdx.x, H + 2L * (long)blockIdx.x * (B + 1), tw);
+}
+/* batched tuner autocorrelation: blockIdx.y selects the tuner */
+struct gdg_ac_batch { const double *ring[32]; double *work[32]; int pos[32]; };
+__global__ void k_acb_load(gdg_ac_batch b, int n_ring, int F)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < F) ac_load_body(b.ring[blockIdx.y], n_ring, b.pos[blockIdx.y], b.work[blockIdx.y], i);
+}
+__global__ void k_acb_dif(gdg_ac_batch b, int M, int h)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < M / 2) ac_dif_body(b.work[blockIdx.y], h, t);
+}
+__global__ void k_acb_dit(gdg_ac_batch b, int M, int h)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < M / 2) ac_dit_body(b.work[blockIdx.y], h, t);
+}
+__global__ void k_acb_power(gdg_ac_batch b, int M, int logM)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k <= M / 2) ac_power_body(b.work[blockIdx.y], M, logM, k);
+}
+__global__ void k_acb_scale(gdg_ac_batch b, int n, double f)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) b.work[blockIdx.y][i] *= f;
+}
+
 /* ---- backend API ---------------------------------------------------------------- */
 const char *gdgb_error(void) { return t_err.c_str(); }
 const char *gdgb_name(void) { return "cuda:sm_100a"; }
@@ -162,6 +237,7 @@ int gdgb_init(int device)
     for (int i = 0; i < 2; i++) CU(cudaStreamCreateWithFlags(&g_copy_streams[i], cudaStreamNonBlocking));
     for (int i = 0; i < GDGB_EVENTS; i++) CU(cudaEventCreateWithFlags(&g_events[i], cudaEventDisableTiming));
     CU(cudaFuncSetAttribute(k_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, GDG_SMEM_BYTES));
+    CU(cudaFuncSetAttribute(k_ir_partition_spectra, cudaFuncAttributeMaxDynamicSharedMemorySize, GDG_SMEM_BYTES));
     CU(cudaFuncSetAttribute(k_os, cudaFuncAttributeMaxDynamicSharedMemorySize, GDG_OSK_SMEM_BYTES));
     CU(cudaFuncSetAttribute(k_os, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     return 0;
@@ -298,6 +374,71 @@ int gdgb_autocorrelate(const double *d_ring, int n_ring, int pos, double *d_work
     k_ac_power<<<(M / 2 + 1 + 255) / 256, 256, 0, s>>>(d_work, M, logM); g_launches++;
     for (int h = 1; h <= M / 2; h <<= 1) { k_ac_dit<<<(M / 2 + 255) / 256, 256, 0, s>>>(d_work, M, h); g_launches++; }
     k_scale<<<(F + 255) / 256, 256, 0, s>>>(d_work, F, 1.0 / (double)M); g_launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+/* ---- impulse-response compilation ------------------------------------------------------ */
+static int ilog2(int v) { int e = 0; while ((1 << e) < v) e++; return e; }
+int gdgb_ir_real_spectrum(const double *d_x, long n_x, int nfft, double *d_work, double *d_spec, void *stream)
+{
+    cudaStream_t s = (cudaStream_t)stream;
+    const int M = nfft / 2, logM = ilog2(M);
+    k_ir_pad<<<(unsigned)((nfft + 255) / 256), 256, 0, s>>>(d_x, n_x, d_work, nfft); g_launches++;
+    for (int h = M / 2; h >= 1; h >>= 1) { k_ac_dif<<<(M / 2 + 255) / 256, 256, 0, s>>>(d_work, M, h); g_launches++; }
+    k_ir_split<<<(M + 1 + 255) / 256, 256, 0, s>>>(d_work, M, logM, d_spec); g_launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+int gdgb_ir_resample_bins(const double *d_spec_in, int bins_in, double *d_spec_out, int bins_out, void *stream)
+{
+    k_ir_resample_bins<<<(bins_out + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_spec_in, bins_in, d_spec_out, bins_out); g_launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+int gdgb_ir_real_inverse(const double *d_spec, int nfft, double *d_work, double *d_out, long n_keep, void *stream)
+{
+    cudaStream_t s = (cudaStream_t)stream;
+    const int M = nfft / 2, logM = ilog2(M);
+    k_ir_unsplit<<<(M + 255) / 256, 256, 0, s>>>(d_spec, M, logM, d_work); g_launches++;
+    for (int h = 1; h <= M / 2; h <<= 1) { k_ac_dit<<<(M / 2 + 255) / 256, 256, 0, s>>>(d_work, M, h); g_launches++; }
+    k_ir_scale_copy<<<(unsigned)((n_keep + 255) / 256), 256, 0, s>>>(d_work, 1.0 / (double)M, d_out, n_keep); g_launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+int gdgb_ir_sum_squares(const double *d_x, long n, double *d_ss, void *stream)
+{
+    k_ir_sum_squares<<<1, GDG_NT, 0, (cudaStream_t)stream>>>(d_x, n, d_ss); g_launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+int gdgb_ir_scale_add(double *d_acc, const double *d_x, long n, double comp, double fac, const double *d_ss, void *stream)
+{
+    if (n > 0) { k_ir_scale_add<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_acc, d_x, n, comp, fac, d_ss); g_launches++; }
+    CU(cudaGetLastError());
+    return 0;
+}
+int gdgb_ir_partition_spectra(const double *d_coeffs, int L, int B, int logB, int K, double *d_H, void *stream)
+{
+    k_ir_partition_spectra<<<K, GDG_NT, GDG_SMEM_BYTES, (cudaStream_t)stream>>>(d_coeffs, L, B, logB, d_H, g_d_tw); g_launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+int gdgb_autocorrelate_batch(const double *const *d_rings, int n_ring, const int *pos, double *const *d_works, int count, int F, void *stream)
+{
+    cudaStream_t s = (cudaStream_t)stream;
+    const int M = F / 2, logM = ilog2(M);
+    for (int c0 = 0; c0 < count; c0 += 32) {
+        const int cnt = count - c0 < 32 ? count - c0 : 32;
+        gdg_ac_batch b;
+        for (int i = 0; i < cnt; i++) { b.ring[i] = d_rings[c0 + i]; b.work[i] = d_works[c0 + i]; b.pos[i] = pos[c0 + i]; }
+        dim3 gF((F + 255) / 256, cnt), gB((M / 2 + 255) / 256, cnt), gP((M / 2 + 1 + 255) / 256, cnt);
+        k_acb_load<<<gF, 256, 0, s>>>(b, n_ring, F); g_launches++;
+        for (int h = M / 2; h >= 1; h >>= 1) { k_acb_dif<<<gB, 256, 0, s>>>(b, M, h); g_launches++; }
+        k_acb_power<<<gP, 256, 0, s>>>(b, M, logM); g_launches++;
+        for (int h = 1; h <= M / 2; h <<= 1) { k_acb_dit<<<gB, 256, 0, s>>>(b, M, h); g_launches++; }
+        k_acb_scale<<<gF, 256, 0, s>>>(b, F, 1.0 / (double)M); g_launches++;
+    }
     CU(cudaGetLastError());
     return 0;
 }

@@ -115,6 +115,11 @@ typedef struct {
 int gdg_chain_parameter(gdg_chain *chain, int id, int index, gdg_parameter *out);
 const char *gdg_chain_parameter_discrete_value(gdg_chain *chain, int id, int index, int value_index);
 
+/* Filter.Coefficients() (filter/filter.go:258-265) of the composite filter a power amp compiled (effects/poweramp.go:25-127:
+ * Reduce / Normalize / Multiply / Add run on the device).  Returns the number of coefficients (0 when no
+ * filter has been compiled yet - the sample rate is only known at the first Process) and copies them when capacity suffices. */
+long gdg_chain_filter_coefficients(gdg_chain *chain, int id, double *out, size_t capacity);
+
 /* Chain.Process(in, out []float64, sampleRate uint32)  signal.go:361-414.
  * HOST buffers, synchronous: H2D, fused segment kernel(s), D2H.  The JACK-path drop-in. */
 int gdg_chain_process(gdg_chain *chain, const double *in, double *out, size_t n, uint32_t sample_rate);
@@ -176,6 +181,9 @@ int gdg_tuner_process(gdg_tuner *t, const double *samples, size_t n, uint32_t sa
 int gdg_tuner_process_device(gdg_tuner *t, const double *d_samples, size_t n, uint32_t sample_rate, void *stream);
 typedef struct { int8_t cents; double frequency; const char *note; } gdg_tuner_result;    /* tuner.Result :27-43 */
 int gdg_tuner_analyze(gdg_tuner *t, gdg_tuner_result *result);                            /* Analyze :379-577 */
+/* Analyze for `count` tuners at once (one per channel strip, polled together by the UI, controller.go:625-627): the 262144-point
+ * autocorrelations run as ONE batch of launches, results[i] belongs to tuners[i] */
+int gdg_tuner_analyze_batch(gdg_tuner *const *tuners, uint32_t count, gdg_tuner_result *results);
 
 /* ---- level.Meter  level/level.go ------------------------------------------------------ */
 /* CreateMeter(numChannels, names) :318-399 (names may be NULL: empty names); created disabled */

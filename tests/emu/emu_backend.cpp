@@ -31,7 +31,7 @@ const char *gdgb_error(void) { return t_err.c_str(); }
 const char *gdgb_name(void) { return "host-emulation (tests only)"; }
 int gdgb_init(int) { return 0; }
 int gdgb_device(void) { return -1; }
-int gdgb_sm_count(void) { return 0; }
+int gdgb_sm_count(void) { return 148; }            /* the part being emulated: pipeline groups are sized like on a B200 */
 void *gdgb_stream(void) { return nullptr; }
 uint64_t gdgb_launch_count(void) { return g_launches.load(); }
 void *gdgb_alloc(size_t bytes) { return calloc(1, bytes ? bytes : 8); }
@@ -131,5 +131,59 @@ int gdgb_autocorrelate(const double *ring, int n_ring, int pos, double *w, int F
     for (int k = 0; k <= M / 2; k++) ac_power_body(w, M, logM, k);
     for (int h = 1; h <= M / 2; h <<= 1) for (int b = 0; b < M / 2; b++) ac_dit_body(w, h, b);
     for (int i = 0; i < F; i++) w[i] *= 1.0 / (double)M;
+    return 0;
+}
+
+/* ---- impulse-response compilation (host loops over the same bodies) ---- */
+static int ilog2(int v) { int e = 0; while ((1 << e) < v) e++; return e; }
+int gdgb_ir_real_spectrum(const double *x, long n_x, int nfft, double *w, double *spec, void *)
+{
+    const int M = nfft / 2, logM = ilog2(M);
+    for (long i = 0; i < nfft; i++) ir_pad_body(x, n_x, w, i);
+    for (int h = M / 2; h >= 1; h >>= 1) for (int b = 0; b < M / 2; b++) ac_dif_body(w, h, b);
+    for (int k = 0; k <= M; k++) ir_split_body(w, M, logM, spec, k);
+    g_launches++;
+    return 0;
+}
+int gdgb_ir_resample_bins(const double *in, int bins_in, double *out, int bins_out, void *)
+{
+    for (int i = 0; i < bins_out; i++) ir_resample_bins_body(in, bins_in, out, bins_out, i);
+    g_launches++;
+    return 0;
+}
+int gdgb_ir_real_inverse(const double *spec, int nfft, double *w, double *out, long n_keep, void *)
+{
+    const int M = nfft / 2, logM = ilog2(M);
+    for (int k = 0; k < M; k++) ir_unsplit_body(spec, M, logM, w, k);
+    for (int h = 1; h <= M / 2; h <<= 1) for (int b = 0; b < M / 2; b++) ac_dit_body(w, h, b);
+    for (long i = 0; i < n_keep; i++) out[i] = (1.0 / (double)M) * w[i];
+    g_launches++;
+    return 0;
+}
+int gdgb_ir_sum_squares(const double *x, long n, double *ss, void *)
+{
+    double red[GDG_NT];
+    for (int t = 0; t < GDG_NT; t++) { double s = 0.0; for (long i = t; i < n; i += GDG_NT) s += x[i] * x[i]; red[t] = s; }
+    for (int h = GDG_NT / 2; h >= 1; h >>= 1) for (int t = 0; t < h; t++) red[t] += red[t + h];
+    ss[0] = red[0];
+    g_launches++;
+    return 0;
+}
+int gdgb_ir_scale_add(double *acc, const double *x, long n, double comp, double fac, const double *ss, void *)
+{
+    for (long i = 0; i < n; i++) ir_scale_add_body(acc, x, comp, fac, ss, i);
+    g_launches++;
+    return 0;
+}
+int gdgb_ir_partition_spectra(const double *coeffs, int L, int B, int logB, int K, double *H, void *)
+{
+    std::vector<double> smem(GDG_SMEM_DOUBLES);
+    for (int p = 0; p < K; p++) run_partition_spectrum(smem.data(), coeffs, L, B, logB, p, H + 2L * (long)p * (B + 1), g_tw.data());
+    g_launches++;
+    return 0;
+}
+int gdgb_autocorrelate_batch(const double *const *rings, int n_ring, const int *pos, double *const *works, int count, int F, void *st)
+{
+    for (int c = 0; c < count; c++) if (gdgb_autocorrelate(rings[c], n_ring, pos[c], works[c], F, st)) return -1;
     return 0;
 }

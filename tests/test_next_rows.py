@@ -435,3 +435,84 @@ def test_setters_race_free_against_processing(lib):
     finally:
         stop.set(); th.join()
     assert not errors, errors
+
+
+# ---- impulse-response compilation on the device, batched tuner analysis ------------------------------
+def _oracle_composite(h_by_name, comp_db, rate_src, rate, order, picks):
+    """poweramp.compile (poweramp.go:25-127) with the oracle's filter algebra: picks = [(name, level_db)]"""
+    acc = np.zeros(0)
+    for name, level in picks:
+        data = orc.resample_time(h_by_name[name], rate_src, rate)       # filter.Import resamples to EVERY rate, its own included (filter.go:766-780)
+        f = orc.Filter(data, rate)
+        f.set_compensation(10.0 ** (0.05 * comp_db[name]))
+        if order > 0:
+            f = f.reduce(order)
+        c = f.normalize().multiply(10.0 ** (0.05 * level)).coefficients()
+        out = np.zeros(max(len(acc), len(c)))
+        out[:len(acc)] = acc
+        out[:len(c)] += c
+        acc = out
+    return acc
+
+
+@pytest.mark.parametrize("order", ["1048576", "4096", "512", "64"])
+def test_device_ir_compile_matches_oracle_algebra(lib, order):
+    """filter.Import's resampling, Reduce, Normalize, Multiply and Add run on the device (gdg_host.cpp compile_poweramp);
+    the composite's coefficients equal the oracle's filter algebra on the same responses."""
+    rng = np.random.default_rng(17)
+    src_rate = 96000
+    h = {"A": rng.uniform(-1, 1, 3000) * np.exp(-np.arange(3000) / 500.0), "B": rng.uniform(-1, 1, 700) * np.exp(-np.arange(700) / 90.0),
+         "C": rng.uniform(-1, 1, 9600) * np.exp(-np.arange(9600) / 2500.0)}
+    comp = {"A": -3, "B": 2, "C": 0}
+    bank = gdg.IRBank(lib)
+    for k in h:
+        bank.add(k, comp[k], h[k], src_rate)
+    picks = [("A", -2), ("C", -7), ("B", 0)]
+    for rate in (192000, 44100, 96000):
+        ch = gdg.Chain(bank, lib=lib)
+        i = ch.append_unit("power_amp")
+        ch.set_discrete_value(i, "filter_order", order)
+        for slot, (name, level) in enumerate(picks):
+            ch.set_discrete_value(i, "filter_%d" % (slot + 1), name)
+            ch.set_numeric_value(i, "level_%d" % (slot + 1), level)
+        ch.set_bypass(i, False)
+        assert len(ch.filter_coefficients(i)) == 0               # no rate yet: nothing compiled (poweramp.go:132-154 with sampleRate 0)
+        ch.process(np.zeros(256), rate)
+        got = ch.filter_coefficients(i)
+        ref = _oracle_composite(h, comp, src_rate, rate, int(order), picks)
+        assert got.shape == ref.shape, (rate, got.shape, ref.shape)
+        assert np.max(np.abs(got - ref)) <= 1e-12 * max(1.0, np.max(np.abs(ref))), (rate, np.max(np.abs(got - ref)))
+
+
+def test_identical_recipes_share_one_compiled_filter(lib):
+    """1024 chains with the same power-amp settings compile ONE composite filter and ONE spectrum (the recipe cache)."""
+    bank = gdg.IRBank(lib)
+    bank.add_raw("ir", 0, common.synthetic_ir(300), 48000)
+    before = gdg.launch_count(lib)
+    chains = []
+    for _ in range(64):
+        c = common.build_chain(gdg.Chain(bank, lib=lib), [("power_amp", {"level_1": -3}, {"filter_1": "ir"})])
+        chains.append(c)
+    x = np.zeros((64, 256))
+    gdg.process_batch(chains, x, 48000)
+    launches = gdg.launch_count(lib) - before
+    assert launches <= 8, launches                               # sum of squares, scale-add, spectra, the chain kernel - not 64 of each
+
+
+def test_tuner_analyze_batch_equals_single_calls(lib):
+    import os
+    notes = ["A2", "D3", "E4"]
+    tuners, singles = [], []
+    for note in notes:
+        z = np.load(os.path.join(common.GOLD, "tuner_tail_%s.npz" % note))
+        t = gdg.Tuner(lib=lib)
+        t.process(z["samples"], int(z["sample_rate"]))
+        tuners.append(t)
+        o = orc.Tuner()
+        o.process(z["samples"], int(z["sample_rate"]))
+        singles.append(o.analyze())
+    batch = gdg.tuner_analyze_batch(tuners)
+    for note, b, o in zip(notes, batch, singles):
+        assert b["note"] == note == o["note"] and b["cents"] == o["cents"]
+        assert abs(b["frequency"] - o["frequency"]) <= 1e-9 * o["frequency"]
+    assert [t.analyze() for t in tuners] == batch
