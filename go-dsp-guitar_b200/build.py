@@ -13,8 +13,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libgdg.so")
 SOURCES = ["gdg_kernels.cu", "gdg_host.cpp"]
-DEPS = ["gdg_stages.cuh", "gdg_stages2.cuh", "gdg_interp.cuh", "gdg_device.h", "gdg_backend.h",
-        "../../include/gdg.h", "../../include/gdg_tables.h", "../../include/gdg_consts.h", "../../include/gdg_unit_params.def"]
+INCLUDE = os.path.join(os.path.dirname(HERE), "include")
+DEPS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h", ".cu", ".cpp"))) + \
+    sorted(os.path.join("..", "..", "include", f) for f in os.listdir(INCLUDE))        # every source and header: nothing stale ships
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
 

@@ -30,16 +30,18 @@
 #define GDG_OSK_ZPS (((GDG_ZH + GDG_OSK_TILE + 1) * 9) / 8 + 8)      /* doubles per polyphase array */
 #define GDG_OSK_STASH (4 * (GDG_ZH + 1) + 8)    /* per unit: carried halo of 4 branches + the last 8 inputs */
 
-/* shared-memory carve-up (offsets in doubles off gdg_smem).  The signal buffers use the same one-pad-per-8 layout as the
- * polyphase arrays (pz): a thread that owns 8 consecutive outputs (stride 9 across the warp) and a warp that touches 32
- * consecutive samples are both (nearly) bank-conflict-free. */
-#define GDG_OSK_XLEN (((8 + GDG_OSK_TILE) * 9) / 8 + 2)                /* [8 history | tile], padded */
+/* shared-memory carve-up (offsets in doubles off gdg_smem).  The unit input / output buffers XA, XB are PLAIN ([8 history |
+ * tile]): every access to them is unit-stride across the warp, and the up-sampler's six taps are immediate offsets off one
+ * address.  The FIR writes its F branch sums as chunks of 8 consecutive outputs per thread (stride 8 across the warp), so
+ * those go to PART in the one-pad-per-8 layout (pz, stride 9: conflict-free) and the combine pass - unit-stride again - sums
+ * them into the plain output buffer. */
+#define GDG_OSK_XLEN (8 + GDG_OSK_TILE)                                /* [8 history | tile] */
 #define GDG_OSK_PLEN ((GDG_OSK_TILE * 9) / 8 + 2)
 #define GDG_OSK_XA 0
 #define GDG_OSK_XB (GDG_OSK_XA + GDG_OSK_XLEN)
 #define GDG_OSK_Z (GDG_OSK_XB + GDG_OSK_XLEN)                          /* 4 polyphase arrays */
-#define GDG_OSK_PART (GDG_OSK_Z + 4 * GDG_OSK_ZPS)                     /* branch sums 1..3 */
-#define GDG_OSK_ST (GDG_OSK_PART + 3 * GDG_OSK_PLEN)                   /* per unit: halo + input history */
+#define GDG_OSK_PART (GDG_OSK_Z + 4 * GDG_OSK_ZPS)                     /* branch sums 0..3 */
+#define GDG_OSK_ST (GDG_OSK_PART + 4 * GDG_OSK_PLEN)                   /* per unit: halo + input history */
 #define GDG_OSK_FZ (GDG_OSK_ST + GDG_OSK_MAX_UNITS * GDG_OSK_STASH)    /* per unit: fuzz envelope, coupling capacitor */
 #define GDG_OSK_WS (GDG_OSK_FZ + 2 * GDG_OSK_MAX_UNITS)                /* scan warp totals */
 #define GDG_OSK_DESC (GDG_OSK_WS + 2 * (GDG_OSK_NT / 32))              /* nslots + GDG_OSK_MAX_UNITS unit descriptors */
@@ -104,7 +106,93 @@ GDG_DEVI void fir_branch_rolled(const double *zb, int p, double (&acc)[8])
     }
 }
 
-/* one unit of the run on one tile: xin = [8 history | Tt samples] -> xout (same layout); logical index k of a signal buffer lives at pz(k) */
+/* fuzz.go:52-105 on a tile of the oversampled signal, for this kernel's thread shape: a thread owns the TWO base samples
+ * 2 tid and 2 tid + 1 (F oversampled samples each) and walks them as two INDEPENDENT recurrence chains (the second one
+ * starts from the first one's chunk map applied to the carry) - twice the instruction-level parallelism of one chain of 2F
+ * samples in the latency-bound follower / coupling-capacitor replays; all loads of z are issued before the chains start.
+ * Same scans, same update formulas as fuzz_run. */
+template <int MODE> GDG_DEVI double follow_step_t(double env, double abs_s, double d_inv, double d)
+{
+    if (MODE == GDG_FOLLOW_ENVELOPE) { env *= d_inv; if (abs_s > env) env = abs_s; return env; }
+    if (MODE == GDG_FOLLOW_LEVEL) { const double diff = abs_s - env; return env + diff * d; }
+    return 1.0;
+}
+template <int F, int NT, int ZPS, int MODE>
+GDG_DEV void fuzz_run_pair(const gdg_unit_desc &d, double *z, int nbase, double *st, double *ws)
+{
+    constexpr int MP = MODE == GDG_FOLLOW_ENVELOPE;
+    const double gain = d.p[0], lvl = d.p[1], bias = d.p[2], ff = d.p[3], ffi = d.p[4], dinv = d.p[5], dd = d.p[6];
+    const double astep = follow_A(MODE, dinv, dd), aF = pow_int(astep, F), cstep = 1.0 - dd, cF = pow_int(cstep, F);
+    const double inite[1] = {st[GDG_OS_ST_ENV]}, initc[1] = {st[GDG_OS_ST_CCV]};
+    (void)ws;
+    GDG_REGA(double, a, 1); GDG_REGA(double, b, 1); GDG_REGA(double, ein, 1); GDG_REGA(double, cin, 1);
+    GDG_REGA(double, ea, 2); GDG_REGA(double, eb, 2); GDG_REGA(double, ca, 2); GDG_REGA(double, cb, 2);
+    GDG_THREADS_BEGIN_N(NT)
+        const int j0 = 2 * tid;
+        double e[2] = {0.0, 0.0}, xv[2][F];
+#pragma unroll
+        for (int s = 0; s < 2; s++)
+#pragma unroll
+            for (int ph = 0; ph < F; ph++) xv[s][ph] = j0 + s < nbase ? z[zloc(F, j0 + s, ph, ZPS)] : 0.0;
+#pragma unroll
+        for (int ph = 0; ph < F; ph++)
+#pragma unroll
+            for (int s = 0; s < 2; s++) if (j0 + s < nbase) e[s] = follow_step_t<MODE>(e[s], fabs(xv[s][ph]), dinv, dd);
+#pragma unroll
+        for (int s = 0; s < 2; s++) { R(ea)[s] = j0 + s < nbase ? aF : 1.0; R(eb)[s] = j0 + s < nbase ? e[s] : 0.0; }
+        R(a)[0] = R(ea)[1] * R(ea)[0]; R(b)[0] = scan_apply(MP, R(ea)[1], R(eb)[0], R(eb)[1]);
+    GDG_THREADS_END_NOSYNC
+    GDG_SCAN_N(1, NT, ws, MP, a, b, inite, ein);
+    GDG_THREADS_BEGIN_N(NT)
+        const int j0 = 2 * tid;
+        double e[2], c[2] = {0.0, 0.0}, xv[2][F];
+        e[0] = R(ein)[0]; e[1] = scan_apply(MP, R(ea)[0], R(ein)[0], R(eb)[0]);
+#pragma unroll
+        for (int s = 0; s < 2; s++)
+#pragma unroll
+            for (int ph = 0; ph < F; ph++) xv[s][ph] = j0 + s < nbase ? z[zloc(F, j0 + s, ph, ZPS)] : 0.0;
+#pragma unroll
+        for (int ph = 0; ph < F; ph++)
+#pragma unroll
+            for (int s = 0; s < 2; s++) if (j0 + s < nbase) {
+                const double x = xv[s][ph];
+                e[s] = follow_step_t<MODE>(e[s], fabs(x), dinv, dd);
+                double pre = clamp1(gain * (x - (bias * e[s])));
+                pre = (ff * pre) + (ffi * x);
+                c[s] += (pre - c[s]) * dd;
+            }
+#pragma unroll
+        for (int s = 0; s < 2; s++) { R(ca)[s] = j0 + s < nbase ? cF : 1.0; R(cb)[s] = j0 + s < nbase ? c[s] : 0.0; }
+        R(a)[0] = R(ca)[1] * R(ca)[0]; R(b)[0] = (R(ca)[1] * R(cb)[0]) + R(cb)[1];
+    GDG_THREADS_END_NOSYNC
+    GDG_SCAN_N(1, NT, ws, 0, a, b, initc, cin);
+    GDG_THREADS_BEGIN_N(NT)
+        const int j0 = 2 * tid;
+        double e[2], c[2], xv[2][F];
+        e[0] = R(ein)[0]; e[1] = scan_apply(MP, R(ea)[0], R(ein)[0], R(eb)[0]);
+        c[0] = R(cin)[0]; c[1] = (R(ca)[0] * R(cin)[0]) + R(cb)[0];
+#pragma unroll
+        for (int s = 0; s < 2; s++)
+#pragma unroll
+            for (int ph = 0; ph < F; ph++) xv[s][ph] = j0 + s < nbase ? z[zloc(F, j0 + s, ph, ZPS)] : 0.0;
+#pragma unroll
+        for (int ph = 0; ph < F; ph++)
+#pragma unroll
+            for (int s = 0; s < 2; s++) if (j0 + s < nbase) {
+                const double x = xv[s][ph];
+                e[s] = follow_step_t<MODE>(e[s], fabs(x), dinv, dd);
+                double pre = clamp1(gain * (x - (bias * e[s])));
+                pre = (ff * pre) + (ffi * x);
+                const double diff = pre - c[s];
+                c[s] += diff * dd;
+                pre -= c[s];
+                z[zloc(F, j0 + s, ph, ZPS)] = lvl * clamp1(pre);
+            }
+        if (j0 < nbase && j0 + 2 >= nbase) { const bool l = j0 + 1 < nbase; st[GDG_OS_ST_ENV] = l ? e[1] : e[0]; st[GDG_OS_ST_CCV] = l ? c[1] : c[0]; }
+    GDG_THREADS_END
+}
+
+/* one unit of the run on one tile: xin = [8 history | Tt samples] -> xout (same layout); plain layout */
 template <int F, int TYPE>
 GDG_DEV void osk_unit_tile(const gdg_unit_desc &d, const double *xin, double *xout, double *stash, double *fz, int Tt, const double *next_hist)
 {
@@ -120,7 +208,7 @@ GDG_DEV void osk_unit_tile(const gdg_unit_desc &d, const double *xin, double *xo
         for (int jl = tid; jl < Tt; jl += NT) {
             double xs[6];
 #pragma unroll
-            for (int q = 0; q < 6; q++) xs[q] = xin[pz(jl + 2 + q)];             /* in[j - 6 + q] */
+            for (int q = 0; q < 6; q++) xs[q] = xin[jl + 2 + q];                /* in[j - 6 + q] */
             const int m0 = pz(GDG_ZH + jl), m1 = pz(GDG_ZH + jl + 1);
 #pragma unroll
             for (int ph = 0; ph < F; ph++) {
@@ -136,7 +224,13 @@ GDG_DEV void osk_unit_tile(const gdg_unit_desc &d, const double *xin, double *xo
             }
         }
     GDG_THREADS_END
-    if (TYPE == GDG_UNIT_FUZZ) fuzz_run<F, NT, ZPS>(d, z, Tt, fz, ws);
+    if (TYPE == GDG_UNIT_FUZZ) {
+        static_assert(GDG_OSK_TILE <= 2 * GDG_OSK_NT, "fuzz_run_pair: two base samples per thread");
+        const int mode = d.i[1];
+        if (mode == GDG_FOLLOW_ENVELOPE) fuzz_run_pair<F, NT, ZPS, GDG_FOLLOW_ENVELOPE>(d, z, Tt, fz, ws);
+        else if (mode == GDG_FOLLOW_LEVEL) fuzz_run_pair<F, NT, ZPS, GDG_FOLLOW_LEVEL>(d, z, Tt, fz, ws);
+        else fuzz_run_pair<F, NT, ZPS, GDG_FOLLOW_OTHER>(d, z, Tt, fz, ws);
+    }
     /* polyphase FIR branch sums (warp w: branch w % F), then stash the halo and the input history for the next tile */
     GDG_THREADS_BEGIN_N(NT)
         const int warp = tid >> 5, p = warp % F;
@@ -146,26 +240,27 @@ GDG_DEV void osk_unit_tile(const gdg_unit_desc &d, const double *xin, double *xo
             const double *zp = z + p * ZPS;
             if constexpr (F == 2) { if (p == 0) fir_branch<F, 0, RR>(zp, i0, acc); else fir_branch<F, 1, RR>(zp, i0, acc); }
             else fir_branch_rolled<F>(zp + pz(GDG_ZH + i0), p, acc);   /* RR == 8: i0 is a multiple of 8 */
-            double *dst = p == 0 ? xout + pz(8 + i0) : part + (p - 1) * GDG_OSK_PLEN + pz(i0);
+            double *dst = part + p * GDG_OSK_PLEN + pz(i0);
             if (RR == 8 && i0 + RR <= Tt) {
 #pragma unroll
                 for (int r = 0; r < RR; r++) dst[r] = acc[r];            /* 8 | i0: the 8 cells are contiguous */
             } else {
 #pragma unroll
-                for (int r = 0; r < RR; r++) if (i0 + r < Tt) { if (p == 0) xout[pz(8 + i0 + r)] = acc[r]; else part[(p - 1) * GDG_OSK_PLEN + pz(i0 + r)] = acc[r]; }
+                for (int r = 0; r < RR; r++) if (i0 + r < Tt) part[p * GDG_OSK_PLEN + pz(i0 + r)] = acc[r];
             }
         }
         if (tid < F * 64) { const int pp = tid >> 6, m = tid & 63; if (m <= GDG_ZH) stash[pp * (GDG_ZH + 1) + m] = z[pp * ZPS + pz(m + Tt)]; }
-        if (tid >= NT - 8) { const int k = tid - (NT - 8); stash[4 * (GDG_ZH + 1) + k] = xin[pz(Tt + k)]; }     /* last 8 of [history | tile] */
+        if (tid >= NT - 8) { const int k = tid - (NT - 8); stash[4 * (GDG_ZH + 1) + k] = xin[Tt + k]; }     /* last 8 of [history | tile] */
     GDG_THREADS_END
     /* combine in branch order, clamp, -0.5 dB (oversampling.go:150-177); the next unit's input history goes in front */
     GDG_THREADS_BEGIN_N(NT)
 #pragma unroll 1
         for (int i = tid; i < Tt; i += NT) {
-            double acc = xout[pz(8 + i)];
+            const int pi = pz(i);
+            double acc = part[pi];
 #pragma unroll
-            for (int p = 1; p < F; p++) acc += part[(p - 1) * GDG_OSK_PLEN + pz(i)];
-            xout[pz(8 + i)] = 0.9440608762859234 * clamp1(acc);
+            for (int p = 1; p < F; p++) acc += part[p * GDG_OSK_PLEN + pi];
+            xout[8 + i] = 0.9440608762859234 * clamp1(acc);
         }
         if (next_hist && tid < 8) xout[tid] = next_hist[tid];
     GDG_THREADS_END
@@ -222,7 +317,7 @@ GDG_DEV void run_os(double *smem, const gdg_chain_desc *cd, const void *in, int 
         const int Tt = imin(T, n - t0);
         GDG_THREADS_BEGIN_N(NT)
 #pragma unroll
-            for (int k = 0; k < T / NT; k++) { const int i = tid + k * NT; if (i < Tt) xa[pz(8 + i)] = R(nx)[k]; }
+            for (int k = 0; k < T / NT; k++) { const int i = tid + k * NT; if (i < Tt) xa[8 + i] = R(nx)[k]; }
             if (tid < 8) xa[tid] = stash[4 * (GDG_ZH + 1) + tid];
 #pragma unroll
             for (int k = 0; k < T / NT; k++) {
@@ -239,8 +334,8 @@ GDG_DEV void run_os(double *smem, const gdg_chain_desc *cd, const void *in, int 
             double *t = xin; xin = xout; xout = t;
         }
         GDG_THREADS_BEGIN_N(NT)                                   /* xin holds the run's output tile now */
-            if (out_fmt == GDG_FMT_IEEE64) { for (int i = tid; i < Tt; i += NT) ((double *)out)[t0 + i] = xin[pz(8 + i)]; }
-            else { for (int i = tid; i < Tt; i += NT) encode_sample(out_fmt, (unsigned char *)out, t0 + i, xin[pz(8 + i)]); }
+            if (out_fmt == GDG_FMT_IEEE64) { for (int i = tid; i < Tt; i += NT) ((double *)out)[t0 + i] = xin[8 + i]; }
+            else { for (int i = tid; i < Tt; i += NT) encode_sample(out_fmt, (unsigned char *)out, t0 + i, xin[8 + i]); }
         GDG_THREADS_END
     }
     /* carried state back to the units' state words */
