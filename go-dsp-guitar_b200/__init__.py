@@ -129,6 +129,16 @@ ABI = {
     "gdg_controller_wait": (_int, [_int]),
     "gdg_controller_submit_encoded": (_int, [_vp, _u32, _vp, _int, _vp, _vp, _vp, _int, _vp, _int, _u32, _sz, _u32]),
     "gdg_chain_filter_coefficients": (C.c_long, [_vp, _int, _vp, _sz]),
+    "gdg_device_count": (_int, []),
+    "gdg_use_device": (_int, [_int]),
+    "gdg_current_device": (_int, []),
+    "gdg_cluster_create": (_vp, [_vp, _int]),
+    "gdg_cluster_destroy": (None, [_vp]),
+    "gdg_cluster_size": (_int, [_vp]),
+    "gdg_cluster_select": (_int, [_vp, _int]),
+    "gdg_cluster_submit": (_int, [_vp, _vp, _u32, _vp, _int, _vp, _vp, _vp, _u32, _sz, _u32]),
+    "gdg_cluster_wait": (_int, [_vp, _int]),
+    "gdg_cluster_process": (_int, [_vp, _vp, _u32, _vp, _int, _vp, _vp, _vp, _u32, _sz, _u32]),
     "gdg_tuner_analyze_batch": (_int, [_vp, _u32, _vp]),
     "gdg_controller_process_aux": (_int, [_vp, _u32, _vp, _int, _vp, _vp, _vp, _vp, _int, _vp, _u32, _sz, _u32]),
     "gdg_controller_submit_aux": (_int, [_vp, _u32, _vp, _int, _vp, _vp, _vp, _vp, _int, _vp, _u32, _sz, _u32]),
@@ -136,6 +146,17 @@ ABI = {
 }
 
 _LIBS = {}
+
+
+def device_count(lib=None):
+    return (lib if lib is not None else load()).gdg_device_count()
+
+
+def use_device(device, lib=None):
+    """objects created afterwards on this thread live on `device` (gdg_use_device)"""
+    lib = lib if lib is not None else load()
+    if lib.gdg_use_device(device) < 0:
+        raise GdgError(lib.gdg_last_error().decode())
 
 
 def load(path=None, _test_backend=False):
@@ -584,3 +605,34 @@ def controller_wait(ticket, lib=None):
     lib = lib if lib is not None else load()
     if lib.gdg_controller_wait(ticket) < 0:
         raise GdgError(lib.gdg_last_error().decode())
+
+
+class Cluster(_Base):
+    """gdg_cluster: several GPUs driven by ONE process (controller.go:3339-3341 is one process with a worker per channel).
+    Create the members' objects after select(member); process() = controller.process over all members."""
+
+    def __init__(self, devices, lib=None):
+        super().__init__(lib)
+        arr = (C.c_int * len(devices))(*devices)
+        self._h = self._lib.gdg_cluster_create(arr, len(devices))
+        if not self._h:
+            raise self._err()
+        self.devices = list(devices)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._lib.gdg_cluster_destroy(self._h)
+
+    def select(self, member):
+        self._check(self._lib.gdg_cluster_select(self._h, member))
+
+    def process(self, chains, tuner, tuner_channel, spats, inputs, sample_rate):
+        x = _f64(inputs)
+        c, n = x.shape
+        n_out = c + (2 if spats else 0)
+        out = np.zeros((n_out, n))
+        ip = (C.c_void_p * c)(*[x[i].ctypes.data for i in range(c)])
+        op = (C.c_void_p * n_out)(*[out[i].ctypes.data for i in range(n_out)])
+        sp = _handles(spats) if spats else None
+        self._check(self._lib.gdg_cluster_process(self._h, _handles(chains), c, tuner._h if tuner else None, tuner_channel, sp, ip, op, n_out, n, sample_rate))
+        return out

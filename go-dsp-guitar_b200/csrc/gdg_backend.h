@@ -15,7 +15,20 @@
 /* all calls return 0 on success; on failure the message is in gdgb_error() */
 const char *gdgb_error(void);
 const char *gdgb_name(void);                    /* "cuda:sm_100a" or "host-emulation (tests only)" */
-int gdgb_init(int device);                      /* selects the device, uploads constant tables */
+int gdgb_init(int device);                      /* context 0: selects the device, uploads constant tables */
+/* further devices of ONE process (the reference host is one process with a goroutine per channel, controller.go:3339-3341):
+ * a context = device + streams + events + tables; every call works on the context the calling thread selected last */
+#define GDGB_MAX_CONTEXTS 16
+int gdgb_device_count(void);
+int gdgb_context_open(int device);              /* -> context index (existing one if already open) or -1 */
+int gdgb_context_count(void);
+int gdgb_context_device(int ctx);
+int gdgb_current(void);
+int gdgb_select(int ctx);
+int gdgb_enable_peers(int ctx);                 /* peer (NVLink) access from ctx to every other open context */
+int gdgb_wait_other(int ctx, int other, int event);   /* stream 0 of ctx waits for an event recorded on context `other` */
+/* out[r][j] = sum_d parts[d][r * strides[d] + j] (+ aux): the partial stereo masters of the other devices are read through peer addresses */
+int gdgb_master_sum(const double *const *d_parts, const long *strides, int count, const double *d_aux, double *d_outL, double *d_outR, int n, void *stream);
 int gdgb_device(void);
 int gdgb_sm_count(void);
 void *gdgb_stream(void);                        /* the library's stream (cudaStream_t) */

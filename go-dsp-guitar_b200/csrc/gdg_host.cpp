@@ -54,6 +54,15 @@ std::shared_mutex g_edit_mutex;
 typedef std::unique_lock<std::shared_mutex> EditLock;
 typedef std::shared_lock<std::shared_mutex> ProcessLock;
 
+/* One process may drive several GPUs (gdg_use_device / gdg_cluster_*): every object lives on the device context that was
+ * selected on the creating thread and every entry point works under its object's context. */
+struct Use {
+    int prev;
+    explicit Use(int ctx) : prev(gdgb_current()) { if (ctx >= 0 && ctx != prev) gdgb_select(ctx); }
+    ~Use() { if (gdgb_current() != prev) gdgb_select(prev); }
+    Use(const Use &) = delete;
+};
+
 std::once_flag g_init_once;
 int g_init_status = -1;
 std::string g_init_error;
@@ -122,6 +131,7 @@ struct DevFilter {
 } // namespace
 
 struct gdg_irbank {
+    int ctx = -1;                                          /* device context of the responses (set by the first add) */
     std::vector<ImpulseResponse> responses;
     uint64_t generation = 0;                               /* bumped by every add: compiled-filter cache key */
     std::vector<std::string> names() const                 /* filter.go:681-699 */
@@ -587,6 +597,7 @@ struct Slot { std::unique_ptr<Unit> unit; bool bypass; };
 enum { SEG_CHAIN = 0, SEG_OS = 1, SEG_KINDS = 2 };
 #define GDG_OSK_MAX_UNITS_HOST 6                /* == GDG_OSK_MAX_UNITS (gdg_os.cuh) */
 struct gdg_chain {
+    int ctx = 0;                                           /* device context the chain (descriptors, unit state) lives on */
     gdg_irbank *bank;
     std::vector<Slot> slots;
     /* device descriptors: one per segment */
@@ -670,7 +681,8 @@ struct Batch {
 };
 namespace {
 std::mutex g_batch_mutex;
-std::unique_ptr<Batch> g_batch;
+std::unique_ptr<Batch> g_batch_of[GDGB_MAX_CONTEXTS];       /* the batch cache of each device context */
+#define g_batch (g_batch_of[gdgb_current()])
 } // namespace
 gdg_chain::~gdg_chain() { for (auto p : d_desc) gdgb_free(p); if (d_in) gdgb_free(d_in); if (d_out) gdgb_free(d_out); delete self; }
 namespace {
@@ -871,6 +883,7 @@ int host_block(gdg_chain *const *chains, size_t C, gdg_tuner *tuner, int tuner_c
 
 /* ---- spatializer -------------------------------------------------------------- */
 struct gdg_spatializer {
+    int ctx = 0;
     uint32_t count; uint32_t sample_rate = 96000;         /* never updated: spatializer.go:418-431 does not store the rate */
     struct Pos { double az = 0, dist = 0, level = 1.0; };
     std::vector<Pos> pos;
@@ -924,6 +937,7 @@ struct gdg_spatializer {
 
 /* ---- tuner ---------------------------------------------------------------------- */
 struct gdg_tuner {
+    int ctx = 0;
     static const int N = 96000;                           /* tuner.go:16 NUM_SAMPLES */
     double *d_ring = nullptr, *d_work = nullptr, *d_block = nullptr; size_t block_cap = 0;
     int pos = 0; uint32_t rate = 0;
@@ -933,6 +947,7 @@ struct gdg_tuner {
 
 /* ---- level meter ---------------------------------------------------------------- */
 struct gdg_meter {
+    int ctx = 0;
     std::vector<std::string> names;
     uint32_t count = 0;
     bool enabled = false;                                 /* level.go:383-386: created disabled */
@@ -963,8 +978,10 @@ int meter_rows(gdg_meter *m, uint32_t first, const double *d_rows, size_t stride
  * Event ids: slot*28 + {0..7 uploads, 8..15 kernels, 16 spatializer, 17 all downloads, 18 metronome upload}. */
 int block_submit(int si, gdg_chain *const *chains, size_t C, gdg_tuner *tuner, int tuner_channel, gdg_spatializer *spat, gdg_meter *meter,
                  const void *const *in, int in_fmt, void *const *out, int out_fmt, size_t n_out_rows, size_t n, uint32_t rate,
-                 const double *metronome = nullptr, bool metro_master = false)
+                 const double *metronome = nullptr, bool metro_master = false, const double **partial_master = nullptr)
 {
+    /* partial_master != NULL (multi-device blocks): the spatializer's [2][n] result stays on the device (row stride n) and its
+     * address is returned; event slot*28 + 16 marks it ready for the device that sums the partial masters */
     const int rounds = prepare_batch(chains, C, rate, n, gdgb_stream());
     if (rounds < 0) return -1;
     Batch::Slot &b = g_batch->slot[si];
@@ -1025,10 +1042,14 @@ int block_submit(int si, gdg_chain *const *chains, size_t C, gdg_tuner *tuner, i
         if (meter && meter_rows(meter, (uint32_t)(2 * C + 1), b.d_out + C * n, n, 2, n, rate, s0)) return -1;    /* controller.go:2768-2770: master */
         if (recode && gdgb_convert_rows(b.d_out + C * n, (long)(n * sizeof(double)), GDG_FMT_IEEE64, (char *)b.d_enc_out + C * ob, (long)ob, out_fmt, 2, (int)n, s0))
             return backend_fail("payload encode failed");
-        if (gdgb_record(ev + 16, 0) || gdgb_wait(2, ev + 16)) return backend_fail("event failed");
-        const int r = download_rows(b, out, C, 2, ob, down_src, 2);
-        if (r < 0) return -1;
-        if (r == 1) b.staged.push_back({C, 2});
+        if (gdgb_record(ev + 16, 0)) return backend_fail("event failed");
+        if (partial_master) *partial_master = b.d_out + C * n;
+        else {
+            if (gdgb_wait(2, ev + 16)) return backend_fail("event failed");
+            const int r = download_rows(b, out, C, 2, ob, down_src, 2);
+            if (r < 0) return -1;
+            if (r == 1) b.staged.push_back({C, 2});
+        }
     }
     if (gdgb_record(ev + 17, 2)) return backend_fail("event record failed");
     b.busy = true;
@@ -1109,12 +1130,14 @@ int gdg_init(int device)
 
 /* ---- impulse responses ---- */
 gdg_irbank *gdg_irbank_create(void) { return new gdg_irbank(); }
-void gdg_irbank_destroy(gdg_irbank *b) { delete b; }
+void gdg_irbank_destroy(gdg_irbank *b) { if (!b) return; Use use_ctx_(b->ctx); delete b; }
 int gdg_irbank_add(gdg_irbank *b, const char *name, int32_t comp_db, const double *s, size_t n, uint32_t src_rate)
 {
     if (ensure_init()) return -1;
     if (!b || !name || (!s && n)) return fail("gdg_irbank_add: bad argument");
     if (src_rate == 0) return fail("gdg_irbank_add: source rate must not be zero");
+    if (b->ctx < 0) b->ctx = gdgb_current();
+    Use use_ctx_(b->ctx);
     const double fac = std::pow(10.0, 0.05 * (double)comp_db);      /* filter.go:742-745 */
     /* filter.Import's resample.Time to the seven supported rates (filter.go:766-780) runs on the device; the responses stay there */
     double *d_src = (double *)gdgb_alloc(std::max<size_t>(1, n) * sizeof(double));
@@ -1134,6 +1157,8 @@ int gdg_irbank_add_raw(gdg_irbank *b, const char *name, int32_t comp_db, const d
 {
     if (ensure_init()) return -1;
     if (!b || !name || (!s && n)) return fail("gdg_irbank_add_raw: bad argument");
+    if (b->ctx < 0) b->ctx = gdgb_current();
+    Use use_ctx_(b->ctx);
     double *d = (double *)gdgb_alloc(std::max<size_t>(1, n) * sizeof(double));
     if (!d || (n && gdgb_upload(d, s, n * sizeof(double)))) { gdgb_free(d); return backend_fail("impulse response upload failed"); }
     gdgb_sync();
@@ -1289,20 +1314,24 @@ gdg_chain *gdg_chain_create(gdg_irbank *bank)
     if (ensure_init()) return nullptr;
     gdg_chain *c = new gdg_chain();
     c->bank = bank;
+    c->ctx = (bank && bank->ctx >= 0) ? bank->ctx : gdgb_current();      /* a chain lives with its impulse responses */
     return c;
 }
 void gdg_chain_destroy(gdg_chain *c)
 {
+    if (!c) return;
+    Use use_ctx_(c->ctx);
     EditLock el(g_edit_mutex);
     std::lock_guard<std::mutex> lk(g_batch_mutex);
     if (g_batch && std::find(g_batch->chains.begin(), g_batch->chains.end(), c) != g_batch->chains.end()) g_batch.reset();
     delete c;
 }
-#define CHAIN_CHECK(c) if (!(c)) return fail("chain is NULL")
+#define CHAIN_CHECK(c) if (!(c)) return fail("chain is NULL"); Use use_ctx_((c)->ctx)
 int gdg_chain_append_unit(gdg_chain *c, int type)
 {
     EditLock lk(g_edit_mutex);
     if (!c) { fail("chain is NULL"); return -1; }
+    Use use_ctx_(c->ctx);
     Unit *u = create_unit(type, c->bank);
     if (!u) { fail("%s", "Failed to create effects unit."); return -1; }
     c->slots.push_back(Slot{std::unique_ptr<Unit>(u), true});          /* starts bypassed: signal.go:74 */
@@ -1338,6 +1367,7 @@ int gdg_chain_unit_type(gdg_chain *c, int id)
 {
     ProcessLock lk(g_edit_mutex);
     if (!c) { fail("chain is NULL"); return -1; }
+    Use use_ctx_(c->ctx);
     if (id < 0 || id >= (int)c->slots.size()) { fail("Cannot get unit type: No unit %d.", id); return -1; }
     return c->slots[id].unit->type;
 }
@@ -1419,6 +1449,7 @@ int gdg_chain_parameter_count(gdg_chain *c, int id)
 {
     ProcessLock lk(g_edit_mutex);
     if (!c) { fail("chain is NULL"); return -1; }
+    Use use_ctx_(c->ctx);
     if (id < 0 || id >= (int)c->slots.size()) { fail("Cannot get parameters: No unit %d.", id); return -1; }
     return (int)c->slots[id].unit->params.size();
 }
@@ -1449,6 +1480,7 @@ long gdg_chain_filter_coefficients(gdg_chain *c, int id, double *out, size_t cap
 {
     if (ensure_init()) return -1;
     if (!c) { fail("chain is NULL"); return -1; }
+    Use use_ctx_(c->ctx);
     ProcessLock lk(g_edit_mutex);
     if (id < 0 || id >= (int)c->slots.size()) { fail("Cannot get filter coefficients: No unit %d.", id); return -1; }
     Unit *u = c->slots[id].unit.get();
@@ -1465,6 +1497,8 @@ int gdg_process_batch_device(gdg_chain *const *chains, size_t C, const double *d
     if (ensure_init()) return -1;
     if (!chains || !C || !d_in || !d_out) return fail("gdg_process_batch_device: bad argument");
     if (stride < n) return fail("gdg_process_batch_device: stride < n");
+    for (size_t c_ = 1; c_ < (size_t)C; c_++) if (chains[c_] && chains[c_]->ctx != chains[0]->ctx) return fail("the chains of one call must live on one device (use gdg_cluster_* to span devices)");
+    Use use_ctx_(chains[0]->ctx);
     return run_batch_device(chains, C, d_in, d_out, stride, n, rate, stream ? stream : gdgb_stream());
 }
 
@@ -1473,6 +1507,8 @@ int gdg_process_batch(gdg_chain *const *chains, size_t C, const double *const *i
     if (ensure_init()) return -1;
     if (!chains || !C || !in || !out) return fail("gdg_process_batch: bad argument");
     if (check_block(n)) return -1;
+    for (size_t c_ = 1; c_ < (size_t)C; c_++) if (chains[c_] && chains[c_]->ctx != chains[0]->ctx) return fail("the chains of one call must live on one device (use gdg_cluster_* to span devices)");
+    Use use_ctx_(chains[0]->ctx);
     return host_block(chains, C, nullptr, -1, nullptr, nullptr, (const void *const *)in, GDG_FMT_IEEE64, (void *const *)out, GDG_FMT_IEEE64, C, n, rate);
 }
 
@@ -1505,12 +1541,13 @@ gdg_spatializer *gdg_spatializer_create(uint32_t n)
 {
     if (ensure_init()) return nullptr;
     gdg_spatializer *s = new gdg_spatializer();
+    s->ctx = gdgb_current();
     s->count = n; s->pos.resize(n);
     if (s->alloc_hist(96000)) { delete s; return nullptr; }
     return s;
 }
-void gdg_spatializer_destroy(gdg_spatializer *s) { delete s; }
-#define SPAT_CH(s, ch, what) if (!(s)) return fail("spatializer is NULL"); \
+void gdg_spatializer_destroy(gdg_spatializer *s) { if (!s) return; Use use_ctx_(s->ctx); gdgb_sync(); delete s; }
+#define SPAT_CH(s, ch, what) if (!(s)) return fail("spatializer is NULL"); Use use_ctx_((s)->ctx); \
     if ((ch) >= (s)->count) return fail("Cannot " what " for channel %d: Only %d channels exist.", (int)(ch), (int)(s)->count)
 int gdg_spatializer_set_azimuth(gdg_spatializer *s, uint32_t ch, double v) { SPAT_CH(s, ch, "set azimuth"); s->pos[ch].az = v; s->dirty = true; return 0; }
 int gdg_spatializer_get_azimuth(gdg_spatializer *s, uint32_t ch, double *v) { SPAT_CH(s, ch, "get azimuth"); *v = s->pos[ch].az; return 0; }
@@ -1533,6 +1570,7 @@ uint32_t gdg_spatializer_output_count(gdg_spatializer *) { return 2; }
 int gdg_spatializer_set_sample_rate(gdg_spatializer *s, uint32_t rate)
 {
     if (!s) return fail("spatializer is NULL");
+    Use use_ctx_(s->ctx);
     gdgb_sync();
     return s->alloc_hist(rate);
 }
@@ -1541,6 +1579,7 @@ int gdg_spatializer_process_device(gdg_spatializer *s, const double *d_in, size_
 {
     if (ensure_init()) return -1;
     if (!s || !d_in || !d_out) return fail("gdg_spatializer_process_device: bad argument");
+    Use use_ctx_(s->ctx);
     if (n == 0 || n > (size_t)1 << 24) return fail("gdg_spatializer_process_device: bad block length");
     if (s->dirty) { if (s->upload_channels()) return -1; if (stream && stream != gdgb_stream() && gdgb_sync()) return backend_fail("synchronize failed"); }
     if (s->count > 32 && s->part_n < n) {
@@ -1561,6 +1600,7 @@ int gdg_spatializer_process(gdg_spatializer *s, const double *const *in, uint32_
 {
     if (ensure_init()) return -1;
     if (!s || !in || !out) return fail("gdg_spatializer_process: bad argument");
+    Use use_ctx_(s->ctx);
     if (n_in != s->count || n_out != 2) return 0;           /* silent no-op like spatializer.go:149 */
     if (s->cap_n < n) {
         gdgb_free(s->d_in); gdgb_free(s->d_out); gdgb_free(s->d_aux);
@@ -1581,17 +1621,19 @@ gdg_tuner *gdg_tuner_create(void)
 {
     if (ensure_init()) return nullptr;
     gdg_tuner *t = new gdg_tuner();
+    t->ctx = gdgb_current();
     t->d_ring = (double *)gdgb_alloc(gdg_tuner::N * sizeof(double));
     t->d_work = (double *)gdgb_alloc(2 * 262144 * sizeof(double));
     if (!t->d_ring || !t->d_work) { backend_fail("tuner allocation failed"); delete t; return nullptr; }
     return t;
 }
-void gdg_tuner_destroy(gdg_tuner *t) { delete t; }
+void gdg_tuner_destroy(gdg_tuner *t) { if (!t) return; Use use_ctx_(t->ctx); gdgb_sync(); delete t; }
 /* circular.Enqueue (circular/circular.go:33-71) on the device ring */
 int gdg_tuner_process_device(gdg_tuner *t, const double *d, size_t n, uint32_t rate, void *stream)
 {
     if (ensure_init()) return -1;
     if (!t || (!d && n)) return fail("gdg_tuner_process_device: bad argument");
+    Use use_ctx_(t->ctx);
     const size_t N = gdg_tuner::N;
     void *st = stream ? stream : gdgb_stream();
     int rc = 0;
@@ -1613,6 +1655,7 @@ int gdg_tuner_process(gdg_tuner *t, const double *s, size_t n, uint32_t rate)
 {
     if (ensure_init()) return -1;
     if (!t || (!s && n)) return fail("gdg_tuner_process: bad argument");
+    Use use_ctx_(t->ctx);
     const size_t N = gdg_tuner::N;
     if (n > N) { s += n - N; n = N; }                       /* only the tail can survive the enqueue */
     if (t->block_cap < n) { gdgb_free(t->d_block); t->d_block = (double *)gdgb_alloc(std::max<size_t>(1, n) * sizeof(double)); t->block_cap = n; if (!t->d_block) return backend_fail("tuner staging allocation failed"); }
@@ -1663,8 +1706,10 @@ int gdg_tuner_analyze_batch(gdg_tuner *const *tuners, uint32_t count, gdg_tuner_
     std::vector<const double *> rings(count); std::vector<double *> works(count); std::vector<int> pos(count);
     for (uint32_t i = 0; i < count; i++) {
         if (!tuners[i]) return fail("gdg_tuner_analyze_batch: tuner %u is NULL", i);
+        if (tuners[i]->ctx != tuners[0]->ctx) return fail("gdg_tuner_analyze_batch: the tuners of one batch must live on one device");
         rings[i] = tuners[i]->d_ring; works[i] = tuners[i]->d_work; pos[i] = tuners[i]->pos;
     }
+    Use use_ctx_(count ? tuners[0]->ctx : gdgb_current());
     const int fft_size = (int)next_pow2(2 * (uint64_t)gdg_tuner::N);
     if (count && gdgb_autocorrelate_batch(rings.data(), gdg_tuner::N, pos.data(), works.data(), (int)count, fft_size, gdgb_stream()))
         return backend_fail("autocorrelation failed");
@@ -1686,6 +1731,8 @@ int gdg_process_batch_encoded(gdg_chain *const *chains, size_t C, const void *co
     if (!chains || !C || !in || !out) return fail("gdg_process_batch_encoded: bad argument");
     if (!fmt_bytes(in_format) || !fmt_bytes(out_format)) return fail("Unknown sample format: %#04x", fmt_bytes(in_format) ? out_format : in_format);
     if (check_block(n)) return -1;
+    for (size_t c_ = 1; c_ < (size_t)C; c_++) if (chains[c_] && chains[c_]->ctx != chains[0]->ctx) return fail("the chains of one call must live on one device (use gdg_cluster_* to span devices)");
+    Use use_ctx_(chains[0]->ctx);
     return host_block(chains, C, nullptr, -1, nullptr, nullptr, in, in_format, out, out_format, C, n, rate);
 }
 /* the same without waiting: ticket for gdg_controller_wait (two blocks in flight, like gdg_controller_submit) */
@@ -1696,6 +1743,8 @@ int gdg_process_batch_encoded_submit(gdg_chain *const *chains, size_t C, const v
     if (!chains || !C || !in || !out) return fail("gdg_process_batch_encoded_submit: bad argument");
     if (!fmt_bytes(in_format) || !fmt_bytes(out_format)) return fail("Unknown sample format: %#04x", fmt_bytes(in_format) ? out_format : in_format);
     if (check_block(n)) return -1;
+    for (size_t c_ = 1; c_ < (size_t)C; c_++) if (chains[c_] && chains[c_]->ctx != chains[0]->ctx) return fail("the chains of one call must live on one device (use gdg_cluster_* to span devices)");
+    Use use_ctx_(chains[0]->ctx);
     ProcessLock el(g_edit_mutex);
     std::lock_guard<std::mutex> lk(g_batch_mutex);
     const int si = free_slot();
@@ -1714,6 +1763,8 @@ int gdg_process_batch_device_encoded(gdg_chain *const *chains, size_t C, const v
     if (!fmt_bytes(in_format) || !fmt_bytes(out_format)) return fail("Unknown sample format: %#04x", fmt_bytes(in_format) ? out_format : in_format);
     if (in_stride_bytes < n * fmt_bytes(in_format) || out_stride_bytes < n * fmt_bytes(out_format)) return fail("gdg_process_batch_device_encoded: stride too small");
     if (check_block(n)) return -1;
+    for (size_t c_ = 1; c_ < (size_t)C; c_++) if (chains[c_] && chains[c_]->ctx != chains[0]->ctx) return fail("the chains of one call must live on one device (use gdg_cluster_* to span devices)");
+    Use use_ctx_(chains[0]->ctx);
     ProcessLock el(g_edit_mutex);
     std::lock_guard<std::mutex> lk(g_batch_mutex);
     void *st = stream ? stream : gdgb_stream();
@@ -1744,13 +1795,14 @@ gdg_meter *gdg_meter_create(uint32_t channels, const char *const *names)
 {
     if (ensure_init()) return nullptr;
     gdg_meter *m = new gdg_meter();
+    m->ctx = gdgb_current();
     m->count = channels;
     for (uint32_t c = 0; c < channels; c++) m->names.push_back(names && names[c] ? names[c] : "");
     m->d_state = (double *)gdgb_alloc(std::max<size_t>(1, channels) * 4 * sizeof(double));
     if (!m->d_state) { backend_fail("level meter allocation failed"); delete m; return nullptr; }
     return m;
 }
-void gdg_meter_destroy(gdg_meter *m) { delete m; }
+void gdg_meter_destroy(gdg_meter *m) { if (!m) return; Use use_ctx_(m->ctx); gdgb_sync(); delete m; }
 uint32_t gdg_meter_channel_count(gdg_meter *m) { return m ? m->count : 0; }
 const char *gdg_meter_channel_name(gdg_meter *m, uint32_t channel)
 {
@@ -1763,6 +1815,7 @@ int gdg_meter_set_enabled(gdg_meter *m, int value)
 {
     if (ensure_init()) return -1;
     if (!m) return fail("gdg_meter_set_enabled: bad argument");
+    Use use_ctx_(m->ctx);
     const bool v = value != 0;
     if (v != m->enabled) {
         if (!v && gdgb_zero(m->d_state, std::max<size_t>(1, m->count) * 4 * sizeof(double))) return backend_fail("level meter reset failed");   /* level.go:226-230 */
@@ -1775,6 +1828,7 @@ int gdg_meter_process_device(gdg_meter *m, uint32_t first_channel, const double 
 {
     if (ensure_init()) return -1;
     if (!m || (!d_rows && rows && n) || !rate) return fail("gdg_meter_process_device: bad argument");
+    Use use_ctx_(m->ctx);
     if ((uint64_t)first_channel + rows > m->count) return fail("gdg_meter_process_device: channels %u..%u exceed the meter's %u channels", first_channel, first_channel + rows, m->count);
     return meter_rows(m, first_channel, d_rows, stride, rows, n, rate, stream);
 }
@@ -1782,6 +1836,7 @@ int gdg_meter_process(gdg_meter *m, const double *const *bufs, uint32_t nbufs, s
 {
     if (ensure_init()) return -1;
     if (!m || (!bufs && nbufs)) return fail("gdg_meter_process: bad argument");
+    Use use_ctx_(m->ctx);
     if (nbufs != m->count) return fail("Number of input buffers (%u) does not match number of channels (%u) for this level meter.", nbufs, m->count);   /* level.go:311-312 */
     if (!m->enabled || !n || !nbufs) return 0;
     if (!rate) return fail("gdg_meter_process: bad sample rate");
@@ -1802,6 +1857,7 @@ int gdg_meter_state(gdg_meter *m, uint32_t channel, double *cur, double *peak, u
 {
     if (ensure_init()) return -1;
     if (!m) return fail("gdg_meter_state: bad argument");
+    Use use_ctx_(m->ctx);
     if (channel >= m->count) return fail("Requested analysis for channel %u, but level meter only has %u channels.", channel, m->count);
     double w[4];
     if (gdgb_sync_stream(0) || gdgb_download(w, m->d_state + 4 * (size_t)channel, sizeof(w))) return backend_fail("download failed");
@@ -1833,6 +1889,8 @@ int controller_block(const char *who, gdg_chain *const *chains, uint32_t C, gdg_
     if (!chains || !C || !in || !out) return fail("%s: bad argument", who);
     if (!fmt_bytes(in_fmt) || !fmt_bytes(out_fmt)) return fail("Unknown sample format: %#04x", fmt_bytes(in_fmt) ? out_fmt : in_fmt);
     if (check_block(n)) return -1;
+    for (size_t c_ = 1; c_ < (size_t)C; c_++) if (chains[c_] && chains[c_]->ctx != chains[0]->ctx) return fail("the chains of one call must live on one device (use gdg_cluster_* to span devices)");
+    Use use_ctx_(chains[0]->ctx);
     if (meter && meter->count != 2 * C + 3)
         return fail("%s: the level meter has %u channels, %u inputs need %u (inputs, outputs, metronome, master L/R: controller.go:2710-2771)", who, meter->count, C, 2 * C + 3);
     if (n_out < C) {
@@ -1909,6 +1967,154 @@ int gdg_controller_process(gdg_chain *const *chains, uint32_t C, gdg_tuner *tune
                            const double *const *in, double *const *out, uint32_t n_out, size_t n, uint32_t rate)
 {
     return gdg_controller_process_metered(chains, C, tuner, tuner_channel, spat, nullptr, in, out, n_out, n, rate);
+}
+
+
+/* ---- several GPUs in ONE process (controller.go:3339-3341: the reference host is one process, one worker per channel) ---- */
+int gdg_device_count(void) { return gdgb_device_count(); }
+int gdg_use_device(int device)
+{
+    if (ensure_init()) return -1;
+    const int ctx = gdgb_context_open(device);
+    if (ctx < 0) return backend_fail("gdg_use_device");
+    if (gdgb_select(ctx)) return backend_fail("gdg_use_device");
+    return ctx;
+}
+int gdg_current_device(void) { if (ensure_init()) return -1; return gdgb_context_device(gdgb_current()); }
+} /* extern "C" */
+
+struct gdg_cluster {
+    std::vector<int> ctx;                                   /* member -> device context */
+    double *d_master = nullptr; size_t cap_n = 0;           /* on member 0: the summed [2][n] master */
+    double *h_master = nullptr;                             /* pinned staging of the master rows */
+    struct Flight { bool busy = false; std::vector<int> members; double *out_l = nullptr, *out_r = nullptr; size_t n = 0; bool master = false; } flight[2];
+    ~gdg_cluster() { if (!ctx.empty()) { Use u(ctx[0]); gdgb_sync(); gdgb_free(d_master); } gdgb_pinned_free(h_master); }
+};
+
+extern "C" {
+gdg_cluster *gdg_cluster_create(const int *devices, int n_devices)
+{
+    if (ensure_init()) return nullptr;
+    if (!devices || n_devices < 1 || n_devices > GDGB_MAX_CONTEXTS) { fail("gdg_cluster_create: bad argument"); return nullptr; }
+    std::unique_ptr<gdg_cluster> cl(new gdg_cluster());
+    for (int i = 0; i < n_devices; i++) {
+        const int c = gdgb_context_open(devices[i]);
+        if (c < 0) { backend_fail("gdg_cluster_create"); return nullptr; }
+        if (std::find(cl->ctx.begin(), cl->ctx.end(), c) != cl->ctx.end()) { fail("gdg_cluster_create: device %d listed twice", devices[i]); return nullptr; }
+        cl->ctx.push_back(c);
+    }
+    if (n_devices > 1 && gdgb_enable_peers(cl->ctx[0])) { backend_fail("gdg_cluster_create"); return nullptr; }   /* member 0 reads the others' partial masters */
+    return cl.release();
+}
+void gdg_cluster_destroy(gdg_cluster *cl) { delete cl; }
+int gdg_cluster_size(gdg_cluster *cl) { return cl ? (int)cl->ctx.size() : 0; }
+/* objects created after this call live on member `member`'s device */
+int gdg_cluster_select(gdg_cluster *cl, int member)
+{
+    if (!cl || member < 0 || member >= (int)cl->ctx.size()) return fail("gdg_cluster_select: no member %d", member);
+    return gdgb_select(cl->ctx[member]) ? backend_fail("gdg_cluster_select") : 0;
+}
+/* One block of controller.process (controller.go:2648-2783) over the cluster: chains[c] live on the members' devices in
+ * member order (contiguous channel ranges); spats[m] is member m's spatializer over ITS channels (or spats ==
+ * NULL: no master).  Each member runs tuner feed -> chains -> spatializer on its own streams; member 0 then sums the partial
+ * stereo masters with one kernel that reads the other devices' buffers through peer (NVLink) addresses and the master rows
+ * out[C], out[C+1] come back from member 0.  Returns a ticket for gdg_cluster_wait(). */
+int gdg_cluster_submit(gdg_cluster *cl, gdg_chain *const *chains, uint32_t C, gdg_tuner *tuner, int tuner_channel, gdg_spatializer *const *spats,
+                       const double *const *in, double *const *out, uint32_t n_out, size_t n, uint32_t rate)
+{
+    if (ensure_init()) return -1;
+    if (!cl || !chains || !C || !in || !out) return fail("gdg_cluster_submit: bad argument");
+    if (check_block(n)) return -1;
+    if (n_out < C) return fail("gdg_cluster_submit: %u output rows for %u channels", n_out, C);
+    const int M = (int)cl->ctx.size();
+    std::vector<uint32_t> first(M + 1, C);
+    {   /* channel ranges: the chains' device contexts must follow the member order */
+        int m = 0; first[0] = 0;
+        for (uint32_t c = 0; c < C; c++) {
+            if (!chains[c]) return fail("gdg_cluster_submit: chain %u is NULL", c);
+            while (m < M && chains[c]->ctx != cl->ctx[m]) { m++; if (m < M) first[m] = c; }
+            if (m >= M) return fail("gdg_cluster_submit: chain %u does not live on a member device (or the chains are not grouped in member order)", c);
+        }
+        for (int k = m + 1; k <= M; k++) first[k] = C;
+    }
+    const bool master = spats && n_out >= C + 2;
+    int si = -1;
+    {
+        std::lock_guard<std::mutex> lk(g_batch_mutex);
+        for (int k = 0; k < 2 && si < 0; k++) {
+            bool ok = !cl->flight[k].busy;
+            for (int m = 0; m < M && ok; m++) { Use u(cl->ctx[m]); if (g_batch && g_batch->slot[k].busy) ok = false; }
+            if (ok) si = k;
+        }
+    }
+    if (si < 0) return fail("two submitted blocks are in flight: gdg_cluster_wait() for one first");
+    gdg_cluster::Flight &fl = cl->flight[si];
+    fl.members.clear(); fl.master = master; fl.n = n;
+    std::vector<const double *> parts; std::vector<long> strides; std::vector<int> part_ctx;
+    for (int m = 0; m < M; m++) {
+        const uint32_t c0 = first[m], cnt = first[m + 1] - first[m];
+        if (!cnt) continue;
+        Use u(cl->ctx[m]);
+        ProcessLock el(g_edit_mutex);
+        std::lock_guard<std::mutex> lk(g_batch_mutex);
+        gdg_spatializer *sp = master ? spats[m] : nullptr;
+        if (sp && (sp->count != cnt || sp->ctx != cl->ctx[m])) return fail("gdg_cluster_submit: member %d's spatializer must cover its %u channels on its own device", m, cnt);
+        gdg_tuner *tu = (tuner && tuner_channel >= (int)c0 && tuner_channel < (int)(c0 + cnt)) ? tuner : nullptr;
+        const double *pm = nullptr;
+        if (block_submit(si, chains + c0, cnt, tu, tu ? tuner_channel - (int)c0 : -1, sp, nullptr, (const void *const *)(in + c0), GDG_FMT_IEEE64,
+                         (void *const *)(out + c0), GDG_FMT_IEEE64, cnt, n, rate, nullptr, false, sp ? &pm : nullptr)) {
+            gdgb_sync(); if (g_batch) g_batch->slot[si].busy = false;
+            for (int k : fl.members) { Use u2(cl->ctx[k]); gdgb_sync(); if (g_batch) g_batch->slot[si].busy = false; }
+            return -1;
+        }
+        fl.members.push_back(m);
+        if (pm) { parts.push_back(pm); strides.push_back((long)n); part_ctx.push_back(cl->ctx[m]); }
+    }
+    if (master && !parts.empty()) {
+        Use u(cl->ctx[0]);
+        if (cl->cap_n < n) {
+            gdgb_sync(); gdgb_free(cl->d_master); gdgb_pinned_free(cl->h_master);
+            cl->d_master = (double *)gdgb_alloc(2 * n * sizeof(double));
+            cl->h_master = (double *)gdgb_pinned_alloc(2 * n * sizeof(double));
+            if (!cl->d_master || !cl->h_master) return backend_fail("cluster master allocation failed");
+            cl->cap_n = n;
+        }
+        const int ev = si * 28;
+        for (int pc : part_ctx) if (gdgb_wait_other(cl->ctx[0], pc, ev + 16)) return backend_fail("cross-device wait failed");
+        if (gdgb_master_sum(parts.data(), strides.data(), (int)parts.size(), nullptr, cl->d_master, cl->d_master + n, (int)n, gdgb_stream()))
+            return backend_fail("master sum failed");
+        if (gdgb_record(ev + 19, 0) || gdgb_wait(2, ev + 19)) return backend_fail("event failed");
+        if (gdgb_d2h_async(cl->h_master, cl->d_master, 2 * n * sizeof(double), 2) || gdgb_record(ev + 20, 2)) return backend_fail("master download failed");
+        fl.out_l = out[C]; fl.out_r = out[C + 1];
+    } else fl.master = false;
+    fl.busy = true;
+    return si;
+}
+int gdg_cluster_wait(gdg_cluster *cl, int ticket)
+{
+    if (ensure_init()) return -1;
+    if (!cl || ticket < 0 || ticket > 1 || !cl->flight[ticket].busy) return fail("gdg_cluster_wait: ticket %d is not in flight", ticket);
+    gdg_cluster::Flight &fl = cl->flight[ticket];
+    int rc = 0;
+    for (int m : fl.members) {
+        Use u(cl->ctx[m]);
+        std::lock_guard<std::mutex> lk(g_batch_mutex);
+        if (g_batch && g_batch->slot[ticket].busy && block_wait(ticket)) rc = -1;
+    }
+    if (fl.master) {
+        Use u(cl->ctx[0]);
+        if (gdgb_sync_event(ticket * 28 + 20)) rc = backend_fail("synchronize failed");
+        else { memcpy(fl.out_l, cl->h_master, fl.n * sizeof(double)); memcpy(fl.out_r, cl->h_master + fl.n, fl.n * sizeof(double)); }
+    }
+    fl.busy = false;
+    return rc;
+}
+int gdg_cluster_process(gdg_cluster *cl, gdg_chain *const *chains, uint32_t C, gdg_tuner *tuner, int tuner_channel, gdg_spatializer *const *spats,
+                        const double *const *in, double *const *out, uint32_t n_out, size_t n, uint32_t rate)
+{
+    const int t = gdg_cluster_submit(cl, chains, C, tuner, tuner_channel, spats, in, out, n_out, n, rate);
+    if (t < 0) return -1;
+    return gdg_cluster_wait(cl, t);
 }
 
 } /* extern "C" */

@@ -10,16 +10,32 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "gdg_backend.h"
 #include "gdg_interp.cuh"
 #include "gdg_os.cuh"
 
 static thread_local std::string t_err;
-static int g_device = -1, g_sms = 0;
-static cudaStream_t g_stream = nullptr, g_copy_streams[2] = {nullptr, nullptr};
-static cudaEvent_t g_events[GDGB_EVENTS];
-static double *g_d_tw = nullptr;
+/* One context per CUDA device the process uses (gdg_backend.h: gdgb_context_open / gdgb_select): its streams, events and
+ * tables.  Context 0 is the device of gdgb_init(); a thread works on the context it selected last (default 0). */
+struct DevCtx {
+    int device = -1, sms = 0;
+    cudaStream_t stream = nullptr, copy[2] = {nullptr, nullptr};
+    cudaEvent_t events[GDGB_EVENTS];
+    double *d_tw = nullptr;
+};
+static DevCtx g_ctx[GDGB_MAX_CONTEXTS];
+static int g_nctx = 0;
+static thread_local int t_cur = 0;
+static std::vector<double> g_tab_aa2, g_tab_aa4, g_tab_lz2, g_tab_lz4, g_tab_tw;      /* host copies: uploaded to every context */
+#define CX (g_ctx[t_cur])
+#define g_device (CX.device)
+#define g_sms (CX.sms)
+#define g_stream (CX.stream)
+#define g_copy_streams (CX.copy)
+#define g_events (CX.events)
+#define g_d_tw (CX.d_tw)
 static std::atomic<uint64_t> g_launches{0};
 
 static int cu_fail(const char *what, cudaError_t e)
@@ -184,6 +200,19 @@ k_ir_partition_spectra(const double *coeffs, int L, int B, int logB, double *H, 
 {
     run_partition_spectrum(gdg_smem, coeffs, L, B, logB, blockIdx.x, H + 2L * (long)blockIdx.x * (B + 1), tw);
 }
+/* stereo master of a multi-device block: out[r][j] = sum over devices d (ascending) of part[d][r * stride_d + j] (+ aux).
+ * The partial masters live on the OTHER devices: the loads are peer (NVLink) loads - the reduction and its transfer are
+ * one kernel (spatializer.go:140-335 sums channels 0..C-1; here: the per-device partial sums in device order). */
+struct gdg_master_parts { const double *part[GDGB_MAX_CONTEXTS]; long stride[GDGB_MAX_CONTEXTS]; int count; };
+__global__ void k_master_sum(gdg_master_parts p, const double *aux, double *outL, double *outR, int n)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    double l = 0.0, r = 0.0;
+    for (int d = 0; d < p.count; d++) { l += p.part[d][j]; r += p.part[d][p.stride[d] + j]; }
+    if (aux) { l += aux[j]; r += aux[j]; }
+    outL[j] = l; outR[j] = r;
+}
 /* batched tuner autocorrelation: blockIdx.y selects the tuner */
 struct gdg_ac_batch { const double *ring[32]; double *work[32]; int pos[32]; };
 __global__ void k_acb_load(gdg_ac_batch b, int n_ring, int F)
@@ -220,7 +249,7 @@ int gdgb_sm_count(void) { return g_sms; }
 void *gdgb_stream(void) { return (void *)g_stream; }
 uint64_t gdgb_launch_count(void) { return g_launches.load(); }
 
-int gdgb_init(int device)
+static int open_context(int slot, int device)
 {
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
@@ -232,14 +261,83 @@ int gdgb_init(int device)
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10) { t_err = std::string("device '") + prop.name + "' is not a Blackwell (sm_100a) GPU"; return -1; }
-    g_device = device; g_sms = prop.multiProcessorCount;
-    CU(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; i++) CU(cudaStreamCreateWithFlags(&g_copy_streams[i], cudaStreamNonBlocking));
-    for (int i = 0; i < GDGB_EVENTS; i++) CU(cudaEventCreateWithFlags(&g_events[i], cudaEventDisableTiming));
+    DevCtx &c = g_ctx[slot];
+    c.device = device; c.sms = prop.multiProcessorCount;
+    CU(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) CU(cudaStreamCreateWithFlags(&c.copy[i], cudaStreamNonBlocking));
+    for (int i = 0; i < GDGB_EVENTS; i++) CU(cudaEventCreateWithFlags(&c.events[i], cudaEventDisableTiming));
     CU(cudaFuncSetAttribute(k_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, GDG_SMEM_BYTES));
     CU(cudaFuncSetAttribute(k_ir_partition_spectra, cudaFuncAttributeMaxDynamicSharedMemorySize, GDG_SMEM_BYTES));
     CU(cudaFuncSetAttribute(k_os, cudaFuncAttributeMaxDynamicSharedMemorySize, GDG_OSK_SMEM_BYTES));
     CU(cudaFuncSetAttribute(k_os, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    return 0;
+}
+static int upload_tables()
+{
+    if (g_tab_tw.empty()) return 0;
+    CU(cudaMemcpyToSymbol(c_aa2, g_tab_aa2.data(), sizeof(double) * 80));
+    CU(cudaMemcpyToSymbol(c_aa4, g_tab_aa4.data(), sizeof(double) * 160));
+    CU(cudaMemcpyToSymbol(c_lz2, g_tab_lz2.data(), sizeof(double) * 6));
+    CU(cudaMemcpyToSymbol(c_lz4, g_tab_lz4.data(), sizeof(double) * 18));
+    if (!g_d_tw) CU(cudaMalloc((void **)&g_d_tw, sizeof(double) * GDG_MAX_FFT));
+    CU(cudaMemcpy(g_d_tw, g_tab_tw.data(), sizeof(double) * GDG_MAX_FFT, cudaMemcpyHostToDevice));
+    return 0;
+}
+int gdgb_init(int device)
+{
+    t_cur = 0;
+    if (open_context(0, device)) return -1;
+    if (g_nctx < 1) g_nctx = 1;
+    return 0;
+}
+/* a further device of this process: returns its context index (the existing one if the device is open already) or -1 */
+int gdgb_context_open(int device)
+{
+    for (int i = 0; i < g_nctx; i++) if (g_ctx[i].device == device) return i;
+    if (g_nctx >= GDGB_MAX_CONTEXTS) { t_err = "too many device contexts"; return -1; }
+    const int prev = t_cur, slot = g_nctx;
+    t_cur = slot;
+    if (open_context(slot, device) || upload_tables()) { t_cur = prev; if (g_ctx[prev].device >= 0) cudaSetDevice(g_ctx[prev].device); return -1; }
+    g_nctx++;
+    t_cur = prev;
+    if (g_ctx[prev].device >= 0) cudaSetDevice(g_ctx[prev].device);
+    return slot;
+}
+int gdgb_context_count(void) { return g_nctx; }
+int gdgb_context_device(int ctx) { return (ctx >= 0 && ctx < g_nctx) ? g_ctx[ctx].device : -1; }
+int gdgb_current(void) { return t_cur; }
+int gdgb_select(int ctx)
+{
+    if (ctx < 0 || ctx >= g_nctx) { t_err = "no such device context"; return -1; }
+    t_cur = ctx;
+    CU(cudaSetDevice(g_ctx[ctx].device));
+    return 0;
+}
+int gdgb_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; } return n; }
+/* peer access from context `ctx` to every other open context (NVLink / NVSwitch P2P): kernels on `ctx` may then dereference
+ * the other devices' buffers */
+int gdgb_enable_peers(int ctx)
+{
+    const int prev = t_cur;
+    if (gdgb_select(ctx)) return -1;
+    int rc = 0;
+    for (int i = 0; i < g_nctx && !rc; i++) {
+        if (i == ctx) continue;
+        int can = 0;
+        cudaDeviceCanAccessPeer(&can, g_ctx[ctx].device, g_ctx[i].device);
+        if (!can) { t_err = "peer access between the devices is not available"; rc = -1; break; }
+        cudaError_t e = cudaDeviceEnablePeerAccess(g_ctx[i].device, 0);
+        if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+        else if (e != cudaSuccess) rc = cu_fail("cudaDeviceEnablePeerAccess", e);
+    }
+    gdgb_select(prev);
+    return rc;
+}
+/* stream 0 of context `ctx` waits for event `event` of context `other` (events order work across devices) */
+int gdgb_wait_other(int ctx, int other, int event)
+{
+    if (ctx < 0 || ctx >= g_nctx || other < 0 || other >= g_nctx) { t_err = "no such device context"; return -1; }
+    CU(cudaStreamWaitEvent(g_ctx[ctx].stream, g_ctx[other].events[event % GDGB_EVENTS], 0));
     return 0;
 }
 
@@ -286,13 +384,9 @@ int gdgb_is_pinned(const void *p)
 
 int gdgb_set_tables(const double *aa2, const double *aa4, const double *lz2, const double *lz4, const double *tw)
 {
-    CU(cudaMemcpyToSymbol(c_aa2, aa2, sizeof(double) * 80));
-    CU(cudaMemcpyToSymbol(c_aa4, aa4, sizeof(double) * 160));
-    CU(cudaMemcpyToSymbol(c_lz2, lz2, sizeof(double) * 6));
-    CU(cudaMemcpyToSymbol(c_lz4, lz4, sizeof(double) * 18));
-    if (!g_d_tw) CU(cudaMalloc((void **)&g_d_tw, sizeof(double) * GDG_MAX_FFT));
-    CU(cudaMemcpy(g_d_tw, tw, sizeof(double) * GDG_MAX_FFT, cudaMemcpyHostToDevice));
-    return 0;
+    g_tab_aa2.assign(aa2, aa2 + 80); g_tab_aa4.assign(aa4, aa4 + 160); g_tab_lz2.assign(lz2, lz2 + 6); g_tab_lz4.assign(lz4, lz4 + 18);
+    g_tab_tw.assign(tw, tw + GDG_MAX_FFT);
+    return upload_tables();
 }
 
 int gdgb_launch_segments(int kind, const gdg_chain_desc *const *d_descs, const int32_t *d_nseg, int round, int channels,
@@ -439,6 +533,16 @@ int gdgb_autocorrelate_batch(const double *const *d_rings, int n_ring, const int
         for (int h = 1; h <= M / 2; h <<= 1) { k_acb_dit<<<gB, 256, 0, s>>>(b, M, h); g_launches++; }
         k_acb_scale<<<gF, 256, 0, s>>>(b, F, 1.0 / (double)M); g_launches++;
     }
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int gdgb_master_sum(const double *const *d_parts, const long *strides, int count, const double *d_aux, double *d_outL, double *d_outR, int n, void *stream)
+{
+    if (count > GDGB_MAX_CONTEXTS) { t_err = "too many partial masters"; return -1; }
+    gdg_master_parts p; p.count = count;
+    for (int d = 0; d < count; d++) { p.part[d] = d_parts[d]; p.stride[d] = strides[d]; }
+    k_master_sum<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(p, d_aux, d_outL, d_outR, n); g_launches++;
     CU(cudaGetLastError());
     return 0;
 }

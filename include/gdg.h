@@ -242,6 +242,28 @@ int gdg_controller_submit_encoded(gdg_chain *const *chains, uint32_t channels, g
                                   gdg_spatializer *spat, gdg_meter *meter, const void *const *in, int in_format,
                                   void *const *out, int out_format, uint32_t n_out, size_t n, uint32_t sample_rate);
 
+/* ---- several GPUs in ONE process ---------------------------------------------------------------------------
+ * The reference host is one process with one worker per channel (controller/controller.go:3339-3341); a cgo host cannot
+ * call torch.distributed.  Channels shard over devices in contiguous ranges; every object lives on the
+ * device that was selected on the creating thread (gdg_use_device / gdg_cluster_select); the only exchange is the stereo
+ * master: member 0 sums the members' partial masters with ONE kernel that reads the other devices' buffers through peer
+ * (NVLink 5 / NVSwitch) addresses - no NCCL, no host round trip. */
+typedef struct gdg_cluster gdg_cluster;
+int gdg_device_count(void);
+int gdg_use_device(int device);                   /* thread-local: objects created afterwards live on `device`; returns >= 0 */
+int gdg_current_device(void);
+gdg_cluster *gdg_cluster_create(const int *devices, int n_devices);
+void gdg_cluster_destroy(gdg_cluster *cluster);
+int gdg_cluster_size(gdg_cluster *cluster);
+int gdg_cluster_select(gdg_cluster *cluster, int member);       /* == gdg_use_device(devices[member]) */
+/* controller.process over the cluster (see gdg_controller_submit): chains[c] in member order, spats[m] = member m's
+ * spatializer over its own channels (NULL array: no master); ticketed like gdg_controller_submit (two blocks in flight) */
+int gdg_cluster_submit(gdg_cluster *cluster, gdg_chain *const *chains, uint32_t channels, gdg_tuner *tuner, int tuner_channel,
+                       gdg_spatializer *const *spats, const double *const *in, double *const *out, uint32_t n_out, size_t n, uint32_t sample_rate);
+int gdg_cluster_wait(gdg_cluster *cluster, int ticket);
+int gdg_cluster_process(gdg_cluster *cluster, gdg_chain *const *chains, uint32_t channels, gdg_tuner *tuner, int tuner_channel,
+                        gdg_spatializer *const *spats, const double *const *in, double *const *out, uint32_t n_out, size_t n, uint32_t sample_rate);
+
 #ifdef __cplusplus
 }
 #endif

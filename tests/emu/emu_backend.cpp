@@ -29,7 +29,36 @@ static std::atomic<uint64_t> g_launches{0};
 
 const char *gdgb_error(void) { return t_err.c_str(); }
 const char *gdgb_name(void) { return "host-emulation (tests only)"; }
+/* device contexts: the emulation has one memory space; contexts are bookkeeping only (tests of the multi-device host logic) */
+static int g_nctx = 1, g_ctx_dev[GDGB_MAX_CONTEXTS] = {0};
+static thread_local int t_cur = 0;
 int gdgb_init(int) { return 0; }
+int gdgb_device_count(void) { const char *e = getenv("GDG_EMU_DEVICES"); return e ? atoi(e) : 1; }
+int gdgb_context_open(int device)
+{
+    if (device < 0 || device >= gdgb_device_count()) { t_err = "device index out of range"; return -1; }
+    for (int i = 0; i < g_nctx; i++) if (g_ctx_dev[i] == device) return i;
+    if (g_nctx >= GDGB_MAX_CONTEXTS) { t_err = "too many device contexts"; return -1; }
+    g_ctx_dev[g_nctx] = device;
+    return g_nctx++;
+}
+int gdgb_context_count(void) { return g_nctx; }
+int gdgb_context_device(int ctx) { return (ctx >= 0 && ctx < g_nctx) ? g_ctx_dev[ctx] : -1; }
+int gdgb_current(void) { return t_cur; }
+int gdgb_select(int ctx) { if (ctx < 0 || ctx >= g_nctx) { t_err = "no such device context"; return -1; } t_cur = ctx; return 0; }
+int gdgb_enable_peers(int) { return 0; }
+int gdgb_wait_other(int, int, int) { return 0; }
+int gdgb_master_sum(const double *const *parts, const long *strides, int count, const double *aux, double *outL, double *outR, int n, void *)
+{
+    for (int j = 0; j < n; j++) {
+        double l = 0.0, r = 0.0;
+        for (int d = 0; d < count; d++) { l += parts[d][j]; r += parts[d][strides[d] + j]; }
+        if (aux) { l += aux[j]; r += aux[j]; }
+        outL[j] = l; outR[j] = r;
+    }
+    g_launches++;
+    return 0;
+}
 int gdgb_device(void) { return -1; }
 int gdgb_sm_count(void) { return 148; }            /* the part being emulated: pipeline groups are sized like on a B200 */
 void *gdgb_stream(void) { return nullptr; }
