@@ -495,6 +495,18 @@ def main():
             except Exception as e:
                 extras["weak_scaling"] = {"error": str(e)}
 
+    # ---- extra: the SAME N GPUs driven by ONE process through gdg_cluster_* (what a Go host would do: no torch.distributed,
+    # no NCCL; the stereo master is summed on device 0 by one kernel reading the other devices over NVLink peer addresses).
+    # Rank 0 drives every GPU while the other ranks wait at the barrier. ----
+    if world > 1 and not args.no_extras:
+        barrier()
+        if rank == 0:
+            try:
+                extras["single_process_cluster"] = cluster_extra(torch, gdg, presets, lib, world, xsteps)
+            except Exception as e:
+                extras["single_process_cluster"] = {"error": "%s: %s" % (type(e).__name__, e)}
+        barrier()
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         os.sched_setaffinity(0, all_cpus)                        # the CPU baseline gets every host core
@@ -526,6 +538,65 @@ def main():
             "cpu_baseline": cpu_baseline, "extras": extras}))
     if world > 1:
         dist.destroy_process_group()
+
+
+def cluster_extra(torch, gdg, presets, lib, ndev, steps):
+    """CHANNELS_TOTAL channels over `ndev` GPUs from ONE process: gdg_cluster_submit / gdg_cluster_wait on pinned host rows,
+    two blocks in flight; wall clock, every block's H2D and D2H inside."""
+    cl = gdg.Cluster(list(range(ndev)), lib=lib)
+    per, rem = divmod(CHANNELS_TOTAL, ndev)
+    chains, spats, keep = [], [], []
+    g0 = 0
+    for m in range(ndev):
+        cnt = per + (1 if m < rem else 0)
+        cl.select(m)
+        bank = gdg.IRBank(lib)
+        bank.add_raw("syn8192", 0, presets.synthetic_ir(IR_TAPS), FS)
+        keep.append(bank)
+        sp = gdg.Spatializer(cnt, lib=lib)
+        sp.set_sample_rate(FS)
+        for c in range(cnt):
+            g = g0 + c
+            chains.append(presets.build_chain(gdg.Chain(bank, lib=lib), presets.CHAIN12, "syn8192"))
+            sp.set_azimuth(c, -70.0 + 140.0 * g / max(1, CHANNELS_TOTAL - 1))
+            sp.set_distance(c, 1.0 + 0.25 * (g % 8))
+        spats.append(sp)
+        g0 += cnt
+    cl.select(0)
+    tuner = gdg.Tuner(lib=lib)
+    C = CHANNELS_TOTAL
+    h_in = [torch.empty((C, N), dtype=torch.float64).pin_memory() for _ in range(2)]
+    h_out = [torch.empty((C + 2, N), dtype=torch.float64).pin_memory() for _ in range(2)]
+    base = torch.tensor(np.stack([presets.synth_fast(c, FS, N) for c in range(36)]))
+    for k in range(2):
+        h_in[k].copy_(base[torch.arange(C) % 36])
+    handles = (Ct.c_void_p * C)(*[c_._h for c_ in chains])
+    sph = (Ct.c_void_p * ndev)(*[s_._h for s_ in spats])
+    pin = [(Ct.c_void_p * C)(*[h_in[k].data_ptr() + 8 * N * c for c in range(C)]) for k in range(2)]
+    pout = [(Ct.c_void_p * (C + 2))(*[h_out[k].data_ptr() + 8 * N * c for c in range(C + 2)]) for k in range(2)]
+
+    def check(rc):
+        if rc < 0:
+            raise RuntimeError(lib.gdg_last_error().decode())
+        return rc
+
+    def run(nblocks):
+        prev = None
+        for k in range(nblocks):
+            t = check(lib.gdg_cluster_submit(cl._h, handles, C, tuner._h, 0, sph, pin[k % 2], pout[k % 2], C + 2, N, FS))
+            if prev is not None:
+                check(lib.gdg_cluster_wait(cl._h, prev))
+            prev = t
+        check(lib.gdg_cluster_wait(cl._h, prev))
+    run(8)
+    nb = steps * BLOCKS
+    t0 = time.perf_counter()
+    run(nb)
+    dt = time.perf_counter() - t0
+    gdg.use_device(0, lib)
+    return {"value": C * N * nb / dt / 1e6, "unit": "Msamples/s", "devices": ndev, "channels_per_device": per,
+            "api": "gdg_cluster_submit / gdg_cluster_wait from ONE process (host rows, two blocks in flight); master = peer-memory sum kernel on device 0, no NCCL",
+            "blocks": nb}
 
 
 def config_extras(torch, gdg, presets, lib, dev, stream, args):
