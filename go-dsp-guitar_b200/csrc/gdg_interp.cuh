@@ -485,7 +485,7 @@ GDG_DEVI void ir_scale_add_body(double *acc, const double *x, double comp, doubl
 
 /* spectrum of partition p of a filter (filter.go:395-401 per 8192-tap / block-length partition): real FFT of size F = 2B of
  * h[pB .. pB + B) zero-padded, through the chain kernel's own shared-memory FFT (half-size complex transform, DIF, natural ->
- * bit-reversed) and a split pass; H: bins 0..B interleaved (re, im).  One CTA (GDG_NT threads) per partition. */
+ * bit-reversed) and a split pass; H: bins 0..B interleaved (re, im), bin k at index brev(k) (0 and B stay). One CTA per partition. */
 GDG_DEV void run_partition_spectrum(double *smem, const double *coeffs, int L, int B, int logB, int p, double *H, const double *tw)
 {
 #if !defined(__CUDACC__) || defined(GDG_HOST_EMU)
@@ -519,7 +519,8 @@ GDG_DEV void run_partition_spectrum(double *smem, const double *coeffs, int L, i
                 const gdg_c2 t1 = cmul(jw, d1);
                 xr = 0.5 * (s1.re - t1.re); xi = 0.5 * (s1.im - t1.im);
             }
-            H[2 * k] = xr; H[2 * k + 1] = xi;
+            const int at = (k == 0 || k == M) ? k : brev(k, logB);           /* storage order of the chain kernel's transform (stage_poweramp) */
+            H[2 * at] = xr; H[2 * at + 1] = xi;
         }
     GDG_THREADS_END
 }

@@ -164,6 +164,14 @@ GDG_DEVI int imax(int a, int b) { return a > b ? a : b; }
 GDG_DEVI long long st_geti(const double *st, int k) { return ((const long long *)st)[k]; }
 GDG_DEVI void st_seti(double *st, int k, long long v) { ((long long *)st)[k] = v; }
 GDG_DEVI int chunk_len(int n) { return (n + GDG_NT - 1) / GDG_NT; }
+GDG_DEVI int ilog2_floor(int v)                   /* floor(log2(v)), v >= 1 */
+{
+#if defined(__CUDACC__) && !defined(GDG_HOST_EMU)
+    return 31 - __clz(v);
+#else
+    return 31 - __builtin_clz((unsigned)v);
+#endif
+}
 /* the context lives in shared memory (a private copy passed by reference to the non-inlined stages would sit in
  * local memory, and there is next to no L1 left beside the 220 KB carve-out): one thread flips it between barriers.
  * Every stage ends with a barrier before it swaps, so no thread still reads the old orientation. */
@@ -767,7 +775,7 @@ GDG_DEV void stage_chorus(gdg_ctx &cx, const gdg_unit_desc &d_global)
         double cj[5], sj[5];                           /* cos / sin of the voice offsets 0.4*pi*j (p[3..10], host-computed) */
         cj[0] = 1.0; sj[0] = 0.0;
         for (int j = 1; j < 5; j++) { cj[j] = d.p[2 + j]; sj[j] = d.p[6 + j]; }
-#pragma unroll 1
+#pragma unroll 2
         for (int k = tid; k < n; k += GDG_NT) {
             const double t = (double)k / sr;
             const double zero_phase = fmod(GDG_MULADD_RN(ang, t, prev), GDG_TWO_PI);

@@ -545,7 +545,8 @@ GDG_DEV void stage_reverb(gdg_ctx &cx, const gdg_unit_desc &d_global)
  *   i[0] L (taps; 0 = empty filter -> zeros, -1 = no filter compiled -> zeros)
  *   i[1] F (real FFT size = 2*nextPow2(L), capped at GDG_MAX_FFT)   i[2] log2(F/2)
  *   i[3] K partitions (1 unless L > GDG_MAX_FFT/2)   i[4] word offset of the spectrum delay line in st
- *   aux: H_p[k], p < K, k = 0..F/2 (interleaved re,im) = first half of RealFourier(zero-padded partition p of h)
+ *   aux: H_p, p < K: bins 0..F/2 of RealFourier(zero-padded partition p of h), interleaved (re, im), in the STORAGE order of the
+ *        shared-memory transform: bin k at index brev(k) for 0 < k < F/2, bins 0 and F/2 at indices 0 and F/2
  *   st: tail[F], zero-run word, [K > 1: current slot word, then K x (F/2 + 1) complex input spectra]
  * Filters longer than 8192 taps run as a uniformly partitioned convolution (block = partition = 8192):
  * y_t = IFFT(sum_p X_(t-p) H_p) - the same linear convolution the reference evaluates with one
@@ -670,21 +671,33 @@ GDG_DEV void fft_pass(double *D, const double *tws, int logM, int nseg, int logL
             const int seg = b >> (logM - LOGR), rb = b & ((1 << (logM - LOGR)) - 1);
             const int blk = rb >> logS, j = rb & ((1 << logS) - 1);
             const int base = (seg << logM) + (blk << logL) + j;
-            gdg_c2 v[RR], pw[RR];
+            gdg_c2 v[RR];
 #pragma unroll
             for (int k = 0; k < RR; k++) v[k] = cld(D, cz(base + (k << logS)));
             gdg_c2 w1 = cld(tws, j << tshift);
             if (inverse) w1.im = -w1.im;
-            tw_powers<RR>(w1, pw);
-            if (!inverse) {
-                dif_net<RR>(v);
+            if (!inverse) dif_net<RR>(v);
+            if (RR == 16) {
+                /* slot k holds output brev(k): powers w^1..w^15 from w, w^2, w^4, w^8 (4 complex registers) instead of a
+                 * 16-entry table next to the 16 points - the radix-16 pass no longer spills at 128 registers */
+                const gdg_c2 w2 = cmul(w1, w1), w4 = cmul(w2, w2), w8 = cmul(w4, w4);
 #pragma unroll
-                for (int k = 1; k < RR; k++) v[k] = cmul(v[k], pw[brev_small<RR>(k)]);
+                for (int k = 1; k < RR; k++) {
+                    const int q = brev_small<RR>(k);
+                    gdg_c2 t; t.re = 1.0; t.im = 0.0; bool first = true;
+                    if (q & 8) { t = w8; first = false; }
+                    if (q & 4) { t = first ? w4 : cmul(t, w4); first = false; }
+                    if (q & 2) { t = first ? w2 : cmul(t, w2); first = false; }
+                    if (q & 1) { t = first ? w1 : cmul(t, w1); first = false; }
+                    v[k] = cmul(v[k], t);
+                }
             } else {
+                gdg_c2 pw[RR];
+                tw_powers<RR>(w1, pw);
 #pragma unroll
                 for (int k = 1; k < RR; k++) v[k] = cmul(v[k], pw[brev_small<RR>(k)]);
-                dit_net_inv<RR>(v);
             }
+            if (inverse) dit_net_inv<RR>(v);
 #pragma unroll
             for (int k = 0; k < RR; k++) cst(D, cz(base + (k << logS)), v[k]);
         }
@@ -734,7 +747,10 @@ GDG_DEV void stage_poweramp(gdg_ctx &cx, const gdg_unit_desc &d_global, const do
     const int total = nb * M;                                    /* complex points in flight (<= GDG_MAX_N) */
     double *D = SM_R, *tail = d.st;
     const double *tws = SM_TWS;                                  /* 1024 complex: exp(-2 pi i k / 8192), loaded by run_chain */
-    double *wc = SM_SCANA, *wf = SM_SCANA + 130;                 /* W_F^(64 a), a <= 64 and W_F^b, b < 64 for the split */
+    /* split twiddles indexed by STORAGE (bit-reversed) position r = r_hi 2^s + r_lo: W_F^brev(r) = TA[r_lo] TB[r_hi] with
+     * TA[x] = W_F^(brev_s(x) 2^(logM-s)), TB[y] = W_F^brev_(logM-s)(y): a warp reads consecutive TA entries and one TB entry */
+    const int tsplit = imin(7, logM);
+    double *wc = SM_SCANA, *wf = SM_SCANA + 256;
     double *tl = SM_S;                                           /* prefetched overlap tail (plain layout) */
     const double *H = d.aux;
     const int zlen = (int)st_geti(tail, F);                      /* trailing zeros guaranteed in tail[] */
@@ -748,8 +764,8 @@ GDG_DEV void stage_poweramp(gdg_ctx &cx, const gdg_unit_desc &d_global, const do
     GDG_THREADS_BEGIN
 #pragma unroll 4
         for (int k = tid; k < n; k += GDG_NT) tl[k] = x[sw(k)];
-        if (tid < 65) cst(wc, tid, tw_full(tw, imin(64 * tid * fstep, GDG_MAX_FFT - 1) ));
-        if (tid >= 128 && tid < 192) cst(wf, tid - 128, twd(tw, (tid - 128) * fstep));
+        if (tid < (1 << tsplit)) cst(wc, tid, tw_full(tw, (brev(tid, tsplit) << (logM - tsplit)) * fstep));
+        if (tid >= 128 && tid < 128 + (1 << (logM - tsplit))) cst(wf, tid - 128, tw_full(tw, brev(tid - 128, logM - tsplit) * fstep));
     GDG_THREADS_END
     GDG_THREADS_BEGIN
 #pragma unroll 2
@@ -796,17 +812,22 @@ GDG_DEV void stage_poweramp(gdg_ctx &cx, const gdg_unit_desc &d_global, const do
                 cst(D, cz(zb), o);
             }
         }
+        /* the conjugate pairs (k, M - k) sit at storage positions (r, r ^ (2^j - 1)) inside the block [2^j, 2^(j+1)) of the
+         * bit-reversed order: walking r instead of k makes both shared-memory accesses unit-stride across the warp
+         * (walking k, they were 8-way bank-conflicted) */
 #pragma unroll 2
         for (int b = tid; b < nb * (M / 2); b += GDG_NT) {
-            const int seg = b / (M / 2), k = 1 + (b - seg * (M / 2));
+            const int seg = b / (M / 2), bb = b - seg * (M / 2);
             const int zb = seg * M;
             {
-                const int k2 = M - k;
-                gdg_c2 ha, hb; ha.re = GDG_LDG(H + 2 * k); ha.im = GDG_LDG(H + 2 * k + 1);
-                hb.re = GDG_LDG(H + 2 * k2); hb.im = GDG_LDG(H + 2 * k2 + 1);
-                const int p1 = cz(zb + brev(k, logM)), p2 = cz(zb + brev(k2, logM));
+                int r = 1, r2 = 1;
+                if (bb > 0) { const int j = ilog2_floor(bb) + 1; r = (1 << j) + (bb - (1 << (j - 1))); r2 = r ^ ((1 << j) - 1); }
+                /* spectra (H, and the delay line of partitioned filters) are stored in the same storage order: coalesced */
+                gdg_c2 ha, hb; ha.re = GDG_LDG(H + 2 * r); ha.im = GDG_LDG(H + 2 * r + 1);
+                hb.re = GDG_LDG(H + 2 * r2); hb.im = GDG_LDG(H + 2 * r2 + 1);
+                const int p1 = cz(zb + r), p2 = cz(zb + r2);
                 const gdg_c2 za = cld(D, p1), zbv = cld(D, p2);
-                const gdg_c2 wk = cmul(cld(wc, k >> 6), cld(wf, k & 63));  /* W_F^k = W_F^(64 a) W_F^b */
+                const gdg_c2 wk = cmul(cld(wc, r & ((1 << tsplit) - 1)), cld(wf, r >> tsplit));   /* W_F^k, k = brev(r) */
                 gdg_c2 jw; jw.re = -wk.im; jw.im = wk.re;                 /* j * W_F^k */
                 const gdg_c2 s1 = cadd(za, cconj(zbv)), d1 = csub(za, cconj(zbv));
                 const gdg_c2 t1 = cmul(jw, d1);
@@ -819,13 +840,13 @@ GDG_DEV void stage_poweramp(gdg_ctx &cx, const gdg_unit_desc &d_global, const do
                     for (int p = 1; p < K; p++) {
                         const double *X = fdl + (long)((slot - p + K) % K) * hstride, *Hp = H + (long)p * hstride;
                         gdg_c2 xp, hp;
-                        xp.re = GDG_LDST(X + 2 * k); xp.im = GDG_LDST(X + 2 * k + 1); hp.re = GDG_LDG(Hp + 2 * k); hp.im = GDG_LDG(Hp + 2 * k + 1);
+                        xp.re = GDG_LDST(X + 2 * r); xp.im = GDG_LDST(X + 2 * r + 1); hp.re = GDG_LDG(Hp + 2 * r); hp.im = GDG_LDG(Hp + 2 * r + 1);
                         ya = cadd(ya, cmul(xp, hp));
-                        xp.re = GDG_LDST(X + 2 * k2); xp.im = GDG_LDST(X + 2 * k2 + 1); hp.re = GDG_LDG(Hp + 2 * k2); hp.im = GDG_LDG(Hp + 2 * k2 + 1);
+                        xp.re = GDG_LDST(X + 2 * r2); xp.im = GDG_LDST(X + 2 * r2 + 1); hp.re = GDG_LDG(Hp + 2 * r2); hp.im = GDG_LDG(Hp + 2 * r2 + 1);
                         yb = cadd(yb, cmul(xp, hp));
                     }
                     double *Xc = fdl + (long)slot * hstride;
-                    Xc[2 * k] = xa.re; Xc[2 * k + 1] = xa.im; Xc[2 * k2] = xb.re; Xc[2 * k2 + 1] = xb.im;
+                    Xc[2 * r] = xa.re; Xc[2 * r + 1] = xa.im; Xc[2 * r2] = xb.re; Xc[2 * r2 + 1] = xb.im;
                 }
                 const gdg_c2 e1 = cadd(ya, cconj(yb)), o1 = cmul(csub(ya, cconj(yb)), cconj(wk));
                 gdg_c2 ra; ra.re = 0.5 * (e1.re - o1.im); ra.im = 0.5 * (e1.im + o1.re);

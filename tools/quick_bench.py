@@ -16,7 +16,7 @@ ts = torch.cuda.Stream(); torch.cuda.set_stream(ts)
 stream = ts.cuda_stream
 assert stream
 res = {}
-def timeit(name, spec, ir=None, reps=5):
+def timeit(name, spec, ir=None, reps=int(os.environ.get("GDG_REPS", "5"))):
     chains = [common.build_chain(gdg.Chain(banks[1], lib=lib), spec, ir) for _ in range(C)]
     r = gdg.BatchRunner(chains)
     for _ in range(2): r.process_device(x.data_ptr(), y.data_ptr(), n, n, fs, stream)
