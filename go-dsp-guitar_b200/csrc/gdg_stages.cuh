@@ -52,6 +52,7 @@
 /* c + a*b with BOTH roundings, as the reference computes it (no FMA contraction): used where the result feeds a
  * discontinuity (phase wrap, square / sawtooth edge) or is carried as state, so that it stays bit-identical */
 #define GDG_MULADD_RN(a, b, c) __dadd_rn(__dmul_rn((a), (b)), (c))
+#define GDG_SINCOS(x, s, c) sincos((x), (s), (c))
 /* 8-byte global -> shared copy that does not pass through registers (LDGSTS): the issuing thread does not wait for it
  * until async_wait(); a thread only ever reads back cells it requested itself, so no barrier is involved */
 static __device__ __forceinline__ void async_copy8(double *smem_dst, const double *gsrc)
@@ -92,6 +93,7 @@ static __device__ __forceinline__ void bulk_wait(double *mbar_word)
 #define GDG_LDG(p) (*(p))
 #define GDG_LDST(p) (*(p))
 #define GDG_MULADD_RN(a, b, c) (((a) * (b)) + (c))          /* the emulation is built with -ffp-contract=off */
+#define GDG_SINCOS(x, s, c) do { *(s) = sin(x); *(c) = cos(x); } while (0)
 static inline void async_copy8(double *dst, const double *src) { *dst = *src; }
 static inline void async_wait() {}
 static inline void bulk_load(double *, double *dst, const void *src, unsigned bytes) { memcpy(dst, src, bytes); }
@@ -737,6 +739,18 @@ GDG_DEVI double frac_delay_read(const double *blk, const double *ring, int hs, i
     return (we * se) + (wl * sl);
 }
 
+/* the same read with both candidate loads of each tap issued unconditionally (hist_or_block_nb): for units whose taps fall
+ * mostly into the history ring and never before it (chorus: 40 +- 10 ms against a 50 ms ring) - the global loads of the ten
+ * taps of a sample are batched instead of branched around */
+GDG_DEVI double frac_delay_read_nb(const double *blk, const double *ring, int hs, int pos, int i, double ds)
+{
+    const double early = floor(ds), late = ceil(ds);
+    const double se = hist_or_block_nb(blk, ring, hs, pos, i - (int)early);
+    const double sl = hist_or_block_nb(blk, ring, hs, pos, i - (int)late);
+    const double we = 1.0 - (ds - early), wl = 1.0 - (late - ds);
+    return (we * se) + (wl * sl);
+}
+
 /* delay (effects/delay.go:17-91): i[0] delaySamples (= ring size); p[0] feedbackFac p[1] levelFac */
 GDG_DEV void stage_delay(gdg_ctx &cx, const gdg_unit_desc &d_global)
 {
@@ -779,12 +793,13 @@ GDG_DEV void stage_chorus(gdg_ctx &cx, const gdg_unit_desc &d_global)
         for (int k = tid; k < n; k += GDG_NT) {
             const double t = (double)k / sr;
             const double zero_phase = fmod(GDG_MULADD_RN(ang, t, prev), GDG_TWO_PI);
-            const double s0 = sin(zero_phase), c0 = cos(zero_phase);
+            double s0, c0;
+            GDG_SINCOS(zero_phase, &s0, &c0);          /* one argument reduction for both */
             double eff = 0.0;
             for (int j = 0; j < 5; j++) {
                 const double offset = depth * ((s0 * cj[j]) + (c0 * sj[j]));
                 const double dsmp = (0.001 * (40.0 + offset)) * sr;
-                eff += 0.2 * frac_delay_read(x, ring, hs, pos, k, dsmp);
+                eff += 0.2 * frac_delay_read_nb(x, ring, hs, pos, k, dsmp);
             }
             y[sw(k)] = (0.5 * x[sw(k)]) + (0.5 * eff);
         }

@@ -473,8 +473,17 @@ GDG_DEV void stage_reverb(gdg_ctx &cx, const gdg_unit_desc &d_global)
     double *x = SM_CUR(cx), *w = SM_ALT(cx), *P = SM_S, *st = d.st;
     double *lring = st + GDG_RV_ST_DATA;
     const double g = d.p[6];
-    /* delay line taps -> w */
+    /* delay line taps -> w.  The first (longest) all-pass's carried history - up to 63 KB from its ring in HBM - is requested
+     * here with asynchronous copies into P, which nobody touches until the all-pass rounds start: its latency hides behind
+     * the tap gathers. */
     GDG_THREADS_BEGIN
+        {
+            const int lag0 = d.i[5] - 1, nh0 = imin(lag0, n);
+            const double *ring0 = st + d.i[8];
+            const int w00 = (int)st_geti(st, GDG_RV_ST_APPTR + 0);
+#pragma unroll 4
+            for (int k = tid; k < nh0; k += GDG_NT) { int p = w00 + k; if (p >= lag0) p -= lag0; async_copy8(P + k, ring0 + p); }
+        }
         const int pos = (int)st_geti(st, GDG_RV_ST_LINEPOS);
         const int t0 = d.i[1], t1 = d.i[2], t2 = d.i[3], t3 = d.i[4];
         const double c0 = d.p[2], c1 = d.p[3], c2 = d.p[4], c3 = d.p[5];
@@ -513,8 +522,11 @@ GDG_DEV void stage_reverb(gdg_ctx &cx, const gdg_unit_desc &d_global)
         const int nh = imin(lag, n);
         GDG_THREADS_BEGIN
             if (a == 0 && tid == 0) { const int pos = (int)st_geti(st, GDG_RV_ST_LINEPOS); st_seti(st, GDG_RV_ST_LINEPOS, n >= hs ? 0 : (pos + n) % hs); }
+            if (a == 0) async_wait();                            /* requested at the top of the stage; each thread asked for the cells it owns here */
+            else {
 #pragma unroll 4
-            for (int k = tid; k < nh; k += GDG_NT) { int p = w0 + k; if (p >= lag) p -= lag; P[k] = GDG_LDST(ring + p); }
+                for (int k = tid; k < nh; k += GDG_NT) { int p = w0 + k; if (p >= lag) p -= lag; P[k] = GDG_LDST(ring + p); }
+            }
         GDG_THREADS_END
         for (int r0 = 0; r0 < n; r0 += lag) {
             const int r1 = imin(n, r0 + lag);
