@@ -508,8 +508,68 @@ GDG_DEVI double onepole_out(int highpass, double xin, double &v, double k)
     return out;
 }
 
+/* The same cascade for full chunks whose length is a multiple of 4 (every block of >= 4 GDG_NT samples): a thread walks its
+ * chunk as FOUR sub-chunks in parallel - four independent recurrence chains instead of one four times as long - because these
+ * replays are bound by the dependent-issue latency of the FP64 pipe (8.3 cycles per step, tools/fp64_lat.cu), not by its
+ * rate.  The sub-chunk maps are folded into the thread's map for the block scan; the carry into sub-chunk j is the carry into
+ * j-1 pushed through j-1's map. */
+GDG_DEV void stage_cascade_sub4(gdg_ctx &cx, const gdg_unit_desc &d_global, int nsec, int nhp)
+{
+    const gdg_unit_desc &d = GDG_DESC; (void)d_global;
+    const int n = cx.n, S = chunk_len(n), Ls = S / 4;
+    double *x = SM_CUR(cx), *st = d.st;
+    GDG_REGA(double, a, 1); GDG_REGA(double, b, 1); GDG_REGA(double, cin, 1); GDG_REGA(double, bs, 4);
+    GDG_THREADS_BEGIN
+        const int k0 = tid * S;
+        double v[4] = {0.0, 0.0, 0.0, 0.0};
+        const double k1 = d.p[0];
+#pragma unroll 1
+        for (int i = 0; i < Ls; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) v[j] += (x[sw(k0 + j * Ls + i)] - v[j]) * k1;
+#pragma unroll
+        for (int j = 0; j < 4; j++) R(bs)[j] = v[j];
+    GDG_THREADS_END_NOSYNC
+    for (int s = 0; s < nsec; s++) {
+        const double astep = 1.0 - d.p[s], asub = pow_int(astep, Ls), afull = pow_int(asub, 4);
+        const double init[1] = {st[s]};
+        GDG_THREADS_BEGIN
+            double B = R(bs)[0];
+#pragma unroll
+            for (int j = 1; j < 4; j++) B = (asub * B) + R(bs)[j];
+            R(a)[0] = afull; R(b)[0] = B;
+        GDG_THREADS_END_NOSYNC
+        GDG_SCAN(1, cx, 0, a, b, init, cin);
+        const int last = (s == nsec - 1);
+        GDG_THREADS_BEGIN
+            const int k0 = tid * S;
+            double v[4], w[4] = {0.0, 0.0, 0.0, 0.0};
+            v[0] = R(cin)[0];
+#pragma unroll
+            for (int j = 1; j < 4; j++) v[j] = (asub * v[j - 1]) + R(bs)[j - 1];
+            const double kk = d.p[s], kn = last ? 0.0 : d.p[s + 1];
+            const int hp = s < nhp;
+#pragma unroll 1
+            for (int i = 0; i < Ls; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int at = sw(k0 + j * Ls + i);
+                    double y = onepole_out(hp, x[at], v[j], kk);
+                    if (last) y = clamp1(y); else w[j] += (y - w[j]) * kn;
+                    x[at] = y;
+                }
+#pragma unroll
+            for (int j = 0; j < 4; j++) R(bs)[j] = w[j];
+            if (k0 + S == n) st[s] = v[3];
+        GDG_THREADS_END_NOSYNC
+    }
+    GDG_THREADS_BEGIN
+    GDG_THREADS_END
+}
+
 GDG_DEV void stage_cascade(gdg_ctx &cx, const gdg_unit_desc &d_global, int nsec, int nhp)
 {
+    if (cx.n % (4 * GDG_NT) == 0) { stage_cascade_sub4(cx, d_global, nsec, nhp); return; }
     const gdg_unit_desc &d = GDG_DESC; (void)d_global;
     const int n = cx.n, S = chunk_len(n);
     double *x = SM_CUR(cx), *st = d.st;
