@@ -604,6 +604,9 @@ struct gdg_chain {
     std::vector<gdg_chain_desc *> d_desc; std::vector<gdg_chain_desc> h_desc; std::vector<int> seg_kind;
     bool topo_dirty = true;
     bool uploaded = false;                                      /* set when prepare() touched device memory */
+    /* nothing was edited since the last prepare() at this rate and block length: the per-unit parameter resolution (string
+     * look-ups) is skipped - with thousands of chains per block that walk is what bounds the host */
+    bool clean = false; uint32_t clean_rate = 0; size_t clean_n = 0;
     double *d_in = nullptr, *d_out = nullptr; size_t d_n = 0;   /* single-channel staging for gdg_chain_process */
     struct Batch *self = nullptr;                               /* one-chain launch tables of gdg_chain_process */
     ~gdg_chain();
@@ -614,6 +617,13 @@ struct gdg_chain {
     }
     /* bring the device descriptors up to date; returns number of segments or -1 */
     int prepare(uint32_t rate, size_t n)
+    {
+        if (clean && clean_rate == rate && clean_n == n && !h_desc.empty()) return (int)h_desc.size();
+        const int r_ = prepare_units(rate, n);
+        if (r_ > 0) { clean = true; clean_rate = rate; clean_n = n; }
+        return r_;
+    }
+    int prepare_units(uint32_t rate, size_t n)
     {
         bool changed = topo_dirty;
         std::vector<Unit *> active;
@@ -1330,6 +1340,7 @@ void gdg_chain_destroy(gdg_chain *c)
 int gdg_chain_append_unit(gdg_chain *c, int type)
 {
     EditLock lk(g_edit_mutex);
+    if (c) c->clean = false;
     if (!c) { fail("chain is NULL"); return -1; }
     Use use_ctx_(c->ctx);
     Unit *u = create_unit(type, c->bank);
@@ -1341,6 +1352,7 @@ int gdg_chain_append_unit(gdg_chain *c, int type)
 int gdg_chain_remove_unit(gdg_chain *c, int id)
 {
     EditLock lk(g_edit_mutex);
+    if (c) c->clean = false;
     CHAIN_CHECK(c);
     if (id < 0 || id >= (int)c->slots.size()) return fail("Cannot remove unit %d.", id);
     gdgb_sync();
@@ -1350,6 +1362,7 @@ int gdg_chain_remove_unit(gdg_chain *c, int id)
 int gdg_chain_move_up(gdg_chain *c, int id)
 {
     EditLock lk(g_edit_mutex);
+    if (c) c->clean = false;
     CHAIN_CHECK(c);
     if (id <= 0 || id >= (int)c->slots.size()) return fail("Cannot move unit %d up.", id);
     std::swap(c->slots[id], c->slots[id - 1]); c->topo_dirty = true;
@@ -1358,6 +1371,7 @@ int gdg_chain_move_up(gdg_chain *c, int id)
 int gdg_chain_move_down(gdg_chain *c, int id)
 {
     EditLock lk(g_edit_mutex);
+    if (c) c->clean = false;
     CHAIN_CHECK(c);
     if (id < 0 || id >= (int)c->slots.size() - 1) return fail("Cannot move unit %d down.", id);
     std::swap(c->slots[id], c->slots[id + 1]); c->topo_dirty = true;
@@ -1374,6 +1388,7 @@ int gdg_chain_unit_type(gdg_chain *c, int id)
 int gdg_chain_set_bypass(gdg_chain *c, int id, int bypass)
 {
     EditLock lk(g_edit_mutex);
+    if (c) c->clean = false;
     CHAIN_CHECK(c);
     if (id < 0 || id >= (int)c->slots.size()) return fail("Cannot %s bypass: No unit %d.", bypass ? "enable" : "disable", id);
     if (c->slots[id].bypass != (bypass != 0)) { c->slots[id].bypass = bypass != 0; c->topo_dirty = true; }
@@ -1390,6 +1405,7 @@ int gdg_chain_get_bypass(gdg_chain *c, int id, int *bypass)
 int gdg_chain_set_discrete_value(gdg_chain *c, int id, const char *name, const char *value)
 {
     EditLock lk(g_edit_mutex);
+    if (c) c->clean = false;
     CHAIN_CHECK(c);
     if (id < 0 || id >= (int)c->slots.size()) return fail("Cannot set discrete value: No unit %d.", id);
     Unit *u = c->slots[id].unit.get();
@@ -1419,6 +1435,7 @@ int gdg_chain_get_discrete_value(gdg_chain *c, int id, const char *name, const c
 int gdg_chain_set_numeric_value(gdg_chain *c, int id, const char *name, int32_t value)
 {
     EditLock lk(g_edit_mutex);
+    if (c) c->clean = false;
     CHAIN_CHECK(c);
     if (id < 0 || id >= (int)c->slots.size()) return fail("Cannot set numeric value: No unit %d.", id);
     Unit *u = c->slots[id].unit.get();
