@@ -495,22 +495,25 @@ def main():
             except Exception as e:
                 extras["weak_scaling"] = {"error": str(e)}
 
-    # ---- extra: the SAME N GPUs driven by ONE process through gdg_cluster_* (what a Go host would do: no torch.distributed,
-    # no NCCL; the stereo master is summed on device 0 by one kernel reading the other devices over NVLink peer addresses).
-    # Rank 0 drives every GPU while the other ranks wait at the barrier. ----
-    if world > 1 and not args.no_extras:
-        barrier()
-        if rank == 0:
-            try:
-                extras["single_process_cluster"] = cluster_extra(torch, gdg, presets, lib, world, xsteps)
-            except Exception as e:
-                extras["single_process_cluster"] = {"error": "%s: %s" % (type(e).__name__, e)}
-        barrier()
-
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         os.sched_setaffinity(0, all_cpus)                        # the CPU baseline gets every host core
         cpu_baseline = cpu_baseline_record(5)
+
+    # ---- extra: the SAME N GPUs driven by ONE process through gdg_cluster_* (what a Go host would do: no torch.distributed,
+    # no NCCL; the stereo master is summed on device 0 by one kernel reading the other devices over NVLink peer addresses).
+    # Measured by rank 0 AFTER the other ranks have left (their CUDA contexts would share the GPUs with it otherwise). ----
+    if world > 1:
+        barrier()
+        dist.destroy_process_group()
+        if rank != 0:
+            return
+        if not args.no_extras:
+            time.sleep(4.0)                                       # the other ranks tear their contexts down
+            try:
+                extras["single_process_cluster"] = cluster_extra(torch, gdg, presets, lib, world, xsteps)
+            except Exception as e:
+                extras["single_process_cluster"] = {"error": "%s: %s" % (type(e).__name__, e)}
 
     if rank == 0:
         print(json.dumps({
@@ -536,8 +539,6 @@ def main():
                          "fp64": {"achieved_tflops": tfl, "peak_tflops": FP64_PEAK_TFLOPS, "frac": tfl / FP64_PEAK_TFLOPS,
                                   "flop_per_sample": ALGO_FLOP_PER_SAMPLE, "peak_kind": "measured (tools/fp64_peak.cu)"}},
             "cpu_baseline": cpu_baseline, "extras": extras}))
-    if world > 1:
-        dist.destroy_process_group()
 
 
 def cluster_extra(torch, gdg, presets, lib, ndev, steps):
