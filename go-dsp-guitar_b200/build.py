@@ -33,6 +33,7 @@ def build(force=False, verbose=False):
            "-Xcompiler", "-fPIC,-O2,-Wall", "-shared", "-o", OUT]
     if verbose:
         cmd += ["-Xptxas", "-v"]
+    cmd += os.environ.get("GDG_NVCC_EXTRA", "").split()           # development: -D overrides of the launch-shape constants
     cmd += [os.path.join(CSRC, f) for f in SOURCES]
     cmd += ["-lcudart"]
     print(" ".join(cmd), flush=True)

@@ -752,9 +752,10 @@ size_t fmt_bytes(int fmt) { static const size_t b[6] = {1, 2, 3, 4, 4, 8}; retur
 /* launch channels [c0, c0 + cnt) of prepared batch `b`; strides in bytes, samples in the given formats.  Round r of channel
  * c reads the caller's input rows when r == 0 and the float64 rows of the previous round otherwise, and writes the caller's
  * output rows when it is the channel's LAST segment, float64 rows otherwise.  With float64 I/O the in-between rows are the
- * output rows themselves; encoded calls with more than one round keep them in a scratch buffer. */
+ * output rows themselves; encoded calls with more than one round keep them in a scratch buffer.
+ * d_side: optional float64 rows (stride n) that receive a copy of an encoded result. */
 int launch_tables(Batch &b, size_t c0, size_t cnt, int rounds, const void *d_in, size_t in_stride, int in_fmt,
-                  void *d_out, size_t out_stride, int out_fmt, size_t n, void *stream)
+                  void *d_out, size_t out_stride, int out_fmt, size_t n, void *stream, double *d_side = nullptr)
 {
     unsigned char *mid = (unsigned char *)d_out; size_t mid_stride = out_stride;
     if (rounds > 1 && out_fmt != GDG_FMT_IEEE64) {
@@ -775,15 +776,15 @@ int launch_tables(Batch &b, size_t c0, size_t cnt, int rounds, const void *d_in,
             if (gdgb_launch_segments(k, b.d_ptrs[t] + c0, b.d_nseg + c0, r, (int)cnt,
                                      (const unsigned char *)d_in + c0 * in_stride, (long)in_stride, in_fmt,
                                      (unsigned char *)d_out + c0 * out_stride, (long)out_stride, out_fmt,
-                                     mid + c0 * mid_stride, (long)mid_stride, (int)n, stream))
+                                     mid + c0 * mid_stride, (long)mid_stride, d_side ? d_side + c0 * n : nullptr, (long)n, (int)n, stream))
                 return backend_fail("chain kernel launch failed");
         }
     return 0;
 }
 int launch_batch_fmt(size_t c0, size_t cnt, int rounds, const void *d_in, size_t in_stride, int in_fmt,
-                     void *d_out, size_t out_stride, int out_fmt, size_t n, void *stream)
+                     void *d_out, size_t out_stride, int out_fmt, size_t n, void *stream, double *d_side = nullptr)
 {
-    return launch_tables(*g_batch, c0, cnt, rounds, d_in, in_stride, in_fmt, d_out, out_stride, out_fmt, n, stream);
+    return launch_tables(*g_batch, c0, cnt, rounds, d_in, in_stride, in_fmt, d_out, out_stride, out_fmt, n, stream, d_side);
 }
 int launch_batch(size_t c0, size_t cnt, int rounds, const double *d_in, double *d_out, size_t stride, size_t n, void *stream)
 {
@@ -997,10 +998,14 @@ int block_submit(int si, gdg_chain *const *chains, size_t C, gdg_tuner *tuner, i
     Batch::Slot &b = g_batch->slot[si];
     const int ev = si * 28;
     const size_t ib = n * fmt_bytes(in_fmt), ob = n * fmt_bytes(out_fmt);      /* bytes per host row */
-    /* tuner, spatializer and meter read float64 rows: with encoded host rows and any of them present the payload is
-     * converted by a small kernel on either side of the float64 path instead of inside the chain kernel */
-    const bool recode = (tuner || spat || meter) && (in_fmt != GDG_FMT_IEEE64 || out_fmt != GDG_FMT_IEEE64);
-    const int kin = recode ? GDG_FMT_IEEE64 : in_fmt, kout = recode ? GDG_FMT_IEEE64 : out_fmt;   /* formats the chain kernel sees */
+    /* Encoded host rows are decoded / encoded inside the segment kernels.  Tuner, spatializer and meter read float64 rows:
+     * the last segment stores a float64 copy of its result beside the encoded one (d_side), the tuner's single input row is
+     * decoded on its own, and only a level meter (which reads EVERY input row) has the whole input payload converted first. */
+    const bool aux = tuner || spat || meter;
+    const bool enc_in = aux && in_fmt != GDG_FMT_IEEE64, enc_out = aux && out_fmt != GDG_FMT_IEEE64;
+    const bool dec_in = enc_in && meter;
+    const bool recode = enc_in || enc_out;
+    const int kin = dec_in ? GDG_FMT_IEEE64 : in_fmt, kout = out_fmt;             /* formats the chain kernels see */
     const size_t kib = n * fmt_bytes(kin), kob = n * fmt_bytes(kout);
     if (stage_buffers(b, (C + 3) * n)) return -1;                             /* C channel rows + master L/R + metronome */
     if (recode && b.enc_cap < (C + 2) * n) {
@@ -1011,8 +1016,11 @@ int block_submit(int si, gdg_chain *const *chains, size_t C, gdg_tuner *tuner, i
         if (!b.d_enc_in || !b.d_enc_out) return backend_fail("device staging allocation failed");
         b.enc_cap = (C + 2) * n;
     }
-    void *up_dst = recode ? (void *)b.d_enc_in : (void *)b.d_in;
-    const void *down_src = recode ? (const void *)b.d_enc_out : (const void *)b.d_out;
+    void *up_dst = enc_in ? (void *)b.d_enc_in : (void *)b.d_in;
+    const void *k_src = (enc_in && !dec_in) ? (const void *)b.d_enc_in : (const void *)b.d_in;    /* rows the chain kernels read */
+    void *k_dst = enc_out ? (void *)b.d_enc_out : (void *)b.d_out;                                /* ... and write */
+    double *k_side = (enc_out && (spat || meter)) ? b.d_out : nullptr;
+    const void *down_src = k_dst;
     const bool in_direct = contiguous_bytes(in, C, ib) && gdgb_is_pinned(in[0]);
     const bool out_direct = contiguous_bytes((const void *const *)out, n_out_rows, ob) && gdgb_is_pinned(out[0]);
     if ((!in_direct || !out_direct) && ensure_host_stage(b, (C + 2) * n)) return -1;
@@ -1031,15 +1039,17 @@ int block_submit(int si, gdg_chain *const *chains, size_t C, gdg_tuner *tuner, i
         const size_t cnt = std::min(per, C - c0);
         if (upload_rows(b, in, c0, cnt, ib, up_dst, 1)) return -1;
         if (gdgb_record(ev + g % 8, 1) || gdgb_wait(0, ev + g % 8)) return backend_fail("event failed");
-        if (recode && gdgb_convert_rows((const char *)b.d_enc_in + c0 * ib, (long)ib, in_fmt, b.d_in + c0 * n, (long)(n * sizeof(double)), GDG_FMT_IEEE64, (int)cnt, (int)n, s0))
+        if (dec_in && gdgb_convert_rows((const char *)b.d_enc_in + c0 * ib, (long)ib, in_fmt, b.d_in + c0 * n, (long)(n * sizeof(double)), GDG_FMT_IEEE64, (int)cnt, (int)n, s0))
             return backend_fail("payload decode failed");
-        if (tuner && tuner_channel >= 0 && (size_t)tuner_channel >= c0 && (size_t)tuner_channel < c0 + cnt)
-            if (gdg_tuner_process_device(tuner, b.d_in + (size_t)tuner_channel * n, n, rate, s0)) return -1;   /* controller.go:2668-2672 */
+        if (tuner && tuner_channel >= 0 && (size_t)tuner_channel >= c0 && (size_t)tuner_channel < c0 + cnt) {
+            double *row = b.d_in + (size_t)tuner_channel * n;
+            if (enc_in && !dec_in && gdgb_convert_rows((const char *)b.d_enc_in + (size_t)tuner_channel * ib, (long)ib, in_fmt, row, (long)(n * sizeof(double)), GDG_FMT_IEEE64, 1, (int)n, s0))
+                return backend_fail("payload decode failed");
+            if (gdg_tuner_process_device(tuner, row, n, rate, s0)) return -1;                                    /* controller.go:2668-2672 */
+        }
         if (meter && meter_rows(meter, (uint32_t)c0, b.d_in + c0 * n, n, (uint32_t)cnt, n, rate, s0)) return -1;      /* controller.go:2710-2714: inputs */
-        if (launch_batch_fmt(c0, cnt, rounds, b.d_in, kib, kin, b.d_out, kob, kout, n, s0)) return -1;           /* controller.go:2682-2705 */
+        if (launch_batch_fmt(c0, cnt, rounds, k_src, kib, kin, k_dst, kob, kout, n, s0, k_side)) return -1;      /* controller.go:2682-2705 */
         if (meter && meter_rows(meter, (uint32_t)(C + c0), b.d_out + c0 * n, n, (uint32_t)cnt, n, rate, s0)) return -1;   /* outputs */
-        if (recode && gdgb_convert_rows(b.d_out + c0 * n, (long)(n * sizeof(double)), GDG_FMT_IEEE64, (char *)b.d_enc_out + c0 * ob, (long)ob, out_fmt, (int)cnt, (int)n, s0))
-            return backend_fail("payload encode failed");
         if (gdgb_record(ev + 8 + g % 8, 0) || gdgb_wait(2, ev + 8 + g % 8)) return backend_fail("event failed");
         const int r = download_rows(b, out, c0, cnt, ob, down_src, 2);
         if (r < 0) return -1;
@@ -1050,7 +1060,7 @@ int block_submit(int si, gdg_chain *const *chains, size_t C, gdg_tuner *tuner, i
     if (spat) {                                                                                                 /* controller.go:2761 */
         if (gdg_spatializer_process_device(spat, b.d_out, n, (d_metro && metro_master) ? d_metro : nullptr, b.d_out + C * n, n, n, 0, s0)) return -1;
         if (meter && meter_rows(meter, (uint32_t)(2 * C + 1), b.d_out + C * n, n, 2, n, rate, s0)) return -1;    /* controller.go:2768-2770: master */
-        if (recode && gdgb_convert_rows(b.d_out + C * n, (long)(n * sizeof(double)), GDG_FMT_IEEE64, (char *)b.d_enc_out + C * ob, (long)ob, out_fmt, 2, (int)n, s0))
+        if (enc_out && gdgb_convert_rows(b.d_out + C * n, (long)(n * sizeof(double)), GDG_FMT_IEEE64, (char *)b.d_enc_out + C * ob, (long)ob, out_fmt, 2, (int)n, s0))
             return backend_fail("payload encode failed");
         if (gdgb_record(ev + 16, 0)) return backend_fail("event failed");
         if (partial_master) *partial_master = b.d_out + C * n;

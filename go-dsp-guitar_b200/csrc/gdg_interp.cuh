@@ -228,7 +228,7 @@ GDG_DEV void run_unit(gdg_ctx &cx, const gdg_unit_desc &d, const double *tw)
 }
 
 /* one channel, one block: load -> every slot -> store */
-GDG_DEV void run_chain(double *smem, const gdg_chain_desc *cd, const void *in, int in_fmt, void *out, int out_fmt, int n, const double *tw)
+GDG_DEV void run_chain(double *smem, const gdg_chain_desc *cd, const void *in, int in_fmt, void *out, int out_fmt, double *side, int n, const double *tw)
 {
 #if !defined(__CUDACC__) || defined(GDG_HOST_EMU)
     gdg_smem = smem;
@@ -274,7 +274,8 @@ GDG_DEV void run_chain(double *smem, const gdg_chain_desc *cd, const void *in, i
     }
     GDG_THREADS_BEGIN
         if (out_fmt == GDG_FMT_IEEE64) { for (int k = tid; k < n; k += GDG_NT) ((double *)out)[k] = SM_CUR(cx)[sw(k)]; }
-        else { for (int k = tid; k < n; k += GDG_NT) encode_sample(out_fmt, (unsigned char *)out, k, SM_CUR(cx)[sw(k)]); }
+        else if (side == nullptr) { for (int k = tid; k < n; k += GDG_NT) encode_sample(out_fmt, (unsigned char *)out, k, SM_CUR(cx)[sw(k)]); }
+        else { for (int k = tid; k < n; k += GDG_NT) { const double v = SM_CUR(cx)[sw(k)]; side[k] = v; encode_sample(out_fmt, (unsigned char *)out, k, v); } }
     GDG_THREADS_END
 }
 

@@ -47,9 +47,10 @@ static int cu_fail(const char *what, cudaError_t e)
 
 /* ---- kernels ------------------------------------------------------------------- */
 /* source / destination rows of channel c in segment round `round` (see gdgb_launch_segments) */
-struct gdg_io { const unsigned char *src; unsigned char *dst; int src_fmt, dst_fmt; };
+struct gdg_io { const unsigned char *src; unsigned char *dst; double *side; int src_fmt, dst_fmt; };
 __device__ __forceinline__ gdg_io segment_io(int c, int round, int nseg, const unsigned char *in, long in_stride, int in_fmt,
-                                             unsigned char *out, long out_stride, int out_fmt, unsigned char *mid, long mid_stride)
+                                             unsigned char *out, long out_stride, int out_fmt, unsigned char *mid, long mid_stride,
+                                             double *side, long side_stride)
 {
     gdg_io io;
     const bool first = round == 0, last = round == nseg - 1;
@@ -57,28 +58,30 @@ __device__ __forceinline__ gdg_io segment_io(int c, int round, int nseg, const u
     io.src_fmt = first ? in_fmt : GDG_FMT_IEEE64;
     io.dst = last ? out + (long)c * out_stride : mid + (long)c * mid_stride;
     io.dst_fmt = last ? out_fmt : GDG_FMT_IEEE64;
+    io.side = (last && side != nullptr && out_fmt != GDG_FMT_IEEE64) ? side + (long)c * side_stride : nullptr;   /* float64 copy of an encoded result */
     return io;
 }
 __global__ void __launch_bounds__(GDG_NT, GDG_MIN_CTAS)
 k_chain(const gdg_chain_desc *const *descs, const int32_t *nseg, int round, const unsigned char *in, long in_stride, int in_fmt,
-        unsigned char *out, long out_stride, int out_fmt, unsigned char *mid, long mid_stride, int n, const double *tw)
+        unsigned char *out, long out_stride, int out_fmt, unsigned char *mid, long mid_stride, double *side, long side_stride, int n,
+        const double *tw)
 {
     const int c = blockIdx.x;
     const gdg_chain_desc *cd = descs[c];
     if (cd == nullptr) return;                             /* this channel's segment of this round runs in the other kernel (or it has none) */
-    const gdg_io io = segment_io(c, round, nseg[c], in, in_stride, in_fmt, out, out_stride, out_fmt, mid, mid_stride);
-    run_chain(gdg_smem, cd, io.src, io.src_fmt, io.dst, io.dst_fmt, n, tw);
+    const gdg_io io = segment_io(c, round, nseg[c], in, in_stride, in_fmt, out, out_stride, out_fmt, mid, mid_stride, side, side_stride);
+    run_chain(gdg_smem, cd, io.src, io.src_fmt, io.dst, io.dst_fmt, io.side, n, tw);
 }
 /* a run of consecutive oversampled units, tile by tile, GDG_OSK_CTAS CTAs per SM (gdg_os.cuh) */
 __global__ void __launch_bounds__(GDG_OSK_NT, GDG_OSK_CTAS)
 k_os(const gdg_chain_desc *const *descs, const int32_t *nseg, int round, const unsigned char *in, long in_stride, int in_fmt,
-     unsigned char *out, long out_stride, int out_fmt, unsigned char *mid, long mid_stride, int n)
+     unsigned char *out, long out_stride, int out_fmt, unsigned char *mid, long mid_stride, double *side, long side_stride, int n)
 {
     const int c = blockIdx.x;
     const gdg_chain_desc *cd = descs[c];
     if (cd == nullptr) return;
-    const gdg_io io = segment_io(c, round, nseg[c], in, in_stride, in_fmt, out, out_stride, out_fmt, mid, mid_stride);
-    run_os(gdg_smem, cd, io.src, io.src_fmt, io.dst, io.dst_fmt, n);
+    const gdg_io io = segment_io(c, round, nseg[c], in, in_stride, in_fmt, out, out_stride, out_fmt, mid, mid_stride, side, side_stride);
+    run_os(gdg_smem, cd, io.src, io.src_fmt, io.dst, io.dst_fmt, io.side, n);
 }
 /* level meter: CTA c meters row c of d_in into state words d_state + 4*c */
 __global__ void __launch_bounds__(GDG_NT) k_meter(const double *in, long stride, long n, double f, long long hold, double *state)
@@ -391,14 +394,14 @@ int gdgb_set_tables(const double *aa2, const double *aa4, const double *lz2, con
 
 int gdgb_launch_segments(int kind, const gdg_chain_desc *const *d_descs, const int32_t *d_nseg, int round, int channels,
                          const void *d_in, long in_stride_bytes, int in_fmt, void *d_out, long out_stride_bytes, int out_fmt,
-                         void *d_mid, long mid_stride_bytes, int n, void *stream)
+                         void *d_mid, long mid_stride_bytes, double *d_side, long side_stride, int n, void *stream)
 {
     if (kind == 0)
         k_chain<<<channels, GDG_NT, GDG_SMEM_BYTES, (cudaStream_t)stream>>>(d_descs, d_nseg, round, (const unsigned char *)d_in, in_stride_bytes, in_fmt,
-                                                                          (unsigned char *)d_out, out_stride_bytes, out_fmt, (unsigned char *)d_mid, mid_stride_bytes, n, g_d_tw);
+                                                                          (unsigned char *)d_out, out_stride_bytes, out_fmt, (unsigned char *)d_mid, mid_stride_bytes, d_side, side_stride, n, g_d_tw);
     else
         k_os<<<channels, GDG_OSK_NT, GDG_OSK_SMEM_BYTES, (cudaStream_t)stream>>>(d_descs, d_nseg, round, (const unsigned char *)d_in, in_stride_bytes, in_fmt,
-                                                                               (unsigned char *)d_out, out_stride_bytes, out_fmt, (unsigned char *)d_mid, mid_stride_bytes, n);
+                                                                               (unsigned char *)d_out, out_stride_bytes, out_fmt, (unsigned char *)d_mid, mid_stride_bytes, d_side, side_stride, n);
     g_launches++;
     CU(cudaGetLastError());
     return 0;

@@ -21,11 +21,15 @@
 
 #include "gdg_stages2.cuh"
 
+#ifndef GDG_OSK_NT
 #define GDG_OSK_NT 256                          /* threads per CTA */
+#endif
 #ifndef GDG_OSK_CTAS
 #define GDG_OSK_CTAS 4                          /* resident CTAs per SM the kernel is compiled for */
 #endif
+#ifndef GDG_OSK_TILE
 #define GDG_OSK_TILE 512                        /* base-rate samples per tile */
+#endif
 #define GDG_OSK_MAX_UNITS 6                     /* units per run (longer runs are split by the host) */
 #define GDG_OSK_ZPS (((GDG_ZH + GDG_OSK_TILE + 1) * 9) / 8 + 8)      /* doubles per polyphase array */
 #define GDG_OSK_STASH (4 * (GDG_ZH + 1) + 8)    /* per unit: carried halo of 4 branches + the last 8 inputs */
@@ -278,7 +282,7 @@ GDG_DEVI void osk_dispatch(const gdg_unit_desc &d, const double *xin, double *xo
 }
 
 /* one channel, one block: the whole run */
-GDG_DEV void run_os(double *smem, const gdg_chain_desc *cd, const void *in, int in_fmt, void *out, int out_fmt, int n)
+GDG_DEV void run_os(double *smem, const gdg_chain_desc *cd, const void *in, int in_fmt, void *out, int out_fmt, double *side, int n)
 {
 #if !defined(__CUDACC__) || defined(GDG_HOST_EMU)
     gdg_smem = smem;
@@ -335,7 +339,8 @@ GDG_DEV void run_os(double *smem, const gdg_chain_desc *cd, const void *in, int 
         }
         GDG_THREADS_BEGIN_N(NT)                                   /* xin holds the run's output tile now */
             if (out_fmt == GDG_FMT_IEEE64) { for (int i = tid; i < Tt; i += NT) ((double *)out)[t0 + i] = xin[8 + i]; }
-            else { for (int i = tid; i < Tt; i += NT) encode_sample(out_fmt, (unsigned char *)out, t0 + i, xin[8 + i]); }
+            else if (side == nullptr) { for (int i = tid; i < Tt; i += NT) encode_sample(out_fmt, (unsigned char *)out, t0 + i, xin[8 + i]); }
+            else { for (int i = tid; i < Tt; i += NT) { const double v = xin[8 + i]; side[t0 + i] = v; encode_sample(out_fmt, (unsigned char *)out, t0 + i, v); } }
         GDG_THREADS_END
     }
     /* carried state back to the units' state words */

@@ -94,7 +94,7 @@ int gdgb_set_tables(const double *aa2, const double *aa4, const double *lz2, con
 
 int gdgb_launch_segments(int kind, const gdg_chain_desc *const *descs, const int32_t *nseg, int round, int channels,
                          const void *in, long in_stride, int in_fmt, void *out, long out_stride, int out_fmt,
-                         void *mid, long mid_stride, int n, void *)
+                         void *mid, long mid_stride, double *side, long side_stride, int n, void *)
 {
     std::vector<double> smem(kind == 0 ? GDG_SMEM_DOUBLES : GDG_OSK_SMEM_DOUBLES);
     for (int c = 0; c < channels; c++) {
@@ -103,8 +103,9 @@ int gdgb_launch_segments(int kind, const gdg_chain_desc *const *descs, const int
         const unsigned char *src = first ? (const unsigned char *)in + (long)c * in_stride : (const unsigned char *)mid + (long)c * mid_stride;
         unsigned char *dst = last ? (unsigned char *)out + (long)c * out_stride : (unsigned char *)mid + (long)c * mid_stride;
         const int sf = first ? in_fmt : GDG_FMT_IEEE64, df = last ? out_fmt : GDG_FMT_IEEE64;
-        if (kind == 0) run_chain(smem.data(), descs[c], src, sf, dst, df, n, g_tw.data());
-        else run_os(smem.data(), descs[c], src, sf, dst, df, n);
+        double *sd = (last && side && out_fmt != GDG_FMT_IEEE64) ? side + (long)c * side_stride : nullptr;
+        if (kind == 0) run_chain(smem.data(), descs[c], src, sf, dst, df, sd, n, g_tw.data());
+        else run_os(smem.data(), descs[c], src, sf, dst, df, sd, n);
     }
     g_launches++;
     return 0;

@@ -312,10 +312,13 @@ def test_encoded_submit_wait(lib):
             assert outs[k][c].tobytes() == bytes(want[k][c]), (k, c)
 
 
-@pytest.mark.parametrize("fmt", ["PCM16", "PCM24", "IEEE32"])
-def test_controller_submit_encoded(lib, fmt):
+@pytest.mark.parametrize("fmt,aux", [("PCM16", "tsm"), ("PCM24", "tsm"), ("IEEE32", "tsm"), ("PCM16", "s"), ("PCM24", "ts"), ("PCM8", "t"),
+                                     ("PCM32", "sm")])
+def test_controller_submit_encoded(lib, fmt, aux):
     """gdg_controller_submit_encoded: encoded rows in, encoded rows (channels + master pair) out, tuner / spatializer /
-    meter on the float64 in between - byte for byte what decoding, the float64 controller call and encoding give."""
+    meter on the float64 in between - byte for byte what decoding, the float64 controller call and encoding give.
+    aux: which of tuner / spatializer / meter are present (the meter decides whether the input payload is converted ahead of
+    the chain kernels, the spatializer / meter whether the last segment keeps a float64 copy of its result)."""
     import ctypes as Ct
     fs, n, C, blocks = 96000, 2048, 4, 3
     spec = [("overdrive", {"gain": 9}, {"oversampling": "2"}), ("chorus", {}, {}), ("reverb", {"mix": 30}, {})]
@@ -327,17 +330,21 @@ def test_controller_submit_encoded(lib, fmt):
     rm.set_enabled(True); m.set_enabled(True)
     for c in range(C):
         rs.set_azimuth(c, -45.0 + 30.0 * c); s.set_azimuth(c, -45.0 + 30.0 * c)
+    if "t" not in aux: rt = t = None
+    if "s" not in aux: rs = s = None
+    if "m" not in aux: rm = m = None
+    R = C + (2 if s else 0)
     fi = gdg.FORMATS.index(fmt)
     bps = orc.wave_bytes_per_sample(fmt)
     handles = (Ct.c_void_p * C)(*[c._h for c in chains])
     x = np.stack([common.synth_fast(c, fs, blocks * n, 9) for c in range(C)]) * 0.8
     pay = [[np.frombuffer(orc.wave_encode(fmt, x[c, k * n:(k + 1) * n]).tobytes(), dtype=np.uint8).copy() for c in range(C)] for k in range(blocks)]
-    outs = [[np.zeros(n * bps, dtype=np.uint8) for _ in range(C + 2)] for _ in range(blocks)]
+    outs = [[np.zeros(n * bps, dtype=np.uint8) for _ in range(R)] for _ in range(blocks)]
     prev = None
     for k in range(blocks):
         ip = (Ct.c_void_p * C)(*[r.ctypes.data for r in pay[k]])
-        op = (Ct.c_void_p * (C + 2))(*[r.ctypes.data for r in outs[k]])
-        tk = lib.gdg_controller_submit_encoded(handles, C, t._h, 2, s._h, m._h, ip, fi, op, fi, C + 2, n, fs)
+        op = (Ct.c_void_p * R)(*[r.ctypes.data for r in outs[k]])
+        tk = lib.gdg_controller_submit_encoded(handles, C, t._h if t else None, 2, s._h if s else None, m._h if m else None, ip, fi, op, fi, R, n, fs)
         assert tk >= 0, lib.gdg_last_error()
         if prev is not None:
             assert lib.gdg_controller_wait(prev) == 0
@@ -346,10 +353,10 @@ def test_controller_submit_encoded(lib, fmt):
     for k in range(blocks):
         dec = np.stack([orc.wave_decode(fmt, pay[k][c].tobytes()) for c in range(C)])
         y = gdg.controller_process(ref_chains, rt, 2, rs, dec, fs, meter=rm)
-        for c in range(C + 2):
+        for c in range(R):
             assert outs[k][c].tobytes() == orc.wave_encode(fmt, y[c]).tobytes(), (k, c)
-    assert t.analyze() == rt.analyze()
-    for c in (0, C, 2 * C + 1, 2 * C + 2):
+    if t: assert t.analyze() == rt.analyze()
+    for c in (0, C, 2 * C + 1, 2 * C + 2) if m else ():
         assert m.state(c) == rm.state(c)
 
 
