@@ -45,10 +45,13 @@ int gdgb_sync(void);
  * a small pool of events orders them.  Copies are truly asynchronous only for page-locked host memory. */
 #define GDGB_EVENTS 64
 void *gdgb_stream_handle(int stream);
+#define GDGB_SIDE_STREAMS 3
+void *gdgb_side_stream(int i);                         /* kernel streams beside the caller's: channel ranges of one batch run concurrently */
 int gdgb_h2d_async(void *dst, const void *src, size_t bytes, int stream);
 int gdgb_d2h_async(void *dst, const void *src, size_t bytes, int stream);
 int gdgb_record(int event, int stream);
 int gdgb_wait(int stream, int event);
+int gdgb_order(void *first, void *then, int event);   /* `then` continues after what `first` holds now */
 int gdgb_sync_stream(int stream);
 int gdgb_sync_event(int event);                 /* host waits for the last record of `event` */
 void *gdgb_pinned_alloc(size_t bytes);

@@ -798,6 +798,22 @@ int run_batch_device(gdg_chain *const *chains, size_t C, const double *d_in, dou
     std::lock_guard<std::mutex> lk(g_batch_mutex);
     const int rounds = prepare_batch(chains, C, rate, n, stream);
     if (rounds < 0) return -1;
+    /* Two halves of the channels on two kernel streams: the tail of one half's kernel (CTAs of the last wave, the 1.7 waves of
+     * the oversampled-run kernel) overlaps the next kernel of the other half (measured -3 % per CHAIN12 pass; 3 and 4 ways
+     * are no better).  The caller's stream is forked and joined inside this call, so its ordering is unchanged. */
+    static const long ways_env = getenv("GDG_WAYS") ? atol(getenv("GDG_WAYS")) : 0;    /* tuning knob */
+    const size_t ways = ways_env > 0 ? std::min<size_t>((size_t)ways_env, 1 + GDGB_SIDE_STREAMS)
+                                     : (C >= 2 * (size_t)std::max(1, gdgb_sm_count()) ? 2 : 1);
+    if (ways > 1 && C >= 2 * ways) {
+        const size_t per = (C + ways - 1) / ways;
+        for (size_t w = 1; w < ways; w++) if (gdgb_order(stream, gdgb_side_stream((int)w - 1), 56 + (int)w)) return backend_fail("event failed");
+        for (size_t w = 0; w < ways; w++) {
+            const size_t c0 = w * per, cnt = std::min(per, C - c0);
+            if (launch_batch(c0, cnt, rounds, d_in, d_out, stride, n, w ? gdgb_side_stream((int)w - 1) : stream)) return -1;
+        }
+        for (size_t w = 1; w < ways; w++) if (gdgb_order(gdgb_side_stream((int)w - 1), stream, 59 + (int)w)) return backend_fail("event failed");
+        return 0;
+    }
     return launch_batch(0, C, rounds, d_in, d_out, stride, n, stream);
 }
 
@@ -1033,28 +1049,34 @@ int block_submit(int si, gdg_chain *const *chains, size_t C, gdg_tuner *tuner, i
         d_metro = b.d_in + (C + 2) * n;
         if (gdgb_h2d_async(d_metro, metronome, n * sizeof(double), 1) || gdgb_record(ev + 18, 1)) return backend_fail("metronome upload failed");
     }
+    /* groups alternate between the kernel stream and a side stream (forked here, joined after the loop): the kernels of
+     * neighbouring groups overlap each other's tails, see run_batch_device */
+    void *side = G > 1 ? gdgb_side_stream(0) : s0;
+    if (G > 1 && gdgb_order(s0, side, ev + 19)) return backend_fail("event failed");
     for (int g = 0; g < G; g++) {
         const size_t c0 = (size_t)g * per;
         if (c0 >= C) break;
         const size_t cnt = std::min(per, C - c0);
+        void *ks = (g & 1) ? side : s0;                                         /* odd groups run beside the even ones */
         if (upload_rows(b, in, c0, cnt, ib, up_dst, 1)) return -1;
-        if (gdgb_record(ev + g % 8, 1) || gdgb_wait(0, ev + g % 8)) return backend_fail("event failed");
-        if (dec_in && gdgb_convert_rows((const char *)b.d_enc_in + c0 * ib, (long)ib, in_fmt, b.d_in + c0 * n, (long)(n * sizeof(double)), GDG_FMT_IEEE64, (int)cnt, (int)n, s0))
+        if (gdgb_order(gdgb_stream_handle(1), ks, ev + g % 8)) return backend_fail("event failed");
+        if (dec_in && gdgb_convert_rows((const char *)b.d_enc_in + c0 * ib, (long)ib, in_fmt, b.d_in + c0 * n, (long)(n * sizeof(double)), GDG_FMT_IEEE64, (int)cnt, (int)n, ks))
             return backend_fail("payload decode failed");
         if (tuner && tuner_channel >= 0 && (size_t)tuner_channel >= c0 && (size_t)tuner_channel < c0 + cnt) {
             double *row = b.d_in + (size_t)tuner_channel * n;
-            if (enc_in && !dec_in && gdgb_convert_rows((const char *)b.d_enc_in + (size_t)tuner_channel * ib, (long)ib, in_fmt, row, (long)(n * sizeof(double)), GDG_FMT_IEEE64, 1, (int)n, s0))
+            if (enc_in && !dec_in && gdgb_convert_rows((const char *)b.d_enc_in + (size_t)tuner_channel * ib, (long)ib, in_fmt, row, (long)(n * sizeof(double)), GDG_FMT_IEEE64, 1, (int)n, ks))
                 return backend_fail("payload decode failed");
-            if (gdg_tuner_process_device(tuner, row, n, rate, s0)) return -1;                                    /* controller.go:2668-2672 */
+            if (gdg_tuner_process_device(tuner, row, n, rate, ks)) return -1;                                    /* controller.go:2668-2672 */
         }
-        if (meter && meter_rows(meter, (uint32_t)c0, b.d_in + c0 * n, n, (uint32_t)cnt, n, rate, s0)) return -1;      /* controller.go:2710-2714: inputs */
-        if (launch_batch_fmt(c0, cnt, rounds, k_src, kib, kin, k_dst, kob, kout, n, s0, k_side)) return -1;      /* controller.go:2682-2705 */
-        if (meter && meter_rows(meter, (uint32_t)(C + c0), b.d_out + c0 * n, n, (uint32_t)cnt, n, rate, s0)) return -1;   /* outputs */
-        if (gdgb_record(ev + 8 + g % 8, 0) || gdgb_wait(2, ev + 8 + g % 8)) return backend_fail("event failed");
+        if (meter && meter_rows(meter, (uint32_t)c0, b.d_in + c0 * n, n, (uint32_t)cnt, n, rate, ks)) return -1;      /* controller.go:2710-2714: inputs */
+        if (launch_batch_fmt(c0, cnt, rounds, k_src, kib, kin, k_dst, kob, kout, n, ks, k_side)) return -1;      /* controller.go:2682-2705 */
+        if (meter && meter_rows(meter, (uint32_t)(C + c0), b.d_out + c0 * n, n, (uint32_t)cnt, n, rate, ks)) return -1;   /* outputs */
+        if (gdgb_order(ks, gdgb_stream_handle(2), ev + 8 + g % 8)) return backend_fail("event failed");
         const int r = download_rows(b, out, c0, cnt, ob, down_src, 2);
         if (r < 0) return -1;
         if (r == 1) b.staged.push_back({c0, cnt});
     }
+    if (G > 1 && gdgb_order(side, s0, ev + 20)) return backend_fail("event failed");
     if (d_metro && gdgb_wait(0, ev + 18)) return backend_fail("stream wait failed");
     if (d_metro && meter && meter_rows(meter, (uint32_t)(2 * C), d_metro, n, 1, n, rate, s0)) return -1;        /* controller.go:2735-2738: the metronome port */
     if (spat) {                                                                                                 /* controller.go:2761 */

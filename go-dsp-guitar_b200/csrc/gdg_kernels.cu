@@ -21,7 +21,7 @@ static thread_local std::string t_err;
  * tables.  Context 0 is the device of gdgb_init(); a thread works on the context it selected last (default 0). */
 struct DevCtx {
     int device = -1, sms = 0;
-    cudaStream_t stream = nullptr, copy[2] = {nullptr, nullptr};
+    cudaStream_t stream = nullptr, copy[2] = {nullptr, nullptr}, side[GDGB_SIDE_STREAMS] = {};
     cudaEvent_t events[GDGB_EVENTS];
     double *d_tw = nullptr;
 };
@@ -268,6 +268,7 @@ static int open_context(int slot, int device)
     c.device = device; c.sms = prop.multiProcessorCount;
     CU(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
     for (int i = 0; i < 2; i++) CU(cudaStreamCreateWithFlags(&c.copy[i], cudaStreamNonBlocking));
+    for (int i = 0; i < GDGB_SIDE_STREAMS; i++) CU(cudaStreamCreateWithFlags(&c.side[i], cudaStreamNonBlocking));
     for (int i = 0; i < GDGB_EVENTS; i++) CU(cudaEventCreateWithFlags(&c.events[i], cudaEventDisableTiming));
     CU(cudaFuncSetAttribute(k_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, GDG_SMEM_BYTES));
     CU(cudaFuncSetAttribute(k_ir_partition_spectra, cudaFuncAttributeMaxDynamicSharedMemorySize, GDG_SMEM_BYTES));
@@ -370,10 +371,18 @@ int gdgb_copy_on(void *dst, const void *src, size_t bytes, void *stream) { if (b
 int gdgb_sync(void) { if (g_stream) CU(cudaStreamSynchronize(g_stream)); return 0; }
 static cudaStream_t stream_of(int s) { return s == 0 ? g_stream : g_copy_streams[(s - 1) & 1]; }
 void *gdgb_stream_handle(int s) { return (void *)stream_of(s); }
+void *gdgb_side_stream(int i) { return (void *)CX.side[i % GDGB_SIDE_STREAMS]; }
 int gdgb_h2d_async(void *dst, const void *src, size_t bytes, int s) { if (bytes) CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream_of(s))); return 0; }
 int gdgb_d2h_async(void *dst, const void *src, size_t bytes, int s) { if (bytes) CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, stream_of(s))); return 0; }
 int gdgb_record(int ev, int s) { CU(cudaEventRecord(g_events[ev % GDGB_EVENTS], stream_of(s))); return 0; }
 int gdgb_wait(int s, int ev) { CU(cudaStreamWaitEvent(stream_of(s), g_events[ev % GDGB_EVENTS], 0)); return 0; }
+/* everything enqueued on `then` after this call runs after what `first` holds now (event id: one of the pool) */
+int gdgb_order(void *first, void *then, int ev)
+{
+    CU(cudaEventRecord(g_events[ev % GDGB_EVENTS], (cudaStream_t)first));
+    CU(cudaStreamWaitEvent((cudaStream_t)then, g_events[ev % GDGB_EVENTS], 0));
+    return 0;
+}
 int gdgb_sync_stream(int s) { CU(cudaStreamSynchronize(stream_of(s))); return 0; }
 int gdgb_sync_event(int ev) { CU(cudaEventSynchronize(g_events[ev % GDGB_EVENTS])); return 0; }
 void *gdgb_pinned_alloc(size_t bytes) { void *p = nullptr; if (cudaMallocHost(&p, bytes ? bytes : 8) != cudaSuccess) return nullptr; return p; }

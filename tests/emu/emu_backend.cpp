@@ -72,9 +72,11 @@ int gdgb_copy(void *d, const void *s, size_t b) { memmove(d, s, b); return 0; }
 int gdgb_copy_on(void *d, const void *s, size_t b, void *) { memmove(d, s, b); return 0; }
 int gdgb_sync(void) { return 0; }
 void *gdgb_stream_handle(int) { return nullptr; }
+void *gdgb_side_stream(int) { return nullptr; }
 int gdgb_h2d_async(void *d, const void *s, size_t b, int) { memcpy(d, s, b); return 0; }
 int gdgb_d2h_async(void *d, const void *s, size_t b, int) { memcpy(d, s, b); return 0; }
 int gdgb_record(int, int) { return 0; }
+int gdgb_order(void *, void *, int) { return 0; }
 int gdgb_wait(int, int) { return 0; }
 int gdgb_sync_stream(int) { return 0; }
 int gdgb_sync_event(int) { return 0; }
