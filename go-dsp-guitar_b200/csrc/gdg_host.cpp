@@ -819,16 +819,20 @@ int run_batch_device(gdg_chain *const *chains, size_t C, const double *d_in, dou
 
 /* Host-buffer pipeline: channels are cut into groups; H2D of group g+1, the kernel of group g and D2H of
  * group g-1 overlap on three streams.  `extra_out` rows (spatializer master) follow the channel rows. */
-size_t pipeline_group_size(size_t C)
+size_t pipeline_group_size(size_t C, bool blocking)
 {
     static const long forced = getenv("GDG_PIPE_GROUP") ? atol(getenv("GDG_PIPE_GROUP")) : 0;   /* tuning knob */
     if (forced > 0) return (size_t)forced;
-    if (C < 64) return C;
-    /* a group = four CTA-per-SM waves of the chain kernel = one full wave of the oversampled-run kernel (4 CTAs per SM):
-     * smaller groups would run k_os at a quarter of its occupancy */
+    /* An EVEN number of equal groups (they alternate between two kernel streams, block_submit), each at most four
+     * CTA-per-SM waves of the chain kernel = one full wave of the oversampled-run kernel (smaller groups run k_os below its
+     * occupancy).  A blocking call has nothing else in flight to hide its first upload and last download behind, so it cuts
+     * finer (two waves).  Measured at 1024 channels, Msamples/s e2e submit/wait | blocking call:
+     *   groups of 1024: 3639 | 1858,  592 + 432: 3820 | 2380,  2 x 512: 3940 | 2332,  4 x 256: 3598 | 2620. */
     const size_t sms = (size_t)std::max(1, gdgb_sm_count());
-    const size_t wave = 4 * sms;
-    return C >= wave + wave / 2 ? wave : C;
+    if (C < 2 * sms) return C;
+    const size_t target = (blocking ? 2 : 4) * sms;
+    const size_t G = 2 * ((C + 2 * target - 1) / (2 * target));
+    return (C + G - 1) / G;
 }
 
 bool contiguous(const double *const *p, size_t C, size_t n)
@@ -1005,7 +1009,7 @@ int meter_rows(gdg_meter *m, uint32_t first, const double *d_rows, size_t stride
  * Event ids: slot*28 + {0..7 uploads, 8..15 kernels, 16 spatializer, 17 all downloads, 18 metronome upload}. */
 int block_submit(int si, gdg_chain *const *chains, size_t C, gdg_tuner *tuner, int tuner_channel, gdg_spatializer *spat, gdg_meter *meter,
                  const void *const *in, int in_fmt, void *const *out, int out_fmt, size_t n_out_rows, size_t n, uint32_t rate,
-                 const double *metronome = nullptr, bool metro_master = false, const double **partial_master = nullptr)
+                 const double *metronome = nullptr, bool metro_master = false, const double **partial_master = nullptr, bool blocking = false)
 {
     /* partial_master != NULL (multi-device blocks): the spatializer's [2][n] result stays on the device (row stride n) and its
      * address is returned; event slot*28 + 16 marks it ready for the device that sums the partial masters */
@@ -1040,7 +1044,7 @@ int block_submit(int si, gdg_chain *const *chains, size_t C, gdg_tuner *tuner, i
     const bool in_direct = contiguous_bytes(in, C, ib) && gdgb_is_pinned(in[0]);
     const bool out_direct = contiguous_bytes((const void *const *)out, n_out_rows, ob) && gdgb_is_pinned(out[0]);
     if ((!in_direct || !out_direct) && ensure_host_stage(b, (C + 2) * n)) return -1;
-    const size_t per = pipeline_group_size(C);
+    const size_t per = pipeline_group_size(C, blocking);
     const int G = (int)((C + per - 1) / per);
     void *s0 = gdgb_stream_handle(0);
     b.staged.clear(); b.out.assign(out, out + n_out_rows); b.ob = ob;
@@ -1121,7 +1125,7 @@ int host_block(gdg_chain *const *chains, size_t C, gdg_tuner *tuner, int tuner_c
     std::lock_guard<std::mutex> lk(g_batch_mutex);
     const int si = free_slot();
     if (si < 0) return fail("two submitted blocks are in flight: gdg_controller_wait() for one first");
-    if (block_submit(si, chains, C, tuner, tuner_channel, spat, meter, in, in_fmt, out, out_fmt, n_out_rows, n, rate, metronome, metro_master)) {
+    if (block_submit(si, chains, C, tuner, tuner_channel, spat, meter, in, in_fmt, out, out_fmt, n_out_rows, n, rate, metronome, metro_master, nullptr, true)) {
         if (g_batch) { gdgb_sync(); g_batch->slot[si].busy = false; }
         return -1;
     }

@@ -358,27 +358,32 @@ GDG_DEVI void ac_twiddle(int pos, int h, double &re, double &im)
     GDG_SINCOSPI(-(double)pos / (double)h, &s, &c);            /* exp(-2 pi i pos / (2h)) */
     re = c; im = s;
 }
+/* one radix-2 butterfly on the cells i0, i1 = i0 + (row distance) of w; pos / h name its twiddle exp(-2 pi i pos / (2h)) */
+GDG_DEVI void ac_dif_pair(double *w, int i0, int i1, int pos, int h)
+{
+    const double ar = w[2 * i0], ai = w[2 * i0 + 1], cr = w[2 * i1], ci = w[2 * i1 + 1];
+    double tr, ti; ac_twiddle(pos, h, tr, ti);
+    const double dr = ar - cr, di = ai - ci;
+    w[2 * i0] = ar + cr; w[2 * i0 + 1] = ai + ci;
+    w[2 * i1] = dr * tr - di * ti; w[2 * i1 + 1] = dr * ti + di * tr;
+}
+GDG_DEVI void ac_dit_pair(double *w, int i0, int i1, int pos, int h)
+{
+    const double ar = w[2 * i0], ai = w[2 * i0 + 1], cr = w[2 * i1], ci = w[2 * i1 + 1];
+    double tr, ti; ac_twiddle(pos, h, tr, ti); ti = -ti;
+    const double xr = cr * tr - ci * ti, xi = cr * ti + ci * tr;
+    w[2 * i0] = ar + xr; w[2 * i0 + 1] = ai + xi;
+    w[2 * i1] = ar - xr; w[2 * i1 + 1] = ai - xi;
+}
 GDG_DEVI void ac_dif_body(double *w, int h, int b)
 {
-    {
-        const int grp = b / h, pos = b - grp * h, i0 = grp * 2 * h + pos, i1 = i0 + h;
-        const double ar = w[2 * i0], ai = w[2 * i0 + 1], cr = w[2 * i1], ci = w[2 * i1 + 1];
-        double tr, ti; ac_twiddle(pos, h, tr, ti);
-        const double dr = ar - cr, di = ai - ci;
-        w[2 * i0] = ar + cr; w[2 * i0 + 1] = ai + ci;
-        w[2 * i1] = dr * tr - di * ti; w[2 * i1 + 1] = dr * ti + di * tr;
-    }
+    const int grp = b / h, pos = b - grp * h, i0 = grp * 2 * h + pos;
+    ac_dif_pair(w, i0, i0 + h, pos, h);
 }
 GDG_DEVI void ac_dit_body(double *w, int h, int b)
 {
-    {
-        const int grp = b / h, pos = b - grp * h, i0 = grp * 2 * h + pos, i1 = i0 + h;
-        const double ar = w[2 * i0], ai = w[2 * i0 + 1], cr = w[2 * i1], ci = w[2 * i1 + 1];
-        double tr, ti; ac_twiddle(pos, h, tr, ti); ti = -ti;
-        const double xr = cr * tr - ci * ti, xi = cr * ti + ci * tr;
-        w[2 * i0] = ar + xr; w[2 * i0 + 1] = ai + xi;
-        w[2 * i1] = ar - xr; w[2 * i1 + 1] = ai - xi;
-    }
+    const int grp = b / h, pos = b - grp * h, i0 = grp * 2 * h + pos;
+    ac_dit_pair(w, i0, i0 + h, pos, h);
 }
 /* split -> |X|^2 (tuner.go:437-440) -> inverse split, on bit-reversed storage */
 GDG_DEVI void ac_power_body(double *w, int M, int logM, int k)

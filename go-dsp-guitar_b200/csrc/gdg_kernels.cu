@@ -223,16 +223,6 @@ __global__ void k_acb_load(gdg_ac_batch b, int n_ring, int F)
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < F) ac_load_body(b.ring[blockIdx.y], n_ring, b.pos[blockIdx.y], b.work[blockIdx.y], i);
 }
-__global__ void k_acb_dif(gdg_ac_batch b, int M, int h)
-{
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < M / 2) ac_dif_body(b.work[blockIdx.y], h, t);
-}
-__global__ void k_acb_dit(gdg_ac_batch b, int M, int h)
-{
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < M / 2) ac_dit_body(b.work[blockIdx.y], h, t);
-}
 __global__ void k_acb_power(gdg_ac_batch b, int M, int logM)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -242,6 +232,73 @@ __global__ void k_acb_scale(gdg_ac_batch b, int n, double f)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) b.work[blockIdx.y][i] *= f;
+}
+
+/* ---- radix-2 passes fused through shared memory ----------------------------------------------------------------------
+ * The 2^17-point transform of tuner.Analyze ran as one launch per radix-2 stage (17 + 17 launches, each a full round trip of
+ * the work buffer through HBM).  The same butterflies - same twiddles, same order, bit-identical results - now run as two
+ * launches per direction (the IR compiler's single, smaller transforms keep one launch per stage: spread over more SMs
+ * they finish sooner than 16 fused CTAs - measured, tools/recompile_bench.py): `k_acb_lo` does the lowest (up to 11) stages of a
+ * contiguous block of <= 2048 points in shared memory, `k_acb_hi` up to 6 of the stages above on a tile of 2^S rows x
+ * 2048 / 2^S contiguous columns (rows `hl` points apart).  blockIdx.y selects the transform of a batch. */
+#define GDG_ACF_N 2048
+#define GDG_ACF_NT 512
+__global__ void __launch_bounds__(GDG_ACF_NT) k_acb_lo(gdg_ac_batch b, int N, int inverse)
+{
+    __shared__ double sm[2 * GDG_ACF_N];
+    double *w = b.work[blockIdx.y] + 2L * (long)blockIdx.x * N;
+    const int tid = (int)threadIdx.x;
+    for (int i = tid; i < 2 * N; i += GDG_ACF_NT) sm[i] = w[i];
+    __syncthreads();
+    if (!inverse) { for (int h = N / 2; h >= 1; h >>= 1) { for (int t = tid; t < N / 2; t += GDG_ACF_NT) ac_dif_body(sm, h, t); __syncthreads(); } }
+    else { for (int h = 1; h <= N / 2; h <<= 1) { for (int t = tid; t < N / 2; t += GDG_ACF_NT) ac_dit_body(sm, h, t); __syncthreads(); } }
+    for (int i = tid; i < 2 * N; i += GDG_ACF_NT) w[i] = sm[i];
+}
+/* stages with half-distances h0, h0/2, .., hl = h0 >> (S - 1) (forward: in this order, inverse: reversed); hl >= 2048 */
+__global__ void __launch_bounds__(GDG_ACF_NT) k_acb_hi(gdg_ac_batch b, int h0, int S, int inverse)
+{
+    __shared__ double sm[2 * GDG_ACF_N];
+    const int tid = (int)threadIdx.x;
+    const int Rr = 1 << S, T = GDG_ACF_N >> S, logT = 11 - S, hl = h0 >> (S - 1);
+    const int tiles_per_hi = hl / T, hi = (int)blockIdx.x / tiles_per_hi, mid = (int)blockIdx.x - hi * tiles_per_hi;
+    double *w = b.work[blockIdx.y] + 2L * ((long)hi * 2 * h0 + (long)mid * T);
+    for (int e = tid; e < GDG_ACF_N; e += GDG_ACF_NT) {
+        const int r = e >> logT, c = e & (T - 1);
+        const double2 v = *(const double2 *)(w + 2L * ((long)r * hl + c));
+        sm[2 * e] = v.x; sm[2 * e + 1] = v.y;
+    }
+    __syncthreads();
+    for (int st = 0; st < S; st++) {
+        const int hr = inverse ? (1 << st) : (Rr >> (st + 1));                 /* row half-distance of this stage */
+        const int h = hr * hl;
+        for (int t = tid; t < GDG_ACF_N / 2; t += GDG_ACF_NT) {
+            const int c = t & (T - 1), q = t >> logT;
+            const int grp = q / hr, rp = q - grp * hr, r0 = grp * 2 * hr + rp;
+            const int l0 = r0 * T + c, l1 = l0 + hr * T, pos = rp * hl + mid * T + c;
+            if (!inverse) ac_dif_pair(sm, l0, l1, pos, h); else ac_dit_pair(sm, l0, l1, pos, h);
+        }
+        __syncthreads();
+    }
+    for (int e = tid; e < GDG_ACF_N; e += GDG_ACF_NT) {
+        const int r = e >> logT, c = e & (T - 1);
+        *(double2 *)(w + 2L * ((long)r * hl + c)) = make_double2(sm[2 * e], sm[2 * e + 1]);
+    }
+}
+/* all radix-2 stages of `count` M-point transforms (work buffers in b), forward (natural -> bit-reversed) or inverse */
+static void ac_fft_launch(const gdg_ac_batch &b, int count, int M, int inverse, cudaStream_t s)
+{
+    int logM = 0; while ((1 << logM) < M) logM++;
+    const int lo_bits = logM < 11 ? logM : 11, N = 1 << lo_bits;
+    /* chunks of the upper stages, from the largest half-distance down */
+    int chunk_h0[8], chunk_S[8], nch = 0;
+    for (int top = logM - 1; top >= lo_bits;) { const int S = (top - lo_bits + 1) < 6 ? (top - lo_bits + 1) : 6; chunk_h0[nch] = 1 << top; chunk_S[nch] = S; nch++; top -= S; }
+    if (!inverse) {
+        for (int k = 0; k < nch; k++) { k_acb_hi<<<dim3(M / GDG_ACF_N, count), GDG_ACF_NT, 0, s>>>(b, chunk_h0[k], chunk_S[k], 0); g_launches++; }
+        if (lo_bits > 0) { k_acb_lo<<<dim3(M / N, count), GDG_ACF_NT, 0, s>>>(b, N, 0); g_launches++; }
+    } else {
+        if (lo_bits > 0) { k_acb_lo<<<dim3(M / N, count), GDG_ACF_NT, 0, s>>>(b, N, 1); g_launches++; }
+        for (int k = nch - 1; k >= 0; k--) { k_acb_hi<<<dim3(M / GDG_ACF_N, count), GDG_ACF_NT, 0, s>>>(b, chunk_h0[k], chunk_S[k], 1); g_launches++; }
+    }
 }
 
 /* ---- backend API ---------------------------------------------------------------- */
@@ -538,11 +595,11 @@ int gdgb_autocorrelate_batch(const double *const *d_rings, int n_ring, const int
         const int cnt = count - c0 < 32 ? count - c0 : 32;
         gdg_ac_batch b;
         for (int i = 0; i < cnt; i++) { b.ring[i] = d_rings[c0 + i]; b.work[i] = d_works[c0 + i]; b.pos[i] = pos[c0 + i]; }
-        dim3 gF((F + 255) / 256, cnt), gB((M / 2 + 255) / 256, cnt), gP((M / 2 + 1 + 255) / 256, cnt);
+        dim3 gF((F + 255) / 256, cnt), gP((M / 2 + 1 + 255) / 256, cnt);
         k_acb_load<<<gF, 256, 0, s>>>(b, n_ring, F); g_launches++;
-        for (int h = M / 2; h >= 1; h >>= 1) { k_acb_dif<<<gB, 256, 0, s>>>(b, M, h); g_launches++; }
+        ac_fft_launch(b, cnt, M, 0, s);
         k_acb_power<<<gP, 256, 0, s>>>(b, M, logM); g_launches++;
-        for (int h = 1; h <= M / 2; h <<= 1) { k_acb_dit<<<gB, 256, 0, s>>>(b, M, h); g_launches++; }
+        ac_fft_launch(b, cnt, M, 1, s);
         k_acb_scale<<<gF, 256, 0, s>>>(b, F, 1.0 / (double)M); g_launches++;
     }
     CU(cudaGetLastError());
