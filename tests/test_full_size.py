@@ -74,3 +74,30 @@ def test_cfg5_full_batch():
     for k in range(BLOCKS):
         ys = gdg.process_batch(small, x[k][CHECK], FS)
         assert np.array_equal(ys, outs[k][CHECK]), k
+
+
+def test_cfg5_device_resident_batch_on_two_kernel_streams():
+    """gdg_process_batch_device at full size: the two halves of the channels run on two kernel streams inside the call
+    (forked from and joined to the caller's stream).  Every channel must produce the bits it produces in a small batch on one
+    stream, block after block, and the caller's stream must still order consecutive calls (block k + 1 reads the state block k
+    wrote)."""
+    import torch
+    lib = common.backend_lib("cuda")
+    ob, pb = common.make_banks(lib, with_fixture=False, synthetic=[("syn8192", 8192, FS)])
+    x = _inputs()
+    chains = _chains(lib, pb, C)
+    small = _chains(lib, pb, len(CHECK))
+    stream = torch.cuda.Stream()
+    runner = gdg.BatchRunner(chains)
+    xin = [torch.tensor(x[k], device="cuda") for k in range(BLOCKS)]
+    yout = [torch.empty_like(xin[k]) for k in range(BLOCKS)]
+    torch.cuda.synchronize()
+    for k in range(BLOCKS):                                   # both blocks enqueued back to back, no host synchronisation in between
+        runner.process_device(xin[k].data_ptr(), yout[k].data_ptr(), N, N, FS, stream.cuda_stream)
+    stream.synchronize()
+    for k in range(BLOCKS):
+        y = yout[k].cpu().numpy()
+        ys = gdg.process_batch(small, x[k][CHECK], FS)
+        assert np.array_equal(ys, y[CHECK]), k
+        yy = y.reshape(C // PATTERNS, PATTERNS, N)
+        assert np.array_equal(yy, np.broadcast_to(yy[0], yy.shape)), k
