@@ -67,10 +67,12 @@ int gdgb_set_tables(const double *aa2, const double *aa4, const double *lz2, con
  * Channel c reads d_in (in_fmt, GDG_FMT_*) when round == 0 and the float64 rows d_mid otherwise; it writes d_out (out_fmt)
  * when round == d_nseg[c] - 1 (its last segment) and d_mid otherwise.  Row c of a buffer starts at base + c * stride.
  * d_side (may be NULL; row stride in doubles): when out_fmt is an encoded format, the last segment also stores the
- * float64 result there (what the spatializer and the level meter read, controller.go:2746-2770). */
+ * float64 result there (what the spatializer and the level meter read, controller.go:2746-2770).
+ * max_units (kind 1): the longest run among the channels of this launch - with few channels the backend spreads a run over
+ * a cluster of CTAs, one unit each (gdg_os.cuh: run_os_pipe). */
 int gdgb_launch_segments(int kind, const gdg_chain_desc *const *d_descs, const int32_t *d_nseg, int round, int channels,
                          const void *d_in, long in_stride_bytes, int in_fmt, void *d_out, long out_stride_bytes, int out_fmt,
-                         void *d_mid, long mid_stride_bytes, double *d_side, long side_stride, int n, void *stream);
+                         void *d_mid, long mid_stride_bytes, double *d_side, long side_stride, int n, int max_units, void *stream);
 /* level meter (level/level.go:147-208): row c = d_in + c*stride (n samples) updates the 4-word state d_state + 4*c
  * {cur, peak, counter (int64), unused}; f = decay factor per sample, hold = peak hold time in samples */
 int gdgb_launch_meter(const double *d_in, long stride, int channels, long n, double f, long long hold, double *d_state, void *stream);

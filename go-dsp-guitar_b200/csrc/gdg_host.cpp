@@ -671,6 +671,7 @@ struct Batch {
     std::vector<std::vector<const gdg_chain_desc *>> h_ptrs;     /* [round * SEG_KINDS + kind][channel] */
     std::vector<const gdg_chain_desc **> d_ptrs;
     std::vector<bool> kind_used;                                 /* [round * SEG_KINDS + kind] */
+    std::vector<int> max_units;                                  /* [round * SEG_KINDS + kind]: longest segment among the channels */
     std::vector<int32_t> h_nseg; int32_t *d_nseg = nullptr;
     double *d_scratch = nullptr; size_t scratch_cap = 0;         /* float64 rows between the rounds of encoded calls */
     /* two staging slots: block k+1 can be submitted (its upload overlapping block k's kernels and download) before
@@ -717,6 +718,13 @@ int prepare_tables(Batch &b, gdg_chain *const *chains, size_t C, uint32_t rate, 
                 const size_t t = r * SEG_KINDS + (size_t)chains[c]->seg_kind[r];
                 ptrs[t][c] = chains[c]->d_desc[r]; used[t] = true;
             }
+        std::vector<int> mu(rounds * SEG_KINDS, 0);
+        for (size_t c = 0; c < C; c++)
+            for (size_t r = 0; r < (size_t)nseg[c]; r++) {
+                int &m = mu[r * SEG_KINDS + (size_t)chains[c]->seg_kind[r]];
+                m = std::max(m, (int)chains[c]->h_desc[r].nslots);
+            }
+        b.max_units = mu;
         if (ptrs != b.h_ptrs || nseg != b.h_nseg) {
             gdgb_sync();                                              /* launches still reading the old tables */
             for (auto p : b.d_ptrs) gdgb_free((void *)p);
@@ -776,7 +784,8 @@ int launch_tables(Batch &b, size_t c0, size_t cnt, int rounds, const void *d_in,
             if (gdgb_launch_segments(k, b.d_ptrs[t] + c0, b.d_nseg + c0, r, (int)cnt,
                                      (const unsigned char *)d_in + c0 * in_stride, (long)in_stride, in_fmt,
                                      (unsigned char *)d_out + c0 * out_stride, (long)out_stride, out_fmt,
-                                     mid + c0 * mid_stride, (long)mid_stride, d_side ? d_side + c0 * n : nullptr, (long)n, (int)n, stream))
+                                     mid + c0 * mid_stride, (long)mid_stride, d_side ? d_side + c0 * n : nullptr, (long)n, (int)n,
+                                     t < b.max_units.size() ? b.max_units[t] : 0, stream))
                 return backend_fail("chain kernel launch failed");
         }
     return 0;

@@ -24,6 +24,7 @@ struct DevCtx {
     cudaStream_t stream = nullptr, copy[2] = {nullptr, nullptr}, side[GDGB_SIDE_STREAMS] = {};
     cudaEvent_t events[GDGB_EVENTS];
     double *d_tw = nullptr;
+    int pipe_fit[3] = {-1, -1, -1};                        /* resident clusters of k_os_pipe for P = 2, 4, 8 (queried on first use) */
 };
 static DevCtx g_ctx[GDGB_MAX_CONTEXTS];
 static int g_nctx = 0;
@@ -82,6 +83,17 @@ k_os(const gdg_chain_desc *const *descs, const int32_t *nseg, int round, const u
     if (cd == nullptr) return;
     const gdg_io io = segment_io(c, round, nseg[c], in, in_stride, in_fmt, out, out_stride, out_fmt, mid, mid_stride, side, side_stride);
     run_os(gdg_smem, cd, io.src, io.src_fmt, io.dst, io.dst_fmt, io.side, n);
+}
+/* the same run pipelined over a thread-block cluster of P CTAs per channel (gdg_os.cuh: run_os_pipe); grid = channels * P */
+__global__ void __launch_bounds__(GDG_OSK_NT, GDG_OSK_CTAS)
+k_os_pipe(const gdg_chain_desc *const *descs, const int32_t *nseg, int round, const unsigned char *in, long in_stride, int in_fmt,
+          unsigned char *out, long out_stride, int out_fmt, unsigned char *mid, long mid_stride, double *side, long side_stride, int n, int P)
+{
+    const int c = blockIdx.x / P;
+    const gdg_chain_desc *cd = descs[c];
+    if (cd == nullptr) return;                             /* the whole cluster leaves */
+    const gdg_io io = segment_io(c, round, nseg[c], in, in_stride, in_fmt, out, out_stride, out_fmt, mid, mid_stride, side, side_stride);
+    run_os_pipe(cd, io.src, io.src_fmt, io.dst, io.dst_fmt, io.side, n);
 }
 /* level meter: CTA c meters row c of d_in into state words d_state + 4*c */
 __global__ void __launch_bounds__(GDG_NT) k_meter(const double *in, long stride, long n, double f, long long hold, double *state)
@@ -331,6 +343,8 @@ static int open_context(int slot, int device)
     CU(cudaFuncSetAttribute(k_ir_partition_spectra, cudaFuncAttributeMaxDynamicSharedMemorySize, GDG_SMEM_BYTES));
     CU(cudaFuncSetAttribute(k_os, cudaFuncAttributeMaxDynamicSharedMemorySize, GDG_OSK_SMEM_BYTES));
     CU(cudaFuncSetAttribute(k_os, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CU(cudaFuncSetAttribute(k_os_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, GDG_OSK_SMEM_BYTES));
+    CU(cudaFuncSetAttribute(k_os_pipe, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     return 0;
 }
 static int upload_tables()
@@ -460,8 +474,29 @@ int gdgb_set_tables(const double *aa2, const double *aa4, const double *lz2, con
 
 int gdgb_launch_segments(int kind, const gdg_chain_desc *const *d_descs, const int32_t *d_nseg, int round, int channels,
                          const void *d_in, long in_stride_bytes, int in_fmt, void *d_out, long out_stride_bytes, int out_fmt,
-                         void *d_mid, long mid_stride_bytes, double *d_side, long side_stride, int n, void *stream)
+                         void *d_mid, long mid_stride_bytes, double *d_side, long side_stride, int n, int max_units, void *stream)
 {
+    /* few channels and runs of several units: one cluster of P CTAs per channel, the units of a run pipelined over the tiles
+     * (all clusters resident at once) - otherwise one CTA per channel */
+    static const bool no_pipe = getenv("GDG_NO_OS_PIPE") != nullptr;        /* development knob */
+    const int P = max_units <= 2 ? 2 : (max_units <= 4 ? 4 : 8);
+    if (kind == 1 && !no_pipe && max_units >= 2 && max_units <= GDG_OSK_MAX_UNITS && (long)channels * P <= (long)GDG_OSK_CTAS * g_sms) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(channels * P)); cfg.blockDim = dim3(GDG_OSK_NT); cfg.dynamicSmemBytes = GDG_OSK_SMEM_BYTES; cfg.stream = (cudaStream_t)stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = (unsigned)P; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        /* only when every cluster is resident at once (clusters live inside one GPC: fewer fit than CTAs / P) - a second
+         * wave of clusters would double the latency this shape exists to cut */
+        int &fit = CX.pipe_fit[P == 2 ? 0 : (P == 4 ? 1 : 2)];
+        if (fit < 0) { int nc = 0; fit = cudaOccupancyMaxActiveClusters(&nc, k_os_pipe, &cfg) == cudaSuccess ? nc : 0; cudaGetLastError(); }
+        if (channels <= fit) {
+        CU(cudaLaunchKernelEx(&cfg, k_os_pipe, d_descs, d_nseg, round, (const unsigned char *)d_in, in_stride_bytes, in_fmt,
+                              (unsigned char *)d_out, out_stride_bytes, out_fmt, (unsigned char *)d_mid, mid_stride_bytes, d_side, side_stride, n, P));
+        g_launches++;
+        return 0;
+        }
+    }
     if (kind == 0)
         k_chain<<<channels, GDG_NT, GDG_SMEM_BYTES, (cudaStream_t)stream>>>(d_descs, d_nseg, round, (const unsigned char *)d_in, in_stride_bytes, in_fmt,
                                                                           (unsigned char *)d_out, out_stride_bytes, out_fmt, (unsigned char *)d_mid, mid_stride_bytes, d_side, side_stride, n, g_d_tw);

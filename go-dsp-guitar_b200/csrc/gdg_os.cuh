@@ -13,6 +13,11 @@
  * Arithmetic, state words (GDG_OS_ST_*) and carries are exactly those of stage_oversampled (gdg_stages2.cuh): the two
  * code paths are interchangeable block by block (a unit may move between them when the chain is edited).
  *
+ * Two drivers share the unit tile (osk_unit_tile): run_os - one CTA per channel, every unit of the run on a tile before the
+ * next tile (many channels: the channels fill the GPU) - and run_os_pipe at the end of this file - a thread-block cluster
+ * per channel, one CTA per unit, tiles handed from CTA to CTA through distributed shared memory (few channels: the latency
+ * of a block is what counts).
+ *
  * Reference: effects/{excess,fuzz,overdrive,distortion}.go Process wrappers (e.g. overdrive.go:83-144),
  * oversampling/oversampling.go:54-184, resample/resample.go:148-176, filter/filter.go:342-515 (the decimator's FIR).
  */
@@ -357,5 +362,89 @@ GDG_DEV void run_os(double *smem, const gdg_chain_desc *cd, const void *in, int 
         }
     GDG_THREADS_END
 }
+
+#if defined(__CUDACC__) && !defined(GDG_HOST_EMU)
+/* --------------------------------------------------------------------------------------------------------------------
+ * The same run as a PIPELINE over a thread-block cluster (few channels: one CTA per channel leaves the GPU idle and a block
+ * costs the latency of U x ntiles unit-tiles in sequence).  CTA r of the cluster owns unit r of the run; in step s it
+ * applies its unit to tile s - r and writes the result straight into the input buffer of CTA r + 1 - distributed shared
+ * memory, no trip through L2 - then the cluster synchronises: U + ntiles - 1 steps instead of U x ntiles.  Every unit sees
+ * exactly the tiles, carries and arithmetic of run_os (osk_unit_tile is shared), so the two are interchangeable block by
+ * block.  Input buffers alternate between XA and XB (the producer of step s writes the buffer the consumer reads in step
+ * s + 1); the last unit stages its output in the stash area of the unused units.
+ * Launch: cluster of P >= U CTAs per channel (ranks >= U only take part in the barriers). */
+#include <cooperative_groups.h>
+GDG_DEV void run_os_pipe(const gdg_chain_desc *cd, const void *in, int in_fmt, void *out, int out_fmt, double *side, int n)
+{
+    namespace cg = cooperative_groups;
+    cg::cluster_group cl = cg::this_cluster();
+    constexpr int NT = GDG_OSK_NT, T = GDG_OSK_TILE;
+    const int r = (int)cl.block_rank(), P = (int)cl.num_blocks();
+    const int tid = (int)threadIdx.x;
+    const int U = imin(GDG_LDG(&cd->nslots), imin(GDG_OSK_MAX_UNITS, P));
+    const bool mine = r < U;
+    double *const xb0 = gdg_smem + GDG_OSK_XA, *const xb1 = gdg_smem + GDG_OSK_XB;
+    double *xc = gdg_smem + GDG_OSK_ST + GDG_OSK_STASH;                 /* output staging of the last unit (stash slots 1.. are free here) */
+    static_assert((GDG_OSK_MAX_UNITS - 1) * GDG_OSK_STASH >= GDG_OSK_XLEN, "staging buffer does not fit the unused stash slots");
+    double *stash = gdg_smem + GDG_OSK_ST, *fz = gdg_smem + GDG_OSK_FZ;
+    gdg_chain_desc *scd = (gdg_chain_desc *)(gdg_smem + GDG_OSK_DESC);
+    if (mine) {                                                          /* my unit's descriptor -> slot 0 of the shared-memory copy */
+        const int words = (int)(sizeof(gdg_unit_desc) / 4);
+        for (int k = tid; k < words; k += NT) ((int *)&scd->slot[0])[k] = ((const int *)&cd->slot[r])[k];
+    }
+    __syncthreads();
+    const gdg_unit_desc &d = scd->slot[0];
+    if (mine) {
+        const int F = d.i[0];
+        const double *st = d.st;
+        const double *zh = st + (F == 2 ? GDG_OS_ST_Z2 : GDG_OS_ST_Z4), *uph = st + (F == 2 ? GDG_OS_ST_UP2 : GDG_OS_ST_UP4);
+        if (tid < F * (GDG_ZH + 1)) stash[tid] = GDG_LDST(zh + tid);
+        if (tid >= NT - 8) stash[4 * (GDG_ZH + 1) + tid - (NT - 8)] = GDG_LDST(uph + tid - (NT - 8));
+        if (tid == 32) { fz[0] = st[GDG_OS_ST_ENV]; fz[1] = st[GDG_OS_ST_CCV]; }
+    }
+    const int ntiles = (n + T - 1) / T;
+    double nx[T / NT];
+    if (r == 0) {
+#pragma unroll
+        for (int k = 0; k < T / NT; k++) { const int i = tid + k * NT; nx[k] = i < n ? (in_fmt == GDG_FMT_IEEE64 ? ((const double *)in)[i] : decode_sample(in_fmt, (const unsigned char *)in, i)) : 0.0; }
+    }
+    cl.sync();                                                           /* every CTA of the cluster runs: remote shared memory may be written */
+    for (int s = 0; s < ntiles + U - 1; s++) {
+        const int t = s - r;
+        if (mine && t >= 0 && t < ntiles) {
+            const int t0 = t * T, Tt = imin(T, n - t0);
+            double *xin = (s & 1) ? xb1 : xb0;
+            if (r == 0) {
+#pragma unroll
+                for (int k = 0; k < T / NT; k++) { const int i = tid + k * NT; if (i < Tt) xin[8 + i] = nx[k]; }
+#pragma unroll
+                for (int k = 0; k < T / NT; k++) {
+                    const int i = t0 + T + tid + k * NT;
+                    if (i < n) nx[k] = in_fmt == GDG_FMT_IEEE64 ? ((const double *)in)[i] : decode_sample(in_fmt, (const unsigned char *)in, i);
+                }
+            }
+            if (tid < 8) xin[tid] = stash[4 * (GDG_ZH + 1) + tid];           /* my unit's last 8 inputs */
+            __syncthreads();
+            const bool last = r == U - 1;
+            double *xout = last ? xc : cl.map_shared_rank((s & 1) ? xb0 : xb1, r + 1);
+            osk_dispatch(d, xin, xout, stash, fz, Tt, nullptr);
+            if (last) {
+                if (out_fmt == GDG_FMT_IEEE64) { for (int i = tid; i < Tt; i += NT) ((double *)out)[t0 + i] = xc[8 + i]; }
+                else if (side == nullptr) { for (int i = tid; i < Tt; i += NT) encode_sample(out_fmt, (unsigned char *)out, t0 + i, xc[8 + i]); }
+                else { for (int i = tid; i < Tt; i += NT) { const double v = xc[8 + i]; side[t0 + i] = v; encode_sample(out_fmt, (unsigned char *)out, t0 + i, v); } }
+            }
+        }
+        cl.sync();
+    }
+    if (mine) {
+        const int F = d.i[0];
+        double *st = d.st;
+        double *zh = st + (F == 2 ? GDG_OS_ST_Z2 : GDG_OS_ST_Z4), *uph = st + (F == 2 ? GDG_OS_ST_UP2 : GDG_OS_ST_UP4);
+        if (tid < F * (GDG_ZH + 1)) zh[tid] = stash[tid];
+        if (tid >= NT - 8) uph[tid - (NT - 8)] = stash[4 * (GDG_ZH + 1) + tid - (NT - 8)];
+        if (tid == 32 && d.type == GDG_UNIT_FUZZ) { st[GDG_OS_ST_ENV] = fz[0]; st[GDG_OS_ST_CCV] = fz[1]; }
+    }
+}
+#endif
 
 #endif /* GDG_OS_CUH */

@@ -96,7 +96,7 @@ int gdgb_set_tables(const double *aa2, const double *aa4, const double *lz2, con
 
 int gdgb_launch_segments(int kind, const gdg_chain_desc *const *descs, const int32_t *nseg, int round, int channels,
                          const void *in, long in_stride, int in_fmt, void *out, long out_stride, int out_fmt,
-                         void *mid, long mid_stride, double *side, long side_stride, int n, void *)
+                         void *mid, long mid_stride, double *side, long side_stride, int n, int, void *)
 {
     std::vector<double> smem(kind == 0 ? GDG_SMEM_DOUBLES : GDG_OSK_SMEM_DOUBLES);
     for (int c = 0; c < channels; c++) {

@@ -177,3 +177,17 @@ def test_flanger_phaser_full_depth_history_edge(lib, unit, fs, n):
     a, b = common.make_chain_pair(lib, [(unit, {"depth": 100, "speed": 37}, {})])
     x = common.synth_fast(11, fs, 600 * n)
     common.compare_stream(a, b, x, n, fs, label="%s depth 100 @%d" % (unit, fs))
+
+
+@pytest.mark.gpu
+def test_oversampled_run_one_cta_per_channel_at_small_batches():
+    """Small batches run an oversampled run as a cluster pipeline (k_os_pipe, one CTA per unit); big ones as one CTA per
+    channel (k_os).  The rest of this suite uses small batches, so re-run the CHAIN12 parity cases in a process that has the
+    cluster path switched off (GDG_NO_OS_PIPE): both shapes must match the oracle."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, GDG_NO_OS_PIPE="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_parity.py"), "-m", "gpu", "-q", "-x", "-k", "chain12 or all_21_units or process_batch_matches or parameter_change",
+                        "-p", "no:cacheprovider"], env=env, cwd=root, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout
