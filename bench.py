@@ -156,10 +156,34 @@ def cpu_quota():
     return n, quota
 
 
+def cpu_throttle_stat():
+    """(nr_throttled, throttled_usec) of this container's cgroup: when they move during the CPU arm, the quota - not the code -
+    set the rate"""
+    for path in ("/sys/fs/cgroup/cpu.stat", "/sys/fs/cgroup/cpu/cpu.stat"):
+        try:
+            kv = dict(l.split()[:2] for l in open(path).read().splitlines() if l.strip())
+            return int(kv.get("nr_throttled", 0)), int(kv.get("throttled_usec", int(kv.get("throttled_time", 0)) // 1000))
+        except Exception:
+            continue
+    return None
+
+
+def cpu_model():
+    try:
+        for l in open("/proc/cpuinfo"):
+            if l.startswith("model name"):
+                return l.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return None
+
+
 def cpu_baseline_record(reps, blocks=64):
     host_cpus, quota = cpu_quota()
     cores = max(1, min(host_cpus, int(math.ceil(quota)) if quota else host_cpus))
+    th0 = cpu_throttle_stat()
     vals = time_oracle(cores, blocks, cores, reps)
+    th1 = cpu_throttle_stat()
     one = time_oracle(1, 4, 1, 2)
     v = float(np.median(vals))
     sample = "%d channels (one pinned worker each, like the reference's goroutine per channel) x %d blocks of %d, CHAIN12 @192 kHz + spatializer; median of %d repetitions" % (cores, blocks, N, len(vals))
@@ -167,6 +191,8 @@ def cpu_baseline_record(reps, blocks=64):
             "host_logical_cpus": host_cpus, "cgroup_cpu_quota": quota, "blocks_per_repetition": blocks,
             "repetitions": [round(a, 3) for a in vals], "spread": (max(vals) - min(vals)) / v if v else None,
             "per_core_single_thread": float(np.median(one)), "per_core_in_full_run": v / cores,
+            "best_repetition": float(max(vals)), "cpu_model": cpu_model(),
+            "cgroup_throttled_during_run": ({"periods": th1[0] - th0[0], "usec": th1[1] - th0[1]} if th0 and th1 else None),
             "note": "threads = min(logical CPUs, cgroup CPU quota): the pool's boxes expose 128 logical CPUs but schedule the container on a quota (16 CPUs per GPU); per_core_single_thread x physical cores is the figure to extrapolate to a whole host"}
 
 
