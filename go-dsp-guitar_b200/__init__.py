@@ -138,6 +138,8 @@ ABI = {
     "gdg_cluster_select": (_int, [_vp, _int]),
     "gdg_cluster_submit": (_int, [_vp, _vp, _u32, _vp, _int, _vp, _vp, _vp, _u32, _sz, _u32]),
     "gdg_cluster_wait": (_int, [_vp, _int]),
+    "gdg_cluster_submit_aux": (_int, [_vp, _vp, _u32, _vp, _int, _vp, _vp, _vp, _vp, _int, _vp, _u32, _sz, _u32]),
+    "gdg_cluster_submit_encoded": (_int, [_vp, _vp, _u32, _vp, _int, _vp, _vp, _vp, _int, _vp, _int, _u32, _sz, _u32]),
     "gdg_cluster_process": (_int, [_vp, _vp, _u32, _vp, _int, _vp, _vp, _vp, _u32, _sz, _u32]),
     "gdg_tuner_analyze_batch": (_int, [_vp, _u32, _vp]),
     "gdg_controller_process_aux": (_int, [_vp, _u32, _vp, _int, _vp, _vp, _vp, _vp, _int, _vp, _u32, _sz, _u32]),
@@ -626,7 +628,9 @@ class Cluster(_Base):
     def select(self, member):
         self._check(self._lib.gdg_cluster_select(self._h, member))
 
-    def process(self, chains, tuner, tuner_channel, spats, inputs, sample_rate):
+    def process(self, chains, tuner, tuner_channel, spats, inputs, sample_rate, meters=None, metronome=None, metronome_to_master=True):
+        """controller.process over the members: returns out[C (+2)][n].  meters: one Meter per member (2 * cnt_m + 3 channels,
+        entries may be None); metronome: the click row of this block (see controller_process)."""
         x = _f64(inputs)
         c, n = x.shape
         n_out = c + (2 if spats else 0)
@@ -634,5 +638,47 @@ class Cluster(_Base):
         ip = (C.c_void_p * c)(*[x[i].ctypes.data for i in range(c)])
         op = (C.c_void_p * n_out)(*[out[i].ctypes.data for i in range(n_out)])
         sp = _handles(spats) if spats else None
-        self._check(self._lib.gdg_cluster_process(self._h, _handles(chains), c, tuner._h if tuner else None, tuner_channel, sp, ip, op, n_out, n, sample_rate))
+        if meters is None and metronome is None:
+            self._check(self._lib.gdg_cluster_process(self._h, _handles(chains), c, tuner._h if tuner else None, tuner_channel, sp, ip, op, n_out, n, sample_rate))
+            return out
+        mt = (C.c_void_p * len(self.devices))(*[(m._h if m is not None else None) for m in meters]) if meters else None
+        click = _f64(metronome) if metronome is not None else None
+        t = self._lib.gdg_cluster_submit_aux(self._h, _handles(chains), c, tuner._h if tuner else None, tuner_channel, sp, mt, ip,
+                                             _ptr(click) if click is not None else None, 1 if metronome_to_master else 0, op, n_out, n, sample_rate)
+        self._check(t)
+        self._check(self._lib.gdg_cluster_wait(self._h, t))
         return out
+
+    def submit(self, chains, tuner, tuner_channel, spats, inputs, outputs, sample_rate, meters=None, metronome=None, metronome_to_master=True):
+        """gdg_cluster_submit(_aux): enqueue one block on every member without waiting; `inputs` [C][n] / `outputs` [C (+2)][n]
+        are caller-owned C-contiguous float64 arrays that stay alive until wait(ticket).  Returns the ticket."""
+        if inputs.dtype != np.float64 or outputs.dtype != np.float64 or not inputs.flags.c_contiguous or not outputs.flags.c_contiguous:
+            raise GdgError("Cluster.submit needs C-contiguous float64 arrays")
+        c, n = inputs.shape
+        n_out = outputs.shape[0]
+        ip = (C.c_void_p * c)(*[inputs[i].ctypes.data for i in range(c)])
+        op = (C.c_void_p * n_out)(*[outputs[i].ctypes.data for i in range(n_out)])
+        sp = _handles(spats) if spats else None
+        mt = (C.c_void_p * len(self.devices))(*[(m._h if m is not None else None) for m in meters]) if meters else None
+        click = _f64(metronome) if metronome is not None else None
+        t = self._lib.gdg_cluster_submit_aux(self._h, _handles(chains), c, tuner._h if tuner else None, tuner_channel, sp, mt, ip,
+                                             _ptr(click) if click is not None else None, 1 if metronome_to_master else 0, op, n_out, n, sample_rate)
+        self._check(t)
+        return t
+
+    def submit_encoded(self, chains, tuner, tuner_channel, spats, rows, in_format, outputs, out_format, n, sample_rate, meters=None):
+        """gdg_cluster_submit_encoded: rows / outputs are lists of caller-owned uint8 arrays (one payload row per channel, the
+        master pair last) that stay alive until wait(ticket)."""
+        fi, fo = FORMATS.index(in_format), FORMATS.index(out_format)
+        c, n_out = len(rows), len(outputs)
+        ip = (C.c_void_p * c)(*[a.ctypes.data for a in rows])
+        op = (C.c_void_p * n_out)(*[a.ctypes.data for a in outputs])
+        sp = _handles(spats) if spats else None
+        mt = (C.c_void_p * len(self.devices))(*[(m._h if m is not None else None) for m in meters]) if meters else None
+        t = self._lib.gdg_cluster_submit_encoded(self._h, _handles(chains), c, tuner._h if tuner else None, tuner_channel, sp, mt, ip, fi, op, fo,
+                                                 n_out, n, sample_rate)
+        self._check(t)
+        return t
+
+    def wait(self, ticket):
+        self._check(self._lib.gdg_cluster_wait(self._h, ticket))

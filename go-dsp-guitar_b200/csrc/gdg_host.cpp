@@ -1094,8 +1094,8 @@ int block_submit(int si, gdg_chain *const *chains, size_t C, gdg_tuner *tuner, i
     if (d_metro && meter && meter_rows(meter, (uint32_t)(2 * C), d_metro, n, 1, n, rate, s0)) return -1;        /* controller.go:2735-2738: the metronome port */
     if (spat) {                                                                                                 /* controller.go:2761 */
         if (gdg_spatializer_process_device(spat, b.d_out, n, (d_metro && metro_master) ? d_metro : nullptr, b.d_out + C * n, n, n, 0, s0)) return -1;
-        if (meter && meter_rows(meter, (uint32_t)(2 * C + 1), b.d_out + C * n, n, 2, n, rate, s0)) return -1;    /* controller.go:2768-2770: master */
-        if (enc_out && gdgb_convert_rows(b.d_out + C * n, (long)(n * sizeof(double)), GDG_FMT_IEEE64, (char *)b.d_enc_out + C * ob, (long)ob, out_fmt, 2, (int)n, s0))
+        if (meter && !partial_master && meter_rows(meter, (uint32_t)(2 * C + 1), b.d_out + C * n, n, 2, n, rate, s0)) return -1;    /* controller.go:2768-2770: master (a partial master is metered after the sum) */
+        if (enc_out && !partial_master && gdgb_convert_rows(b.d_out + C * n, (long)(n * sizeof(double)), GDG_FMT_IEEE64, (char *)b.d_enc_out + C * ob, (long)ob, out_fmt, 2, (int)n, s0))
             return backend_fail("payload encode failed");
         if (gdgb_record(ev + 16, 0)) return backend_fail("event failed");
         if (partial_master) *partial_master = b.d_out + C * n;
@@ -2047,11 +2047,148 @@ int gdg_current_device(void) { if (ensure_init()) return -1; return gdgb_context
 
 struct gdg_cluster {
     std::vector<int> ctx;                                   /* member -> device context */
-    double *d_master = nullptr; size_t cap_n = 0;           /* on member 0: the summed [2][n] master */
-    double *h_master = nullptr;                             /* pinned staging of the master rows */
-    struct Flight { bool busy = false; std::vector<int> members; double *out_l = nullptr, *out_r = nullptr; size_t n = 0; bool master = false; } flight[2];
-    ~gdg_cluster() { if (!ctx.empty()) { Use u(ctx[0]); gdgb_sync(); gdgb_free(d_master); } gdgb_pinned_free(h_master); }
+    /* on member 0, one set per block in flight: the summed [2][n] master, its encoded copy, the metronome row, the pinned
+     * staging of the master rows */
+    double *d_master[2] = {nullptr, nullptr}, *d_master_enc[2] = {nullptr, nullptr}, *d_metro[2] = {nullptr, nullptr}, *h_master[2] = {nullptr, nullptr};
+    size_t cap_n = 0;
+    struct Flight { bool busy = false; std::vector<int> members; void *out_l = nullptr, *out_r = nullptr; size_t ob = 0; bool master = false; } flight[2];
+    void release()
+    {
+        for (int k = 0; k < 2; k++) {
+            gdgb_free(d_master[k]); gdgb_free(d_master_enc[k]); gdgb_free(d_metro[k]); gdgb_pinned_free(h_master[k]);
+            d_master[k] = d_master_enc[k] = d_metro[k] = h_master[k] = nullptr;
+        }
+        cap_n = 0;
+    }
+    ~gdg_cluster()
+    {
+        if (!ctx.empty()) { Use u(ctx[0]); gdgb_sync(); release(); }
+    }
 };
+
+namespace {
+/* One block of controller.process (controller.go:2648-2783) over the cluster: chains[c] live on the members' devices in
+ * member order (contiguous channel ranges, SURVEY.md 8e); spats[m] is member m's spatializer over ITS channels (or spats ==
+ * NULL: no master); meters[m] is member m's level meter with 2 * cnt_m + 3 channels laid out like the one-device call's
+ * (inputs, outputs, metronome port, master L / R - the last three are fed on member 0 only, which owns the summed master).
+ * Each member runs tuner feed -> chains -> spatializer (-> meter) on its own streams; member 0 then sums the partial stereo
+ * masters (+ the metronome row, spatializer.go:300-308) with one kernel that reads the other devices' buffers through peer
+ * (NVLink) addresses and the master rows out[C], out[C+1] come back from member 0.  Host rows in any wave.go sample format.
+ * Returns a ticket for gdg_cluster_wait(). */
+int cluster_block(const char *who, gdg_cluster *cl, gdg_chain *const *chains, uint32_t C, gdg_tuner *tuner, int tuner_channel,
+                  gdg_spatializer *const *spats, gdg_meter *const *meters, const void *const *in, int in_fmt, const double *metronome,
+                  int metro_master, void *const *out, int out_fmt, uint32_t n_out, size_t n, uint32_t rate)
+{
+    if (ensure_init()) return -1;
+    if (!cl || !chains || !C || !in || !out) return fail("%s: bad argument", who);
+    if (!fmt_bytes(in_fmt) || !fmt_bytes(out_fmt)) return fail("Unknown sample format: %#04x", fmt_bytes(in_fmt) ? out_fmt : in_fmt);
+    if (check_block(n)) return -1;
+    if (n_out < C) return fail("%s: %u output rows for %u channels", who, n_out, C);
+    const int M = (int)cl->ctx.size();
+    std::vector<uint32_t> first(M + 1, C);
+    {   /* channel ranges: the chains' device contexts must follow the member order */
+        int m = 0; first[0] = 0;
+        for (uint32_t c = 0; c < C; c++) {
+            if (!chains[c]) return fail("%s: chain %u is NULL", who, c);
+            while (m < M && chains[c]->ctx != cl->ctx[m]) { m++; if (m < M) first[m] = c; }
+            if (m >= M) return fail("%s: chain %u does not live on a member device (or the chains are not grouped in member order)", who, c);
+        }
+        for (int k = m + 1; k <= M; k++) first[k] = C;
+    }
+    const bool master = spats && n_out >= C + 2;
+    for (int m = 0; m < M; m++) {                           /* every check before anything is enqueued */
+        const uint32_t cnt = first[m + 1] - first[m];
+        gdg_spatializer *sp = master ? spats[m] : nullptr;
+        if (cnt && sp && (sp->count != cnt || sp->ctx != cl->ctx[m]))
+            return fail("%s: member %d's spatializer must cover its %u channels on its own device", who, m, cnt);
+        gdg_meter *mt = meters ? meters[m] : nullptr;
+        if (mt && (mt->count != 2 * cnt + 3 || mt->ctx != cl->ctx[m]))
+            return fail("%s: member %d's level meter must have %u channels (its %u inputs, %u outputs, metronome, master L/R) on its own device", who, m, 2 * cnt + 3, cnt, cnt);
+    }
+    gdg_meter *meter0 = (meters && meters[0] && meters[0]->enabled) ? meters[0] : nullptr;
+    const uint32_t cnt0 = first[1] - first[0];
+    int si = -1;
+    {
+        std::lock_guard<std::mutex> lk(g_batch_mutex);
+        for (int k = 0; k < 2 && si < 0; k++) {
+            bool ok = !cl->flight[k].busy;
+            for (int m = 0; m < M && ok; m++) { Use u(cl->ctx[m]); if (g_batch && g_batch->slot[k].busy) ok = false; }
+            if (ok) si = k;
+        }
+    }
+    if (si < 0) return fail("two submitted blocks are in flight: gdg_cluster_wait() for one first");
+    gdg_cluster::Flight &fl = cl->flight[si];
+    const size_t ob = n * fmt_bytes(out_fmt);
+    fl.members.clear(); fl.master = master; fl.ob = ob;
+    auto unwind = [&]() {
+        for (int k : fl.members) { Use u2(cl->ctx[k]); gdgb_sync(); if (g_batch) g_batch->slot[si].busy = false; }
+        fl.members.clear();
+        return -1;
+    };
+    std::vector<const double *> parts; std::vector<long> strides; std::vector<int> part_ctx;
+    for (int m = 0; m < M; m++) {
+        const uint32_t c0 = first[m], cnt = first[m + 1] - first[m];
+        if (!cnt) continue;
+        Use u(cl->ctx[m]);
+        ProcessLock el(g_edit_mutex);
+        std::lock_guard<std::mutex> lk(g_batch_mutex);
+        gdg_spatializer *sp = master ? spats[m] : nullptr;
+        gdg_meter *mt = (meters && meters[m] && meters[m]->enabled) ? meters[m] : nullptr;
+        gdg_tuner *tu = (tuner && tuner_channel >= (int)c0 && tuner_channel < (int)(c0 + cnt)) ? tuner : nullptr;
+        const double *pm = nullptr;
+        if (block_submit(si, chains + c0, cnt, tu, tu ? tuner_channel - (int)c0 : -1, sp, mt, in + c0, in_fmt, out + c0, out_fmt, cnt, n, rate,
+                         nullptr, false, sp ? &pm : nullptr)) {
+            gdgb_sync(); if (g_batch) g_batch->slot[si].busy = false;
+            return unwind();
+        }
+        fl.members.push_back(m);
+        if (pm) { parts.push_back(pm); strides.push_back((long)n); part_ctx.push_back(cl->ctx[m]); }
+    }
+    const bool metro = metronome && (master || meter0);
+    if ((master && !parts.empty()) || metro) {
+        Use u(cl->ctx[0]);
+        if (cl->cap_n < n) {
+            gdgb_sync(); cl->release();
+            bool ok = true;
+            for (int k = 0; k < 2; k++) {
+                cl->d_master[k] = (double *)gdgb_alloc(2 * n * sizeof(double));
+                cl->d_master_enc[k] = (double *)gdgb_alloc(2 * n * sizeof(double));
+                cl->d_metro[k] = (double *)gdgb_alloc(n * sizeof(double));
+                cl->h_master[k] = (double *)gdgb_pinned_alloc(2 * n * sizeof(double));
+                ok = ok && cl->d_master[k] && cl->d_master_enc[k] && cl->d_metro[k] && cl->h_master[k];
+            }
+            if (!ok) { cl->release(); backend_fail("cluster master allocation failed"); return unwind(); }
+            cl->cap_n = n;
+        }
+        const int ev = si * 28;
+        void *s0 = gdgb_stream();
+        double *d_metro = nullptr;
+        if (metro) {                                        /* controller.go:2724-2738: the metronome's row of this block */
+            d_metro = cl->d_metro[si];
+            if (gdgb_h2d_async(d_metro, metronome, n * sizeof(double), 1) || gdgb_record(ev + 21, 1) || gdgb_wait(0, ev + 21)) { backend_fail("metronome upload failed"); return unwind(); }
+            if (meter0 && meter_rows(meter0, 2 * cnt0, d_metro, n, 1, n, rate, s0)) return unwind();
+        }
+        if (master && !parts.empty()) {
+            double *dm = cl->d_master[si];
+            for (int pc : part_ctx) if (gdgb_wait_other(cl->ctx[0], pc, ev + 16)) { backend_fail("cross-device wait failed"); return unwind(); }
+            if (gdgb_master_sum(parts.data(), strides.data(), (int)parts.size(), (d_metro && metro_master) ? d_metro : nullptr, dm, dm + n, (int)n, s0))
+                { backend_fail("master sum failed"); return unwind(); }
+            if (meter0 && meter_rows(meter0, 2 * cnt0 + 1, dm, n, 2, n, rate, s0)) return unwind();      /* controller.go:2768-2770 */
+            const void *src = dm;
+            if (out_fmt != GDG_FMT_IEEE64) {
+                if (gdgb_convert_rows(dm, (long)(n * sizeof(double)), GDG_FMT_IEEE64, cl->d_master_enc[si], (long)ob, out_fmt, 2, (int)n, s0))
+                    { backend_fail("payload encode failed"); return unwind(); }
+                src = cl->d_master_enc[si];
+            }
+            if (gdgb_record(ev + 22, 0) || gdgb_wait(2, ev + 22)) { backend_fail("event failed"); return unwind(); }
+            if (gdgb_d2h_async(cl->h_master[si], src, 2 * ob, 2) || gdgb_record(ev + 23, 2)) { backend_fail("master download failed"); return unwind(); }
+            fl.out_l = out[C]; fl.out_r = out[C + 1];
+        } else fl.master = false;
+    } else fl.master = false;
+    fl.busy = true;
+    return si;
+}
+} // namespace
 
 extern "C" {
 gdg_cluster *gdg_cluster_create(const int *devices, int n_devices)
@@ -2076,81 +2213,25 @@ int gdg_cluster_select(gdg_cluster *cl, int member)
     if (!cl || member < 0 || member >= (int)cl->ctx.size()) return fail("gdg_cluster_select: no member %d", member);
     return gdgb_select(cl->ctx[member]) ? backend_fail("gdg_cluster_select") : 0;
 }
-/* One block of controller.process (controller.go:2648-2783) over the cluster: chains[c] live on the members' devices in
- * member order (contiguous channel ranges, SURVEY.md 8e); spats[m] is member m's spatializer over ITS channels (or spats ==
- * NULL: no master).  Each member runs tuner feed -> chains -> spatializer on its own streams; member 0 then sums the partial
- * stereo masters with one kernel that reads the other devices' buffers through peer (NVLink) addresses and the master rows
- * out[C], out[C+1] come back from member 0.  Returns a ticket for gdg_cluster_wait(). */
 int gdg_cluster_submit(gdg_cluster *cl, gdg_chain *const *chains, uint32_t C, gdg_tuner *tuner, int tuner_channel, gdg_spatializer *const *spats,
                        const double *const *in, double *const *out, uint32_t n_out, size_t n, uint32_t rate)
 {
-    if (ensure_init()) return -1;
-    if (!cl || !chains || !C || !in || !out) return fail("gdg_cluster_submit: bad argument");
-    if (check_block(n)) return -1;
-    if (n_out < C) return fail("gdg_cluster_submit: %u output rows for %u channels", n_out, C);
-    const int M = (int)cl->ctx.size();
-    std::vector<uint32_t> first(M + 1, C);
-    {   /* channel ranges: the chains' device contexts must follow the member order */
-        int m = 0; first[0] = 0;
-        for (uint32_t c = 0; c < C; c++) {
-            if (!chains[c]) return fail("gdg_cluster_submit: chain %u is NULL", c);
-            while (m < M && chains[c]->ctx != cl->ctx[m]) { m++; if (m < M) first[m] = c; }
-            if (m >= M) return fail("gdg_cluster_submit: chain %u does not live on a member device (or the chains are not grouped in member order)", c);
-        }
-        for (int k = m + 1; k <= M; k++) first[k] = C;
-    }
-    const bool master = spats && n_out >= C + 2;
-    int si = -1;
-    {
-        std::lock_guard<std::mutex> lk(g_batch_mutex);
-        for (int k = 0; k < 2 && si < 0; k++) {
-            bool ok = !cl->flight[k].busy;
-            for (int m = 0; m < M && ok; m++) { Use u(cl->ctx[m]); if (g_batch && g_batch->slot[k].busy) ok = false; }
-            if (ok) si = k;
-        }
-    }
-    if (si < 0) return fail("two submitted blocks are in flight: gdg_cluster_wait() for one first");
-    gdg_cluster::Flight &fl = cl->flight[si];
-    fl.members.clear(); fl.master = master; fl.n = n;
-    std::vector<const double *> parts; std::vector<long> strides; std::vector<int> part_ctx;
-    for (int m = 0; m < M; m++) {
-        const uint32_t c0 = first[m], cnt = first[m + 1] - first[m];
-        if (!cnt) continue;
-        Use u(cl->ctx[m]);
-        ProcessLock el(g_edit_mutex);
-        std::lock_guard<std::mutex> lk(g_batch_mutex);
-        gdg_spatializer *sp = master ? spats[m] : nullptr;
-        if (sp && (sp->count != cnt || sp->ctx != cl->ctx[m])) return fail("gdg_cluster_submit: member %d's spatializer must cover its %u channels on its own device", m, cnt);
-        gdg_tuner *tu = (tuner && tuner_channel >= (int)c0 && tuner_channel < (int)(c0 + cnt)) ? tuner : nullptr;
-        const double *pm = nullptr;
-        if (block_submit(si, chains + c0, cnt, tu, tu ? tuner_channel - (int)c0 : -1, sp, nullptr, (const void *const *)(in + c0), GDG_FMT_IEEE64,
-                         (void *const *)(out + c0), GDG_FMT_IEEE64, cnt, n, rate, nullptr, false, sp ? &pm : nullptr)) {
-            gdgb_sync(); if (g_batch) g_batch->slot[si].busy = false;
-            for (int k : fl.members) { Use u2(cl->ctx[k]); gdgb_sync(); if (g_batch) g_batch->slot[si].busy = false; }
-            return -1;
-        }
-        fl.members.push_back(m);
-        if (pm) { parts.push_back(pm); strides.push_back((long)n); part_ctx.push_back(cl->ctx[m]); }
-    }
-    if (master && !parts.empty()) {
-        Use u(cl->ctx[0]);
-        if (cl->cap_n < n) {
-            gdgb_sync(); gdgb_free(cl->d_master); gdgb_pinned_free(cl->h_master);
-            cl->d_master = (double *)gdgb_alloc(2 * n * sizeof(double));
-            cl->h_master = (double *)gdgb_pinned_alloc(2 * n * sizeof(double));
-            if (!cl->d_master || !cl->h_master) return backend_fail("cluster master allocation failed");
-            cl->cap_n = n;
-        }
-        const int ev = si * 28;
-        for (int pc : part_ctx) if (gdgb_wait_other(cl->ctx[0], pc, ev + 16)) return backend_fail("cross-device wait failed");
-        if (gdgb_master_sum(parts.data(), strides.data(), (int)parts.size(), nullptr, cl->d_master, cl->d_master + n, (int)n, gdgb_stream()))
-            return backend_fail("master sum failed");
-        if (gdgb_record(ev + 19, 0) || gdgb_wait(2, ev + 19)) return backend_fail("event failed");
-        if (gdgb_d2h_async(cl->h_master, cl->d_master, 2 * n * sizeof(double), 2) || gdgb_record(ev + 20, 2)) return backend_fail("master download failed");
-        fl.out_l = out[C]; fl.out_r = out[C + 1];
-    } else fl.master = false;
-    fl.busy = true;
-    return si;
+    return cluster_block("gdg_cluster_submit", cl, chains, C, tuner, tuner_channel, spats, nullptr, (const void *const *)in, GDG_FMT_IEEE64, nullptr, 0,
+                         (void *const *)out, GDG_FMT_IEEE64, n_out, n, rate);
+}
+int gdg_cluster_submit_aux(gdg_cluster *cl, gdg_chain *const *chains, uint32_t C, gdg_tuner *tuner, int tuner_channel, gdg_spatializer *const *spats,
+                           gdg_meter *const *meters, const double *const *in, const double *metronome, int metronome_to_master,
+                           double *const *out, uint32_t n_out, size_t n, uint32_t rate)
+{
+    return cluster_block("gdg_cluster_submit_aux", cl, chains, C, tuner, tuner_channel, spats, meters, (const void *const *)in, GDG_FMT_IEEE64, metronome,
+                         metronome_to_master, (void *const *)out, GDG_FMT_IEEE64, n_out, n, rate);
+}
+int gdg_cluster_submit_encoded(gdg_cluster *cl, gdg_chain *const *chains, uint32_t C, gdg_tuner *tuner, int tuner_channel, gdg_spatializer *const *spats,
+                               gdg_meter *const *meters, const void *const *in, int in_format, void *const *out, int out_format,
+                               uint32_t n_out, size_t n, uint32_t rate)
+{
+    return cluster_block("gdg_cluster_submit_encoded", cl, chains, C, tuner, tuner_channel, spats, meters, in, in_format, nullptr, 0, out, out_format,
+                         n_out, n, rate);
 }
 int gdg_cluster_wait(gdg_cluster *cl, int ticket)
 {
@@ -2165,8 +2246,8 @@ int gdg_cluster_wait(gdg_cluster *cl, int ticket)
     }
     if (fl.master) {
         Use u(cl->ctx[0]);
-        if (gdgb_sync_event(ticket * 28 + 20)) rc = backend_fail("synchronize failed");
-        else { memcpy(fl.out_l, cl->h_master, fl.n * sizeof(double)); memcpy(fl.out_r, cl->h_master + fl.n, fl.n * sizeof(double)); }
+        if (gdgb_sync_event(ticket * 28 + 23)) rc = backend_fail("synchronize failed");
+        else { memcpy(fl.out_l, cl->h_master[ticket], fl.ob); memcpy(fl.out_r, (const char *)cl->h_master[ticket] + fl.ob, fl.ob); }
     }
     fl.busy = false;
     return rc;

@@ -261,6 +261,20 @@ int gdg_cluster_select(gdg_cluster *cluster, int member);       /* == gdg_use_de
 int gdg_cluster_submit(gdg_cluster *cluster, gdg_chain *const *chains, uint32_t channels, gdg_tuner *tuner, int tuner_channel,
                        gdg_spatializer *const *spats, const double *const *in, double *const *out, uint32_t n_out, size_t n, uint32_t sample_rate);
 int gdg_cluster_wait(gdg_cluster *cluster, int ticket);
+/* The same block WITH the level meter and the metronome of controller.go:2710-2771.  meters[m] (array of gdg_cluster_size
+ * entries, or NULL; entries may be NULL) is member m's level meter, created on member m's device with 2 * cnt_m + 3 channels
+ * for its cnt_m channels: [0, cnt_m) inputs, [cnt_m, 2 cnt_m) chain outputs, then the metronome port and master left / right -
+ * those three are fed on member 0 only (it owns the summed master); the reference's meter channel c of controller.go:2710-2714
+ * is channel c - first_m of member m's meter, its output channel C + c is cnt_m + c - first_m.  `metronome`: see
+ * gdg_controller_submit_aux; the row is added to the master inside the peer-memory sum (spatializer.go:300-308). */
+int gdg_cluster_submit_aux(gdg_cluster *cluster, gdg_chain *const *chains, uint32_t channels, gdg_tuner *tuner, int tuner_channel,
+                           gdg_spatializer *const *spats, gdg_meter *const *meters, const double *const *in, const double *metronome,
+                           int metronome_to_master, double *const *out, uint32_t n_out, size_t n, uint32_t sample_rate);
+/* ... and on ENCODED host rows (GDG_FORMAT_*, see gdg_controller_submit_encoded): every member decodes / encodes its own rows
+ * inside its segment kernels, the master pair comes back from member 0 in out_format */
+int gdg_cluster_submit_encoded(gdg_cluster *cluster, gdg_chain *const *chains, uint32_t channels, gdg_tuner *tuner, int tuner_channel,
+                               gdg_spatializer *const *spats, gdg_meter *const *meters, const void *const *in, int in_format,
+                               void *const *out, int out_format, uint32_t n_out, size_t n, uint32_t sample_rate);
 int gdg_cluster_process(gdg_cluster *cluster, gdg_chain *const *chains, uint32_t channels, gdg_tuner *tuner, int tuner_channel,
                         gdg_spatializer *const *spats, const double *const *in, double *const *out, uint32_t n_out, size_t n, uint32_t sample_rate);
 
