@@ -401,6 +401,12 @@ class BatchRunner:
         if self._lib.gdg_process_batch_device(self._arr, len(self.chains), d_in_ptr, d_out_ptr, stride, n, sample_rate, stream) < 0:
             raise GdgError(self._lib.gdg_last_error().decode())
 
+    def process_device_encoded(self, d_in_ptr, in_format, in_stride_bytes, d_out_ptr, out_format, out_stride_bytes, n, sample_rate, stream=None):
+        """gdg_process_batch_device_encoded: payload rows already on the device, decoded / encoded inside the segment kernels"""
+        if self._lib.gdg_process_batch_device_encoded(self._arr, len(self.chains), d_in_ptr, FORMATS.index(in_format), in_stride_bytes,
+                                                      d_out_ptr, FORMATS.index(out_format), out_stride_bytes, n, sample_rate, stream) < 0:
+            raise GdgError(self._lib.gdg_last_error().decode())
+
     def process_host(self, in_ptrs, out_ptrs, n, sample_rate):
         if self._lib.gdg_process_batch(self._arr, len(self.chains), in_ptrs, out_ptrs, n, sample_rate) < 0:
             raise GdgError(self._lib.gdg_last_error().decode())
@@ -586,7 +592,7 @@ def controller_process(chains, tuner, tuner_channel, spat, inputs, sample_rate, 
     return out
 
 
-def controller_submit(chains, tuner, tuner_channel, spat, inputs, outputs, sample_rate, meter=None):
+def controller_submit(chains, tuner, tuner_channel, spat, inputs, outputs, sample_rate, meter=None, metronome=None, metronome_to_master=True):
     """gdg_controller_submit: enqueue one block without waiting.  `inputs` [C][n] and `outputs` [C (+2)][n] are caller-owned
     C-contiguous float64 arrays that must stay alive (inputs untouched) until controller_wait(ticket).  Returns the ticket."""
     lib = chains[0]._lib
@@ -596,8 +602,12 @@ def controller_submit(chains, tuner, tuner_channel, spat, inputs, outputs, sampl
     n_out = outputs.shape[0]
     ip = (C.c_void_p * c)(*[inputs[i].ctypes.data for i in range(c)])
     op = (C.c_void_p * n_out)(*[outputs[i].ctypes.data for i in range(n_out)])
-    t = lib.gdg_controller_submit(_handles(chains), c, tuner._h if tuner else None, tuner_channel, spat._h if spat else None,
-                                  meter._h if meter else None, ip, op, n_out, n, sample_rate)
+    if metronome is not None:                     # the row is uploaded inside the call: it need not outlive it
+        t = lib.gdg_controller_submit_aux(_handles(chains), c, tuner._h if tuner else None, tuner_channel, spat._h if spat else None,
+                                          meter._h if meter else None, ip, _ptr(_f64(metronome)), 1 if metronome_to_master else 0, op, n_out, n, sample_rate)
+    else:
+        t = lib.gdg_controller_submit(_handles(chains), c, tuner._h if tuner else None, tuner_channel, spat._h if spat else None,
+                                      meter._h if meter else None, ip, op, n_out, n, sample_rate)
     if t < 0:
         raise GdgError(lib.gdg_last_error().decode())
     return t

@@ -228,7 +228,8 @@ int gdg_controller_wait(int ticket);
  * metronome.Process just wrote (the reference hands it to the spatializer as auxInputBuffer, spatializer.go:300-308), or NULL
  * when there is no metronome.  It feeds level-meter channel 2C (controller.go:2735-2738) and - when metronome_to_master is
  * non-zero (controller.go:2746-2748 metrMasterOutput) - is added to both master channels.  The metronome generator itself
- * stays on the host (out of scope). */
+ * stays on the host (out of scope).  With the _submit call the row is like the rows of `in`: leave it untouched
+ * until gdg_controller_wait (a pageable row has been staged when the call returns, a pinned one is read asynchronously). */
 int gdg_controller_process_aux(gdg_chain *const *chains, uint32_t channels, gdg_tuner *tuner, int tuner_channel,
                                gdg_spatializer *spat, gdg_meter *meter, const double *const *in, const double *metronome,
                                int metronome_to_master, double *const *out, uint32_t n_out, size_t n, uint32_t sample_rate);

@@ -523,3 +523,77 @@ def test_tuner_analyze_batch_equals_single_calls(lib):
         assert b["note"] == note == o["note"] and b["cents"] == o["cents"]
         assert abs(b["frequency"] - o["frequency"]) <= 1e-9 * o["frequency"]
     assert [t.analyze() for t in tuners] == batch
+
+
+# ---- ABI entry points that had no test of their own ---------------------------------------------------------------
+def test_controller_submit_aux_two_blocks_in_flight(lib):
+    """gdg_controller_submit_aux: the ticketed call with the metronome row (controller.go:2722-2761), two blocks in flight,
+    against the blocking call on a second set of chains."""
+    fs, n, C, blocks = 96000, 1024, 4, 6
+    spec = [("overdrive", {"gain": 9}, {"oversampling": "2"}), ("delay", {"delay_time": 5}, {})]
+    a = [common.build_chain(gdg.Chain(lib=lib), spec) for _ in range(C)]
+    b = [common.build_chain(gdg.Chain(lib=lib), spec) for _ in range(C)]
+    sa, sb = gdg.Spatializer(C, lib=lib), gdg.Spatializer(C, lib=lib)
+    ma, mb = gdg.Meter(2 * C + 3, lib=lib), gdg.Meter(2 * C + 3, lib=lib)
+    ma.set_enabled(True); mb.set_enabled(True)
+    for c in range(C):
+        sa.set_azimuth(c, -60.0 + 40.0 * c); sb.set_azimuth(c, -60.0 + 40.0 * c)
+    rng = np.random.default_rng(23)
+    x = np.stack([common.synth_fast(c, fs, blocks * n, 2) for c in range(C)])
+    ins = [np.ascontiguousarray(x[:, k * n:(k + 1) * n]) for k in range(blocks)]
+    clicks = [np.where(np.arange(n) < 64, 0.2 * rng.uniform(-1, 1, n), 0.0) for _ in range(blocks)]
+    outs = [np.zeros((C + 2, n)) for _ in range(blocks)]
+    prev = None
+    for k in range(blocks):
+        t = gdg.controller_submit(a, None, -1, sa, ins[k], outs[k], fs, meter=ma, metronome=clicks[k], metronome_to_master=k % 3 != 1)
+        if prev is not None:
+            gdg.controller_wait(prev, lib)
+        prev = t
+    gdg.controller_wait(prev, lib)
+    for k in range(blocks):
+        ref = gdg.controller_process(b, None, -1, sb, ins[k], fs, meter=mb, metronome=clicks[k], metronome_to_master=k % 3 != 1)
+        assert np.array_equal(outs[k], ref), k
+        assert np.max(np.abs(ref[C:])) > 0
+    for c in range(2 * C + 3):
+        assert ma.state(c) == mb.state(c), c
+    assert ma.analyze(2 * C)[0] > -60
+
+
+def _device_rows(lib, host_u8):
+    """a [rows][bytes] uint8 array as device memory of the backend under test: (pointer, keep-alive, fetch())"""
+    if gdg.backend_name(lib).startswith("cuda"):
+        import torch
+        t = torch.from_numpy(host_u8).cuda()
+        return t.data_ptr(), t, lambda: t.cpu().numpy()
+    buf = host_u8.copy()                                   # the emulation's device memory is host memory
+    return buf.ctypes.data, buf, lambda: buf
+
+
+@pytest.mark.parametrize("fmt_in,fmt_out", [("PCM16", "PCM24"), ("IEEE32", "PCM16"), ("PCM8", "IEEE64")])
+def test_process_batch_device_encoded(lib, fmt_in, fmt_out):
+    """gdg_process_batch_device_encoded: payload rows that already sit on the device (row strides larger than the rows),
+    byte-exact against the host-row call on a second set of chains."""
+    fs, n, C, blocks = 48000, 2048, 5, 3
+    spec = [("distortion", {"gain": 12}, {"oversampling": "4"}), ("tone_stack", {}, {}), ("chorus", {}, {})]
+    a = [common.build_chain(gdg.Chain(lib=lib), spec) for _ in range(C)]
+    b = [common.build_chain(gdg.Chain(lib=lib), spec) for _ in range(C)]
+    runner = gdg.BatchRunner(a)
+    bi = lib.gdg_format_bytes_per_sample(gdg.FORMATS.index(fmt_in)); bo = lib.gdg_format_bytes_per_sample(gdg.FORMATS.index(fmt_out))
+    si, so = n * bi + 64, n * bo + 128                     # strides: rows do not touch
+    x = np.stack([common.synth_fast(c, fs, blocks * n, 2) for c in range(C)])
+    for k in range(blocks):
+        rows = [orc.wave_encode(fmt_in, x[c, k * n:(k + 1) * n]).tobytes() for c in range(C)]
+        hin = np.zeros((C, si), dtype=np.uint8)
+        for c in range(C):
+            hin[c, :n * bi] = np.frombuffer(rows[c], dtype=np.uint8)
+        pin, keep_in, _ = _device_rows(lib, hin)
+        pout, keep_out, fetch = _device_rows(lib, np.full((C, so), 0xA5, dtype=np.uint8))
+        runner.process_device_encoded(pin, fmt_in, si, pout, fmt_out, so, n, fs)
+        lib.gdg_synchronize()
+        got = fetch()
+        want = gdg.process_batch_encoded(b, rows, fmt_in, fmt_out, n, fs)
+        for c in range(C):
+            assert got[c, :n * bo].tobytes() == want[c], (k, c)
+            assert np.all(got[c, n * bo:] == 0xA5)          # nothing written between the rows
+    with pytest.raises(gdg.GdgError, match="stride too small"):
+        runner.process_device_encoded(pin, fmt_in, n * bi - 1, pout, fmt_out, so, n, fs)
