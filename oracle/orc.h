@@ -13,6 +13,12 @@
  * tuner/tuner_test.go (+ tuner/samples/ WAV tails) - see tests/test_oracle_goldens.py.
  * Units, chain driver, IR algebra and spatializer have NO tests in the reference
  * ("parity unpinned by the reference").  For those rows the pin is
+ * (i) OUTPUTS OF THE REFERENCE'S OWN SOURCES: tests/golden/go2py translates the .go
+ * files mechanically to Python (its translation is validated on the reference's own
+ * unit-test vectors), executes every unit / the chain driver / the power amp's IR
+ * algebra / the spatializer / the level meter, and this oracle must reproduce the 267
+ * recorded streams at <= 1e-12 (tests/test_reference_translated.py, vectors committed
+ * under tests/golden/translated_reference_vectors.*); further
  * (ii) a second restatement written independently from the Go sources in Python
  * (tests/goref.py, parameter tables extracted from the Go Parameter{} literals),
  * diffed against this oracle at <= 1e-12 per unit / parameter corner / CHAIN12 /
@@ -20,8 +26,8 @@
  * closed forms (distortion = clamp, ECC83 = tanh(g x / 2), excess = triangle fold,
  * ...): tests/test_oracle_crosscheck.py, part of the CPU suite.
  *
- * The Go toolchain is absent from the build image, so the reference itself can
- * not be executed; math.Sin/Exp/Atan/Pow/Log10 are replaced by glibc libm
+ * The Go toolchain is absent from the build image, so the reference binary itself
+ * can not be executed; math.Sin/Exp/Atan/Pow/Log10 are replaced by glibc libm
  * (<= 1-2 ulp apart; far inside the 1e-9 RMS budget).
  */
 #ifndef ORC_H
