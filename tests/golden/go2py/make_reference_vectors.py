@@ -140,28 +140,31 @@ def main():
 
     seen = set()
 
-    def stream_case(kind, label, spec, fs, n, blocks, seed, ir_name=None, edits=None):
-        ident = json.dumps([spec, fs, n, blocks, seed, ir_name, sorted((edits or {}).items())], sort_keys=True, default=list)
+    def stream_case(kind, label, spec, fs, n, blocks, seed, ir_name=None, edits=None, ns=None, amp=1.0):
+        """ns: block lengths when they vary (then n is the longest and blocks = len(ns))"""
+        ident = json.dumps([spec, fs, n, blocks, seed, ir_name, sorted((edits or {}).items()), ns, amp], sort_keys=True, default=list)
         if ident in seen:                                             # e.g. a unit whose only discrete parameter has one value
             return
         seen.add(ident)
-        key, x = signal(fs, n * blocks, seed)
+        lens = list(ns) if ns else [n] * blocks
+        key, x = signal(fs, sum(lens), seed)
         t0 = time.time()
         ch = ref.chain(spec, ir_name)
-        ys = []
-        for k in range(blocks):
+        ys, pos = [], 0
+        for k in range(len(lens)):
             for op in (edits or {}).get(k, ()):                       # chain edits BEFORE block k
                 r = getattr(ch, op[0])(*op[1:])
                 if isinstance(r, tuple):
                     r = r[-1]
                 assert r is None, (op, r)
-            ys.append(ref.process(ch, x[k * n:(k + 1) * n], fs))
+            ys.append(ref.process(ch, amp * x[pos:pos + lens[k]], fs))
+            pos += lens[k]
         y = np.concatenate(ys)
         assert np.all(np.isfinite(y)), label
         cid = "c%04d" % len(cases)
         arrays[cid] = y
         cases.append({"id": cid, "kind": kind, "label": label, "spec": [[u, nu, di] for u, nu, di in spec], "ir": ir_name, "fs": fs, "n": n,
-                      "blocks": blocks, "input": key, "edits": {str(k): [list(op) for op in v] for k, v in (edits or {}).items()},
+                      "blocks": len(lens), "ns": lens, "amp": amp, "input": key, "edits": {str(k): [list(op) for op in v] for k, v in (edits or {}).items()},
                       "peak": float(np.max(np.abs(y)))})
         print("%-6s %-64s %6.1f s  peak %.3g" % (cid, label[:64], time.time() - t0, np.max(np.abs(y))), flush=True)
 
@@ -205,6 +208,55 @@ def main():
     stream_case("chain", "edits between blocks: move, bypass, remove, append", base, 48000, 256, 8, 25,
                 edits={1: [("MoveDown", 0)], 2: [("SetBypass", 2, True)], 3: [("MoveUp", 3)], 4: [("RemoveUnit", 1)],
                        5: [("AppendUnit", ref.unit_names.index("ring_modulator")), ("SetBypass", 3, False)], 6: [("SetBypass", 1, False)]})
+
+    # ---- block length changes between calls (the up-sampler's history is re-made, the decimator's tail survives: oversampling.go:74-84)
+    for name in os_units:
+        for f in ("2", "4"):
+            stream_case("varn", "%s x%s, block length changes" % (name, f), [(name, {"gain": 9}, {"oversampling": f})], 96000, 512, 0, 61,
+                        ns=[256, 256, 512, 128, 128, 256, 64, 512])
+    stream_case("varn", "delay / chorus / reverb / tone_stack, block length changes",
+                [("delay", {"delay_time": 4}, {}), ("chorus", {}, {}), ("reverb", {}, {}), ("tone_stack", {}, {})], 48000, 1024, 0, 62,
+                ns=[128, 1024, 256, 256, 64, 512, 32, 1024])
+    stream_case("varn", "power amp (short response), block length changes", [("power_amp", {"level_1": -3}, {"filter_order": "512", "filter_1": pa})],
+                48000, 512, 0, 63, ns=[256, 512, 128, 128, 512, 64])
+
+    # ---- random chains: units, parameter values, block length and rate drawn at random (seeded) ------------------------------
+    rates = [22050, 32000, 44100, 48000, 88200, 96000, 192000]
+    schema = {u: ref.params(u) for u in ref.unit_names}
+    for seed in range(48):
+        rng = np.random.default_rng(7000 + seed)
+        fs = int(rng.choice(rates))
+        n = int(rng.choice([64, 256, 1024, 2048]))
+        spec = []
+        for _ in range(int(rng.integers(2, 9))):
+            u = str(rng.choice(ref.unit_names))
+            num, disc = schema[u]
+            numeric, discrete = {}, {}
+            for k, (mn, mx, _d) in num.items():
+                if rng.random() >= 0.35:
+                    numeric[k] = int(rng.integers(mn, mx + 1))
+            for k, (vals, _d) in disc.items():
+                if rng.random() < 0.35:
+                    continue
+                if u == "power_amp" and k == "filter_order":
+                    vals = [v for v in vals if int(v) <= 8192]
+                if u == "power_amp" and k.startswith("filter_") and k != "filter_order":
+                    vals = ["- NONE -"] + IR_NAMES[:2]
+                discrete[k] = str(rng.choice(vals))
+            if u == "power_amp" and "filter_order" not in discrete:
+                discrete["filter_order"] = "8192"
+            if u == "power_amp" and all(discrete.get("filter_%d" % i, "- NONE -") == "- NONE -" for i in range(1, 9)):
+                discrete["filter_1"] = IR_NAMES[0]                     # a power amp without a response is silence (covered above)
+            spec.append((u, numeric, discrete))
+        if fs in (22050, 44100, 88200) and any(u[0] in ("flanger", "phaser") for u in spec):
+            fs = 48000                                                 # the reference panics there at depth 100 (see below)
+        # discontinuous units where their input is bit-identical (tests/test_random_chains.py): gates, then one octaver / auto_yoy
+        gates = [u for u in spec if u[0] == "noise_gate"]
+        octs = [u for u in spec if u[0] in ("octaver", "auto_yoy")][:1]
+        spec = gates + octs + [u for u in spec if u[0] not in ("noise_gate", "octaver", "auto_yoy")]
+        blocks = 3 if n >= 1024 else 5
+        stream_case("random", "seed %d: %s @%d n=%d" % (seed, "+".join(u[0] for u in spec), fs, n), spec, fs, n, blocks, 100 + seed,
+                    amp=float(rng.choice([0.15, 1.0, 1.4])))
 
     # ---- spatializer ------------------------------------------------------------------------------------------------------
     C, fs, n, blocks = 5, 96000, 512, 4

@@ -44,13 +44,14 @@ def apply_edit(chain, op):
 
 
 def run_case(chain, case):
-    x = Z[case["input"]]
-    n, fs = case["n"], case["fs"]
-    ys = []
-    for k in range(case["blocks"]):
+    x = case["amp"] * Z[case["input"]]
+    fs = case["fs"]
+    ys, pos = [], 0
+    for k, n in enumerate(case["ns"]):
         for op in case["edits"].get(str(k), ()):
             apply_edit(chain, op)
-        ys.append(chain.process(x[k * n:(k + 1) * n], fs))
+        ys.append(chain.process(np.ascontiguousarray(x[pos:pos + n]), fs))
+        pos += n
     return np.concatenate(ys)
 
 
@@ -101,13 +102,14 @@ def test_product_reproduces_translated_reference(kind, group, backend):
         chain = common.build_chain(gdg.Chain(bank, lib=lib), spec_of(case), case["ir"])
         y = run_case(chain, case)
         ref = Z[case["id"]]
-        n = case["n"]
-        for k in range(case["blocks"]):
-            e = common.rms(y[k * n:(k + 1) * n] - ref[k * n:(k + 1) * n])
-            r = common.rms(ref[k * n:(k + 1) * n])
+        pos = 0
+        for k, n in enumerate(case["ns"]):
+            e = common.rms(y[pos:pos + n] - ref[pos:pos + n])
+            r = common.rms(ref[pos:pos + n])
             assert e <= common.TOL_RMS, "%s (%s) block %d: rms error %.3e" % (case["id"], case["label"], k, e)
             if r > 1e-6:
                 assert e <= 1e-8 * r, "%s (%s) block %d: relative rms error %.3e" % (case["id"], case["label"], k, e / r)
+            pos += n
         n_cases += 1
     assert n_cases > 0
 
