@@ -316,6 +316,66 @@ def main():
     meter = {"fs": fs, "n": n, "blocks": blocks, "readouts": reads}
     print("level meter read-outs:", reads[-1])
 
+    # ---- parameter tables (effects.Unit.Parameters through signal.Chain, the power amp after PreparePowerAmp) and error strings ----
+    ch = ref.signal.CreateChain(ref.irs)
+    tables = []
+    for t in range(len(ref.unit_names)):
+        uid, err = ch.AppendUnit(t)
+        assert err is None
+        ps, err = ch.Parameters(uid)
+        assert err is None
+        tables.append([{"Name": p.Name, "Type": int(p.Type), "PhysicalUnit": p.PhysicalUnit, "Minimum": int(p.Minimum), "Maximum": int(p.Maximum),
+                        "NumericValue": int(p.NumericValue), "DiscreteValueIndex": int(p.DiscreteValueIndex),
+                        "DiscreteValues": list(p.DiscreteValues) if p.DiscreteValues is not None else []} for p in ps])
+        assert ch.UnitType(uid)[0] == t and ch.GetBypass(uid)[0] is True          # appended bypassed (signal.go:74)
+    ch = ref.signal.CreateChain(ref.irs)
+    od, _ = ch.AppendUnit(ref.unit_names.index("overdrive"))
+
+    def msg(r):
+        e = r[-1] if isinstance(r, tuple) else r
+        assert e is not None
+        return e.Error()
+    errors = {
+        "set_numeric_value out of range": msg(ch.SetNumericValue(od, "gain", 31)),
+        "set_numeric_value unknown": msg(ch.SetNumericValue(od, "nope", 1)),
+        "set_numeric_value on discrete": msg(ch.SetNumericValue(od, "valve", 1)),
+        "set_discrete_value bad value": msg(ch.SetDiscreteValue(od, "valve", "EL34")),
+        "set_discrete_value on numeric": msg(ch.SetDiscreteValue(od, "gain", "x")),
+        "get_discrete_value on numeric": msg(ch.GetDiscreteValue(od, "gain")),
+        "get_numeric_value unknown": msg(ch.GetNumericValue(od, "nope")),
+        "set_numeric_value no unit": msg(ch.SetNumericValue(7, "gain", 1)),
+        "set_bypass true no unit": msg(ch.SetBypass(3, True)),
+        "set_bypass false no unit": msg(ch.SetBypass(3, False)),
+        "get_bypass no unit": msg(ch.GetBypass(3)),
+        "remove_unit -1": msg(ch.RemoveUnit(-1)),
+        "move_up 0": msg(ch.MoveUp(0)),
+        "move_down 0": msg(ch.MoveDown(0)),
+        "unit_type no unit": msg(ch.UnitType(5)),
+        "append_unit 21": msg(ch.AppendUnit(21)),
+        "parameters no unit": msg(ch.Parameters(9)),
+    }
+    assert ch.GetNumericValue(od, "gain")[0] == 0                              # a rejected value leaves the parameter unchanged
+    print("parameter tables of %d units, %d error strings" % (len(tables), len(errors)))
+
+    # ---- tuner.Process / Analyze on synthetic tones (the six recordings of tuner_test.go are in the self-check / oracle goldens) ----
+    tn = ref.loader.load("tuner")
+    tuner_cases = []
+    for f0, fs, n in ((82.4069, 96000, 8192), (110.0, 48000, 4096), (329.63, 44100, 2048), (246.94, 192000, 8192)):
+        t = np.arange(2 * 96000) / fs
+        x = 0.5 * np.sin(2 * np.pi * f0 * t) + 0.2 * np.sin(2 * np.pi * 2 * f0 * t + 0.4) + 0.1 * np.sin(2 * np.pi * 3 * f0 * t + 1.1)
+        nb = (96000 + 3 * n) // n                                                # more than one ring of 96000 samples
+        x = x[:nb * n]
+        tu = tn.Create()
+        for k in range(nb):
+            tu.Process(G.lit([float(v) for v in x[k * n:(k + 1) * n]], 'f'), fs)
+        t0 = time.time()
+        res, err = tu.Analyze()
+        assert err is None, err
+        key = "tuner_%d_%d" % (int(f0), fs)
+        arrays[key] = x
+        tuner_cases.append({"input": key, "fs": fs, "n": n, "f0": f0, "note": res.Note(), "cents": int(res.Cents()), "frequency": float(res.Frequency())})
+        print("tuner %.2f Hz @%d: %s %+d cents %.4f Hz (%.1f s)" % (f0, fs, res.Note(), res.Cents(), res.Frequency(), time.time() - t0))
+
     # ---- the reference's out-of-range read: flanger / phaser at 22.05 / 44.1 / 88.2 kHz with depth 100 --------
     panics = []
     for unit, fs, n in (("flanger", 44100, 64), ("phaser", 22050, 32), ("flanger", 88200, 128), ("flanger", 48000, 64)):
@@ -334,7 +394,7 @@ def main():
     np.savez_compressed(OUT + ".npz", **arrays)
     manifest = {"generator": "tests/golden/go2py/make_reference_vectors.py", "reference": "andrepxx/go-dsp-guitar v1.8.0 (the tree under /root/reference)",
                 "selfcheck_vectors": ref.selfcheck_vectors, "ir_names": IR_NAMES, "unit_names": ref.unit_names, "cases": cases, "spatializer": spat, "ir": ir_info,
-                "level_meter": meter, "reference_panics": panics, "integer_division_sites": sorted(G.intdiv_sites)}
+                "level_meter": meter, "reference_panics": panics, "parameters": tables, "errors": errors, "tuner": tuner_cases, "integer_division_sites": sorted(G.intdiv_sites)}
     json.dump(manifest, open(OUT + ".json", "w"), indent=0)
     print("%d stream cases, %d arrays, %.1f MB" % (len(cases), len(arrays), os.path.getsize(OUT + ".npz") / 1e6))
     print("integer-division sites executed:", sorted(G.intdiv_sites))

@@ -225,3 +225,97 @@ def test_reference_panics_where_the_documented_difference_says():
     for key in (("flanger", 44100), ("phaser", 22050), ("flanger", 88200)):
         assert got[key] is not None and "index out of range [-1]" in got[key]["message"], key
     assert got[("flanger", 48000)] is None
+
+
+# ---- parameter tables, error strings (effects.Unit / signal.Chain API surface) ------------------------
+def _three_response_banks(lib):
+    """the responses the generator imported (manifest ir_names), in index.json order like filter.Import keeps them"""
+    z = np.load(os.path.join(GOLD, "ir_bank.npz"))
+    ob, pb = orc.IRBank(), gdg.IRBank(lib)
+    for k, name in enumerate(z["names"]):
+        if str(name) in M["ir_names"]:
+            for b in (ob, pb):
+                b.add(str(name), int(z["compensation"][k]), orc.pcm16_decode(z["pcm_%02d" % k]), int(z["sample_rate"]))
+    return ob, pb
+
+
+def test_parameter_tables_equal_the_executed_reference():
+    """names, types, physical units, ranges, defaults and discrete value lists of all 21 units - the power amp's after
+    effects.PreparePowerAmp (filter_1..8 over the imported response names) - as the translated reference's Parameters() returns them"""
+    lib = common.backend_lib("emu")
+    ob, pb = _three_response_banks(lib)
+    c, o = gdg.Chain(pb, lib=lib), orc.Chain(ob)
+    for t, want in enumerate(M["parameters"]):
+        i = c.append_unit(t); o.append_unit(t)
+        got = c.parameters(i)
+        assert [p["Name"] for p in got] == [p["Name"] for p in want], UNIT_NAMES[t]
+        for g, w in zip(got, want):
+            for key in ("Type", "PhysicalUnit", "Minimum", "Maximum", "NumericValue", "DiscreteValueIndex"):
+                assert g[key] == w[key], (UNIT_NAMES[t], w["Name"], key, g[key], w[key])
+            assert list(g["DiscreteValues"]) == w["DiscreteValues"], (UNIT_NAMES[t], w["Name"])
+            if w["Type"] == 2:
+                assert o.get_numeric_value(i, w["Name"]) == w["NumericValue"]
+            elif w["Type"] == 1:
+                assert o.get_discrete_value(i, w["Name"]) == w["DiscreteValues"][w["DiscreteValueIndex"]]
+        assert c.get_bypass(i) is True and c.unit_type(i) == t
+
+
+def test_error_strings_equal_the_executed_reference():
+    lib = common.backend_lib("emu")
+    E = M["errors"]
+    for ch, exc in ((gdg.Chain(lib=lib), gdg.GdgError), (orc.Chain(), orc.OracleError)):
+        i = ch.append_unit("overdrive")
+
+        def fails(fn, *a):
+            with pytest.raises(exc) as e:
+                getattr(ch, fn)(*a)
+            return str(e.value)
+        assert fails("set_numeric_value", i, "gain", 31) == E["set_numeric_value out of range"]
+        assert fails("set_numeric_value", i, "nope", 1) == E["set_numeric_value unknown"]
+        assert fails("set_numeric_value", i, "valve", 1) == E["set_numeric_value on discrete"]
+        assert fails("set_discrete_value", i, "valve", "EL34") == E["set_discrete_value bad value"]
+        assert fails("set_discrete_value", i, "gain", "x") == E["set_discrete_value on numeric"]
+        assert fails("get_discrete_value", i, "gain") == E["get_discrete_value on numeric"]
+        assert fails("get_numeric_value", i, "nope") == E["get_numeric_value unknown"]
+        assert fails("set_numeric_value", 7, "gain", 1) == E["set_numeric_value no unit"]
+        assert fails("set_bypass", 3, True) == E["set_bypass true no unit"]
+        assert fails("set_bypass", 3, False) == E["set_bypass false no unit"]
+        assert fails("get_bypass", 3) == E["get_bypass no unit"]
+        assert fails("remove_unit", -1) == E["remove_unit -1"]
+        assert fails("move_up", 0) == E["move_up 0"]
+        assert fails("move_down", 0) == E["move_down 0"]
+        assert fails("unit_type", 5) == E["unit_type no unit"]
+        assert fails("append_unit", 21) == E["append_unit 21"]
+        assert ch.get_numeric_value(i, "gain") == 0
+
+
+# ---- tuner.Process / Analyze ---------------------------------------------------------------------------------------------
+def _tuner_check(make, analyze):
+    for t in M["tuner"]:
+        x, n = Z[t["input"]], t["n"]
+        tu = make()
+        for k in range(len(x) // n):
+            tu.process(np.ascontiguousarray(x[k * n:(k + 1) * n]), t["fs"])
+        note, cents, freq = analyze(tu)
+        assert (note, cents) == (t["note"], t["cents"]), (t["f0"], note, cents)
+        assert abs(freq - t["frequency"]) <= 1e-9 * t["frequency"], (t["f0"], freq, t["frequency"])
+        assert abs(freq - t["f0"]) < 0.02 * t["f0"]
+
+
+def _tuner_fields(r):
+    if isinstance(r, dict):
+        return r["note"], int(r["cents"]), float(r["frequency"])
+    if hasattr(r, "note"):
+        nt = r.note.decode() if isinstance(r.note, bytes) else r.note
+        return nt, int(r.cents), float(r.frequency)
+    return r[0], int(r[1]), float(r[2])
+
+
+def test_oracle_tuner_reproduces_translated_reference():
+    _tuner_check(orc.Tuner, lambda tu: _tuner_fields(tu.analyze()))
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_product_tuner_reproduces_translated_reference(backend):
+    lib = common.backend_lib(backend)
+    _tuner_check(lambda: gdg.Tuner(lib=lib), lambda tu: _tuner_fields(tu.analyze()))
