@@ -46,6 +46,12 @@ def test_signal(fs, n_total, seed, amp=0.7):
     return amp * x * env
 
 
+def tuner_signal(f0, fs, total):
+    """three partials; the test regenerates it from (f0, fs, total) instead of storing 100k samples per case"""
+    t = np.arange(total) / fs
+    return 0.5 * np.sin(2 * np.pi * f0 * t) + 0.2 * np.sin(2 * np.pi * 2 * f0 * t + 0.4) + 0.1 * np.sin(2 * np.pi * 3 * f0 * t + 1.1)
+
+
 class Ref(object):
     """the translated reference"""
 
@@ -140,9 +146,10 @@ def main():
 
     seen = set()
 
-    def stream_case(kind, label, spec, fs, n, blocks, seed, ir_name=None, edits=None, ns=None, amp=1.0):
-        """ns: block lengths when they vary (then n is the longest and blocks = len(ns))"""
-        ident = json.dumps([spec, fs, n, blocks, seed, ir_name, sorted((edits or {}).items()), ns, amp], sort_keys=True, default=list)
+    def stream_case(kind, label, spec, fs, n, blocks, seed, ir_name=None, edits=None, ns=None, amp=1.0, fss=None):
+        """ns: block lengths when they vary (then n is the longest and blocks = len(ns)); fss: the sample rate of every block when
+        it changes between calls"""
+        ident = json.dumps([spec, fs, n, blocks, seed, ir_name, sorted((edits or {}).items()), ns, amp, fss], sort_keys=True, default=list)
         if ident in seen:                                             # e.g. a unit whose only discrete parameter has one value
             return
         seen.add(ident)
@@ -157,14 +164,14 @@ def main():
                 if isinstance(r, tuple):
                     r = r[-1]
                 assert r is None, (op, r)
-            ys.append(ref.process(ch, amp * x[pos:pos + lens[k]], fs))
+            ys.append(ref.process(ch, amp * x[pos:pos + lens[k]], fss[k] if fss else fs))
             pos += lens[k]
         y = np.concatenate(ys)
         assert np.all(np.isfinite(y)), label
         cid = "c%04d" % len(cases)
         arrays[cid] = y
         cases.append({"id": cid, "kind": kind, "label": label, "spec": [[u, nu, di] for u, nu, di in spec], "ir": ir_name, "fs": fs, "n": n,
-                      "blocks": len(lens), "ns": lens, "amp": amp, "input": key, "edits": {str(k): [list(op) for op in v] for k, v in (edits or {}).items()},
+                      "blocks": len(lens), "ns": lens, "fss": list(fss) if fss else [fs] * len(lens), "amp": amp, "input": key, "edits": {str(k): [list(op) for op in v] for k, v in (edits or {}).items()},
                       "peak": float(np.max(np.abs(y)))})
         print("%-6s %-64s %6.1f s  peak %.3g" % (cid, label[:64], time.time() - t0, np.max(np.abs(y))), flush=True)
 
@@ -219,6 +226,16 @@ def main():
                 ns=[128, 1024, 256, 256, 64, 512, 32, 1024])
     stream_case("varn", "power amp (short response), block length changes", [("power_amp", {"level_1": -3}, {"filter_order": "512", "filter_1": pa})],
                 48000, 512, 0, 63, ns=[256, 512, 128, 128, 512, 64])
+
+    # ---- the sample rate changes between calls (units re-derive coefficients, delay-type units re-make their histories) ----------
+    rates_seq = [48000] * 3 + [96000] * 3 + [48000] * 2 + [192000] * 2
+    for spec in ([("delay", {"delay_time": 3}, {}), ("chorus", {}, {})], [("reverb", {"mix": 60}, {})], [("flanger", {}, {}), ("phaser", {}, {})],
+                 [("tone_stack", {}, {}), ("cabinet", {}, {}), ("bandpass", {}, {}), ("auto_wah", {}, {})],
+                 [("overdrive", {"gain": 10}, {"oversampling": "2"}), ("fuzz", {}, {"oversampling": "4"})],
+                 [("compressor", {}, {}), ("tremolo", {}, {}), ("ring_modulator", {}, {}), ("signal_generator", {"signal_amplitude": 20}, {})],
+                 [("noise_gate", {}, {}), ("octaver", {}, {})], [("auto_yoy", {}, {})],
+                 [("power_amp", {"level_1": -3}, {"filter_order": "1024", "filter_1": pa})]):
+        stream_case("ratechange", "%s, sample rate changes" % "+".join(u[0] for u in spec), spec, 48000, 256, 0, 71, ns=[256] * len(rates_seq), fss=rates_seq)
 
     # ---- random chains: units, parameter values, block length and rate drawn at random (seeded) ------------------------------
     rates = [22050, 32000, 44100, 48000, 88200, 96000, 192000]
@@ -361,19 +378,15 @@ def main():
     tn = ref.loader.load("tuner")
     tuner_cases = []
     for f0, fs, n in ((82.4069, 96000, 8192), (110.0, 48000, 4096), (329.63, 44100, 2048), (246.94, 192000, 8192)):
-        t = np.arange(2 * 96000) / fs
-        x = 0.5 * np.sin(2 * np.pi * f0 * t) + 0.2 * np.sin(2 * np.pi * 2 * f0 * t + 0.4) + 0.1 * np.sin(2 * np.pi * 3 * f0 * t + 1.1)
         nb = (96000 + 3 * n) // n                                                # more than one ring of 96000 samples
-        x = x[:nb * n]
+        x = tuner_signal(f0, fs, nb * n)
         tu = tn.Create()
         for k in range(nb):
             tu.Process(G.lit([float(v) for v in x[k * n:(k + 1) * n]], 'f'), fs)
         t0 = time.time()
         res, err = tu.Analyze()
         assert err is None, err
-        key = "tuner_%d_%d" % (int(f0), fs)
-        arrays[key] = x
-        tuner_cases.append({"input": key, "fs": fs, "n": n, "f0": f0, "note": res.Note(), "cents": int(res.Cents()), "frequency": float(res.Frequency())})
+        tuner_cases.append({"blocks": nb, "fs": fs, "n": n, "f0": f0, "note": res.Note(), "cents": int(res.Cents()), "frequency": float(res.Frequency())})
         print("tuner %.2f Hz @%d: %s %+d cents %.4f Hz (%.1f s)" % (f0, fs, res.Note(), res.Cents(), res.Frequency(), time.time() - t0))
 
     # ---- the reference's out-of-range read: flanger / phaser at 22.05 / 44.1 / 88.2 kHz with depth 100 --------

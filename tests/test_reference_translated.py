@@ -45,12 +45,11 @@ def apply_edit(chain, op):
 
 def run_case(chain, case):
     x = case["amp"] * Z[case["input"]]
-    fs = case["fs"]
     ys, pos = [], 0
     for k, n in enumerate(case["ns"]):
         for op in case["edits"].get(str(k), ()):
             apply_edit(chain, op)
-        ys.append(chain.process(np.ascontiguousarray(x[pos:pos + n]), fs))
+        ys.append(chain.process(np.ascontiguousarray(x[pos:pos + n]), case["fss"][k]))
         pos += n
     return np.concatenate(ys)
 
@@ -292,7 +291,10 @@ def test_error_strings_equal_the_executed_reference():
 # ---- tuner.Process / Analyze ---------------------------------------------------------------------------------------------
 def _tuner_check(make, analyze):
     for t in M["tuner"]:
-        x, n = Z[t["input"]], t["n"]
+        n = t["n"]
+        tt = np.arange(t["blocks"] * n) / t["fs"]                  # make_reference_vectors.tuner_signal
+        f0 = t["f0"]
+        x = 0.5 * np.sin(2 * np.pi * f0 * tt) + 0.2 * np.sin(2 * np.pi * 2 * f0 * tt + 0.4) + 0.1 * np.sin(2 * np.pi * 3 * f0 * tt + 1.1)
         tu = make()
         for k in range(len(x) // n):
             tu.process(np.ascontiguousarray(x[k * n:(k + 1) * n]), t["fs"])
