@@ -16,7 +16,7 @@
  * (i) OUTPUTS OF THE REFERENCE'S OWN SOURCES: tests/golden/go2py translates the .go
  * files mechanically to Python (its translation is validated on the reference's own
  * unit-test vectors), executes every unit / the chain driver / the power amp's IR
- * algebra / the spatializer / the level meter, and this oracle must reproduce the 334
+ * algebra / the spatializer / the level meter, and this oracle must reproduce the 435
  * recorded streams at <= 1e-12 (tests/test_reference_translated.py, vectors committed
  * under tests/golden/translated_reference_vectors.*); further
  * (ii) a second restatement written independently from the Go sources in Python

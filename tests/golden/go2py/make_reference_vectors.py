@@ -187,6 +187,15 @@ def main():
             for fs, n, blocks in combos:
                 stream_case("unit", "%s %s %s @%d n=%d" % (name, json.dumps(num), json.dumps(disc), fs, n), [(name, num, disc)], fs, n, blocks,
                             seed=zlib.crc32(("%s%d" % (name, fs)).encode()) % 1000)
+    # ---- every unit at the other five supported rates (filter.go:25-33), defaults, short blocks ------------------------------------
+    for name in ref.unit_names:
+        if name == "power_amp":
+            continue
+        for fs in (22050, 32000, 44100, 88200, 96000):
+            if name in ("flanger", "phaser") and fs in (22050, 44100, 88200):
+                continue                                              # the reference panics there at depth 100 (recorded below)
+            disc = {"oversampling": "2" if fs < 50000 else "4"} if name in os_units else {}
+            stream_case("rates", "%s defaults @%d n=128" % (name, fs), [(name, {}, disc)], fs, 128, 5, seed=200 + fs % 97)
     # ---- long-memory units need more blocks than their delay: low rate, many blocks --------------------------------------
     stream_case("unit", "reverb mix 70, taps reached", [("reverb", {"mix": 70}, {})], 22050, 512, 20, 5)
     stream_case("unit", "delay 30 ms feedback", [("delay", {"delay_time": 30, "feedback": -3, "level": 0}, {})], 32000, 256, 12, 6)
@@ -205,6 +214,9 @@ def main():
                 edits={2: [("SetNumericValue", 0, "level_1", -12)], 4: [("SetDiscreteValue", 0, "filter_2", "Guitar: Custom BP")]})
     stream_case("power_amp", "long response partitioned at a JACK period (HC 4-way Sub, 9599 taps at 96 kHz)",
                 [("power_amp", {"level_1": -6}, {"filter_1": "PA: HC 4-way (Sub)"})], 96000, 1024, 12, 17)
+    for fs in (22050, 32000, 44100, 48000, 88200, 96000, 192000):     # filter.Import's resampling at every supported rate
+        stream_case("power_amp", "Custom BP reduced to 256 @%d" % fs, [("power_amp", {"level_1": -2}, {"filter_order": "256", "filter_1": "Guitar: Custom BP"})],
+                    fs, 256, 3, 18)
     # ---- chains -----------------------------------------------------------------------------------------------------------
     stream_case("chain", "CHAIN12 @96 kHz n=1024", CHAIN12, 96000, 1024, 4, 21, ir_name=pa)
     stream_case("chain", "CHAIN12 @192 kHz n=2048", CHAIN12, 192000, 2048, 2, 22, ir_name=pa)
