@@ -306,7 +306,19 @@ def main():
         sp.Process(ins, a, o)
         outs.append(np.array([o[0].tolist(), o[1].tolist()]))
     arrays["spat_in"], arrays["spat_aux"], arrays["spat_out"] = xs, aux, np.concatenate(outs, axis=1)
-    spat = {"channels": C, "fs": fs, "n": n, "blocks": blocks, "geometry": geo, "aux_on_even_blocks": True}
+    spat = {"channels": C, "fs": fs, "n": n, "blocks": blocks, "geometry": geo, "aux_on_even_blocks": True, "other_rates": [192000, 44100]}
+    for rate in spat["other_rates"]:                                   # SetSampleRate never stores the rate (spatializer.go:418-431): observed here
+        sp2 = ref.spatializer.Create(C)
+        sp2.SetSampleRate(rate)
+        for c, (az, dist, lvl) in enumerate(geo):
+            assert sp2.SetAzimuth(c, az) is None and sp2.SetDistance(c, dist) is None and sp2.SetLevel(c, lvl) is None
+        outs2 = []
+        for k in range(blocks):
+            ins = G.lit([G.lit([float(v) for v in xs[c, k * n:(k + 1) * n]], 'f') for c in range(C)])
+            o = G.lit([G.make_slice(0.0, n, None, 'f'), G.make_slice(0.0, n, None, 'f')])
+            sp2.Process(ins, None, o)
+            outs2.append(np.array([o[0].tolist(), o[1].tolist()]))
+        arrays["spat_out_%d" % rate] = np.concatenate(outs2, axis=1)
     print("spatializer: %d channels x %d blocks" % (C, blocks))
 
     # ---- IR algebra: what filter.Import resampled, and Reduce / Normalize / Multiply / Add on it ---------------------------

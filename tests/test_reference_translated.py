@@ -145,6 +145,21 @@ def test_product_spatializer_reproduces_translated_reference(backend):
         assert np.max(np.abs(np.asarray(y) - ref[:, k * n:(k + 1) * n])) <= 1e-12 * max(1.0, np.max(np.abs(ref))), k
 
 
+def test_spatializer_at_other_rates_like_the_executed_reference():
+    """spatializer.SetSampleRate never stores the rate (spatializer.go:418-431), so the inter-aural delays stay those of 96 kHz:
+    the executed reference at 192 kHz and 44.1 kHz against the oracle and the emulated product (CPU)"""
+    s = M["spatializer"]
+    x, n = Z["spat_in"], s["n"]
+    lib = common.backend_lib("emu")
+    for rate in s["other_rates"]:
+        ref = Z["spat_out_%d" % rate]
+        for sp in (orc.Spatializer(s["channels"]), gdg.Spatializer(s["channels"], lib=lib)):
+            _spat_setup(sp, s["geometry"], rate)
+            for k in range(s["blocks"]):
+                y = sp.process(np.ascontiguousarray(x[:, k * n:(k + 1) * n]), None)
+                assert np.max(np.abs(np.asarray(y) - ref[:, k * n:(k + 1) * n])) <= 1e-12 * max(1.0, np.max(np.abs(ref))), (rate, k)
+
+
 # ---- filter.Import / Reduce / Normalize / Multiply ---------------------------------------------------------------------
 def _fixture_ir(name):
     z = np.load(os.path.join(GOLD, "ir_bank.npz"))
