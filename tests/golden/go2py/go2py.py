@@ -14,6 +14,37 @@ precedence, composite literals, slices (aliasing views), maps, type assertions, 
 Not supported (absent from the translated packages): goroutines, channels, select, defer, goto, labels, closures, generics.
 See goruntime.py for how values are represented."""
 import re
+from fractions import Fraction
+
+# Untyped constants are exact in Go (arbitrary precision; rounded once, when they meet a typed operand): constant expressions -
+# package-level const declarations and constant sub-expressions inside functions alike - are folded here with exact rationals
+# and emitted as the correctly rounded float64 literal.  K = (value, is_float): an int for integer constants, a Fraction
+# otherwise.  math's constants as in Go's math/const.go.
+KCONST = {"math": {
+    "Pi": (Fraction("3.14159265358979323846264338327950288419716939937510582097494459"), True),
+    "E": (Fraction("2.71828182845904523536028747135266249775724709369995957496696763"), True),
+    "Phi": (Fraction("1.61803398874989484820458683436563811772030917980576286213544862"), True),
+    "Sqrt2": (Fraction("1.41421356237309504880168872420969807856967187537694807317667974"), True),
+    "SqrtE": (Fraction("1.64872127070012814684865078781416357165377610071014801157507931"), True),
+    "SqrtPi": (Fraction("1.77245385090551602729816748334114518279754945612238712821380779"), True),
+    "SqrtPhi": (Fraction("1.27201964951406896425242246173749149171560804184009624861664038"), True),
+    "Ln2": (Fraction("0.693147180559945309417232121458176568075500134360255254120680009"), True),
+    "Ln10": (Fraction("2.30258509299404568401799145468436420760110148862877297603332790"), True),
+    "MaxInt8": (127, False), "MinInt8": (-128, False), "MaxInt16": (32767, False), "MinInt16": (-32768, False),
+    "MaxInt32": (2147483647, False), "MinInt32": (-2147483648, False), "MaxInt64": ((1 << 63) - 1, False), "MinInt64": (-(1 << 63), False),
+    "MaxUint8": (255, False), "MaxUint16": (65535, False), "MaxUint32": ((1 << 32) - 1, False), "MaxUint64": ((1 << 64) - 1, False),
+}}
+KCONST["math"]["Log2E"] = (1 / KCONST["math"]["Ln2"][0], True)
+KCONST["math"]["Log10E"] = (1 / KCONST["math"]["Ln10"][0], True)
+
+
+def kcode(k):
+    """python literal of an exact constant"""
+    v, is_float = k
+    if is_float:
+        return repr(float(v))                               # int / int true division: correctly rounded
+    return str(int(v))
+
 
 PY_RESERVED = {"False", "None", "True", "and", "as", "assert", "async", "await", "class", "def", "del", "elif", "except",
                "finally", "from", "global", "import", "in", "is", "lambda", "nonlocal", "not", "or", "pass", "raise", "try",
@@ -150,6 +181,7 @@ class Ex(object):
         self.code, self.kind, self.intconst = code, kind, intconst
         self.is_index = self.is_assert = self.is_call = False
         self.ityp = None                # a sized integer type (uint64, int32, ...) when statically known: arithmetic wraps
+        self.k = None                   # (exact value, is_float) when the expression is a Go constant expression
 
 
 def sized_int(t):
@@ -186,6 +218,9 @@ class PackageTranslator(object):
         self.methods = []               # (type, method)
         self.tmp = 0
         self.scopes, self.iota, self.nolit, self.stop_at_type_assert = [], None, 0, False
+        self.kconsts = {}               # package-level constants with an exact value: name -> (value, is_float)
+        KCONST["github.com/andrepxx/go-dsp-guitar/" + pkgname] = self.kconsts
+        KCONST[pkgname] = self.kconsts
         for path, src in files:
             for m in re.finditer(r"^type\s+(\w+)\s+(\S+)", src, re.M):
                 self._note_type(m.group(1), m.group(2))
@@ -515,6 +550,13 @@ class PackageTranslator(object):
             for nm, v in zip(names, vals):
                 code = v.code
                 kind = kind_of_type(ty) if ty else (v.kind if not v.intconst else "i")
+                if toplevel and v.k is not None and nm != "_":
+                    if ty is None:
+                        self.kconsts[nm] = v.k
+                    elif kind == "f":
+                        self.kconsts[nm] = (Fraction(float(v.k[0])), True)   # typed float constant: rounded at its declaration
+                    elif kind == "i" and not v.k[1]:
+                        self.kconsts[nm] = v.k
                 if ty and kind == "f":
                     code = "G.f64(%s)" % code
                 elif ty and ty[0] == "name" and ty[1] in INT_TYPES and v.kind == "f":
@@ -1147,7 +1189,52 @@ class PackageTranslator(object):
             right = self.parse_expr(BINPREC[op] + 1)
             left = self.binop(op, left, right, t)
 
+    def fold(self, op, a, b):
+        """exact value of `a op b` for two constants, or None"""
+        (x, xf), (y, yf) = a, b
+        f = xf or yf
+        try:
+            if op == "+":
+                return (x + y, f)
+            if op == "-":
+                return (x - y, f)
+            if op == "*":
+                return (x * y, f)
+            if op == "/":
+                if y == 0:
+                    return None
+                if not f:
+                    q = abs(x) // abs(y)
+                    return (q if (x >= 0) == (y >= 0) else -q, False)
+                return (Fraction(x) / Fraction(y), True)
+            if f:
+                return None
+            if op == "%":
+                r = abs(x) % abs(y)
+                return (r if x >= 0 else -r, False)
+            if op == "<<":
+                return (x << y, False)
+            if op == ">>":
+                return (x >> y, False)
+            if op == "&":
+                return (x & y, False)
+            if op == "|":
+                return (x | y, False)
+            if op == "^":
+                return (x ^ y, False)
+            if op == "&^":
+                return (x & ~y, False)
+        except (ZeroDivisionError, ValueError, OverflowError):
+            return None
+        return None
+
     def binop(self, op, a, b, t):
+        if a.k is not None and b.k is not None and a.ityp is None and b.ityp is None:
+            k = self.fold(op, a.k, b.k)
+            if k is not None:
+                r = Ex("(%s)" % kcode(k), "f" if k[1] else None, not k[1])
+                r.k = k
+                return r
         both_const = a.intconst and b.intconst
         if op in ("==", "!=", "<", "<=", ">", ">="):
             return Ex("(%s %s %s)" % (a.code, op, b.code), "b")
@@ -1191,6 +1278,11 @@ class PackageTranslator(object):
         if t.k == "op" and t.v in ("-", "+", "!", "^", "*", "&", "<-"):
             self.next()
             e = self.parse_unary()
+            if t.v == "-" and e.k is not None:
+                r = Ex("", "f" if e.k[1] else None, not e.k[1])
+                r.k = (-e.k[0], e.k[1])
+                r.code = "(%s)" % kcode(r.k)
+                return r
             if t.v == "-":
                 r = Ex("(-%s)" % e.code, e.kind, e.intconst)
                 if e.ityp:
@@ -1216,13 +1308,21 @@ class PackageTranslator(object):
                 val = int(txt, 8)
             else:
                 val = int(txt, 0)
-            return Ex(str(val), None, True)
+            e = Ex(str(val), None, True)
+            e.k = (val, False)
+            return e
         if t.k == "float":
-            return Ex(repr(float(t.v.replace("_", ""))), "f")
+            txt = t.v.replace("_", "")
+            e = Ex(repr(float(txt)), "f")
+            if not txt.lower().startswith("0x"):
+                e.k = (Fraction(txt), True)
+            return e
         if t.k == "imag":
             return Ex("complex(0.0, %r)" % float(t.v.replace("_", "")), "c")
         if t.k == "char":
-            return Ex(str(ord(t.v)), None, True)
+            e = Ex(str(ord(t.v)), None, True)
+            e.k = (ord(t.v), False)
+            return e
         if t.k == "string":
             return Ex(repr(t.v), "s")
         if t.k == "op" and t.v == "(":
@@ -1231,7 +1331,9 @@ class PackageTranslator(object):
             e = self.parse_expr()
             self.nolit = nolit_save
             self.expect(")")
-            return Ex("(%s)" % e.code if not e.code.startswith("(") else e.code, e.kind, e.intconst)
+            r = Ex("(%s)" % e.code if not e.code.startswith("(") else e.code, e.kind, e.intconst)
+            r.k, r.ityp = e.k, e.ityp
+            return r
         if t.k == "op" and t.v == "[":
             self.p -= 1
             ty = self.parse_type()
@@ -1268,10 +1370,17 @@ class PackageTranslator(object):
             if name == "iota":
                 if getattr(self, "iota", None) is None:
                     self.err("iota outside a constant declaration")
-                return Ex(str(self.iota), None, True)
+                e = Ex(str(self.iota), None, True)
+                e.k = (self.iota, False)
+                return e
             e = Ex(safe(name))
             e.goname = name
             e.is_global = True
+            if name in self.kconsts:
+                e.k = self.kconsts[name]
+                e.kind = "f" if e.k[1] else None
+                e.intconst = not e.k[1]
+                e.code = kcode(e.k)
             return e
         self.err("unexpected token %r in expression" % (t.v,), t)
 
@@ -1302,6 +1411,11 @@ class PackageTranslator(object):
                 self.next(); self.next()
                 a = self.parse_expr(); self.expect(")")
                 k = kind_of_type(("name", name))
+                if name == "float64" and a.k is not None:
+                    cv = Ex("", "f")
+                    cv.k = (Fraction(float(a.k[0])), True)          # a typed constant: rounded to float64 here
+                    cv.code = kcode(cv.k)
+                    return self.parse_postfix(cv)
                 if k == "f" and a.kind == "f":
                     return self.parse_postfix(Ex(a.code, "f"))
                 cv = Ex("%s(%s)" % (BASIC_CONV[name], a.code), k)
@@ -1350,6 +1464,12 @@ class PackageTranslator(object):
                 n = Ex("%s.%s" % (e.code, safe(name)))
                 if base_is_pkg:
                     n.qual = (e.goname, name)
+                    kt = KCONST.get(self.imports[e.goname], {})
+                    if name in kt:
+                        n.k = kt[name]
+                        n.kind = "f" if n.k[1] else None
+                        n.intconst = not n.k[1]
+                        n.code = kcode(n.k)
                 e = n
                 continue
             if t.v == "(":

@@ -390,3 +390,18 @@ def test_random_chains_oracle_equals_executed_reference():
     parameter extremes, any rate, varying block lengths - the C oracle against the executed reference at 1e-12 of the peak"""
     import hunt
     assert hunt.hunt(20000, 20080, REFERENCE, verbose=False) == []
+
+
+@pytest.mark.skipif(not have_reference, reason="build container only: the vectors were generated with this machine's libm")
+def test_oracle_is_bit_identical_to_the_executed_reference_here():
+    """with the same libm under both (Python's math and the C oracle link glibc here) the oracle does not just stay within
+    1e-12 of the executed reference - every one of the committed streams is reproduced bit for bit"""
+    sys.path.insert(0, HERE)
+    sys.path.insert(0, os.path.join(HERE, "..", "oracle"))
+    import common
+    import test_reference_translated as T
+    bank = common.orc.IRBank()
+    common.fill_bank_from_fixture(bank, common.orc.pcm16_decode)
+    different = [c["id"] for c in T.CASES
+                 if not np.array_equal(T.run_case(common.build_chain(common.orc.Chain(bank), T.spec_of(c), c["ir"]), c), T.Z[c["id"]])]
+    assert different == []
