@@ -2148,17 +2148,20 @@ int cluster_block(const char *who, gdg_cluster *cl, gdg_chain *const *chains, ui
     if ((master && !parts.empty()) || metro) {
         Use u(cl->ctx[0]);
         if (cl->cap_n < n) {
+            /* sized once for the longest block the library accepts: the buffers of a ticket still in flight (its master rows
+             * are copied out of h_master in gdg_cluster_wait) are never re-made under it when the block length grows */
+            const size_t cap = std::max<size_t>(n, GDG_MAX_N);
             gdgb_sync(); cl->release();
             bool ok = true;
             for (int k = 0; k < 2; k++) {
-                cl->d_master[k] = (double *)gdgb_alloc(2 * n * sizeof(double));
-                cl->d_master_enc[k] = (double *)gdgb_alloc(2 * n * sizeof(double));
-                cl->d_metro[k] = (double *)gdgb_alloc(n * sizeof(double));
-                cl->h_master[k] = (double *)gdgb_pinned_alloc(2 * n * sizeof(double));
+                cl->d_master[k] = (double *)gdgb_alloc(2 * cap * sizeof(double));
+                cl->d_master_enc[k] = (double *)gdgb_alloc(2 * cap * sizeof(double));
+                cl->d_metro[k] = (double *)gdgb_alloc(cap * sizeof(double));
+                cl->h_master[k] = (double *)gdgb_pinned_alloc(2 * cap * sizeof(double));
                 ok = ok && cl->d_master[k] && cl->d_master_enc[k] && cl->d_metro[k] && cl->h_master[k];
             }
             if (!ok) { cl->release(); backend_fail("cluster master allocation failed"); return unwind(); }
-            cl->cap_n = n;
+            cl->cap_n = cap;
         }
         const int ev = si * 28;
         void *s0 = gdgb_stream();

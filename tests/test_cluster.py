@@ -235,3 +235,33 @@ def test_cluster_encoded_rows(lib, fmt):
         ometer.process(list(dec) + list(y) + [np.zeros(n)] + list(master), fs)
     _assert_cluster_meters_agree(meters, counts, ometer)
     lib.gdg_use_device(devices[0])
+
+
+def test_cluster_block_length_grows_while_a_block_is_in_flight(lib):
+    """submit(n = 128), submit(n = 512), then the waits: the first ticket's master rows must survive the second submit (the
+    cluster's master / staging buffers are sized once for the longest block, never re-made under a ticket in flight)"""
+    ndev = lib.gdg_device_count()
+    if ndev < 2:
+        pytest.skip("needs two devices (gpurun --gpus 2)")
+    devices = list(range(min(ndev, 3)))
+    counts = [2, 2, 1][:len(devices)]
+    fs = 48000
+    cl, chains, spats, ochains, ospat = _build(lib, devices, counts, fs)
+    C = sum(counts)
+    lens = [128, 512, 256, 1024]
+    x = np.stack([common.synth_fast(c, fs, sum(lens), 2) for c in range(C)])
+    ins, outs, refs, pos = [], [], [], 0
+    for n in lens:
+        ins.append(np.ascontiguousarray(x[:, pos:pos + n])); outs.append(np.zeros((C + 2, n))); pos += n
+        refs.append(orc.controller_process(ochains, None, -1, ospat, ins[-1], fs))
+    prev = None
+    for k in range(len(lens)):
+        t = cl.submit(chains, None, -1, spats, ins[k], outs[k], fs)
+        if prev is not None:
+            cl.wait(prev)
+        prev = t
+    cl.wait(prev)
+    for k in range(len(lens)):
+        assert np.max(np.abs(outs[k][:C] - refs[k][:C])) <= 1e-9, k
+        assert np.max(np.abs(outs[k][C:] - refs[k][C:])) <= 1e-12 * max(1.0, np.max(np.abs(refs[k][C:]))), k
+    lib.gdg_use_device(devices[0])
