@@ -1,9 +1,10 @@
 #!/usr/bin/env python3
 """Random chains (1 - 6 units, parameters at random incl. their extremes, any supported rate, fixed or varying block lengths)
 through the EXECUTED reference (go2py) and the C oracle, compared block by block at 1e-12 of the peak.  Needs the reference
-tree.    python tests/golden/go2py/hunt.py FIRST_SEED LAST_SEED [--edits | --product]
+tree.    python tests/golden/go2py/hunt.py FIRST_SEED LAST_SEED [--edits | --product | --spat]
 Round 2: 4400 random chains, 3200 edit sequences (--edits: a live chain edited between blocks, error strings compared as well)
-and 3300 random chains through the emulated product (--product, 1e-9 RMS per block): 0 mismatches, no reference panic."""
+3300 random chains through the emulated product (--product, 1e-9 RMS per block) and 3200 random spatializers (--spat: oracle and
+emulated product): 0 mismatches, no reference panic."""
 import sys, os, json, time
 HERE = os.path.dirname(os.path.abspath(__file__))
 for p_ in (HERE, os.path.join(HERE, '..', '..'), os.path.join(HERE, '..', '..', '..', 'oracle')):
@@ -174,6 +175,47 @@ def hunt_edits(lo, hi, root='/root/reference', ref=None, verbose=True):
     return bad
 
 
+def hunt_spatializer(lo, hi, root='/root/reference', ref=None, verbose=True, backend="emu"):
+    """spatializer.Process with 1 - 70 channels (more than 32: the product's group-partial path), random geometry including the
+    extremes, aux now and then, a few block lengths: executed reference vs oracle (1e-13) and vs the product (1e-12)"""
+    from common import gdg
+    ref = ref or gen.Ref(root)
+    lib = common.backend_lib(backend)
+    bad = []; t0 = time.time()
+    for seed in range(lo, hi):
+        rng = np.random.default_rng(80000 + seed)
+        C = int(rng.choice([1, 2, 3, 8, 31, 32, 33, 40, 64, 70]))
+        n = int(rng.choice([32, 128, 512]))
+        rate = int(rng.choice([44100, 48000, 96000, 192000]))
+        gs, os_, ps = ref.spatializer.Create(C), orc.Spatializer(C), gdg.Spatializer(C, lib=lib)
+        gs.SetSampleRate(rate); os_.set_sample_rate(rate); ps.set_sample_rate(rate)
+        for c in range(C):
+            az = float(rng.choice([-90.0, 90.0, 0.0, float(rng.uniform(-90, 90))]))
+            dist = float(rng.choice([0.0, 10.0, float(rng.uniform(0, 10))]))
+            lvl = float(rng.choice([0.0, 1.0, float(rng.uniform(0, 1))]))
+            e1, e2, e3 = gs.SetAzimuth(c, az), gs.SetDistance(c, dist), gs.SetLevel(c, lvl)
+            assert e1 is None and e2 is None and e3 is None, (az, dist, lvl, e1, e2, e3)
+            for sp in (os_, ps):
+                sp.set_azimuth(c, az); sp.set_distance(c, dist); sp.set_level(c, lvl)
+        for blk in range(3):
+            x = rng.uniform(-1, 1, (C, n))
+            aux = rng.uniform(-0.2, 0.2, n) if rng.random() < 0.4 else None
+            ins = gen.G.lit([gen.G.lit([float(v) for v in x[c]], 'f') for c in range(C)])
+            o = gen.G.lit([gen.G.make_slice(0.0, n, None, 'f'), gen.G.make_slice(0.0, n, None, 'f')])
+            gs.Process(ins, gen.G.lit([float(v) for v in aux], 'f') if aux is not None else None, o)
+            yr = np.array([o[0].tolist(), o[1].tolist()])
+            yo = np.asarray(os_.process(x, aux)); yp = np.asarray(ps.process(np.ascontiguousarray(x), aux))
+            pk = max(1.0, float(np.max(np.abs(yr))))
+            eo, ep = float(np.max(np.abs(yo - yr))), float(np.max(np.abs(yp - yr)))
+            if not (eo <= 1e-13 * pk and ep <= 1e-12 * pk):
+                bad.append((seed, eo, ep))
+                print("seed %d block %d MISMATCH oracle %.3e product %.3e (C %d n %d rate %d)" % (seed, blk, eo, ep, C, n, rate))
+                break
+    if verbose:
+        print("spatializer %d..%d: %d mismatches, %.0f s" % (lo, hi, len(bad), time.time() - t0))
+    return bad
+
+
 def hunt(lo, hi, root='/root/reference', ref=None, verbose=True):
     """returns the list of (seed, worst error, label) that differ; reference panics are reported and skipped"""
     ref = ref or gen.Ref(root)
@@ -229,6 +271,6 @@ def hunt(lo, hi, root='/root/reference', ref=None, verbose=True):
 
 
 if __name__ == "__main__":
-    fn = hunt_product if "--product" in sys.argv else (hunt_edits if "--edits" in sys.argv else hunt)
+    fn = hunt_product if "--product" in sys.argv else (hunt_edits if "--edits" in sys.argv else (hunt_spatializer if "--spat" in sys.argv else hunt))
     args = [a_ for a_ in sys.argv[1:] if not a_.startswith("--")]
     sys.exit(1 if fn(int(args[0]), int(args[1])) else 0)
