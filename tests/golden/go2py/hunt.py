@@ -1,10 +1,11 @@
 #!/usr/bin/env python3
 """Random chains (1 - 6 units, parameters at random incl. their extremes, any supported rate, fixed or varying block lengths)
 through the EXECUTED reference (go2py) and the C oracle, compared block by block at 1e-12 of the peak.  Needs the reference
-tree.    python tests/golden/go2py/hunt.py FIRST_SEED LAST_SEED [--edits | --product | --spat]
+tree.    python tests/golden/go2py/hunt.py FIRST_SEED LAST_SEED [--edits | --product | --spat | --compile | --meter | --resample]
 Round 2: 4400 random chains, 3200 edit sequences (--edits: a live chain edited between blocks, error strings compared as well)
 3300 random chains through the emulated product (--product, 1e-9 RMS per block) and 3200 random spatializers (--spat: oracle and
-emulated product): 0 mismatches, no reference panic."""
+emulated product), 1060 compiled power-amp filters (--compile: the product's device-side IR compilation), 2150 streamed level meters
+(--meter) and 600 resample.Time calls (--resample): 0 mismatches, no reference panic."""
 import sys, os, json, time
 HERE = os.path.dirname(os.path.abspath(__file__))
 for p_ in (HERE, os.path.join(HERE, '..', '..'), os.path.join(HERE, '..', '..', '..', 'oracle')):
@@ -216,6 +217,121 @@ def hunt_spatializer(lo, hi, root='/root/reference', ref=None, verbose=True, bac
     return bad
 
 
+def hunt_compile(lo, hi, root='/root/reference', ref=None, verbose=True, backend="emu"):
+    """the power amp's compiled composite filter (filter.Import resampling -> Reduce -> Normalize -> Multiply -> Add,
+    poweramp.go:25-127): executed reference vs the product's DEVICE-side IR compilation (gdg_chain_filter_coefficients), random
+    mixes of the imported responses, levels, filter orders and rates; 1e-11 of the largest coefficient"""
+    from common import gdg
+    ref = ref or gen.Ref(root)
+    lib = common.backend_lib(backend)
+    z = np.load(os.path.join(HERE, '..', 'ir_bank.npz'))
+    pb = gdg.IRBank(lib)
+    for k, name in enumerate(z["names"]):
+        if str(name) in gen.IR_NAMES:
+            pb.add(str(name), int(z["compensation"][k]), orc.pcm16_decode(z["pcm_%02d" % k]), int(z["sample_rate"]))
+    rates = [22050, 32000, 44100, 48000, 88200, 96000, 192000]
+    orders = [str(1 << k) for k in range(6, 14)] + ["1048576"]
+    bad = []; t0 = time.time()
+    for seed in range(lo, hi):
+        rng = np.random.default_rng(10000 + seed)
+        fs = int(rng.choice(rates))
+        numeric, discrete = {}, {"filter_order": str(rng.choice(orders))}
+        for i in range(1, 9):
+            if rng.random() < 0.35:
+                discrete["filter_%d" % i] = str(rng.choice(gen.IR_NAMES))
+                numeric["level_%d" % i] = int(rng.integers(-60, 1))
+        if not any(k.startswith("filter_") and k != "filter_order" for k in discrete):
+            discrete["filter_1"] = gen.IR_NAMES[0]
+        spec = [("power_amp", numeric, discrete)]
+        ch = ref.chain(spec); pc = common.build_chain(gdg.Chain(pb, lib=lib), spec)
+        n = 8192 if (discrete["filter_order"] == "1048576" or int(discrete["filter_order"]) > 4096) else 256
+        x = np.zeros(n)
+        ref.process(ch, x, fs); pc.process(x, fs)                 # compiles for this rate
+        want = np.array(ch.slots[0].unit.currentFilter.Coefficients().tolist())
+        got = np.asarray(pc.filter_coefficients(0))
+        ok = len(got) == len(want) and (len(want) == 0 or float(np.max(np.abs(got - want))) <= 1e-11 * max(1e-300, float(np.max(np.abs(want)))))
+        if not ok:
+            bad.append((seed, json.dumps(spec)))
+            print("seed %d MISMATCH len %d / %d err %s fs %d spec %s" % (seed, len(got), len(want),
+                  ("%.3e" % np.max(np.abs(got - want))) if len(got) == len(want) and len(want) else "-", fs, json.dumps(spec)))
+    if verbose:
+        print("compiled filters %d..%d: %d mismatches, %.0f s" % (lo, hi, len(bad), time.time() - t0))
+    return bad
+
+
+def hunt_meter(lo, hi, root='/root/reference', ref=None, verbose=True, backend="emu"):
+    """level.Meter streamed in random block lengths at random rates, with decays long enough for the 2 s peak hold to expire and
+    bursts that reset it, enable / disable toggles: executed reference vs oracle (read-outs and state exact to 1e-12) and vs the
+    product's parallel formulation (integer read-outs and the counter exact, state within 1e-10)"""
+    from common import gdg
+    ref = ref or gen.Ref(root)
+    lib = common.backend_lib(backend)
+    bad = []; t0 = time.time()
+    for seed in range(lo, hi):
+        rng = np.random.default_rng(110000 + seed)
+        C = int(rng.integers(1, 5)); fs = int(rng.choice([4096, 8000, 22050, 48000, 192000]))
+        gm, err = ref.level.CreateMeter(C, gen.G.lit(["c%d" % c for c in range(C)]))
+        assert err is None
+        om, pm = orc.Meter(C), gdg.Meter(C, lib=lib)
+        for m_ in (om, pm): m_.set_enabled(True)
+        gm.SetEnabled(True)
+        ok = True
+        for blk in range(int(rng.integers(6, 16))):
+            n = int(rng.choice([64, 256, 1024, 4096, 8192]))
+            env = np.exp(-np.arange(n) / float(rng.choice([50.0, 2000.0, 1e6])))
+            x = [float(rng.choice([0.0, 0.02, 0.9])) * rng.uniform(-1, 1, n) * env for _ in range(C)]
+            if rng.random() < 0.1:
+                on = bool(rng.integers(0, 2))
+                gm.SetEnabled(on); om.set_enabled(on); pm.set_enabled(on)
+            assert gm.Process(gen.G.lit([gen.G.lit([float(v) for v in r], 'f') for r in x]), fs) is None
+            om.process(x, fs); pm.process([np.ascontiguousarray(r) for r in x], fs)
+            for c in range(C):
+                r, e = gm.Analyze(c)
+                want = (int(r.Level()), int(r.Peak()))
+                cm = gm.channelMeters[c]
+                st = (float(cm.currentValue), float(cm.peakValue), int(cm.sampleCounter))
+                so, sp = om.state(c), pm.state(c)
+                good = (tuple(om.analyze(c)) == want and tuple(pm.analyze(c)) == want and so[2] == st[2] and sp[2] == st[2]
+                        and abs(so[0] - st[0]) <= 1e-12 * st[0] + 1e-300 and abs(so[1] - st[1]) <= 1e-12 * st[1] + 1e-300
+                        and abs(sp[0] - st[0]) <= 1e-10 * st[0] + 1e-300 and abs(sp[1] - st[1]) <= 1e-10 * st[1] + 1e-300)
+                if not good:
+                    ok = False
+                    bad.append((seed, blk, c))
+                    print("seed %d block %d ch %d MISMATCH want %s %s oracle %s %s product %s %s (fs %d n %d)" % (seed, blk, c, want, st, tuple(om.analyze(c)), so, tuple(pm.analyze(c)), sp, fs, n))
+                    break
+            if not ok:
+                break
+    if verbose:
+        print("level meters %d..%d: %d mismatches, %.0f s" % (lo, hi, len(bad), time.time() - t0))
+    return bad
+
+
+def hunt_resample(lo, hi, root='/root/reference', ref=None, verbose=True, backend="emu"):
+    """resample.Time (the batch path's input rate conversion, controller.go:2991-3003) on random lengths and rate pairs: executed
+    reference vs oracle and product (1e-12)"""
+    from common import gdg
+    ref = ref or gen.Ref(root)
+    lib = common.backend_lib(backend)
+    rs = ref.loader.load("resample")
+    rates = [8000, 11025, 22050, 32000, 44100, 48000, 88200, 96000, 192000]
+    bad = []; t0 = time.time()
+    for seed in range(lo, hi):
+        rng = np.random.default_rng(120000 + seed)
+        n = int(rng.choice([0, 1, 2, 7, 100, 1000, 4097])); a, b = int(rng.choice(rates)), int(rng.choice(rates))
+        x = rng.uniform(-1, 1, n)
+        try:
+            want = np.array(rs.Time(gen.G.lit([float(v) for v in x], 'f'), a, b).tolist())
+        except GoPanic:
+            continue                                               # too short an input: the reference asks make() for a negative length
+        go_, gp = np.asarray(orc.resample_time(x, a, b)), np.asarray(gdg.resample_time(x, a, b, lib=lib))
+        if not (len(go_) == len(want) == len(gp) and (len(want) == 0 or (np.max(np.abs(go_ - want)) <= 1e-12 and np.max(np.abs(gp - want)) <= 1e-12))):
+            bad.append((seed, n, a, b))
+            print("seed %d MISMATCH n %d %d -> %d lens %d %d %d" % (seed, n, a, b, len(want), len(go_), len(gp)))
+    if verbose:
+        print("resample.Time %d..%d: %d mismatches, %.0f s" % (lo, hi, len(bad), time.time() - t0))
+    return bad
+
+
 def hunt(lo, hi, root='/root/reference', ref=None, verbose=True):
     """returns the list of (seed, worst error, label) that differ; reference panics are reported and skipped"""
     ref = ref or gen.Ref(root)
@@ -271,6 +387,8 @@ def hunt(lo, hi, root='/root/reference', ref=None, verbose=True):
 
 
 if __name__ == "__main__":
-    fn = hunt_product if "--product" in sys.argv else (hunt_edits if "--edits" in sys.argv else (hunt_spatializer if "--spat" in sys.argv else hunt))
+    modes = {"--product": hunt_product, "--edits": hunt_edits, "--spat": hunt_spatializer, "--compile": hunt_compile, "--meter": hunt_meter,
+             "--resample": hunt_resample}
+    fn = next((f for k, f in modes.items() if k in sys.argv), hunt)
     args = [a_ for a_ in sys.argv[1:] if not a_.startswith("--")]
     sys.exit(1 if fn(int(args[0]), int(args[1])) else 0)

@@ -430,3 +430,16 @@ def test_spatializer_oracle_and_emulated_product_equal_executed_reference():
     group-partial path), geometry at random including its extremes, aux now and then"""
     import hunt
     assert hunt.hunt_spatializer(70000, 70060, REFERENCE, verbose=False) == []
+
+
+@pytest.mark.skipif(not have_reference, reason="needs the reference tree (build container)")
+def test_compiled_filters_meters_resampler_equal_executed_reference():
+    """hunt.py --compile / --meter / --resample on fresh seeds (1060 / 2150 / 600 hunted in round 2 without a mismatch): the power
+    amp's compiled composite filter from the product's device-side IR compilation, the level meter's parallel formulation and
+    resample.Time - emulated product and oracle against the executed reference"""
+    import hunt
+    import make_reference_vectors as gen
+    ref = gen.Ref(REFERENCE)
+    assert hunt.hunt_compile(90000, 90025, REFERENCE, ref=ref, verbose=False) == []
+    assert hunt.hunt_meter(90000, 90080, REFERENCE, ref=ref, verbose=False) == []
+    assert hunt.hunt_resample(90000, 90150, REFERENCE, ref=ref, verbose=False) == []
