@@ -1,11 +1,11 @@
 #!/usr/bin/env python3
 """Random chains (1 - 6 units, parameters at random incl. their extremes, any supported rate, fixed or varying block lengths)
 through the EXECUTED reference (go2py) and the C oracle, compared block by block at 1e-12 of the peak.  Needs the reference
-tree.    python tests/golden/go2py/hunt.py FIRST_SEED LAST_SEED [--edits | --product | --spat | --compile | --meter | --resample]
+tree.    python tests/golden/go2py/hunt.py FIRST_SEED LAST_SEED [--edits | --product | --spat | --compile | --meter | --resample | --tuner]
 Round 2: 4400 random chains, 3200 edit sequences (--edits: a live chain edited between blocks, error strings compared as well)
 3300 random chains through the emulated product (--product, 1e-9 RMS per block) and 3200 random spatializers (--spat: oracle and
 emulated product), 1060 compiled power-amp filters (--compile: the product's device-side IR compilation), 2150 streamed level meters
-(--meter) and 600 resample.Time calls (--resample): 0 mismatches, no reference panic."""
+(--meter), 600 resample.Time calls (--resample) and 300 tuner analyses (--tuner): 0 mismatches, no reference panic."""
 import sys, os, json, time
 HERE = os.path.dirname(os.path.abspath(__file__))
 for p_ in (HERE, os.path.join(HERE, '..', '..'), os.path.join(HERE, '..', '..', '..', 'oracle')):
@@ -332,6 +332,40 @@ def hunt_resample(lo, hi, root='/root/reference', ref=None, verbose=True, backen
     return bad
 
 
+def hunt_tuner(lo, hi, root='/root/reference', ref=None, verbose=True, backend="emu"):
+    """tuner.Process / Analyze on random tones (fundamental 70 - 1000 Hz, two harmonics, noise), fed in random block lengths:
+    executed reference vs oracle and product - note and cents equal, frequency to 1e-9"""
+    from common import gdg
+    ref = ref or gen.Ref(root)
+    lib = common.backend_lib(backend)
+    tn = ref.loader.load("tuner")
+    bad = []; t0 = time.time()
+    for seed in range(lo, hi):
+        rng = np.random.default_rng(130000 + seed)
+        fs = int(rng.choice([44100, 48000, 96000, 192000])); f0 = float(rng.uniform(70.0, 1000.0))
+        total = 96000 + int(rng.integers(0, 30000))
+        t = np.arange(total) / fs
+        x = (0.5 * np.sin(2 * np.pi * f0 * t) + float(rng.uniform(0, 0.3)) * np.sin(2 * np.pi * 2 * f0 * t + 0.7)
+             + float(rng.uniform(0, 0.2)) * np.sin(2 * np.pi * 3 * f0 * t + 1.9) + 0.02 * rng.uniform(-1, 1, total))
+        gt, ot, pt = tn.Create(), orc.Tuner(), gdg.Tuner(lib=lib)
+        pos = 0
+        while pos < total:
+            nb = min(int(rng.choice([64, 1024, 8192, 5000])), total - pos)
+            blk = np.ascontiguousarray(x[pos:pos + nb]); pos += nb
+            gt.Process(gen.G.lit([float(v) for v in blk], 'f'), fs); ot.process(blk, fs); pt.process(blk, fs)
+        r, err = gt.Analyze()
+        assert err is None, err
+        want = (r.Note(), int(r.Cents()), float(r.Frequency()))
+        for who, res in (("oracle", ot.analyze()), ("product", pt.analyze())):
+            got = (res["note"], int(res["cents"]), float(res["frequency"]))
+            if not (got[:2] == want[:2] and abs(got[2] - want[2]) <= 1e-9 * want[2]):
+                bad.append((seed, who))
+                print("seed %d %s MISMATCH want %s got %s (f0 %.3f fs %d)" % (seed, who, want, got, f0, fs))
+    if verbose:
+        print("tuner %d..%d: %d mismatches, %.0f s" % (lo, hi, len(bad), time.time() - t0))
+    return bad
+
+
 def hunt(lo, hi, root='/root/reference', ref=None, verbose=True):
     """returns the list of (seed, worst error, label) that differ; reference panics are reported and skipped"""
     ref = ref or gen.Ref(root)
@@ -388,7 +422,7 @@ def hunt(lo, hi, root='/root/reference', ref=None, verbose=True):
 
 if __name__ == "__main__":
     modes = {"--product": hunt_product, "--edits": hunt_edits, "--spat": hunt_spatializer, "--compile": hunt_compile, "--meter": hunt_meter,
-             "--resample": hunt_resample}
+             "--resample": hunt_resample, "--tuner": hunt_tuner}
     fn = next((f for k, f in modes.items() if k in sys.argv), hunt)
     args = [a_ for a_ in sys.argv[1:] if not a_.startswith("--")]
     sys.exit(1 if fn(int(args[0]), int(args[1])) else 0)

@@ -443,3 +443,10 @@ def test_compiled_filters_meters_resampler_equal_executed_reference():
     assert hunt.hunt_compile(90000, 90025, REFERENCE, ref=ref, verbose=False) == []
     assert hunt.hunt_meter(90000, 90080, REFERENCE, ref=ref, verbose=False) == []
     assert hunt.hunt_resample(90000, 90150, REFERENCE, ref=ref, verbose=False) == []
+
+
+@pytest.mark.skipif(not have_reference, reason="needs the reference tree (build container)")
+def test_tuner_equals_executed_reference_on_random_tones():
+    """hunt.py --tuner on three fresh tones (300 hunted in round 2 without a mismatch)"""
+    import hunt
+    assert hunt.hunt_tuner(95000, 95003, REFERENCE, verbose=False) == []
