@@ -427,6 +427,8 @@ class PackageTranslator(object):
         """python expression for the element kind of a slice of t: 'f' / 'c' (literal coercion), 'v' (struct VALUES: copied by
         range / copy / append), None"""
         k = kind_of_type(t)
+        if t and t[0] == "name" and (t[1] == "float32" or (t[1] in INT_TYPES and t[1] not in ("int", "uint"))):
+            return repr("byte" if t[1] == "uint8" else t[1])  # sized elements: what encoding/binary needs to know
         if k in ("f", "c"):
             return repr(k)
         if t and t[0] == "name" and self.types.get(t[1]) == "struct":

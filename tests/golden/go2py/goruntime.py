@@ -662,5 +662,100 @@ class _Strconv(object):
         return ("%." + str(prec) + fmtc) % float(f)
 
 
-STDLIB = {"math": _Math(), "math/cmplx": _Cmplx(), "math/bits": _Bits(), "sync": _Sync(), "fmt": _Fmt(), "errors": _Errors(),
+class _BytesBuffer(GoStruct):
+    """bytes.Buffer: the write side the translated packages use"""
+
+    def _zero(self):
+        self.__dict__["data"] = bytearray()
+
+    def WriteByte(self, b):
+        self.data.append(int(b) & 0xFF)
+        return None
+
+    def Write(self, p):
+        vals = p.tolist() if isinstance(p, GoSlice) else list(p)
+        self.data.extend(int(v) & 0xFF for v in vals)
+        return len(vals), None
+
+    def Bytes(self):
+        return GoSlice(list(self.data), 0, len(self.data), len(self.data), "byte")
+
+    def Len(self):
+        return len(self.data)
+
+
+class _BytesReader(object):
+    def __init__(self, data):
+        self.data, self.pos = bytes(data.tolist()) if data is not None else b"", 0
+
+    def Read(self, buf):
+        n = min(len(buf), len(self.data) - self.pos)
+        if n <= 0 and len(buf) > 0:
+            return 0, GoError("EOF")
+        for i in range(n):
+            buf[i] = self.data[self.pos + i]
+        self.pos += n
+        return n, None
+
+    def Len(self):
+        return len(self.data) - self.pos
+
+    def Seek(self, offset, whence):
+        base = 0 if whence == 0 else (self.pos if whence == 1 else len(self.data))
+        p = base + int(offset)
+        if p < 0:
+            return 0, GoError("bytes.Reader.Seek: negative position")
+        self.pos = p
+        return p, None
+
+
+class _Bytes(object):
+    Buffer = _BytesBuffer
+
+    def NewReader(self, data):
+        return _BytesReader(data)
+
+    def NewBuffer(self, data):
+        b = _BytesBuffer()
+        if data is not None:
+            b.data.extend(data.tolist())
+        return b
+
+
+_PACK = {"int8": "b", "byte": "B", "uint8": "B", "int16": "h", "uint16": "H", "int32": "i", "uint32": "I", "rune": "i", "int64": "q", "uint64": "Q",
+         "float32": "f", "f": "d"}
+
+
+class _Binary(object):
+    """encoding/binary for slices of sized numbers (the sample conversions of wave.go); struct headers are not supported"""
+    LittleEndian, BigEndian = "<", ">"
+
+    def Write(self, w, order, data):
+        if not isinstance(data, GoSlice) or data.k not in _PACK:
+            return GoError("binary.Write: unsupported data (the translation handles slices of sized numbers)")
+        vals = data.tolist()
+        try:
+            w.data.extend(_struct.pack(order + "%d%s" % (len(vals), _PACK[data.k]), *vals))
+        except _struct.error as e:
+            return GoError("binary.Write: %s" % e)
+        return None
+
+    def Read(self, r, order, data):
+        if not isinstance(data, GoSlice) or data.k not in _PACK:
+            return GoError("binary.Read: unsupported data (the translation handles slices of sized numbers)")
+        size = _struct.calcsize(order + _PACK[data.k]) * len(data)
+        if len(r.data) - r.pos < size:
+            return GoError("unexpected EOF")
+        vals = _struct.unpack(order + "%d%s" % (len(data), _PACK[data.k]), r.data[r.pos:r.pos + size])
+        r.pos += size
+        for i, v in enumerate(vals):
+            data.a[data.o + i] = v
+        return None
+
+
+class _Io(object):
+    SeekStart, SeekCurrent, SeekEnd = 0, 1, 2
+
+
+STDLIB = {"bytes": _Bytes(), "encoding/binary": _Binary(), "io": _Io(), "math": _Math(), "math/cmplx": _Cmplx(), "math/bits": _Bits(), "sync": _Sync(), "fmt": _Fmt(), "errors": _Errors(),
           "strconv": _Strconv()}

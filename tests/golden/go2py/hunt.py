@@ -1,11 +1,12 @@
 #!/usr/bin/env python3
 """Random chains (1 - 6 units, parameters at random incl. their extremes, any supported rate, fixed or varying block lengths)
 through the EXECUTED reference (go2py) and the C oracle, compared block by block at 1e-12 of the peak.  Needs the reference
-tree.    python tests/golden/go2py/hunt.py FIRST_SEED LAST_SEED [--edits | --product | --spat | --compile | --meter | --resample | --tuner]
+tree.    python tests/golden/go2py/hunt.py FIRST_SEED LAST_SEED [--edits | --product | --spat | --compile | --meter | --resample | --tuner | --codecs]
 Round 2: 4400 random chains, 3200 edit sequences (--edits: a live chain edited between blocks, error strings compared as well)
 3300 random chains through the emulated product (--product, 1e-9 RMS per block) and 3200 random spatializers (--spat: oracle and
 emulated product), 1060 compiled power-amp filters (--compile: the product's device-side IR compilation), 2150 streamed level meters
-(--meter), 600 resample.Time calls (--resample) and 300 tuner analyses (--tuner): 0 mismatches, no reference panic."""
+(--meter), 600 resample.Time calls (--resample), 300 tuner analyses (--tuner) and 6300 codec round trips (--codecs, byte for byte):
+0 mismatches, no reference panic."""
 import sys, os, json, time
 HERE = os.path.dirname(os.path.abspath(__file__))
 for p_ in (HERE, os.path.join(HERE, '..', '..'), os.path.join(HERE, '..', '..', '..', 'oracle')):
@@ -366,6 +367,39 @@ def hunt_tuner(lo, hi, root='/root/reference', ref=None, verbose=True, backend="
     return bad
 
 
+def hunt_codecs(lo, hi, root='/root/reference', ref=None, verbose=True, backend="emu"):
+    """wave.go's sample conversions (wave/wave.go:275-732), all 36 (input format, output format) pairs: executed bytesToSamples ->
+    samplesToBytes against the oracle's codecs and the product's fused load / store (an empty chain through
+    gdg_process_batch_encoded), byte for byte; samples beyond +-1, at the quantisation edges and tiny ones included"""
+    from common import gdg
+    ref = ref or gen.Ref(root)
+    lib = common.backend_lib(backend)
+    wv = ref.loader.load("wave")
+    fns = {"PCM8": "LPCM8", "PCM16": "LPCM16", "PCM24": "LPCM24", "PCM32": "LPCM32", "IEEE32": "IEEE32", "IEEE64": "IEEE64"}
+    bad = []; t0 = time.time()
+    for seed in range(lo, hi):
+        rng = np.random.default_rng(140000 + seed)
+        n = int(rng.choice([64, 256, 1024]))
+        x = rng.uniform(-1.3, 1.3, n) * rng.choice([1.0, 1.0, 1e-3, 1e-7], n)
+        x[rng.integers(0, n, 8)] = rng.choice([1.0, -1.0, 0.0, 0.5 / 32767.5, -0.5 / 32767.5, 1.0 - 2.0 ** -24, 3.0, -3.0], 8)
+        fi, fo = str(rng.choice(list(fns))), str(rng.choice(list(fns)))
+        raw, err = getattr(wv, "samplesToBytes" + fns[fi])(gen.G.lit([float(v) for v in x], 'f'))
+        assert err is None
+        smp, err = getattr(wv, "bytesToSamples" + fns[fi])(raw)
+        assert err is None
+        want, err = getattr(wv, "samplesToBytes" + fns[fo])(smp)
+        assert err is None
+        want = bytes(want.tolist()); raw = bytes(raw.tolist())
+        got_o = orc.wave_encode(fo, orc.wave_decode(fi, raw)).tobytes()
+        got_p = gdg.process_batch_encoded([gdg.Chain(lib=lib)], [raw], fi, fo, n, 48000)[0]
+        if not (got_o == want and got_p == want and orc.wave_encode(fi, x).tobytes() == raw):
+            bad.append((seed, fi, fo))
+            print("seed %d MISMATCH %s -> %s oracle %s product %s encode %s" % (seed, fi, fo, got_o == want, got_p == want, orc.wave_encode(fi, x).tobytes() == raw))
+    if verbose:
+        print("codecs %d..%d: %d mismatches, %.0f s" % (lo, hi, len(bad), time.time() - t0))
+    return bad
+
+
 def hunt(lo, hi, root='/root/reference', ref=None, verbose=True):
     """returns the list of (seed, worst error, label) that differ; reference panics are reported and skipped"""
     ref = ref or gen.Ref(root)
@@ -422,7 +456,7 @@ def hunt(lo, hi, root='/root/reference', ref=None, verbose=True):
 
 if __name__ == "__main__":
     modes = {"--product": hunt_product, "--edits": hunt_edits, "--spat": hunt_spatializer, "--compile": hunt_compile, "--meter": hunt_meter,
-             "--resample": hunt_resample, "--tuner": hunt_tuner}
+             "--resample": hunt_resample, "--tuner": hunt_tuner, "--codecs": hunt_codecs}
     fn = next((f for k, f in modes.items() if k in sys.argv), hunt)
     args = [a_ for a_ in sys.argv[1:] if not a_.startswith("--")]
     sys.exit(1 if fn(int(args[0]), int(args[1])) else 0)

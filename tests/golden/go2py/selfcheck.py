@@ -139,6 +139,18 @@ def run(loader, verbose=False):
     assert read() == [t["after_disable"]["level"], t["after_disable"]["peak"]]
     n += 3
 
+    # wave/wave_test.go: the sample conversions of all six formats (the RIFF container stays out: encoding/binary on structs)
+    wv = loader.load("wave")
+    t = json.load(open(os.path.join(HERE, "..", "wave_goldens.json")))
+    for fmt, fn in (("PCM8", "LPCM8"), ("PCM16", "LPCM16"), ("PCM24", "LPCM24"), ("PCM32", "LPCM32"), ("IEEE32", "IEEE32"), ("IEEE64", "IEEE64")):
+        g = t[fmt]
+        data, err = getattr(wv, "samplesToBytes" + fn)(fl(g["export_samples"]))
+        assert err is None and data.tolist() == g["export_data"], fmt          # TestExport<fmt>Mono: byte-identical payload
+        smp, err = getattr(wv, "bytesToSamples" + fn)(G.lit(list(g["import_data"]), "byte"))
+        assert err is None
+        close(smp.tolist(), g["import_samples"], g["import_tolerance"])          # TestImport<fmt>Mono
+        n += 2
+
     # tuner/tuner_test.go: one of the six recordings (the last 96000 frames: tests/golden/tuner_tail_*.npz)
     if os.environ.get("GO2PY_SELFCHECK_TUNER", "1") != "0":
         tn = loader.load("tuner")

@@ -2,7 +2,7 @@
 
 There is no Go toolchain here or on the GPU box, so tests/golden/go2py/ translates the reference's .go files mechanically
 (statement by statement, no knowledge of the DSP) into Python, checks the translation against the reference's OWN unit-test
-vectors (fft, oversampling, resample, random, circular, level, tuner: 60 vectors) and then runs every unit, the chain driver,
+vectors (fft, oversampling, resample, random, circular, level, wave codecs, tuner: 72 vectors) and then runs every unit, the chain driver,
 the power amp's IR algebra, the spatializer and the level meter to produce tests/golden/translated_reference_vectors.npz
 (generator: tests/golden/go2py/make_reference_vectors.py; it needs /root/reference, the committed vectors do not).
 
