@@ -11,7 +11,9 @@ packages before anything else is generated.
 Supported: package-level const (iota) / var / type (struct, interface, named basic) / func / methods; statements: := = op=
 ++ -- var if/else for (all forms, range) switch (tag, tagless, type switch) return break continue; expressions with Go
 precedence, composite literals, slices (aliasing views), maps, type assertions, conversions, variadics, multiple results.
-Not supported (absent from the translated packages): goroutines, channels, select, defer, goto, labels, closures, generics.
+Channels exist as far as controller.process needs them: `ch <- v`, `<-ch`, make(chan T), close - a G.Chan runs a handler on send
+(the worker that the reference starts as a goroutine) and hands its result to the next receive.
+Not supported (absent from the translated code): goroutines (`go`), select, defer, goto, labels, closures, generics.
 See goruntime.py for how values are represented."""
 import re
 from fractions import Fraction
@@ -207,8 +209,10 @@ def kind_of_type(t):
 
 
 class PackageTranslator(object):
-    def __init__(self, pkgname, files):
-        """files: list of (path, source)"""
+    def __init__(self, pkgname, files, tolerant=False):
+        """files: list of (path, source); tolerant: a top-level declaration that uses an unsupported construct is left out
+        (recorded in self.skipped) instead of failing the package - for packages of which only some functions are wanted"""
+        self.tolerant, self.skipped = tolerant, []
         self.pkg = pkgname
         self.files = files
         self.types = {}                 # package-level type name -> 'struct' | 'iface' | 'func' | ('basic', underlying type)
@@ -313,18 +317,39 @@ class PackageTranslator(object):
             t = self.peek()
             if t.k != "kw":
                 self.err("unexpected token %r at top level" % (t.v,))
-            if t.v == "import":
-                self.parse_import()
-            elif t.v == "const":
-                self.parse_const_decl(toplevel=True)
-            elif t.v == "var":
-                self.parse_var_decl(toplevel=True)
-            elif t.v == "type":
-                self.parse_type_decl()
-            elif t.v == "func":
-                self.parse_func()
-            else:
-                self.err("unsupported top-level declaration %r" % (t.v,))
+            start, ndefs, ninits = self.p, len(self.defs), len(self.inits)
+            try:
+                if t.v == "import":
+                    self.parse_import()
+                elif t.v == "const":
+                    self.parse_const_decl(toplevel=True)
+                elif t.v == "var":
+                    self.parse_var_decl(toplevel=True)
+                elif t.v == "type":
+                    self.parse_type_decl()
+                elif t.v == "func":
+                    self.parse_func()
+                else:
+                    self.err("unsupported top-level declaration %r" % (t.v,))
+            except GoSyntaxError as e:
+                if not self.tolerant:
+                    raise
+                del self.defs[ndefs:]
+                del self.inits[ninits:]
+                self.scopes, self.nolit, self.iota = [], 0, None
+                self.p = start
+                depth = 0
+                while self.peek().k != "eof":                # resynchronise: the `;` that ends this declaration at depth 0
+                    tk = self.next()
+                    if tk.k == "op" and tk.v in ("{", "(", "["):
+                        depth += 1
+                    elif tk.k == "op" and tk.v in ("}", ")", "]"):
+                        depth -= 1
+                    elif tk.k == "op" and tk.v == ";" and depth == 0 and self.peek().k in ("kw", "eof") \
+                            and self.peek().v in ("func", "var", "const", "type", "import", ""):
+                        break
+                what = " ".join(x.v for x in self.toks[start:start + 6])
+                self.skipped.append((what, str(e)))
             self.skip_semis()
 
     def parse_import(self):
@@ -392,7 +417,13 @@ class PackageTranslator(object):
             self.next(); self.parse_signature()
             return ("func",)
         if t.k == "kw" and t.v == "chan":
-            self.err("channels are not supported")
+            self.next()
+            self.accept("<-")
+            self.parse_type()
+            return ("chan",)
+        if t.k == "op" and t.v == "<-":
+            self.next(); self.expect("chan", "kw"); self.parse_type()
+            return ("chan",)
         self.err("expected a type, got %r" % (t.v,))
 
     def parse_struct_body(self):
@@ -862,6 +893,10 @@ class PackageTranslator(object):
         while self.accept(","):
             lhs.append(self.parse_expr())
         t = self.peek()
+        if t.k == "op" and t.v == "<-" and len(lhs) == 1:        # ch <- v
+            self.next()
+            v = self.parse_expr()
+            return ["G.send(%s, %s)" % (lhs[0].code, v.code)]
         if t.k == "op" and (t.v in ("++", "--", "=") or (t.v.endswith("=") and t.v not in ("==", "!=", "<=", ">=", ":="))):
             for l in lhs:
                 if getattr(l, "is_global", False) and l.code != "_":
@@ -1299,7 +1334,7 @@ class PackageTranslator(object):
                 return Ex("(~%s)" % e.code, "i", e.intconst)
             if t.v in ("*", "&"):
                 return Ex(e.code, e.kind)                   # pointers to structs are the objects themselves
-            self.err("channel operations are not supported")
+            return Ex("G.recv(%s)" % e.code)                 # <-ch
         return self.parse_primary()
 
     def parse_operand(self):
@@ -1402,6 +1437,8 @@ class PackageTranslator(object):
                     e = Ex("G.make_slice(%s, %s, %s, %s)" % (self.zero_code(ty[1], True), args[0].code, args[1].code if len(args) > 1 else "None", self.kind_code(ty[1])))
                 elif ty[0] == "map":
                     e = Ex("{}")
+                elif ty[0] == "chan":
+                    e = Ex("G.Chan(%s)" % (args[0].code if args else "0"))
                 else:
                     self.err("make of %r is not supported" % (ty[0],))
                 return self.parse_postfix(e)
@@ -1479,7 +1516,7 @@ class PackageTranslator(object):
                 save_nolit = self.nolit
                 self.nolit = 0
                 callee = getattr(e, "goname", None)
-                if callee in ("len", "cap", "append", "copy", "complex", "real", "imag", "panic", "delete", "min", "max", "print", "println") \
+                if callee in ("len", "cap", "append", "copy", "complex", "real", "imag", "panic", "delete", "min", "max", "print", "println", "close") \
                         and self.lookup(callee) is None and callee not in self.toplevel:
                     args, spread = self.parse_args()
                     self.nolit = save_nolit
@@ -1547,6 +1584,8 @@ class PackageTranslator(object):
             return Ex("G.panic(%s)" % c[0])
         if name == "delete":
             return Ex("%s.pop(%s, None)" % (c[0], c[1]))
+        if name == "close":
+            return Ex("G.close(%s)" % c[0])
         if name in ("min", "max"):
             return Ex("%s(%s)" % (name, ", ".join(c)), args[0].kind)
         return Ex("print(%s)" % ", ".join(c))

@@ -463,6 +463,31 @@ class _G(object):
         return GoError(_G.sprintf(fmt, *args))
 
 
+class Chan(object):
+    """a channel as far as controller.process needs one: `handler(value)` stands for the goroutine that serves the channel - it
+    runs at once on send; what it returns is queued on `reply` (another Chan) for the next receive"""
+
+    def __init__(self, capacity=0, handler=None, reply=None):
+        self.queue, self.handler, self.reply, self.closed = [], handler, reply, False
+
+    def send(self, v):
+        if self.handler is not None:
+            r = self.handler(v)
+            (self.reply if self.reply is not None else self).queue.append(r)
+        else:
+            self.queue.append(v)
+
+    def recv(self):
+        if not self.queue:
+            raise GoPanic("receive from an empty channel (no goroutines here: nothing would ever send)")
+        return self.queue.pop(0)
+
+
+_G.Chan = Chan
+_G.send = staticmethod(lambda ch, v: ch.send(v))
+_G.recv = staticmethod(lambda ch: ch.recv())
+_G.close = staticmethod(lambda ch: setattr(ch, "closed", True))
+
 G = _G()
 
 

@@ -23,8 +23,9 @@ class Missing(object):
 
 
 class Loader(object):
-    def __init__(self, root, overrides=None, skip=()):
+    def __init__(self, root, overrides=None, skip=(), tolerant=()):
         self.root, self.mods, self.sources = root, {}, {}
+        self.tolerant, self.skipped = set(tolerant), {}       # packages of which only part is translatable (e.g. controller)
         self.overrides = overrides or {}                    # import path -> python object standing in for the package
         self.skip = set(skip)
 
@@ -37,7 +38,8 @@ class Loader(object):
         for fn in sorted(os.listdir(d)):
             if fn.endswith(".go") and not fn.endswith("_test.go"):
                 files.append((os.path.join(d, fn), open(os.path.join(d, fn), encoding="utf-8").read()))
-        tr = go2py.PackageTranslator(pkg, files).translate()
+        tr = go2py.PackageTranslator(pkg, files, tolerant=pkg in self.tolerant).translate()
+        self.skipped[pkg] = tr.skipped
         src, inits = tr.module_source()
         mod = types.ModuleType("goref_" + pkg.replace("/", "_"))
         g = mod.__dict__
