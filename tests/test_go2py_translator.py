@@ -346,7 +346,7 @@ def test_float_literals_into_float_contexts(tmp_path):
 
 def test_unsupported_constructs_are_rejected(tmp_path):
     """what the translator does not implement fails at translation time - it is never guessed at"""
-    for k, body in enumerate(("go f()", "defer f()", "ch := make(chan int)\n_ = ch", "h := func() {}\n_ = h", "goto done")):
+    for k, body in enumerate(("go f()", "defer f()", "select {\n}", "h := func() {}\n_ = h", "goto done")):
         with pytest.raises(go2py.GoSyntaxError):
             run_go(tmp_path, "package p\n\nfunc f() {}\n\nfunc g() {\n\t%s\n}\n" % body.replace("\n", "\n\t"), pkg="q%d" % k)
 
