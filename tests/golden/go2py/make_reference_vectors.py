@@ -413,6 +413,26 @@ def main():
         tuner_cases.append({"blocks": nb, "fs": fs, "n": n, "f0": f0, "note": res.Note(), "cents": int(res.Cents()), "frequency": float(res.Frequency())})
         print("tuner %.2f Hz @%d: %s %+d cents %.4f Hz (%.1f s)" % (f0, fs, res.Note(), res.Cents(), res.Frequency(), time.time() - t0))
 
+    # ---- BASELINE.json config 1 in miniature: PCM16 payload -> overdrive -> tone_stack -> PCM16 payload, 48 kHz, blocks of 8192 with
+    # the last one zero-padded (controller.go:3022-3107), every step the reference's own code: wave.go's conversions and the chain
+    wv = ref.loader.load("wave")
+    fs1, total = 48000, 24000
+    x1 = test_signal(fs1, total, 77, 0.9)
+    pcm_in, err = wv.samplesToBytesLPCM16(G.lit([float(v) for v in x1], 'f'))
+    assert err is None
+    smp, err = wv.bytesToSamplesLPCM16(pcm_in)
+    assert err is None
+    ch1 = ref.chain([("overdrive", {"gain": 12}, {}), ("tone_stack", {}, {})])
+    nblk = (total + 8191) // 8192
+    padded = np.zeros(nblk * 8192); padded[:total] = np.array(smp.tolist())
+    y1 = np.concatenate([ref.process(ch1, padded[k * 8192:(k + 1) * 8192], fs1) for k in range(nblk)])
+    pcm_out, err = wv.samplesToBytesLPCM16(G.lit([float(v) for v in y1], 'f'))
+    assert err is None
+    arrays["cfg1_pcm_in"] = np.array(pcm_in.tolist(), dtype=np.uint8)
+    arrays["cfg1_pcm_out"] = np.array(pcm_out.tolist(), dtype=np.uint8)
+    cfg1 = {"fs": fs1, "samples": total, "block": 8192, "blocks": nblk, "spec": [["overdrive", {"gain": 12}, {}], ["tone_stack", {}, {}]]}
+    print("config 1: %d PCM16 samples -> %d blocks -> %d bytes" % (total, nblk, len(pcm_out)))
+
     # ---- the reference's out-of-range read: flanger / phaser at 22.05 / 44.1 / 88.2 kHz with depth 100 --------
     panics = []
     for unit, fs, n in (("flanger", 44100, 64), ("phaser", 22050, 32), ("flanger", 88200, 128), ("flanger", 48000, 64)):
@@ -431,7 +451,7 @@ def main():
     np.savez_compressed(OUT + ".npz", **arrays)
     manifest = {"generator": "tests/golden/go2py/make_reference_vectors.py", "reference": "andrepxx/go-dsp-guitar v1.8.0 (the tree under /root/reference)",
                 "selfcheck_vectors": ref.selfcheck_vectors, "ir_names": IR_NAMES, "unit_names": ref.unit_names, "cases": cases, "spatializer": spat, "ir": ir_info,
-                "level_meter": meter, "reference_panics": panics, "parameters": tables, "errors": errors, "tuner": tuner_cases, "integer_division_sites": sorted(G.intdiv_sites)}
+                "level_meter": meter, "reference_panics": panics, "config1": cfg1, "parameters": tables, "errors": errors, "tuner": tuner_cases, "integer_division_sites": sorted(G.intdiv_sites)}
     json.dump(manifest, open(OUT + ".json", "w"), indent=0)
     print("%d stream cases, %d arrays, %.1f MB" % (len(cases), len(arrays), os.path.getsize(OUT + ".npz") / 1e6))
     print("integer-division sites executed:", sorted(G.intdiv_sites))

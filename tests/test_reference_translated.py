@@ -241,6 +241,24 @@ def test_reference_panics_where_the_documented_difference_says():
     assert got[("flanger", 48000)] is None
 
 
+def test_config1_pcm16_bytes_equal_the_executed_reference():
+    """BASELINE.json config 1 in miniature (1-ch overdrive -> tone_stack, 48 kHz, PCM16 in and out, blocks of 8192 with the last one
+    zero-padded): the output payload of the executed reference (wave.go's conversions + signal.Chain), byte for byte, from the
+    oracle and from the product's fused codecs (host emulation; the same path runs on the GPU in tests/test_parity.py)"""
+    c = M["config1"]
+    n, nb = c["block"], c["blocks"]
+    raw = bytes(Z["cfg1_pcm_in"].tobytes()) + b"\x00" * (2 * (n * nb - c["samples"]))
+    want = Z["cfg1_pcm_out"].tobytes()
+    spec = [(u, nu, di) for u, nu, di in c["spec"]]
+    oc = common.build_chain(orc.Chain(), spec)
+    got = b"".join(orc.wave_encode("PCM16", oc.process(orc.wave_decode("PCM16", raw[2 * n * k:2 * n * (k + 1)]), c["fs"])).tobytes() for k in range(nb))
+    assert got == want
+    lib = common.backend_lib("emu")
+    pc = common.build_chain(gdg.Chain(lib=lib), spec)
+    got = b"".join(gdg.process_batch_encoded([pc], [raw[2 * n * k:2 * n * (k + 1)]], "PCM16", "PCM16", n, c["fs"])[0] for k in range(nb))
+    assert got == want
+
+
 # ---- parameter tables, error strings (effects.Unit / signal.Chain API surface, SURVEY.md 8a row 2 / 8b) ------------------------
 def _three_response_banks(lib):
     """the responses the generator imported (manifest ir_names), in index.json order like filter.Import keeps them"""
