@@ -18,6 +18,7 @@
 #include "gdg_device.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <complex>
 #include <cstdarg>
@@ -145,7 +146,7 @@ struct gdg_irbank {
         for (auto &r : responses) if (r.name == name && r.rate == rate) return &r;
         return nullptr;
     }
-    std::vector<std::string> name_cache;
+    std::vector<std::string> name_cache; uint64_t name_cache_generation = ~0ull;    /* gdg_irbank_name's strings: stable until the next add */
 };
 
 namespace {
@@ -603,7 +604,10 @@ struct gdg_chain {
     /* device descriptors: one per segment */
     std::vector<gdg_chain_desc *> d_desc; std::vector<gdg_chain_desc> h_desc; std::vector<int> seg_kind;
     bool topo_dirty = true;
-    bool uploaded = false;                                      /* set when prepare() touched device memory */
+    /* bumped whenever prepare() re-made the segment descriptors: every launch-table cache (the context's batch, the chain's own
+     * one-chain batch) remembers the version it was built from, so a chain that is driven through gdg_chain_process AND through
+     * the batch entry points can never leave one of them with stale tables */
+    uint64_t version = 0;
     /* nothing was edited since the last prepare() at this rate and block length: the per-unit parameter resolution (string
      * look-ups) is skipped - with thousands of chains per block that walk is what bounds the host */
     bool clean = false; uint32_t clean_rate = 0; size_t clean_n = 0;
@@ -646,7 +650,7 @@ struct gdg_chain {
             segs.back().slot[segs.back().nslots++] = u->desc;
         }
         if (segs.empty()) { gdg_chain_desc cd; memset(&cd, 0, sizeof cd); segs.push_back(cd); kinds.push_back(SEG_CHAIN); }   /* pass-through */
-        uploaded = true;
+        version++;
         h_desc = segs; seg_kind = kinds;
         const size_t nseg = h_desc.size();
         while (d_desc.size() < nseg) {
@@ -673,6 +677,7 @@ struct Batch {
     std::vector<bool> kind_used;                                 /* [round * SEG_KINDS + kind] */
     std::vector<int> max_units;                                  /* [round * SEG_KINDS + kind]: longest segment among the channels */
     std::vector<int32_t> h_nseg; int32_t *d_nseg = nullptr;
+    std::vector<uint64_t> seen;                                  /* chains[c]->version the tables were built from */
     double *d_scratch = nullptr; size_t scratch_cap = 0;         /* float64 rows between the rounds of encoded calls */
     /* two staging slots: block k+1 can be submitted (its upload overlapping block k's kernels and download) before
      * block k is waited for; the synchronous entry points use whichever slot is free */
@@ -708,8 +713,8 @@ int prepare_tables(Batch &b, gdg_chain *const *chains, size_t C, uint32_t rate, 
         if (r < 0) return -1;
         nseg[c] = r; rounds = std::max(rounds, (size_t)r);
     }
-    bool touched = false;
-    for (size_t c = 0; c < C; c++) if (chains[c]->uploaded) { touched = true; chains[c]->uploaded = false; }
+    bool touched = b.seen.size() != C;
+    for (size_t c = 0; c < C && !touched; c++) touched = chains[c]->version != b.seen[c];
     if (touched || b.h_ptrs.size() != rounds * SEG_KINDS) {          /* tables only change when some chain changed */
         std::vector<std::vector<const gdg_chain_desc *>> ptrs(rounds * SEG_KINDS, std::vector<const gdg_chain_desc *>(C, nullptr));
         std::vector<bool> used(rounds * SEG_KINDS, false);
@@ -741,6 +746,8 @@ int prepare_tables(Batch &b, gdg_chain *const *chains, size_t C, uint32_t rate, 
         }
         /* descriptor / state uploads run on the library stream: order a foreign stream after them */
         if (stream != gdgb_stream() && gdgb_sync()) return backend_fail("synchronize failed");
+        b.seen.resize(C);
+        for (size_t c = 0; c < C; c++) b.seen[c] = chains[c]->version;
     }
     return (int)rounds;
 }
@@ -924,6 +931,10 @@ int host_block(gdg_chain *const *chains, size_t C, gdg_tuner *tuner, int tuner_c
 /* ---- spatializer -------------------------------------------------------------- */
 struct gdg_spatializer {
     int ctx = 0;
+    /* spatializer.go:59: setters arrive from the UI thread while the audio thread processes.  A leaf lock (nothing else is
+     * taken under it): setters hold it while they write a position, the processing call while it turns the positions into
+     * the per-channel constants and enqueues its kernel, SetSampleRate while it re-makes the histories */
+    std::mutex mu;
     uint32_t count; uint32_t sample_rate = 96000;         /* never updated: spatializer.go:418-431 does not store the rate */
     struct Pos { double az = 0, dist = 0, level = 1.0; };
     std::vector<Pos> pos;
@@ -984,13 +995,20 @@ struct gdg_tuner {
     std::vector<double> corr;
     ~gdg_tuner() { gdgb_free(d_ring); gdgb_free(d_work); gdgb_free(d_block); }
 };
+namespace {
+/* tuner.go:50-53 has two locks and so does this side: g_tuner_mutex (mutexBuffer) is a leaf lock around a ring's write
+ * position - Process holds it while it enqueues the ring copy, Analyze while it reads the position and enqueues the
+ * autocorrelation, so an analysis never pairs a new position with an old ring; g_analyze_mutex (mutexAnalyze) serialises
+ * whole analyses (they share a tuner's work buffer).  Lock order: g_analyze_mutex -> g_batch_mutex -> g_tuner_mutex. */
+std::mutex g_tuner_mutex, g_analyze_mutex;
+}
 
 /* ---- level meter ---------------------------------------------------------------- */
 struct gdg_meter {
     int ctx = 0;
     std::vector<std::string> names;
     uint32_t count = 0;
-    bool enabled = false;                                 /* level.go:383-386: created disabled */
+    std::atomic<bool> enabled{false};                     /* level.go:383-386: created disabled; SetEnabled may come from the UI thread (level.go:333-356) */
     double *d_state = nullptr;                            /* [count][4]: cur, peak, counter, unused */
     double *d_stage = nullptr; size_t stage_cap = 0;      /* rows of the host entry point */
     ~gdg_meter() { gdgb_free(d_state); gdgb_free(d_stage); }
@@ -1226,7 +1244,9 @@ const char *gdg_irbank_name(const gdg_irbank *b, size_t i)
 {
     if (!b) return nullptr;
     gdg_irbank *mb = const_cast<gdg_irbank *>(b);
-    mb->name_cache = b->names();
+    static std::mutex m;
+    std::lock_guard<std::mutex> lk(m);
+    if (mb->name_cache_generation != b->generation) { mb->name_cache = b->names(); mb->name_cache_generation = b->generation; }
     return i < mb->name_cache.size() ? mb->name_cache[i].c_str() : nullptr;
 }
 
@@ -1236,7 +1256,8 @@ static bool read_file(const std::string &path, std::vector<unsigned char> &out)
     FILE *f = fopen(path.c_str(), "rb");
     if (!f) return false;
     fseek(f, 0, SEEK_END); long sz = ftell(f); fseek(f, 0, SEEK_SET);
-    out.resize(sz > 0 ? (size_t)sz : 0);
+    if (sz < 0 || sz > (1l << 31)) { fclose(f); return false; }                 /* a directory, or nothing an impulse response could be */
+    out.resize((size_t)sz);
     const size_t got = sz > 0 ? fread(out.data(), 1, (size_t)sz, f) : 0;
     fclose(f);
     return got == out.size();
@@ -1444,6 +1465,7 @@ int gdg_chain_get_bypass(gdg_chain *c, int id, int *bypass)
     ProcessLock lk(g_edit_mutex);
     CHAIN_CHECK(c);
     if (id < 0 || id >= (int)c->slots.size()) return fail("Cannot get bypass value: No unit %d.", id);
+    if (!bypass) return fail("gdg_chain_get_bypass: bad argument");
     *bypass = c->slots[id].bypass;
     return 0;
 }
@@ -1453,6 +1475,7 @@ int gdg_chain_set_discrete_value(gdg_chain *c, int id, const char *name, const c
     if (c) c->clean = false;
     CHAIN_CHECK(c);
     if (id < 0 || id >= (int)c->slots.size()) return fail("Cannot set discrete value: No unit %d.", id);
+    if (!name || !value) return fail("gdg_chain_set_discrete_value: bad argument");
     Unit *u = c->slots[id].unit.get();
     const int idx = u->find(name);
     if (idx < 0) return fail("Failed to set discrete value: Could not find parameter with name '%s'.", name);
@@ -1470,6 +1493,7 @@ int gdg_chain_get_discrete_value(gdg_chain *c, int id, const char *name, const c
     ProcessLock lk(g_edit_mutex);
     CHAIN_CHECK(c);
     if (id < 0 || id >= (int)c->slots.size()) return fail("Cannot get discrete value: No unit %d.", id);
+    if (!name || !value) return fail("gdg_chain_get_discrete_value: bad argument");
     Unit *u = c->slots[id].unit.get();
     const int idx = u->find(name);
     if (idx < 0) return fail("Failed to get discrete value: Could not find parameter with name '%s'.", name);
@@ -1483,6 +1507,7 @@ int gdg_chain_set_numeric_value(gdg_chain *c, int id, const char *name, int32_t 
     if (c) c->clean = false;
     CHAIN_CHECK(c);
     if (id < 0 || id >= (int)c->slots.size()) return fail("Cannot set numeric value: No unit %d.", id);
+    if (!name) return fail("gdg_chain_set_numeric_value: bad argument");
     Unit *u = c->slots[id].unit.get();
     const int idx = u->find(name);
     if (idx < 0) return fail("Failed to set numeric value: Could not find parameter with name '%s'.", name);
@@ -1499,6 +1524,7 @@ int gdg_chain_get_numeric_value(gdg_chain *c, int id, const char *name, int32_t 
     ProcessLock lk(g_edit_mutex);
     CHAIN_CHECK(c);
     if (id < 0 || id >= (int)c->slots.size()) return fail("Cannot get numeric value: No unit %d.", id);
+    if (!name || !value) return fail("gdg_chain_get_numeric_value: bad argument");
     Unit *u = c->slots[id].unit.get();
     const int idx = u->find(name);
     if (idx < 0) return fail("Failed to get numeric value: Could not find parameter with name '%s'.", name);
@@ -1522,6 +1548,7 @@ int gdg_chain_parameter(gdg_chain *c, int id, int index, gdg_parameter *out)
     if (id < 0 || id >= (int)c->slots.size()) return fail("Cannot get parameters: No unit %d.", id);
     Unit *u = c->slots[id].unit.get();
     if (index < 0 || index >= (int)u->params.size()) return fail("Cannot get parameter %d of unit %d.", index, id);
+    if (!out) return fail("gdg_chain_parameter: bad argument");
     const Param &p = u->params[index];
     out->name = p.name.c_str(); out->type = p.type; out->physical_unit = p.phys.c_str();
     out->minimum = p.min; out->maximum = p.max; out->numeric_value = p.num;
@@ -1530,6 +1557,7 @@ int gdg_chain_parameter(gdg_chain *c, int id, int index, gdg_parameter *out)
 }
 const char *gdg_chain_parameter_discrete_value(gdg_chain *c, int id, int index, int vi)
 {
+    ProcessLock lk(g_edit_mutex);
     if (!c || id < 0 || id >= (int)c->slots.size()) return nullptr;
     Unit *u = c->slots[id].unit.get();
     if (index < 0 || index >= (int)u->params.size()) return nullptr;
@@ -1610,29 +1638,31 @@ gdg_spatializer *gdg_spatializer_create(uint32_t n)
 }
 void gdg_spatializer_destroy(gdg_spatializer *s) { if (!s) return; Use use_ctx_(s->ctx); gdgb_sync(); delete s; }
 #define SPAT_CH(s, ch, what) if (!(s)) return fail("spatializer is NULL"); Use use_ctx_((s)->ctx); \
-    if ((ch) >= (s)->count) return fail("Cannot " what " for channel %d: Only %d channels exist.", (int)(ch), (int)(s)->count)
+    if ((ch) >= (s)->count) return fail("Cannot " what " for channel %d: Only %d channels exist.", (int)(ch), (int)(s)->count); \
+    std::lock_guard<std::mutex> spat_lock_((s)->mu)
 int gdg_spatializer_set_azimuth(gdg_spatializer *s, uint32_t ch, double v) { SPAT_CH(s, ch, "set azimuth"); s->pos[ch].az = v; s->dirty = true; return 0; }
-int gdg_spatializer_get_azimuth(gdg_spatializer *s, uint32_t ch, double *v) { SPAT_CH(s, ch, "get azimuth"); *v = s->pos[ch].az; return 0; }
+int gdg_spatializer_get_azimuth(gdg_spatializer *s, uint32_t ch, double *v) { SPAT_CH(s, ch, "get azimuth"); if (!v) return fail("gdg_spatializer_get_azimuth: bad argument"); *v = s->pos[ch].az; return 0; }
 int gdg_spatializer_set_distance(gdg_spatializer *s, uint32_t ch, double v)
 {
     SPAT_CH(s, ch, "set distance");
     if (v < 0.0 || v > 10.0) return fail("%s", "Failed to set distance: Value must be within [0, 10].");
     s->pos[ch].dist = v; s->dirty = true; return 0;
 }
-int gdg_spatializer_get_distance(gdg_spatializer *s, uint32_t ch, double *v) { SPAT_CH(s, ch, "get distance"); *v = s->pos[ch].dist; return 0; }
+int gdg_spatializer_get_distance(gdg_spatializer *s, uint32_t ch, double *v) { SPAT_CH(s, ch, "get distance"); if (!v) return fail("gdg_spatializer_get_distance: bad argument"); *v = s->pos[ch].dist; return 0; }
 int gdg_spatializer_set_level(gdg_spatializer *s, uint32_t ch, double v)
 {
     SPAT_CH(s, ch, "set distance");                         /* sic: spatializer.go:393 reuses the "distance" wording */
     if (v < 0.0 || v > 1.0) return fail("%s", "Failed to set level: Value must be within [0, 1].");
     s->pos[ch].level = v; s->dirty = true; return 0;
 }
-int gdg_spatializer_get_level(gdg_spatializer *s, uint32_t ch, double *v) { SPAT_CH(s, ch, "get level"); *v = s->pos[ch].level; return 0; }
+int gdg_spatializer_get_level(gdg_spatializer *s, uint32_t ch, double *v) { SPAT_CH(s, ch, "get level"); if (!v) return fail("gdg_spatializer_get_level: bad argument"); *v = s->pos[ch].level; return 0; }
 uint32_t gdg_spatializer_input_count(gdg_spatializer *s) { return s ? s->count : 0; }
 uint32_t gdg_spatializer_output_count(gdg_spatializer *) { return 2; }
 int gdg_spatializer_set_sample_rate(gdg_spatializer *s, uint32_t rate)
 {
     if (!s) return fail("spatializer is NULL");
     Use use_ctx_(s->ctx);
+    std::lock_guard<std::mutex> lk(s->mu);
     gdgb_sync();
     return s->alloc_hist(rate);
 }
@@ -1643,6 +1673,7 @@ int gdg_spatializer_process_device(gdg_spatializer *s, const double *d_in, size_
     if (!s || !d_in || !d_out) return fail("gdg_spatializer_process_device: bad argument");
     Use use_ctx_(s->ctx);
     if (n == 0 || n > (size_t)1 << 24) return fail("gdg_spatializer_process_device: bad block length");
+    std::lock_guard<std::mutex> lk(s->mu);
     if (s->dirty) { if (s->upload_channels()) return -1; if (stream && stream != gdgb_stream() && gdgb_sync()) return backend_fail("synchronize failed"); }
     if (s->count > 32 && s->part_n < n) {
         gdgb_sync(); gdgb_free(s->d_part);
@@ -1699,6 +1730,7 @@ int gdg_tuner_process_device(gdg_tuner *t, const double *d, size_t n, uint32_t r
     const size_t N = gdg_tuner::N;
     void *st = stream ? stream : gdgb_stream();
     int rc = 0;
+    std::lock_guard<std::mutex> lk(g_tuner_mutex);
     if (n >= N) { rc = gdgb_copy_on(t->d_ring, d + (n - N), N * sizeof(double), st); t->pos = 0; }
     else if (n > 0) {
         const size_t inc = (size_t)t->pos + n;
@@ -1726,14 +1758,14 @@ int gdg_tuner_process(gdg_tuner *t, const double *s, size_t n, uint32_t rate)
 }
 /* tuner.Analyze: tuner/tuner.go:379-577 - the 262144-point autocorrelation runs on the device (all tuners of a batch in
  * one set of launches); the scalar peak pick / note lookup below is the control-plane tail of the call. */
-static int tuner_pick(gdg_tuner *t, gdg_tuner_result *res)
+static int tuner_pick(gdg_tuner *t, uint32_t rate, gdg_tuner_result *res)
 {
     static const char *names[GDG_TUNER_NOTE_COUNT] = GDG_TUNER_NOTE_NAMES_INIT;
     static const double freqs[GDG_TUNER_NOTE_COUNT] = GDG_TUNER_NOTE_FREQS_INIT;
     const long n = gdg_tuner::N;
     const uint64_t two_n = 2 * (uint64_t)n;
     const int fft_size = (int)next_pow2(two_n);
-    const double sr = (double)t->rate;
+    const double sr = (double)rate;
     long low = (long)((sr / freqs[GDG_TUNER_NOTE_COUNT - 1]) + 0.5);
     if (low < 0 || (uint64_t)low >= two_n) low = 0;
     long high = (long)((sr / freqs[0]) + 0.5);
@@ -1765,17 +1797,25 @@ int gdg_tuner_analyze_batch(gdg_tuner *const *tuners, uint32_t count, gdg_tuner_
 {
     if (ensure_init()) return -1;
     if ((!tuners || !results) && count) return fail("gdg_tuner_analyze_batch: bad argument");
-    std::vector<const double *> rings(count); std::vector<double *> works(count); std::vector<int> pos(count);
+    std::vector<const double *> rings(count); std::vector<double *> works(count); std::vector<int> pos(count); std::vector<uint32_t> rates(count);
     for (uint32_t i = 0; i < count; i++) {
         if (!tuners[i]) return fail("gdg_tuner_analyze_batch: tuner %u is NULL", i);
         if (tuners[i]->ctx != tuners[0]->ctx) return fail("gdg_tuner_analyze_batch: the tuners of one batch must live on one device");
-        rings[i] = tuners[i]->d_ring; works[i] = tuners[i]->d_work; pos[i] = tuners[i]->pos;
     }
     Use use_ctx_(count ? tuners[0]->ctx : gdgb_current());
     const int fft_size = (int)next_pow2(2 * (uint64_t)gdg_tuner::N);
-    if (count && gdgb_autocorrelate_batch(rings.data(), gdg_tuner::N, pos.data(), works.data(), (int)count, fft_size, gdgb_stream()))
-        return backend_fail("autocorrelation failed");
-    for (uint32_t i = 0; i < count; i++) if (tuner_pick(tuners[i], &results[i])) return -1;
+    std::lock_guard<std::mutex> analyses(g_analyze_mutex);
+    {
+        /* A block being enqueued feeds its tuner on one of the two kernel streams and joins them at its end (block_submit):
+         * with the batch lock held no block is half enqueued, so the library stream - where the analysis runs - is ordered
+         * after every ring copy enqueued so far, and later blocks fork from it, i.e. run after the analysis has read the ring */
+        std::lock_guard<std::mutex> blocks(g_batch_mutex);
+        std::lock_guard<std::mutex> lk(g_tuner_mutex);
+        for (uint32_t i = 0; i < count; i++) { rings[i] = tuners[i]->d_ring; works[i] = tuners[i]->d_work; pos[i] = tuners[i]->pos; rates[i] = tuners[i]->rate; }
+        if (count && gdgb_autocorrelate_batch(rings.data(), gdg_tuner::N, pos.data(), works.data(), (int)count, fft_size, gdgb_stream()))
+            return backend_fail("autocorrelation failed");
+    }
+    for (uint32_t i = 0; i < count; i++) if (tuner_pick(tuners[i], rates[i], &results[i])) return -1;
     return 0;
 }
 int gdg_tuner_analyze(gdg_tuner *t, gdg_tuner_result *res)

@@ -89,6 +89,30 @@ def test_chains_do_not_share_state(lib):
             assert common.rms(ref - out[c]) <= common.TOL_RMS, (k, c)
 
 
+def test_edit_between_single_chain_and_batch_calls(lib):
+    """A chain driven through gdg_chain_process (the JACK path) AND through gdg_process_batch: an edit that changes its
+    segment structure (the oversampled unit leaves / rejoins its own kernel's run) must reach BOTH launch-table caches,
+    whichever entry point sees the edited chain first.  (The tables used to share one 'descriptors re-made' flag: the
+    single-chain call consumed it and the batch kept launching the old segment layout.)"""
+    fs, n = 48000, 256
+    spec = [("overdrive", {"gain": 10}, {"oversampling": "4"}), ("cabinet", {}, {})]
+    pairs = [common.make_chain_pair(lib, spec) for _ in range(2)]
+    x = [common.synth_fast(c, fs, 9 * n) for c in range(2)]
+
+    def block(k, batched):
+        blk = [x[c][k * n:(k + 1) * n] for c in range(2)]
+        out = gdg.process_batch([p[1] for p in pairs], np.stack(blk), fs) if batched else [p[1].process(b, fs) for p, b in zip(pairs, blk)]
+        for c in range(2):
+            ref = pairs[c][0].process(blk[c], fs)
+            assert common.rms(ref - out[c]) <= common.TOL_RMS, (k, c, batched)
+    block(0, True)
+    for k, (bypass, first) in enumerate([(True, False), (False, True), (True, True), (False, False)]):
+        for ch in pairs[0]:
+            ch.set_bypass(0, bypass)
+        block(1 + 2 * k, first)                 # the edited chain is seen by one entry point ...
+        block(2 + 2 * k, not first)             # ... and then by the other
+
+
 def test_scattered_host_buffers(lib):
     """gdg_process_batch with non-contiguous, unpinned row pointers (the Go [][]float64 case)."""
     fs, n, Cn = 48000, 1024, 5

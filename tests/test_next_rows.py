@@ -444,6 +444,120 @@ def test_setters_race_free_against_processing(lib):
     assert not errors, errors
 
 
+def test_spatializer_setters_from_a_second_thread_are_never_lost(lib):
+    """spatializer.go:59: SetAzimuth / SetDistance / SetLevel arrive from the UI thread while Process runs.  Every block must
+    be finite and bounded, and once the edits stop the NEXT block must be computed from the final positions - a setter
+    that lands between "positions read" and "clean flag set" on the processing side must not be forgotten."""
+    import threading
+    fs, n, C = 48000, 256, 6
+    gs, osp = gdg.Spatializer(C, lib=lib), orc.Spatializer(C)
+    gs.set_sample_rate(fs); osp.set_sample_rate(fs)
+    x = np.stack([common.synth_fast(c, fs, 64 * n) for c in range(C)])
+    final = [(-75.0 + 30.0 * c, 0.5 + 0.7 * c, 1.0 - 0.1 * c) for c in range(C)]
+    for rounds in range(12):
+        stop = threading.Event()
+        errors = []
+
+        def hammer():
+            k = 0
+            try:
+                while not stop.is_set():
+                    c = k % C
+                    gs.set_azimuth(c, -90.0 + (7 * k) % 180); gs.set_distance(c, (k % 100) / 10.0); gs.set_level(c, (k % 11) / 10.0)
+                    gs.get_azimuth(c)
+                    k += 1
+            except Exception as e:                           # noqa: BLE001
+                errors.append(e)
+            for c, (az, d, lv) in enumerate(final):         # the last thing the thread does: the final positions
+                gs.set_azimuth(c, az); gs.set_distance(c, d); gs.set_level(c, lv)
+        th = threading.Thread(target=hammer)
+        th.start()
+        try:
+            for k in range(4):
+                y = gs.process(x[:, (4 * rounds + k) * n:(4 * rounds + k + 1) * n])
+                assert np.all(np.isfinite(y)) and np.max(np.abs(y)) <= C + 1e-9
+        finally:
+            stop.set(); th.join()
+        assert not errors, errors
+    # histories are the inputs themselves (spatializer.go:310-333) and do not depend on the positions: feed the oracle the
+    # same stream, set the final positions, and the next block must match
+    for k in range(48):
+        osp.process(x[:, k * n:(k + 1) * n])
+    for c, (az, d, lv) in enumerate(final):
+        osp.set_azimuth(c, az); osp.set_distance(c, d); osp.set_level(c, lv)
+    blk = x[:, 48 * n:49 * n]
+    ya, yb = osp.process(blk), gs.process(blk)
+    assert common.rms(ya - yb) <= common.TOL_RMS and common.rms(ya) > 0
+
+
+def test_tuner_analyze_from_a_second_thread_during_processing(lib):
+    """tuner.go:50-53 (mutexBuffer / mutexAnalyze): the UI polls Analyze (controller.go:625-627) while the audio thread
+    keeps feeding the ring through controller.process.  A steady tone must read as the same note whenever the poll
+    lands, and the final read-out equals the oracle's."""
+    import threading
+    fs, n, C = 48000, 2048, 2
+    chains = [common.build_chain(gdg.Chain(lib=lib), [("tone_stack", {}, {})]) for _ in range(C)]
+    gt, ot = gdg.Tuner(lib=lib), orc.Tuner()
+    blocks = 96
+    t = np.arange(blocks * n) / fs
+    x = 0.5 * np.sin(2 * np.pi * 146.83 * t)                 # D3
+    for k in range(48):                                      # fill the 96000-sample ring once before polling starts
+        gt.process(x[k * n:(k + 1) * n], fs); ot.process(x[k * n:(k + 1) * n], fs)
+    stop = threading.Event()
+    seen, errors = [], []
+
+    def poll():
+        try:
+            while not stop.is_set():
+                seen.append(gt.analyze()["note"])
+                gdg.tuner_analyze_batch([gt])
+        except Exception as e:                               # noqa: BLE001
+            errors.append(e)
+    th = threading.Thread(target=poll)
+    th.start()
+    try:
+        for k in range(48, blocks):
+            rows = np.stack([x[k * n:(k + 1) * n], np.zeros(n)])
+            gdg.controller_process(chains, gt, 0, None, rows, fs)
+            ot.process(rows[0], fs)
+    finally:
+        stop.set(); th.join()
+    assert not errors, errors
+    assert seen and set(seen) == {"D3"}, sorted(set(seen))
+    a, b = ot.analyze(), gt.analyze()
+    assert a["note"] == b["note"] == "D3" and a["cents"] == b["cents"] and abs(a["frequency"] - b["frequency"]) <= 1e-9 * a["frequency"]
+
+
+def test_getters_reject_null_result_pointers(lib):
+    c = common.build_chain(gdg.Chain(lib=lib), [("overdrive", {}, {})])
+    assert lib.gdg_chain_get_bypass(c._h, 0, None) < 0
+    assert lib.gdg_chain_get_numeric_value(c._h, 0, b"gain", None) < 0 and lib.gdg_chain_get_numeric_value(c._h, 0, None, None) < 0
+    assert lib.gdg_chain_get_discrete_value(c._h, 0, b"valve", None) < 0
+    assert lib.gdg_chain_set_numeric_value(c._h, 0, None, 3) < 0
+    assert lib.gdg_chain_set_discrete_value(c._h, 0, b"valve", None) < 0 and lib.gdg_chain_set_discrete_value(c._h, 0, None, b"x") < 0
+    assert lib.gdg_chain_parameter(c._h, 0, 0, None) < 0
+    assert b"bad argument" in lib.gdg_last_error()
+    s = gdg.Spatializer(2, lib=lib)
+    assert lib.gdg_spatializer_get_azimuth(s._h, 0, None) < 0 and lib.gdg_spatializer_get_level(s._h, 1, None) < 0
+    assert c.get_numeric_value(0, "gain") == 0 and c.get_discrete_value(0, "valve")      # the chain is untouched
+
+
+def test_irbank_names_stay_valid_between_adds(lib):
+    """ImpulseResponses.Names() (filter.go:681-699): the strings a caller got stay where they are until the bank changes
+    (a cgo caller reads them with C.GoString after the call; a second lookup must not move the first one's bytes)"""
+    bank = gdg.IRBank(lib)
+    for k in range(3):
+        bank.add_raw("response %d" % k, 0, common.synthetic_ir(64), 48000)
+    raw = C_.CFUNCTYPE(C_.c_void_p, C_.c_void_p, C_.c_size_t)(("gdg_irbank_name", lib))
+    first = [raw(bank._h, i) for i in range(3)]
+    again = [raw(bank._h, i) for i in reversed(range(3))][::-1]
+    assert first == again and all(first)
+    assert [C_.string_at(q) for q in first] == [b"response 0", b"response 1", b"response 2"]
+    assert raw(bank._h, 3) is None
+    bank.add_raw("response 3", 0, common.synthetic_ir(64), 48000)
+    assert bank.names() == ["response 0", "response 1", "response 2", "response 3"]
+
+
 # ---- SURVEY 8f row 4: impulse-response compilation on the device, batched tuner analysis ------------------------------
 def _oracle_composite(h_by_name, comp_db, rate_src, rate, order, picks):
     """poweramp.compile (poweramp.go:25-127) with the oracle's filter algebra: picks = [(name, level_db)]"""
