@@ -25,6 +25,7 @@ int gdgb_context_count(void);
 int gdgb_context_device(int ctx);
 int gdgb_current(void);
 int gdgb_select(int ctx);
+int gdgb_bind(void);                            /* make the calling OS thread's CUDA device the one of its current context */
 int gdgb_enable_peers(int ctx);                 /* peer (NVLink) access from ctx to every other open context */
 int gdgb_wait_other(int ctx, int other, int event);   /* stream 0 of ctx waits for an event recorded on context `other` */
 /* out[r][j] = sum_d parts[d][r * strides[d] + j] (+ aux): the partial stereo masters of the other devices are read through peer addresses */

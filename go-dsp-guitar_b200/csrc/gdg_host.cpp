@@ -59,7 +59,7 @@ typedef std::shared_lock<std::shared_mutex> ProcessLock;
  * selected on the creating thread and every entry point works under its object's context. */
 struct Use {
     int prev;
-    explicit Use(int ctx) : prev(gdgb_current()) { if (ctx >= 0 && ctx != prev) gdgb_select(ctx); }
+    explicit Use(int ctx) : prev(gdgb_current()) { if (ctx >= 0 && ctx != prev) gdgb_select(ctx); else gdgb_bind(); }
     ~Use() { if (gdgb_current() != prev) gdgb_select(prev); }
     Use(const Use &) = delete;
 };
@@ -577,6 +577,7 @@ int ensure_init()
         g_init_status = gdg_init(dev);
     });
     if (g_init_status) { g_error = g_init_error; return -1; }
+    if (gdgb_bind()) return backend_fail("cudaSetDevice");      /* this OS thread may never have seen the device (cgo, UI threads) */
     return 0;
 }
 

@@ -29,6 +29,11 @@ struct DevCtx {
 static DevCtx g_ctx[GDGB_MAX_CONTEXTS];
 static int g_nctx = 0;
 static thread_local int t_cur = 0;
+/* CUDA's current device belongs to the OS thread, the library's contexts to the process: a thread that never called
+ * cudaSetDevice (a Go host's cgo calls arrive on whatever thread the scheduler picked, a UI thread polls the tuner) would
+ * launch context 0's kernels with device 0 current - wrong whenever context 0 is another device.  t_dev remembers what this
+ * thread was bound to; gdgb_bind() (every entry point of the host runtime passes through it) binds it to its context's device. */
+static thread_local int t_dev = -1;
 static std::vector<double> g_tab_aa2, g_tab_aa4, g_tab_lz2, g_tab_lz4, g_tab_tw;      /* host copies: uploaded to every context */
 #define CX (g_ctx[t_cur])
 #define g_device (CX.device)
@@ -330,6 +335,7 @@ static int open_context(int slot, int device)
     if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) device = 0; }
     if (device >= count) { t_err = "device index out of range"; return -1; }
     CU(cudaSetDevice(device));
+    t_dev = device;
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10) { t_err = std::string("device '") + prop.name + "' is not a Blackwell (sm_100a) GPU"; return -1; }
@@ -372,20 +378,27 @@ int gdgb_context_open(int device)
     if (g_nctx >= GDGB_MAX_CONTEXTS) { t_err = "too many device contexts"; return -1; }
     const int prev = t_cur, slot = g_nctx;
     t_cur = slot;
-    if (open_context(slot, device) || upload_tables()) { t_cur = prev; if (g_ctx[prev].device >= 0) cudaSetDevice(g_ctx[prev].device); return -1; }
+    if (open_context(slot, device) || upload_tables()) { t_cur = prev; t_dev = -1; gdgb_bind(); return -1; }
     g_nctx++;
     t_cur = prev;
-    if (g_ctx[prev].device >= 0) cudaSetDevice(g_ctx[prev].device);
+    t_dev = -1; gdgb_bind();
     return slot;
 }
 int gdgb_context_count(void) { return g_nctx; }
 int gdgb_context_device(int ctx) { return (ctx >= 0 && ctx < g_nctx) ? g_ctx[ctx].device : -1; }
 int gdgb_current(void) { return t_cur; }
+int gdgb_bind(void)
+{
+    const int d = CX.device;
+    if (d >= 0 && t_dev != d) { CU(cudaSetDevice(d)); t_dev = d; }
+    return 0;
+}
 int gdgb_select(int ctx)
 {
     if (ctx < 0 || ctx >= g_nctx) { t_err = "no such device context"; return -1; }
     t_cur = ctx;
     CU(cudaSetDevice(g_ctx[ctx].device));
+    t_dev = g_ctx[ctx].device;
     return 0;
 }
 int gdgb_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; } return n; }

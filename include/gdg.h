@@ -22,7 +22,12 @@
  *     "resolve parameters + enqueue kernels" part of the processing calls, a change takes effect at the next block
  *     boundary.  Processing the SAME chain from two threads at once is not allowed (as in the reference);
  *     gdg_last_error() is per thread: fetch it on the thread that made the failing call (cgo: runtime.LockOSThread,
- *     see INTEGRATION.md).
+ *     see INTEGRATION.md).  The other objects keep the reference's own locks: a spatializer's setters / getters and
+ *     SetSampleRate against its Process (spatializer/spatializer.go:59), a tuner's Analyze against Process and against
+ *     other Analyze calls (tuner/tuner.go:50-53), a level meter's SetEnabled against Process (level/level.go:40-52);
+ *   - any OS thread may call in: CUDA's "current device" is per thread, the library binds the calling thread to the device
+ *     of the object it is handed (or of the context selected with gdg_use_device) on entry, so goroutines that migrate
+ *     between threads need no cudaSetDevice of their own.
  */
 #ifndef GDG_H
 #define GDG_H

@@ -46,6 +46,7 @@ int gdgb_context_count(void) { return g_nctx; }
 int gdgb_context_device(int ctx) { return (ctx >= 0 && ctx < g_nctx) ? g_ctx_dev[ctx] : -1; }
 int gdgb_current(void) { return t_cur; }
 int gdgb_select(int ctx) { if (ctx < 0 || ctx >= g_nctx) { t_err = "no such device context"; return -1; } t_cur = ctx; return 0; }
+int gdgb_bind(void) { return 0; }
 int gdgb_enable_peers(int) { return 0; }
 int gdgb_wait_other(int, int, int) { return 0; }
 int gdgb_master_sum(const double *const *parts, const long *strides, int count, const double *aux, double *outL, double *outR, int n, void *)
