@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Random chains (1 - 6 units, parameters at random incl. their extremes, any supported rate, fixed or varying block lengths)
 through the EXECUTED reference (go2py) and the C oracle, compared block by block at 1e-12 of the peak.  Needs the reference
-tree.    python tests/golden/go2py/hunt.py FIRST_SEED LAST_SEED [--edits | --product | --spat | --compile | --meter | --resample | --tuner | --codecs | --controller]
+tree.    python tests/golden/go2py/hunt.py FIRST_SEED LAST_SEED [--edits | --product | --spat | --compile | --meter | --resample | --tuner | --codecs | --controller | --big]
 Round 2: 4400 random chains, 3200 edit sequences (--edits: a live chain edited between blocks, error strings compared as well)
 3300 random chains through the emulated product (--product, 1e-9 RMS per block) and 3200 random spatializers (--spat: oracle and
 emulated product), 1060 compiled power-amp filters (--compile: the product's device-side IR compilation), 2150 streamed level meters
@@ -74,6 +74,66 @@ def hunt_product(lo, hi, root='/root/reference', ref=None, verbose=True, backend
             print("seed", seed, "reference panic:", ex, [s_[0] for s_ in spec], fs)
     if verbose:
         print("product seeds %d..%d: %d mismatches, %.0f s" % (lo, hi, len(bad), time.time() - t0))
+    return bad
+
+
+def hunt_big(lo, hi, root='/root/reference', ref=None, verbose=True, backend="emu"):
+    """the batch path's own shapes, three ways: blocks of 4096 / 8192 samples at 96 / 192 kHz (controller.go:36), chains of
+    3 - 10 units of any type, power amps on the long responses WITHOUT reduction (default filter_order: 15359 / 19199 taps at
+    192 kHz - the product's partitioned convolution with K = 2 - 3 partitions) or reduced to 8192 / 4096 - executed reference
+    vs the oracle (1e-12 of the peak) and vs the emulated product (1e-9 RMS, 1e-8 of the block's RMS)"""
+    from common import gdg
+    ref = ref or gen.Ref(root)
+    lib = common.backend_lib(backend)
+    z = np.load(os.path.join(HERE, '..', 'ir_bank.npz'))
+    pb, ob = gdg.IRBank(lib), orc.IRBank()
+    for k, name in enumerate(z["names"]):
+        if str(name) in gen.IR_NAMES:
+            for bank in (pb, ob):
+                bank.add(str(name), int(z["compensation"][k]), orc.pcm16_decode(z["pcm_%02d" % k]), int(z["sample_rate"]))
+    schema = {u: ref.params(u) for u in ref.unit_names}
+    bad = []; t0 = time.time(); partitioned = 0
+    for seed in range(lo, hi):
+        rng = np.random.default_rng(90000 + seed)
+        fs = int(rng.choice([96000, 192000])); n = int(rng.choice([4096, 8192]))
+        spec = []
+        for _ in range(int(rng.integers(3, 11))):
+            u = str(rng.choice(ref.unit_names))
+            num, disc = schema[u]
+            numeric, discrete = {}, {}
+            for k, (mn, mx, _d) in num.items():
+                r = rng.random()
+                if r < 0.1: numeric[k] = mn
+                elif r < 0.2: numeric[k] = mx
+                elif r < 0.7: numeric[k] = int(rng.integers(mn, mx + 1))
+            for k, (vals, _d) in disc.items():
+                if rng.random() < 0.4: continue
+                if u == "power_amp" and k == "filter_order": vals = ["1048576", "1048576", "8192", "4096"]
+                if u == "power_amp" and k.startswith("filter_") and k != "filter_order": vals = ["- NONE -"] + gen.IR_NAMES
+                discrete[k] = str(rng.choice(vals))
+            if u == "power_amp":
+                if all(discrete.get("filter_%d" % i, "- NONE -") == "- NONE -" for i in range(1, 9)): discrete["filter_1"] = str(rng.choice(gen.IR_NAMES[1:]))
+                if discrete.get("filter_order", "1048576") == "1048576": partitioned += 1
+            spec.append((u, numeric, discrete))
+        gates = [u for u in spec if u[0] == "noise_gate"]
+        octs = [u for u in spec if u[0] in ("octaver", "auto_yoy")][:1]
+        spec = gates + octs + [u for u in spec if u[0] not in ("noise_gate", "octaver", "auto_yoy")]
+        blocks = int(rng.integers(2, 5))
+        x = gen.test_signal(fs, n * blocks, seed) * float(rng.choice([0.1, 1.0, 1.6]))
+        ch = ref.chain(spec); pc = common.build_chain(gdg.Chain(pb, lib=lib), spec); oc = common.build_chain(orc.Chain(ob), spec)
+        try:
+            for bi in range(blocks):
+                blk = np.ascontiguousarray(x[bi * n:(bi + 1) * n])
+                yr = ref.process(ch, blk, fs); yo = oc.process(blk, fs); yp = pc.process(blk, fs)
+                eo = float(np.max(np.abs(yr - yo))); e, r = common.rms(yr - yp), common.rms(yr)
+                if eo > 1e-12 * max(1.0, float(np.max(np.abs(yr)))) or not (e <= 1e-9 and (r <= 1e-6 or e <= 1e-8 * r)):
+                    bad.append((seed, eo, e, json.dumps(spec)))
+                    print("seed %d block %d MISMATCH oracle %.3e product rms %.3e (ref rms %.3g) fs %d n %d spec %s" % (seed, bi, eo, e, r, fs, n, json.dumps(spec)))
+                    break
+        except GoPanic as ex:
+            print("seed", seed, "reference panic:", ex, [s_[0] for s_ in spec], fs)
+    if verbose:
+        print("big blocks %d..%d: %d mismatches, %d unreduced power amps, %.0f s" % (lo, hi, len(bad), partitioned, time.time() - t0))
     return bad
 
 
@@ -579,7 +639,7 @@ def hunt(lo, hi, root='/root/reference', ref=None, verbose=True):
 
 if __name__ == "__main__":
     modes = {"--product": hunt_product, "--edits": hunt_edits, "--spat": hunt_spatializer, "--compile": hunt_compile, "--meter": hunt_meter,
-             "--resample": hunt_resample, "--tuner": hunt_tuner, "--codecs": hunt_codecs, "--controller": hunt_controller}
+             "--resample": hunt_resample, "--tuner": hunt_tuner, "--codecs": hunt_codecs, "--controller": hunt_controller, "--big": hunt_big}
     fn = next((f for k, f in modes.items() if k in sys.argv), hunt)
     args = [a_ for a_ in sys.argv[1:] if not a_.startswith("--")]
     sys.exit(1 if fn(int(args[0]), int(args[1])) else 0)
