@@ -503,3 +503,12 @@ def test_channels_as_far_as_the_controller_needs_them(tmp_path):
     assert c.Run(4) == 4 and seen == [0, 1, 2, 3]
     with pytest.raises(goruntime.GoPanic):
         G.recv(resp)
+
+
+@pytest.mark.skipif(not have_reference, reason="needs the reference tree (build container)")
+def test_batch_block_lengths_three_ways_equal_executed_reference():
+    """hunt.py --big on 8 fresh seeds: blocks of 4096 / 8192 samples at 96 / 192 kHz (the batch path's own shapes), chains of
+    3 - 10 units, power amps on the long responses without reduction (the product's partitioned convolution) - executed
+    reference vs oracle (1e-12) and vs the emulated product (1e-9 RMS)"""
+    import hunt
+    assert hunt.hunt_big(98000, 98008, REFERENCE, verbose=False) == []
