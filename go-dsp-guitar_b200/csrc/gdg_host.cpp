@@ -1865,6 +1865,13 @@ int gdg_process_batch_device_encoded(gdg_chain *const *chains, size_t C, const v
     if (!chains || !C || !d_in || !d_out) return fail("gdg_process_batch_device_encoded: bad argument");
     if (!fmt_bytes(in_format) || !fmt_bytes(out_format)) return fail("Unknown sample format: %#04x", fmt_bytes(in_format) ? out_format : in_format);
     if (in_stride_bytes < n * fmt_bytes(in_format) || out_stride_bytes < n * fmt_bytes(out_format)) return fail("gdg_process_batch_device_encoded: stride too small");
+    /* the float formats are read and written as float / double words: every row must start on a multiple of the sample size
+     * (the integer formats go byte by byte and may sit anywhere) */
+    {
+        const size_t ia = in_format == GDG_FMT_IEEE64 ? 8 : (in_format == GDG_FMT_IEEE32 ? 4 : 1), oa = out_format == GDG_FMT_IEEE64 ? 8 : (out_format == GDG_FMT_IEEE32 ? 4 : 1);
+        if ((uintptr_t)d_in % ia || in_stride_bytes % ia || (uintptr_t)d_out % oa || out_stride_bytes % oa)
+            return fail("gdg_process_batch_device_encoded: rows of a float format must be aligned to the sample size");
+    }
     if (check_block(n)) return -1;
     for (size_t c_ = 1; c_ < (size_t)C; c_++) if (chains[c_] && chains[c_]->ctx != chains[0]->ctx) return fail("the chains of one call must live on one device (use gdg_cluster_* to span devices)");
     Use use_ctx_(chains[0]->ctx);

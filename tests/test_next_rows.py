@@ -711,3 +711,9 @@ def test_process_batch_device_encoded(lib, fmt_in, fmt_out):
             assert np.all(got[c, n * bo:] == 0xA5)          # nothing written between the rows
     with pytest.raises(gdg.GdgError, match="stride too small"):
         runner.process_device_encoded(pin, fmt_in, n * bi - 1, pout, fmt_out, so, n, fs)
+    if "IEEE" in fmt_in:                                     # float rows are read as words: a row may not start off the sample grid
+        with pytest.raises(gdg.GdgError, match="aligned to the sample size"):
+            runner.process_device_encoded(pin, fmt_in, si + 1, pout, fmt_out, so, n, fs)
+    if "IEEE" in fmt_out:
+        with pytest.raises(gdg.GdgError, match="aligned to the sample size"):
+            runner.process_device_encoded(pin, fmt_in, si, pout + 4, fmt_out, so, n, fs)
