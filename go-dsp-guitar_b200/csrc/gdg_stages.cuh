@@ -134,7 +134,7 @@ GDG_CONST double c_lz4[3][6];          /* ... x4: phase p/4, taps q: L(2 - q + p
 #if defined(__CUDACC__) && !defined(GDG_HOST_EMU)
 extern __shared__ __align__(16) double gdg_smem[];
 #else
-static double *gdg_smem;                                     /* host emulation: set by run_chain */
+static thread_local double *gdg_smem;                        /* host emulation: set by run_chain (per thread: concurrent calls) */
 #endif
 
 struct gdg_ctx {

@@ -23,7 +23,7 @@
 #include "../../go-dsp-guitar_b200/csrc/gdg_interp.cuh"
 #include "../../go-dsp-guitar_b200/csrc/gdg_os.cuh"
 
-static std::string t_err;
+static thread_local std::string t_err;
 static std::vector<double> g_tw;
 static std::atomic<uint64_t> g_launches{0};
 

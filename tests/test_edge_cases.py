@@ -113,6 +113,46 @@ def test_edit_between_single_chain_and_batch_calls(lib):
         block(2 + 2 * k, not first)             # ... and then by the other
 
 
+def test_one_thread_per_channel_like_the_reference_fan_out(lib):
+    """controller.go:2682-2705 / 3339-3341: the reference runs Chain.Process of every channel on its own goroutine, all at
+    once.  Four threads, each driving ITS chain through gdg_chain_process for 24 blocks while the others do the same (and
+    one more thread keeps editing a fifth chain): every channel equals its oracle chain."""
+    import threading
+    fs, n, blocks = 96000, 1024, 24
+    banks = common.make_banks(lib)
+    specs = [common.CHAIN12, MIXED, common.CHAIN12[:6], MIXED[2:]]
+    pairs = [common.make_chain_pair(lib, sp, banks, ir_name="Guitar: American Vintage (Center)") for sp in specs]
+    x = [common.synth_fast(c, fs, blocks * n) for c in range(len(pairs))]
+    outs = [np.zeros(blocks * n) for _ in pairs]
+    errors = []
+    stop = threading.Event()
+
+    def worker(c):
+        try:
+            for k in range(blocks):
+                outs[c][k * n:(k + 1) * n] = pairs[c][1].process(x[c][k * n:(k + 1) * n], fs)
+        except Exception as e:                               # noqa: BLE001
+            errors.append((c, e))
+
+    def editor():
+        ch = common.build_chain(gdg.Chain(banks[1], lib=lib), [("power_amp", {}, {"filter_order": "2048", "filter_1": "Guitar: Custom BP"})])
+        k = 0
+        while not stop.is_set():
+            ch.set_numeric_value(0, "level_1", -(k % 30)); ch.process(x[0][:n], fs)      # recompiles a filter every block
+            k += 1
+    ts = [threading.Thread(target=worker, args=(c,)) for c in range(len(pairs))] + [threading.Thread(target=editor)]
+    for t in ts:
+        t.start()
+    for t in ts[:-1]:
+        t.join()
+    stop.set(); ts[-1].join()
+    assert not errors, errors
+    for c in range(len(pairs)):
+        for k in range(blocks):
+            ref = pairs[c][0].process(x[c][k * n:(k + 1) * n], fs)
+            assert common.rms(ref - outs[c][k * n:(k + 1) * n]) <= common.TOL_RMS, (c, k)
+
+
 def test_scattered_host_buffers(lib):
     """gdg_process_batch with non-contiguous, unpinned row pointers (the Go [][]float64 case)."""
     fs, n, Cn = 48000, 1024, 5

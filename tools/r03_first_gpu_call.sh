@@ -6,6 +6,7 @@ mkdir -p gpurun_out
 T=${TAG:-r03a}
 timeout 600 python -m pytest -q -m gpu -x \
     tests/test_edge_cases.py::test_edit_between_single_chain_and_batch_calls \
+    tests/test_edge_cases.py::test_one_thread_per_channel_like_the_reference_fan_out \
     tests/test_next_rows.py::test_spatializer_setters_from_a_second_thread_are_never_lost \
     tests/test_next_rows.py::test_tuner_analyze_from_a_second_thread_during_processing \
     tests/test_next_rows.py::test_getters_reject_null_result_pointers \

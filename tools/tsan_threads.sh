@@ -1,7 +1,7 @@
 #!/bin/bash
 # The host runtime's threading contract under ThreadSanitizer: the test-only emulation library (gdg_host.cpp + the stage
 # source as host code) is built with -fsanitize=thread in a scratch copy of the tree and the tests that drive the library from
-# two threads (setters vs processing, spatializer setters, tuner polls) run there.  Prints TSan's report count.
+# two threads (setters vs processing, spatializer setters, tuner polls, one processing thread per channel) run there.  Prints TSan's report count.
 set -e
 SRC=$(cd "$(dirname "$0")/.." && pwd)
 DST=${TSAN_DIR:-/tmp/gdg_tsan}
@@ -14,5 +14,5 @@ cp "$SRC/go-dsp-guitar_b200/libgdg.so" "$DST/go-dsp-guitar_b200/" 2>/dev/null ||
 touch "$DST/tests/emu/libgdg_emu.so" "$DST/oracle/liborc.so" "$DST/go-dsp-guitar_b200/libgdg.so"
 cd "$DST"
 LD_PRELOAD=$(gcc -print-file-name=libtsan.so) TSAN_OPTIONS="halt_on_error=0 report_signal_unsafe=0" \
-    python -m pytest tests/test_next_rows.py -q -m "not gpu" -p no:cacheprovider -k "second_thread or race_free" "$@" 2>&1 | tee /tmp/gdg_tsan.log | tail -3
+    python -m pytest tests/test_next_rows.py tests/test_edge_cases.py -q -m "not gpu" -p no:cacheprovider -k "second_thread or race_free or one_thread_per_channel" "$@" 2>&1 | tee /tmp/gdg_tsan.log | tail -3
 echo "ThreadSanitizer reports: $(grep -o 'reported [0-9]* warnings' /tmp/gdg_tsan.log || echo 'reported 0 warnings')"
