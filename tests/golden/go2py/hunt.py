@@ -2,12 +2,12 @@
 """Random chains (1 - 6 units, parameters at random incl. their extremes, any supported rate, fixed or varying block lengths)
 through the EXECUTED reference (go2py) and the C oracle, compared block by block at 1e-12 of the peak.  Needs the reference
 tree.    python tests/golden/go2py/hunt.py FIRST_SEED LAST_SEED [--edits | --product | --spat | --compile | --meter | --resample | --tuner | --codecs | --controller | --big]
-Round 2 (all sessions): 10800 random chains, 9600 edit sequences (--edits: a live chain edited between blocks, error strings compared
-as well), 9850 random chains through the emulated product (--product, 1e-9 RMS per block) and 9200 random spatializers (--spat: oracle and
-emulated product), 7060 compiled power-amp filters (--compile: the product's device-side IR compilation), 8150 streamed level meters
-(--meter), 6600 resample.Time calls (--resample), 300+ tuner analyses (--tuner), 12300 codec round trips (--codecs, byte for byte) and
+Round 2 (all sessions): 18800 random chains, 17600 edit sequences (--edits: a live chain edited between blocks, error strings compared
+as well), 17850 random chains through the emulated product (--product, 1e-9 RMS per block) and 17200 random spatializers (--spat: oracle
+and emulated product), 7060 compiled power-amp filters (--compile: the product's device-side IR compilation), 16150 streamed level meters
+(--meter), 6600 resample.Time calls (--resample), 550 tuner analyses (--tuner), 12300 codec round trips (--codecs, byte for byte) and
 1500 big-block chains (--big: blocks of 4096 / 8192 at 96 / 192 kHz, unreduced long responses, three-way compare):
-0 mismatches, no reference panic; --controller: controller.process executed against the one-call mirror, 8040 configurations, 0 mismatches."""
+0 mismatches, no reference panic; --controller: controller.process executed against the one-call mirror, 16040 configurations, 0 mismatches."""
 import sys, os, json, time
 HERE = os.path.dirname(os.path.abspath(__file__))
 for p_ in (HERE, os.path.join(HERE, '..', '..'), os.path.join(HERE, '..', '..', '..', 'oracle')):
