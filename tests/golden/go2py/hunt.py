@@ -5,8 +5,8 @@ tree.    python tests/golden/go2py/hunt.py FIRST_SEED LAST_SEED [--edits | --pro
 Round 2 (all sessions): 18800 random chains, 17600 edit sequences (--edits: a live chain edited between blocks, error strings compared
 as well), 17850 random chains through the emulated product (--product, 1e-9 RMS per block) and 17200 random spatializers (--spat: oracle
 and emulated product), 7060 compiled power-amp filters (--compile: the product's device-side IR compilation), 16150 streamed level meters
-(--meter), 6600 resample.Time calls (--resample), 550 tuner analyses (--tuner), 12300 codec round trips (--codecs, byte for byte) and
-1500 big-block chains (--big: blocks of 4096 / 8192 at 96 / 192 kHz, unreduced long responses, three-way compare):
+(--meter), 12600 resample.Time calls (--resample), 550 tuner analyses (--tuner), 16300 codec round trips (--codecs, byte for byte) and
+4500 big-block chains (--big: blocks of 4096 / 8192 at 96 / 192 kHz, unreduced long responses, three-way compare):
 0 mismatches, no reference panic; --controller: controller.process executed against the one-call mirror, 16040 configurations, 0 mismatches."""
 import sys, os, json, time
 HERE = os.path.dirname(os.path.abspath(__file__))
